@@ -1,0 +1,524 @@
+/*
+ * f3b_api.cu — the C-ABI of libflam3_b200.so (include/flam3_b200.h): context, device
+ * buffers, and the launches that replace render_rectangle's thread machinery
+ * (rect.c:685-1247). Host-side glue only; the kernels are in f3b_iterate.cu / f3b_post.cu.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "f3b_internal.h"
+
+struct DevBuf {
+   void *p = nullptr;
+   size_t cap = 0;
+};
+
+struct f3b_ctx {
+   int device = 0;
+   int sms = 0;
+   int iter_blocks_per_sm = 0;
+   cudaStream_t stream = nullptr;
+   char err[512] = {0};
+
+   int width = 0, height = 0;
+   int count_channel = 1;
+   DevBuf hist_color, hist_count, accum, image;
+   DevBuf blobs, jobs, groups, de_coefs, de_radius, filter;
+   unsigned long long *d_badvals = nullptr;
+
+   /* instrumentation */
+   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+   struct Rec {
+      int stage;
+      int ev;
+   };
+   std::vector<Rec> recs;
+   size_t ev_used = 0;
+   double stage_ms[F3B_NSTAGES] = {0, 0, 0};
+   uint64_t stage_launches[F3B_NSTAGES] = {0, 0, 0};
+};
+
+static int fail(f3b_ctx *c, const char *fmt, ...) {
+   va_list ap;
+   va_start(ap, fmt);
+   if (c) vsnprintf(c->err, sizeof(c->err), fmt, ap);
+   va_end(ap);
+   if (c && getenv("F3B_VERBOSE")) fprintf(stderr, "flam3_b200: %s\n", c->err);
+   return 1;
+}
+
+#define CK(call)                                                                         \
+   do {                                                                                  \
+      cudaError_t e_ = (call);                                                           \
+      if (e_ != cudaSuccess)                                                             \
+         return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                     __LINE__);                                                          \
+   } while (0)
+
+static int ensure(f3b_ctx *ctx, DevBuf &b, size_t bytes) {
+   if (bytes <= b.cap) return 0;
+   if (b.p) cudaFree(b.p);
+   b.p = nullptr;
+   b.cap = 0;
+   size_t want = bytes + bytes / 8 + 256;
+   CK(cudaMalloc(&b.p, want));
+   b.cap = want;
+   return 0;
+}
+
+static int stage_begin(f3b_ctx *ctx, int stage) {
+   if (ctx->ev_used == ctx->ev_pool.size()) {
+      cudaEvent_t a, b;
+      CK(cudaEventCreate(&a));
+      CK(cudaEventCreate(&b));
+      ctx->ev_pool.push_back({a, b});
+   }
+   ctx->recs.push_back({stage, (int)ctx->ev_used});
+   CK(cudaEventRecord(ctx->ev_pool[ctx->ev_used].first, ctx->stream));
+   return 0;
+}
+static int stage_end(f3b_ctx *ctx, int launches) {
+   const f3b_ctx::Rec &r = ctx->recs.back();
+   CK(cudaEventRecord(ctx->ev_pool[ctx->ev_used].second, ctx->stream));
+   ctx->ev_used++;
+   ctx->stage_launches[r.stage] += (uint64_t)launches;
+   return 0;
+}
+static int stats_collect(f3b_ctx *ctx) {
+   CK(cudaStreamSynchronize(ctx->stream));
+   for (const f3b_ctx::Rec &r : ctx->recs) {
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, ctx->ev_pool[r.ev].first, ctx->ev_pool[r.ev].second));
+      ctx->stage_ms[r.stage] += ms;
+   }
+   ctx->recs.clear();
+   ctx->ev_used = 0;
+   return 0;
+}
+
+extern "C" {
+
+int f3b_abi_version(void) { return F3B_ABI_VERSION; }
+
+int f3b_ctx_create(int device, f3b_ctx **out) {
+   if (!out) return 1;
+   *out = nullptr;
+   f3b_ctx *ctx = new f3b_ctx();
+   ctx->device = device;
+   cudaError_t e = cudaSetDevice(device);
+   if (e != cudaSuccess) {
+      fprintf(stderr, "flam3_b200: cudaSetDevice(%d) failed: %s\n", device, cudaGetErrorString(e));
+      delete ctx;
+      return 1;
+   }
+   cudaDeviceProp prop;
+   e = cudaGetDeviceProperties(&prop, device);
+   if (e != cudaSuccess || prop.major < 10) {
+      fprintf(stderr, "flam3_b200: device %d is not an sm_100-class GPU (%s)\n", device,
+              e == cudaSuccess ? prop.name : cudaGetErrorString(e));
+      delete ctx;
+      return 1;
+   }
+   ctx->sms = prop.multiProcessorCount;
+   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+       cudaMalloc(&ctx->d_badvals, sizeof(unsigned long long)) != cudaSuccess) {
+      fprintf(stderr, "flam3_b200: context setup failed: %s\n",
+              cudaGetErrorString(cudaGetLastError()));
+      delete ctx;
+      return 1;
+   }
+   cudaMemsetAsync(ctx->d_badvals, 0, sizeof(unsigned long long), ctx->stream);
+   ctx->iter_blocks_per_sm = f3b_iterate_max_blocks_per_sm(16 * 1024);
+   if (ctx->iter_blocks_per_sm <= 0) ctx->iter_blocks_per_sm = 1;
+   *out = ctx;
+   return 0;
+}
+
+void f3b_ctx_destroy(f3b_ctx *ctx) {
+   if (!ctx) return;
+   cudaSetDevice(ctx->device);
+   cudaStreamSynchronize(ctx->stream);
+   DevBuf *bufs[] = {&ctx->hist_color, &ctx->hist_count, &ctx->accum,    &ctx->image,
+                     &ctx->blobs,      &ctx->jobs,       &ctx->groups,   &ctx->de_coefs,
+                     &ctx->de_radius,  &ctx->filter};
+   for (DevBuf *b : bufs)
+      if (b->p) cudaFree(b->p);
+   if (ctx->d_badvals) cudaFree(ctx->d_badvals);
+   for (auto &p : ctx->ev_pool) {
+      cudaEventDestroy(p.first);
+      cudaEventDestroy(p.second);
+   }
+   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+   delete ctx;
+}
+
+const char *f3b_last_error(const f3b_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int f3b_device_info(f3b_ctx *ctx, int *info) {
+   if (!ctx || !info) return 1;
+   info[0] = ctx->sms;
+   info[1] = ctx->iter_blocks_per_sm;
+   info[2] = F3B_CHAINS_PER_GROUP;
+   return 0;
+}
+
+int f3b_sync(f3b_ctx *ctx) {
+   CK(cudaSetDevice(ctx->device));
+   CK(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel) {
+   if (!ctx) return 1;
+   if (width <= 0 || height <= 0) return fail(ctx, "bad buffer size %dx%d", width, height);
+   CK(cudaSetDevice(ctx->device));
+   const size_t n = (size_t)width * height;
+   if (ensure(ctx, ctx->hist_color, n * sizeof(float4))) return 1;
+   if (ensure(ctx, ctx->accum, n * sizeof(float4))) return 1;
+   if (count_channel && ensure(ctx, ctx->hist_count, n * sizeof(float))) return 1;
+   ctx->width = width;
+   ctx->height = height;
+   ctx->count_channel = count_channel ? 1 : 0;
+   CK(cudaMemsetAsync(ctx->d_badvals, 0, sizeof(unsigned long long), ctx->stream));
+   if (f3b_hist_clear(ctx)) return 1;
+   return f3b_accum_clear(ctx);
+}
+
+int f3b_hist_clear(f3b_ctx *ctx) {
+   const size_t n = (size_t)ctx->width * ctx->height;
+   CK(cudaSetDevice(ctx->device));
+   CK(cudaMemsetAsync(ctx->hist_color.p, 0, n * sizeof(float4), ctx->stream));
+   if (ctx->count_channel) CK(cudaMemsetAsync(ctx->hist_count.p, 0, n * sizeof(float), ctx->stream));
+   return 0;
+}
+
+int f3b_accum_clear(f3b_ctx *ctx) {
+   const size_t n = (size_t)ctx->width * ctx->height;
+   CK(cudaSetDevice(ctx->device));
+   CK(cudaMemsetAsync(ctx->accum.p, 0, n * sizeof(float4), ctx->stream));
+   return 0;
+}
+
+/* Chain planning. The reference gives each of its `nthreads` workers batch_size/nthreads
+ * iterations cut into sub-batches of sub_batch_size (rect.c:279-284, 840); here the
+ * "workers" are the resident GPU threads. */
+uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len, uint32_t n_jobs) {
+   if (!ctx || n_iters == 0) return 0;
+   if (max_chain_len == 0) max_chain_len = 10000;
+   if (n_jobs == 0) n_jobs = 1;
+   const uint64_t T = (uint64_t)ctx->sms * ctx->iter_blocks_per_sm * F3B_CHAINS_PER_GROUP;
+   uint64_t Ts = T / n_jobs;
+   if (Ts < 32) Ts = 32;
+   if (Ts >= F3B_CHAINS_PER_GROUP) Ts -= Ts % F3B_CHAINS_PER_GROUP;
+   const uint64_t lmin = 64; /* keeps the fuse overhead (15 discarded) below ~25% */
+   uint64_t chains;
+   if (n_iters >= Ts * lmin) {
+      const uint64_t rounds = (n_iters + Ts * max_chain_len - 1) / (Ts * (uint64_t)max_chain_len);
+      chains = Ts * rounds;
+   } else {
+      chains = n_iters / (max_chain_len < lmin ? max_chain_len : lmin);
+      if (chains == 0) chains = 1;
+   }
+   /* never exceed the per-chain cap */
+   const uint64_t need = (n_iters + max_chain_len - 1) / max_chain_len;
+   if (chains < need) chains = need;
+   if (chains > 0xfffffff0ull) chains = 0xfffffff0ull;
+   return (uint32_t)chains;
+}
+
+int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *jobs, int n_jobs,
+                uint64_t seed, int floor_adds, uint32_t max_chain_len, int rank, int nranks) {
+   if (!ctx || !blobs || !jobs || n_jobs <= 0) return fail(ctx, "f3b_iterate: bad arguments");
+   if (nranks <= 0 || rank < 0 || rank >= nranks) return fail(ctx, "f3b_iterate: bad rank");
+   if (!ctx->hist_color.p) return fail(ctx, "f3b_iterate: f3b_frame_begin not called");
+   CK(cudaSetDevice(ctx->device));
+
+   /* plan chains and groups */
+   std::vector<uint32_t> group_job;
+   size_t max_blob = 0;
+   for (int j = 0; j < n_jobs; j++) {
+      f3b_job &jb = jobs[j];
+      if (jb.blob_offset % 16 || jb.blob_offset + F3B_H_SIZE * 4 > blob_bytes)
+         return fail(ctx, "f3b_iterate: job %d blob offset invalid", j);
+      const uint32_t words = ((const uint32_t *)((const char *)blobs + jb.blob_offset))[F3B_H_WORDS];
+      if (words < F3B_H_SIZE || words > F3B_MAX_BLOB_WORDS ||
+          jb.blob_offset + (size_t)words * 4 > blob_bytes)
+         return fail(ctx, "f3b_iterate: job %d blob of %u words does not fit (max %u)", j, words,
+                     F3B_MAX_BLOB_WORDS);
+      if ((size_t)words * 4 > max_blob) max_blob = (size_t)words * 4;
+      if (jb.n_chains == 0) jb.n_chains = f3b_plan_chains(ctx, jb.n_iters, max_chain_len, n_jobs);
+      jb.first_group = (uint32_t)group_job.size();
+      const uint32_t ng = (jb.n_chains + F3B_CHAINS_PER_GROUP - 1) / F3B_CHAINS_PER_GROUP;
+      for (uint32_t g = 0; g < ng; g++) group_job.push_back((uint32_t)j);
+   }
+   const uint32_t n_groups = (uint32_t)group_job.size();
+   if (n_groups == 0) return 0;
+
+   if (ensure(ctx, ctx->blobs, blob_bytes)) return 1;
+   if (ensure(ctx, ctx->jobs, sizeof(f3b_job) * (size_t)n_jobs)) return 1;
+   if (ensure(ctx, ctx->groups, sizeof(uint32_t) * (size_t)n_groups)) return 1;
+   CK(cudaMemcpyAsync(ctx->blobs.p, blobs, blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
+   CK(cudaMemcpyAsync(ctx->jobs.p, jobs, sizeof(f3b_job) * (size_t)n_jobs, cudaMemcpyHostToDevice,
+                      ctx->stream));
+   CK(cudaMemcpyAsync(ctx->groups.p, group_job.data(), sizeof(uint32_t) * (size_t)n_groups,
+                      cudaMemcpyHostToDevice, ctx->stream));
+   /* the three host buffers above are pageable: the async copies have staged them before
+    * returning, but keep it simple and make that explicit */
+   CK(cudaStreamSynchronize(ctx->stream));
+
+   F3IterateParams P;
+   P.blobs = (const uint8_t *)ctx->blobs.p;
+   P.jobs = (const f3b_sample_job *)ctx->jobs.p;
+   P.group_job = (const uint32_t *)ctx->groups.p;
+   P.n_groups = n_groups;
+   P.rank = (uint32_t)rank;
+   P.nranks = (uint32_t)nranks;
+   P.hist_color = (float4 *)ctx->hist_color.p;
+   P.hist_count = ctx->count_channel ? (float *)ctx->hist_count.p : nullptr;
+   P.width = ctx->width;
+   P.height = ctx->height;
+   P.floor_adds = floor_adds;
+   P.seed = seed;
+   P.badvals = ctx->d_badvals;
+
+   const uint32_t local_groups = (n_groups - (uint32_t)rank + (uint32_t)nranks - 1) / (uint32_t)nranks;
+   if (local_groups == 0) return 0;
+   const int bps = f3b_iterate_max_blocks_per_sm(max_blob);
+   if (bps <= 0) return fail(ctx, "f3b_iterate: kernel does not fit with %zu bytes of shared memory", max_blob);
+   int grid = ctx->sms * bps;
+   if ((uint32_t)grid > local_groups) grid = (int)local_groups;
+
+   if (stage_begin(ctx, F3B_STAGE_ITERATE)) return 1;
+   const int nl = f3b_launch_iterate(P, ctx->count_channel != 0, grid, max_blob, ctx->stream);
+   if (!nl) return fail(ctx, "chaos-game launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+   return stage_end(ctx, nl);
+}
+
+int f3b_badvals(f3b_ctx *ctx, double *out) {
+   unsigned long long v = 0;
+   CK(cudaSetDevice(ctx->device));
+   CK(cudaMemcpyAsync(&v, ctx->d_badvals, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+   CK(cudaStreamSynchronize(ctx->stream));
+   *out = (double)v;
+   return 0;
+}
+
+int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1) {
+   if (!ctx || !d) return 1;
+   if (!ctx->accum.p) return fail(ctx, "f3b_density: f3b_frame_begin not called");
+   CK(cudaSetDevice(ctx->device));
+   if (row0 < 0) row0 = 0;
+   if (row1 > ctx->height) row1 = ctx->height;
+
+   F3DensityParams P;
+   memset(&P, 0, sizeof(P));
+   P.hist_color = (const float4 *)ctx->hist_color.p;
+   P.hist_count = ctx->count_channel ? (const float *)ctx->hist_count.p : nullptr;
+   P.accum = (float4 *)ctx->accum.p;
+   P.width = ctx->width;
+   P.height = ctx->height;
+   P.row_begin = row0;
+   P.row_end = row1;
+   P.oversample = d->oversample;
+   P.k1 = (float)d->k1;
+   P.k2 = (float)d->k2;
+   P.int_accum = d->int_accum;
+   P.n_kernels = 0;
+
+   if (d->n_kernels > 0) {
+      if (!d->coefs || !d->widths || d->kernel_size <= 0)
+         return fail(ctx, "f3b_density: missing DE tables");
+      if (d->max_filter_index >= d->n_kernels)
+         return fail(ctx, "f3b_density: max_filter_index %d >= n_kernels %d", d->max_filter_index,
+                     d->n_kernels);
+      const size_t nc = (size_t)d->n_kernels * d->kernel_size;
+      std::vector<float> coefs(nc);
+      std::vector<uint8_t> radius(d->n_kernels);
+      int maxr = 0;
+      for (size_t i = 0; i < nc; i++) coefs[i] = (float)d->coefs[i];
+      /* largest half-width the octant table can address: kernel_size = (h+1)(h+2)/2 */
+      int half = 0;
+      while ((half + 2) * (half + 3) / 2 <= d->kernel_size) half++;
+      for (int k = 0; k < d->n_kernels; k++) {
+         int r = (int)ceil(d->widths[k]) - 1; /* arr_filt_width, rect.c:123 */
+         if (r < 0) r = 0;
+         if (r > half) r = half;
+         if (r > 254) return fail(ctx, "f3b_density: kernel radius %d too large", r);
+         radius[k] = (uint8_t)r;
+         if (k <= d->max_filter_index && r > maxr) maxr = r;
+      }
+      if (ensure(ctx, ctx->de_coefs, nc * sizeof(float))) return 1;
+      if (ensure(ctx, ctx->de_radius, (size_t)d->n_kernels)) return 1;
+      CK(cudaMemcpyAsync(ctx->de_coefs.p, coefs.data(), nc * sizeof(float), cudaMemcpyHostToDevice,
+                         ctx->stream));
+      CK(cudaMemcpyAsync(ctx->de_radius.p, radius.data(), (size_t)d->n_kernels,
+                         cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      P.de_coefs = (const float *)ctx->de_coefs.p;
+      P.de_radius = (const uint8_t *)ctx->de_radius.p;
+      P.n_kernels = d->n_kernels;
+      P.kernel_size = d->kernel_size;
+      P.max_radius = maxr;
+      P.max_filtered_counts = d->max_filtered_counts;
+      P.max_filter_index = d->max_filter_index;
+      P.curve = (float)d->curve;
+   }
+   if (stage_begin(ctx, F3B_STAGE_DENSITY)) return 1;
+   const int nl = f3b_launch_density(P, ctx->stream);
+   if (!nl) return fail(ctx, "density launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+   return stage_end(ctx, nl);
+}
+
+int f3b_density(f3b_ctx *ctx, const f3b_density_desc *d) {
+   return f3b_density_rows(ctx, d, 0, ctx ? ctx->height : 0);
+}
+
+int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out) {
+   if (!ctx || !d) return 1;
+   if (!ctx->accum.p) return fail(ctx, "f3b_finish: f3b_frame_begin not called");
+   CK(cudaSetDevice(ctx->device));
+   if (d->nchan != 3 && d->nchan != 4) return fail(ctx, "f3b_finish: nchan must be 3 or 4");
+   if (d->bytes_per_channel != 1 && d->bytes_per_channel != 2)
+      return fail(ctx, "f3b_finish: bytes_per_channel must be 1 or 2");
+   if (d->filter_width <= 0 || !d->filter) return fail(ctx, "f3b_finish: missing spatial filter");
+   /* the filter footprint of the last pixel must stay inside the bucket grid */
+   const long xmax = (long)d->de_offset + (long)(d->image_width - 1) * d->oversample + d->filter_width;
+   const long ymax = (long)d->de_offset + (long)(d->image_height - 1) * d->oversample + d->filter_width;
+   if (xmax > ctx->width || ymax > ctx->height)
+      return fail(ctx, "f3b_finish: filter footprint %ldx%ld exceeds buffer %dx%d", xmax, ymax,
+                  ctx->width, ctx->height);
+   const size_t fbytes = sizeof(double) * (size_t)d->filter_width * d->filter_width;
+   const size_t ibytes = (size_t)d->image_width * d->image_height * d->nchan * d->bytes_per_channel;
+   if (ensure(ctx, ctx->filter, fbytes)) return 1;
+   if (ensure(ctx, ctx->image, ibytes)) return 1;
+   CK(cudaMemcpyAsync(ctx->filter.p, d->filter, fbytes, cudaMemcpyHostToDevice, ctx->stream));
+   CK(cudaStreamSynchronize(ctx->stream));
+
+   F3FinalParams P;
+   memset(&P, 0, sizeof(P));
+   P.accum = (float4 *)ctx->accum.p;
+   P.width = ctx->width;
+   P.height = ctx->height;
+   P.image_width = d->image_width;
+   P.image_height = d->image_height;
+   P.oversample = d->oversample;
+   P.de_offset = d->de_offset;
+   P.filter = (const double *)ctx->filter.p;
+   P.filter_width = d->filter_width;
+   P.earlyclip = d->earlyclip;
+   P.nchan = d->nchan;
+   P.transp = d->transp;
+   P.bytes_per_channel = d->bytes_per_channel;
+   P.g = 1.0 / d->gamma; /* rect.c:1071 */
+   P.linrange = d->gam_lin_thresh;
+   P.vibrancy = d->vibrancy;
+   P.highpow = d->highlight_power;
+   for (int i = 0; i < 3; i++) P.background[i] = d->background[i];
+   P.out = ctx->image.p;
+
+   if (stage_begin(ctx, F3B_STAGE_FINAL)) return 1;
+   const int nl = f3b_launch_final(P, ctx->stream);
+   if (!nl) return fail(ctx, "final-pass launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+   if (stage_end(ctx, nl)) return 1;
+   if (dev_out) *dev_out = ctx->image.p;
+   return 0;
+}
+
+int f3b_finish(f3b_ctx *ctx, const f3b_final_desc *d, void *out, size_t row_stride) {
+   if (!out) return fail(ctx, "f3b_finish: null output");
+   void *dev = nullptr;
+   if (f3b_finish_device(ctx, d, &dev)) return 1;
+   const size_t row = (size_t)d->image_width * d->nchan * d->bytes_per_channel;
+   if (row_stride < row) return fail(ctx, "f3b_finish: row stride too small");
+   CK(cudaMemcpy2DAsync(out, row_stride, dev, row, row, (size_t)d->image_height,
+                        cudaMemcpyDeviceToHost, ctx->stream));
+   CK(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+int f3b_hist_upload_u32(f3b_ctx *ctx, const uint32_t *buckets5) {
+   if (!ctx || !ctx->hist_color.p) return 1;
+   CK(cudaSetDevice(ctx->device));
+   const size_t n = (size_t)ctx->width * ctx->height;
+   uint32_t *tmp = nullptr;
+   CK(cudaMalloc(&tmp, n * 5 * sizeof(uint32_t)));
+   cudaError_t e = cudaMemcpyAsync(tmp, buckets5, n * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                   ctx->stream);
+   if (e == cudaSuccess)
+      f3b_launch_hist_from_u32(tmp, (float4 *)ctx->hist_color.p,
+                               ctx->count_channel ? (float *)ctx->hist_count.p : nullptr, n,
+                               ctx->stream);
+   e = cudaStreamSynchronize(ctx->stream);
+   cudaFree(tmp);
+   if (e != cudaSuccess) return fail(ctx, "hist upload failed: %s", cudaGetErrorString(e));
+   return 0;
+}
+
+int f3b_hist_download_u32(f3b_ctx *ctx, uint32_t *buckets5) {
+   if (!ctx || !ctx->hist_color.p) return 1;
+   CK(cudaSetDevice(ctx->device));
+   const size_t n = (size_t)ctx->width * ctx->height;
+   uint32_t *tmp = nullptr;
+   CK(cudaMalloc(&tmp, n * 5 * sizeof(uint32_t)));
+   f3b_launch_hist_to_u32((const float4 *)ctx->hist_color.p,
+                          ctx->count_channel ? (const float *)ctx->hist_count.p : nullptr, tmp, n,
+                          ctx->stream);
+   cudaError_t e = cudaMemcpyAsync(buckets5, tmp, n * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                   ctx->stream);
+   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+   cudaFree(tmp);
+   if (e != cudaSuccess) return fail(ctx, "hist download failed: %s", cudaGetErrorString(e));
+   return 0;
+}
+
+int f3b_accum_upload(f3b_ctx *ctx, const float *acc4) {
+   if (!ctx || !ctx->accum.p) return 1;
+   CK(cudaSetDevice(ctx->device));
+   const size_t n = (size_t)ctx->width * ctx->height;
+   CK(cudaMemcpyAsync(ctx->accum.p, acc4, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+   CK(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+int f3b_accum_download(f3b_ctx *ctx, float *acc4) {
+   if (!ctx || !ctx->accum.p) return 1;
+   CK(cudaSetDevice(ctx->device));
+   const size_t n = (size_t)ctx->width * ctx->height;
+   CK(cudaMemcpyAsync(acc4, ctx->accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+   CK(cudaStreamSynchronize(ctx->stream));
+   return 0;
+}
+
+void *f3b_hist_color_ptr(f3b_ctx *ctx) { return ctx ? ctx->hist_color.p : nullptr; }
+void *f3b_hist_count_ptr(f3b_ctx *ctx) {
+   return (ctx && ctx->count_channel) ? ctx->hist_count.p : nullptr;
+}
+void *f3b_accum_ptr(f3b_ctx *ctx) { return ctx ? ctx->accum.p : nullptr; }
+void *f3b_stream_ptr(f3b_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int f3b_stage_stats(f3b_ctx *ctx, int stage, double *ms, uint64_t *launches) {
+   if (!ctx || stage < 0 || stage >= F3B_NSTAGES) return 1;
+   CK(cudaSetDevice(ctx->device));
+   if (stats_collect(ctx)) return 1;
+   if (ms) *ms = ctx->stage_ms[stage];
+   if (launches) *launches = ctx->stage_launches[stage];
+   return 0;
+}
+
+void f3b_stats_reset(f3b_ctx *ctx) {
+   if (!ctx) return;
+   cudaSetDevice(ctx->device);
+   stats_collect(ctx);
+   for (int i = 0; i < F3B_NSTAGES; i++) {
+      ctx->stage_ms[i] = 0.0;
+      ctx->stage_launches[i] = 0;
+   }
+}
+
+} /* extern "C" */

@@ -1,0 +1,73 @@
+/*
+ * f3b_internal.h — launch wrappers shared between the CUDA translation units of
+ * libflam3_b200.so. Not part of the public C-ABI (that is include/flam3_b200.h).
+ */
+#ifndef F3B_INTERNAL_H
+#define F3B_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/flam3_b200.h"
+#include "f3b_pack.h"
+
+typedef f3b_job f3b_sample_job;
+
+#define F3B_CHAINS_PER_GROUP 256 /* = threads per block of the chaos-game kernel */
+
+struct F3IterateParams {
+   const uint8_t *blobs;         /* device: packed temporal samples */
+   const f3b_sample_job *jobs;   /* device */
+   const uint32_t *group_job;    /* device: job index of every chain group */
+   uint32_t n_groups;            /* total chain groups in this launch */
+   uint32_t rank, nranks;        /* this launch runs groups g with g % nranks == rank */
+   float4 *hist_color;           /* [height*width] r,g,b,a sums */
+   float *hist_count;            /* [height*width] 255*logvis sums; may alias nothing when !count */
+   int width, height;
+   int floor_adds;               /* bits 32/33: add floor(value) like the integer buckets */
+   uint64_t seed;
+   unsigned long long *badvals;  /* device counter */
+};
+
+/* returns the number of kernel launches made (0 on error; see cudaGetLastError) */
+int f3b_launch_iterate(const F3IterateParams &p, bool count_channel, int grid_blocks,
+                       size_t smem_bytes, cudaStream_t stream);
+int f3b_iterate_max_blocks_per_sm(size_t smem_bytes);
+
+struct F3DensityParams {
+   const float4 *hist_color;
+   const float *hist_count; /* == nullptr -> use hist_color[].w as the count channel */
+   float4 *accum;
+   int width, height;
+   int row_begin, row_end;    /* target bucket rows written by this launch */
+   int oversample;
+   float k1, k2;
+   int int_accum;             /* bits 32: accumulators are integers (truncate after add) */
+   /* density estimation tables (device); n_kernels == 0 -> plain log scale (rect.c:947-974) */
+   const float *de_coefs;     /* [n_kernels * kernel_size] octant-packed, filters.c:322-384 */
+   const uint8_t *de_radius;  /* [n_kernels] ceil(width)-1, rect.c:123 */
+   int n_kernels, kernel_size, max_radius;
+   int max_filtered_counts, max_filter_index;
+   float curve;
+};
+int f3b_launch_density(const F3DensityParams &p, cudaStream_t stream);
+
+struct F3FinalParams {
+   float4 *accum; /* modified in place when earlyclip */
+   int width, height; /* bucket grid */
+   int image_width, image_height, oversample, de_offset;
+   const double *filter; /* device [fw*fw] */
+   int filter_width;
+   int earlyclip, nchan, transp, bytes_per_channel;
+   double g, linrange, vibrancy, highpow;
+   double background[3];
+   void *out;          /* device image, tightly packed image_width*nchan*bpc per row */
+};
+int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream);
+
+int f3b_launch_hist_from_u32(const uint32_t *src5, float4 *color, float *count, size_t n,
+                             cudaStream_t stream);
+int f3b_launch_hist_to_u32(const float4 *color, const float *count, uint32_t *dst5, size_t n,
+                           cudaStream_t stream);
+
+#endif

@@ -1,0 +1,228 @@
+/*
+ * f3b_iterate.cu — the chaos game + histogram accumulation for sm_100a.
+ *
+ * Replaces the reference's iter_thread (rect.c:253-527) + flam3_iterate (flam3.c:232-299)
+ * + apply_xform (variations.c:2129-2399). Design:
+ *
+ *  - one persistent walker per thread; a thread runs whole "chains" (= the reference's
+ *    sub-batches: random start point, `fuse` discarded iterations, then stored ones);
+ *  - a block (256 threads) works on a "chain group": 256 chains of the SAME temporal
+ *    sample, whose packed genome/chooser/palette/camera blob is staged once in shared
+ *    memory; blocks walk the group list with a grid stride (persistent CTAs);
+ *  - xform selection reproduces the 16384-grain table exactly through per-row cumulative
+ *    counts held in shared memory (flam3.c:165-224), including xaos rows;
+ *  - the 5-channel bucket bump (rect.c:500-512) becomes ONE 16-byte vector reduction
+ *    `red.global.add.v4.f32` into L2-resident float4 colour buckets, plus a scalar
+ *    `red.global.add.f32` into the count plane only when the count channel is not
+ *    identical to the alpha channel (COUNT=false: palette alpha == 1 and temporal filter
+ *    weight == 1 everywhere, the common case, where b[3] == b[4] bucket by bucket).
+ *
+ * Adds are integer valued (floor, like bump_no_overflow with unsigned buckets,
+ * flam3.c:3838-3854), so float accumulation is exact up to 2^24 per channel.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "f3b_internal.h"
+#include "f3b_variations.cuh"
+
+#define F3B_BLOCK F3B_CHAINS_PER_GROUP
+
+__device__ __forceinline__ void f3b_red_v4(float4 *addr, float r, float g, float b, float a) {
+   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(r), "f"(g),
+                "f"(b), "f"(a)
+                : "memory");
+}
+__device__ __forceinline__ void f3b_red_f32(float *addr, float v) {
+   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(F3B_BLOCK, 4) f3b_iterate_kernel(const F3IterateParams P) {
+   extern __shared__ __align__(16) uint32_t smem[];
+   const float *sf = reinterpret_cast<const float *>(smem);
+
+   const uint32_t tid = threadIdx.x;
+   uint32_t loaded_job = 0xffffffffu;
+   unsigned int bad = 0;
+
+   /* local group index lg -> global group g = lg * nranks + rank */
+   for (uint32_t lg = blockIdx.x;; lg += gridDim.x) {
+      const uint64_t g64 = (uint64_t)lg * P.nranks + P.rank;
+      if (g64 >= P.n_groups) break;
+      const uint32_t g = (uint32_t)g64;
+      const uint32_t ji = P.group_job[g];
+      const f3b_sample_job job = P.jobs[ji];
+
+      if (ji != loaded_job) {
+         __syncthreads(); /* everyone is done with the previous blob */
+         const uint32_t *src = reinterpret_cast<const uint32_t *>(P.blobs + job.blob_offset);
+         const uint32_t words = src[F3B_H_WORDS];
+         for (uint32_t i = tid; i < words; i += F3B_BLOCK) smem[i] = src[i];
+         __syncthreads();
+         loaded_job = ji;
+      }
+
+      const uint32_t chain = (g - job.first_group) * F3B_BLOCK + tid;
+      if (chain >= job.n_chains) continue;
+
+      /* stored iterations of this chain */
+      const uint64_t base = job.n_iters / job.n_chains;
+      const uint32_t rem = (uint32_t)(job.n_iters % job.n_chains);
+      const int n_store = (int)(base + (chain < rem ? 1u : 0u));
+      if (n_store == 0) continue;
+
+      /* header */
+      const uint32_t nstd = smem[F3B_H_NSTD];
+      const int final_idx = (int)smem[F3B_H_FINAL];
+      const bool xaos = smem[F3B_H_XAOS] != 0;
+      const float final_opacity = sf[F3B_H_FINAL_OPACITY];
+      const bool pal_linear = smem[F3B_H_PALMODE] != 0;
+      const int cmap_size = (int)smem[F3B_H_CMAPSIZE];
+      const bool rotate = smem[F3B_H_ROTATE] != 0;
+      const uint32_t *cum = smem + smem[F3B_H_OFF_CHOOSER];
+      const uint32_t *xftab = smem + smem[F3B_H_OFF_XFTAB];
+      const float4 *dmap = reinterpret_cast<const float4 *>(smem + smem[F3B_H_OFF_PALETTE]);
+      const float b0 = sf[F3B_H_B0], b1 = sf[F3B_H_B1], b2 = sf[F3B_H_B2], b3 = sf[F3B_H_B3];
+      const float ws0 = sf[F3B_H_WS0], hs1 = sf[F3B_H_HS1];
+
+      F3Rng rng;
+      f3b_rng_seed(rng, P.seed, job.sample_id, chain);
+
+      /* rect.c:394-397: start point in [-1,1]^2, colour in [0,1] (the 4th draw seeds an
+       * opacity that is overwritten before first use) */
+      float px = rng.u11();
+      float py = rng.u11();
+      float pc = rng.u01();
+      float pv = rng.u01();
+      uint32_t lastxf = 0;
+      int consec = 0;
+
+      for (int i = -(int)job.fuse; i < n_store; i++) {
+         float qx, qy, qc, qv;
+         uint32_t fn;
+         /* flam3.c:249-270: pick + apply, retrying a bad value up to 4 times in place */
+         for (;;) {
+            const uint32_t k = rng.next() & (F3B_CHOOSER_GRAIN - 1u);
+            const uint32_t *row = cum + (xaos ? lastxf * nstd : 0u);
+            fn = 0;
+            for (uint32_t j = 0; j + 1 < nstd; j++) fn += (k >= row[j]) ? 1u : 0u;
+            const bool isbad =
+                f3b_apply_xform(sf + xftab[fn], px, py, pc, qx, qy, qc, qv, rng);
+            if (!isbad) {
+               consec = 0;
+               break;
+            }
+            bad++;
+            if (++consec >= 5) {
+               consec = 0;
+               break;
+            }
+            px = qx;
+            py = qy;
+            pc = qc;
+            pv = qv;
+         }
+         lastxf = fn + 1;
+         px = qx;
+         py = qy;
+         pc = qc;
+         pv = qv;
+
+         /* flam3.c:280-287: final xform does not feed back into the orbit */
+         if (final_idx >= 0) {
+            bool apply = (final_opacity == 1.0f);
+            if (!apply) apply = rng.u01() < final_opacity;
+            if (apply) {
+               float fx, fy, fc, fv;
+               f3b_apply_xform(sf + xftab[final_idx], px, py, pc, fx, fy, fc, fv, rng);
+               qx = fx;
+               qy = fy;
+               qc = fc; /* opacity stays that of the regular xform */
+            }
+         }
+
+         if (i < 0) continue;
+
+         /* rect.c:419-441: camera */
+         float x = qx, y = qy;
+         if (rotate) {
+            const float dx = qx - sf[F3B_H_RCX], dy = qy - sf[F3B_H_RCY];
+            x = dx * sf[F3B_H_ROT00] + dy * sf[F3B_H_ROT01] + sf[F3B_H_RCX];
+            y = dx * sf[F3B_H_ROT10] + dy * sf[F3B_H_ROT11] + sf[F3B_H_RCY];
+         }
+         if (!(x >= b0 && y >= b1 && x <= b2 && y <= b3) || qv == 0.0f) continue;
+         const int ix = (int)((x - b0) * ws0);
+         const int iy = (int)((y - b1) * hs1);
+         if (ix >= P.width || iy >= P.height) continue;
+         const size_t bidx = (size_t)ix + (size_t)P.width * (size_t)iy;
+
+         /* rect.c:465-498: palette lookup */
+         const float findex = qc * (float)cmap_size;
+         int ci = (int)findex;
+         float4 col;
+         if (pal_linear) {
+            float frac;
+            if (ci < 0) {
+               ci = 0;
+               frac = 0.0f;
+            } else if (ci >= cmap_size - 1) {
+               ci = cmap_size - 2;
+               frac = 1.0f;
+            } else
+               frac = findex - (float)ci;
+            const float4 c0 = dmap[ci], c1 = dmap[ci + 1];
+            col.x = c0.x * (1.0f - frac) + c1.x * frac;
+            col.y = c0.y * (1.0f - frac) + c1.y * frac;
+            col.z = c0.z * (1.0f - frac) + c1.z * frac;
+            col.w = c0.w * (1.0f - frac) + c1.w * frac;
+         } else {
+            ci = ci < 0 ? 0 : (ci >= cmap_size - 1 ? cmap_size - 1 : ci);
+            col = dmap[ci];
+         }
+         float cnt = 255.0f;
+         if (qv != 1.0f) {
+            col.x *= qv;
+            col.y *= qv;
+            col.z *= qv;
+            col.w *= qv;
+            cnt *= qv;
+         }
+         if (P.floor_adds) {
+            col.x = floorf(col.x);
+            col.y = floorf(col.y);
+            col.z = floorf(col.z);
+            col.w = floorf(col.w);
+            cnt = floorf(cnt);
+         }
+         f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
+         if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
+      }
+   }
+
+   /* fic.badvals += badcount (rect.c:408) */
+   for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+   if ((tid & 31u) == 0 && bad) atomicAdd(P.badvals, (unsigned long long)bad);
+}
+
+int f3b_iterate_max_blocks_per_sm(size_t smem_bytes) {
+   int nb = 0;
+   cudaFuncSetAttribute(f3b_iterate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)(F3B_MAX_BLOB_WORDS * 4));
+   cudaFuncSetAttribute(f3b_iterate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)(F3B_MAX_BLOB_WORDS * 4));
+   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true>, F3B_BLOCK,
+                                                     smem_bytes) != cudaSuccess)
+      return 0;
+   return nb;
+}
+
+int f3b_launch_iterate(const F3IterateParams &p, bool count_channel, int grid_blocks,
+                       size_t smem_bytes, cudaStream_t stream) {
+   if (grid_blocks <= 0) return 0;
+   if (count_channel)
+      f3b_iterate_kernel<true><<<grid_blocks, F3B_BLOCK, smem_bytes, stream>>>(p);
+   else
+      f3b_iterate_kernel<false><<<grid_blocks, F3B_BLOCK, smem_bytes, stream>>>(p);
+   return cudaGetLastError() == cudaSuccess ? 1 : 0;
+}

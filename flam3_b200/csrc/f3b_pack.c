@@ -1,0 +1,431 @@
+/*
+ * f3b_pack.c — host packer: one interpolated flam3_genome -> one packed temporal sample
+ * (layout: f3b_pack.h). Compiled against the reference's public header flam3.h, like any
+ * libflam3 client; it is the only place (with f3b_render.c) that reads flam3 structs.
+ *
+ * It restates, for the packed representation:
+ *   prepare_precalc_flags   variations.c:2016-2126  (active variation list, A/T/Y flags,
+ *                                                    vis_adjusted, has_post, has_preblur)
+ *   xform_precalc + *_precalc   variations.c:1942-2014
+ *   flam3_create_xform_distrib / flam3_create_chaos_distrib   flam3.c:76-224
+ *   the dmap and camera set-up of render_rectangle              rect.c:778-827
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "f3b_host.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+#define P_EPS 1e-10 /* EPS, private.h:47 */
+
+static inline uint32_t f2u(double v) {
+   float f = (float)v;
+   uint32_t u;
+   memcpy(&u, &f, 4);
+   return u;
+}
+
+/* interpolation.c:22-29 */
+static double vis_adjust(double opacity) {
+   if (opacity == 0.0) return 0.0;
+   return pow(10.0, -log(1.0 / opacity) / log(2.0));
+}
+
+/* which per-point precalcs a variation consumes (variations.c:2050-2115) */
+static unsigned var_precalc_flags(int id) {
+   switch (id) {
+   case VAR_POLAR: case VAR_HANDKERCHIEF: case VAR_HEART: case VAR_DISC: case VAR_EX:
+   case VAR_JULIA: case VAR_FAN: case VAR_FAN2: case VAR_DISC2: case VAR_POLAR2:
+      return F3B_XF_ATAN_XY;
+   case VAR_SPIRAL: case VAR_HYPERBOLIC: case VAR_DIAMOND: case VAR_POWER: case VAR_RINGS:
+   case VAR_RINGS2:
+      return F3B_XF_ANGLES;
+   case VAR_BLOB:
+      return F3B_XF_ATAN_XY | F3B_XF_ANGLES;
+   case VAR_JULIAN: case VAR_JULIASCOPE: case VAR_RADIAL_BLUR: case VAR_NGON:
+   case VAR_SUPER_SHAPE: case VAR_FLOWER: case VAR_CONIC: case VAR_CPOW: case VAR_ESCHER:
+   case VAR_WEDGE: case VAR_WEDGE_JULIA: case VAR_WEDGE_SPH: case VAR_WHORL: case VAR_LOG:
+      return F3B_XF_ATAN_YX;
+   default:
+      return 0;
+   }
+}
+
+/* Packed parameters of variation `id`, in the order f3b_variations.cuh consumes them.
+ * Returns the number of words written (== f3b_var_nparams[id]). */
+static int pack_var_params(const flam3_xform *x, int id, double *p) {
+   switch (id) {
+   case VAR_WAVES: { /* waves_precalc, variations.c:1969 */
+      const double dx = x->c[2][0], dy = x->c[2][1];
+      p[0] = x->c[1][0];
+      p[1] = 1.0 / (dx * dx + P_EPS);
+      p[2] = x->c[1][1];
+      p[3] = 1.0 / (dy * dy + P_EPS);
+      return 4;
+   }
+   case VAR_POPCORN: p[0] = x->c[2][0]; p[1] = x->c[2][1]; return 2;
+   case VAR_RINGS: p[0] = x->c[2][0] * x->c[2][0] + P_EPS; return 1;
+   case VAR_FAN:
+      p[0] = M_PI * (x->c[2][0] * x->c[2][0] + P_EPS);
+      p[1] = x->c[2][1];
+      p[2] = 0.5 * p[0];
+      return 3;
+   case VAR_BLOB:
+      p[0] = x->blob_low; p[1] = x->blob_high - x->blob_low; p[2] = x->blob_waves;
+      return 3;
+   case VAR_PDJ: p[0] = x->pdj_a; p[1] = x->pdj_b; p[2] = x->pdj_c; p[3] = x->pdj_d; return 4;
+   case VAR_FAN2:
+      p[0] = M_PI * (x->fan2_x * x->fan2_x + P_EPS);
+      p[1] = x->fan2_y;
+      p[2] = 0.5 * p[0];
+      return 3;
+   case VAR_RINGS2: p[0] = x->rings2_val * x->rings2_val + P_EPS; return 1;
+   case VAR_PERSPECTIVE: { /* perspective_precalc, variations.c:1942 */
+      const double ang = x->perspective_angle * M_PI / 2.0;
+      p[0] = x->perspective_dist;
+      p[1] = sin(ang);
+      p[2] = x->perspective_dist * cos(ang);
+      return 3;
+   }
+   case VAR_JULIAN: /* juliaN_precalc, variations.c:1948 */
+      p[0] = x->julian_power;
+      p[1] = x->julian_dist / x->julian_power / 2.0;
+      p[2] = fabs(x->julian_power);
+      return 3;
+   case VAR_JULIASCOPE: /* juliaScope_precalc, variations.c:1959 */
+      p[0] = x->juliascope_power;
+      p[1] = x->juliascope_dist / x->juliascope_power / 2.0;
+      p[2] = fabs(x->juliascope_power);
+      return 3;
+   case VAR_RADIAL_BLUR: /* radial_blur_precalc, variations.c:1964 */
+      p[0] = sin(x->radial_blur_angle * M_PI / 2.0);
+      p[1] = cos(x->radial_blur_angle * M_PI / 2.0);
+      return 2;
+   case VAR_PIE: p[0] = x->pie_slices; p[1] = x->pie_rotation; p[2] = x->pie_thickness; return 3;
+   case VAR_NGON:
+      p[0] = x->ngon_power / 2.0;
+      p[1] = 2.0 * M_PI / x->ngon_sides;
+      p[2] = x->ngon_corners;
+      p[3] = x->ngon_circle;
+      return 4;
+   case VAR_CURL: p[0] = x->curl_c1; p[1] = x->curl_c2; return 2;
+   case VAR_RECTANGLES: p[0] = x->rectangles_x; p[1] = x->rectangles_y; return 2;
+   case VAR_DISC2: { /* disc2_precalc, variations.c:1977 */
+      const double add = x->disc2_twist;
+      double s = sin(add), c = cos(add) - 1.0;
+      if (add > 2 * M_PI) {
+         const double k = 1 + add - 2 * M_PI;
+         c *= k;
+         s *= k;
+      }
+      if (add < -2 * M_PI) {
+         const double k = 1 + add + 2 * M_PI;
+         c *= k;
+         s *= k;
+      }
+      p[0] = x->disc2_rot * M_PI;
+      p[1] = s;
+      p[2] = c;
+      return 3;
+   }
+   case VAR_SUPER_SHAPE: /* supershape_precalc, variations.c:1999 */
+      p[0] = x->super_shape_m / 4.0;
+      p[1] = x->super_shape_n2;
+      p[2] = x->super_shape_n3;
+      p[3] = x->super_shape_rnd;
+      p[4] = x->super_shape_holes;
+      p[5] = -1.0 / x->super_shape_n1;
+      return 6;
+   case VAR_FLOWER: p[0] = x->flower_petals; p[1] = x->flower_holes; return 2;
+   case VAR_CONIC: p[0] = x->conic_eccentricity; p[1] = x->conic_holes; return 2;
+   case VAR_PARABOLA: p[0] = x->parabola_height; p[1] = x->parabola_width; return 2;
+   case VAR_BENT2: p[0] = x->bent2_x; p[1] = x->bent2_y; return 2;
+   case VAR_BIPOLAR: p[0] = -(M_PI / 2.0) * x->bipolar_shift; return 1;
+   case VAR_CELL: p[0] = x->cell_size; p[1] = 1.0 / x->cell_size; return 2;
+   case VAR_CPOW:
+      p[0] = 2.0 * M_PI / x->cpow_power;
+      p[1] = x->cpow_r / x->cpow_power;
+      p[2] = x->cpow_i / x->cpow_power;
+      p[3] = x->cpow_power;
+      return 4;
+   case VAR_CURVE: {
+      double xl = x->curve_xlength * x->curve_xlength, yl = x->curve_ylength * x->curve_ylength;
+      if (xl < 1e-20) xl = 1e-20;
+      if (yl < 1e-20) yl = 1e-20;
+      p[0] = x->curve_xamp;
+      p[1] = x->curve_yamp;
+      p[2] = 1.0 / xl;
+      p[3] = 1.0 / yl;
+      return 4;
+   }
+   case VAR_ESCHER:
+      p[0] = 0.5 * (1.0 + cos(x->escher_beta));
+      p[1] = 0.5 * sin(x->escher_beta);
+      return 2;
+   case VAR_LAZYSUSAN:
+      p[0] = x->lazysusan_spin; p[1] = x->lazysusan_space; p[2] = x->lazysusan_twist;
+      p[3] = x->lazysusan_x; p[4] = x->lazysusan_y;
+      return 5;
+   case VAR_MODULUS: p[0] = x->modulus_x; p[1] = x->modulus_y; return 2;
+   case VAR_OSCILLOSCOPE:
+      p[0] = 2.0 * M_PI * x->oscope_frequency;
+      p[1] = x->oscope_amplitude;
+      p[2] = x->oscope_separation;
+      p[3] = x->oscope_damping;
+      return 4;
+   case VAR_POPCORN2: p[0] = x->popcorn2_x; p[1] = x->popcorn2_y; p[2] = x->popcorn2_c; return 3;
+   case VAR_SEPARATION:
+      p[0] = x->separation_x * x->separation_x;
+      p[1] = x->separation_xinside;
+      p[2] = x->separation_y * x->separation_y;
+      p[3] = x->separation_yinside;
+      return 4;
+   case VAR_SPLIT: p[0] = x->split_xsize * M_PI; p[1] = x->split_ysize * M_PI; return 2;
+   case VAR_SPLITS: p[0] = x->splits_x; p[1] = x->splits_y; return 2;
+   case VAR_STRIPES: p[0] = 1.0 - x->stripes_space; p[1] = x->stripes_warp; return 2;
+   case VAR_WEDGE:
+      p[0] = x->wedge_angle; p[1] = x->wedge_hole; p[2] = x->wedge_count; p[3] = x->wedge_swirl;
+      p[4] = 1.0 - x->wedge_angle * x->wedge_count * M_1_PI * 0.5;
+      return 5;
+   case VAR_WEDGE_JULIA: /* wedgeJulia_precalc, variations.c:1953 */
+      p[0] = x->wedge_julia_dist / x->wedge_julia_power / 2.0;
+      p[1] = fabs(x->wedge_julia_power);
+      p[2] = x->wedge_julia_power;
+      p[3] = x->wedge_julia_count;
+      p[4] = 1.0 - x->wedge_julia_angle * x->wedge_julia_count * M_1_PI * 0.5;
+      p[5] = x->wedge_julia_angle;
+      return 6;
+   case VAR_WEDGE_SPH:
+      p[0] = x->wedge_sph_angle; p[1] = x->wedge_sph_hole; p[2] = x->wedge_sph_count;
+      p[3] = x->wedge_sph_swirl;
+      p[4] = 1.0 - x->wedge_sph_angle * x->wedge_sph_count * M_1_PI * 0.5;
+      return 5;
+   case VAR_WHORL: p[0] = x->whorl_inside; p[1] = x->whorl_outside; return 2;
+   case VAR_WAVES2:
+      p[0] = x->waves2_freqx; p[1] = x->waves2_scalex; p[2] = x->waves2_freqy;
+      p[3] = x->waves2_scaley;
+      return 4;
+   case VAR_AUGER:
+      p[0] = x->auger_sym; p[1] = x->auger_weight; p[2] = x->auger_freq; p[3] = x->auger_scale;
+      return 4;
+   case VAR_FLUX: p[0] = 2.0 + x->flux_spread; return 1;
+   case VAR_MOBIUS:
+      p[0] = x->mobius_re_a; p[1] = x->mobius_im_a; p[2] = x->mobius_re_b; p[3] = x->mobius_im_b;
+      p[4] = x->mobius_re_c; p[5] = x->mobius_im_c; p[6] = x->mobius_re_d; p[7] = x->mobius_im_d;
+      return 8;
+   default:
+      return 0;
+   }
+}
+
+/* One row of the xform chooser as cumulative counts: cum[j] = number of entries of the
+ * reference's 16384-entry table whose value is <= j. Walks the same double-precision
+ * accumulation as flam3_create_chaos_distrib (flam3.c:165-224), so the step positions
+ * are identical. xi < 0 -> plain weights; else weights scaled by chaos[xi][.] */
+static int chooser_row(const flam3_genome *cp, int nstd, int xi, uint32_t *cum) {
+   double dr = 0.0;
+   for (int i = 0; i < nstd; i++) {
+      double d = cp->xform[i].density;
+      if (xi >= 0) d *= cp->chaos[xi][i];
+      if (d < 0.0) {
+         fprintf(stderr, "xform weight must be non-negative, not %g.\n", d);
+         return 1;
+      }
+      dr += d;
+   }
+   if (dr == 0.0) {
+      fprintf(stderr, "cannot iterate empty flame.\n");
+      return 1;
+   }
+   dr /= (double)F3B_CHOOSER_GRAIN;
+
+   for (int i = 0; i < nstd; i++) cum[i] = 0;
+   int j = 0;
+   double t = cp->xform[0].density;
+   if (xi >= 0) t *= cp->chaos[xi][0];
+   double r = 0.0;
+   for (unsigned i = 0; i < F3B_CHOOSER_GRAIN; i++) {
+      while (r >= t && j < nstd - 1) {
+         j++;
+         t += (xi >= 0) ? cp->xform[j].density * cp->chaos[xi][j] : cp->xform[j].density;
+      }
+      cum[j]++; /* histogram of picked xforms, made cumulative below */
+      r += dr;
+   }
+   for (int i = 1; i < nstd; i++) cum[i] += cum[i - 1];
+   return 0;
+}
+
+int f3b_chaos_enabled(const flam3_genome *cp, int nstd) {
+   /* flam3_check_unity_chaos, flam3.c:148-163 */
+   for (int i = 0; i < nstd; i++)
+      for (int j = 0; j < nstd; j++)
+         if (fabs(cp->chaos[i][j] - 1.0) > P_EPS) return 1;
+   return 0;
+}
+
+static int pack_xform(const flam3_xform *x, uint32_t *w, size_t cap, size_t *pos) {
+   size_t o = *pos;
+   if (o + F3B_X_VARS > cap) return 1;
+   uint32_t *r = w + o;
+   r[F3B_X_C00] = f2u(x->c[0][0]); r[F3B_X_C10] = f2u(x->c[1][0]); r[F3B_X_C20] = f2u(x->c[2][0]);
+   r[F3B_X_C01] = f2u(x->c[0][1]); r[F3B_X_C11] = f2u(x->c[1][1]); r[F3B_X_C21] = f2u(x->c[2][1]);
+   r[F3B_X_P00] = f2u(x->post[0][0]); r[F3B_X_P10] = f2u(x->post[1][0]); r[F3B_X_P20] = f2u(x->post[2][0]);
+   r[F3B_X_P01] = f2u(x->post[0][1]); r[F3B_X_P11] = f2u(x->post[1][1]); r[F3B_X_P21] = f2u(x->post[2][1]);
+   r[F3B_X_SCOLOR] = f2u(x->color_speed * x->color);
+   r[F3B_X_ONEMS] = f2u(1.0 - x->color_speed);
+   r[F3B_X_VIS] = f2u(vis_adjust(x->opacity));
+   r[F3B_X_PREBLUR] = f2u(x->var[VAR_PRE_BLUR]);
+
+   unsigned flags = 0;
+   const int has_post = !(x->post[0][0] == 1.0 && x->post[0][1] == 0.0 && x->post[1][0] == 0.0 &&
+                          x->post[1][1] == 1.0 && x->post[2][0] == 0.0 && x->post[2][1] == 0.0);
+   if (has_post) flags |= F3B_XF_HAS_POST;
+   if (x->var[VAR_PRE_BLUR] != 0.0) flags |= F3B_XF_PREBLUR;
+
+   o += F3B_X_VARS;
+   unsigned nv = 0;
+   for (int id = 0; id < flam3_nvariations; id++) {
+      if (x->var[id] == 0.0) continue;
+      /* pre_blur is listed by the reference but has no case in its switch
+       * (variations.c:2181-2379): it only acts through has_preblur */
+      if (id == VAR_PRE_BLUR) continue;
+      double p[8];
+      const int np = pack_var_params(x, id, p);
+      if (np != f3b_var_nparams[id]) {
+         fprintf(stderr, "flam3_b200: internal error, variation %d packs %d params\n", id, np);
+         return 1;
+      }
+      if (o + 2 + (size_t)np > cap) return 1;
+      w[o++] = (uint32_t)id | ((uint32_t)np << 8);
+      w[o++] = f2u(x->var[id]);
+      for (int k = 0; k < np; k++) w[o++] = f2u(p[k]);
+      flags |= var_precalc_flags(id);
+      nv++;
+   }
+   r[F3B_X_FLAGS] = flags;
+   r[F3B_X_NVARS] = nv;
+   *pos = o;
+   return 0;
+}
+
+int f3b_camera_setup(const flam3_genome *cp, const f3b_frame_geom *g, f3b_camera *cam) {
+   /* rect.c:785-827 */
+   if (cp->sample_density <= 0.0) {
+      fprintf(stderr, "sample density (quality) must be greater than zero, not %g.\n",
+              cp->sample_density);
+      return 1;
+   }
+   const double scale = pow(2.0, cp->zoom);
+   cam->sample_density = cp->sample_density * scale * scale;
+   double ppux = cp->pixels_per_unit * scale;
+   const double ppuy = g->field ? (ppux / 2.0) : ppux;
+   ppux /= g->pixel_aspect_ratio;
+   double shift = 0.0;
+   if (g->field == flam3_field_even) shift = -0.5;
+   else if (g->field == flam3_field_odd) shift = 0.5;
+   shift = shift / ppux;
+   const double t0 = (double)g->gutter_width / (g->oversample * ppux);
+   const double t1 = (double)g->gutter_width / (g->oversample * ppuy);
+   const double corner0 = cp->center[0] - g->image_width / ppux / 2.0;
+   const double corner1 = cp->center[1] - g->image_height / ppuy / 2.0;
+   cam->bounds[0] = corner0 - t0;
+   cam->bounds[1] = corner1 - t1 + shift;
+   cam->bounds[2] = corner0 + g->image_width / ppux + t0;
+   cam->bounds[3] = corner1 + g->image_height / ppuy + t1 + shift;
+   const double size0 = 1.0 / (cam->bounds[2] - cam->bounds[0]);
+   const double size1 = 1.0 / (cam->bounds[3] - cam->bounds[1]);
+   cam->rot[0][0] = cos(cp->rotate * 2 * M_PI / 360.0);
+   cam->rot[0][1] = -sin(cp->rotate * 2 * M_PI / 360.0);
+   cam->rot[1][0] = -cam->rot[0][1];
+   cam->rot[1][1] = cam->rot[0][0];
+   cam->ws0 = g->width * size0;
+   cam->hs1 = g->height * size1;
+   cam->ppux = ppux;
+   cam->ppuy = ppuy;
+   return 0;
+}
+
+int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_scalar,
+                    int cmap_size, uint32_t *w, size_t cap, size_t *used, int *count_is_alpha) {
+   const int has_final_slot = cp->final_xform_index >= 0;
+   const int nstd = cp->num_xforms - has_final_slot;
+   const int final_on = (cp->final_xform_enable == 1 && has_final_slot);
+   if (nstd <= 0) {
+      fprintf(stderr, "cannot iterate empty flame.\n");
+      return 1;
+   }
+   for (int i = 0; i < cp->num_xforms; i++)
+      if (cp->xform[i].density < 0.0) {
+         fprintf(stderr, "xform %d weight must be non-negative, not %g.\n", i,
+                 cp->xform[i].density);
+         return 1;
+      }
+   const int xaos = f3b_chaos_enabled(cp, nstd);
+   const int rows = xaos ? nstd + 1 : 1;
+   const int nxf = nstd + (final_on ? 1 : 0);
+
+   size_t o = F3B_H_SIZE;
+   if (o + (size_t)rows * nstd + (size_t)nxf > cap) return 2;
+   memset(w, 0, F3B_H_SIZE * 4);
+   w[F3B_H_NSTD] = (uint32_t)nstd;
+   w[F3B_H_FINAL] = final_on ? (uint32_t)nstd : (uint32_t)-1;
+   w[F3B_H_XAOS] = (uint32_t)xaos;
+   w[F3B_H_FINAL_OPACITY] = f2u(final_on ? cp->xform[cp->final_xform_index].opacity : 1.0);
+   w[F3B_H_PALMODE] = (cp->palette_mode == flam3_palette_mode_linear) ? 1u : 0u;
+   w[F3B_H_CMAPSIZE] = (uint32_t)cmap_size;
+   w[F3B_H_ROTATE] = (cp->rotate != 0.0) ? 1u : 0u;
+   w[F3B_H_ROT00] = f2u(cam->rot[0][0]); w[F3B_H_ROT01] = f2u(cam->rot[0][1]);
+   w[F3B_H_ROT10] = f2u(cam->rot[1][0]); w[F3B_H_ROT11] = f2u(cam->rot[1][1]);
+   w[F3B_H_RCX] = f2u(cp->rot_center[0]); w[F3B_H_RCY] = f2u(cp->rot_center[1]);
+   w[F3B_H_B0] = f2u(cam->bounds[0]); w[F3B_H_B1] = f2u(cam->bounds[1]);
+   w[F3B_H_B2] = f2u(cam->bounds[2]); w[F3B_H_B3] = f2u(cam->bounds[3]);
+   w[F3B_H_WS0] = f2u(cam->ws0); w[F3B_H_HS1] = f2u(cam->hs1);
+   w[F3B_H_NXF] = (uint32_t)nxf;
+
+   /* chooser rows: row 0 plain weights, row i+1 conditioned on previous xform i */
+   w[F3B_H_OFF_CHOOSER] = (uint32_t)o;
+   if (chooser_row(cp, nstd, -1, w + o)) return 1;
+   o += (size_t)nstd;
+   if (xaos)
+      for (int i = 0; i < nstd; i++) {
+         if (chooser_row(cp, nstd, i, w + o)) return 1;
+         o += (size_t)nstd;
+      }
+
+   /* xform table + records. The reference indexes standard xforms 0..nstd-1 and assumes
+    * the final xform, if any, is the last one (flam3.c:176). */
+   w[F3B_H_OFF_XFTAB] = (uint32_t)o;
+   uint32_t *tab = w + o;
+   o += (size_t)nxf;
+   for (int i = 0; i < nstd; i++) {
+      tab[i] = (uint32_t)o;
+      if (pack_xform(&cp->xform[i], w, cap, &o)) return 2;
+   }
+   if (final_on) {
+      tab[nstd] = (uint32_t)o;
+      if (pack_xform(&cp->xform[cp->final_xform_index], w, cap, &o)) return 2;
+   }
+
+   /* dmap (rect.c:778-782): palette * WHITE_LEVEL * temporal filter weight */
+   o = (o + 3) & ~(size_t)3;
+   if (o + 256 * 4 > cap) return 2;
+   w[F3B_H_OFF_PALETTE] = (uint32_t)o;
+   /* With step lookup, alpha == 1 and weight == 1 the alpha sum equals the count sum hit
+    * by hit. Linear lookup blends alpha in floating point (rect.c:482-485), which the
+    * truncating bucket add can round down, so it keeps its own count plane. */
+   int alpha_ok = (cp->palette_mode != flam3_palette_mode_linear);
+   for (int j = 0; j < 256; j++) {
+      for (int k = 0; k < 4; k++) w[o + j * 4 + k] = f2u(cp->palette[j].color[k] * 255.0 * color_scalar);
+      if (cp->palette[j].color[3] * 255.0 * color_scalar != 255.0) alpha_ok = 0;
+   }
+   o += 256 * 4;
+   w[F3B_H_WORDS] = (uint32_t)o;
+   *used = o;
+   if (count_is_alpha) *count_is_alpha = alpha_ok;
+   return 0;
+}

@@ -1,0 +1,423 @@
+/*
+ * f3b_render.c — the drop-in boundary: `flam3_render` and `flam3_render_memory_required`
+ * with the reference's exact C ABI (flam3.h:623,625), so flam3-render, flam3-animate and
+ * flam3-genome link against it unchanged.
+ *
+ * This is the host half of render_rectangle (rect.c:529-1286) re-expressed as a driver of
+ * the GPU stages in include/flam3_b200.h: it keeps the batch / temporal-sample structure,
+ * the filter and gutter sizing, the camera, k1/k2, the averaging of gamma / vibrancy /
+ * background, the bits / field / nchan / transp / earlyclip semantics, the stats and the
+ * evolution of the frame's ISAAC context; the iter_thread / de_thread pthreads are gone.
+ * All temporal samples of a batch are packed first and run in ONE chaos-game launch.
+ *
+ * Host-side genome interpolation (`flam3_interpolate`) is not part of the hot path and is
+ * resolved from the libflam3 this file is dropped into.
+ *
+ * There is no CPU fallback: if no sm_100-class GPU is usable the call fails loudly.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "f3b_host.h"
+
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static f3b_ctx *g_ctx = NULL;
+
+static f3b_ctx *get_ctx(void) {
+   if (!g_ctx) {
+      const char *e = getenv("F3B_DEVICE");
+      int dev = e ? atoi(e) : 0;
+      if (f3b_ctx_create(dev, &g_ctx)) {
+         fprintf(stderr, "flam3_render (B200): cannot create a GPU context on device %d; "
+                         "this build has no CPU path.\n", dev);
+         g_ctx = NULL;
+      }
+   }
+   return g_ctx;
+}
+
+/* Exposed so hosts embedding the library (and the tests / bench) can reach the context
+ * the drop-in renders with, e.g. for per-stage GPU timings. */
+f3b_ctx *f3b_render_context(void) {
+   pthread_mutex_lock(&g_lock);
+   f3b_ctx *c = get_ctx();
+   pthread_mutex_unlock(&g_lock);
+   return c;
+}
+
+double flam3_render_memory_required(flam3_frame *spec) {
+   /* flam3.c:3874-3887: the reference's planning model (bytes), kept verbatim in meaning so
+    * that flam3-render's nstrips / use_mem logic (flam3-render.c:36-101) behaves the same */
+   flam3_genome *cps = spec->genomes;
+   int real_bits = spec->bits;
+   if (33 == real_bits) real_bits = 32;
+   return (double)cps[0].spatial_oversample * cps[0].spatial_oversample * (double)cps[0].width *
+          cps[0].height * (real_bits / 8) * 9.0;
+}
+
+static int poll_progress(flam3_frame *spec, double percent, int stage) {
+   /* 0 continue, 1 abort, 2 pause (rect.c:324-373) */
+   if (!spec->progress) return 0;
+   int rv = (*spec->progress)(spec->progress_parameter, percent, stage, 0.0);
+   while (rv == 2) {
+      struct timespec ts = {0, 100000000};
+      nanosleep(&ts, NULL);
+      rv = (*spec->progress)(spec->progress_parameter, percent, stage, 0.0);
+   }
+   return rv == 1;
+}
+
+typedef struct {
+   uint32_t *words;
+   size_t cap, used; /* in words */
+} blob_buf;
+
+static int blob_reserve(blob_buf *b, size_t extra) {
+   if (b->used + extra <= b->cap) return 0;
+   size_t ncap = b->cap ? b->cap * 2 : 1u << 16;
+   while (ncap < b->used + extra) ncap *= 2;
+   uint32_t *n = (uint32_t *)realloc(b->words, ncap * 4);
+   if (!n) return 1;
+   b->words = n;
+   b->cap = ncap;
+   return 0;
+}
+
+static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, int nchan,
+                         int transp, stat_struct *stats, int force_count_plane) {
+   const time_t tstart = time(NULL);
+   int rv = 1;
+   int verbose = spec->verbose;
+   const int nthreads = spec->nthreads > 0 ? spec->nthreads : 1;
+   const int bytes_per_channel = spec->bytes_per_channel;
+   const char *ai = getenv("apo_palette");
+   const int cmap_size = 256 - (ai ? atoi(ai) : 0);
+
+   double *filter = NULL, *temporal_filter = NULL, *temporal_deltas = NULL;
+   blob_buf blobs = {NULL, 0, 0};
+   f3b_job *jobs = NULL;
+   f3b_de_filters de;
+   int de_alive = 0;
+   double last_dmap[256][3];
+   flam3_genome cp;
+   memset(&cp, 0, sizeof(cp));
+   memset(last_dmap, 0, sizeof(last_dmap));
+
+   stats->num_iters = 0;
+   stats->badvals = 0;
+
+   flam3_interpolate(spec->genomes, spec->ngenomes, spec->time, 0, &cp);
+   const int oversample = cp.spatial_oversample;
+   const double highpow = cp.highlight_power;
+   const int nbatches = cp.nbatches;
+   const int ntemporal_samples = cp.ntemporal_samples;
+
+   if (nbatches < 1) {
+      fprintf(stderr, "nbatches must be positive, not %d.\n", nbatches);
+      goto done;
+   }
+   if (oversample < 1) {
+      fprintf(stderr, "oversample must be positive, not %d.\n", oversample);
+      goto done;
+   }
+   if (ntemporal_samples < 1) {
+      fprintf(stderr, "temporal_samples must be positive, not %d.\n", ntemporal_samples);
+      goto done;
+   }
+
+   /* output geometry, adjusted for scanline fields (rect.c:611-624) */
+   f3b_frame_geom g;
+   memset(&g, 0, sizeof(g));
+   g.field = field;
+   g.pixel_aspect_ratio = spec->pixel_aspect_ratio;
+   g.oversample = oversample;
+   g.image_width = cp.width;
+   g.out_width = g.image_width;
+   if (field) {
+      g.image_height = cp.height / 2;
+      if (field == flam3_field_odd)
+         out = (unsigned char *)out + (size_t)nchan * bytes_per_channel * g.out_width;
+      g.out_width *= 2;
+   } else
+      g.image_height = cp.height;
+
+   /* spatial filter from genomes[0], NOT the interpolated cp (filters.c:219-222) */
+   g.filter_width = f3b_spatial_filter_create(
+       spec->genomes[0].spatial_filter_select, spec->genomes[0].spatial_oversample,
+       spec->genomes[0].spatial_filter_radius, spec->pixel_aspect_ratio, field, &filter);
+   if (g.filter_width < 0) {
+      fprintf(stderr, "Spatial filter value is too small: %g.  Terminating.\n",
+              spec->genomes[0].spatial_filter_radius);
+      fprintf(stderr, "flam3_create_spatial_filter returned error: aborting\n");
+      goto done;
+   }
+
+   const double sumfilt = f3b_temporal_filter_create(
+       nbatches * ntemporal_samples, cp.temporal_filter_type, cp.temporal_filter_exp,
+       cp.temporal_filter_width, &temporal_filter, &temporal_deltas);
+
+   /* gutter: room for the spatial filter and for the widest DE kernel (rect.c:656-681) */
+   g.gutter_width = (g.filter_width - oversample) / 2;
+   int max_de = 0;
+   for (int i = 0; i < spec->ngenomes; i++) {
+      const int w = (int)ceil(spec->genomes[i].estimator) * oversample;
+      if (w > max_de) max_de = w;
+   }
+   if (max_de > 0) max_de += oversample - 1;
+   if (max_de > g.gutter_width) {
+      g.de_offset = max_de - g.gutter_width;
+      g.gutter_width = max_de;
+   } else
+      g.de_offset = 0;
+   g.height = oversample * g.image_height + 2 * g.gutter_width;
+   g.width = oversample * g.image_width + 2 * g.gutter_width;
+
+   /* Can the alpha plane double as the hit-count plane? (f3b_pack.c, dmap section) */
+   int count_plane = force_count_plane;
+   for (int i = 0; i < nbatches * ntemporal_samples && !count_plane; i++)
+      if (temporal_filter[i] != 1.0) count_plane = 1;
+   for (int i = 0; i < spec->ngenomes && !count_plane; i++) {
+      if (spec->genomes[i].palette_mode == flam3_palette_mode_linear) count_plane = 1;
+      for (int j = 0; j < 256 && !count_plane; j++)
+         if (spec->genomes[i].palette[j].color[3] != 1.0) count_plane = 1;
+   }
+
+   if (f3b_frame_begin(ctx, g.width, g.height, count_plane)) {
+      fprintf(stderr, "render_rectangle (B200): cannot allocate %dx%d buckets: %s\n", g.width,
+              g.height, f3b_last_error(ctx));
+      goto done;
+   }
+
+   if (verbose) fprintf(stderr, "chaos: ");
+   const time_t progress_began = time(NULL);
+
+   double vibrancy = 0.0, gamma = 0.0, background[3] = {0.0, 0.0, 0.0};
+   int vib_gam_n = 0;
+   f3b_camera cam;
+   memset(&cam, 0, sizeof(cam));
+   jobs = (f3b_job *)calloc((size_t)ntemporal_samples, sizeof(f3b_job));
+   if (!jobs) goto done;
+
+   for (int batch_num = 0; batch_num < nbatches; batch_num++) {
+      const double de_time = spec->time + temporal_deltas[batch_num * ntemporal_samples];
+
+      if (batch_num > 0 && f3b_hist_clear(ctx)) goto gpu_error;
+
+      /* DE parameters come from the genome at the batch's first time (rect.c:726-751) */
+      flam3_interpolate(spec->genomes, spec->ngenomes, de_time, 0, &cp);
+      if (cp.estimator < 0.0 || cp.estimator_minimum < 0.0) {
+         fprintf(stderr, "density estimator filter widths must be >= 0\n");
+         goto done;
+      }
+      if (spec->bits <= 32 && cp.estimator > 0.0) {
+         fprintf(stderr, "warning: density estimation disabled with %d bit buffers.\n", spec->bits);
+         cp.estimator = 0.0;
+      }
+      memset(&de, 0, sizeof(de));
+      de_alive = 0;
+      if (cp.estimator > 0.0) {
+         if (f3b_de_filters_create(cp.estimator, cp.estimator_minimum, cp.estimator_curve,
+                                   oversample, &de)) {
+            fprintf(stderr, "de.kernel_size returned 0 - aborting.\n");
+            goto done;
+         }
+         de_alive = 1;
+      }
+
+      /* ---- pack every temporal sample of this batch (rect.c:754-884) ---- */
+      blobs.used = 0;
+      uint64_t seed = 0x243f6a8885a308d3ull;
+      for (int ts = 0; ts < ntemporal_samples; ts++) {
+         const int fi = batch_num * ntemporal_samples + ts;
+         const double color_scalar = temporal_filter[fi];
+         flam3_interpolate(spec->genomes, spec->ngenomes, spec->time + temporal_deltas[fi], 0, &cp);
+
+         if (f3b_camera_setup(&cp, &g, &cam)) goto done;
+
+         if (blob_reserve(&blobs, F3B_MAX_BLOB_WORDS + 4)) goto done;
+         size_t used = 0;
+         int alpha_ok = 0;
+         const int prv = f3b_pack_sample(&cp, &cam, color_scalar, cmap_size,
+                                         blobs.words + blobs.used, F3B_MAX_BLOB_WORDS, &used,
+                                         &alpha_ok);
+         if (prv == 2) {
+            fprintf(stderr, "flam3_render (B200): genome too large for the packed format "
+                            "(%d xforms).\n", cp.num_xforms);
+            goto done;
+         }
+         if (prv) {
+            fprintf(stderr, "create xform distrib returned error: aborting.\n");
+            goto done;
+         }
+         if (!alpha_ok && !count_plane) {
+            rv = -2; /* caller retries with a count plane */
+            goto done;
+         }
+
+         /* sample budget (rect.c:830-835) */
+         const double nsamples = cam.sample_density * g.image_width * g.image_height;
+         const double batch_size = nsamples / (nbatches * ntemporal_samples);
+         stats->num_iters += batch_size;
+
+         /* The reference seeds one ISAAC context per worker thread from the frame's
+          * context, 16 words each (rect.c:858-865). Draw the same words, so spec->rc
+          * ends in the same state, and fold them into the seed of this sample's streams. */
+         uint64_t h = 0x9e3779b97f4a7c15ull ^ (uint64_t)fi;
+         for (int k = 0; k < 16 * nthreads; k++) {
+            h ^= (uint64_t)f3b_isaac_next(&spec->rc) & 0xffffffffull;
+            h *= 0x100000001b3ull;
+            h ^= h >> 29;
+         }
+         if (ts == 0) seed ^= h;
+
+         f3b_job *jb = &jobs[ts];
+         jb->blob_offset = (uint64_t)blobs.used * 4;
+         jb->n_iters = batch_size > 0 ? (uint64_t)batch_size : 0;
+         jb->n_chains = 0;
+         jb->fuse = spec->earlyclip ? 100 : 15; /* FUSE_28 : FUSE_27, rect.c:39-40,266 */
+         jb->first_group = 0;
+         jb->sample_id = (uint32_t)(h ^ (h >> 32));
+         blobs.used += (used + 3) & ~(size_t)3;
+
+         vibrancy += cp.vibrancy;
+         gamma += cp.gamma;
+         background[0] += cp.background[0];
+         background[1] += cp.background[1];
+         background[2] += cp.background[2];
+         vib_gam_n++;
+         if (ts == ntemporal_samples - 1 && batch_num == nbatches - 1)
+            for (int j = 0; j < 256; j++)
+               for (int k = 0; k < 3; k++)
+                  last_dmap[j][k] = cp.palette[j].color[k] * 255.0 * color_scalar;
+      }
+
+      if (poll_progress(spec, 100.0 * batch_num / nbatches, 0)) {
+         if (verbose) fprintf(stderr, "\naborted!\n");
+         rv = 0;
+         goto done;
+      }
+
+      /* ---- chaos game: one launch for the whole batch ---- */
+      const uint32_t max_chain = spec->sub_batch_size > 0 ? (uint32_t)spec->sub_batch_size : 10000u;
+      if (f3b_iterate(ctx, blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
+                      spec->bits != 64, max_chain, 0, 1))
+         goto gpu_error;
+
+      /* ---- log scale + density estimation (rect.c:933-1058); cp/cam are those of the
+       * batch's LAST temporal sample, as in the reference ---- */
+      f3b_density_desc dd;
+      memset(&dd, 0, sizeof(dd));
+      dd.k1 = (cp.contrast * cp.brightness * 255.0 * 268.0 * (1.0 / nbatches)) / 256;
+      const double area = g.image_width * g.image_height / (cam.ppux * cam.ppuy);
+      dd.k2 = (oversample * oversample * nbatches) /
+              (cp.contrast * area * 255.0 * cam.sample_density * sumfilt);
+      dd.oversample = oversample;
+      dd.int_accum = (spec->bits == 32);
+      if (de_alive && de.max_filter_index > 0) {
+         dd.n_kernels = de.n_kernels;
+         dd.kernel_size = de.kernel_size;
+         dd.max_filtered_counts = de.max_filtered_counts;
+         dd.max_filter_index = de.max_filter_index;
+         dd.curve = cp.estimator_curve;
+         dd.coefs = de.coefs;
+         dd.widths = de.widths;
+      }
+      if (poll_progress(spec, 0.0, 1)) {
+         if (verbose) fprintf(stderr, "\naborted!\n");
+         rv = 0;
+         goto done;
+      }
+      if (f3b_density(ctx, &dd)) goto gpu_error;
+      if (de_alive) {
+         f3b_de_filters_free(&de);
+         de_alive = 0;
+      }
+   }
+
+   if (verbose) {
+      fprintf(stderr, "\rchaos: 100.0%%  took: %ld seconds   \n", (long)(time(NULL) - progress_began));
+      fprintf(stderr, "filtering...");
+   }
+
+   /* ---- spatial filter + tone map (rect.c:1067-1247) ---- */
+   {
+      f3b_final_desc fd;
+      memset(&fd, 0, sizeof(fd));
+      fd.image_width = g.image_width;
+      fd.image_height = g.image_height;
+      fd.oversample = oversample;
+      fd.de_offset = g.de_offset;
+      fd.filter_width = g.filter_width;
+      fd.filter = filter;
+      fd.earlyclip = spec->earlyclip;
+      fd.nchan = nchan;
+      fd.transp = transp;
+      fd.bytes_per_channel = bytes_per_channel;
+      fd.gamma = gamma / vib_gam_n;
+      fd.vibrancy = vibrancy / vib_gam_n;
+      for (int k = 0; k < 3; k++) fd.background[k] = background[k] / (vib_gam_n / 256.0);
+      fd.highlight_power = highpow;
+      fd.gam_lin_thresh = cp.gam_lin_thresh;
+      const size_t stride = (size_t)g.out_width * nchan * bytes_per_channel;
+      if (f3b_finish(ctx, &fd, out, stride)) goto gpu_error;
+   }
+
+   {
+      double bv = 0.0;
+      if (f3b_badvals(ctx, &bv)) goto gpu_error;
+      stats->badvals = bv;
+   }
+
+   if (getenv("insert_palette")) { /* debug aid of the reference, rect.c:1267-1279 */
+      int ph = 100;
+      if (ph >= g.image_height) ph = g.image_height;
+      for (int j = 0; j < ph; j++)
+         for (int i = 0; i < g.image_width; i++) {
+            unsigned char *p = (unsigned char *)out + (size_t)nchan * (i + (size_t)j * g.out_width);
+            for (int k = 0; k < 3; k++) p[k] = (unsigned char)last_dmap[i * 256 / g.image_width][k];
+         }
+   }
+   rv = 0;
+   goto done;
+
+gpu_error:
+   fprintf(stderr, "flam3_render (B200): %s\n", f3b_last_error(ctx));
+   rv = 1;
+
+done:
+   if (de_alive) f3b_de_filters_free(&de);
+   free(temporal_filter);
+   free(temporal_deltas);
+   free(filter);
+   free(blobs.words);
+   free(jobs);
+   clear_cp(&cp, 0);
+   stats->render_seconds = (int)(time(NULL) - tstart);
+   return rv;
+}
+
+int flam3_render(flam3_frame *spec, void *out, int field, int nchan, int transp,
+                 stat_struct *stats) {
+   if (spec->bits != 32 && spec->bits != 33 && spec->bits != 64) {
+      fprintf(stderr, "flam3: bits must be 32, 33, or 64 not %d.\n", spec->bits);
+      return 1;
+   }
+   pthread_mutex_lock(&g_lock);
+   f3b_ctx *ctx = get_ctx();
+   int rv = 1;
+   if (ctx) {
+      const randctx rc0 = spec->rc;
+      rv = render_locked(ctx, spec, out, field, nchan, transp, stats, 0);
+      if (rv == -2) { /* a palette with alpha appeared mid-frame: redo with a count plane */
+         spec->rc = rc0;
+         rv = render_locked(ctx, spec, out, field, nchan, transp, stats, 1);
+      }
+      if (rv < 0) rv = 1;
+   }
+   pthread_mutex_unlock(&g_lock);
+   return rv;
+}

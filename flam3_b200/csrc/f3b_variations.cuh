@@ -1,0 +1,843 @@
+/*
+ * f3b_variations.cuh — the 99 flam3 variations and apply_xform as fp32 device code.
+ *
+ * Behavioural specification: variations.c:142-1937 (the var functions),
+ * variations.c:2129-2399 (apply_xform), flam3.c:2519-2544 (the 28-bit uniform draws).
+ * This is a re-expression for one-walker-per-thread SIMT execution: xform records live in
+ * shared memory as flat word arrays (f3b_pack.h), host-side precalcs are already folded
+ * into the packed parameters, and all math is single precision. The per-variation
+ * parameter order is the one documented in f3b_pack.c:pack_var_params.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "f3b_pack.h"
+
+#define F3B_EPS 1e-10f           /* EPS, private.h:47 */
+#define F3B_PI 3.14159265358979323846f
+#define F3B_1_PI 0.31830988618379067154f
+#define F3B_2_PI 0.63661977236758134308f
+#define F3B_PI_2 1.57079632679489661923f
+#define F3B_PI_4 0.78539816339744830962f
+
+/* ------------------------------------------------------------------------------------
+ * Per-walker random stream: xoshiro128++ (4 x 32-bit state, all-bits-good output, so
+ * the `& 16383` xform pick (flam3.c:253) and the `& 1` coin flip (flam3.c:2541) are safe).
+ * It stands in for the per-thread ISAAC context of rect.c:858-865; streams are derived
+ * from the frame's ISAAC state by the host (f3b_render.c) and split per chain by hashing
+ * (seed, temporal sample, chain) -> state, i.e. counter-based stream derivation.
+ * ------------------------------------------------------------------------------------ */
+struct F3Rng {
+   uint32_t s0, s1, s2, s3;
+
+   __device__ __forceinline__ uint32_t next() {
+      uint32_t r = __funnelshift_l(s0 + s3, s0 + s3, 7) + s0;
+      uint32_t t = s1 << 9;
+      s2 ^= s0;
+      s3 ^= s1;
+      s1 ^= s2;
+      s0 ^= s3;
+      s2 ^= t;
+      s3 = __funnelshift_l(s3, s3, 11);
+      return r;
+   }
+   /* flam3_random_isaac_01: (irand & 0xfffffff) / 0xfffffff in [0,1] */
+   __device__ __forceinline__ float u01() {
+      return (float)(next() & 0xfffffffu) * (1.0f / 268435455.0f);
+   }
+   /* flam3_random_isaac_11: ((irand & 0xfffffff) - 0x7ffffff) / 0x7ffffff in [-1,1] */
+   __device__ __forceinline__ float u11() {
+      return (float)((int)(next() & 0xfffffffu) - 0x7ffffff) * (1.0f / 134217727.0f);
+   }
+   __device__ __forceinline__ uint32_t bit() { return next() & 1u; }
+};
+
+__host__ __device__ __forceinline__ uint64_t f3b_mix64(uint64_t z) {
+   /* splitmix64 finaliser */
+   z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+   z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+   return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ void f3b_rng_seed(F3Rng &r, uint64_t seed, uint32_t sample_id,
+                                             uint32_t chain) {
+   uint64_t a = f3b_mix64(seed + 0x9e3779b97f4a7c15ULL * ((uint64_t)sample_id + 1));
+   uint64_t b = f3b_mix64(a ^ (0xd1b54a32d192ed03ULL * ((uint64_t)chain + 1)));
+   uint64_t c = f3b_mix64(b + 0x9e3779b97f4a7c15ULL);
+   r.s0 = (uint32_t)b;
+   r.s1 = (uint32_t)(b >> 32);
+   r.s2 = (uint32_t)c;
+   r.s3 = (uint32_t)(c >> 32) | 1u; /* never the all-zero state */
+}
+
+/* badvalue(), variations.c:22 */
+__device__ __forceinline__ bool f3b_bad(float v) { return !(fabsf(v) <= 1e10f); }
+
+/* pseudo-gaussian used by gaussian_blur / radial_blur / pre_blur: sum of 4 uniforms - 2 */
+__device__ __forceinline__ float f3b_gauss4(F3Rng &rng) {
+   float a = rng.u01();
+   float b = rng.u01();
+   float c = rng.u01();
+   float d = rng.u01();
+   return a + b + c + d - 2.0f;
+}
+
+/*
+ * Applies xform record `xf` (shared memory) to (px,py,pc). Returns true when the result is
+ * a "bad value", in which case (qx,qy) are fresh uniform draws (variations.c:2391-2395).
+ */
+__device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, float px, float py,
+                                                float pc, float &qx, float &qy, float &qc,
+                                                float &qvis, F3Rng &rng) {
+   const uint32_t *xu = reinterpret_cast<const uint32_t *>(xf);
+   qc = xf[F3B_X_SCOLOR] + xf[F3B_X_ONEMS] * pc;
+   qvis = xf[F3B_X_VIS];
+
+   float tx = xf[F3B_X_C00] * px + xf[F3B_X_C10] * py + xf[F3B_X_C20];
+   float ty = xf[F3B_X_C01] * px + xf[F3B_X_C11] * py + xf[F3B_X_C21];
+   const uint32_t flags = xu[F3B_X_FLAGS];
+
+   if (flags & F3B_XF_PREBLUR) { /* var67_pre_blur, variations.c:1480 */
+      float g = xf[F3B_X_PREBLUR] * f3b_gauss4(rng);
+      float sa, ca;
+      sincosf(rng.u01() * 2.0f * F3B_PI, &sa, &ca);
+      tx += g * ca;
+      ty += g * sa;
+   }
+
+   const float sumsq = tx * tx + ty * ty;
+   const float rad = sqrtf(sumsq);
+   float atan_xy = 0.0f, atan_yx = 0.0f, sina = 0.0f, cosa = 0.0f;
+   if (flags & F3B_XF_ATAN_XY) atan_xy = atan2f(tx, ty);
+   if (flags & F3B_XF_ANGLES) {
+      sina = tx / rad;
+      cosa = ty / rad;
+   }
+   if (flags & F3B_XF_ATAN_YX) atan_yx = atan2f(ty, tx);
+
+   float p0 = 0.0f, p1 = 0.0f;
+   const int nvars = (int)xu[F3B_X_NVARS];
+   const float *v = xf + F3B_X_VARS;
+
+   for (int k = 0; k < nvars; k++) {
+      const uint32_t w0 = __float_as_uint(v[0]); /* id | nparams << 8 */
+      const uint32_t id = w0 & 0xffu;
+      const float w = v[1];
+      const float *p = v + 2;
+      switch (id) {
+      case 0: /* linear */
+         p0 += w * tx;
+         p1 += w * ty;
+         break;
+      case 1: /* sinusoidal */
+         p0 += w * sinf(tx);
+         p1 += w * sinf(ty);
+         break;
+      case 2: { /* spherical */
+         float r2 = w / (sumsq + F3B_EPS);
+         p0 += r2 * tx;
+         p1 += r2 * ty;
+      } break;
+      case 3: { /* swirl */
+         float s, c;
+         sincosf(sumsq, &s, &c);
+         p0 += w * (s * tx - c * ty);
+         p1 += w * (c * tx + s * ty);
+      } break;
+      case 4: { /* horseshoe */
+         float r = w / (rad + F3B_EPS);
+         p0 += (tx - ty) * (tx + ty) * r;
+         p1 += 2.0f * tx * ty * r;
+      } break;
+      case 5: /* polar */
+         p0 += w * (atan_xy * F3B_1_PI);
+         p1 += w * (rad - 1.0f);
+         break;
+      case 6: /* handkerchief */
+         p0 += w * rad * sinf(atan_xy + rad);
+         p1 += w * rad * cosf(atan_xy - rad);
+         break;
+      case 7: { /* heart */
+         float s, c;
+         sincosf(rad * atan_xy, &s, &c);
+         float r = w * rad;
+         p0 += r * s;
+         p1 -= r * c;
+      } break;
+      case 8: { /* disc */
+         float a = atan_xy * F3B_1_PI, s, c;
+         sincosf(F3B_PI * rad, &s, &c);
+         p0 += w * s * a;
+         p1 += w * c * a;
+      } break;
+      case 9: { /* spiral */
+         float r = rad + F3B_EPS, s, c;
+         float r1 = w / r;
+         sincosf(r, &s, &c);
+         p0 += r1 * (cosa + s);
+         p1 += r1 * (sina - c);
+      } break;
+      case 10: { /* hyperbolic */
+         float r = rad + F3B_EPS;
+         p0 += w * sina / r;
+         p1 += w * cosa * r;
+      } break;
+      case 11: { /* diamond */
+         float s, c;
+         sincosf(rad, &s, &c);
+         p0 += w * sina * c;
+         p1 += w * cosa * s;
+      } break;
+      case 12: { /* ex */
+         float n0 = sinf(atan_xy + rad);
+         float n1 = cosf(atan_xy - rad);
+         float m0 = n0 * n0 * n0 * rad;
+         float m1 = n1 * n1 * n1 * rad;
+         p0 += w * (m0 + m1);
+         p1 += w * (m0 - m1);
+      } break;
+      case 13: { /* julia */
+         float a = 0.5f * atan_xy, s, c;
+         if (rng.bit()) a += F3B_PI;
+         float r = w * sqrtf(rad);
+         sincosf(a, &s, &c);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 14: { /* bent */
+         float nx = tx < 0.0f ? tx * 2.0f : tx;
+         float ny = ty < 0.0f ? ty * 0.5f : ty;
+         p0 += w * nx;
+         p1 += w * ny;
+      } break;
+      case 15: { /* waves: p = {c10, dx2, c11, dy2} */
+         p0 += w * (tx + p[0] * sinf(ty * p[1]));
+         p1 += w * (ty + p[2] * sinf(tx * p[3]));
+      } break;
+      case 16: { /* fisheye (x/y swap is intentional in the reference) */
+         float r = 2.0f * w / (rad + 1.0f);
+         p0 += r * ty;
+         p1 += r * tx;
+      } break;
+      case 17: { /* popcorn: p = {c20, c21} */
+         float dx = tanf(3.0f * ty);
+         float dy = tanf(3.0f * tx);
+         p0 += w * (tx + p[0] * sinf(dx));
+         p1 += w * (ty + p[1] * sinf(dy));
+      } break;
+      case 18: { /* exponential */
+         float dx = w * expf(tx - 1.0f), s, c;
+         sincosf(F3B_PI * ty, &s, &c);
+         p0 += dx * c;
+         p1 += dx * s;
+      } break;
+      case 19: { /* power */
+         float r = w * powf(rad, sina);
+         p0 += r * cosa;
+         p1 += r * sina;
+      } break;
+      case 20: { /* cosine */
+         float s, c;
+         sincosf(tx * F3B_PI, &s, &c);
+         p0 += w * (c * coshf(ty));
+         p1 -= w * (s * sinhf(ty));
+      } break;
+      case 21: { /* rings: p = {dx} */
+         float dx = p[0];
+         float r = w * (fmodf(rad + dx, 2.0f * dx) - dx + rad * (1.0f - dx));
+         p0 += r * cosa;
+         p1 += r * sina;
+      } break;
+      case 22: { /* fan: p = {dx, dy, dx2} */
+         float a = atan_xy, s, c;
+         a += (fmodf(a + p[1], p[0]) > p[2]) ? -p[2] : p[2];
+         sincosf(a, &s, &c);
+         float r = w * rad;
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 23: { /* blob: p = {low, high-low, waves} */
+         float r = rad * (p[0] + p[1] * (0.5f + 0.5f * sinf(p[2] * atan_xy)));
+         p0 += w * sina * r;
+         p1 += w * cosa * r;
+      } break;
+      case 24: { /* pdj: p = {a,b,c,d} */
+         float nx1 = cosf(p[1] * tx);
+         float nx2 = sinf(p[2] * tx);
+         float ny1 = sinf(p[0] * ty);
+         float ny2 = cosf(p[3] * ty);
+         p0 += w * (ny1 - nx1);
+         p1 += w * (nx2 - ny2);
+      } break;
+      case 25: { /* fan2: p = {dx, dy, dx2} */
+         float a = atan_xy, s, c;
+         float t = a + p[1] - p[0] * truncf((a + p[1]) / p[0]);
+         a = (t > p[2]) ? a - p[2] : a + p[2];
+         sincosf(a, &s, &c);
+         float r = w * rad;
+         p0 += r * s;
+         p1 += r * c;
+      } break;
+      case 26: { /* rings2: p = {dx} */
+         float dx = p[0];
+         float r = rad;
+         r += -2.0f * dx * truncf((r + dx) / (2.0f * dx)) + r * (1.0f - dx);
+         p0 += w * sina * r;
+         p1 += w * cosa * r;
+      } break;
+      case 27: { /* eyefish */
+         float r = (w * 2.0f) / (rad + 1.0f);
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 28: { /* bubble */
+         float r = w / (0.25f * sumsq + 1.0f);
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 29: /* cylinder */
+         p0 += w * sinf(tx);
+         p1 += w * ty;
+         break;
+      case 30: { /* perspective: p = {dist, vsin, vfcos} */
+         float t = 1.0f / (p[0] - ty * p[1]);
+         p0 += w * p[0] * tx * t;
+         p1 += w * p[2] * ty * t;
+      } break;
+      case 31: { /* noise */
+         float s, c;
+         sincosf(rng.u01() * 2.0f * F3B_PI, &s, &c);
+         float r = w * rng.u01();
+         p0 += tx * r * c;
+         p1 += ty * r * s;
+      } break;
+      case 32: { /* julian: p = {power, cn, rN} */
+         float t_rnd = truncf(p[2] * rng.u01());
+         float a = (atan_yx + 2.0f * F3B_PI * t_rnd) / p[0], s, c;
+         float r = w * powf(sumsq, p[1]);
+         sincosf(a, &s, &c);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 33: { /* juliascope: p = {power, cn, rN} */
+         int t_rnd = (int)truncf(p[2] * rng.u01());
+         float a, s, c;
+         if ((t_rnd & 1) == 0) a = (2.0f * F3B_PI * (float)t_rnd + atan_yx) / p[0];
+         else a = (2.0f * F3B_PI * (float)t_rnd - atan_yx) / p[0];
+         sincosf(a, &s, &c);
+         float r = w * powf(sumsq, p[1]);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 34: { /* blur */
+         float s, c;
+         sincosf(rng.u01() * 2.0f * F3B_PI, &s, &c);
+         float r = w * rng.u01();
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 35: { /* gaussian_blur */
+         float s, c;
+         sincosf(rng.u01() * 2.0f * F3B_PI, &s, &c);
+         float r = w * f3b_gauss4(rng);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 36: { /* radial_blur: p = {spinvar, zoomvar} */
+         float g = w * f3b_gauss4(rng), s, c;
+         sincosf(atan_yx + p[0] * g, &s, &c);
+         float rz = p[1] * g - 1.0f;
+         p0 += rad * c + rz * tx;
+         p1 += rad * s + rz * ty;
+      } break;
+      case 37: { /* pie: p = {slices, rotation, thickness} */
+         int sl = (int)(rng.u01() * p[0] + 0.5f);
+         float a = p[1] + 2.0f * F3B_PI * ((float)sl + rng.u01() * p[2]) / p[0], s, c;
+         float r = w * rng.u01();
+         sincosf(a, &s, &c);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 38: { /* ngon: p = {power/2, b=2pi/sides, corners, circle} */
+         float r_factor = powf(sumsq, p[0]);
+         float b = p[1];
+         float phi = atan_yx - b * floorf(atan_yx / b);
+         if (phi > 0.5f * b) phi -= b;
+         float amp = p[2] * (1.0f / (cosf(phi) + F3B_EPS) - 1.0f) + p[3];
+         amp /= (r_factor + F3B_EPS);
+         p0 += w * tx * amp;
+         p1 += w * ty * amp;
+      } break;
+      case 39: { /* curl: p = {c1, c2} */
+         float re = 1.0f + p[0] * tx + p[1] * (tx * tx - ty * ty);
+         float im = p[0] * ty + 2.0f * p[1] * tx * ty;
+         float r = w / (re * re + im * im);
+         p0 += (tx * re + ty * im) * r;
+         p1 += (ty * re - tx * im) * r;
+      } break;
+      case 40: { /* rectangles: p = {x, y} */
+         if (p[0] == 0.0f) p0 += w * tx;
+         else p0 += w * ((2.0f * floorf(tx / p[0]) + 1.0f) * p[0] - tx);
+         if (p[1] == 0.0f) p1 += w * ty;
+         else p1 += w * ((2.0f * floorf(ty / p[1]) + 1.0f) * p[1] - ty);
+      } break;
+      case 41: { /* arch (weight used non-linearly, as in the reference) */
+         float s, c;
+         sincosf(rng.u01() * w * F3B_PI, &s, &c);
+         p0 += w * s;
+         p1 += w * (s * s) / c;
+      } break;
+      case 42: /* tangent */
+         p0 += w * sinf(tx) / cosf(ty);
+         p1 += w * tanf(ty);
+         break;
+      case 43: { /* square */
+         float a = rng.u01();
+         float b = rng.u01();
+         p0 += w * (a - 0.5f);
+         p1 += w * (b - 0.5f);
+      } break;
+      case 44: { /* rays */
+         float ang = w * rng.u01() * F3B_PI;
+         float r = w / (sumsq + F3B_EPS);
+         float tanr = w * tanf(ang) * r;
+         p0 += tanr * cosf(tx);
+         p1 += tanr * sinf(ty);
+      } break;
+      case 45: { /* blade */
+         float r = rng.u01() * w * rad, s, c;
+         sincosf(r, &s, &c);
+         p0 += w * tx * (c + s);
+         p1 += w * tx * (c - s);
+      } break;
+      case 46: { /* secant2 */
+         float cr = cosf(w * rad);
+         float icr = 1.0f / cr;
+         p0 += w * tx;
+         p1 += (cr < 0.0f) ? w * (icr + 1.0f) : w * (icr - 1.0f);
+      } break;
+      case 47: { /* twintrian */
+         float r = rng.u01() * w * rad, s, c;
+         sincosf(r, &s, &c);
+         float diff = log10f(s * s) + c;
+         if (f3b_bad(diff)) diff = -30.0f;
+         p0 += w * tx * diff;
+         p1 += w * tx * (diff - s * F3B_PI);
+      } break;
+      case 48: { /* cross */
+         float s = tx * tx - ty * ty;
+         float r = w * sqrtf(1.0f / (s * s + F3B_EPS));
+         p0 += tx * r;
+         p1 += ty * r;
+      } break;
+      case 49: { /* disc2: p = {timespi, sinadd, cosadd} */
+         float s, c;
+         sincosf(p[0] * (tx + ty), &s, &c);
+         float r = w * atan_xy * F3B_1_PI;
+         p0 += (s + p[2]) * r;
+         p1 += (c + p[1]) * r;
+      } break;
+      case 50: { /* super_shape: p = {pm_4, n2, n3, rnd, holes, pneg1_n1} */
+         float st, ct;
+         sincosf(p[0] * atan_yx + F3B_PI_4, &st, &ct);
+         float t1 = powf(fabsf(ct), p[1]);
+         float t2 = powf(fabsf(st), p[2]);
+         float r = w * ((p[3] * rng.u01() + (1.0f - p[3]) * rad) - p[4]) * powf(t1 + t2, p[5]) /
+                   rad;
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 51: { /* flower: p = {petals, holes} */
+         float r = w * (rng.u01() - p[1]) * cosf(p[0] * atan_yx) / rad;
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 52: { /* conic: p = {eccentricity, holes} */
+         float ct = tx / rad;
+         float r = w * (rng.u01() - p[1]) * p[0] / (1.0f + p[0] * ct) / rad;
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 53: { /* parabola: p = {height, width} */
+         float s, c;
+         sincosf(rad, &s, &c);
+         float a = rng.u01();
+         float b = rng.u01();
+         p0 += p[0] * w * s * s * a;
+         p1 += p[1] * w * c * b;
+      } break;
+      case 54: { /* bent2: p = {x, y} */
+         float nx = tx < 0.0f ? tx * p[0] : tx;
+         float ny = ty < 0.0f ? ty * p[1] : ty;
+         p0 += w * nx;
+         p1 += w * ny;
+      } break;
+      case 55: { /* bipolar: p = {ps = -pi/2 * shift} */
+         float t = sumsq + 1.0f;
+         float x2 = 2.0f * tx;
+         float y = 0.5f * atan2f(2.0f * ty, sumsq - 1.0f) + p[0];
+         if (y > F3B_PI_2) y = -F3B_PI_2 + fmodf(y + F3B_PI_2, F3B_PI);
+         else if (y < -F3B_PI_2) y = F3B_PI_2 - fmodf(F3B_PI_2 - y, F3B_PI);
+         p0 += w * 0.25f * F3B_2_PI * logf((t + x2) / (t - x2));
+         p1 += w * F3B_2_PI * y;
+      } break;
+      case 56: { /* boarders */
+         float rx = rintf(tx), ry = rintf(ty);
+         float ox = tx - rx, oy = ty - ry;
+         if (rng.u01() >= 0.75f) {
+            p0 += w * (ox * 0.5f + rx);
+            p1 += w * (oy * 0.5f + ry);
+         } else if (fabsf(ox) >= fabsf(oy)) {
+            if (ox >= 0.0f) {
+               p0 += w * (ox * 0.5f + rx + 0.25f);
+               p1 += w * (oy * 0.5f + ry + 0.25f * oy / ox);
+            } else {
+               p0 += w * (ox * 0.5f + rx - 0.25f);
+               p1 += w * (oy * 0.5f + ry - 0.25f * oy / ox);
+            }
+         } else {
+            if (oy >= 0.0f) {
+               p1 += w * (oy * 0.5f + ry + 0.25f);
+               p0 += w * (ox * 0.5f + rx + ox / oy * 0.25f);
+            } else {
+               p1 += w * (oy * 0.5f + ry - 0.25f);
+               p0 += w * (ox * 0.5f + rx - ox / oy * 0.25f);
+            }
+         }
+      } break;
+      case 57: { /* butterfly; 4/sqrt(3*pi) */
+         float wx = w * 1.3029400317411197908970256609023f;
+         float y2 = ty * 2.0f;
+         float r = wx * sqrtf(fabsf(ty * tx) / (F3B_EPS + tx * tx + y2 * y2));
+         p0 += r * tx;
+         p1 += r * y2;
+      } break;
+      case 58: { /* cell: p = {size, 1/size} */
+         int x = (int)floorf(tx * p[1]);
+         int y = (int)floorf(ty * p[1]);
+         float dx = tx - (float)x * p[0];
+         float dy = ty - (float)y * p[0];
+         if (y >= 0) {
+            if (x >= 0) { y *= 2; x *= 2; }
+            else { y *= 2; x = -(2 * x + 1); }
+         } else {
+            if (x >= 0) { y = -(2 * y + 1); x *= 2; }
+            else { y = -(2 * y + 1); x = -(2 * x + 1); }
+         }
+         p0 += w * (dx + (float)x * p[0]);
+         p1 -= w * (dy + (float)y * p[0]);
+      } break;
+      case 59: { /* cpow: p = {va, vc, vd, power} */
+         float lnr = 0.5f * logf(sumsq), s, c;
+         float ang = p[1] * atan_yx + p[2] * lnr + p[0] * floorf(p[3] * rng.u01());
+         float m = w * expf(p[1] * lnr - p[2] * atan_yx);
+         sincosf(ang, &s, &c);
+         p0 += m * c;
+         p1 += m * s;
+      } break;
+      case 60: { /* curve: p = {xamp, yamp, 1/xlen^2, 1/ylen^2} */
+         p0 += w * (tx + p[0] * expf(-ty * ty * p[2]));
+         p1 += w * (ty + p[1] * expf(-tx * tx * p[3]));
+      } break;
+      case 61: { /* edisc */
+         float tmp = sumsq + 1.0f;
+         float tmp2 = 2.0f * tx;
+         float xmax = (sqrtf(tmp + tmp2) + sqrtf(tmp - tmp2)) * 0.5f;
+         float a1 = logf(xmax + sqrtf(xmax - 1.0f));
+         float a2 = -acosf(tx / xmax);
+         float ww = w / 11.57034632f, snv, csv;
+         sincosf(a1, &snv, &csv);
+         float snhu = sinhf(a2), cshu = coshf(a2);
+         if (ty > 0.0f) snv = -snv;
+         p0 += ww * cshu * csv;
+         p1 += ww * snhu * snv;
+      } break;
+      case 62: { /* elliptic */
+         float tmp = sumsq + 1.0f;
+         float x2 = 2.0f * tx;
+         float xmax = 0.5f * (sqrtf(tmp + x2) + sqrtf(tmp - x2));
+         float a = tx / xmax;
+         float b = 1.0f - a * a;
+         float ssx = xmax - 1.0f;
+         float ww = w / F3B_PI_2;
+         b = b < 0.0f ? 0.0f : sqrtf(b);
+         ssx = ssx < 0.0f ? 0.0f : sqrtf(ssx);
+         p0 += ww * atan2f(a, b);
+         if (ty > 0.0f) p1 += ww * logf(xmax + ssx);
+         else p1 -= ww * logf(xmax + ssx);
+      } break;
+      case 63: { /* escher: p = {vc, vd} */
+         float lnr = 0.5f * logf(sumsq), s, c;
+         float m = w * expf(p[0] * lnr - p[1] * atan_yx);
+         float n = p[0] * atan_yx + p[1] * lnr;
+         sincosf(n, &s, &c);
+         p0 += m * c;
+         p1 += m * s;
+      } break;
+      case 64: { /* foci */
+         float expx = expf(tx) * 0.5f;
+         float expnx = 0.25f / expx, s, c;
+         sincosf(ty, &s, &c);
+         float t = w / (expx + expnx - c);
+         p0 += t * (expx - expnx);
+         p1 += t * s;
+      } break;
+      case 65: { /* lazysusan: p = {spin, space, twist, x, y} */
+         float x = tx - p[3];
+         float y = ty + p[4];
+         float r = sqrtf(x * x + y * y);
+         if (r < w) {
+            float a = atan2f(y, x) + p[0] + p[2] * (w - r), s, c;
+            sincosf(a, &s, &c);
+            r = w * r;
+            p0 += r * c + p[3];
+            p1 += r * s - p[4];
+         } else {
+            r = w * (1.0f + p[1] / r);
+            p0 += r * x + p[3];
+            p1 += r * y - p[4];
+         }
+      } break;
+      case 66: { /* loonie */
+         float w2 = w * w;
+         if (sumsq < w2) {
+            float r = w * sqrtf(w2 / sumsq - 1.0f);
+            p0 += r * tx;
+            p1 += r * ty;
+         } else {
+            p0 += w * tx;
+            p1 += w * ty;
+         }
+      } break;
+      /* 67 pre_blur is applied before the loop and never packed as a loop entry */
+      case 68: { /* modulus: p = {x, y} */
+         float xr = 2.0f * p[0], yr = 2.0f * p[1];
+         if (tx > p[0]) p0 += w * (-p[0] + fmodf(tx + p[0], xr));
+         else if (tx < -p[0]) p0 += w * (p[0] - fmodf(p[0] - tx, xr));
+         else p0 += w * tx;
+         if (ty > p[1]) p1 += w * (-p[1] + fmodf(ty + p[1], yr));
+         else if (ty < -p[1]) p1 += w * (p[1] - fmodf(p[1] - ty, yr));
+         else p1 += w * ty;
+      } break;
+      case 69: { /* oscilloscope: p = {2*pi*freq, amplitude, separation, damping} */
+         float t;
+         if (p[3] == 0.0f) t = p[1] * cosf(p[0] * tx) + p[2];
+         else t = p[1] * expf(-fabsf(tx) * p[3]) * cosf(p[0] * tx) + p[2];
+         p0 += w * tx;
+         if (fabsf(ty) <= t) p1 -= w * ty;
+         else p1 += w * ty;
+      } break;
+      case 70: { /* polar2 */
+         float p2v = w * F3B_1_PI;
+         p0 += p2v * atan_xy;
+         p1 += p2v * 0.5f * logf(sumsq);
+      } break;
+      case 71: { /* popcorn2: p = {x, y, c} */
+         p0 += w * (tx + p[0] * sinf(tanf(ty * p[2])));
+         p1 += w * (ty + p[1] * sinf(tanf(tx * p[2])));
+      } break;
+      case 72: { /* scry */
+         float r = 1.0f / (rad * (sumsq + 1.0f / (w + F3B_EPS)));
+         p0 += tx * r;
+         p1 += ty * r;
+      } break;
+      case 73: { /* separation: p = {x^2, xinside, y^2, yinside} */
+         if (tx > 0.0f) p0 += w * (sqrtf(tx * tx + p[0]) - tx * p[1]);
+         else p0 -= w * (sqrtf(tx * tx + p[0]) + tx * p[1]);
+         if (ty > 0.0f) p1 += w * (sqrtf(ty * ty + p[2]) - ty * p[3]);
+         else p1 -= w * (sqrtf(ty * ty + p[2]) + ty * p[3]);
+      } break;
+      case 74: { /* split: p = {xsize*pi, ysize*pi} */
+         if (cosf(tx * p[0]) >= 0.0f) p1 += w * ty;
+         else p1 -= w * ty;
+         if (cosf(ty * p[1]) >= 0.0f) p0 += w * tx;
+         else p0 -= w * tx;
+      } break;
+      case 75: { /* splits: p = {x, y} */
+         p0 += w * (tx >= 0.0f ? tx + p[0] : tx - p[0]);
+         p1 += w * (ty >= 0.0f ? ty + p[1] : ty - p[1]);
+      } break;
+      case 76: { /* stripes: p = {1-space, warp} */
+         float roundx = floorf(tx + 0.5f);
+         float offx = tx - roundx;
+         p0 += w * (offx * p[0] + roundx);
+         p1 += w * (ty + offx * offx * p[1]);
+      } break;
+      case 77: { /* wedge: p = {angle, hole, count, swirl, comp_fac} */
+         float a = atan_yx + p[3] * rad, s, c;
+         float cc = floorf((p[2] * a + F3B_PI) * F3B_1_PI * 0.5f);
+         a = a * p[4] + cc * p[0];
+         sincosf(a, &s, &c);
+         float r = w * (rad + p[1]);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 78: { /* wedge_julia: p = {cn, rN, power, count, cf, angle} */
+         float r = w * powf(sumsq, p[0]), s, c;
+         int t_rnd = (int)(p[1] * rng.u01());
+         float a = (atan_yx + 2.0f * F3B_PI * (float)t_rnd) / p[2];
+         float cc = floorf((p[3] * a + F3B_PI) * F3B_1_PI * 0.5f);
+         a = a * p[4] + cc * p[5];
+         sincosf(a, &s, &c);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 79: { /* wedge_sph: p = {angle, hole, count, swirl, comp_fac} */
+         float r = 1.0f / (rad + F3B_EPS), s, c;
+         float a = atan_yx + p[3] * r;
+         float cc = floorf((p[2] * a + F3B_PI) * F3B_1_PI * 0.5f);
+         a = a * p[4] + cc * p[0];
+         sincosf(a, &s, &c);
+         r = w * (r + p[1]);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 80: { /* whorl: p = {inside, outside} */
+         float a, s, c;
+         if (rad < w) a = atan_yx + p[0] / (w - rad);
+         else a = atan_yx + p[1] / (w - rad);
+         sincosf(a, &s, &c);
+         p0 += w * rad * c;
+         p1 += w * rad * s;
+      } break;
+      case 81: { /* waves2: p = {freqx, scalex, freqy, scaley} */
+         p0 += w * (tx + p[1] * sinf(ty * p[0]));
+         p1 += w * (ty + p[3] * sinf(tx * p[2]));
+      } break;
+      case 82: { /* exp */
+         float e = expf(tx), s, c;
+         sincosf(ty, &s, &c);
+         p0 += w * e * c;
+         p1 += w * e * s;
+      } break;
+      case 83: /* log */
+         p0 += w * 0.5f * logf(sumsq);
+         p1 += w * atan_yx;
+         break;
+      case 84: { /* sin */
+         float s, c;
+         sincosf(tx, &s, &c);
+         p0 += w * s * coshf(ty);
+         p1 += w * c * sinhf(ty);
+      } break;
+      case 85: { /* cos */
+         float s, c;
+         sincosf(tx, &s, &c);
+         p0 += w * c * coshf(ty);
+         p1 -= w * s * sinhf(ty);
+      } break;
+      case 86: { /* tan */
+         float s, c;
+         sincosf(2.0f * tx, &s, &c);
+         float den = 1.0f / (c + coshf(2.0f * ty));
+         p0 += w * den * s;
+         p1 += w * den * sinhf(2.0f * ty);
+      } break;
+      case 87: { /* sec */
+         float s, c;
+         sincosf(tx, &s, &c);
+         float den = 2.0f / (cosf(2.0f * tx) + coshf(2.0f * ty));
+         p0 += w * den * c * coshf(ty);
+         p1 += w * den * s * sinhf(ty);
+      } break;
+      case 88: { /* csc */
+         float s, c;
+         sincosf(tx, &s, &c);
+         float den = 2.0f / (coshf(2.0f * ty) - cosf(2.0f * tx));
+         p0 += w * den * s * coshf(ty);
+         p1 -= w * den * c * sinhf(ty);
+      } break;
+      case 89: { /* cot */
+         float s, c;
+         sincosf(2.0f * tx, &s, &c);
+         float den = 1.0f / (coshf(2.0f * ty) - c);
+         p0 += w * den * s;
+         p1 -= w * den * sinhf(2.0f * ty);
+      } break;
+      case 90: { /* sinh */
+         float s, c;
+         sincosf(ty, &s, &c);
+         p0 += w * sinhf(tx) * c;
+         p1 += w * coshf(tx) * s;
+      } break;
+      case 91: { /* cosh */
+         float s, c;
+         sincosf(ty, &s, &c);
+         p0 += w * coshf(tx) * c;
+         p1 += w * sinhf(tx) * s;
+      } break;
+      case 92: { /* tanh */
+         float s, c;
+         sincosf(2.0f * ty, &s, &c);
+         float den = 1.0f / (c + coshf(2.0f * tx));
+         p0 += w * den * sinhf(2.0f * tx);
+         p1 += w * den * s;
+      } break;
+      case 93: { /* sech */
+         float s, c;
+         sincosf(ty, &s, &c);
+         float den = 2.0f / (cosf(2.0f * ty) + coshf(2.0f * tx));
+         p0 += w * den * c * coshf(tx);
+         p1 -= w * den * s * sinhf(tx);
+      } break;
+      case 94: { /* csch */
+         float s, c;
+         sincosf(ty, &s, &c);
+         float den = 2.0f / (coshf(2.0f * tx) - cosf(2.0f * ty));
+         p0 += w * den * sinhf(tx) * c;
+         p1 -= w * den * coshf(tx) * s;
+      } break;
+      case 95: { /* coth */
+         float s, c;
+         sincosf(2.0f * ty, &s, &c);
+         float den = 1.0f / (coshf(2.0f * tx) - c);
+         p0 += w * den * sinhf(2.0f * tx);
+         p1 += w * den * s;
+      } break;
+      case 96: { /* auger: p = {sym, weight, freq, scale} */
+         float s = sinf(p[2] * tx);
+         float t = sinf(p[2] * ty);
+         float dy = ty + p[1] * (p[3] * s * 0.5f + fabsf(ty) * s);
+         float dx = tx + p[1] * (p[3] * t * 0.5f + fabsf(tx) * t);
+         p0 += w * (tx + p[0] * (dx - tx));
+         p1 += w * dy;
+      } break;
+      case 97: { /* flux: p = {2 + spread} */
+         float xpw = tx + w, xmw = tx - w;
+         float avgr = w * p[0] * sqrtf(sqrtf(ty * ty + xpw * xpw) / sqrtf(ty * ty + xmw * xmw));
+         float avga = (atan2f(ty, xmw) - atan2f(ty, xpw)) * 0.5f, s, c;
+         sincosf(avga, &s, &c);
+         p0 += avgr * c;
+         p1 += avgr * s;
+      } break;
+      case 98: { /* mobius: p = {re_a, im_a, re_b, im_b, re_c, im_c, re_d, im_d} */
+         float re_u = p[0] * tx - p[1] * ty + p[2];
+         float im_u = p[0] * ty + p[1] * tx + p[3];
+         float re_v = p[4] * tx - p[5] * ty + p[6];
+         float im_v = p[4] * ty + p[5] * tx + p[7];
+         float rv = w / (re_v * re_v + im_v * im_v);
+         p0 += rv * (re_u * re_v + im_u * im_v);
+         p1 += rv * (im_u * re_v - re_u * im_v);
+      } break;
+      default:
+         break;
+      }
+      v += 2 + (w0 >> 8);
+   }
+
+   if (flags & F3B_XF_HAS_POST) {
+      qx = xf[F3B_X_P00] * p0 + xf[F3B_X_P10] * p1 + xf[F3B_X_P20];
+      qy = xf[F3B_X_P01] * p0 + xf[F3B_X_P11] * p1 + xf[F3B_X_P21];
+   } else {
+      qx = p0;
+      qy = p1;
+   }
+   if (f3b_bad(qx) || f3b_bad(qy)) {
+      qx = rng.u11();
+      qy = rng.u11();
+      return true;
+   }
+   return false;
+}

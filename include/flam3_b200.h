@@ -1,0 +1,147 @@
+/*
+ * flam3_b200.h — C-ABI of libflam3_b200.so, the B200 (sm_100a) implementation of flam3's
+ * render hot path. Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * Two levels:
+ *
+ *  (1) The drop-in symbols `flam3_render` / `flam3_render_memory_required` with the
+ *      reference's exact ABI are declared in flam3_b200_dropin.h (they need the
+ *      reference's public header flam3.h for flam3_frame) and implemented in
+ *      flam3_b200/csrc/f3b_render.c on top of this file.
+ *
+ *  (2) This file: the stage-level interface that replaces rect.c's
+ *      render_rectangle / iter_thread / de_thread machinery. One f3b_ctx owns one GPU's
+ *      buffers: the histogram ("buckets", rect.c:699), the accumulator (rect.c:700) and
+ *      the output image. A frame is rendered as
+ *
+ *         f3b_frame_begin                      rect.c:685-710   allocate + clear
+ *         for each batch:
+ *            f3b_hist_clear                    rect.c:721
+ *            f3b_iterate  (all temporal samples of the batch in one launch)
+ *                                              rect.c:754-931 + iter_thread + flam3_iterate
+ *            f3b_density                       rect.c:933-1058  k1/k2 log scale + DE
+ *         f3b_finish                           rect.c:1067-1247 filter + tone map -> out
+ *
+ *      Multi-GPU callers shard f3b_iterate with (rank, nranks), sum the histograms
+ *      through f3b_hist_*_ptr with their own collective, and run f3b_density/f3b_finish
+ *      per strip.
+ *
+ * Every function returns 0 on success and non-zero on error (f3b_last_error has the
+ * text) unless documented otherwise, mirroring the reference's 0/1 convention
+ * (rect.c:598-606).
+ */
+#ifndef FLAM3_B200_H
+#define FLAM3_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F3B_ABI_VERSION 1
+
+typedef struct f3b_ctx f3b_ctx;
+
+/* ---- context ------------------------------------------------------------------- */
+int f3b_abi_version(void);
+int f3b_ctx_create(int device, f3b_ctx **out);
+void f3b_ctx_destroy(f3b_ctx *ctx);
+const char *f3b_last_error(const f3b_ctx *ctx);
+/* info[0]=SM count, info[1]=resident chaos-game CTAs per SM, info[2]=threads per CTA */
+int f3b_device_info(f3b_ctx *ctx, int *info);
+int f3b_sync(f3b_ctx *ctx);
+
+/* ---- frame buffers (rect.c:685-710) ---------------------------------------------- */
+/* width/height are the BUCKET grid (oversample*image + 2*gutter). count_channel=0 lets
+ * the alpha plane double as the hit-count plane (valid when every palette alpha is 1 and
+ * every temporal-filter weight is 1; f3b_render.c decides). Clears both buffers. */
+int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel);
+int f3b_hist_clear(f3b_ctx *ctx);
+int f3b_accum_clear(f3b_ctx *ctx);
+
+/* ---- chaos game + histogram (iter_thread rect.c:253-527, flam3_iterate flam3.c:232) - */
+/* One entry per temporal sample; layout documented in flam3_b200/csrc/f3b_pack.h. */
+typedef struct {
+   uint64_t blob_offset; /* byte offset of the packed sample inside `blobs` (16-aligned) */
+   uint64_t n_iters;     /* stored iterations (fic.batch_size * nthreads, rect.c:833-840) */
+   uint32_t n_chains;    /* independent chains; 0 = let the library plan (f3b_plan_chains) */
+   uint32_t fuse;        /* discarded iterations per chain (rect.c:266) */
+   uint32_t first_group; /* filled by the library */
+   uint32_t sample_id;   /* RNG stream id of this temporal sample */
+} f3b_job;
+
+/* Number of chains the library would use for n_iters stored iterations when the launch
+ * holds n_jobs temporal samples and no chain may store more than max_chain_len iterations
+ * (= flam3_frame.sub_batch_size, rect.c:279). */
+uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len, uint32_t n_jobs);
+
+/* Runs the jobs' chains with chain-group index g where g % nranks == rank and adds the
+ * hits into this context's histogram. floor_adds=1 reproduces the integer bucket
+ * semantics of bits 32/33 (flam3.c:3838-3854). seed selects the random streams. */
+int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *jobs, int n_jobs,
+                uint64_t seed, int floor_adds, uint32_t max_chain_len, int rank, int nranks);
+/* bad values since f3b_frame_begin (stat_struct.badvals, rect.c:1251) */
+int f3b_badvals(f3b_ctx *ctx, double *out);
+
+/* ---- log scale + density estimation (rect.c:933-1058, de_thread rect.c:57-251) ---- */
+typedef struct {
+   double k1, k2;              /* rect.c:933-937 */
+   int oversample;
+   int int_accum;              /* bits=32: integer accumulators (flam3.c:3772-3786) */
+   /* flam3_de_helper (filters.c:272-407). n_kernels=0 disables DE (rect.c:947). */
+   int n_kernels;              /* de_max_ind rows present in coefs/widths */
+   int kernel_size;            /* coefficients per kernel, octant packed */
+   int max_filtered_counts;
+   int max_filter_index;
+   double curve;               /* estimator_curve (rect.c:997) */
+   const double *coefs;        /* host, n_kernels*kernel_size */
+   const double *widths;       /* host, n_kernels */
+} f3b_density_desc;
+int f3b_density(f3b_ctx *ctx, const f3b_density_desc *d);
+/* Same, restricted to bucket rows [row0,row1) of the accumulator (multi-GPU strips). */
+int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1);
+
+/* ---- spatial filter + tone map + quantise (rect.c:1067-1247) ---------------------- */
+typedef struct {
+   int image_width, image_height; /* output pixels (field-adjusted height) */
+   int oversample, de_offset;
+   int filter_width;
+   const double *filter;          /* host, filter_width^2 (filters.c:217-270) */
+   int earlyclip, nchan, transp, bytes_per_channel;
+   double gamma;                  /* mean gamma over temporal samples (rect.c:1071) */
+   double vibrancy;               /* mean vibrancy */
+   double background[3];          /* mean background * 256 (rect.c:1078-1080) */
+   double highlight_power;
+   double gam_lin_thresh;
+} f3b_final_desc;
+/* Writes image rows to host memory `out`; consecutive rows are row_stride bytes apart
+ * (2x the row size for interlaced fields, rect.c:616-624). */
+int f3b_finish(f3b_ctx *ctx, const f3b_final_desc *d, void *out, size_t row_stride);
+/* Same but leaves the image in device memory (tightly packed); *dev_out receives it. */
+int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out);
+
+/* ---- raw buffer access: tests, histogram exchange between GPUs --------------------- */
+/* reference bits=33 bucket layout: uint32[5] = r,g,b,a,count per bucket (flam3.c:3824) */
+int f3b_hist_upload_u32(f3b_ctx *ctx, const uint32_t *buckets5);
+int f3b_hist_download_u32(f3b_ctx *ctx, uint32_t *buckets5);
+/* accumulator: float[4] per bucket (abucket_float, flam3.c:3825) */
+int f3b_accum_upload(f3b_ctx *ctx, const float *acc4);
+int f3b_accum_download(f3b_ctx *ctx, float *acc4);
+void *f3b_hist_color_ptr(f3b_ctx *ctx); /* device float4[height*width] */
+void *f3b_hist_count_ptr(f3b_ctx *ctx); /* device float[height*width] or NULL */
+void *f3b_accum_ptr(f3b_ctx *ctx);      /* device float4[height*width] */
+void *f3b_stream_ptr(f3b_ctx *ctx);     /* cudaStream_t the context launches on */
+
+/* ---- instrumentation ------------------------------------------------------------- */
+enum { F3B_STAGE_ITERATE = 0, F3B_STAGE_DENSITY = 1, F3B_STAGE_FINAL = 2, F3B_NSTAGES = 3 };
+/* GPU milliseconds (CUDA events on the context stream) and launch count of a stage since
+ * f3b_stats_reset; synchronises the stream. */
+int f3b_stage_stats(f3b_ctx *ctx, int stage, double *ms, uint64_t *launches);
+void f3b_stats_reset(f3b_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

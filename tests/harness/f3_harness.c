@@ -1,0 +1,147 @@
+/*
+ * tests/harness/f3_harness.c — TEST INFRASTRUCTURE. A few plain-C entry points over the
+ * public flam3.h API so that Python (ctypes) can drive either the unmodified reference
+ * library (oracle/_ref/libflam3_ref.so) or the B200 drop-in (dropin/_build/libflam3.so)
+ * the same way flam3-render.c / flam3-animate.c do: parse genomes from XML, fill a
+ * flam3_frame, seed it like flam3_init_frame (flam3.c:2494-2516), call flam3_render.
+ * Compiled once against each library; contains no rendering logic of its own.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "flam3.h"
+
+typedef struct {
+   int bits, bytes_per_channel, earlyclip, nthreads, sub_batch_size, verbose;
+   int field, nchan, transp;
+   int first_genome, ngenomes; /* slice of the parsed array handed to the frame */
+   double time, pixel_aspect_ratio;
+   char isaac_seed[128];
+} h_render_args;
+
+void *h_parse(const char *xml, int *ncps) {
+   char *copy = strdup(xml);
+   char name[] = "harness.flam3";
+   flam3_genome *g = flam3_parse_xml2(copy, name, flam3_defaults_on, ncps);
+   free(copy);
+   return g;
+}
+
+void h_free_genomes(void *cps, int n) {
+   flam3_genome *g = (flam3_genome *)cps;
+   if (!g) return;
+   for (int i = 0; i < n; i++) clear_cp(&g[i], 0);
+   free(g);
+}
+
+int h_genome_dims(void *cps, int idx, int *w, int *h, int *oversample) {
+   flam3_genome *g = (flam3_genome *)cps;
+   *w = g[idx].width;
+   *h = g[idx].height;
+   *oversample = g[idx].spatial_oversample;
+   return 0;
+}
+
+static void seed_frame(flam3_frame *f, const char *seed) {
+   /* same steps as flam3_init_frame with isaac_seed set (flam3.c:2501-2515) */
+   memset(f->rc.randrsl, 0, RANDSIZ * sizeof(ub4));
+   strncpy((char *)&f->rc.randrsl, seed, RANDSIZ * sizeof(ub4));
+   irandinit(&f->rc, 1);
+}
+
+/* stats_out = {badvals, num_iters, render_seconds}; rc_out (optional) receives the
+ * frame's randctx after the call (sizeof(randctx) bytes). Returns flam3_render's value. */
+int h_render(void *cps, const h_render_args *a, void *out, double *stats_out, void *rc_out) {
+   flam3_genome *g = (flam3_genome *)cps;
+   flam3_frame f;
+   stat_struct st;
+   memset(&f, 0, sizeof(f));
+   memset(&st, 0, sizeof(st));
+   f.pixel_aspect_ratio = a->pixel_aspect_ratio;
+   f.genomes = g + a->first_genome;
+   f.ngenomes = a->ngenomes;
+   f.verbose = a->verbose;
+   f.bits = a->bits;
+   f.bytes_per_channel = a->bytes_per_channel;
+   f.earlyclip = a->earlyclip;
+   f.time = a->time;
+   f.progress = 0;
+   f.progress_parameter = 0;
+   f.nthreads = a->nthreads;
+   f.sub_batch_size = a->sub_batch_size;
+   seed_frame(&f, a->isaac_seed);
+   int rv = flam3_render(&f, out, a->field, a->nchan, a->transp, &st);
+   if (stats_out) {
+      stats_out[0] = st.badvals;
+      stats_out[1] = (double)st.num_iters;
+      stats_out[2] = (double)st.render_seconds;
+   }
+   if (rc_out) memcpy(rc_out, &f.rc, sizeof(randctx));
+   return rv;
+}
+
+double h_memory_required(void *cps, int idx, int bits) {
+   flam3_frame f;
+   memset(&f, 0, sizeof(f));
+   f.genomes = (flam3_genome *)cps + idx;
+   f.ngenomes = 1;
+   f.bits = bits;
+   return flam3_render_memory_required(&f);
+}
+
+/* Geometry of the render buffers for a frame, by the formulas of rect.c:628-686, using
+ * the library's own flam3_interpolate/flam3_create_spatial_filter. dims = {fic.width,
+ * fic.height, filter_width, gutter_width, de_offset, oversample}. */
+extern int flam3_create_spatial_filter(flam3_frame *spec, int field, double **filter);
+int h_buffer_geometry(void *cps, const h_render_args *a, int *dims) {
+   flam3_genome *g = (flam3_genome *)cps;
+   flam3_frame f;
+   flam3_genome cp;
+   double *filter = NULL;
+   memset(&f, 0, sizeof(f));
+   memset(&cp, 0, sizeof(cp));
+   f.pixel_aspect_ratio = a->pixel_aspect_ratio;
+   f.genomes = g + a->first_genome;
+   f.ngenomes = a->ngenomes;
+   f.time = a->time;
+   flam3_interpolate(f.genomes, f.ngenomes, f.time, 0, &cp);
+   int os = cp.spatial_oversample;
+   int iw = cp.width, ih = a->field ? cp.height / 2 : cp.height;
+   int fw = flam3_create_spatial_filter(&f, a->field, &filter);
+   free(filter);
+   if (fw < 0) return 1;
+   int gutter = (fw - os) / 2, maxde = 0, de_offset = 0;
+   for (int i = 0; i < f.ngenomes; i++) {
+      double e = f.genomes[i].estimator;
+      int w = (int)ceil(e) * os;
+      if (w > maxde) maxde = w;
+   }
+   if (maxde > 0) maxde += os - 1;
+   if (maxde > gutter) {
+      de_offset = maxde - gutter;
+      gutter = maxde;
+   }
+   dims[0] = os * iw + 2 * gutter;
+   dims[1] = os * ih + 2 * gutter;
+   dims[2] = fw;
+   dims[3] = gutter;
+   dims[4] = de_offset;
+   dims[5] = os;
+   clear_cp(&cp, 0);
+   return 0;
+}
+
+/* Print genome idx back to XML (explicit palette) — used to make self-contained fixtures. */
+char *h_print_genome(void *cps, int idx) {
+   return flam3_print_to_string((flam3_genome *)cps + idx);
+}
+
+/* sizes the Python side asserts against SURVEY.md §8(b) */
+void h_abi_sizes(int *out) {
+   out[0] = (int)sizeof(randctx);
+   out[1] = (int)sizeof(flam3_xform);
+   out[2] = (int)sizeof(flam3_genome);
+   out[3] = (int)sizeof(flam3_frame);
+}
