@@ -125,6 +125,31 @@ class Flam3Lib:
         d.h_print_genome.argtypes = [C.c_void_p, C.c_int]
         d.h_abi_sizes.argtypes = [C.POINTER(C.c_int)]
 
+    # ---- drop-in only: post-pass from a supplied histogram, and the render context ----
+    def inject_histogram(self, buckets5):
+        """Make the following flam3_render calls skip the chaos game and use `buckets5`
+        (uint32[h, w, 5], the reference's bits=33 bucket layout). None switches back."""
+        f = self._dll.f3b_render_inject_histogram
+        f.argtypes = [C.c_void_p, C.c_size_t]
+        f.restype = None
+        if buckets5 is None:
+            self._inject_keep = None
+            f(None, 0)
+            return
+        b = np.ascontiguousarray(buckets5, dtype=np.uint32)
+        self._inject_keep = b
+        f(b.ctypes.data_as(C.c_void_p), b.size // 5)
+
+    def render_context(self, core):
+        """The f3b_ctx the drop-in renders with, wrapped for stage stats / buffer access."""
+        f = self._dll.f3b_render_context
+        f.restype = C.c_void_p
+        f.argtypes = []
+        p = f()
+        if not p:
+            raise RuntimeError("drop-in has no GPU context")
+        return Context(core, C.c_void_p(p))
+
     def parse(self, xml):
         if isinstance(xml, str):
             xml = xml.encode()

@@ -49,6 +49,20 @@ f3b_ctx *f3b_render_context(void) {
    return c;
 }
 
+/* Render the next frame(s) from a caller-supplied histogram instead of running the chaos
+ * game: `buckets5` is the reference's bits=33 bucket layout, uint32[5] per bucket
+ * (flam3.c:3824), nbuckets must equal the frame's bucket grid. Pass NULL to return to
+ * normal operation. Used to drive the post-pass from a histogram produced elsewhere
+ * (another GPU, or the reference itself in the parity tests). */
+static const uint32_t *g_inject = NULL;
+static size_t g_inject_n = 0;
+void f3b_render_inject_histogram(const uint32_t *buckets5, size_t nbuckets) {
+   pthread_mutex_lock(&g_lock);
+   g_inject = buckets5;
+   g_inject_n = nbuckets;
+   pthread_mutex_unlock(&g_lock);
+}
+
 double flam3_render_memory_required(flam3_frame *spec) {
    /* flam3.c:3874-3887: the reference's planning model (bytes), kept verbatim in meaning so
     * that flam3-render's nstrips / use_mem logic (flam3-render.c:36-101) behaves the same */
@@ -303,8 +317,15 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
 
       /* ---- chaos game: one launch for the whole batch ---- */
       const uint32_t max_chain = spec->sub_batch_size > 0 ? (uint32_t)spec->sub_batch_size : 10000u;
-      if (f3b_iterate(ctx, blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
-                      spec->bits != 64, max_chain, 0, 1))
+      if (g_inject) {
+         if (g_inject_n != (size_t)g.width * g.height) {
+            fprintf(stderr, "flam3_render (B200): injected histogram has %zu buckets, frame needs "
+                            "%dx%d\n", g_inject_n, g.width, g.height);
+            goto done;
+         }
+         if (f3b_hist_upload_u32(ctx, g_inject)) goto gpu_error;
+      } else if (f3b_iterate(ctx, blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
+                             spec->bits != 64, max_chain, 0, 1))
          goto gpu_error;
 
       /* ---- log scale + density estimation (rect.c:933-1058); cp/cam are those of the
@@ -411,7 +432,7 @@ int flam3_render(flam3_frame *spec, void *out, int field, int nchan, int transp,
    int rv = 1;
    if (ctx) {
       const randctx rc0 = spec->rc;
-      rv = render_locked(ctx, spec, out, field, nchan, transp, stats, 0);
+      rv = render_locked(ctx, spec, out, field, nchan, transp, stats, g_inject != NULL);
       if (rv == -2) { /* a palette with alpha appeared mid-frame: redo with a count plane */
          spec->rc = rc0;
          rv = render_locked(ctx, spec, out, field, nchan, transp, stats, 1);
