@@ -140,6 +140,26 @@ class Flam3Lib:
         self._inject_keep = b
         f(b.ctypes.data_as(C.c_void_p), b.size // 5)
 
+    def set_device_only(self, on):
+        self._dll.f3b_render_set_device_only(int(bool(on)))
+
+    def set_shard(self, rank, nranks):
+        self._dll.f3b_render_set_shard(int(rank), int(nranks))
+
+    def set_exchange(self, fn):
+        """fn(ctx_ptr) is called after every batch's chaos game (histogram exchange hook)."""
+        proto = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+        f = self._dll.f3b_render_set_exchange
+        f.argtypes = [C.c_void_p, C.c_void_p]
+        f.restype = None
+        if fn is None:
+            self._exchange_keep = None
+            f(None, None)
+            return
+        cb = proto(lambda ctx, user: fn(ctx))
+        self._exchange_keep = cb
+        f(C.cast(cb, C.c_void_p), None)
+
     def render_context(self, core):
         """The f3b_ctx the drop-in renders with, wrapped for stage stats / buffer access."""
         f = self._dll.f3b_render_context
@@ -234,7 +254,8 @@ CORE_SYMBOLS = [
     "f3b_iterate", "f3b_badvals", "f3b_density", "f3b_density_rows", "f3b_finish",
     "f3b_finish_device", "f3b_hist_upload_u32", "f3b_hist_download_u32", "f3b_accum_upload",
     "f3b_accum_download", "f3b_hist_color_ptr", "f3b_hist_count_ptr", "f3b_accum_ptr",
-    "f3b_stream_ptr", "f3b_stage_stats", "f3b_stats_reset",
+    "f3b_stream_ptr", "f3b_stage_stats", "f3b_stats_reset", "f3b_xfer_stats", "f3b_timer_start",
+    "f3b_timer_stop",
 ]
 
 
@@ -431,6 +452,28 @@ class Context:
 
     def stats_reset(self):
         self.lib._dll.f3b_stats_reset(self.ptr)
+
+    def xfer_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        f = self.lib._dll.f3b_xfer_stats
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        self._ck(f(self.ptr, C.byref(a), C.byref(b)), "xfer_stats")
+        return a.value, b.value
+
+    def timer_start(self):
+        f = self.lib._dll.f3b_timer_start
+        f.argtypes = [C.c_void_p]
+        self._ck(f(self.ptr), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        f = self.lib._dll.f3b_timer_stop
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        self._ck(f(self.ptr, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def sync(self):
+        self._ck(self.lib._dll.f3b_sync(self.ptr), "sync")
 
     def hist_ptrs(self):
         d = self.lib._dll

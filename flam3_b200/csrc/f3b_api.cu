@@ -42,6 +42,8 @@ struct f3b_ctx {
    size_t ev_used = 0;
    double stage_ms[F3B_NSTAGES] = {0, 0, 0};
    uint64_t stage_launches[F3B_NSTAGES] = {0, 0, 0};
+   uint64_t h2d_bytes = 0, d2h_bytes = 0;
+   cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 };
 
 static int fail(f3b_ctx *c, const char *fmt, ...) {
@@ -72,7 +74,9 @@ static int ensure(f3b_ctx *ctx, DevBuf &b, size_t bytes) {
    return 0;
 }
 
+static int stats_collect(f3b_ctx *ctx);
 static int stage_begin(f3b_ctx *ctx, int stage) {
+   if (ctx->ev_used >= 1024 && stats_collect(ctx)) return 1; /* bound the event pool */
    if (ctx->ev_used == ctx->ev_pool.size()) {
       cudaEvent_t a, b;
       CK(cudaEventCreate(&a));
@@ -154,6 +158,8 @@ void f3b_ctx_destroy(f3b_ctx *ctx) {
       cudaEventDestroy(p.first);
       cudaEventDestroy(p.second);
    }
+   if (ctx->timer0) cudaEventDestroy(ctx->timer0);
+   if (ctx->timer1) cudaEventDestroy(ctx->timer1);
    if (ctx->stream) cudaStreamDestroy(ctx->stream);
    delete ctx;
 }
@@ -268,6 +274,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
                       ctx->stream));
    CK(cudaMemcpyAsync(ctx->groups.p, group_job.data(), sizeof(uint32_t) * (size_t)n_groups,
                       cudaMemcpyHostToDevice, ctx->stream));
+   ctx->h2d_bytes += blob_bytes + sizeof(f3b_job) * (size_t)n_jobs + sizeof(uint32_t) * (size_t)n_groups;
    /* the three host buffers above are pageable: the async copies have staged them before
     * returning, but keep it simple and make that explicit */
    CK(cudaStreamSynchronize(ctx->stream));
@@ -304,6 +311,7 @@ int f3b_badvals(f3b_ctx *ctx, double *out) {
    unsigned long long v = 0;
    CK(cudaSetDevice(ctx->device));
    CK(cudaMemcpyAsync(&v, ctx->d_badvals, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+   ctx->d2h_bytes += sizeof(v);
    CK(cudaStreamSynchronize(ctx->stream));
    *out = (double)v;
    return 0;
@@ -359,6 +367,7 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
                          ctx->stream));
       CK(cudaMemcpyAsync(ctx->de_radius.p, radius.data(), (size_t)d->n_kernels,
                          cudaMemcpyHostToDevice, ctx->stream));
+      ctx->h2d_bytes += nc * sizeof(float) + (size_t)d->n_kernels;
       CK(cudaStreamSynchronize(ctx->stream));
       P.de_coefs = (const float *)ctx->de_coefs.p;
       P.de_radius = (const uint8_t *)ctx->de_radius.p;
@@ -398,6 +407,7 @@ int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out) {
    if (ensure(ctx, ctx->filter, fbytes)) return 1;
    if (ensure(ctx, ctx->image, ibytes)) return 1;
    CK(cudaMemcpyAsync(ctx->filter.p, d->filter, fbytes, cudaMemcpyHostToDevice, ctx->stream));
+   ctx->h2d_bytes += fbytes;
    CK(cudaStreamSynchronize(ctx->stream));
 
    F3FinalParams P;
@@ -438,6 +448,7 @@ int f3b_finish(f3b_ctx *ctx, const f3b_final_desc *d, void *out, size_t row_stri
    if (row_stride < row) return fail(ctx, "f3b_finish: row stride too small");
    CK(cudaMemcpy2DAsync(out, row_stride, dev, row, row, (size_t)d->image_height,
                         cudaMemcpyDeviceToHost, ctx->stream));
+   ctx->d2h_bytes += row * (size_t)d->image_height;
    CK(cudaStreamSynchronize(ctx->stream));
    return 0;
 }
@@ -511,10 +522,40 @@ int f3b_stage_stats(f3b_ctx *ctx, int stage, double *ms, uint64_t *launches) {
    return 0;
 }
 
+int f3b_xfer_stats(f3b_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+   if (!ctx) return 1;
+   if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+   if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+   return 0;
+}
+
+int f3b_timer_start(f3b_ctx *ctx) {
+   if (!ctx) return 1;
+   CK(cudaSetDevice(ctx->device));
+   if (!ctx->timer0) {
+      CK(cudaEventCreate(&ctx->timer0));
+      CK(cudaEventCreate(&ctx->timer1));
+   }
+   CK(cudaEventRecord(ctx->timer0, ctx->stream));
+   return 0;
+}
+
+int f3b_timer_stop(f3b_ctx *ctx, double *ms) {
+   if (!ctx || !ctx->timer0) return 1;
+   CK(cudaSetDevice(ctx->device));
+   CK(cudaEventRecord(ctx->timer1, ctx->stream));
+   CK(cudaEventSynchronize(ctx->timer1));
+   float f = 0.f;
+   CK(cudaEventElapsedTime(&f, ctx->timer0, ctx->timer1));
+   if (ms) *ms = (double)f;
+   return 0;
+}
+
 void f3b_stats_reset(f3b_ctx *ctx) {
    if (!ctx) return;
    cudaSetDevice(ctx->device);
    stats_collect(ctx);
+   ctx->h2d_bytes = ctx->d2h_bytes = 0;
    for (int i = 0; i < F3B_NSTAGES; i++) {
       ctx->stage_ms[i] = 0.0;
       ctx->stage_launches[i] = 0;

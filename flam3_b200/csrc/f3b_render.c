@@ -63,6 +63,33 @@ void f3b_render_inject_histogram(const uint32_t *buckets5, size_t nbuckets) {
    pthread_mutex_unlock(&g_lock);
 }
 
+/* Knobs for hosts that embed the library (bench.py, the multi-GPU driver). Defaults give
+ * the plain single-GPU drop-in behaviour.
+ *  - device_only: leave the finished image on the GPU (no device->host copy); `out` is
+ *    not written.
+ *  - shard (rank, nranks): this process runs only its share of the chaos-game chains
+ *    (f3b_iterate's rank/nranks) into its private histogram.
+ *  - exchange callback: called after the chaos game of every batch, with the stream
+ *    idle, so the host can sum the per-GPU histograms (e.g. an NCCL all-reduce on
+ *    f3b_hist_color_ptr / f3b_hist_count_ptr) before density estimation runs. */
+static int g_device_only = 0;
+static int g_rank = 0, g_nranks = 1;
+static void (*g_exchange)(f3b_ctx *, void *) = NULL;
+static void *g_exchange_user = NULL;
+void f3b_render_set_device_only(int on) { g_device_only = on; }
+void f3b_render_set_shard(int rank, int nranks) {
+   if (nranks < 1 || rank < 0 || rank >= nranks) {
+      rank = 0;
+      nranks = 1;
+   }
+   g_rank = rank;
+   g_nranks = nranks;
+}
+void f3b_render_set_exchange(void (*cb)(f3b_ctx *, void *), void *user) {
+   g_exchange = cb;
+   g_exchange_user = user;
+}
+
 double flam3_render_memory_required(flam3_frame *spec) {
    /* flam3.c:3874-3887: the reference's planning model (bytes), kept verbatim in meaning so
     * that flam3-render's nstrips / use_mem logic (flam3-render.c:36-101) behaves the same */
@@ -325,8 +352,12 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          }
          if (f3b_hist_upload_u32(ctx, g_inject)) goto gpu_error;
       } else if (f3b_iterate(ctx, blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
-                             spec->bits != 64, max_chain, 0, 1))
+                             spec->bits != 64, max_chain, g_rank, g_nranks))
          goto gpu_error;
+      if (g_exchange) {
+         if (f3b_sync(ctx)) goto gpu_error;
+         (*g_exchange)(ctx, g_exchange_user);
+      }
 
       /* ---- log scale + density estimation (rect.c:933-1058); cp/cam are those of the
        * batch's LAST temporal sample, as in the reference ---- */
@@ -384,7 +415,10 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       fd.highlight_power = highpow;
       fd.gam_lin_thresh = cp.gam_lin_thresh;
       const size_t stride = (size_t)g.out_width * nchan * bytes_per_channel;
-      if (f3b_finish(ctx, &fd, out, stride)) goto gpu_error;
+      if (g_device_only) {
+         if (f3b_finish_device(ctx, &fd, NULL)) goto gpu_error;
+      } else if (f3b_finish(ctx, &fd, out, stride))
+         goto gpu_error;
    }
 
    {

@@ -140,6 +140,12 @@ enum { F3B_STAGE_ITERATE = 0, F3B_STAGE_DENSITY = 1, F3B_STAGE_FINAL = 2, F3B_NS
  * f3b_stats_reset; synchronises the stream. */
 int f3b_stage_stats(f3b_ctx *ctx, int stage, double *ms, uint64_t *launches);
 void f3b_stats_reset(f3b_ctx *ctx);
+/* Bytes copied host->device / device->host by this context since f3b_stats_reset. */
+int f3b_xfer_stats(f3b_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+/* A CUDA-event stopwatch on the context's stream: start records an event, stop records a
+ * second one, waits for it and returns the elapsed GPU milliseconds. */
+int f3b_timer_start(f3b_ctx *ctx);
+int f3b_timer_stop(f3b_ctx *ctx, double *ms);
 
 #ifdef __cplusplus
 }
