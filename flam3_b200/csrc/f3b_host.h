@@ -39,8 +39,8 @@ int f3b_camera_setup(const flam3_genome *cp, const f3b_frame_geom *g, f3b_camera
 int f3b_chaos_enabled(const flam3_genome *cp, int nstd);
 /* returns 0 ok, 1 genome error (message printed), 2 out of space */
 int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_scalar,
-                    int cmap_size, uint32_t *words, size_t cap_words, size_t *used_words,
-                    int *count_is_alpha);
+                    int cmap_size, int floor_adds, uint32_t *words, size_t cap_words,
+                    size_t *used_words, int *count_is_alpha);
 
 /* ISAAC as the reference runs it on LP64 (isaac.c + isaac.h): next 32-bit draw from ctx. */
 unsigned long f3b_isaac_next(randctx *ctx);

@@ -27,6 +27,9 @@
 #include "f3b_variations.cuh"
 
 #define F3B_BLOCK F3B_CHAINS_PER_GROUP
+#ifndef F3B_ITER_MIN_BLOCKS
+#define F3B_ITER_MIN_BLOCKS 3 /* 80 registers, 24 warps/SM: best of {2,3,4} on B200 (profiles/r01) */
+#endif
 
 __device__ __forceinline__ void f3b_red_v4(float4 *addr, float r, float g, float b, float a) {
    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(r), "f"(g),
@@ -37,8 +40,19 @@ __device__ __forceinline__ void f3b_red_f32(float *addr, float v) {
    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
+/* The final xform (flam3.c:280-287) is applied out of line: few genomes have one, and a
+ * second inlined copy of the variation interpreter would double the hot loop's code. */
+__device__ __noinline__ float4 f3b_apply_final(const float *xf, float px, float py, float pc,
+                                               F3Rng *rngp) {
+   F3Rng rng = *rngp;
+   float fx, fy, fc, fv;
+   f3b_apply_xform(xf, px, py, pc, fx, fy, fc, fv, rng);
+   *rngp = rng;
+   return make_float4(fx, fy, fc, fv);
+}
+
 template <bool COUNT>
-__global__ void __launch_bounds__(F3B_BLOCK, 4) f3b_iterate_kernel(const F3IterateParams P) {
+__global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_kernel(const F3IterateParams P) {
    extern __shared__ __align__(16) uint32_t smem[];
    const float *sf = reinterpret_cast<const float *>(smem);
 
@@ -73,13 +87,14 @@ __global__ void __launch_bounds__(F3B_BLOCK, 4) f3b_iterate_kernel(const F3Itera
       if (n_store == 0) continue;
 
       /* header */
-      const uint32_t nstd = smem[F3B_H_NSTD];
+      const uint32_t cstride = smem[F3B_H_CHOOSER_STRIDE];
       const int final_idx = (int)smem[F3B_H_FINAL];
       const bool xaos = smem[F3B_H_XAOS] != 0;
       const float final_opacity = sf[F3B_H_FINAL_OPACITY];
       const bool pal_linear = smem[F3B_H_PALMODE] != 0;
       const int cmap_size = (int)smem[F3B_H_CMAPSIZE];
       const bool rotate = smem[F3B_H_ROTATE] != 0;
+      const bool plot_ready = (smem[F3B_H_PLOT] & F3B_PLOT_READY) != 0;
       const uint32_t *cum = smem + smem[F3B_H_OFF_CHOOSER];
       const uint32_t *xftab = smem + smem[F3B_H_OFF_XFTAB];
       const float4 *dmap = reinterpret_cast<const float4 *>(smem + smem[F3B_H_OFF_PALETTE]);
@@ -104,9 +119,18 @@ __global__ void __launch_bounds__(F3B_BLOCK, 4) f3b_iterate_kernel(const F3Itera
          /* flam3.c:249-270: pick + apply, retrying a bad value up to 4 times in place */
          for (;;) {
             const uint32_t k = rng.next() & (F3B_CHOOSER_GRAIN - 1u);
-            const uint32_t *row = cum + (xaos ? lastxf * nstd : 0u);
-            fn = 0;
-            for (uint32_t j = 0; j + 1 < nstd; j++) fn += (k >= row[j]) ? 1u : 0u;
+            /* fn = number of cumulative thresholds <= k; rows are padded with 16384 */
+            const uint4 *row = reinterpret_cast<const uint4 *>(cum + (xaos ? lastxf * cstride : 0u));
+            {
+               const uint4 c = row[0]; /* up to 4 xforms: one LDS.128, no loop */
+               fn = (k >= c.x ? 1u : 0u) + (k >= c.y ? 1u : 0u) + (k >= c.z ? 1u : 0u) +
+                    (k >= c.w ? 1u : 0u);
+            }
+            for (uint32_t j = 4; j < cstride; j += 4) {
+               const uint4 c = row[j >> 2];
+               fn += (k >= c.x ? 1u : 0u) + (k >= c.y ? 1u : 0u) + (k >= c.z ? 1u : 0u) +
+                     (k >= c.w ? 1u : 0u);
+            }
             const bool isbad =
                 f3b_apply_xform(sf + xftab[fn], px, py, pc, qx, qy, qc, qv, rng);
             if (!isbad) {
@@ -134,11 +158,12 @@ __global__ void __launch_bounds__(F3B_BLOCK, 4) f3b_iterate_kernel(const F3Itera
             bool apply = (final_opacity == 1.0f);
             if (!apply) apply = rng.u01() < final_opacity;
             if (apply) {
-               float fx, fy, fc, fv;
-               f3b_apply_xform(sf + xftab[final_idx], px, py, pc, fx, fy, fc, fv, rng);
-               qx = fx;
-               qy = fy;
-               qc = fc; /* opacity stays that of the regular xform */
+               F3Rng tmp = rng;
+               const float4 f = f3b_apply_final(sf + xftab[final_idx], px, py, pc, &tmp);
+               rng = tmp;
+               qx = f.x;
+               qy = f.y;
+               qc = f.z; /* opacity stays that of the regular xform */
             }
          }
 
@@ -161,6 +186,14 @@ __global__ void __launch_bounds__(F3B_BLOCK, 4) f3b_iterate_kernel(const F3Itera
          const float findex = qc * (float)cmap_size;
          int ci = (int)findex;
          float4 col;
+         if (plot_ready) {
+            /* step lookup, every xform fully visible, dmap truncated on the host */
+            ci = ci < 0 ? 0 : (ci >= cmap_size - 1 ? cmap_size - 1 : ci);
+            col = dmap[ci];
+            f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
+            if (COUNT) f3b_red_f32(P.hist_count + bidx, 255.0f);
+            continue;
+         }
          if (pal_linear) {
             float frac;
             if (ci < 0) {

@@ -55,6 +55,22 @@ static unsigned var_precalc_flags(int id) {
    }
 }
 
+/* does the variation read precalc_sqrt (f->precalc_sqrt in variations.c)? */
+static int var_needs_sqrt(int id) {
+   switch (id) {
+   case VAR_HORSESHOE: case VAR_POLAR: case VAR_HANDKERCHIEF: case VAR_HEART: case VAR_DISC:
+   case VAR_SPIRAL: case VAR_HYPERBOLIC: case VAR_DIAMOND: case VAR_EX: case VAR_JULIA:
+   case VAR_FISHEYE: case VAR_POWER: case VAR_RINGS: case VAR_FAN: case VAR_BLOB:
+   case VAR_FAN2: case VAR_RINGS2: case VAR_EYEFISH: case VAR_RADIAL_BLUR: case VAR_BLADE:
+   case VAR_SECANT2: case VAR_TWINTRIAN: case VAR_SUPER_SHAPE: case VAR_FLOWER:
+   case VAR_CONIC: case VAR_PARABOLA: case VAR_SCRY: case VAR_WEDGE: case VAR_WEDGE_SPH:
+   case VAR_WHORL:
+      return 1;
+   default:
+      return 0;
+   }
+}
+
 /* Packed parameters of variation `id`, in the order f3b_variations.cuh consumes them.
  * Returns the number of words written (== f3b_var_nparams[id]). */
 static int pack_var_params(const flam3_xform *x, int id, double *p) {
@@ -269,9 +285,11 @@ int f3b_chaos_enabled(const flam3_genome *cp, int nstd) {
 }
 
 static int pack_xform(const flam3_xform *x, uint32_t *w, size_t cap, size_t *pos) {
-   size_t o = *pos;
+   size_t o = (*pos + 3) & ~(size_t)3; /* records are 16-byte aligned */
    if (o + F3B_X_VARS > cap) return 1;
    uint32_t *r = w + o;
+   memset(r, 0, F3B_X_VARS * 4);
+   *pos = o;
    r[F3B_X_C00] = f2u(x->c[0][0]); r[F3B_X_C10] = f2u(x->c[1][0]); r[F3B_X_C20] = f2u(x->c[2][0]);
    r[F3B_X_C01] = f2u(x->c[0][1]); r[F3B_X_C11] = f2u(x->c[1][1]); r[F3B_X_C21] = f2u(x->c[2][1]);
    r[F3B_X_P00] = f2u(x->post[0][0]); r[F3B_X_P10] = f2u(x->post[1][0]); r[F3B_X_P20] = f2u(x->post[2][0]);
@@ -300,15 +318,18 @@ static int pack_xform(const flam3_xform *x, uint32_t *w, size_t cap, size_t *pos
          fprintf(stderr, "flam3_b200: internal error, variation %d packs %d params\n", id, np);
          return 1;
       }
-      if (o + 2 + (size_t)np > cap) return 1;
-      w[o++] = (uint32_t)id | ((uint32_t)np << 8);
+      const int len = (np + 1) & ~1; /* even length keeps records 8-byte aligned */
+      if (o + 2 + (size_t)len > cap) return 1;
+      w[o++] = (uint32_t)id | ((uint32_t)len << 8);
       w[o++] = f2u(x->var[id]);
-      for (int k = 0; k < np; k++) w[o++] = f2u(p[k]);
+      for (int k = 0; k < len; k++) w[o++] = k < np ? f2u(p[k]) : 0u;
       flags |= var_precalc_flags(id);
-      nv++;
+      if (var_needs_sqrt(id)) flags |= F3B_XF_NEED_SQRT;
+      nv += 2 + (unsigned)len;
    }
+   if (flags & F3B_XF_ANGLES) flags |= F3B_XF_NEED_SQRT; /* sina/cosa divide by it */
    r[F3B_X_FLAGS] = flags;
-   r[F3B_X_NVARS] = nv;
+   r[F3B_X_NVARS] = nv; /* total words of the variation list */
    *pos = o;
    return 0;
 }
@@ -351,7 +372,8 @@ int f3b_camera_setup(const flam3_genome *cp, const f3b_frame_geom *g, f3b_camera
 }
 
 int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_scalar,
-                    int cmap_size, uint32_t *w, size_t cap, size_t *used, int *count_is_alpha) {
+                    int cmap_size, int floor_adds, uint32_t *w, size_t cap, size_t *used,
+                    int *count_is_alpha) {
    const int has_final_slot = cp->final_xform_index >= 0;
    const int nstd = cp->num_xforms - has_final_slot;
    const int final_on = (cp->final_xform_enable == 1 && has_final_slot);
@@ -369,8 +391,11 @@ int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_
    const int rows = xaos ? nstd + 1 : 1;
    const int nxf = nstd + (final_on ? 1 : 0);
 
+   /* chooser rows are padded to a multiple of 4 entries with 16384 ("never picked") so the
+    * device compares four thresholds per LDS.128 */
+   const int stride = (nstd + 3) & ~3;
    size_t o = F3B_H_SIZE;
-   if (o + (size_t)rows * nstd + (size_t)nxf > cap) return 2;
+   if (o + (size_t)rows * stride + (size_t)nxf > cap) return 2;
    memset(w, 0, F3B_H_SIZE * 4);
    w[F3B_H_NSTD] = (uint32_t)nstd;
    w[F3B_H_FINAL] = final_on ? (uint32_t)nstd : (uint32_t)-1;
@@ -389,13 +414,12 @@ int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_
 
    /* chooser rows: row 0 plain weights, row i+1 conditioned on previous xform i */
    w[F3B_H_OFF_CHOOSER] = (uint32_t)o;
-   if (chooser_row(cp, nstd, -1, w + o)) return 1;
-   o += (size_t)nstd;
-   if (xaos)
-      for (int i = 0; i < nstd; i++) {
-         if (chooser_row(cp, nstd, i, w + o)) return 1;
-         o += (size_t)nstd;
-      }
+   w[F3B_H_CHOOSER_STRIDE] = (uint32_t)stride;
+   for (int r = 0; r < rows; r++) {
+      for (int j = nstd; j < stride; j++) w[o + j] = F3B_CHOOSER_GRAIN;
+      if (chooser_row(cp, nstd, r - 1, w + o)) return 1;
+      o += (size_t)stride;
+   }
 
    /* xform table + records. The reference indexes standard xforms 0..nstd-1 and assumes
     * the final xform, if any, is the last one (flam3.c:176). */
@@ -403,10 +427,12 @@ int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_
    uint32_t *tab = w + o;
    o += (size_t)nxf;
    for (int i = 0; i < nstd; i++) {
+      o = (o + 3) & ~(size_t)3;
       tab[i] = (uint32_t)o;
       if (pack_xform(&cp->xform[i], w, cap, &o)) return 2;
    }
    if (final_on) {
+      o = (o + 3) & ~(size_t)3;
       tab[nstd] = (uint32_t)o;
       if (pack_xform(&cp->xform[cp->final_xform_index], w, cap, &o)) return 2;
    }
@@ -419,8 +445,18 @@ int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_
     * by hit. Linear lookup blends alpha in floating point (rect.c:482-485), which the
     * truncating bucket add can round down, so it keeps its own count plane. */
    int alpha_ok = (cp->palette_mode != flam3_palette_mode_linear);
+   /* all hits add dmap[i] unchanged when every xform is fully visible (vis_adjusted == 1
+    * <=> opacity == 1) and the lookup is a plain step */
+   int plot_ready = (cp->palette_mode != flam3_palette_mode_linear);
+   for (int i = 0; i < cp->num_xforms; i++)
+      if (cp->xform[i].opacity != 1.0) plot_ready = 0;
+   w[F3B_H_PLOT] = plot_ready ? F3B_PLOT_READY : 0u;
    for (int j = 0; j < 256; j++) {
-      for (int k = 0; k < 4; k++) w[o + j * 4 + k] = f2u(cp->palette[j].color[k] * 255.0 * color_scalar);
+      for (int k = 0; k < 4; k++) {
+         double c = cp->palette[j].color[k] * 255.0 * color_scalar;
+         if (plot_ready && floor_adds) c = floor(c); /* what the integer bucket add keeps */
+         w[o + j * 4 + k] = f2u(c);
+      }
       if (cp->palette[j].color[3] * 255.0 * color_scalar != 255.0) alpha_ok = 0;
    }
    o += 256 * 4;

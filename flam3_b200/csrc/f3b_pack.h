@@ -37,22 +37,33 @@ enum {
    F3B_H_OFF_XFTAB,     /* u32 -> u32 word offset of each xform record [nxf] */
    F3B_H_OFF_PALETTE,   /* u32 -> float4 dmap[256] (16-byte aligned) */
    F3B_H_NXF,           /* u32 number of xform records (nstd + 1 if final present) */
+   F3B_H_PLOT,          /* u32 F3B_PLOT_*: what the bucket bump may skip */
+   F3B_H_CHOOSER_STRIDE, /* u32 entries per chooser row: nstd rounded up to 4, pad = 16384 */
    F3B_H_SIZE = 32      /* header padded to 32 words */
 };
 
+/* F3B_H_PLOT bits. READY: every xform has vis_adjusted == 1, the palette lookup is "step"
+ * and the dmap entries were already truncated on the host when the buckets are integer
+ * (bits 32/33), so a hit adds dmap[i] as is (rect.c:499-505 with p[3]==1). */
+#define F3B_PLOT_READY 1u
+
 /* xform record: word indices relative to the record start (all f32 unless noted) */
+/* Records start on a 16-byte boundary and the fixed part is laid out as five float4 groups
+ * so the device reads it with LDS.128. */
 enum {
    F3B_X_C00 = 0, F3B_X_C10, F3B_X_C20, /* tx = c00*x + c10*y + c20  (variations.c:2144) */
    F3B_X_C01, F3B_X_C11, F3B_X_C21,     /* ty = c01*x + c11*y + c21 */
-   F3B_X_P00, F3B_X_P10, F3B_X_P20,     /* post affine (variations.c:2383-2385) */
-   F3B_X_P01, F3B_X_P11, F3B_X_P21,
    F3B_X_SCOLOR,   /* color_speed * color          (variations.c:2139) */
    F3B_X_ONEMS,    /* 1 - color_speed */
    F3B_X_VIS,      /* vis_adjusted                 (variations.c:2030, interpolation.c:22) */
    F3B_X_FLAGS,    /* u32 F3B_XF_* */
    F3B_X_PREBLUR,  /* pre_blur weight              (variations.c:2149-2150) */
-   F3B_X_NVARS,    /* u32 number of active variations */
-   F3B_X_VARS      /* first variation record: {u32 id | nparams<<8, f32 weight, f32 params[nparams]} */
+   F3B_X_NVARS,    /* u32 total length in words of the variation records that follow */
+   F3B_X_P00, F3B_X_P10, F3B_X_P20,     /* post affine (variations.c:2383-2385) */
+   F3B_X_P01, F3B_X_P11, F3B_X_P21,
+   F3B_X_PAD0, F3B_X_PAD1,
+   F3B_X_VARS      /* first variation record: {u32 id | len<<8, f32 weight, f32 params[len]}, len =
+                      nparams rounded up to even */
 };
 
 #define F3B_XF_HAS_POST 1u
@@ -60,6 +71,7 @@ enum {
 #define F3B_XF_ANGLES 4u  /* precalc_sina/cosa = tx/r, ty/r  variations.c:2162 */
 #define F3B_XF_ATAN_YX 8u /* precalc_atanyx = atan2(ty,tx)   variations.c:2168 */
 #define F3B_XF_PREBLUR 16u
+#define F3B_XF_NEED_SQRT 32u /* some active variation reads precalc_sqrt (variations.c:2154) */
 
 /*
  * Number of packed parameter words per variation id (after id and weight). The order of

@@ -282,7 +282,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          if (blob_reserve(&blobs, F3B_MAX_BLOB_WORDS + 4)) goto done;
          size_t used = 0;
          int alpha_ok = 0;
-         const int prv = f3b_pack_sample(&cp, &cam, color_scalar, cmap_size,
+         const int prv = f3b_pack_sample(&cp, &cam, color_scalar, cmap_size, spec->bits != 64,
                                          blobs.words + blobs.used, F3B_MAX_BLOB_WORDS, &used,
                                          &alpha_ok);
          if (prv == 2) {

@@ -7,6 +7,12 @@
  * shared memory as flat word arrays (f3b_pack.h), host-side precalcs are already folded
  * into the packed parameters, and all math is single precision. The per-variation
  * parameter order is the one documented in f3b_pack.c:pack_var_params.
+ *
+ * The variation switch is split in two so the hot loop stays small in registers and
+ * instructions: the cheap, common variations (pure FMA / divide / sqrt / fast sincos) are
+ * inlined in f3b_apply_xform; everything that needs a libm-class routine (pow, exp, log,
+ * tan, sinh, fmod, atan2 inside the variation, ...) lives in the __noinline__
+ * f3b_var_slow and costs a call only when a genome actually uses it.
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -72,6 +78,8 @@ __device__ __forceinline__ void f3b_rng_seed(F3Rng &r, uint64_t seed, uint32_t s
    r.s3 = (uint32_t)(c >> 32) | 1u; /* never the all-zero state */
 }
 
+#define F3B_NOSPEC asm volatile("")
+
 /* badvalue(), variations.c:22 */
 __device__ __forceinline__ bool f3b_bad(float v) { return !(fabsf(v) <= 1e10f); }
 
@@ -84,152 +92,54 @@ __device__ __forceinline__ float f3b_gauss4(F3Rng &rng) {
    return a + b + c + d - 2.0f;
 }
 
-/*
- * Applies xform record `xf` (shared memory) to (px,py,pc). Returns true when the result is
- * a "bad value", in which case (qx,qy) are fresh uniform draws (variations.c:2391-2395).
- */
-__device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, float px, float py,
-                                                float pc, float &qx, float &qy, float &qc,
-                                                float &qvis, F3Rng &rng) {
-   const uint32_t *xu = reinterpret_cast<const uint32_t *>(xf);
-   qc = xf[F3B_X_SCOLOR] + xf[F3B_X_ONEMS] * pc;
-   qvis = xf[F3B_X_VIS];
 
-   float tx = xf[F3B_X_C00] * px + xf[F3B_X_C10] * py + xf[F3B_X_C20];
-   float ty = xf[F3B_X_C01] * px + xf[F3B_X_C11] * py + xf[F3B_X_C21];
-   const uint32_t flags = xu[F3B_X_FLAGS];
+/* sin/cos with a two-constant Cody-Waite reduction to [-pi, pi] and the SFU approximations
+ * there (|abs err| ~ 1e-6). Arguments beyond 2^14 fall back to the exact libm path. */
+__device__ __noinline__ void f3b_sincos_big(float x, float *s, float *c) { sincosf(x, s, c); }
 
-   if (flags & F3B_XF_PREBLUR) { /* var67_pre_blur, variations.c:1480 */
-      float g = xf[F3B_X_PREBLUR] * f3b_gauss4(rng);
-      float sa, ca;
-      sincosf(rng.u01() * 2.0f * F3B_PI, &sa, &ca);
-      tx += g * ca;
-      ty += g * sa;
-   }
+__device__ __forceinline__ void f3b_sincos(float x, float *s, float *c) {
+   if (fabsf(x) < 16384.0f) {
+      const float k = rintf(x * 0.15915494309189535f);
+      float r = fmaf(k, -6.28318548202514648f, x);
+      r = fmaf(k, 1.74845553e-07f, r);
+      *s = __sinf(r);
+      *c = __cosf(r);
+   } else
+      f3b_sincos_big(x, s, c);
+}
+__device__ __forceinline__ float f3b_sin(float x) {
+   float s, c;
+   f3b_sincos(x, &s, &c);
+   return s;
+}
+__device__ __forceinline__ float f3b_cos(float x) {
+   float s, c;
+   f3b_sincos(x, &s, &c);
+   return c;
+}
 
-   const float sumsq = tx * tx + ty * ty;
-   const float rad = sqrtf(sumsq);
-   float atan_xy = 0.0f, atan_yx = 0.0f, sina = 0.0f, cosa = 0.0f;
-   if (flags & F3B_XF_ATAN_XY) atan_xy = atan2f(tx, ty);
-   if (flags & F3B_XF_ANGLES) {
-      sina = tx / rad;
-      cosa = ty / rad;
-   }
-   if (flags & F3B_XF_ATAN_YX) atan_yx = atan2f(ty, tx);
+/* per-point quantities shared by the variations (flam3_iter_helper, private.h:102-119) */
+struct F3Pt {
+   float tx, ty, sumsq, rad, atan_xy, atan_yx, sina, cosa;
+};
 
+/* The heavyweight variations. `p` points at the packed parameters in shared memory. */
+__device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p, F3Pt pt,
+                                            F3Rng *rngp) {
+   const float tx = pt.tx, ty = pt.ty, sumsq = pt.sumsq, rad = pt.rad;
+   const float atan_xy = pt.atan_xy, atan_yx = pt.atan_yx, sina = pt.sina, cosa = pt.cosa;
+   F3Rng rng = *rngp;
    float p0 = 0.0f, p1 = 0.0f;
-   const int nvars = (int)xu[F3B_X_NVARS];
-   const float *v = xf + F3B_X_VARS;
-
-   for (int k = 0; k < nvars; k++) {
-      const uint32_t w0 = __float_as_uint(v[0]); /* id | nparams << 8 */
-      const uint32_t id = w0 & 0xffu;
-      const float w = v[1];
-      const float *p = v + 2;
-      switch (id) {
-      case 0: /* linear */
-         p0 += w * tx;
-         p1 += w * ty;
-         break;
-      case 1: /* sinusoidal */
-         p0 += w * sinf(tx);
-         p1 += w * sinf(ty);
-         break;
-      case 2: { /* spherical */
-         float r2 = w / (sumsq + F3B_EPS);
-         p0 += r2 * tx;
-         p1 += r2 * ty;
-      } break;
-      case 3: { /* swirl */
-         float s, c;
-         sincosf(sumsq, &s, &c);
-         p0 += w * (s * tx - c * ty);
-         p1 += w * (c * tx + s * ty);
-      } break;
-      case 4: { /* horseshoe */
-         float r = w / (rad + F3B_EPS);
-         p0 += (tx - ty) * (tx + ty) * r;
-         p1 += 2.0f * tx * ty * r;
-      } break;
-      case 5: /* polar */
-         p0 += w * (atan_xy * F3B_1_PI);
-         p1 += w * (rad - 1.0f);
-         break;
-      case 6: /* handkerchief */
-         p0 += w * rad * sinf(atan_xy + rad);
-         p1 += w * rad * cosf(atan_xy - rad);
-         break;
-      case 7: { /* heart */
-         float s, c;
-         sincosf(rad * atan_xy, &s, &c);
-         float r = w * rad;
-         p0 += r * s;
-         p1 -= r * c;
-      } break;
-      case 8: { /* disc */
-         float a = atan_xy * F3B_1_PI, s, c;
-         sincosf(F3B_PI * rad, &s, &c);
-         p0 += w * s * a;
-         p1 += w * c * a;
-      } break;
-      case 9: { /* spiral */
-         float r = rad + F3B_EPS, s, c;
-         float r1 = w / r;
-         sincosf(r, &s, &c);
-         p0 += r1 * (cosa + s);
-         p1 += r1 * (sina - c);
-      } break;
-      case 10: { /* hyperbolic */
-         float r = rad + F3B_EPS;
-         p0 += w * sina / r;
-         p1 += w * cosa * r;
-      } break;
-      case 11: { /* diamond */
-         float s, c;
-         sincosf(rad, &s, &c);
-         p0 += w * sina * c;
-         p1 += w * cosa * s;
-      } break;
-      case 12: { /* ex */
-         float n0 = sinf(atan_xy + rad);
-         float n1 = cosf(atan_xy - rad);
-         float m0 = n0 * n0 * n0 * rad;
-         float m1 = n1 * n1 * n1 * rad;
-         p0 += w * (m0 + m1);
-         p1 += w * (m0 - m1);
-      } break;
-      case 13: { /* julia */
-         float a = 0.5f * atan_xy, s, c;
-         if (rng.bit()) a += F3B_PI;
-         float r = w * sqrtf(rad);
-         sincosf(a, &s, &c);
-         p0 += r * c;
-         p1 += r * s;
-      } break;
-      case 14: { /* bent */
-         float nx = tx < 0.0f ? tx * 2.0f : tx;
-         float ny = ty < 0.0f ? ty * 0.5f : ty;
-         p0 += w * nx;
-         p1 += w * ny;
-      } break;
-      case 15: { /* waves: p = {c10, dx2, c11, dy2} */
-         p0 += w * (tx + p[0] * sinf(ty * p[1]));
-         p1 += w * (ty + p[2] * sinf(tx * p[3]));
-      } break;
-      case 16: { /* fisheye (x/y swap is intentional in the reference) */
-         float r = 2.0f * w / (rad + 1.0f);
-         p0 += r * ty;
-         p1 += r * tx;
-      } break;
+   switch (id) {
       case 17: { /* popcorn: p = {c20, c21} */
          float dx = tanf(3.0f * ty);
          float dy = tanf(3.0f * tx);
-         p0 += w * (tx + p[0] * sinf(dx));
-         p1 += w * (ty + p[1] * sinf(dy));
+         p0 += w * (tx + p[0] * f3b_sin(dx));
+         p1 += w * (ty + p[1] * f3b_sin(dy));
       } break;
       case 18: { /* exponential */
          float dx = w * expf(tx - 1.0f), s, c;
-         sincosf(F3B_PI * ty, &s, &c);
+         f3b_sincos(F3B_PI * ty, &s, &c);
          p0 += dx * c;
          p1 += dx * s;
       } break;
@@ -240,7 +150,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
       } break;
       case 20: { /* cosine */
          float s, c;
-         sincosf(tx * F3B_PI, &s, &c);
+         f3b_sincos(tx * F3B_PI, &s, &c);
          p0 += w * (c * coshf(ty));
          p1 -= w * (s * sinhf(ty));
       } break;
@@ -253,21 +163,21 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
       case 22: { /* fan: p = {dx, dy, dx2} */
          float a = atan_xy, s, c;
          a += (fmodf(a + p[1], p[0]) > p[2]) ? -p[2] : p[2];
-         sincosf(a, &s, &c);
+         f3b_sincos(a, &s, &c);
          float r = w * rad;
          p0 += r * c;
          p1 += r * s;
       } break;
       case 23: { /* blob: p = {low, high-low, waves} */
-         float r = rad * (p[0] + p[1] * (0.5f + 0.5f * sinf(p[2] * atan_xy)));
+         float r = rad * (p[0] + p[1] * (0.5f + 0.5f * f3b_sin(p[2] * atan_xy)));
          p0 += w * sina * r;
          p1 += w * cosa * r;
       } break;
       case 24: { /* pdj: p = {a,b,c,d} */
-         float nx1 = cosf(p[1] * tx);
-         float nx2 = sinf(p[2] * tx);
-         float ny1 = sinf(p[0] * ty);
-         float ny2 = cosf(p[3] * ty);
+         float nx1 = f3b_cos(p[1] * tx);
+         float nx2 = f3b_sin(p[2] * tx);
+         float ny1 = f3b_sin(p[0] * ty);
+         float ny2 = f3b_cos(p[3] * ty);
          p0 += w * (ny1 - nx1);
          p1 += w * (nx2 - ny2);
       } break;
@@ -275,40 +185,14 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float a = atan_xy, s, c;
          float t = a + p[1] - p[0] * truncf((a + p[1]) / p[0]);
          a = (t > p[2]) ? a - p[2] : a + p[2];
-         sincosf(a, &s, &c);
+         f3b_sincos(a, &s, &c);
          float r = w * rad;
          p0 += r * s;
          p1 += r * c;
       } break;
-      case 26: { /* rings2: p = {dx} */
-         float dx = p[0];
-         float r = rad;
-         r += -2.0f * dx * truncf((r + dx) / (2.0f * dx)) + r * (1.0f - dx);
-         p0 += w * sina * r;
-         p1 += w * cosa * r;
-      } break;
-      case 27: { /* eyefish */
-         float r = (w * 2.0f) / (rad + 1.0f);
-         p0 += r * tx;
-         p1 += r * ty;
-      } break;
-      case 28: { /* bubble */
-         float r = w / (0.25f * sumsq + 1.0f);
-         p0 += r * tx;
-         p1 += r * ty;
-      } break;
-      case 29: /* cylinder */
-         p0 += w * sinf(tx);
-         p1 += w * ty;
-         break;
-      case 30: { /* perspective: p = {dist, vsin, vfcos} */
-         float t = 1.0f / (p[0] - ty * p[1]);
-         p0 += w * p[0] * tx * t;
-         p1 += w * p[2] * ty * t;
-      } break;
       case 31: { /* noise */
          float s, c;
-         sincosf(rng.u01() * 2.0f * F3B_PI, &s, &c);
+         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &s, &c);
          float r = w * rng.u01();
          p0 += tx * r * c;
          p1 += ty * r * s;
@@ -317,7 +201,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float t_rnd = truncf(p[2] * rng.u01());
          float a = (atan_yx + 2.0f * F3B_PI * t_rnd) / p[0], s, c;
          float r = w * powf(sumsq, p[1]);
-         sincosf(a, &s, &c);
+         f3b_sincos(a, &s, &c);
          p0 += r * c;
          p1 += r * s;
       } break;
@@ -326,28 +210,28 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float a, s, c;
          if ((t_rnd & 1) == 0) a = (2.0f * F3B_PI * (float)t_rnd + atan_yx) / p[0];
          else a = (2.0f * F3B_PI * (float)t_rnd - atan_yx) / p[0];
-         sincosf(a, &s, &c);
+         f3b_sincos(a, &s, &c);
          float r = w * powf(sumsq, p[1]);
          p0 += r * c;
          p1 += r * s;
       } break;
       case 34: { /* blur */
          float s, c;
-         sincosf(rng.u01() * 2.0f * F3B_PI, &s, &c);
+         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &s, &c);
          float r = w * rng.u01();
          p0 += r * c;
          p1 += r * s;
       } break;
       case 35: { /* gaussian_blur */
          float s, c;
-         sincosf(rng.u01() * 2.0f * F3B_PI, &s, &c);
+         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &s, &c);
          float r = w * f3b_gauss4(rng);
          p0 += r * c;
          p1 += r * s;
       } break;
       case 36: { /* radial_blur: p = {spinvar, zoomvar} */
          float g = w * f3b_gauss4(rng), s, c;
-         sincosf(atan_yx + p[0] * g, &s, &c);
+         f3b_sincos(atan_yx + p[0] * g, &s, &c);
          float rz = p[1] * g - 1.0f;
          p0 += rad * c + rz * tx;
          p1 += rad * s + rz * ty;
@@ -356,7 +240,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          int sl = (int)(rng.u01() * p[0] + 0.5f);
          float a = p[1] + 2.0f * F3B_PI * ((float)sl + rng.u01() * p[2]) / p[0], s, c;
          float r = w * rng.u01();
-         sincosf(a, &s, &c);
+         f3b_sincos(a, &s, &c);
          p0 += r * c;
          p1 += r * s;
       } break;
@@ -365,83 +249,58 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float b = p[1];
          float phi = atan_yx - b * floorf(atan_yx / b);
          if (phi > 0.5f * b) phi -= b;
-         float amp = p[2] * (1.0f / (cosf(phi) + F3B_EPS) - 1.0f) + p[3];
+         float amp = p[2] * (1.0f / (f3b_cos(phi) + F3B_EPS) - 1.0f) + p[3];
          amp /= (r_factor + F3B_EPS);
          p0 += w * tx * amp;
          p1 += w * ty * amp;
       } break;
-      case 39: { /* curl: p = {c1, c2} */
-         float re = 1.0f + p[0] * tx + p[1] * (tx * tx - ty * ty);
-         float im = p[0] * ty + 2.0f * p[1] * tx * ty;
-         float r = w / (re * re + im * im);
-         p0 += (tx * re + ty * im) * r;
-         p1 += (ty * re - tx * im) * r;
-      } break;
-      case 40: { /* rectangles: p = {x, y} */
-         if (p[0] == 0.0f) p0 += w * tx;
-         else p0 += w * ((2.0f * floorf(tx / p[0]) + 1.0f) * p[0] - tx);
-         if (p[1] == 0.0f) p1 += w * ty;
-         else p1 += w * ((2.0f * floorf(ty / p[1]) + 1.0f) * p[1] - ty);
-      } break;
       case 41: { /* arch (weight used non-linearly, as in the reference) */
          float s, c;
-         sincosf(rng.u01() * w * F3B_PI, &s, &c);
+         f3b_sincos(rng.u01() * w * F3B_PI, &s, &c);
          p0 += w * s;
          p1 += w * (s * s) / c;
       } break;
       case 42: /* tangent */
-         p0 += w * sinf(tx) / cosf(ty);
+         p0 += w * f3b_sin(tx) / f3b_cos(ty);
          p1 += w * tanf(ty);
          break;
-      case 43: { /* square */
-         float a = rng.u01();
-         float b = rng.u01();
-         p0 += w * (a - 0.5f);
-         p1 += w * (b - 0.5f);
-      } break;
       case 44: { /* rays */
          float ang = w * rng.u01() * F3B_PI;
          float r = w / (sumsq + F3B_EPS);
          float tanr = w * tanf(ang) * r;
-         p0 += tanr * cosf(tx);
-         p1 += tanr * sinf(ty);
+         p0 += tanr * f3b_cos(tx);
+         p1 += tanr * f3b_sin(ty);
       } break;
       case 45: { /* blade */
          float r = rng.u01() * w * rad, s, c;
-         sincosf(r, &s, &c);
+         f3b_sincos(r, &s, &c);
          p0 += w * tx * (c + s);
          p1 += w * tx * (c - s);
       } break;
       case 46: { /* secant2 */
-         float cr = cosf(w * rad);
+         float cr = f3b_cos(w * rad);
          float icr = 1.0f / cr;
          p0 += w * tx;
          p1 += (cr < 0.0f) ? w * (icr + 1.0f) : w * (icr - 1.0f);
       } break;
       case 47: { /* twintrian */
          float r = rng.u01() * w * rad, s, c;
-         sincosf(r, &s, &c);
+         f3b_sincos(r, &s, &c);
          float diff = log10f(s * s) + c;
          if (f3b_bad(diff)) diff = -30.0f;
          p0 += w * tx * diff;
          p1 += w * tx * (diff - s * F3B_PI);
       } break;
-      case 48: { /* cross */
-         float s = tx * tx - ty * ty;
-         float r = w * sqrtf(1.0f / (s * s + F3B_EPS));
-         p0 += tx * r;
-         p1 += ty * r;
-      } break;
       case 49: { /* disc2: p = {timespi, sinadd, cosadd} */
          float s, c;
-         sincosf(p[0] * (tx + ty), &s, &c);
+         f3b_sincos(p[0] * (tx + ty), &s, &c);
          float r = w * atan_xy * F3B_1_PI;
          p0 += (s + p[2]) * r;
          p1 += (c + p[1]) * r;
       } break;
       case 50: { /* super_shape: p = {pm_4, n2, n3, rnd, holes, pneg1_n1} */
          float st, ct;
-         sincosf(p[0] * atan_yx + F3B_PI_4, &st, &ct);
+         f3b_sincos(p[0] * atan_yx + F3B_PI_4, &st, &ct);
          float t1 = powf(fabsf(ct), p[1]);
          float t2 = powf(fabsf(st), p[2]);
          float r = w * ((p[3] * rng.u01() + (1.0f - p[3]) * rad) - p[4]) * powf(t1 + t2, p[5]) /
@@ -450,7 +309,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          p1 += r * ty;
       } break;
       case 51: { /* flower: p = {petals, holes} */
-         float r = w * (rng.u01() - p[1]) * cosf(p[0] * atan_yx) / rad;
+         float r = w * (rng.u01() - p[1]) * f3b_cos(p[0] * atan_yx) / rad;
          p0 += r * tx;
          p1 += r * ty;
       } break;
@@ -462,17 +321,11 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
       } break;
       case 53: { /* parabola: p = {height, width} */
          float s, c;
-         sincosf(rad, &s, &c);
+         f3b_sincos(rad, &s, &c);
          float a = rng.u01();
          float b = rng.u01();
          p0 += p[0] * w * s * s * a;
          p1 += p[1] * w * c * b;
-      } break;
-      case 54: { /* bent2: p = {x, y} */
-         float nx = tx < 0.0f ? tx * p[0] : tx;
-         float ny = ty < 0.0f ? ty * p[1] : ty;
-         p0 += w * nx;
-         p1 += w * ny;
       } break;
       case 55: { /* bipolar: p = {ps = -pi/2 * shift} */
          float t = sumsq + 1.0f;
@@ -507,13 +360,6 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
             }
          }
       } break;
-      case 57: { /* butterfly; 4/sqrt(3*pi) */
-         float wx = w * 1.3029400317411197908970256609023f;
-         float y2 = ty * 2.0f;
-         float r = wx * sqrtf(fabsf(ty * tx) / (F3B_EPS + tx * tx + y2 * y2));
-         p0 += r * tx;
-         p1 += r * y2;
-      } break;
       case 58: { /* cell: p = {size, 1/size} */
          int x = (int)floorf(tx * p[1]);
          int y = (int)floorf(ty * p[1]);
@@ -533,7 +379,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float lnr = 0.5f * logf(sumsq), s, c;
          float ang = p[1] * atan_yx + p[2] * lnr + p[0] * floorf(p[3] * rng.u01());
          float m = w * expf(p[1] * lnr - p[2] * atan_yx);
-         sincosf(ang, &s, &c);
+         f3b_sincos(ang, &s, &c);
          p0 += m * c;
          p1 += m * s;
       } break;
@@ -548,7 +394,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float a1 = logf(xmax + sqrtf(xmax - 1.0f));
          float a2 = -acosf(tx / xmax);
          float ww = w / 11.57034632f, snv, csv;
-         sincosf(a1, &snv, &csv);
+         f3b_sincos(a1, &snv, &csv);
          float snhu = sinhf(a2), cshu = coshf(a2);
          if (ty > 0.0f) snv = -snv;
          p0 += ww * cshu * csv;
@@ -572,14 +418,14 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float lnr = 0.5f * logf(sumsq), s, c;
          float m = w * expf(p[0] * lnr - p[1] * atan_yx);
          float n = p[0] * atan_yx + p[1] * lnr;
-         sincosf(n, &s, &c);
+         f3b_sincos(n, &s, &c);
          p0 += m * c;
          p1 += m * s;
       } break;
       case 64: { /* foci */
          float expx = expf(tx) * 0.5f;
          float expnx = 0.25f / expx, s, c;
-         sincosf(ty, &s, &c);
+         f3b_sincos(ty, &s, &c);
          float t = w / (expx + expnx - c);
          p0 += t * (expx - expnx);
          p1 += t * s;
@@ -590,7 +436,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float r = sqrtf(x * x + y * y);
          if (r < w) {
             float a = atan2f(y, x) + p[0] + p[2] * (w - r), s, c;
-            sincosf(a, &s, &c);
+            f3b_sincos(a, &s, &c);
             r = w * r;
             p0 += r * c + p[3];
             p1 += r * s - p[4];
@@ -600,18 +446,6 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
             p1 += r * y - p[4];
          }
       } break;
-      case 66: { /* loonie */
-         float w2 = w * w;
-         if (sumsq < w2) {
-            float r = w * sqrtf(w2 / sumsq - 1.0f);
-            p0 += r * tx;
-            p1 += r * ty;
-         } else {
-            p0 += w * tx;
-            p1 += w * ty;
-         }
-      } break;
-      /* 67 pre_blur is applied before the loop and never packed as a loop entry */
       case 68: { /* modulus: p = {x, y} */
          float xr = 2.0f * p[0], yr = 2.0f * p[1];
          if (tx > p[0]) p0 += w * (-p[0] + fmodf(tx + p[0], xr));
@@ -623,8 +457,8 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
       } break;
       case 69: { /* oscilloscope: p = {2*pi*freq, amplitude, separation, damping} */
          float t;
-         if (p[3] == 0.0f) t = p[1] * cosf(p[0] * tx) + p[2];
-         else t = p[1] * expf(-fabsf(tx) * p[3]) * cosf(p[0] * tx) + p[2];
+         if (p[3] == 0.0f) t = p[1] * f3b_cos(p[0] * tx) + p[2];
+         else t = p[1] * expf(-fabsf(tx) * p[3]) * f3b_cos(p[0] * tx) + p[2];
          p0 += w * tx;
          if (fabsf(ty) <= t) p1 -= w * ty;
          else p1 += w * ty;
@@ -635,41 +469,20 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          p1 += p2v * 0.5f * logf(sumsq);
       } break;
       case 71: { /* popcorn2: p = {x, y, c} */
-         p0 += w * (tx + p[0] * sinf(tanf(ty * p[2])));
-         p1 += w * (ty + p[1] * sinf(tanf(tx * p[2])));
-      } break;
-      case 72: { /* scry */
-         float r = 1.0f / (rad * (sumsq + 1.0f / (w + F3B_EPS)));
-         p0 += tx * r;
-         p1 += ty * r;
-      } break;
-      case 73: { /* separation: p = {x^2, xinside, y^2, yinside} */
-         if (tx > 0.0f) p0 += w * (sqrtf(tx * tx + p[0]) - tx * p[1]);
-         else p0 -= w * (sqrtf(tx * tx + p[0]) + tx * p[1]);
-         if (ty > 0.0f) p1 += w * (sqrtf(ty * ty + p[2]) - ty * p[3]);
-         else p1 -= w * (sqrtf(ty * ty + p[2]) + ty * p[3]);
+         p0 += w * (tx + p[0] * f3b_sin(tanf(ty * p[2])));
+         p1 += w * (ty + p[1] * f3b_sin(tanf(tx * p[2])));
       } break;
       case 74: { /* split: p = {xsize*pi, ysize*pi} */
-         if (cosf(tx * p[0]) >= 0.0f) p1 += w * ty;
+         if (f3b_cos(tx * p[0]) >= 0.0f) p1 += w * ty;
          else p1 -= w * ty;
-         if (cosf(ty * p[1]) >= 0.0f) p0 += w * tx;
+         if (f3b_cos(ty * p[1]) >= 0.0f) p0 += w * tx;
          else p0 -= w * tx;
-      } break;
-      case 75: { /* splits: p = {x, y} */
-         p0 += w * (tx >= 0.0f ? tx + p[0] : tx - p[0]);
-         p1 += w * (ty >= 0.0f ? ty + p[1] : ty - p[1]);
-      } break;
-      case 76: { /* stripes: p = {1-space, warp} */
-         float roundx = floorf(tx + 0.5f);
-         float offx = tx - roundx;
-         p0 += w * (offx * p[0] + roundx);
-         p1 += w * (ty + offx * offx * p[1]);
       } break;
       case 77: { /* wedge: p = {angle, hole, count, swirl, comp_fac} */
          float a = atan_yx + p[3] * rad, s, c;
          float cc = floorf((p[2] * a + F3B_PI) * F3B_1_PI * 0.5f);
          a = a * p[4] + cc * p[0];
-         sincosf(a, &s, &c);
+         f3b_sincos(a, &s, &c);
          float r = w * (rad + p[1]);
          p0 += r * c;
          p1 += r * s;
@@ -680,7 +493,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float a = (atan_yx + 2.0f * F3B_PI * (float)t_rnd) / p[2];
          float cc = floorf((p[3] * a + F3B_PI) * F3B_1_PI * 0.5f);
          a = a * p[4] + cc * p[5];
-         sincosf(a, &s, &c);
+         f3b_sincos(a, &s, &c);
          p0 += r * c;
          p1 += r * s;
       } break;
@@ -689,7 +502,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float a = atan_yx + p[3] * r;
          float cc = floorf((p[2] * a + F3B_PI) * F3B_1_PI * 0.5f);
          a = a * p[4] + cc * p[0];
-         sincosf(a, &s, &c);
+         f3b_sincos(a, &s, &c);
          r = w * (r + p[1]);
          p0 += r * c;
          p1 += r * s;
@@ -698,17 +511,17 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float a, s, c;
          if (rad < w) a = atan_yx + p[0] / (w - rad);
          else a = atan_yx + p[1] / (w - rad);
-         sincosf(a, &s, &c);
+         f3b_sincos(a, &s, &c);
          p0 += w * rad * c;
          p1 += w * rad * s;
       } break;
       case 81: { /* waves2: p = {freqx, scalex, freqy, scaley} */
-         p0 += w * (tx + p[1] * sinf(ty * p[0]));
-         p1 += w * (ty + p[3] * sinf(tx * p[2]));
+         p0 += w * (tx + p[1] * f3b_sin(ty * p[0]));
+         p1 += w * (ty + p[3] * f3b_sin(tx * p[2]));
       } break;
       case 82: { /* exp */
          float e = expf(tx), s, c;
-         sincosf(ty, &s, &c);
+         f3b_sincos(ty, &s, &c);
          p0 += w * e * c;
          p1 += w * e * s;
       } break;
@@ -718,87 +531,87 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          break;
       case 84: { /* sin */
          float s, c;
-         sincosf(tx, &s, &c);
+         f3b_sincos(tx, &s, &c);
          p0 += w * s * coshf(ty);
          p1 += w * c * sinhf(ty);
       } break;
       case 85: { /* cos */
          float s, c;
-         sincosf(tx, &s, &c);
+         f3b_sincos(tx, &s, &c);
          p0 += w * c * coshf(ty);
          p1 -= w * s * sinhf(ty);
       } break;
       case 86: { /* tan */
          float s, c;
-         sincosf(2.0f * tx, &s, &c);
+         f3b_sincos(2.0f * tx, &s, &c);
          float den = 1.0f / (c + coshf(2.0f * ty));
          p0 += w * den * s;
          p1 += w * den * sinhf(2.0f * ty);
       } break;
       case 87: { /* sec */
          float s, c;
-         sincosf(tx, &s, &c);
-         float den = 2.0f / (cosf(2.0f * tx) + coshf(2.0f * ty));
+         f3b_sincos(tx, &s, &c);
+         float den = 2.0f / (f3b_cos(2.0f * tx) + coshf(2.0f * ty));
          p0 += w * den * c * coshf(ty);
          p1 += w * den * s * sinhf(ty);
       } break;
       case 88: { /* csc */
          float s, c;
-         sincosf(tx, &s, &c);
-         float den = 2.0f / (coshf(2.0f * ty) - cosf(2.0f * tx));
+         f3b_sincos(tx, &s, &c);
+         float den = 2.0f / (coshf(2.0f * ty) - f3b_cos(2.0f * tx));
          p0 += w * den * s * coshf(ty);
          p1 -= w * den * c * sinhf(ty);
       } break;
       case 89: { /* cot */
          float s, c;
-         sincosf(2.0f * tx, &s, &c);
+         f3b_sincos(2.0f * tx, &s, &c);
          float den = 1.0f / (coshf(2.0f * ty) - c);
          p0 += w * den * s;
          p1 -= w * den * sinhf(2.0f * ty);
       } break;
       case 90: { /* sinh */
          float s, c;
-         sincosf(ty, &s, &c);
+         f3b_sincos(ty, &s, &c);
          p0 += w * sinhf(tx) * c;
          p1 += w * coshf(tx) * s;
       } break;
       case 91: { /* cosh */
          float s, c;
-         sincosf(ty, &s, &c);
+         f3b_sincos(ty, &s, &c);
          p0 += w * coshf(tx) * c;
          p1 += w * sinhf(tx) * s;
       } break;
       case 92: { /* tanh */
          float s, c;
-         sincosf(2.0f * ty, &s, &c);
+         f3b_sincos(2.0f * ty, &s, &c);
          float den = 1.0f / (c + coshf(2.0f * tx));
          p0 += w * den * sinhf(2.0f * tx);
          p1 += w * den * s;
       } break;
       case 93: { /* sech */
          float s, c;
-         sincosf(ty, &s, &c);
-         float den = 2.0f / (cosf(2.0f * ty) + coshf(2.0f * tx));
+         f3b_sincos(ty, &s, &c);
+         float den = 2.0f / (f3b_cos(2.0f * ty) + coshf(2.0f * tx));
          p0 += w * den * c * coshf(tx);
          p1 -= w * den * s * sinhf(tx);
       } break;
       case 94: { /* csch */
          float s, c;
-         sincosf(ty, &s, &c);
-         float den = 2.0f / (coshf(2.0f * tx) - cosf(2.0f * ty));
+         f3b_sincos(ty, &s, &c);
+         float den = 2.0f / (coshf(2.0f * tx) - f3b_cos(2.0f * ty));
          p0 += w * den * sinhf(tx) * c;
          p1 -= w * den * coshf(tx) * s;
       } break;
       case 95: { /* coth */
          float s, c;
-         sincosf(2.0f * ty, &s, &c);
+         f3b_sincos(2.0f * ty, &s, &c);
          float den = 1.0f / (coshf(2.0f * tx) - c);
          p0 += w * den * sinhf(2.0f * tx);
          p1 += w * den * s;
       } break;
       case 96: { /* auger: p = {sym, weight, freq, scale} */
-         float s = sinf(p[2] * tx);
-         float t = sinf(p[2] * ty);
+         float s = f3b_sin(p[2] * tx);
+         float t = f3b_sin(p[2] * ty);
          float dy = ty + p[1] * (p[3] * s * 0.5f + fabsf(ty) * s);
          float dx = tx + p[1] * (p[3] * t * 0.5f + fabsf(tx) * t);
          p0 += w * (tx + p[0] * (dx - tx));
@@ -808,11 +621,306 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          float xpw = tx + w, xmw = tx - w;
          float avgr = w * p[0] * sqrtf(sqrtf(ty * ty + xpw * xpw) / sqrtf(ty * ty + xmw * xmw));
          float avga = (atan2f(ty, xmw) - atan2f(ty, xpw)) * 0.5f, s, c;
-         sincosf(avga, &s, &c);
+         f3b_sincos(avga, &s, &c);
          p0 += avgr * c;
          p1 += avgr * s;
       } break;
+   default:
+      break;
+   }
+   *rngp = rng;
+   return make_float2(p0, p1);
+}
+
+/*
+ * Applies xform record `xf` (shared memory, 16-byte aligned, layout f3b_pack.h) to
+ * (px,py,pc). Returns true when the result is a "bad value", in which case (qx,qy) are
+ * fresh uniform draws (variations.c:2391-2395).
+ */
+__device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, float px, float py,
+                                                float pc, float &qx, float &qy, float &qc,
+                                                float &qvis, F3Rng &rng) {
+   const float4 a0 = *reinterpret_cast<const float4 *>(xf);      /* c00 c10 c20 c01 */
+   const float4 a1 = *reinterpret_cast<const float4 *>(xf + 4);  /* c11 c21 scolor 1-s */
+   const float4 a2 = *reinterpret_cast<const float4 *>(xf + 8);  /* vis flags preblur nvars */
+   qc = fmaf(a1.w, pc, a1.z);
+   qvis = a2.x;
+   const uint32_t flags = __float_as_uint(a2.y);
+
+   F3Pt pt;
+   pt.tx = fmaf(a0.x, px, fmaf(a0.y, py, a0.z));
+   pt.ty = fmaf(a0.w, px, fmaf(a1.x, py, a1.y));
+
+   if (flags & F3B_XF_PREBLUR) { /* var67_pre_blur, variations.c:1480 */
+      const float g = a2.z * f3b_gauss4(rng);
+      float sa, ca;
+      f3b_sincos(rng.u01() * 2.0f * F3B_PI, &sa, &ca);
+      pt.tx += g * ca;
+      pt.ty += g * sa;
+   }
+
+   pt.sumsq = pt.tx * pt.tx + pt.ty * pt.ty;
+   pt.rad = 0.0f;
+   pt.atan_xy = pt.atan_yx = pt.sina = pt.cosa = 0.0f;
+   if (flags & F3B_XF_NEED_SQRT) pt.rad = sqrtf(pt.sumsq);
+   if (flags & F3B_XF_ATAN_XY) pt.atan_xy = atan2f(pt.tx, pt.ty);
+   if (flags & F3B_XF_ANGLES) {
+      pt.sina = pt.tx / pt.rad;
+      pt.cosa = pt.ty / pt.rad;
+   }
+   if (flags & F3B_XF_ATAN_YX) pt.atan_yx = atan2f(pt.ty, pt.tx);
+
+   float tx = pt.tx, ty = pt.ty, sumsq = pt.sumsq, rad = pt.rad;
+   float atan_xy = pt.atan_xy, sina = pt.sina, cosa = pt.cosa;
+   float p0 = 0.0f, p1 = 0.0f;
+   /* variation records: {id | len << 8, weight, params[len]} with len even, so every
+    * record starts 8-byte aligned; a2.w holds the total length of the list in words */
+   const float *v = xf + F3B_X_VARS;
+   const float *const vend = v + __float_as_uint(a2.w);
+
+   while (v < vend) {
+      /* Opaque redefinition of the per-point values: without it the compiler treats them as
+       * invariant in this loop and hoists the arithmetic of EVERY case (range reductions,
+       * reciprocals, ...) in front of it, to be executed for every point whatever
+       * variations the xform uses (54 of 272 instructions per iteration, profiles/r01). */
+      asm volatile("" : "+f"(tx), "+f"(ty), "+f"(sumsq), "+f"(rad), "+f"(atan_xy), "+f"(sina),
+                        "+f"(cosa));
+      const float2 hw = *reinterpret_cast<const float2 *>(v);
+      const uint32_t w0 = __float_as_uint(hw.x);
+      const uint32_t id = w0 & 0xffu;
+      const float w = hw.y;
+      const float *p = v + 2;
+      v += 2 + (w0 >> 8);
+      /* the two variations almost every flame uses are tested first; the rest go through
+       * the switch. F3B_NOSPEC keeps the compiler from if-converting the small cases into
+       * straight-line code that would execute all of them for every point. */
+      if (id == 0) { /* linear */
+         p0 = fmaf(w, tx, p0);
+         p1 = fmaf(w, ty, p1);
+         continue;
+      }
+      if (id == 2) { /* spherical */
+         const float r2 = w / (sumsq + F3B_EPS);
+         p0 = fmaf(r2, tx, p0);
+         p1 = fmaf(r2, ty, p1);
+         continue;
+      }
+      switch (id) {
+      case 1: /* sinusoidal */
+         F3B_NOSPEC;
+         p0 += w * f3b_sin(tx);
+         p1 += w * f3b_sin(ty);
+         break;
+      case 3: { /* swirl */
+         F3B_NOSPEC;
+         float s, c;
+         f3b_sincos(sumsq, &s, &c);
+         p0 += w * (s * tx - c * ty);
+         p1 += w * (c * tx + s * ty);
+      } break;
+      case 4: { /* horseshoe */
+         F3B_NOSPEC;
+         float r = w / (rad + F3B_EPS);
+         p0 += (tx - ty) * (tx + ty) * r;
+         p1 += 2.0f * tx * ty * r;
+      } break;
+      case 5: /* polar */
+         F3B_NOSPEC;
+         p0 += w * (atan_xy * F3B_1_PI);
+         p1 += w * (rad - 1.0f);
+         break;
+      case 6: /* handkerchief */
+         F3B_NOSPEC;
+         p0 += w * rad * f3b_sin(atan_xy + rad);
+         p1 += w * rad * f3b_cos(atan_xy - rad);
+         break;
+      case 7: { /* heart */
+         F3B_NOSPEC;
+         float s, c;
+         f3b_sincos(rad * atan_xy, &s, &c);
+         float r = w * rad;
+         p0 += r * s;
+         p1 -= r * c;
+      } break;
+      case 8: { /* disc */
+         F3B_NOSPEC;
+         float a = atan_xy * F3B_1_PI, s, c;
+         f3b_sincos(F3B_PI * rad, &s, &c);
+         p0 += w * s * a;
+         p1 += w * c * a;
+      } break;
+      case 9: { /* spiral */
+         F3B_NOSPEC;
+         float r = rad + F3B_EPS, s, c;
+         float r1 = w / r;
+         f3b_sincos(r, &s, &c);
+         p0 += r1 * (cosa + s);
+         p1 += r1 * (sina - c);
+      } break;
+      case 10: { /* hyperbolic */
+         F3B_NOSPEC;
+         float r = rad + F3B_EPS;
+         p0 += w * sina / r;
+         p1 += w * cosa * r;
+      } break;
+      case 11: { /* diamond */
+         F3B_NOSPEC;
+         float s, c;
+         f3b_sincos(rad, &s, &c);
+         p0 += w * sina * c;
+         p1 += w * cosa * s;
+      } break;
+      case 12: { /* ex */
+         F3B_NOSPEC;
+         float n0 = f3b_sin(atan_xy + rad);
+         float n1 = f3b_cos(atan_xy - rad);
+         float m0 = n0 * n0 * n0 * rad;
+         float m1 = n1 * n1 * n1 * rad;
+         p0 += w * (m0 + m1);
+         p1 += w * (m0 - m1);
+      } break;
+      case 13: { /* julia */
+         F3B_NOSPEC;
+         float a = 0.5f * atan_xy, s, c;
+         if (rng.bit()) a += F3B_PI;
+         float r = w * sqrtf(rad);
+         f3b_sincos(a, &s, &c);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 14: { /* bent */
+         F3B_NOSPEC;
+         float nx = tx < 0.0f ? tx * 2.0f : tx;
+         float ny = ty < 0.0f ? ty * 0.5f : ty;
+         p0 += w * nx;
+         p1 += w * ny;
+      } break;
+      case 15: { /* waves: p = {c10, dx2, c11, dy2} */
+         F3B_NOSPEC;
+         p0 += w * (tx + p[0] * f3b_sin(ty * p[1]));
+         p1 += w * (ty + p[2] * f3b_sin(tx * p[3]));
+      } break;
+      case 16: { /* fisheye (x/y swap is intentional in the reference) */
+         F3B_NOSPEC;
+         float r = 2.0f * w / (rad + 1.0f);
+         p0 += r * ty;
+         p1 += r * tx;
+      } break;
+      case 26: { /* rings2: p = {dx} */
+         F3B_NOSPEC;
+         float dx = p[0];
+         float r = rad;
+         r += -2.0f * dx * truncf((r + dx) / (2.0f * dx)) + r * (1.0f - dx);
+         p0 += w * sina * r;
+         p1 += w * cosa * r;
+      } break;
+      case 27: { /* eyefish */
+         F3B_NOSPEC;
+         float r = (w * 2.0f) / (rad + 1.0f);
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 28: { /* bubble */
+         F3B_NOSPEC;
+         float r = w / (0.25f * sumsq + 1.0f);
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 29: /* cylinder */
+         F3B_NOSPEC;
+         p0 += w * f3b_sin(tx);
+         p1 += w * ty;
+         break;
+      case 30: { /* perspective: p = {dist, vsin, vfcos} */
+         F3B_NOSPEC;
+         float t = 1.0f / (p[0] - ty * p[1]);
+         p0 += w * p[0] * tx * t;
+         p1 += w * p[2] * ty * t;
+      } break;
+      case 39: { /* curl: p = {c1, c2} */
+         F3B_NOSPEC;
+         float re = 1.0f + p[0] * tx + p[1] * (tx * tx - ty * ty);
+         float im = p[0] * ty + 2.0f * p[1] * tx * ty;
+         float r = w / (re * re + im * im);
+         p0 += (tx * re + ty * im) * r;
+         p1 += (ty * re - tx * im) * r;
+      } break;
+      case 40: { /* rectangles: p = {x, y} */
+         F3B_NOSPEC;
+         if (p[0] == 0.0f) p0 += w * tx;
+         else p0 += w * ((2.0f * floorf(tx / p[0]) + 1.0f) * p[0] - tx);
+         if (p[1] == 0.0f) p1 += w * ty;
+         else p1 += w * ((2.0f * floorf(ty / p[1]) + 1.0f) * p[1] - ty);
+      } break;
+      case 43: { /* square */
+         F3B_NOSPEC;
+         float a = rng.u01();
+         float b = rng.u01();
+         p0 += w * (a - 0.5f);
+         p1 += w * (b - 0.5f);
+      } break;
+      case 48: { /* cross */
+         F3B_NOSPEC;
+         float s = tx * tx - ty * ty;
+         float r = w * sqrtf(1.0f / (s * s + F3B_EPS));
+         p0 += tx * r;
+         p1 += ty * r;
+      } break;
+      case 54: { /* bent2: p = {x, y} */
+         F3B_NOSPEC;
+         float nx = tx < 0.0f ? tx * p[0] : tx;
+         float ny = ty < 0.0f ? ty * p[1] : ty;
+         p0 += w * nx;
+         p1 += w * ny;
+      } break;
+      case 57: { /* butterfly; 4/sqrt(3*pi) */
+         F3B_NOSPEC;
+         float wx = w * 1.3029400317411197908970256609023f;
+         float y2 = ty * 2.0f;
+         float r = wx * sqrtf(fabsf(ty * tx) / (F3B_EPS + tx * tx + y2 * y2));
+         p0 += r * tx;
+         p1 += r * y2;
+      } break;
+      case 66: { /* loonie */
+         F3B_NOSPEC;
+         float w2 = w * w;
+         if (sumsq < w2) {
+            float r = w * sqrtf(w2 / sumsq - 1.0f);
+            p0 += r * tx;
+            p1 += r * ty;
+         } else {
+            p0 += w * tx;
+            p1 += w * ty;
+         }
+      } break;
+      /* 67 pre_blur is applied before the loop and never packed as a loop entry */
+      case 72: { /* scry */
+         F3B_NOSPEC;
+         float r = 1.0f / (rad * (sumsq + 1.0f / (w + F3B_EPS)));
+         p0 += tx * r;
+         p1 += ty * r;
+      } break;
+      case 73: { /* separation: p = {x^2, xinside, y^2, yinside} */
+         F3B_NOSPEC;
+         if (tx > 0.0f) p0 += w * (sqrtf(tx * tx + p[0]) - tx * p[1]);
+         else p0 -= w * (sqrtf(tx * tx + p[0]) + tx * p[1]);
+         if (ty > 0.0f) p1 += w * (sqrtf(ty * ty + p[2]) - ty * p[3]);
+         else p1 -= w * (sqrtf(ty * ty + p[2]) + ty * p[3]);
+      } break;
+      case 75: { /* splits: p = {x, y} */
+         F3B_NOSPEC;
+         p0 += w * (tx >= 0.0f ? tx + p[0] : tx - p[0]);
+         p1 += w * (ty >= 0.0f ? ty + p[1] : ty - p[1]);
+      } break;
+      case 76: { /* stripes: p = {1-space, warp} */
+         F3B_NOSPEC;
+         float roundx = floorf(tx + 0.5f);
+         float offx = tx - roundx;
+         p0 += w * (offx * p[0] + roundx);
+         p1 += w * (ty + offx * offx * p[1]);
+      } break;
       case 98: { /* mobius: p = {re_a, im_a, re_b, im_b, re_c, im_c, re_d, im_d} */
+         F3B_NOSPEC;
          float re_u = p[0] * tx - p[1] * ty + p[2];
          float im_u = p[0] * ty + p[1] * tx + p[3];
          float re_v = p[4] * tx - p[5] * ty + p[6];
@@ -821,15 +929,21 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
          p0 += rv * (re_u * re_v + im_u * im_v);
          p1 += rv * (im_u * re_v - re_u * im_v);
       } break;
-      default:
-         break;
+      default: {
+         F3Rng tmp = rng; /* only this copy has its address taken */
+         const float2 d = f3b_var_slow(id, w, p, pt, &tmp);
+         rng = tmp;
+         p0 += d.x;
+         p1 += d.y;
+      } break;
       }
-      v += 2 + (w0 >> 8);
    }
 
    if (flags & F3B_XF_HAS_POST) {
-      qx = xf[F3B_X_P00] * p0 + xf[F3B_X_P10] * p1 + xf[F3B_X_P20];
-      qy = xf[F3B_X_P01] * p0 + xf[F3B_X_P11] * p1 + xf[F3B_X_P21];
+      const float4 b0 = *reinterpret_cast<const float4 *>(xf + 12); /* p00 p10 p20 p01 */
+      const float2 b1 = *reinterpret_cast<const float2 *>(xf + 16); /* p11 p21 */
+      qx = fmaf(b0.x, p0, fmaf(b0.y, p1, b0.z));
+      qy = fmaf(b0.w, p0, fmaf(b1.x, p1, b1.y));
    } else {
       qx = p0;
       qy = p1;
