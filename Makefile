@@ -49,7 +49,7 @@ REF_CFLAGS = -g -O3 -std=gnu99 -ffast-math -fPIC -w -I$(SHIMS) -I$(F3_REF) \
              -DPACKAGE_DATA_DIR='"$(F3_REF)"' -DGIT_REV='""'
 HOST_SRCS  = variations.c filters.c isaac.c interpolation.c palettes.c parser.c
 HOST_OBJS  = $(addprefix $(DROP)/host_,$(HOST_SRCS:.c=.o))
-GLUE_OBJS  = $(DROP)/f3b_render.o $(DROP)/f3b_pack.o $(DROP)/f3b_isaac.o
+GLUE_OBJS  = $(DROP)/f3b_render.o $(DROP)/f3b_pack.o $(DROP)/f3b_isaac.o $(DROP)/f3b_debug.o
 MISC_OBJS  = $(DROP)/xmlshim.o $(DROP)/imgshim.o $(DROP)/harness.o
 CLIS       = $(DROP)/flam3-render $(DROP)/flam3-animate $(DROP)/flam3-genome
 

@@ -307,6 +307,38 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    return stage_end(ctx, nl);
 }
 
+int f3b_debug_apply_xform(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int xform_index,
+                          const float *in_xyc, int n, float *out_xycvb, uint64_t seed) {
+   if (!ctx || !blob || !in_xyc || !out_xycvb || n <= 0) return fail(ctx, "debug_apply: bad arguments");
+   CK(cudaSetDevice(ctx->device));
+   const uint32_t *w = (const uint32_t *)blob;
+   if (blob_bytes < F3B_H_SIZE * 4 || (size_t)w[F3B_H_WORDS] * 4 > blob_bytes ||
+       w[F3B_H_WORDS] > F3B_MAX_BLOB_WORDS)
+      return fail(ctx, "debug_apply: malformed blob");
+   if (xform_index < 0 || (uint32_t)xform_index >= w[F3B_H_NXF])
+      return fail(ctx, "debug_apply: xform index %d out of range", xform_index);
+   void *d_blob = nullptr, *d_in = nullptr, *d_out = nullptr;
+   cudaError_t e = cudaMalloc(&d_blob, blob_bytes);
+   if (e == cudaSuccess) e = cudaMalloc(&d_in, sizeof(float) * 3 * (size_t)n);
+   if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(float) * 5 * (size_t)n);
+   if (e == cudaSuccess) e = cudaMemcpyAsync(d_blob, blob, blob_bytes, cudaMemcpyHostToDevice, ctx->stream);
+   if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d_in, in_xyc, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+   if (e == cudaSuccess &&
+       !f3b_launch_debug_apply((const uint32_t *)d_blob, (size_t)w[F3B_H_WORDS] * 4, xform_index,
+                               (const float *)d_in, n, (float *)d_out, seed, ctx->stream))
+      e = cudaGetLastError();
+   if (e == cudaSuccess)
+      e = cudaMemcpyAsync(out_xycvb, d_out, sizeof(float) * 5 * (size_t)n, cudaMemcpyDeviceToHost,
+                          ctx->stream);
+   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+   cudaFree(d_blob);
+   cudaFree(d_in);
+   cudaFree(d_out);
+   if (e != cudaSuccess) return fail(ctx, "debug_apply failed: %s", cudaGetErrorString(e));
+   return 0;
+}
+
 int f3b_badvals(f3b_ctx *ctx, double *out) {
    unsigned long long v = 0;
    CK(cudaSetDevice(ctx->device));

@@ -33,6 +33,8 @@ struct F3IterateParams {
 int f3b_launch_iterate(const F3IterateParams &p, bool count_channel, int grid_blocks,
                        size_t smem_bytes, cudaStream_t stream);
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes);
+int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_index, const float *in,
+                           int n, float *out, uint64_t seed, cudaStream_t stream);
 
 struct F3DensityParams {
    const float4 *hist_color;

@@ -238,6 +238,39 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
    if ((tid & 31u) == 0 && bad) atomicAdd(P.badvals, (unsigned long long)bad);
 }
 
+/* One application of one xform to caller-supplied points (parity tests of the variation
+ * maths against the reference's apply_xform). in: {x, y, color}; out: {x, y, color, vis, bad} */
+__global__ void f3b_debug_apply_kernel(const uint32_t *blob, int xform_index, const float *in, int n,
+                                       float *out, uint64_t seed) {
+   extern __shared__ __align__(16) uint32_t smem[];
+   const float *sf = reinterpret_cast<const float *>(smem);
+   const uint32_t words = blob[F3B_H_WORDS];
+   for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) smem[i] = blob[i];
+   __syncthreads();
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   const uint32_t *xftab = smem + smem[F3B_H_OFF_XFTAB];
+   F3Rng rng;
+   f3b_rng_seed(rng, seed, 0u, (uint32_t)i);
+   float qx, qy, qc, qv;
+   const bool bad = f3b_apply_xform(sf + xftab[xform_index], in[3 * i], in[3 * i + 1], in[3 * i + 2],
+                                    qx, qy, qc, qv, rng);
+   out[5 * i] = qx;
+   out[5 * i + 1] = qy;
+   out[5 * i + 2] = qc;
+   out[5 * i + 3] = qv;
+   out[5 * i + 4] = bad ? 1.0f : 0.0f;
+}
+
+int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_index, const float *in,
+                           int n, float *out, uint64_t seed, cudaStream_t stream) {
+   cudaFuncSetAttribute(f3b_debug_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)(F3B_MAX_BLOB_WORDS * 4));
+   f3b_debug_apply_kernel<<<(n + 127) / 128, 128, blob_bytes, stream>>>(blob, xform_index, in, n, out,
+                                                                         seed);
+   return cudaGetLastError() == cudaSuccess ? 1 : 0;
+}
+
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes) {
    int nb = 0;
    cudaFuncSetAttribute(f3b_iterate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -82,6 +82,11 @@ uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len,
  * semantics of bits 32/33 (flam3.c:3838-3854). seed selects the random streams. */
 int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *jobs, int n_jobs,
                 uint64_t seed, int floor_adds, uint32_t max_chain_len, int rank, int nranks);
+/* One application of xform `xform_index` of a packed sample to n caller-supplied points
+ * (apply_xform, variations.c:2129-2399): in = {x, y, color} per point, out = {x, y, color,
+ * vis_adjusted, bad} per point. For testing the variation maths in isolation. */
+int f3b_debug_apply_xform(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int xform_index,
+                          const float *in_xyc, int n, float *out_xycvb, uint64_t seed);
 /* bad values since f3b_frame_begin (stat_struct.badvals, rect.c:1251) */
 int f3b_badvals(f3b_ctx *ctx, double *out);
 

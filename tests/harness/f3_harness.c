@@ -145,3 +145,76 @@ void h_abi_sizes(int *out) {
    out[2] = (int)sizeof(flam3_genome);
    out[3] = (int)sizeof(flam3_frame);
 }
+
+/* ---- finer-grained probes used to pin the oracle and the packer ------------------- */
+
+/* the xform chooser table of genome idx (flam3.c:76-111); out must hold rows*16384 */
+int h_xform_distrib(void *cps, int idx, unsigned short *out, int *rows) {
+   flam3_genome *g = (flam3_genome *)cps + idx;
+   unsigned short *d = flam3_create_xform_distrib(g);
+   if (!d) return 1;
+   int nstd = g->num_xforms - (g->final_xform_index >= 0);
+   int nr = g->chaos_enable ? nstd + 1 : 1;
+   memcpy(out, d, (size_t)nr * 16384 * sizeof(unsigned short));
+   *rows = nr;
+   free(d);
+   return 0;
+}
+
+/* apply_xform (variations.c:2129) of xform fn to n points in[i] = {x, y, color}; out[i] =
+ * {x, y, color, vis, bad}. Every point gets a fresh ISAAC context seeded from `seed` and its
+ * index, so variations that draw random numbers are reproducible per point. */
+extern int prepare_precalc_flags(flam3_genome *);
+extern void xform_precalc(flam3_genome *, int);
+extern int apply_xform(flam3_genome *cp, int fn, double *p, double *q, randctx *rc);
+int h_apply_xform(void *cps, int idx, int fn, const double *in, int n, double *out,
+                  const char *seed) {
+   flam3_genome *g = (flam3_genome *)cps + idx;
+   if (prepare_precalc_flags(g)) return 1;
+   for (int i = 0; i < g->num_xforms; i++) xform_precalc(g, i);
+   for (int i = 0; i < n; i++) {
+      randctx rc;
+      double p[4] = {in[3 * i], in[3 * i + 1], in[3 * i + 2], 1.0}, q[4];
+      memset(&rc, 0, sizeof(rc));
+      strncpy((char *)rc.randrsl, seed, RANDSIZ * sizeof(ub4));
+      rc.randrsl[RANDSIZ - 1] ^= (ub4)i;
+      irandinit(&rc, 1);
+      int bad = apply_xform(g, fn, p, q, &rc);
+      out[5 * i] = q[0];
+      out[5 * i + 1] = q[1];
+      out[5 * i + 2] = q[2];
+      out[5 * i + 3] = q[3];
+      out[5 * i + 4] = bad;
+   }
+   return 0;
+}
+
+/* n draws of irand() (isaac.h:49-52) from a context seeded like flam3_init_frame; also
+ * returns the context so another implementation can be run from the same state. */
+int h_isaac_draws(const char *seed, int n, unsigned long *out, void *ctx_before, void *ctx_after) {
+   randctx rc;
+   memset(&rc, 0, sizeof(rc));
+   strncpy((char *)rc.randrsl, seed, RANDSIZ * sizeof(ub4));
+   irandinit(&rc, 1);
+   if (ctx_before) memcpy(ctx_before, &rc, sizeof(rc));
+   for (int i = 0; i < n; i++) out[i] = irand(&rc);
+   if (ctx_after) memcpy(ctx_after, &rc, sizeof(rc));
+   return 0;
+}
+
+/* flam3_iterate (flam3.c:232) on genome idx: n samples from start point p0[4]. */
+int h_iterate(void *cps, int idx, int n, int fuse, const double *p0, double *samples,
+              const char *seed) {
+   flam3_genome *g = (flam3_genome *)cps + idx;
+   randctx rc;
+   if (prepare_precalc_flags(g)) return -1;
+   unsigned short *d = flam3_create_xform_distrib(g);
+   if (!d) return -1;
+   memset(&rc, 0, sizeof(rc));
+   strncpy((char *)rc.randrsl, seed, RANDSIZ * sizeof(ub4));
+   irandinit(&rc, 1);
+   memcpy(samples, p0, 4 * sizeof(double));
+   int bad = flam3_iterate(g, n, fuse, samples, d, &rc);
+   free(d);
+   return bad;
+}

@@ -1,0 +1,165 @@
+"""CPU tests of the drop-in boundary and the host logic: the C-ABI libraries load and export
+every symbol their headers declare, struct sizes are the reference's, error paths that do
+not need a GPU behave like the reference, and the multi-GPU sharding rule partitions the
+work (world_size 2, gloo)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(f3b_\w+|flam3_render\w*)\s*\(", txt)))
+
+
+def test_core_library_exports_every_declared_symbol(core):
+    names = declared_functions("flam3_b200.h")
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(core._dll, n), "libflam3_b200.so lacks %s" % n
+    from flam3_b200.capi import CORE_SYMBOLS
+
+    assert set(CORE_SYMBOLS) <= set(names)
+    assert core._dll.f3b_abi_version() == 1
+
+
+def test_dropin_exports_the_reference_entry_points(gpu):
+    for n in declared_functions("flam3_b200_dropin.h"):
+        assert hasattr(gpu._dll, n), "drop-in libflam3.so lacks %s" % n
+    # and the rest of flam3.h still resolves in the same library (parser, interpolation ...)
+    for n in ("flam3_parse_xml2", "flam3_interpolate", "flam3_init_frame", "flam3_print_to_string",
+              "flam3_iterate", "flam3_make_strip", "flam3_estimate_bounding_box"):
+        assert hasattr(gpu._dll, n)
+
+
+def test_struct_sizes_are_the_reference_abi(gpu):
+    # layouts are ABI
+    assert gpu.abi_sizes() == dict(randctx=288, flam3_xform=3240, flam3_genome=10728,
+                                   flam3_frame=360)
+
+
+def test_memory_required_matches_reference_formula(gpu, flame0):
+    g = gpu.parse(flame0)
+    # os^2 * W * H * bytes * 9 (flam3.c:3884-3886), bits 33 counts as 32
+    assert gpu.memory_required(g, 0, 33) == 640 * 480 * 4 * 9.0
+    assert gpu.memory_required(g, 0, 64) == 640 * 480 * 8 * 9.0
+
+
+def test_memory_required_matches_reference(gpu, ref, flame0):
+    from flam3_b200.genome_xml import resize
+
+    xml = resize(flame0, 800, 600, oversample=3)
+    for bits in (32, 33, 64):
+        assert gpu.memory_required(gpu.parse(xml), 0, bits) == ref.memory_required(ref.parse(xml), 0, bits)
+
+
+def test_bad_bits_is_rejected_before_any_gpu_work(gpu, flame0):
+    g = gpu.parse(flame0)
+    img, st, _ = gpu.render(g, bits=16)
+    assert st["rv"] == 1 and img.max() == 0
+
+
+def test_no_cpu_fallback_without_gpu(gpu, flame0):
+    """On a box without a usable GPU the render must fail loudly (return 1), never fall
+    back to a CPU path. (On the GPU box this test is skipped.)"""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = gpu.parse(flame0)
+    img, st, _ = gpu.render(g)
+    assert st["rv"] == 1 and img.max() == 0
+
+
+def test_product_does_not_link_the_oracle():
+    out = subprocess.run(["ldd", os.path.join(ROOT, "dropin", "_build", "libflam3.so")],
+                         capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libflam3_ref" not in out
+    out = subprocess.run(["ldd", os.path.join(ROOT, "flam3_b200", "lib", "libflam3_b200.so")],
+                         capture_output=True, text=True).stdout
+    assert "oracle" not in out and "flam3_ref" not in out
+
+
+def test_packed_sample_layout(gpu, flame0):
+    """Host packer: header fields, 16-byte aligned xform records, pre-truncated palette."""
+    f = gpu._dll.f3b_debug_pack_genome
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    g = gpu.parse(flame0)
+    w = np.zeros(12288, dtype=np.uint32)
+    used = C.c_size_t()
+    assert f(g.ptr, 0, 1, w.ctypes.data, w.size, C.byref(used)) == 0
+    fl = w.view(np.float32)
+    assert w[1] == 4 and w[2] == 0xFFFFFFFF and w[3] == 0   # 4 xforms, no final, no xaos
+    assert w[23] == 4 and w[24] == 1 and w[25] == 4          # nxf, plot-ready, chooser stride
+    xftab = w[w[21]: w[21] + 4]
+    assert all(int(o) % 4 == 0 for o in xftab)
+    # xform 0: spherical only -> one variation record of 2 words, id 2
+    rec = int(xftab[0])
+    assert w[rec + 11] == 2 and (w[rec + 20] & 0xFF) == 2
+    assert abs(fl[rec + 0] - (-0.681206)) < 1e-6 and abs(fl[rec + 3] - (-0.0779465)) < 1e-6
+    pal = fl[w[22]: w[22] + 1024].reshape(256, 4)
+    assert np.all(pal == np.floor(pal)) and np.all(pal[:, 3] == 255.0)
+    # the chooser row: four equal weights -> 4096 / 8192 / 12288 / 16384
+    assert list(w[w[20]: w[20] + 4]) == [4096, 8192, 12288, 16384]
+
+
+def test_shard_rule_partitions_groups():
+    from flam3_b200.multigpu import shard_groups
+
+    for n_groups in (1, 7, 592, 1777):
+        for nranks in (1, 2, 3, 8):
+            parts = [shard_groups(n_groups, r, nranks) for r in range(nranks)]
+            allg = sorted(g for p in parts for g in p)
+            assert allg == list(range(n_groups))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+from flam3_b200.multigpu import shard_groups
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+os.environ["MASTER_ADDR"] = "127.0.0.1"
+os.environ["MASTER_PORT"] = sys.argv[3]
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# every chain group g deposits (g+1) hits into bucket g % nb: a stand-in for the kernel that
+# makes the exchanged histogram predictable
+n_groups, nb = 101, 16
+hist = np.zeros(nb * 4, dtype=np.float32)
+for g in shard_groups(n_groups, rank, world):
+    hist[(g % nb) * 4: (g % nb) * 4 + 4] += float(g + 1)
+t = torch.from_numpy(hist)
+dist.all_reduce(t, op=dist.ReduceOp.SUM)
+want = np.zeros(nb * 4, dtype=np.float32)
+for g in range(n_groups):
+    want[(g % nb) * 4: (g % nb) * 4 + 4] += float(g + 1)
+assert np.array_equal(t.numpy(), want), (rank, t.numpy()[:8], want[:8])
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_histogram_exchange_world_size_2_gloo(tmp_path):
+    """The N>1 path: private histograms of disjoint chain-group shards, summed by one
+    all-reduce, equal the single-process histogram. gloo on CPU, world_size 2."""
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER.format(root=ROOT))
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", port],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o

@@ -1,0 +1,117 @@
+"""Variation coverage (config C5 of SURVEY.md §8(d), correctness side): every one of the 99
+variations of variations.c, on the GPU, against the unmodified reference.
+
+ (a) one application of apply_xform to the same input points: deterministic variations
+     must agree point by point within single-precision tolerance; variations that draw
+     random numbers are compared as distributions (the GPU uses its own random streams);
+ (b) a small rendered image per variation, compared like tests/test_gpu_chaos.py.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from parity_util import libs, psnr
+from variation_cases import RANDOM_VARS, VAR_NAMES, genome_xml
+from variation_cases import test_points as make_points
+
+pytestmark = pytest.mark.gpu
+
+# fp32 vs fp64: relative tolerance on |value| + 1, met by at least FRACTION of the points
+# (points next to a pole of tan / a branch cut legitimately differ more)
+TOL = 2e-3
+FRACTION = 0.985
+MEDIAN_TOL = 2e-5
+
+
+def _ctx():
+    ref, gpu, core = libs()
+    if not hasattr(_ctx, "c"):
+        _ctx.c = gpu.render_context(core)
+    return ref, gpu, core, _ctx.c
+
+
+def gpu_apply(gpu, core, ctx, xml, pts, seed=7):
+    g = gpu.parse(xml)
+    pack = gpu._dll.f3b_debug_pack_genome
+    pack.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    words = np.zeros(12288, dtype=np.uint32)
+    used = C.c_size_t()
+    assert pack(g.ptr, 0, 1, words.ctypes.data, words.size, C.byref(used)) == 0
+    f = core._dll.f3b_debug_apply_xform
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_uint64]
+    pin = np.ascontiguousarray(pts, dtype=np.float32)
+    out = np.zeros((len(pts), 5), dtype=np.float32)
+    rv = f(ctx.ptr, words.ctypes.data, used.value * 4, 0, pin.ctypes.data, len(pts),
+           out.ctypes.data, seed)
+    assert rv == 0, core._dll.f3b_last_error(ctx.ptr)
+    return out.astype(np.float64)
+
+
+def ref_apply(ref, xml, pts, seed=b"vseed"):
+    g = ref.parse(xml)
+    f = ref._dll.h_apply_xform
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_char_p]
+    pin = np.ascontiguousarray(pts, dtype=np.float64)
+    out = np.zeros((len(pts), 5))
+    assert f(g.ptr, 0, 0, pin.ctypes.data, len(pts), out.ctypes.data, seed) == 0
+    return out
+
+
+@pytest.mark.parametrize("vid", [v for v in range(99) if v not in RANDOM_VARS])
+def test_deterministic_variation_single_step(vid):
+    ref, gpu, core, ctx = _ctx()
+    # inputs rounded to float so both sides start from identical points
+    pts = make_points(1024).astype(np.float32).astype(np.float64)
+    xml = genome_xml(vid)
+    r = ref_apply(ref, xml, pts)
+    g = gpu_apply(gpu, core, ctx, xml, pts)
+    good = (r[:, 4] == 0) & (g[:, 4] == 0)
+    assert good.mean() > 0.9, "too many bad values to compare (%s)" % VAR_NAMES[vid]
+    # bad-value decisions (|v| > 1e10 or NaN) must agree except at the numerical edge
+    assert (r[:, 4] != g[:, 4]).mean() < 0.01
+    err = np.abs(g[good, :2] - r[good, :2]) / (1.0 + np.abs(r[good, :2]))
+    assert np.median(err) < MEDIAN_TOL, (VAR_NAMES[vid], np.median(err))
+    assert (err.max(axis=1) < TOL).mean() >= FRACTION, (VAR_NAMES[vid], np.sort(err.max(axis=1))[-8:])
+    # colour and opacity are exact functions of the inputs
+    np.testing.assert_allclose(g[good, 2], r[good, 2], atol=1e-6)
+    np.testing.assert_allclose(g[good, 3], r[good, 3], atol=1e-6)
+
+
+@pytest.mark.parametrize("vid", sorted(RANDOM_VARS))
+def test_random_variation_distribution(vid):
+    """Same input point replicated many times; the clouds of outputs must have the same
+    mean, spread and quartiles (the two sides use different random generators)."""
+    ref, gpu, core, ctx = _ctx()
+    n = 20000
+    xml = genome_xml(vid)
+    for base in ((0.6, -0.4, 0.3), (-1.1, 0.7, 0.8)):
+        pts = np.tile(np.array(base, dtype=np.float32).astype(np.float64), (n, 1))
+        r = ref_apply(ref, xml, pts)
+        g = gpu_apply(gpu, core, ctx, xml, pts)
+        gr, gg = r[r[:, 4] == 0, :2], g[g[:, 4] == 0, :2]
+        assert abs(len(gr) - len(gg)) < 0.02 * n
+        for axis in (0, 1):
+            a, b = gr[:, axis], gg[:, axis]
+            # robust comparison: heavy-tailed outputs (arch, rays, ...) are clipped
+            lo, hi = np.percentile(a, [1, 99])
+            span = max(hi - lo, 1e-6)
+            qa = np.percentile(a, [10, 25, 50, 75, 90])
+            qb = np.percentile(b, [10, 25, 50, 75, 90])
+            assert np.all(np.abs(qa - qb) < 0.03 * span + 1e-4), (VAR_NAMES[vid], axis, qa, qb)
+
+
+@pytest.mark.parametrize("vid", range(99))
+def test_variation_image(vid):
+    ref, gpu, _, _ = _ctx()
+    xml = genome_xml(vid, size=96, quality=40)
+    gr, gg = ref.parse(xml), gpu.parse(xml)
+    a, sa, _ = ref.render(gr, isaac_seed="va", nthreads=1)
+    b, sb, _ = ref.render(gr, isaac_seed="vb", nthreads=1)
+    g, sg, _ = gpu.render(gg, isaac_seed="va")
+    assert sg["rv"] == 0 and sg["num_iters"] == sa["num_iters"]
+    noise = psnr(a, b)
+    got = min(psnr(g, a), psnr(g, b))
+    assert got >= noise - 2.0, "%s: gpu-vs-ref %.2f dB, ref-vs-ref %.2f dB" % (VAR_NAMES[vid], got, noise)
+    assert abs(g.mean() - a.mean()) <= max(1.0, 0.04 * a.mean()), (g.mean(), a.mean())
