@@ -222,18 +222,17 @@ uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len,
    uint64_t Ts = T / n_jobs;
    if (Ts < 32) Ts = 32;
    if (Ts >= F3B_CHAINS_PER_GROUP) Ts -= Ts % F3B_CHAINS_PER_GROUP;
-   const uint64_t lmin = 64; /* keeps the fuse overhead (15 discarded) below ~25% */
-   uint64_t chains;
-   if (n_iters >= Ts * lmin) {
-      const uint64_t rounds = (n_iters + Ts * max_chain_len - 1) / (Ts * (uint64_t)max_chain_len);
-      chains = Ts * rounds;
-   } else {
-      chains = n_iters / (max_chain_len < lmin ? max_chain_len : lmin);
-      if (chains == 0) chains = 1;
-   }
-   /* never exceed the per-chain cap */
-   const uint64_t need = (n_iters + max_chain_len - 1) / max_chain_len;
-   if (chains < need) chains = need;
+   /* Chain length is an observable of the reference: every chain starts at a random point
+    * and only `fuse` (15) iterations are discarded, so for slowly converging systems the
+    * image depends on how often the orbit is restarted (measured: the reference's own
+    * output moves by 10+ dB of PSNR between sub_batch_size 10000 and 2048 on such genomes,
+    * tests/test_gpu_variations.py). Chains are therefore sub_batch_size long, as in
+    * iter_thread (rect.c:279-284): as few chains as that allows, and once there are more
+    * chains than resident threads their number is rounded up to whole rounds of threads so
+    * no tail wave is left (the chains get marginally shorter, never longer). */
+   uint64_t chains = (n_iters + max_chain_len - 1) / max_chain_len;
+   if (chains == 0) chains = 1;
+   if (chains > Ts) chains = ((chains + Ts - 1) / Ts) * Ts;
    if (chains > 0xfffffff0ull) chains = 0xfffffff0ull;
    return (uint32_t)chains;
 }

@@ -1,0 +1,79 @@
+"""The reference's own command-line programs, compiled UNMODIFIED from its sources and
+linked against the drop-in libflam3 (dropin/_build), run on the GPU box: README.txt:42-51's
+smoke test (`flam3-render < test.flam3`, `flam3-animate`) with the B200 path underneath, next
+to the same program linked against the unmodified library (oracle/_ref/flam3-render-ref).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from imgio import read_ppm
+from parity_util import psnr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIXTURE = os.path.join(ROOT, "tests", "golden", "test_both.flam3")
+
+
+def run_cli(exe, tmp, prefix, extra_env=None, stdin=FIXTURE):
+    env = dict(os.environ)
+    env.update({"format": "ppm", "isaac_seed": "flam3b200", "prefix": os.path.join(tmp, prefix),
+                "verbose": "0"})
+    env.update(extra_env or {})
+    with open(stdin) as f:
+        p = subprocess.run([exe], stdin=f, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p
+
+
+def test_flam3_render_cli_both_flames(tmp_path):
+    tmp = str(tmp_path)
+    run_cli(os.path.join(ROOT, "dropin", "_build", "flam3-render"), tmp, "gpu_")
+    run_cli(os.path.join(ROOT, "oracle", "_ref", "flam3-render-ref"), tmp, "refa_",
+            {"nthreads": "1"})
+    run_cli(os.path.join(ROOT, "oracle", "_ref", "flam3-render-ref"), tmp, "refb_",
+            {"nthreads": "1", "isaac_seed": "another"})
+    for i in range(2):
+        g = read_ppm(os.path.join(tmp, "gpu_%05d.ppm" % i))
+        a = read_ppm(os.path.join(tmp, "refa_%05d.ppm" % i))
+        b = read_ppm(os.path.join(tmp, "refb_%05d.ppm" % i))
+        assert g.shape == (480, 640, 3)
+        assert min(psnr(g, a), psnr(g, b)) >= psnr(a, b) - 1.5
+
+
+def test_flam3_render_cli_strips(tmp_path):
+    """nstrips is implemented by the CALLER (flam3-render.c:311-348) on top of flam3_render:
+    height/center/sample_density are rewritten per strip and f.rc is restored. It must
+    keep working with the drop-in underneath."""
+    tmp = str(tmp_path)
+    run_cli(os.path.join(ROOT, "dropin", "_build", "flam3-render"), tmp, "s1_")
+    run_cli(os.path.join(ROOT, "dropin", "_build", "flam3-render"), tmp, "s4_", {"nstrips": "4"})
+    a = read_ppm(os.path.join(tmp, "s1_00000.ppm"))
+    b = read_ppm(os.path.join(tmp, "s4_00000.ppm"))
+    assert a.shape == b.shape
+    assert psnr(a, b) > 30.0
+
+
+def test_flam3_render_cli_png_rgba16(tmp_path):
+    tmp = str(tmp_path)
+    run_cli(os.path.join(ROOT, "dropin", "_build", "flam3-render"), tmp, "p_",
+            {"format": "png", "transparency": "1", "bpc": "16", "qs": "0.5"})
+    data = open(os.path.join(tmp, "p_00000.png"), "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    # IHDR: 640x480, 16 bit, colour type 6
+    assert data[16:26] == (640).to_bytes(4, "big") + (480).to_bytes(4, "big") + bytes([16, 6])
+
+
+def test_flam3_animate_cli_frames(tmp_path):
+    """flam3-animate interpolates between the two key frames with the default 1000
+    temporal samples per frame (motion blur), all in one chaos-game launch per frame."""
+    tmp = str(tmp_path)
+    run_cli(os.path.join(ROOT, "dropin", "_build", "flam3-animate"), tmp, "an_",
+            {"begin": "40", "end": "42"})
+    frames = [read_ppm(os.path.join(tmp, "an_%05d.ppm" % t)) for t in (40, 41, 42)]
+    for f in frames:
+        assert f.shape == (480, 640, 3) and f.mean() > 5
+    # consecutive frames of a smooth interpolation are close but not identical
+    assert 20.0 < psnr(frames[0], frames[1]) < 60.0

@@ -95,7 +95,11 @@ def genome_xml(vid, size=96, quality=40):
     return ('<flame time="0" size="%d %d" center="0 0" scale="%g" quality="%g" temporal_samples="1" '
             'brightness="4" gamma="3" vibrancy="1" supersample="1" filter="0.5" '
             'estimator_radius="4">\n'
-            '<xform %s coefs="%s" post="%s"/>\n%s\n</flame>\n'
+            '<xform %s coefs="%s" post="%s"/>\n'
+            # a plain rotating contraction as second map, so the pair has a proper attractor
+            # instead of the fixed point a lone contractive xform collapses to
+            '<xform weight="0.6" color="0.85" color_speed="0.5" linear="1" '
+            'coefs="0.55 0.35 -0.35 0.55 0.4 -0.2"/>\n%s\n</flame>\n'
             % (size, size, size / 4.0, quality, attrs, " ".join(map(repr, COEFS)),
                " ".join(map(repr, POST)), pal))
 
