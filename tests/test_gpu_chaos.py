@@ -125,6 +125,36 @@ def test_deterministic_per_seed(flame0):
     assert not np.array_equal(a, c)
 
 
+def test_sharded_histograms_sum_to_the_unsharded_one(flame0):
+    """Multi-GPU rule: rank r runs chain groups g = r (mod N) into a private
+    histogram; the sum over ranks must be the single-GPU histogram for the same seed —
+    exactly, because bucket adds are integer valued. Both "ranks" run here on one GPU."""
+    ref, gpu, core = libs()
+    # enough chains for several chain groups per rank, few enough hits per bucket that the
+    # float buckets stay exact (< 2^24 / 255 = 65 793 hits)
+    xml = resize(flame0, 320, 240, scale=120, quality=60, temporal_samples=3)
+    gg = gpu.parse(xml)
+    geo = gpu.buffer_geometry(gg)
+    ctx = gpu.render_context(core)
+    ctx.width, ctx.height = geo["width"], geo["height"]
+    try:
+        gpu.set_shard(0, 1)
+        full_img, st, _ = gpu.render(gg, isaac_seed="shard", sub_batch_size=100)
+        full = ctx.hist_download_u32().astype(np.uint64)
+        parts = []
+        for r in range(3):
+            gpu.set_shard(r, 3)
+            _, st_r, _ = gpu.render(gg, isaac_seed="shard", sub_batch_size=100)
+            assert st_r["rv"] == 0
+            parts.append(ctx.hist_download_u32().astype(np.uint64))
+    finally:
+        gpu.set_shard(0, 1)
+    assert all(p.sum() > 0 for p in parts)
+    total = parts[0] + parts[1] + parts[2]
+    assert full.max() < 2 ** 24
+    assert np.array_equal(total, full), "%d buckets differ" % int((total != full).any(axis=-1).sum())
+
+
 XFORM_FREQ_GENOME = """
 <flame time="0" size="256 256" center="0 0" scale="64" quality="200" temporal_samples="1"
        estimator_radius="0" brightness="4" gamma="4" vibrancy="1" supersample="1" filter="0.5">
