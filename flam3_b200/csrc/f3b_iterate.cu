@@ -28,7 +28,7 @@
 
 #define F3B_BLOCK F3B_CHAINS_PER_GROUP
 #ifndef F3B_ITER_MIN_BLOCKS
-#define F3B_ITER_MIN_BLOCKS 3 /* 80 registers, 24 warps/SM: best of {2,3,4} on B200 (profiles/r01) */
+#define F3B_ITER_MIN_BLOCKS 4 /* 64 registers, 32 warps/SM: best of {2,3,4} on B200 (profiles/r01) */
 #endif
 
 __device__ __forceinline__ void f3b_red_v4(float4 *addr, float r, float g, float b, float a) {
@@ -42,14 +42,21 @@ __device__ __forceinline__ void f3b_red_f32(float *addr, float v) {
 
 /* The final xform (flam3.c:280-287) is applied out of line: few genomes have one, and a
  * second inlined copy of the variation interpreter would double the hot loop's code. */
-__device__ __noinline__ float4 f3b_apply_final(const float *xf, float px, float py, float pc,
-                                               F3Rng *rngp) {
+__device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, float px, float py,
+                                               float pc, F3Rng *rngp) {
    F3Rng rng = *rngp;
    float fx, fy, fc, fv;
-   f3b_apply_xform(xf, px, py, pc, fx, fy, fc, fv, rng);
+   f3b_apply_xform(sf, xo, px, py, pc, fx, fy, fc, fv, rng);
    *rngp = rng;
    return make_float4(fx, fy, fc, fv);
 }
+
+/* per-sample constants folded into one register */
+#define HF_XAOS 1u
+#define HF_ROTATE 2u
+#define HF_PLOT_READY 4u
+#define HF_PAL_LINEAR 8u
+#define HF_FINAL 16u
 
 template <bool COUNT>
 __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_kernel(const F3IterateParams P) {
@@ -86,80 +93,69 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
       const int n_store = (int)(base + (chain < rem ? 1u : 0u));
       if (n_store == 0) continue;
 
-      /* header */
-      const uint32_t cstride = smem[F3B_H_CHOOSER_STRIDE];
-      const int final_idx = (int)smem[F3B_H_FINAL];
-      const bool xaos = smem[F3B_H_XAOS] != 0;
-      const float final_opacity = sf[F3B_H_FINAL_OPACITY];
-      const bool pal_linear = smem[F3B_H_PALMODE] != 0;
-      const int cmap_size = (int)smem[F3B_H_CMAPSIZE];
-      const bool rotate = smem[F3B_H_ROTATE] != 0;
-      const bool plot_ready = (smem[F3B_H_PLOT] & F3B_PLOT_READY) != 0;
-      const uint32_t *cum = smem + smem[F3B_H_OFF_CHOOSER];
-      const uint32_t *xftab = smem + smem[F3B_H_OFF_XFTAB];
-      const float4 *dmap = reinterpret_cast<const float4 *>(smem + smem[F3B_H_OFF_PALETTE]);
-      const float b0 = sf[F3B_H_B0], b1 = sf[F3B_H_B1], b2 = sf[F3B_H_B2], b3 = sf[F3B_H_B3];
-      const float ws0 = sf[F3B_H_WS0], hs1 = sf[F3B_H_HS1];
+      /* Header: flags, chooser stride and palette size share one register; the camera is
+       * re-read from shared memory (two LDS.128) when a point is plotted instead of living
+       * in six registers across the variation code. */
+      const uint32_t hf = (smem[F3B_H_XAOS] ? HF_XAOS : 0u) | (smem[F3B_H_ROTATE] ? HF_ROTATE : 0u) |
+                          ((smem[F3B_H_PLOT] & F3B_PLOT_READY) ? HF_PLOT_READY : 0u) |
+                          (smem[F3B_H_PALMODE] ? HF_PAL_LINEAR : 0u) |
+                          ((int)smem[F3B_H_FINAL] >= 0 ? HF_FINAL : 0u) |
+                          (smem[F3B_H_CHOOSER_STRIDE] << 8) | (smem[F3B_H_CMAPSIZE] << 20);
+      const uint32_t cum_off = smem[F3B_H_OFF_CHOOSER];
+      const uint32_t xftab_off = smem[F3B_H_OFF_XFTAB];
+      const uint32_t dmap_off = smem[F3B_H_OFF_PALETTE];
 
       F3Rng rng;
       f3b_rng_seed(rng, P.seed, job.sample_id, chain);
 
-      /* rect.c:394-397: start point in [-1,1]^2, colour in [0,1] (the 4th draw seeds an
-       * opacity that is overwritten before first use) */
+      /* rect.c:394-397: start point in [-1,1]^2, colour in [0,1]; the 4th draw seeds an
+       * opacity that is overwritten before first use, it is drawn to keep the pattern */
       float px = rng.u11();
       float py = rng.u11();
       float pc = rng.u01();
-      float pv = rng.u01();
+      (void)rng.u01();
       uint32_t lastxf = 0;
-      int consec = 0;
 
       for (int i = -(int)job.fuse; i < n_store; i++) {
          float qx, qy, qc, qv;
          uint32_t fn;
          /* flam3.c:249-270: pick + apply, retrying a bad value up to 4 times in place */
-         for (;;) {
+         for (int consec = 0;;) {
             const uint32_t k = rng.next() & (F3B_CHOOSER_GRAIN - 1u);
             /* fn = number of cumulative thresholds <= k; rows are padded with 16384 */
-            const uint4 *row = reinterpret_cast<const uint4 *>(cum + (xaos ? lastxf * cstride : 0u));
+            const uint32_t cstride = (hf >> 8) & 0xfffu;
+            const uint32_t ro = cum_off + ((hf & HF_XAOS) ? lastxf * cstride : 0u);
             {
-               const uint4 c = row[0]; /* up to 4 xforms: one LDS.128, no loop */
+               const uint4 c = *reinterpret_cast<const uint4 *>(smem + ro); /* <= 4 xforms: no loop */
                fn = (k >= c.x ? 1u : 0u) + (k >= c.y ? 1u : 0u) + (k >= c.z ? 1u : 0u) +
                     (k >= c.w ? 1u : 0u);
             }
             for (uint32_t j = 4; j < cstride; j += 4) {
-               const uint4 c = row[j >> 2];
+               const uint4 c = *reinterpret_cast<const uint4 *>(smem + ro + j);
                fn += (k >= c.x ? 1u : 0u) + (k >= c.y ? 1u : 0u) + (k >= c.z ? 1u : 0u) +
                      (k >= c.w ? 1u : 0u);
             }
-            const bool isbad =
-                f3b_apply_xform(sf + xftab[fn], px, py, pc, qx, qy, qc, qv, rng);
-            if (!isbad) {
-               consec = 0;
-               break;
-            }
+            const bool isbad = f3b_apply_xform(sf, smem[xftab_off + fn], px, py, pc, qx, qy, qc, qv, rng);
+            if (!isbad) break;
             bad++;
-            if (++consec >= 5) {
-               consec = 0;
-               break;
-            }
+            if (++consec >= 5) break;
             px = qx;
             py = qy;
             pc = qc;
-            pv = qv;
          }
          lastxf = fn + 1;
          px = qx;
          py = qy;
          pc = qc;
-         pv = qv;
 
          /* flam3.c:280-287: final xform does not feed back into the orbit */
-         if (final_idx >= 0) {
+         if (hf & HF_FINAL) {
+            const float final_opacity = sf[F3B_H_FINAL_OPACITY];
             bool apply = (final_opacity == 1.0f);
             if (!apply) apply = rng.u01() < final_opacity;
             if (apply) {
                F3Rng tmp = rng;
-               const float4 f = f3b_apply_final(sf + xftab[final_idx], px, py, pc, &tmp);
+               const float4 f = f3b_apply_final(sf, smem[xftab_off + smem[F3B_H_FINAL]], px, py, pc, &tmp);
                rng = tmp;
                qx = f.x;
                qy = f.y;
@@ -170,23 +166,28 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
          if (i < 0) continue;
 
          /* rect.c:419-441: camera */
+         const float4 bb = *reinterpret_cast<const float4 *>(sf + F3B_H_B0);  /* b0 b1 b2 b3 */
+         const float4 cs = *reinterpret_cast<const float4 *>(sf + F3B_H_WS0); /* ws0 hs1 rcx rcy */
          float x = qx, y = qy;
-         if (rotate) {
-            const float dx = qx - sf[F3B_H_RCX], dy = qy - sf[F3B_H_RCY];
-            x = dx * sf[F3B_H_ROT00] + dy * sf[F3B_H_ROT01] + sf[F3B_H_RCX];
-            y = dx * sf[F3B_H_ROT10] + dy * sf[F3B_H_ROT11] + sf[F3B_H_RCY];
+         if (hf & HF_ROTATE) {
+            const float4 rot = *reinterpret_cast<const float4 *>(sf + F3B_H_ROT00);
+            const float dx = qx - cs.z, dy = qy - cs.w;
+            x = dx * rot.x + dy * rot.y + cs.z;
+            y = dx * rot.z + dy * rot.w + cs.w;
          }
-         if (!(x >= b0 && y >= b1 && x <= b2 && y <= b3) || qv == 0.0f) continue;
-         const int ix = (int)((x - b0) * ws0);
-         const int iy = (int)((y - b1) * hs1);
+         if (!(x >= bb.x && y >= bb.y && x <= bb.z && y <= bb.w) || qv == 0.0f) continue;
+         const int ix = (int)((x - bb.x) * cs.x);
+         const int iy = (int)((y - bb.y) * cs.y);
          if (ix >= P.width || iy >= P.height) continue;
          const size_t bidx = (size_t)ix + (size_t)P.width * (size_t)iy;
 
          /* rect.c:465-498: palette lookup */
+         const int cmap_size = (int)(hf >> 20);
          const float findex = qc * (float)cmap_size;
          int ci = (int)findex;
+         const float4 *dmap = reinterpret_cast<const float4 *>(sf + dmap_off);
          float4 col;
-         if (plot_ready) {
+         if (hf & HF_PLOT_READY) {
             /* step lookup, every xform fully visible, dmap truncated on the host */
             ci = ci < 0 ? 0 : (ci >= cmap_size - 1 ? cmap_size - 1 : ci);
             col = dmap[ci];
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
             if (COUNT) f3b_red_f32(P.hist_count + bidx, 255.0f);
             continue;
          }
-         if (pal_linear) {
+         if (hf & HF_PAL_LINEAR) {
             float frac;
             if (ci < 0) {
                ci = 0;
@@ -253,7 +254,7 @@ __global__ void f3b_debug_apply_kernel(const uint32_t *blob, int xform_index, co
    F3Rng rng;
    f3b_rng_seed(rng, seed, 0u, (uint32_t)i);
    float qx, qy, qc, qv;
-   const bool bad = f3b_apply_xform(sf + xftab[xform_index], in[3 * i], in[3 * i + 1], in[3 * i + 2],
+   const bool bad = f3b_apply_xform(sf, xftab[xform_index], in[3 * i], in[3 * i + 1], in[3 * i + 2],
                                     qx, qy, qc, qv, rng);
    out[5 * i] = qx;
    out[5 * i + 1] = qy;

@@ -298,6 +298,8 @@ static int pack_xform(const flam3_xform *x, uint32_t *w, size_t cap, size_t *pos
    r[F3B_X_ONEMS] = f2u(1.0 - x->color_speed);
    r[F3B_X_VIS] = f2u(vis_adjust(x->opacity));
    r[F3B_X_PREBLUR] = f2u(x->var[VAR_PRE_BLUR]);
+   r[F3B_X_WLINEAR] = f2u(x->var[VAR_LINEAR]);
+   r[F3B_X_WSPHERICAL] = f2u(x->var[VAR_SPHERICAL]);
 
    unsigned flags = 0;
    const int has_post = !(x->post[0][0] == 1.0 && x->post[0][1] == 0.0 && x->post[1][0] == 0.0 &&
@@ -312,6 +314,8 @@ static int pack_xform(const flam3_xform *x, uint32_t *w, size_t cap, size_t *pos
       /* pre_blur is listed by the reference but has no case in its switch
        * (variations.c:2181-2379): it only acts through has_preblur */
       if (id == VAR_PRE_BLUR) continue;
+      /* linear and spherical live in fixed slots of the record header */
+      if (id == VAR_LINEAR || id == VAR_SPHERICAL) continue;
       double p[8];
       const int np = pack_var_params(x, id, p);
       if (np != f3b_var_nparams[id]) {

@@ -29,10 +29,11 @@ enum {
    F3B_H_PALMODE,       /* u32 0 = step, 1 = linear (rect.c:471-498) */
    F3B_H_CMAPSIZE,      /* u32 256, or 255 with apo_palette (rect.c:587) */
    F3B_H_ROTATE,        /* u32 camera rotation on (cp.rotate != 0, rect.c:419) */
+   /* three float4 groups at words 8, 12, 16 (read with LDS.128 when a point is plotted) */
    F3B_H_ROT00, F3B_H_ROT01, F3B_H_ROT10, F3B_H_ROT11, /* f32 rect.c:815-818 */
-   F3B_H_RCX, F3B_H_RCY,                               /* f32 rot_center */
    F3B_H_B0, F3B_H_B1, F3B_H_B2, F3B_H_B3,             /* f32 bounds, rect.c:809-812 */
    F3B_H_WS0, F3B_H_HS1,                               /* f32 buckets per unit, rect.c:819-822 */
+   F3B_H_RCX, F3B_H_RCY,                               /* f32 rot_center */
    F3B_H_OFF_CHOOSER,   /* u32 -> u32 cum[rows][nstd]: entries of the 16384 table <= j */
    F3B_H_OFF_XFTAB,     /* u32 -> u32 word offset of each xform record [nxf] */
    F3B_H_OFF_PALETTE,   /* u32 -> float4 dmap[256] (16-byte aligned) */
@@ -59,9 +60,12 @@ enum {
    F3B_X_FLAGS,    /* u32 F3B_XF_* */
    F3B_X_PREBLUR,  /* pre_blur weight              (variations.c:2149-2150) */
    F3B_X_NVARS,    /* u32 total length in words of the variation records that follow */
+   F3B_X_WLINEAR,  /* weight of var0 linear: fixed-function slot, not in the record list */
+   F3B_X_WSPHERICAL, /* weight of var2 spherical: fixed-function slot */
+   F3B_X_PAD0, F3B_X_PAD1,
    F3B_X_P00, F3B_X_P10, F3B_X_P20,     /* post affine (variations.c:2383-2385) */
    F3B_X_P01, F3B_X_P11, F3B_X_P21,
-   F3B_X_PAD0, F3B_X_PAD1,
+   F3B_X_PAD2, F3B_X_PAD3,
    F3B_X_VARS      /* first variation record: {u32 id | len<<8, f32 weight, f32 params[len]}, len =
                       nparams rounded up to even */
 };

@@ -637,12 +637,16 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
  * (px,py,pc). Returns true when the result is a "bad value", in which case (qx,qy) are
  * fresh uniform draws (variations.c:2391-2395).
  */
-__device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, float px, float py,
-                                                float pc, float &qx, float &qy, float &qc,
+/* `sf` is the shared-memory copy of the packed sample, `xo` the word offset of the xform
+ * record inside it. Offsets (not pointers) keep every access a 32-bit LDS address. */
+__device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, uint32_t xo, float px,
+                                                float py, float pc, float &qx, float &qy, float &qc,
                                                 float &qvis, F3Rng &rng) {
-   const float4 a0 = *reinterpret_cast<const float4 *>(xf);      /* c00 c10 c20 c01 */
-   const float4 a1 = *reinterpret_cast<const float4 *>(xf + 4);  /* c11 c21 scolor 1-s */
-   const float4 a2 = *reinterpret_cast<const float4 *>(xf + 8);  /* vis flags preblur nvars */
+   const float4 *xf4 = reinterpret_cast<const float4 *>(sf + xo);
+   const float4 a0 = xf4[0]; /* c00 c10 c20 c01 */
+   const float4 a1 = xf4[1]; /* c11 c21 scolor 1-s */
+   const float4 a2 = xf4[2]; /* vis flags preblur words-of-variation-list */
+   const float4 a3 = xf4[3]; /* linear weight, spherical weight, -, - */
    qc = fmaf(a1.w, pc, a1.z);
    qvis = a2.x;
    const uint32_t flags = __float_as_uint(a2.y);
@@ -650,62 +654,72 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
    F3Pt pt;
    pt.tx = fmaf(a0.x, px, fmaf(a0.y, py, a0.z));
    pt.ty = fmaf(a0.w, px, fmaf(a1.x, py, a1.y));
-
-   if (flags & F3B_XF_PREBLUR) { /* var67_pre_blur, variations.c:1480 */
-      const float g = a2.z * f3b_gauss4(rng);
-      float sa, ca;
-      f3b_sincos(rng.u01() * 2.0f * F3B_PI, &sa, &ca);
-      pt.tx += g * ca;
-      pt.ty += g * sa;
-   }
-
-   pt.sumsq = pt.tx * pt.tx + pt.ty * pt.ty;
    pt.rad = 0.0f;
    pt.atan_xy = pt.atan_yx = pt.sina = pt.cosa = 0.0f;
-   if (flags & F3B_XF_NEED_SQRT) pt.rad = sqrtf(pt.sumsq);
-   if (flags & F3B_XF_ATAN_XY) pt.atan_xy = atan2f(pt.tx, pt.ty);
-   if (flags & F3B_XF_ANGLES) {
-      pt.sina = pt.tx / pt.rad;
-      pt.cosa = pt.ty / pt.rad;
+
+   /* one test covers every optional per-point precalc (variations.c:2149-2170) */
+   if (flags & (F3B_XF_PREBLUR | F3B_XF_NEED_SQRT | F3B_XF_ATAN_XY | F3B_XF_ANGLES | F3B_XF_ATAN_YX)) {
+      if (flags & F3B_XF_PREBLUR) { /* var67_pre_blur, variations.c:1480 */
+         const float g = a2.z * f3b_gauss4(rng);
+         float sa, ca;
+         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &sa, &ca);
+         pt.tx += g * ca;
+         pt.ty += g * sa;
+      }
+      if (flags & F3B_XF_NEED_SQRT) pt.rad = sqrtf(pt.tx * pt.tx + pt.ty * pt.ty);
+      if (flags & F3B_XF_ATAN_XY) pt.atan_xy = atan2f(pt.tx, pt.ty);
+      if (flags & F3B_XF_ANGLES) {
+         pt.sina = pt.tx / pt.rad;
+         pt.cosa = pt.ty / pt.rad;
+      }
+      if (flags & F3B_XF_ATAN_YX) pt.atan_yx = atan2f(pt.ty, pt.tx);
    }
-   if (flags & F3B_XF_ATAN_YX) pt.atan_yx = atan2f(pt.ty, pt.tx);
+   pt.sumsq = pt.tx * pt.tx + pt.ty * pt.ty;
 
    float tx = pt.tx, ty = pt.ty, sumsq = pt.sumsq, rad = pt.rad;
    float atan_xy = pt.atan_xy, sina = pt.sina, cosa = pt.cosa;
-   float p0 = 0.0f, p1 = 0.0f;
-   /* variation records: {id | len << 8, weight, params[len]} with len even, so every
-    * record starts 8-byte aligned; a2.w holds the total length of the list in words */
-   const float *v = xf + F3B_X_VARS;
-   const float *const vend = v + __float_as_uint(a2.w);
 
-   while (v < vend) {
+   /* Fixed-function slots: linear and spherical, the two variations nearly every flame
+    * uses, are weights in the record header and are applied without entering the loop. */
+   float p0 = a3.x * tx, p1 = a3.x * ty;
+   if (a3.y != 0.0f) {
+      const float r2 = __fdividef(a3.y, sumsq + F3B_EPS);
+      p0 = fmaf(r2, tx, p0);
+      p1 = fmaf(r2, ty, p1);
+   }
+
+   /* remaining variations: {id | len << 8, weight, params[len]} records, len even so each
+    * starts 8-byte aligned; a2.w is the total length of the list in words */
+   uint32_t vi = xo + F3B_X_VARS;
+   const uint32_t vend = vi + __float_as_uint(a2.w);
+
+   while (vi < vend) {
       /* Opaque redefinition of the per-point values: without it the compiler treats them as
        * invariant in this loop and hoists the arithmetic of EVERY case (range reductions,
        * reciprocals, ...) in front of it, to be executed for every point whatever
        * variations the xform uses (54 of 272 instructions per iteration, profiles/r01). */
       asm volatile("" : "+f"(tx), "+f"(ty), "+f"(sumsq), "+f"(rad), "+f"(atan_xy), "+f"(sina),
                         "+f"(cosa));
-      const float2 hw = *reinterpret_cast<const float2 *>(v);
+      const float2 hw = *reinterpret_cast<const float2 *>(sf + vi);
       const uint32_t w0 = __float_as_uint(hw.x);
       const uint32_t id = w0 & 0xffu;
       const float w = hw.y;
-      const float *p = v + 2;
-      v += 2 + (w0 >> 8);
-      /* the two variations almost every flame uses are tested first; the rest go through
-       * the switch. F3B_NOSPEC keeps the compiler from if-converting the small cases into
-       * straight-line code that would execute all of them for every point. */
-      if (id == 0) { /* linear */
+      const float *p = sf + vi + 2;
+      vi += 2 + (w0 >> 8);
+      /* F3B_NOSPEC keeps the compiler from if-converting the small cases into straight-line
+       * code that would execute all of them for every point. */
+      switch (id) {
+      case 0: /* linear (normally in the fixed slot; kept for completeness) */
+         F3B_NOSPEC;
          p0 = fmaf(w, tx, p0);
          p1 = fmaf(w, ty, p1);
-         continue;
-      }
-      if (id == 2) { /* spherical */
+         break;
+      case 2: { /* spherical (idem) */
+         F3B_NOSPEC;
          const float r2 = w / (sumsq + F3B_EPS);
          p0 = fmaf(r2, tx, p0);
          p1 = fmaf(r2, ty, p1);
-         continue;
-      }
-      switch (id) {
+      } break;
       case 1: /* sinusoidal */
          F3B_NOSPEC;
          p0 += w * f3b_sin(tx);
@@ -940,8 +954,8 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ xf, fl
    }
 
    if (flags & F3B_XF_HAS_POST) {
-      const float4 b0 = *reinterpret_cast<const float4 *>(xf + 12); /* p00 p10 p20 p01 */
-      const float2 b1 = *reinterpret_cast<const float2 *>(xf + 16); /* p11 p21 */
+      const float4 b0 = xf4[4];                                              /* p00 p10 p20 p01 */
+      const float2 b1 = *reinterpret_cast<const float2 *>(sf + xo + F3B_X_P11); /* p11 p21 */
       qx = fmaf(b0.x, p0, fmaf(b0.y, p1, b0.z));
       qy = fmaf(b0.w, p0, fmaf(b1.x, p1, b1.y));
    } else {
