@@ -293,17 +293,41 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    P.seed = seed;
    P.badvals = ctx->d_badvals;
 
-   const uint32_t local_groups = (n_groups - (uint32_t)rank + (uint32_t)nranks - 1) / (uint32_t)nranks;
-   if (local_groups == 0) return 0;
    const int bps = f3b_iterate_max_blocks_per_sm(max_blob);
    if (bps <= 0) return fail(ctx, "f3b_iterate: kernel does not fit with %zu bytes of shared memory", max_blob);
-   int grid = ctx->sms * bps;
-   if ((uint32_t)grid > local_groups) grid = (int)local_groups;
 
+   /* One launch per `cap` temporal samples (their warp-uniform camera and chooser constants
+    * travel through the constant cache); a still frame is one launch. */
+   const int cap = f3b_iterate_const_capacity();
+   std::vector<F3ConstSample> consts((size_t)(n_jobs < cap ? n_jobs : cap));
+   int launches = 0;
    if (stage_begin(ctx, F3B_STAGE_ITERATE)) return 1;
-   const int nl = f3b_launch_iterate(P, ctx->count_channel != 0, grid, max_blob, ctx->stream);
-   if (!nl) return fail(ctx, "chaos-game launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-   return stage_end(ctx, nl);
+   for (int j0 = 0; j0 < n_jobs; j0 += cap) {
+      const int j1 = (j0 + cap < n_jobs) ? j0 + cap : n_jobs;
+      for (int j = j0; j < j1; j++) {
+         const uint32_t *w = (const uint32_t *)((const char *)blobs + jobs[j].blob_offset);
+         const float *f = (const float *)w;
+         F3ConstSample &c = consts[(size_t)(j - j0)];
+         c.bounds = make_float4(f[F3B_H_B0], f[F3B_H_B1], f[F3B_H_B2], f[F3B_H_B3]);
+         c.cs = make_float4(f[F3B_H_WS0], f[F3B_H_HS1], f[F3B_H_RCX], f[F3B_H_RCY]);
+         c.rot = make_float4(f[F3B_H_ROT00], f[F3B_H_ROT01], f[F3B_H_ROT10], f[F3B_H_ROT11]);
+         const uint32_t *cum = w + w[F3B_H_OFF_CHOOSER];
+         c.cum = make_uint4(cum[0], cum[1], cum[2], cum[3]);
+      }
+      P.job_base = (uint32_t)j0;
+      P.group_begin = jobs[j0].first_group;
+      P.n_groups = (j1 < n_jobs) ? jobs[j1].first_group : n_groups;
+      const uint32_t span = P.n_groups - P.group_begin;
+      const uint32_t local_groups = (span + (uint32_t)nranks - 1) / (uint32_t)nranks;
+      if (span == 0) continue;
+      int grid = ctx->sms * bps;
+      if ((uint32_t)grid > local_groups) grid = (int)local_groups;
+      const int nl = f3b_launch_iterate(P, consts.data(), j1 - j0, ctx->count_channel != 0, grid,
+                                        max_blob, ctx->stream);
+      if (!nl) return fail(ctx, "chaos-game launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      launches += nl;
+   }
+   return stage_end(ctx, launches);
 }
 
 int f3b_debug_apply_xform(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int xform_index,

@@ -15,23 +15,37 @@ typedef f3b_job f3b_sample_job;
 
 #define F3B_CHAINS_PER_GROUP 256 /* = threads per block of the chaos-game kernel */
 
+/* Warp-uniform per-sample values served from the kernel parameters (constant bank 0). */
+struct F3ConstSample {
+   float4 bounds; /* b0 b1 b2 b3       (rect.c:809-812) */
+   float4 cs;     /* ws0 hs1 rcx rcy   (rect.c:819-822, rot_center) */
+   float4 rot;    /* rot00 rot01 rot10 rot11 */
+   uint4 cum;     /* first chooser row when it has <= 4 entries */
+};
+#define F3B_PARAM_SAMPLES 48  /* temporal samples per launch via parameters (3 of 4 KB) */
+
 struct F3IterateParams {
    const uint8_t *blobs;         /* device: packed temporal samples */
    const f3b_sample_job *jobs;   /* device */
    const uint32_t *group_job;    /* device: job index of every chain group */
-   uint32_t n_groups;            /* total chain groups in this launch */
-   uint32_t rank, nranks;        /* this launch runs groups g with g % nranks == rank */
+   uint32_t group_begin;         /* this launch covers chain groups [group_begin, n_groups) */
+   uint32_t n_groups;
+   uint32_t job_base;            /* job index of samp[0] */
+   uint32_t rank, nranks;        /* a rank runs the groups g with g % nranks == rank */
    float4 *hist_color;           /* [height*width] r,g,b,a sums */
    float *hist_count;            /* [height*width] 255*logvis sums; may alias nothing when !count */
    int width, height;
    int floor_adds;               /* bits 32/33: add floor(value) like the integer buckets */
    uint64_t seed;
    unsigned long long *badvals;  /* device counter */
+   F3ConstSample samp[F3B_PARAM_SAMPLES]; /* parameter-space home of the per-sample constants */
 };
 
-/* returns the number of kernel launches made (0 on error; see cudaGetLastError) */
-int f3b_launch_iterate(const F3IterateParams &p, bool count_channel, int grid_blocks,
-                       size_t smem_bytes, cudaStream_t stream);
+/* returns the number of kernel launches made (0 on error; see cudaGetLastError). `consts`
+ * holds the constants of jobs [p.job_base, p.job_base + n_consts), n_consts <= capacity */
+int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_consts,
+                       bool count_channel, int grid_blocks, size_t smem_bytes, cudaStream_t stream);
+int f3b_iterate_const_capacity(void);
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes);
 int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_index, const float *in,
                            int n, float *out, uint64_t seed, cudaStream_t stream);

@@ -22,13 +22,15 @@
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "f3b_internal.h"
 #include "f3b_variations.cuh"
 
 #define F3B_BLOCK F3B_CHAINS_PER_GROUP
 #ifndef F3B_ITER_MIN_BLOCKS
-#define F3B_ITER_MIN_BLOCKS 4 /* 64 registers, 32 warps/SM: best of {2,3,4} on B200 (profiles/r01) */
+#define F3B_ITER_MIN_BLOCKS 3 /* 80 registers, 24 warps/SM: best of {2,3,4} on B200 (profiles/r01) */
 #endif
 
 __device__ __forceinline__ void f3b_red_v4(float4 *addr, float r, float g, float b, float a) {
@@ -57,9 +59,18 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
 #define HF_PLOT_READY 4u
 #define HF_PAL_LINEAR 8u
 #define HF_FINAL 16u
+#define HF_CHOOSER_CONST 32u /* <= 4 xforms, no xaos: thresholds come from c_samp[].cum */
+
+/* Warp-uniform per-sample values (camera, small chooser row) travel in the kernel
+ * parameters and are served by the constant cache: every lane needs them every iteration,
+ * and fetching them through shared memory costs L1TEX data-pipe bandwidth per lane
+ * (128 B/clk/SM however uniform the address), which is what bounds this kernel
+ * (profiles/r01_v2: 94% of peak). A __constant__ array was tried and dropped: its speed
+ * depended on the module loading mode (31 ms lazy vs 23 ms eager for the same code). */
+#define c_samp(ci) P.samp[ci]
 
 template <bool COUNT>
-__global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_kernel(const F3IterateParams P) {
+__global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
    extern __shared__ __align__(16) uint32_t smem[];
    const float *sf = reinterpret_cast<const float *>(smem);
 
@@ -67,9 +78,12 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
    uint32_t loaded_job = 0xffffffffu;
    unsigned int bad = 0;
 
-   /* local group index lg -> global group g = lg * nranks + rank */
+   /* this launch covers groups [group_begin, n_groups); a rank runs the groups g with
+    * g % nranks == rank: local index lg -> g = first_g + lg * nranks */
+   const uint32_t first_g =
+       P.group_begin + (P.rank + P.nranks - P.group_begin % P.nranks) % P.nranks;
    for (uint32_t lg = blockIdx.x;; lg += gridDim.x) {
-      const uint64_t g64 = (uint64_t)lg * P.nranks + P.rank;
+      const uint64_t g64 = (uint64_t)first_g + (uint64_t)lg * P.nranks;
       if (g64 >= P.n_groups) break;
       const uint32_t g = (uint32_t)g64;
       const uint32_t ji = P.group_job[g];
@@ -100,9 +114,11 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
                           ((smem[F3B_H_PLOT] & F3B_PLOT_READY) ? HF_PLOT_READY : 0u) |
                           (smem[F3B_H_PALMODE] ? HF_PAL_LINEAR : 0u) |
                           ((int)smem[F3B_H_FINAL] >= 0 ? HF_FINAL : 0u) |
+                          ((!smem[F3B_H_XAOS] && smem[F3B_H_CHOOSER_STRIDE] == 4) ? HF_CHOOSER_CONST : 0u) |
                           (smem[F3B_H_CHOOSER_STRIDE] << 8) | (smem[F3B_H_CMAPSIZE] << 20);
+      uint32_t ci = ji - P.job_base; /* index into c_samp[] */
       const uint32_t cum_off = smem[F3B_H_OFF_CHOOSER];
-      const uint32_t xftab_off = smem[F3B_H_OFF_XFTAB];
+      const uint32_t xf_base = smem[F3B_H_XF_BASE], xf_stride = smem[F3B_H_XF_STRIDE];
       const uint32_t dmap_off = smem[F3B_H_OFF_PALETTE];
 
       F3Rng rng;
@@ -122,20 +138,25 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
          /* flam3.c:249-270: pick + apply, retrying a bad value up to 4 times in place */
          for (int consec = 0;;) {
             const uint32_t k = rng.next() & (F3B_CHOOSER_GRAIN - 1u);
+            /* `ci` is redefined opaquely so the constant loads below stay in the loop; hoisted,
+             * they would occupy a dozen registers across the variation code */
+            asm volatile("" : "+r"(ci));
             /* fn = number of cumulative thresholds <= k; rows are padded with 16384 */
-            const uint32_t cstride = (hf >> 8) & 0xfffu;
-            const uint32_t ro = cum_off + ((hf & HF_XAOS) ? lastxf * cstride : 0u);
-            {
-               const uint4 c = *reinterpret_cast<const uint4 *>(smem + ro); /* <= 4 xforms: no loop */
-               fn = (k >= c.x ? 1u : 0u) + (k >= c.y ? 1u : 0u) + (k >= c.z ? 1u : 0u) +
-                    (k >= c.w ? 1u : 0u);
+            if (hf & HF_CHOOSER_CONST) {
+               const uint4 c = c_samp(ci).cum;
+               fn = (k >= c.x ? 1u : 0u) + (k >= c.y ? 1u : 0u) + (k >= c.z ? 1u : 0u);
+            } else {
+               const uint32_t cstride = (hf >> 8) & 0xfffu;
+               const uint32_t ro = cum_off + ((hf & HF_XAOS) ? lastxf * cstride : 0u);
+               fn = 0;
+               for (uint32_t j = 0; j < cstride; j += 4) {
+                  const uint4 c = *reinterpret_cast<const uint4 *>(smem + ro + j);
+                  fn += (k >= c.x ? 1u : 0u) + (k >= c.y ? 1u : 0u) + (k >= c.z ? 1u : 0u) +
+                        (k >= c.w ? 1u : 0u);
+               }
             }
-            for (uint32_t j = 4; j < cstride; j += 4) {
-               const uint4 c = *reinterpret_cast<const uint4 *>(smem + ro + j);
-               fn += (k >= c.x ? 1u : 0u) + (k >= c.y ? 1u : 0u) + (k >= c.z ? 1u : 0u) +
-                     (k >= c.w ? 1u : 0u);
-            }
-            const bool isbad = f3b_apply_xform(sf, smem[xftab_off + fn], px, py, pc, qx, qy, qc, qv, rng);
+            const bool isbad =
+                f3b_apply_xform(sf, xf_base + fn * xf_stride, px, py, pc, qx, qy, qc, qv, rng);
             if (!isbad) break;
             bad++;
             if (++consec >= 5) break;
@@ -155,7 +176,8 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
             if (!apply) apply = rng.u01() < final_opacity;
             if (apply) {
                F3Rng tmp = rng;
-               const float4 f = f3b_apply_final(sf, smem[xftab_off + smem[F3B_H_FINAL]], px, py, pc, &tmp);
+               const float4 f =
+                   f3b_apply_final(sf, xf_base + smem[F3B_H_FINAL] * xf_stride, px, py, pc, &tmp);
                rng = tmp;
                qx = f.x;
                qy = f.y;
@@ -166,11 +188,12 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
          if (i < 0) continue;
 
          /* rect.c:419-441: camera */
-         const float4 bb = *reinterpret_cast<const float4 *>(sf + F3B_H_B0);  /* b0 b1 b2 b3 */
-         const float4 cs = *reinterpret_cast<const float4 *>(sf + F3B_H_WS0); /* ws0 hs1 rcx rcy */
+         asm volatile("" : "+r"(ci));
+         const float4 bb = c_samp(ci).bounds; /* b0 b1 b2 b3 */
+         const float4 cs = c_samp(ci).cs;     /* ws0 hs1 rcx rcy */
          float x = qx, y = qy;
          if (hf & HF_ROTATE) {
-            const float4 rot = *reinterpret_cast<const float4 *>(sf + F3B_H_ROT00);
+            const float4 rot = c_samp(ci).rot;
             const float dx = qx - cs.z, dy = qy - cs.w;
             x = dx * rot.x + dy * rot.y + cs.z;
             y = dx * rot.z + dy * rot.w + cs.w;
@@ -272,6 +295,8 @@ int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_in
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
 }
 
+int f3b_iterate_const_capacity(void) { return F3B_PARAM_SAMPLES; }
+
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes) {
    int nb = 0;
    cudaFuncSetAttribute(f3b_iterate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -284,9 +309,10 @@ int f3b_iterate_max_blocks_per_sm(size_t smem_bytes) {
    return nb;
 }
 
-int f3b_launch_iterate(const F3IterateParams &p, bool count_channel, int grid_blocks,
-                       size_t smem_bytes, cudaStream_t stream) {
-   if (grid_blocks <= 0) return 0;
+int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_consts,
+                       bool count_channel, int grid_blocks, size_t smem_bytes, cudaStream_t stream) {
+   if (grid_blocks <= 0 || n_consts <= 0 || n_consts > F3B_PARAM_SAMPLES) return 0;
+   for (int i = 0; i < n_consts; i++) p.samp[i] = consts[i];
    if (count_channel)
       f3b_iterate_kernel<true><<<grid_blocks, F3B_BLOCK, smem_bytes, stream>>>(p);
    else

@@ -332,8 +332,7 @@ static int pack_xform(const flam3_xform *x, uint32_t *w, size_t cap, size_t *pos
       nv += 2 + (unsigned)len;
    }
    if (flags & F3B_XF_ANGLES) flags |= F3B_XF_NEED_SQRT; /* sina/cosa divide by it */
-   r[F3B_X_FLAGS] = flags;
-   r[F3B_X_NVARS] = nv; /* total words of the variation list */
+   r[F3B_X_FLAGS] = flags | (nv << 8); /* nv = total words of the variation list */
    *pos = o;
    return 0;
 }
@@ -439,6 +438,29 @@ int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_
       o = (o + 3) & ~(size_t)3;
       tab[nstd] = (uint32_t)o;
       if (pack_xform(&cp->xform[cp->final_xform_index], w, cap, &o)) return 2;
+   }
+   /* Equal record stride: the device computes record k at base + k * stride instead of
+    * looking the offset up (one dependent shared-memory load less per iteration). Records
+    * were packed back to back; spread them out from the last one so nothing is clobbered. */
+   {
+      o = (o + 3) & ~(size_t)3;
+      size_t xstride = 0;
+      for (int i = 0; i < nxf; i++) {
+         const size_t end = (i + 1 < nxf) ? tab[i + 1] : o;
+         if (end - tab[i] > xstride) xstride = end - tab[i];
+      }
+      const size_t base = tab[0];
+      if (base + xstride * (size_t)nxf > cap) return 2;
+      for (int i = nxf - 1; i >= 0; i--) {
+         const size_t end = (i + 1 < nxf) ? tab[i + 1] : o;
+         const size_t len = end - tab[i], dst = base + xstride * (size_t)i;
+         memmove(w + dst, w + tab[i], len * 4);
+         memset(w + dst + len, 0, (xstride - len) * 4);
+      }
+      for (int i = 0; i < nxf; i++) tab[i] = (uint32_t)(base + xstride * (size_t)i);
+      o = base + xstride * (size_t)nxf;
+      w[F3B_H_XF_BASE] = (uint32_t)base;
+      w[F3B_H_XF_STRIDE] = (uint32_t)xstride;
    }
 
    /* dmap (rect.c:778-782): palette * WHITE_LEVEL * temporal filter weight */

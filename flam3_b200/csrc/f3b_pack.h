@@ -40,6 +40,8 @@ enum {
    F3B_H_NXF,           /* u32 number of xform records (nstd + 1 if final present) */
    F3B_H_PLOT,          /* u32 F3B_PLOT_*: what the bucket bump may skip */
    F3B_H_CHOOSER_STRIDE, /* u32 entries per chooser row: nstd rounded up to 4, pad = 16384 */
+   F3B_H_XF_BASE,       /* u32 word offset of xform record 0 */
+   F3B_H_XF_STRIDE,     /* u32 words between consecutive xform records (all padded alike) */
    F3B_H_SIZE = 32      /* header padded to 32 words */
 };
 
@@ -49,23 +51,23 @@ enum {
 #define F3B_PLOT_READY 1u
 
 /* xform record: word indices relative to the record start (all f32 unless noted) */
-/* Records start on a 16-byte boundary and the fixed part is laid out as five float4 groups
- * so the device reads it with LDS.128. */
+/* Records start on a 16-byte boundary. The first 12 words are what every application of
+ * the xform needs and are read with three LDS.128 (shared-memory bandwidth, 128 B/clk/SM
+ * whatever the broadcast pattern, is what bounds the kernel: profiles/r01_v2); the post
+ * affine and the pre_blur weight follow and are read only when flagged. */
 enum {
    F3B_X_C00 = 0, F3B_X_C10, F3B_X_C20, /* tx = c00*x + c10*y + c20  (variations.c:2144) */
    F3B_X_C01, F3B_X_C11, F3B_X_C21,     /* ty = c01*x + c11*y + c21 */
    F3B_X_SCOLOR,   /* color_speed * color          (variations.c:2139) */
    F3B_X_ONEMS,    /* 1 - color_speed */
    F3B_X_VIS,      /* vis_adjusted                 (variations.c:2030, interpolation.c:22) */
-   F3B_X_FLAGS,    /* u32 F3B_XF_* */
-   F3B_X_PREBLUR,  /* pre_blur weight              (variations.c:2149-2150) */
-   F3B_X_NVARS,    /* u32 total length in words of the variation records that follow */
+   F3B_X_FLAGS,    /* u32 F3B_XF_* in bits 0-7 | (length in words of the variation list) << 8 */
    F3B_X_WLINEAR,  /* weight of var0 linear: fixed-function slot, not in the record list */
    F3B_X_WSPHERICAL, /* weight of var2 spherical: fixed-function slot */
-   F3B_X_PAD0, F3B_X_PAD1,
    F3B_X_P00, F3B_X_P10, F3B_X_P20,     /* post affine (variations.c:2383-2385) */
    F3B_X_P01, F3B_X_P11, F3B_X_P21,
-   F3B_X_PAD2, F3B_X_PAD3,
+   F3B_X_PREBLUR,  /* pre_blur weight              (variations.c:2149-2150) */
+   F3B_X_PAD0,
    F3B_X_VARS      /* first variation record: {u32 id | len<<8, f32 weight, f32 params[len]}, len =
                       nparams rounded up to even */
 };

@@ -637,61 +637,39 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
  * (px,py,pc). Returns true when the result is a "bad value", in which case (qx,qy) are
  * fresh uniform draws (variations.c:2391-2395).
  */
-/* `sf` is the shared-memory copy of the packed sample, `xo` the word offset of the xform
- * record inside it. Offsets (not pointers) keep every access a 32-bit LDS address. */
-__device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, uint32_t xo, float px,
-                                                float py, float pc, float &qx, float &qy, float &qc,
-                                                float &qvis, F3Rng &rng) {
-   const float4 *xf4 = reinterpret_cast<const float4 *>(sf + xo);
-   const float4 a0 = xf4[0]; /* c00 c10 c20 c01 */
-   const float4 a1 = xf4[1]; /* c11 c21 scolor 1-s */
-   const float4 a2 = xf4[2]; /* vis flags preblur words-of-variation-list */
-   const float4 a3 = xf4[3]; /* linear weight, spherical weight, -, - */
-   qc = fmaf(a1.w, pc, a1.z);
-   qvis = a2.x;
-   const uint32_t flags = __float_as_uint(a2.y);
-
-   F3Pt pt;
-   pt.tx = fmaf(a0.x, px, fmaf(a0.y, py, a0.z));
-   pt.ty = fmaf(a0.w, px, fmaf(a1.x, py, a1.y));
-   pt.rad = 0.0f;
-   pt.atan_xy = pt.atan_yx = pt.sina = pt.cosa = 0.0f;
-
-   /* one test covers every optional per-point precalc (variations.c:2149-2170) */
-   if (flags & (F3B_XF_PREBLUR | F3B_XF_NEED_SQRT | F3B_XF_ATAN_XY | F3B_XF_ANGLES | F3B_XF_ATAN_YX)) {
-      if (flags & F3B_XF_PREBLUR) { /* var67_pre_blur, variations.c:1480 */
-         const float g = a2.z * f3b_gauss4(rng);
-         float sa, ca;
-         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &sa, &ca);
-         pt.tx += g * ca;
-         pt.ty += g * sa;
-      }
-      if (flags & F3B_XF_NEED_SQRT) pt.rad = sqrtf(pt.tx * pt.tx + pt.ty * pt.ty);
-      if (flags & F3B_XF_ATAN_XY) pt.atan_xy = atan2f(pt.tx, pt.ty);
-      if (flags & F3B_XF_ANGLES) {
-         pt.sina = pt.tx / pt.rad;
-         pt.cosa = pt.ty / pt.rad;
-      }
-      if (flags & F3B_XF_ATAN_YX) pt.atan_yx = atan2f(pt.ty, pt.tx);
+/* Optional per-point precalcs (variations.c:2149-2170): pre_blur, sqrt, atan2s, sin/cos of
+ * the angle. Out of line: the hot loop only pays a flag test when none is needed. */
+__device__ __noinline__ void f3b_precalc(const float *sf, uint32_t xo, uint32_t flags, F3Pt *ptp,
+                                         F3Rng *rngp) {
+   F3Pt pt = *ptp;
+   if (flags & F3B_XF_PREBLUR) { /* var67_pre_blur, variations.c:1480 */
+      F3Rng rng = *rngp;
+      const float g = sf[xo + F3B_X_PREBLUR] * f3b_gauss4(rng);
+      float sa, ca;
+      f3b_sincos(rng.u01() * 2.0f * F3B_PI, &sa, &ca);
+      pt.tx += g * ca;
+      pt.ty += g * sa;
+      *rngp = rng;
    }
-   pt.sumsq = pt.tx * pt.tx + pt.ty * pt.ty;
+   if (flags & F3B_XF_NEED_SQRT) pt.rad = sqrtf(pt.tx * pt.tx + pt.ty * pt.ty);
+   if (flags & F3B_XF_ATAN_XY) pt.atan_xy = atan2f(pt.tx, pt.ty);
+   if (flags & F3B_XF_ANGLES) {
+      pt.sina = pt.tx / pt.rad;
+      pt.cosa = pt.ty / pt.rad;
+   }
+   if (flags & F3B_XF_ATAN_YX) pt.atan_yx = atan2f(pt.ty, pt.tx);
+   *ptp = pt;
+}
 
+/* The variation records of one xform beyond the fixed-function slots:
+ * {id | len << 8, weight, params[len]}, len even so each starts 8-byte aligned, stored at
+ * word offsets [vi, vend) of the shared sample. Out of line for the same reason. */
+__device__ __noinline__ float2 f3b_apply_varlist(const float *sf, uint32_t vi, uint32_t vend, F3Pt pt,
+                                                 F3Rng *rngp) {
+   F3Rng rng = *rngp;
    float tx = pt.tx, ty = pt.ty, sumsq = pt.sumsq, rad = pt.rad;
    float atan_xy = pt.atan_xy, sina = pt.sina, cosa = pt.cosa;
-
-   /* Fixed-function slots: linear and spherical, the two variations nearly every flame
-    * uses, are weights in the record header and are applied without entering the loop. */
-   float p0 = a3.x * tx, p1 = a3.x * ty;
-   if (a3.y != 0.0f) {
-      const float r2 = __fdividef(a3.y, sumsq + F3B_EPS);
-      p0 = fmaf(r2, tx, p0);
-      p1 = fmaf(r2, ty, p1);
-   }
-
-   /* remaining variations: {id | len << 8, weight, params[len]} records, len even so each
-    * starts 8-byte aligned; a2.w is the total length of the list in words */
-   uint32_t vi = xo + F3B_X_VARS;
-   const uint32_t vend = vi + __float_as_uint(a2.w);
+   float p0 = 0.0f, p1 = 0.0f;
 
    while (vi < vend) {
       /* Opaque redefinition of the per-point values: without it the compiler treats them as
@@ -952,9 +930,66 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, ui
       } break;
       }
    }
+   *rngp = rng;
+   return make_float2(p0, p1);
+}
+
+/*
+ * apply_xform (variations.c:2129-2399). `sf` is the shared-memory copy of the packed
+ * sample, `xo` the word offset of the xform record inside it (offsets, not pointers, keep
+ * every access a 32-bit LDS address). Returns true when the result is a "bad value", in
+ * which case (qx,qy) are fresh uniform draws (variations.c:2391-2395).
+ *
+ * The inlined part is what EVERY application needs: three LDS.128 of coefficients, the
+ * affine map, the colour blend, and the two fixed-function variation slots (linear and
+ * spherical, which nearly every flame uses). Everything else is reached through two flag
+ * tests and runs out of line, so the hot loop's registers and instruction footprint are
+ * those of the common case.
+ */
+__device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, uint32_t xo, float px,
+                                                float py, float pc, float &qx, float &qy, float &qc,
+                                                float &qvis, F3Rng &rng) {
+   const float4 *xf4 = reinterpret_cast<const float4 *>(sf + xo);
+   const float4 a0 = xf4[0]; /* c00 c10 c20 c01 */
+   const float4 a1 = xf4[1]; /* c11 c21 scolor 1-s */
+   const float4 a2 = xf4[2]; /* vis, flags | list words << 8, linear weight, spherical weight */
+   qc = fmaf(a1.w, pc, a1.z);
+   qvis = a2.x;
+   const uint32_t flags = __float_as_uint(a2.y);
+
+   F3Pt pt;
+   pt.tx = fmaf(a0.x, px, fmaf(a0.y, py, a0.z));
+   pt.ty = fmaf(a0.w, px, fmaf(a1.x, py, a1.y));
+   pt.rad = 0.0f;
+   pt.atan_xy = pt.atan_yx = pt.sina = pt.cosa = 0.0f;
+   if (flags & (F3B_XF_PREBLUR | F3B_XF_NEED_SQRT | F3B_XF_ATAN_XY | F3B_XF_ANGLES | F3B_XF_ATAN_YX)) {
+      /* only these copies have their address taken; `pt` and `rng` stay in registers */
+      F3Rng tmp = rng;
+      F3Pt tpt = pt;
+      f3b_precalc(sf, xo, flags, &tpt, &tmp);
+      rng = tmp;
+      pt = tpt;
+   }
+   pt.sumsq = pt.tx * pt.tx + pt.ty * pt.ty;
+
+   /* fixed-function slots */
+   float p0 = a2.z * pt.tx, p1 = a2.z * pt.ty;
+   if (a2.w != 0.0f) {
+      const float r2 = __fdividef(a2.w, pt.sumsq + F3B_EPS);
+      p0 = fmaf(r2, pt.tx, p0);
+      p1 = fmaf(r2, pt.ty, p1);
+   }
+   /* the rest of the variation list, if any */
+   if (flags >> 8) {
+      F3Rng tmp = rng;
+      const float2 d = f3b_apply_varlist(sf, xo + F3B_X_VARS, xo + F3B_X_VARS + (flags >> 8), pt, &tmp);
+      rng = tmp;
+      p0 += d.x;
+      p1 += d.y;
+   }
 
    if (flags & F3B_XF_HAS_POST) {
-      const float4 b0 = xf4[4];                                              /* p00 p10 p20 p01 */
+      const float4 b0 = xf4[3];                                              /* p00 p10 p20 p01 */
       const float2 b1 = *reinterpret_cast<const float2 *>(sf + xo + F3B_X_P11); /* p11 p21 */
       qx = fmaf(b0.x, p0, fmaf(b0.y, p1, b0.z));
       qy = fmaf(b0.w, p0, fmaf(b1.x, p1, b1.y));

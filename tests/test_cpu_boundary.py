@@ -103,7 +103,7 @@ def test_packed_sample_layout(gpu, flame0):
     assert all(int(o) % 4 == 0 for o in xftab)
     # xform 0: spherical only -> fixed-function slot, empty variation list
     rec = int(xftab[0])
-    assert w[rec + 11] == 0 and fl[rec + 12] == 0.0 and fl[rec + 13] == 1.0
+    assert (w[rec + 9] >> 8) == 0 and fl[rec + 10] == 0.0 and fl[rec + 11] == 1.0
     assert abs(fl[rec + 0] - (-0.681206)) < 1e-6 and abs(fl[rec + 3] - (-0.0779465)) < 1e-6
     pal = fl[w[22]: w[22] + 1024].reshape(256, 4)
     assert np.all(pal == np.floor(pal)) and np.all(pal[:, 3] == 255.0)
