@@ -22,7 +22,9 @@ struct F3ConstSample {
    float4 rot;    /* rot00 rot01 rot10 rot11 */
    uint4 cum;     /* first chooser row when it has <= 4 entries */
 };
-#define F3B_PARAM_SAMPLES 48  /* temporal samples per launch via parameters (3 of 4 KB) */
+/* temporal samples per launch: 448 x 64 B = 28 KB of the 32 KB parameter space that CUDA
+ * 12.1+ gives sm_70+ kernels. An animation frame with 1000 temporal samples is 3 launches. */
+#define F3B_PARAM_SAMPLES 448
 
 struct F3IterateParams {
    const uint8_t *blobs;         /* device: packed temporal samples */

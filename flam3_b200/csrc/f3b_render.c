@@ -21,6 +21,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "f3b_host.h"
 
@@ -128,6 +129,107 @@ static int blob_reserve(blob_buf *b, size_t extra) {
    return 0;
 }
 
+/* ---- host-parallel packing of the temporal samples of one batch ------------------- */
+typedef struct {
+   int rc, alpha_ok; /* rc: 0 ok, 1 genome error, 2 too large, 3 camera error */
+   size_t used;      /* words */
+   uint32_t *words;  /* malloc'd packed sample */
+   f3b_camera cam;
+   double vibrancy, gamma, background[3];
+   double contrast, brightness, estimator_curve, gam_lin_thresh;
+} packed_sample;
+
+typedef struct {
+   packed_sample *s;
+   int n;
+} packed_batch;
+
+typedef struct {
+   flam3_frame *spec;
+   const f3b_frame_geom *g;
+   const double *tfilter, *tdeltas;
+   int batch_num, nts, cmap_size, floor_adds;
+   volatile int next;
+   packed_sample *out;
+} pack_job;
+
+static void packed_free(packed_batch *b) {
+   if (!b->s) return;
+   for (int i = 0; i < b->n; i++) free(b->s[i].words);
+   free(b->s);
+   b->s = NULL;
+   b->n = 0;
+}
+
+static void *pack_worker(void *arg) {
+   pack_job *j = (pack_job *)arg;
+   uint32_t *scratch = (uint32_t *)malloc(F3B_MAX_BLOB_WORDS * 4);
+   flam3_genome cp;
+   memset(&cp, 0, sizeof(cp));
+   for (;;) {
+      const int ts = __sync_fetch_and_add(&j->next, 1);
+      if (ts >= j->nts) break;
+      packed_sample *ps = &j->out[ts];
+      const int fi = j->batch_num * j->nts + ts;
+      if (!scratch) {
+         ps->rc = 2;
+         continue;
+      }
+      flam3_interpolate(j->spec->genomes, j->spec->ngenomes, j->spec->time + j->tdeltas[fi], 0, &cp);
+      if (f3b_camera_setup(&cp, j->g, &ps->cam)) {
+         ps->rc = 3;
+         continue;
+      }
+      ps->rc = f3b_pack_sample(&cp, &ps->cam, j->tfilter[fi], j->cmap_size, j->floor_adds, scratch,
+                               F3B_MAX_BLOB_WORDS, &ps->used, &ps->alpha_ok);
+      if (ps->rc) continue;
+      ps->words = (uint32_t *)malloc(ps->used * 4);
+      if (!ps->words) {
+         ps->rc = 2;
+         continue;
+      }
+      memcpy(ps->words, scratch, ps->used * 4);
+      ps->vibrancy = cp.vibrancy;
+      ps->gamma = cp.gamma;
+      ps->background[0] = cp.background[0];
+      ps->background[1] = cp.background[1];
+      ps->background[2] = cp.background[2];
+      ps->contrast = cp.contrast;
+      ps->brightness = cp.brightness;
+      ps->estimator_curve = cp.estimator_curve;
+      ps->gam_lin_thresh = cp.gam_lin_thresh;
+   }
+   clear_cp(&cp, 0);
+   free(scratch);
+   return NULL;
+}
+
+static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *tfilter,
+                      const double *tdeltas, int batch_num, int nts, int cmap_size, int floor_adds,
+                      packed_batch *out) {
+   packed_free(out);
+   out->s = (packed_sample *)calloc((size_t)nts, sizeof(packed_sample));
+   if (!out->s) return 1;
+   out->n = nts;
+   pack_job job = {spec, g, tfilter, tdeltas, batch_num, nts, cmap_size, floor_adds, 0, out->s};
+   int nthreads = 1;
+   if (nts >= 32) {
+      const char *e = getenv("F3B_HOST_THREADS");
+      long nproc = sysconf(_SC_NPROCESSORS_ONLN);
+      nthreads = e ? atoi(e) : (int)(nproc > 8 ? 8 : nproc);
+      if (nthreads > nts / 8) nthreads = nts / 8;
+      if (nthreads < 1) nthreads = 1;
+   }
+   pthread_t th[64];
+   if (nthreads > 64) nthreads = 64;
+   int started = 0;
+   for (int i = 1; i < nthreads; i++)
+      if (pthread_create(&th[started], NULL, pack_worker, &job) == 0) started++;
+   pack_worker(&job);
+   for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
+   return 0;
+}
+
 static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, int nchan,
                          int transp, stat_struct *stats, int force_count_plane) {
    const time_t tstart = time(NULL);
@@ -141,6 +243,9 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
    double *filter = NULL, *temporal_filter = NULL, *temporal_deltas = NULL;
    blob_buf blobs = {NULL, 0, 0};
    f3b_job *jobs = NULL;
+   packed_batch packed = {NULL, 0};
+   packed_sample last;
+   memset(&last, 0, sizeof(last));
    f3b_de_filters de;
    int de_alive = 0;
    double last_dmap[256][3];
@@ -269,35 +374,37 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          de_alive = 1;
       }
 
-      /* ---- pack every temporal sample of this batch (rect.c:754-884) ---- */
+      /* ---- pack every temporal sample of this batch (rect.c:754-884). Interpolating and
+       * packing a sample is independent host work (~45 us), so with many temporal samples
+       * (flam3-animate: 1000 per frame) it is spread over a few host threads. ---- */
       blobs.used = 0;
       uint64_t seed = 0x243f6a8885a308d3ull;
+      if (pack_batch(spec, &g, temporal_filter, temporal_deltas, batch_num, ntemporal_samples,
+                     cmap_size, spec->bits != 64, &packed)) {
+         fprintf(stderr, "flam3_render (B200): out of memory packing temporal samples\n");
+         goto done;
+      }
       for (int ts = 0; ts < ntemporal_samples; ts++) {
          const int fi = batch_num * ntemporal_samples + ts;
          const double color_scalar = temporal_filter[fi];
-         flam3_interpolate(spec->genomes, spec->ngenomes, spec->time + temporal_deltas[fi], 0, &cp);
-
-         if (f3b_camera_setup(&cp, &g, &cam)) goto done;
-
-         if (blob_reserve(&blobs, F3B_MAX_BLOB_WORDS + 4)) goto done;
-         size_t used = 0;
-         int alpha_ok = 0;
-         const int prv = f3b_pack_sample(&cp, &cam, color_scalar, cmap_size, spec->bits != 64,
-                                         blobs.words + blobs.used, F3B_MAX_BLOB_WORDS, &used,
-                                         &alpha_ok);
-         if (prv == 2) {
-            fprintf(stderr, "flam3_render (B200): genome too large for the packed format "
-                            "(%d xforms).\n", cp.num_xforms);
+         const packed_sample *ps = &packed.s[ts];
+         const size_t used = ps->used;
+         if (ps->rc == 3) goto done; /* camera error, message already printed */
+         if (ps->rc == 2) {
+            fprintf(stderr, "flam3_render (B200): genome too large for the packed format.\n");
             goto done;
          }
-         if (prv) {
+         if (ps->rc) {
             fprintf(stderr, "create xform distrib returned error: aborting.\n");
             goto done;
          }
-         if (!alpha_ok && !count_plane) {
+         if (!ps->alpha_ok && !count_plane) {
             rv = -2; /* caller retries with a count plane */
             goto done;
          }
+         if (blob_reserve(&blobs, used + 4)) goto done;
+         memcpy(blobs.words + blobs.used, ps->words, used * 4);
+         cam = ps->cam;
 
          /* sample budget (rect.c:830-835) */
          const double nsamples = cam.sample_density * g.image_width * g.image_height;
@@ -324,16 +431,23 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          jb->sample_id = (uint32_t)(h ^ (h >> 32));
          blobs.used += (used + 3) & ~(size_t)3;
 
-         vibrancy += cp.vibrancy;
-         gamma += cp.gamma;
-         background[0] += cp.background[0];
-         background[1] += cp.background[1];
-         background[2] += cp.background[2];
+         vibrancy += ps->vibrancy;
+         gamma += ps->gamma;
+         background[0] += ps->background[0];
+         background[1] += ps->background[1];
+         background[2] += ps->background[2];
          vib_gam_n++;
-         if (ts == ntemporal_samples - 1 && batch_num == nbatches - 1)
-            for (int j = 0; j < 256; j++)
-               for (int k = 0; k < 3; k++)
-                  last_dmap[j][k] = cp.palette[j].color[k] * 255.0 * color_scalar;
+         if (ts == ntemporal_samples - 1) {
+            /* the reference's k1/k2, DE curve and gamma threshold come from the cp of the
+             * batch's last temporal sample (rect.c:933-937, 997, 1076) */
+            last = *ps;
+            if (batch_num == nbatches - 1) {
+               const float *pal = (const float *)(ps->words + ps->words[F3B_H_OFF_PALETTE]);
+               for (int j = 0; j < 256; j++)
+                  for (int k = 0; k < 3; k++) last_dmap[j][k] = pal[j * 4 + k];
+            }
+         }
+         (void)color_scalar;
       }
 
       if (poll_progress(spec, 100.0 * batch_num / nbatches, 0)) {
@@ -363,10 +477,10 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
        * batch's LAST temporal sample, as in the reference ---- */
       f3b_density_desc dd;
       memset(&dd, 0, sizeof(dd));
-      dd.k1 = (cp.contrast * cp.brightness * 255.0 * 268.0 * (1.0 / nbatches)) / 256;
+      dd.k1 = (last.contrast * last.brightness * 255.0 * 268.0 * (1.0 / nbatches)) / 256;
       const double area = g.image_width * g.image_height / (cam.ppux * cam.ppuy);
       dd.k2 = (oversample * oversample * nbatches) /
-              (cp.contrast * area * 255.0 * cam.sample_density * sumfilt);
+              (last.contrast * area * 255.0 * cam.sample_density * sumfilt);
       dd.oversample = oversample;
       dd.int_accum = (spec->bits == 32);
       if (de_alive && de.max_filter_index > 0) {
@@ -374,7 +488,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          dd.kernel_size = de.kernel_size;
          dd.max_filtered_counts = de.max_filtered_counts;
          dd.max_filter_index = de.max_filter_index;
-         dd.curve = cp.estimator_curve;
+         dd.curve = last.estimator_curve;
          dd.coefs = de.coefs;
          dd.widths = de.widths;
       }
@@ -413,7 +527,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       fd.vibrancy = vibrancy / vib_gam_n;
       for (int k = 0; k < 3; k++) fd.background[k] = background[k] / (vib_gam_n / 256.0);
       fd.highlight_power = highpow;
-      fd.gam_lin_thresh = cp.gam_lin_thresh;
+      fd.gam_lin_thresh = last.gam_lin_thresh;
       const size_t stride = (size_t)g.out_width * nchan * bytes_per_channel;
       if (g_device_only) {
          if (f3b_finish_device(ctx, &fd, NULL)) goto gpu_error;
@@ -450,6 +564,7 @@ done:
    free(filter);
    free(blobs.words);
    free(jobs);
+   packed_free(&packed);
    clear_cp(&cp, 0);
    stats->render_seconds = (int)(time(NULL) - tstart);
    return rv;
