@@ -29,7 +29,8 @@ struct f3b_ctx {
    int width = 0, height = 0;
    int count_channel = 1;
    DevBuf hist_color, hist_count, accum, image;
-   DevBuf blobs, jobs, groups, de_coefs, de_radius, filter;
+   DevBuf blobs, jobs, groups, de_coefs, de_radius, filter, de_kidx, de_tiles;
+   bool accum_zero_pending = false; /* accumulators are logically zero, memset not yet issued */
    unsigned long long *d_badvals = nullptr;
 
    /* instrumentation */
@@ -150,7 +151,7 @@ void f3b_ctx_destroy(f3b_ctx *ctx) {
    cudaStreamSynchronize(ctx->stream);
    DevBuf *bufs[] = {&ctx->hist_color, &ctx->hist_count, &ctx->accum,    &ctx->image,
                      &ctx->blobs,      &ctx->jobs,       &ctx->groups,   &ctx->de_coefs,
-                     &ctx->de_radius,  &ctx->filter};
+                     &ctx->de_radius,  &ctx->filter,     &ctx->de_kidx,  &ctx->de_tiles};
    for (DevBuf *b : bufs)
       if (b->p) cudaFree(b->p);
    if (ctx->d_badvals) cudaFree(ctx->d_badvals);
@@ -204,10 +205,19 @@ int f3b_hist_clear(f3b_ctx *ctx) {
    return 0;
 }
 
+/* The clear is deferred: the first density pass of a frame writes every accumulator, so the
+ * memset (and that pass's read of the zeros) is only issued when something else looks first. */
 int f3b_accum_clear(f3b_ctx *ctx) {
+   ctx->accum_zero_pending = true;
+   return 0;
+}
+
+static int accum_materialize(f3b_ctx *ctx) {
+   if (!ctx->accum_zero_pending) return 0;
    const size_t n = (size_t)ctx->width * ctx->height;
    CK(cudaSetDevice(ctx->device));
    CK(cudaMemsetAsync(ctx->accum.p, 0, n * sizeof(float4), ctx->stream));
+   ctx->accum_zero_pending = false;
    return 0;
 }
 
@@ -433,6 +443,19 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
       P.max_filter_index = d->max_filter_index;
       P.curve = (float)d->curve;
    }
+   if (P.n_kernels > 0) {
+      const size_t tiles = (size_t)((ctx->width + 31) / 32) * ((ctx->height + 31) / 32);
+      if (ensure(ctx, ctx->de_kidx, (size_t)ctx->width * ctx->height * sizeof(uint16_t))) return 1;
+      if (ensure(ctx, ctx->de_tiles, tiles * sizeof(int))) return 1;
+      P.de_kidx = (uint16_t *)ctx->de_kidx.p;
+      P.tile_maxrad = (int *)ctx->de_tiles.p;
+   }
+   if (ctx->accum_zero_pending && P.n_kernels > 0 && row0 == 0 && row1 == ctx->height) {
+      P.overwrite_accum = 1;
+      ctx->accum_zero_pending = false;
+   } else if (accum_materialize(ctx)) {
+      return 1;
+   }
    if (stage_begin(ctx, F3B_STAGE_DENSITY)) return 1;
    const int nl = f3b_launch_density(P, ctx->stream);
    if (!nl) return fail(ctx, "density launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -447,6 +470,7 @@ int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out) {
    if (!ctx || !d) return 1;
    if (!ctx->accum.p) return fail(ctx, "f3b_finish: f3b_frame_begin not called");
    CK(cudaSetDevice(ctx->device));
+   if (accum_materialize(ctx)) return 1;
    if (d->nchan != 3 && d->nchan != 4) return fail(ctx, "f3b_finish: nchan must be 3 or 4");
    if (d->bytes_per_channel != 1 && d->bytes_per_channel != 2)
       return fail(ctx, "f3b_finish: bytes_per_channel must be 1 or 2");
@@ -547,6 +571,7 @@ int f3b_accum_upload(f3b_ctx *ctx, const float *acc4) {
    if (!ctx || !ctx->accum.p) return 1;
    CK(cudaSetDevice(ctx->device));
    const size_t n = (size_t)ctx->width * ctx->height;
+   ctx->accum_zero_pending = false;
    CK(cudaMemcpyAsync(ctx->accum.p, acc4, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
    CK(cudaStreamSynchronize(ctx->stream));
    return 0;
@@ -556,6 +581,7 @@ int f3b_accum_download(f3b_ctx *ctx, float *acc4) {
    if (!ctx || !ctx->accum.p) return 1;
    CK(cudaSetDevice(ctx->device));
    const size_t n = (size_t)ctx->width * ctx->height;
+   if (accum_materialize(ctx)) return 1;
    CK(cudaMemcpyAsync(acc4, ctx->accum.p, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
    CK(cudaStreamSynchronize(ctx->stream));
    return 0;
@@ -565,7 +591,10 @@ void *f3b_hist_color_ptr(f3b_ctx *ctx) { return ctx ? ctx->hist_color.p : nullpt
 void *f3b_hist_count_ptr(f3b_ctx *ctx) {
    return (ctx && ctx->count_channel) ? ctx->hist_count.p : nullptr;
 }
-void *f3b_accum_ptr(f3b_ctx *ctx) { return ctx ? ctx->accum.p : nullptr; }
+void *f3b_accum_ptr(f3b_ctx *ctx) {
+   if (!ctx || accum_materialize(ctx)) return nullptr;
+   return ctx->accum.p;
+}
 void *f3b_stream_ptr(f3b_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int f3b_stage_stats(f3b_ctx *ctx, int stage, double *ms, uint64_t *launches) {

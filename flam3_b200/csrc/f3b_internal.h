@@ -67,6 +67,13 @@ struct F3DensityParams {
    int n_kernels, kernel_size, max_radius;
    int max_filtered_counts, max_filter_index;
    float curve;
+   /* scratch planes of the two-pass density estimator (device) */
+   uint16_t *de_kidx;         /* [height*width] kernel index per bucket, 0xffff = not a source */
+   int *tile_maxrad;          /* [tiles_y*tiles_x] largest radius >= 1 in each 32x32 tile */
+   int overwrite_accum;       /* first batch of a frame: write the accumulators, do not add */
+   /* filled by f3b_launch_density */
+   int class_row_begin, class_row_end; /* rows classified: the target rows +- max_radius */
+   int class_tile_y0, class_tile_y1, gather_tile_y0;
 };
 int f3b_launch_density(const F3DensityParams &p, cudaStream_t stream);
 

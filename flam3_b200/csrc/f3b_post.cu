@@ -7,22 +7,18 @@
  * (rect.c:1137-1247) with palettes.c:199-349 (calc_alpha / calc_newrgb / hsv).
  *
  * Density estimation is reformulated from the reference's per-source SCATTER (racy across
- * thread swaths, rect.c:148-168) into a race-free per-target GATHER: a CTA stages a tile of
- * buckets plus a halo of the maximum kernel radius in shared memory, converts every staged
- * bucket once to (log-scaled colour, kernel index), then each thread sums the kernels of
- * the neighbours that reach it. The gather window is clamped to the largest radius
- * actually present in the staged region, so dense regions (radius 0-2) cost a few taps
- * while sparse ones pay for their wide kernels, as in the reference.
+ * thread swaths, rect.c:148-168) into a streaming classify pass plus a race-free per-target
+ * GATHER over the tiles that wide kernels can reach; see the section below.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "f3b_internal.h"
 
-#define DE_TX 32
-#define DE_TY 16
-#define DE_THREADS (DE_TX * DE_TY)
-#define DE_EMPTY 0xffu
+#define DE_TILE 32       /* density-estimation tile edge, buckets */
+#define DE_ROWS 8        /* thread rows per CTA: 32x8 threads, 4 buckets each */
+#define DE_PER_THREAD (DE_TILE / DE_ROWS)
+#define DE_NO_SOURCE 0xffffu
 
 /* ---------------------------------------------------------------------------------- */
 /* log scale without density estimation (rect.c:947-974)                               */
@@ -51,139 +47,243 @@ __global__ void __launch_bounds__(256) f3b_logscale_kernel(const F3DensityParams
 }
 
 /* ---------------------------------------------------------------------------------- */
-/* density estimation, gather form                                                     */
+/* density estimation: classify (streaming) + gather (active tiles only)               */
 /* ---------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(DE_THREADS) f3b_density_kernel(const F3DensityParams P) {
-   extern __shared__ __align__(16) unsigned char de_smem[];
-   const int R = P.max_radius;
+/*
+ * Pass 1, f3b_de_classify_kernel — one streaming sweep over the buckets. Every bucket gets
+ * its kernel index (rect.c:84-121) written to a 2-byte plane; a bucket whose kernel has
+ * radius 0 (the dense majority of a converged frame) contributes only to itself, so its
+ * log-scaled colour times the centre coefficient goes straight into the accumulator here.
+ * Each 32x32 tile records the largest radius >= 1 it holds.
+ *
+ * Pass 2, f3b_de_gather_kernel — one CTA per 32x32 tile; tiles that no wide kernel can reach
+ * (the recorded radii of the tile and its neighbours are all 0) exit at once. The others
+ * stage the sources with radius >= 1 of tile + halo in shared memory and every target sums
+ * the kernels that reach it, in a fixed order, so the result is deterministic.
+ *
+ * Algorithmic traffic per bucket: 16 B histogram read + 16 B accumulator write (+16 B read
+ * when this is not the first batch) + 2 B index plane.
+ */
+__device__ __forceinline__ float f3b_de_count(const F3DensityParams &P, int x, int y) {
+   if (x < 0 || x >= P.width || y < 0 || y >= P.height) return 0.0f;
+   const size_t gi = (size_t)x + (size_t)P.width * y;
+   return P.hist_count ? __ldg(P.hist_count + gi) : __ldg(&P.hist_color[gi].w);
+}
+
+__global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(const F3DensityParams P) {
    const int os = P.oversample;
    const int ss = os / 2; /* floor(oversample/2), rect.c:61 */
-   const int SW = DE_TX + 2 * R, SH = DE_TY + 2 * R; /* staged bucket region */
-   const int CW = SW + 2 * ss, CH = SH + 2 * ss;     /* staged count region  */
+   const double scfact = (os & 1) ? 1.0 : ((double)os / (os + 1.0)) * ((double)os / (os + 1.0));
+   const int gx = blockIdx.x * DE_TILE + threadIdx.x;
+   const int tile_y = P.class_tile_y0 + blockIdx.y;
+   int my_maxrad = 0;
 
-   float4 *s_col = reinterpret_cast<float4 *>(de_smem);
-   float *s_cnt = reinterpret_cast<float *>(s_col + (size_t)SW * SH);
-   uint16_t *s_kidx = reinterpret_cast<uint16_t *>(s_cnt + (size_t)CW * CH);
-   uint8_t *s_rad = reinterpret_cast<uint8_t *>(s_kidx + (size_t)SW * SH);
-   __shared__ int s_maxrad;
-
-   const int tid = threadIdx.y * DE_TX + threadIdx.x;
-   const int x0 = blockIdx.x * DE_TX - R; /* bucket coords of staged (0,0) */
-   const int y0 = P.row_begin + blockIdx.y * DE_TY - R;
-   const bool have_count = (P.hist_count != nullptr);
-
-   if (tid == 0) s_maxrad = 0;
-
-   /* stage counts (only needed separately when oversample > 1 or a count plane exists) */
-   for (int i = tid; i < CW * CH; i += DE_THREADS) {
-      const int cx = x0 - ss + (i % CW), cy = y0 - ss + (i / CW);
-      float c = 0.0f;
-      if (cx >= 0 && cx < P.width && cy >= 0 && cy < P.height) {
-         const size_t gi = (size_t)cx + (size_t)P.width * cy;
-         c = have_count ? P.hist_count[gi] : P.hist_color[gi].w;
+   float4 c[DE_PER_THREAD];
+   int gy[DE_PER_THREAD];
+   bool live[DE_PER_THREAD];
+#pragma unroll
+   for (int q = 0; q < DE_PER_THREAD; q++) {
+      gy[q] = tile_y * DE_TILE + threadIdx.y + q * DE_ROWS;
+      live[q] = gx < P.width && gy[q] >= P.class_row_begin && gy[q] < P.class_row_end;
+      c[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live[q]) c[q] = P.hist_color[(size_t)gx + (size_t)P.width * gy[q]];
+   }
+#pragma unroll
+   for (int q = 0; q < DE_PER_THREAD; q++) {
+      if (!live[q]) continue;
+      const size_t gi = (size_t)gx + (size_t)P.width * gy[q];
+      const float cnt = P.hist_count ? P.hist_count[gi] : c[q].w;
+      unsigned kidx = DE_NO_SOURCE;
+      float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool has_self = false;
+      /* source range of the reference loops (rect.c:79-80), minus its out-of-range row */
+      if (gx >= os - 1 && gx <= P.width - os && gy[q] >= os - 1 && gy[q] <= P.height - os &&
+          cnt != 0.0f && c[q].w != 0.0f) {
+         double f = (double)cnt;
+         if (ss > 0) {
+            f = 0.0;
+            for (int jj = -ss; jj <= ss; jj++)
+               for (int ii = -ss; ii <= ss; ii++) f += (double)f3b_de_count(P, gx + ii, gy[q] + jj);
+         }
+         f *= (1.0 / 255.0);
+         f *= scfact;
+         int k;
+         if (f > (double)P.max_filtered_counts) k = P.max_filter_index;
+         else if (f <= 100.0) k = (int)ceil(f) - 1;
+         else k = 100 + (int)floor(pow(f - 100.0, (double)P.curve));
+         if (k > P.max_filter_index) k = P.max_filter_index;
+         if (k < 0) k = 0;
+         kidx = (unsigned)k;
+         const int rad = __ldg(P.de_radius + k);
+         if (rad == 0) {
+            const float ls = (P.k1 * log1pf(c[q].w * P.k2)) / c[q].w;
+            const float coef = __ldg(P.de_coefs + (size_t)k * P.kernel_size) * ls;
+            self = make_float4(coef * c[q].x, coef * c[q].y, coef * c[q].z, coef * c[q].w);
+            has_self = true;
+         } else {
+            my_maxrad = max(my_maxrad, rad);
+         }
       }
-      s_cnt[i] = c;
+      P.de_kidx[gi] = (uint16_t)kidx;
+      if (gy[q] >= P.row_begin && gy[q] < P.row_end) {
+         if (P.overwrite_accum) {
+            P.accum[gi] = self;
+         } else if (has_self) {
+            float4 a = P.accum[gi];
+            a.x += self.x;
+            a.y += self.y;
+            a.z += self.z;
+            a.w += self.w;
+            P.accum[gi] = a;
+         }
+      }
+   }
+   /* largest wide-kernel radius of this tile */
+   for (int o = 16; o > 0; o >>= 1) my_maxrad = max(my_maxrad, __shfl_xor_sync(0xffffffffu, my_maxrad, o));
+   __shared__ int s_rad[DE_ROWS];
+   if (threadIdx.x == 0) s_rad[threadIdx.y] = my_maxrad;
+   __syncthreads();
+   if (threadIdx.x == 0 && threadIdx.y == 0) {
+      int m = 0;
+      for (int i = 0; i < DE_ROWS; i++) m = max(m, s_rad[i]);
+      P.tile_maxrad[(size_t)tile_y * gridDim.x + blockIdx.x] = m;
+   }
+}
+
+__global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_kernel(const F3DensityParams P) {
+   extern __shared__ __align__(16) unsigned char de_smem[];
+   __shared__ int s_reach;
+   const int tiles_x = gridDim.x;
+   const int tile_y = P.gather_tile_y0 + blockIdx.y;
+   const int tid = threadIdx.y * DE_TILE + threadIdx.x;
+
+   /* the widest kernel that can reach this tile */
+   if (tid == 0) s_reach = 0;
+   __syncthreads();
+   {
+      const int nt = (P.max_radius + DE_TILE - 1) / DE_TILE, span = 2 * nt + 1;
+      int m = 0;
+      for (int i = tid; i < span * span; i += DE_TILE * DE_ROWS) {
+         const int tx = (int)blockIdx.x + (i % span) - nt, ty = tile_y + (i / span) - nt;
+         if (tx >= 0 && tx < tiles_x && ty >= P.class_tile_y0 && ty < P.class_tile_y1)
+            m = max(m, P.tile_maxrad[(size_t)ty * tiles_x + tx]);
+      }
+      if (m) atomicMax(&s_reach, m);
    }
    __syncthreads();
+   const int R = s_reach;
+   if (R == 0) return;
 
-   /* prep: every staged bucket -> (scaled colour, kernel index, radius) */
-   const double scfact = (os & 1) ? 1.0 : ((double)os / (os + 1.0)) * ((double)os / (os + 1.0));
-   int my_maxrad = 0;
-   for (int i = tid; i < SW * SH; i += DE_THREADS) {
+   const int SW = DE_TILE + 2 * R;
+   float4 *s_col = reinterpret_cast<float4 *>(de_smem);
+   uint32_t *s_meta = reinterpret_cast<uint32_t *>(s_col + (size_t)SW * SW); /* kidx | radius<<16 */
+   int *s_rowmax = reinterpret_cast<int *>(s_meta + (size_t)SW * SW); /* widest kernel per staged row */
+   const int x0 = blockIdx.x * DE_TILE - R, y0 = tile_y * DE_TILE - R;
+
+   for (int i = tid; i < SW; i += DE_TILE * DE_ROWS) s_rowmax[i] = 0;
+   __syncthreads();
+   for (int i = tid; i < SW * SW; i += DE_TILE * DE_ROWS) {
       const int lx = i % SW, ly = i / SW;
       const int gx = x0 + lx, gy = y0 + ly;
+      uint32_t meta = 0; /* radius 0 = nothing to gather from here */
       float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
-      unsigned rad = DE_EMPTY;
-      unsigned kidx = 0;
-      /* source range of the reference loops (rect.c:79-80), minus its out-of-range row */
-      if (gx >= os - 1 && gx <= P.width - os && gy >= os - 1 && gy <= P.height - os) {
+      if (gx >= 0 && gx < P.width && gy >= P.class_row_begin && gy < P.class_row_end) {
          const size_t gi = (size_t)gx + (size_t)P.width * gy;
-         const float4 c = P.hist_color[gi];
-         const float cnt = s_cnt[(lx + ss) + (ly + ss) * CW];
-         if (cnt != 0.0f && c.w != 0.0f) {
-            double f = 0.0;
-            for (int jj = -ss; jj <= ss; jj++)
-               for (int ii = -ss; ii <= ss; ii++)
-                  f += (double)s_cnt[(lx + ss + ii) + (ly + ss + jj) * CW];
-            f *= (1.0 / 255.0);
-            f *= scfact;
-            int k;
-            if (f > (double)P.max_filtered_counts) k = P.max_filter_index;
-            else if (f <= 100.0) k = (int)ceil(f) - 1;
-            else k = 100 + (int)floor(pow(f - 100.0, (double)P.curve));
-            if (k > P.max_filter_index) k = P.max_filter_index;
-            if (k < 0) k = 0;
-            kidx = (unsigned)k;
-            rad = P.de_radius[k];
-            const float ls = (P.k1 * log1pf(c.w * P.k2)) / c.w;
-            col = make_float4(c.x * ls, c.y * ls, c.z * ls, c.w * ls);
-            my_maxrad = max(my_maxrad, (int)rad);
+         const unsigned k = P.de_kidx[gi];
+         if (k != DE_NO_SOURCE) {
+            const unsigned rad = __ldg(P.de_radius + k);
+            if (rad) {
+               const float4 c = P.hist_color[gi];
+               const float ls = (P.k1 * log1pf(c.w * P.k2)) / c.w;
+               col = make_float4(c.x * ls, c.y * ls, c.z * ls, c.w * ls);
+               meta = k | (rad << 16);
+               if ((int)rad > s_rowmax[ly]) atomicMax(&s_rowmax[ly], (int)rad);
+            }
          }
       }
       s_col[i] = col;
-      s_kidx[i] = (uint16_t)kidx;
-      s_rad[i] = (uint8_t)rad;
+      s_meta[i] = meta;
    }
-   if (my_maxrad) atomicMax(&s_maxrad, my_maxrad);
    __syncthreads();
 
-   const int gx = blockIdx.x * DE_TX + threadIdx.x;
-   const int gy = P.row_begin + blockIdx.y * DE_TY + threadIdx.y;
-   if (gx >= P.width || gy >= P.row_end) return;
-
-   const int Rb = s_maxrad;
-   const int cx = threadIdx.x + R, cy = threadIdx.y + R;
-   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-   for (int dy = -Rb; dy <= Rb; dy++) {
-      const int ady = abs(dy);
-      const int rowbase = (cy + dy) * SW + cx;
-      for (int dx = -Rb; dx <= Rb; dx++) {
-         const int n = rowbase + dx;
-         const unsigned rn = s_rad[n];
-         const int adx = abs(dx);
-         const int hi = max(adx, ady), lo = min(adx, ady);
-         if (rn == DE_EMPTY || hi > (int)rn) continue;
-         /* octant-packed coefficient: index jj*(jj+1)/2 + ii with jj >= ii (filters.c:362) */
-         const float coef =
-             __ldg(P.de_coefs + (size_t)s_kidx[n] * P.kernel_size + (hi * (hi + 1)) / 2 + lo);
-         const float4 c = s_col[n];
-         acc.x += coef * c.x;
-         acc.y += coef * c.y;
-         acc.z += coef * c.z;
-         acc.w += coef * c.w;
+   const int gx = blockIdx.x * DE_TILE + threadIdx.x;
+   if (gx >= P.width) return;
+#pragma unroll 1
+   for (int q = 0; q < DE_PER_THREAD; q++) {
+      const int ly = threadIdx.y + q * DE_ROWS;
+      const int gy = tile_y * DE_TILE + ly;
+      if (gy < P.row_begin || gy >= P.row_end) continue;
+      const int cx = threadIdx.x + R, cy = ly + R;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool any = false;
+      for (int dy = -R; dy <= R; dy++) {
+         const int ady = abs(dy);
+         /* the whole warp shares cy: rows whose widest kernel is shorter than the vertical
+          * distance are skipped, the others are scanned only as far as that kernel reaches */
+         const int rm = s_rowmax[cy + dy];
+         if (rm < ady) continue;
+         const int rowbase = (cy + dy) * SW + cx;
+         for (int dx = -rm; dx <= rm; dx++) {
+            const int n = rowbase + dx;
+            const uint32_t meta = s_meta[n];
+            const int rn = (int)(meta >> 16);
+            const int adx = abs(dx);
+            const int hi = max(adx, ady), lo = min(adx, ady);
+            if (hi > rn || rn == 0) continue;
+            /* octant-packed coefficient: index jj*(jj+1)/2 + ii with jj >= ii (filters.c:362) */
+            const float coef = __ldg(P.de_coefs + (size_t)(meta & 0xffffu) * P.kernel_size +
+                                     (hi * (hi + 1)) / 2 + lo);
+            const float4 c = s_col[n];
+            acc.x += coef * c.x;
+            acc.y += coef * c.y;
+            acc.z += coef * c.z;
+            acc.w += coef * c.w;
+            any = true;
+         }
       }
+      if (!any) continue;
+      const size_t gi = (size_t)gx + (size_t)P.width * gy;
+      float4 a = P.accum[gi];
+      a.x += acc.x;
+      a.y += acc.y;
+      a.z += acc.z;
+      a.w += acc.w;
+      P.accum[gi] = a;
    }
-   const size_t gi = (size_t)gx + (size_t)P.width * gy;
-   float4 a = P.accum[gi];
-   a.x += acc.x;
-   a.y += acc.y;
-   a.z += acc.z;
-   a.w += acc.w;
-   P.accum[gi] = a;
 }
 
-int f3b_launch_density(const F3DensityParams &p, cudaStream_t stream) {
-   if (p.row_end <= p.row_begin) return 1;
-   if (p.n_kernels <= 0) {
-      const size_t i0 = (size_t)p.width * p.row_begin, n = (size_t)p.width * p.row_end;
+int f3b_launch_density(const F3DensityParams &p_in, cudaStream_t stream) {
+   if (p_in.row_end <= p_in.row_begin) return 1;
+   if (p_in.n_kernels <= 0) {
+      const size_t i0 = (size_t)p_in.width * p_in.row_begin, n = (size_t)p_in.width * p_in.row_end;
       int blocks = (int)((n - i0 + 255) / 256);
       if (blocks > 148 * 16) blocks = 148 * 16;
-      f3b_logscale_kernel<<<blocks, 256, 0, stream>>>(p, i0, n);
+      f3b_logscale_kernel<<<blocks, 256, 0, stream>>>(p_in, i0, n);
       return cudaGetLastError() == cudaSuccess ? 1 : 0;
    }
-   const int R = p.max_radius, ss = p.oversample / 2;
-   const size_t SW = DE_TX + 2 * R, SH = DE_TY + 2 * R;
-   const size_t CW = SW + 2 * ss, CH = SH + 2 * ss;
-   size_t smem = SW * SH * sizeof(float4) + CW * CH * sizeof(float) + SW * SH * 2 + SW * SH;
+   F3DensityParams p = p_in;
+   const int R = p.max_radius;
+   /* kernel indices are needed R rows beyond the target rows (sources that reach in) */
+   p.class_row_begin = p.row_begin - R < 0 ? 0 : p.row_begin - R;
+   p.class_row_end = p.row_end + R > p.height ? p.height : p.row_end + R;
+   p.class_tile_y0 = p.class_row_begin / DE_TILE;
+   p.class_tile_y1 = (p.class_row_end + DE_TILE - 1) / DE_TILE;
+   p.gather_tile_y0 = p.row_begin / DE_TILE;
+   const int gather_tile_y1 = (p.row_end + DE_TILE - 1) / DE_TILE;
+   const int tiles_x = (p.width + DE_TILE - 1) / DE_TILE;
+
+   const size_t SW = DE_TILE + 2 * R;
+   size_t smem = SW * SW * (sizeof(float4) + sizeof(uint32_t)) + SW * sizeof(int);
    smem = (smem + 15) & ~(size_t)15;
    if (smem > 220 * 1024) return 0;
-   if (cudaFuncSetAttribute(f3b_density_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+   if (cudaFuncSetAttribute(f3b_de_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)smem) != cudaSuccess)
       return 0;
-   dim3 grid((p.width + DE_TX - 1) / DE_TX, (p.row_end - p.row_begin + DE_TY - 1) / DE_TY);
-   dim3 block(DE_TX, DE_TY);
-   f3b_density_kernel<<<grid, block, smem, stream>>>(p);
-   return cudaGetLastError() == cudaSuccess ? 1 : 0;
+   dim3 block(DE_TILE, DE_ROWS);
+   f3b_de_classify_kernel<<<dim3(tiles_x, p.class_tile_y1 - p.class_tile_y0), block, 0, stream>>>(p);
+   if (cudaGetLastError() != cudaSuccess) return 0;
+   f3b_de_gather_kernel<<<dim3(tiles_x, gather_tile_y1 - p.gather_tile_y0), block, smem, stream>>>(p);
+   return cudaGetLastError() == cudaSuccess ? 2 : 0;
 }
 
 /* ---------------------------------------------------------------------------------- */
