@@ -323,6 +323,16 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          c.rot = make_float4(f[F3B_H_ROT00], f[F3B_H_ROT01], f[F3B_H_ROT10], f[F3B_H_ROT11]);
          const uint32_t *cum = w + w[F3B_H_OFF_CHOOSER];
          c.cum = make_uint4(cum[0], cum[1], cum[2], cum[3]);
+         const uint32_t hf =
+             (w[F3B_H_XAOS] ? F3B_HF_XAOS : 0u) | (w[F3B_H_ROTATE] ? F3B_HF_ROTATE : 0u) |
+             ((w[F3B_H_PLOT] & F3B_PLOT_READY) ? F3B_HF_PLOT_READY : 0u) |
+             (w[F3B_H_PALMODE] ? F3B_HF_PAL_LINEAR : 0u) | ((int)w[F3B_H_FINAL] >= 0 ? F3B_HF_FINAL : 0u) |
+             ((!w[F3B_H_XAOS] && w[F3B_H_CHOOSER_STRIDE] == 4) ? F3B_HF_CHOOSER_CONST : 0u) |
+             (w[F3B_H_CHOOSER_STRIDE] << 8) | (w[F3B_H_CMAPSIZE] << 20);
+         const uint32_t final_off =
+             (int)w[F3B_H_FINAL] >= 0 ? w[F3B_H_XF_BASE] + w[F3B_H_FINAL] * w[F3B_H_XF_STRIDE] : 0u;
+         c.lay = make_uint4(hf, w[F3B_H_XF_BASE] | (w[F3B_H_XF_STRIDE] << 16),
+                            w[F3B_H_OFF_PALETTE] | (w[F3B_H_OFF_CHOOSER] << 16), final_off);
       }
       P.job_base = (uint32_t)j0;
       P.group_begin = jobs[j0].first_group;

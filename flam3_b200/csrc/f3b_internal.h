@@ -21,10 +21,19 @@ struct F3ConstSample {
    float4 cs;     /* ws0 hs1 rcx rcy   (rect.c:819-822, rot_center) */
    float4 rot;    /* rot00 rot01 rot10 rot11 */
    uint4 cum;     /* first chooser row when it has <= 4 entries */
+   uint4 lay;     /* F3B_HF_* flags | chooser stride << 8 | cmap_size << 20;
+                     xform base | stride << 16;  palette offset | chooser offset << 16;
+                     offset of the final xform's record (all in blob words) */
 };
-/* temporal samples per launch: 448 x 64 B = 28 KB of the 32 KB parameter space that CUDA
+#define F3B_HF_XAOS 1u
+#define F3B_HF_ROTATE 2u
+#define F3B_HF_PLOT_READY 4u
+#define F3B_HF_PAL_LINEAR 8u
+#define F3B_HF_FINAL 16u
+#define F3B_HF_CHOOSER_CONST 32u /* <= 4 xforms, no xaos: thresholds come from samp[].cum */
+/* temporal samples per launch: 352 x 80 B = 27.5 KB of the 32 KB parameter space that CUDA
  * 12.1+ gives sm_70+ kernels. An animation frame with 1000 temporal samples is 3 launches. */
-#define F3B_PARAM_SAMPLES 448
+#define F3B_PARAM_SAMPLES 352
 
 struct F3IterateParams {
    const uint8_t *blobs;         /* device: packed temporal samples */

@@ -54,12 +54,12 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
 }
 
 /* per-sample constants folded into one register */
-#define HF_XAOS 1u
-#define HF_ROTATE 2u
-#define HF_PLOT_READY 4u
-#define HF_PAL_LINEAR 8u
-#define HF_FINAL 16u
-#define HF_CHOOSER_CONST 32u /* <= 4 xforms, no xaos: thresholds come from c_samp[].cum */
+#define HF_XAOS F3B_HF_XAOS
+#define HF_ROTATE F3B_HF_ROTATE
+#define HF_PLOT_READY F3B_HF_PLOT_READY
+#define HF_PAL_LINEAR F3B_HF_PAL_LINEAR
+#define HF_FINAL F3B_HF_FINAL
+#define HF_CHOOSER_CONST F3B_HF_CHOOSER_CONST
 
 /* Warp-uniform per-sample values (camera, small chooser row) travel in the kernel
  * parameters and are served by the constant cache: every lane needs them every iteration,
@@ -107,19 +107,12 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
       const int n_store = (int)(base + (chain < rem ? 1u : 0u));
       if (n_store == 0) continue;
 
-      /* Header: flags, chooser stride and palette size share one register; the camera is
-       * re-read from shared memory (two LDS.128) when a point is plotted instead of living
-       * in six registers across the variation code. */
-      const uint32_t hf = (smem[F3B_H_XAOS] ? HF_XAOS : 0u) | (smem[F3B_H_ROTATE] ? HF_ROTATE : 0u) |
-                          ((smem[F3B_H_PLOT] & F3B_PLOT_READY) ? HF_PLOT_READY : 0u) |
-                          (smem[F3B_H_PALMODE] ? HF_PAL_LINEAR : 0u) |
-                          ((int)smem[F3B_H_FINAL] >= 0 ? HF_FINAL : 0u) |
-                          ((!smem[F3B_H_XAOS] && smem[F3B_H_CHOOSER_STRIDE] == 4) ? HF_CHOOSER_CONST : 0u) |
-                          (smem[F3B_H_CHOOSER_STRIDE] << 8) | (smem[F3B_H_CMAPSIZE] << 20);
+      /* Flags, chooser stride and palette size share one register (made opaque, or the
+       * compiler splits it into a register per flag and spills them); the blob offsets are
+       * fetched from the constant bank where they are used. */
       uint32_t ci = ji - P.job_base; /* index into c_samp[] */
-      const uint32_t cum_off = smem[F3B_H_OFF_CHOOSER];
-      const uint32_t xf_base = smem[F3B_H_XF_BASE], xf_stride = smem[F3B_H_XF_STRIDE];
-      const uint32_t dmap_off = smem[F3B_H_OFF_PALETTE];
+      uint32_t hf = c_samp(ci).lay.x;
+      asm volatile("" : "+r"(hf));
 
       F3Rng rng;
       f3b_rng_seed(rng, P.seed, job.sample_id, chain);
@@ -147,7 +140,7 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
                fn = (k >= c.x ? 1u : 0u) + (k >= c.y ? 1u : 0u) + (k >= c.z ? 1u : 0u);
             } else {
                const uint32_t cstride = (hf >> 8) & 0xfffu;
-               const uint32_t ro = cum_off + ((hf & HF_XAOS) ? lastxf * cstride : 0u);
+               const uint32_t ro = (c_samp(ci).lay.z >> 16) + ((hf & HF_XAOS) ? lastxf * cstride : 0u);
                fn = 0;
                for (uint32_t j = 0; j < cstride; j += 4) {
                   const uint4 c = *reinterpret_cast<const uint4 *>(smem + ro + j);
@@ -155,8 +148,9 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
                         (k >= c.w ? 1u : 0u);
                }
             }
-            const bool isbad =
-                f3b_apply_xform(sf, xf_base + fn * xf_stride, px, py, pc, qx, qy, qc, qv, rng);
+            const uint32_t xfl = c_samp(ci).lay.y; /* base | stride << 16 */
+            const bool isbad = f3b_apply_xform(sf, (xfl & 0xffffu) + fn * (xfl >> 16), px, py, pc, qx,
+                                               qy, qc, qv, rng);
             if (!isbad) break;
             bad++;
             if (++consec >= 5) break;
@@ -177,7 +171,7 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
             if (apply) {
                F3Rng tmp = rng;
                const float4 f =
-                   f3b_apply_final(sf, xf_base + smem[F3B_H_FINAL] * xf_stride, px, py, pc, &tmp);
+                   f3b_apply_final(sf, c_samp(ci).lay.w, px, py, pc, &tmp);
                rng = tmp;
                qx = f.x;
                qy = f.y;
@@ -207,35 +201,35 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
          /* rect.c:465-498: palette lookup */
          const int cmap_size = (int)(hf >> 20);
          const float findex = qc * (float)cmap_size;
-         int ci = (int)findex;
-         const float4 *dmap = reinterpret_cast<const float4 *>(sf + dmap_off);
+         int pi = (int)findex;
+         const float4 *dmap = reinterpret_cast<const float4 *>(sf + (c_samp(ci).lay.z & 0xffffu));
          float4 col;
          if (hf & HF_PLOT_READY) {
             /* step lookup, every xform fully visible, dmap truncated on the host */
-            ci = ci < 0 ? 0 : (ci >= cmap_size - 1 ? cmap_size - 1 : ci);
-            col = dmap[ci];
+            pi = pi < 0 ? 0 : (pi >= cmap_size - 1 ? cmap_size - 1 : pi);
+            col = dmap[pi];
             f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
             if (COUNT) f3b_red_f32(P.hist_count + bidx, 255.0f);
             continue;
          }
          if (hf & HF_PAL_LINEAR) {
             float frac;
-            if (ci < 0) {
-               ci = 0;
+            if (pi < 0) {
+               pi = 0;
                frac = 0.0f;
-            } else if (ci >= cmap_size - 1) {
-               ci = cmap_size - 2;
+            } else if (pi >= cmap_size - 1) {
+               pi = cmap_size - 2;
                frac = 1.0f;
             } else
-               frac = findex - (float)ci;
-            const float4 c0 = dmap[ci], c1 = dmap[ci + 1];
+               frac = findex - (float)pi;
+            const float4 c0 = dmap[pi], c1 = dmap[pi + 1];
             col.x = c0.x * (1.0f - frac) + c1.x * frac;
             col.y = c0.y * (1.0f - frac) + c1.y * frac;
             col.z = c0.z * (1.0f - frac) + c1.z * frac;
             col.w = c0.w * (1.0f - frac) + c1.w * frac;
          } else {
-            ci = ci < 0 ? 0 : (ci >= cmap_size - 1 ? cmap_size - 1 : ci);
-            col = dmap[ci];
+            pi = pi < 0 ? 0 : (pi >= cmap_size - 1 ? cmap_size - 1 : pi);
+            col = dmap[pi];
          }
          float cnt = 255.0f;
          if (qv != 1.0f) {
