@@ -219,9 +219,11 @@ def main():
 
     gpu.set_shard(rank, world)
     if world > 1:
-        from flam3_b200.multigpu import make_allreduce_exchange
+        from flam3_b200.multigpu import make_allreduce_exchange, make_strip_gather
 
         gpu.set_exchange(make_allreduce_exchange(core, nb))
+        if not os.environ.get("F3B_NO_STRIPS"):
+            gpu.set_strip_gather(make_strip_gather(rank, world))
 
     ctx = gpu.render_context(core)
     ctx.width, ctx.height = geo["width"], geo["height"]

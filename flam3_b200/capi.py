@@ -160,6 +160,22 @@ class Flam3Lib:
         self._exchange_keep = cb
         f(C.cast(cb, C.c_void_p), None)
 
+    def set_strip_gather(self, fn):
+        """fn(ctx_ptr, image_ptr, row_bytes, rows_per) assembles the per-rank image strips
+        (include/flam3_b200_dropin.h: f3b_render_set_strip_gather). None = whole-frame
+        post-pass on every rank."""
+        proto = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+        f = self._dll.f3b_render_set_strip_gather
+        f.argtypes = [C.c_void_p, C.c_void_p]
+        f.restype = None
+        if fn is None:
+            self._gather_keep = None
+            f(None, None)
+            return
+        cb = proto(lambda ctx, image, row_bytes, rows_per, user: fn(ctx, image, row_bytes, rows_per))
+        self._gather_keep = cb
+        f(C.cast(cb, C.c_void_p), None)
+
     def render_context(self, core):
         """The f3b_ctx the drop-in renders with, wrapped for stage stats / buffer access."""
         f = self._dll.f3b_render_context
@@ -252,7 +268,7 @@ CORE_SYMBOLS = [
     "f3b_abi_version", "f3b_ctx_create", "f3b_ctx_destroy", "f3b_last_error", "f3b_device_info",
     "f3b_sync", "f3b_frame_begin", "f3b_hist_clear", "f3b_accum_clear", "f3b_plan_chains",
     "f3b_iterate", "f3b_badvals", "f3b_density", "f3b_density_rows", "f3b_finish",
-    "f3b_finish_device", "f3b_hist_upload_u32", "f3b_hist_download_u32", "f3b_accum_upload",
+    "f3b_finish_device", "f3b_finish_device_rows", "f3b_image_download", "f3b_hist_upload_u32", "f3b_hist_download_u32", "f3b_accum_upload",
     "f3b_accum_download", "f3b_hist_color_ptr", "f3b_hist_count_ptr", "f3b_accum_ptr",
     "f3b_stream_ptr", "f3b_stage_stats", "f3b_stats_reset", "f3b_xfer_stats", "f3b_timer_start",
     "f3b_timer_stop",

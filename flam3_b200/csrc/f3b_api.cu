@@ -477,6 +477,11 @@ int f3b_density(f3b_ctx *ctx, const f3b_density_desc *d) {
 }
 
 int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out) {
+   return f3b_finish_device_rows(ctx, d, 0, d ? d->image_height : 0, 0, dev_out);
+}
+
+int f3b_finish_device_rows(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int row1, int alloc_rows,
+                           void **dev_out) {
    if (!ctx || !d) return 1;
    if (!ctx->accum.p) return fail(ctx, "f3b_finish: f3b_frame_begin not called");
    CK(cudaSetDevice(ctx->device));
@@ -492,7 +497,10 @@ int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out) {
       return fail(ctx, "f3b_finish: filter footprint %ldx%ld exceeds buffer %dx%d", xmax, ymax,
                   ctx->width, ctx->height);
    const size_t fbytes = sizeof(double) * (size_t)d->filter_width * d->filter_width;
-   const size_t ibytes = (size_t)d->image_width * d->image_height * d->nchan * d->bytes_per_channel;
+   if (row0 < 0) row0 = 0;
+   if (row1 > d->image_height) row1 = d->image_height;
+   if (alloc_rows < d->image_height) alloc_rows = d->image_height;
+   const size_t ibytes = (size_t)d->image_width * alloc_rows * d->nchan * d->bytes_per_channel;
    if (ensure(ctx, ctx->filter, fbytes)) return 1;
    if (ensure(ctx, ctx->image, ibytes)) return 1;
    CK(cudaMemcpyAsync(ctx->filter.p, d->filter, fbytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -520,6 +528,8 @@ int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out) {
    P.highpow = d->highlight_power;
    for (int i = 0; i < 3; i++) P.background[i] = d->background[i];
    P.out = ctx->image.p;
+   P.out_row_begin = row0;
+   P.out_row_end = row1;
 
    if (stage_begin(ctx, F3B_STAGE_FINAL)) return 1;
    const int nl = f3b_launch_final(P, ctx->stream);
@@ -531,8 +541,15 @@ int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out) {
 
 int f3b_finish(f3b_ctx *ctx, const f3b_final_desc *d, void *out, size_t row_stride) {
    if (!out) return fail(ctx, "f3b_finish: null output");
-   void *dev = nullptr;
-   if (f3b_finish_device(ctx, d, &dev)) return 1;
+   if (f3b_finish_device(ctx, d, nullptr)) return 1;
+   return f3b_image_download(ctx, d, out, row_stride);
+}
+
+int f3b_image_download(f3b_ctx *ctx, const f3b_final_desc *d, void *out, size_t row_stride) {
+   if (!ctx || !d || !out) return fail(ctx, "f3b_image_download: null argument");
+   CK(cudaSetDevice(ctx->device));
+   void *dev = ctx->image.p;
+   if (!dev) return fail(ctx, "f3b_image_download: no image (f3b_finish_device not called)");
    const size_t row = (size_t)d->image_width * d->nchan * d->bytes_per_channel;
    if (row_stride < row) return fail(ctx, "f3b_finish: row stride too small");
    CK(cudaMemcpy2DAsync(out, row_stride, dev, row, row, (size_t)d->image_height,

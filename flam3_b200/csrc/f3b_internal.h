@@ -96,6 +96,7 @@ struct F3FinalParams {
    double g, linrange, vibrancy, highpow;
    double background[3];
    void *out;          /* device image, tightly packed image_width*nchan*bpc per row */
+   int out_row_begin, out_row_end; /* image rows produced by this launch */
 };
 int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream);
 

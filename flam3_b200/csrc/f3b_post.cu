@@ -400,8 +400,8 @@ __device__ __forceinline__ void f3b_tonemap(double *t, const F3FinalParams &P) {
    t[3] = alpha;
 }
 
-__global__ void __launch_bounds__(256) f3b_earlyclip_kernel(const F3FinalParams P, size_t n) {
-   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) f3b_earlyclip_kernel(const F3FinalParams P, size_t i0, size_t n) {
+   size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
    const size_t stride = (size_t)gridDim.x * blockDim.x;
    for (; i < n; i += stride) {
       const float4 a = P.accum[i];
@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(256) f3b_earlyclip_kernel(const F3FinalParams 
 
 __global__ void __launch_bounds__(256) f3b_final_kernel(const F3FinalParams P) {
    const int i = blockIdx.x * blockDim.x + threadIdx.x; /* output column */
-   const int j = blockIdx.y * blockDim.y + threadIdx.y; /* output row    */
-   if (i >= P.image_width || j >= P.image_height) return;
+   const int j = P.out_row_begin + blockIdx.y * blockDim.y + threadIdx.y; /* output row */
+   if (i >= P.image_width || j >= P.out_row_end) return;
    const int x = P.de_offset + i * P.oversample;
    const int y = P.de_offset + j * P.oversample;
    const int fw = P.filter_width;
@@ -460,16 +460,20 @@ __global__ void __launch_bounds__(256) f3b_final_kernel(const F3FinalParams P) {
 
 int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream) {
    int launches = 0;
+   if (p.out_row_end <= p.out_row_begin) return 1;
    if (p.earlyclip) {
-      const size_t n = (size_t)p.width * p.height;
-      int blocks = (int)((n + 255) / 256);
+      /* the accumulator rows under the filter footprints of the output rows */
+      const size_t r0 = (size_t)p.de_offset + (size_t)p.out_row_begin * p.oversample;
+      const size_t r1 = (size_t)p.de_offset + (size_t)(p.out_row_end - 1) * p.oversample + p.filter_width;
+      const size_t i0 = r0 * p.width, n = r1 * p.width;
+      int blocks = (int)((n - i0 + 255) / 256);
       if (blocks > 148 * 16) blocks = 148 * 16;
-      f3b_earlyclip_kernel<<<blocks, 256, 0, stream>>>(p, n);
+      f3b_earlyclip_kernel<<<blocks, 256, 0, stream>>>(p, i0, n);
       if (cudaGetLastError() != cudaSuccess) return 0;
       launches++;
    }
    dim3 block(32, 8);
-   dim3 grid((p.image_width + 31) / 32, (p.image_height + 7) / 8);
+   dim3 grid((p.image_width + 31) / 32, (p.out_row_end - p.out_row_begin + 7) / 8);
    f3b_final_kernel<<<grid, block, 0, stream>>>(p);
    if (cudaGetLastError() != cudaSuccess) return 0;
    return launches + 1;

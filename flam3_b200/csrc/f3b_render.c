@@ -77,6 +77,10 @@ static int g_device_only = 0;
 static int g_rank = 0, g_nranks = 1;
 static void (*g_exchange)(f3b_ctx *, void *) = NULL;
 static void *g_exchange_user = NULL;
+/*  - strip gather: see include/flam3_b200_dropin.h (row-strip post-pass across ranks) */
+typedef void (*f3b_gather_fn)(f3b_ctx *, void *image, size_t row_bytes, int rows_per, void *user);
+static f3b_gather_fn g_gather = NULL;
+static void *g_gather_user = NULL;
 void f3b_render_set_device_only(int on) { g_device_only = on; }
 void f3b_render_set_shard(int rank, int nranks) {
    if (nranks < 1 || rank < 0 || rank >= nranks) {
@@ -85,6 +89,10 @@ void f3b_render_set_shard(int rank, int nranks) {
    }
    g_rank = rank;
    g_nranks = nranks;
+}
+void f3b_render_set_strip_gather(f3b_gather_fn cb, void *user) {
+   g_gather = cb;
+   g_gather_user = user;
 }
 void f3b_render_set_exchange(void (*cb)(f3b_ctx *, void *), void *user) {
    g_exchange = cb;
@@ -322,6 +330,13 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
    g.height = oversample * g.image_height + 2 * g.gutter_width;
    g.width = oversample * g.image_width + 2 * g.gutter_width;
 
+   /* multi-GPU row strips of the post-pass (f3b_render_set_strip_gather) */
+   const int strips = (g_gather != NULL && g_nranks > 1 && g_exchange != NULL);
+   const int strip_rows_per = (g.image_height + g_nranks - 1) / (g_nranks > 0 ? g_nranks : 1);
+   int strip_row0 = g_rank * strip_rows_per, strip_row1 = strip_row0 + strip_rows_per;
+   if (strip_row0 > g.image_height) strip_row0 = g.image_height;
+   if (strip_row1 > g.image_height) strip_row1 = g.image_height;
+
    /* Can the alpha plane double as the hit-count plane? (f3b_pack.c, dmap section) */
    int count_plane = force_count_plane;
    for (int i = 0; i < nbatches * ntemporal_samples && !count_plane; i++)
@@ -497,7 +512,13 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          rv = 0;
          goto done;
       }
-      if (f3b_density(ctx, &dd)) goto gpu_error;
+      if (strips) {
+         /* accumulator rows under the filter footprints of this rank's image rows */
+         const int a0 = g.de_offset + strip_row0 * oversample;
+         const int a1 = g.de_offset + (strip_row1 - 1) * oversample + g.filter_width;
+         if (strip_row1 > strip_row0 && f3b_density_rows(ctx, &dd, a0, a1)) goto gpu_error;
+      } else if (f3b_density(ctx, &dd))
+         goto gpu_error;
       if (de_alive) {
          f3b_de_filters_free(&de);
          de_alive = 0;
@@ -529,7 +550,15 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       fd.highlight_power = highpow;
       fd.gam_lin_thresh = last.gam_lin_thresh;
       const size_t stride = (size_t)g.out_width * nchan * bytes_per_channel;
-      if (g_device_only) {
+      if (strips) {
+         void *image = NULL;
+         if (f3b_finish_device_rows(ctx, &fd, strip_row0, strip_row1, strip_rows_per * g_nranks, &image) ||
+             f3b_sync(ctx))
+            goto gpu_error;
+         (*g_gather)(ctx, image, (size_t)g.image_width * nchan * bytes_per_channel, strip_rows_per,
+                     g_gather_user);
+         if (!g_device_only && f3b_image_download(ctx, &fd, out, stride)) goto gpu_error;
+      } else if (g_device_only) {
          if (f3b_finish_device(ctx, &fd, NULL)) goto gpu_error;
       } else if (f3b_finish(ctx, &fd, out, stride))
          goto gpu_error;

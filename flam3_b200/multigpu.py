@@ -18,10 +18,18 @@ class _DeviceArray:
         }
 
 
-def device_tensor(ptr, n):
+def device_tensor(ptr, n, typestr="<f4"):
     import torch
 
-    return torch.as_tensor(_DeviceArray(ptr, n), device="cuda")
+    return torch.as_tensor(_DeviceArray(ptr, n, typestr), device="cuda")
+
+
+def strip_rows(height, rank, nranks):
+    """Image rows [row0, row1) a rank post-processes: equal strips of ceil(height/nranks)
+    rows, the last one(s) clipped (f3b_render.c: strip_rows_per / strip_row0 / strip_row1)."""
+    per = (height + nranks - 1) // nranks
+    r0 = min(rank * per, height)
+    return r0, min(r0 + per, height), per
 
 
 def shard_groups(n_groups, rank, nranks):
@@ -53,3 +61,21 @@ def make_allreduce_exchange(core, nbuckets, dist=None):
         torch.cuda.synchronize()
 
     return exchange
+
+
+def make_strip_gather(rank, nranks, dist=None):
+    """Returns the callback for Flam3Lib.set_strip_gather: an in-place all-gather of the
+    ranks' image strips (rows_per * row_bytes bytes each) so that every rank ends up with
+    the whole image."""
+    import torch
+
+    if dist is None:
+        import torch.distributed as dist
+
+    def gather(ctx_ptr, image_ptr, row_bytes, rows_per):
+        chunk = int(row_bytes) * int(rows_per)
+        t = device_tensor(image_ptr, chunk * nranks, "|u1")
+        dist.all_gather_into_tensor(t, t[rank * chunk:(rank + 1) * chunk])
+        torch.cuda.synchronize()
+
+    return gather

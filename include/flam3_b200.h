@@ -126,6 +126,12 @@ typedef struct {
 int f3b_finish(f3b_ctx *ctx, const f3b_final_desc *d, void *out, size_t row_stride);
 /* Same but leaves the image in device memory (tightly packed); *dev_out receives it. */
 int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out);
+/* Multi-GPU strips: produce only image rows [row0,row1) (the rows of rect.c:1139's loop) in
+ * a device image of at least alloc_rows rows; the other rows are left untouched. */
+int f3b_finish_device_rows(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int row1,
+                           int alloc_rows, void **dev_out);
+/* Copies the device image of the last f3b_finish_device[_rows] to host rows row_stride apart. */
+int f3b_image_download(f3b_ctx *ctx, const f3b_final_desc *d, void *out, size_t row_stride);
 
 /* ---- raw buffer access: tests, histogram exchange between GPUs --------------------- */
 /* reference bits=33 bucket layout: uint32[5] = r,g,b,a,count per bucket (flam3.c:3824) */

@@ -57,6 +57,15 @@ void f3b_render_set_shard(int rank, int nranks);
 /* Called after every batch's chaos game with the stream idle: sum the per-GPU histograms
  * here (f3b_hist_color_ptr / f3b_hist_count_ptr of include/flam3_b200.h). */
 void f3b_render_set_exchange(void (*cb)(struct f3b_ctx *, void *), void *user);
+/* Row-strip post-pass for nranks > 1: after the exchange every rank runs density estimation,
+ * filtering and tone mapping only for image rows [rank*rows_per, (rank+1)*rows_per) with
+ * rows_per = ceil(height/nranks), then calls `gather` with the stream idle. `image` is the
+ * device image of nranks*rows_per rows of row_bytes bytes; gather must fill in the other
+ * ranks' strips (an in-place all-gather of rows_per*row_bytes bytes per rank). NULL = off:
+ * every rank post-processes the whole frame. */
+typedef void (*f3b_gather_fn)(struct f3b_ctx *, void *image, size_t row_bytes, int rows_per,
+                              void *user);
+void f3b_render_set_strip_gather(f3b_gather_fn cb, void *user);
 
 #ifdef __cplusplus
 }

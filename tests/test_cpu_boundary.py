@@ -163,3 +163,16 @@ def test_histogram_exchange_world_size_2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+@pytest.mark.parametrize("height,nranks", [(1080, 8), (480, 3), (5, 8), (1, 2), (7, 7)])
+def test_strip_rows_tile_the_image(height, nranks):
+    """Row strips of the multi-GPU post-pass: equal blocks of ceil(h/n) rows, clipped, that
+    cover every image row exactly once (the rule f3b_render.c applies per rank)."""
+    from flam3_b200.multigpu import strip_rows
+    seen = []
+    for r in range(nranks):
+        r0, r1, per = strip_rows(height, r, nranks)
+        assert per == -(-height // nranks) and 0 <= r0 <= r1 <= height and r1 - r0 <= per
+        seen += list(range(r0, r1))
+    assert seen == list(range(height))

@@ -127,3 +127,38 @@ def test_interlaced_fields(flame0):
 def test_pixel_aspect(flame0):
     rimg, gimg, *_ = run_case(small(flame0), pixel_aspect_ratio=1.2)
     check_images(rimg, gimg)
+
+
+@pytest.mark.parametrize("variant", ["os1", "os2_earlyclip"])
+def test_row_strip_postpass_equals_whole_frame(flame0, variant):
+    """Multi-GPU post-pass: every rank runs density estimation, filtering and
+    tone mapping for its strip of image rows only. The strips of all "ranks" (run here one
+    after the other on one GPU, from the same histogram) must tile the whole-frame image
+    byte for byte."""
+    from flam3_b200.multigpu import strip_rows
+    ref, gpu, core = libs()
+    if variant == "os1":
+        xml, kw = resize(flame0, 200, 150, scale=75, quality=20), {}
+    else:
+        xml, kw = resize(flame0, 160, 122, scale=60, quality=20, oversample=2), {"earlyclip": 1}
+    gr, gg = ref.parse(xml), gpu.parse(xml)
+    _, _, buckets, _, geo, _ = ref_render_capture(ref, gr, **kw)
+    whole, _ = gpu_render_from_histogram(gpu, core, gg, buckets, geo, **kw)
+    H = whole.shape[0]
+    nranks = 3
+    tiled = np.zeros_like(whole)
+    calls = []
+    try:
+        gpu.set_exchange(lambda ctx: None)
+        gpu.set_strip_gather(lambda ctx, image, row_bytes, rows_per: calls.append((row_bytes, rows_per)))
+        for r in range(nranks):
+            gpu.set_shard(r, nranks)
+            img, _ = gpu_render_from_histogram(gpu, core, gg, buckets, geo, **kw)
+            r0, r1, per = strip_rows(H, r, nranks)
+            tiled[r0:r1] = img[r0:r1]
+    finally:
+        gpu.set_shard(0, 1)
+        gpu.set_exchange(None)
+        gpu.set_strip_gather(None)
+    assert len(calls) == nranks and calls[0] == (whole.shape[1] * whole.shape[2], (H + 2) // 3)
+    assert np.array_equal(tiled, whole), "%d bytes differ" % int((tiled != whole).sum())
