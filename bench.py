@@ -112,6 +112,32 @@ def load_ncu_traffic():
         return None
 
 
+def _calibrate(ref, cores):
+    """Reference frame time model t(q) = fixed + per_q * q at the workload's size, from two
+    short renders (the post-pass cost does not scale with quality)."""
+    ts = []
+    for q in (10.0, 40.0):
+        g = ref.parse(workload_xml(q))
+        t = time.perf_counter()
+        ref.render(g, nthreads=cores)
+        ts.append(time.perf_counter() - t)
+    per_q = max(1e-5, (ts[1] - ts[0]) / 30.0)
+    fixed = max(0.0, ts[0] - 10.0 * per_q)
+    # refine the slope on a ~3 s render (short ones overrate the per-iteration speed)
+    q3 = _quality_for(3.0, per_q, fixed)
+    g = ref.parse(workload_xml(q3))
+    t = time.perf_counter()
+    ref.render(g, nthreads=cores)
+    t3 = time.perf_counter() - t
+    if q3 > 40.0:
+        per_q = max(per_q, (t3 - fixed) / q3)
+    return per_q, fixed
+
+
+def _quality_for(seconds, per_q, fixed):
+    return float(max(10.0, min(QUALITY, round((seconds - fixed) / per_q))))
+
+
 def reference_arm(args, rank):
     """Unmodified reference on the host cores, bounded sample of the same workload."""
     if rank != 0:
@@ -121,15 +147,10 @@ def reference_arm(args, rank):
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libflam3_ref.so")
     ref = fb.Flam3Lib(ref_path)
     cores = os.cpu_count() or 1
-    # calibrate: one q=10 frame, then pick a quality giving ~8 s steps (capped so that the
-    # whole run stays within a few minutes)
-    g = ref.parse(workload_xml(10.0))
-    t = time.perf_counter()
-    _, st, _ = ref.render(g, nthreads=cores)
-    t10 = time.perf_counter() - t
-    per_q = max(1e-4, (t10 - 0.4) / 10.0) if t10 > 0.5 else t10 / 10.0
-    budget = min(8.0, 150.0 / max(1, args.steps + args.warmup))
-    q = max(10.0, min(QUALITY, round(budget / per_q)))
+    per_q, fixed = _calibrate(ref, cores)
+    # every step ~10 s, capped so that warm-up + steps stay within a few minutes
+    budget = min(10.0, 170.0 / max(1, args.steps + args.warmup))
+    q = _quality_for(budget, per_q, fixed)
     g = ref.parse(workload_xml(q))
     for _ in range(args.warmup):
         ref.render(g, nthreads=cores)
@@ -140,8 +161,8 @@ def reference_arm(args, rank):
         iters += st["num_iters"]
     dt = time.perf_counter() - t
     v = iters / dt
-    sample = "same genome and size at quality %g (%.3g iters/step), flam3_render CPU path, nthreads=%d" % (
-        q, iters / max(1, args.steps), cores)
+    sample = "same genome and size at quality %g (%.3g iters/step, %.1f s/step), flam3_render CPU path, nthreads=%d" % (
+        q, iters / max(1, args.steps), dt / max(1, args.steps), cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps),
@@ -151,22 +172,18 @@ def reference_arm(args, rank):
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "frame_time_s_extrapolated_q2000": (W * H * QUALITY) / v,
+        "frame_time_s_extrapolated_q2000": fixed + per_q * QUALITY,
     }
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_leg(seconds=12.0):
+def cpu_baseline_leg(seconds=15.0):
     import flam3_b200 as fb
 
     ref = fb.Flam3Lib(os.path.join(ROOT, "oracle", "_ref", "libflam3_ref.so"))
     cores = os.cpu_count() or 1
-    g = ref.parse(workload_xml(10.0))
-    t = time.perf_counter()
-    ref.render(g, nthreads=cores)
-    t10 = time.perf_counter() - t
-    per_q = max(1e-4, (t10 - 0.4) / 10.0) if t10 > 0.5 else t10 / 10.0
-    q = max(10.0, min(QUALITY, round(seconds / per_q)))
+    per_q, fixed = _calibrate(ref, cores)
+    q = _quality_for(seconds, per_q, fixed)
     g = ref.parse(workload_xml(q))
     t = time.perf_counter()
     _, st, _ = ref.render(g, nthreads=cores)
@@ -174,7 +191,7 @@ def cpu_baseline_leg(seconds=12.0):
     return {"value": st["num_iters"] / dt, "unit": UNIT, "cores": cores, "kind": "reference",
             "sample": "same genome and size at quality %g (%.3g iters, %.1f s), unmodified "
                       "reference flam3_render, nthreads=%d" % (q, st["num_iters"], dt, cores),
-            "frame_time_s_extrapolated_q2000": (W * H * QUALITY) / (st["num_iters"] / dt)}
+            "frame_time_s_extrapolated_q2000": fixed + per_q * QUALITY}
 
 
 def main():
@@ -306,17 +323,27 @@ def main():
         "in_bounds_fraction": hits_total / iters_per_step,
         "share_of_step": it_ms / dev_ms,
     }
+    # post-pass stages: 36 B/bucket for log scale + DE, 16 B/bucket + the
+    # image for filter + tone map; with N ranks each one handles a 1/N row strip. These are
+    # per-stage figures (DE = classify + gather launches); at this size both stages are
+    # bound by their arithmetic (DE taps, fp64 pow), not by HBM: see DESIGN.md section 5.
     post = []
+    steps_timed = float(args.steps)
     if de_n:
-        b = nb * 36.0
-        post.append({"kernel": "f3b_density_kernel (log scale + DE gather)", "bound": "hbm",
-                     "achieved": b / (de_ms / 1e3 / de_n) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": b / (de_ms / 1e3 / de_n) / 1e9 / peak, "avg_launch_ms": de_ms / de_n})
+        b = nb * 36.0 / world
+        t_stage = de_ms / 1e3 / steps_timed
+        post.append({"stage": "log scale + density estimation (f3b_de_classify_kernel + "
+                              "f3b_de_gather_kernel)", "bound": "hbm",
+                     "achieved": b / t_stage / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": b / t_stage / 1e9 / peak, "stage_ms": 1e3 * t_stage,
+                     "launches_per_step": de_n / steps_timed})
     if fi_n:
-        b = nb * 16.0 + W * H * 3.0
-        post.append({"kernel": "f3b_final_kernel (spatial filter + tone map)", "bound": "hbm",
-                     "achieved": b / (fi_ms / 1e3 / fi_n) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": b / (fi_ms / 1e3 / fi_n) / 1e9 / peak, "avg_launch_ms": fi_ms / fi_n})
+        b = (nb * 16.0 + W * H * 3.0) / world
+        t_stage = fi_ms / 1e3 / steps_timed
+        post.append({"stage": "spatial filter + tone map (f3b_final_kernel)", "bound": "hbm",
+                     "achieved": b / t_stage / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": b / t_stage / 1e9 / peak, "stage_ms": 1e3 * t_stage,
+                     "launches_per_step": fi_n / steps_timed})
 
     total_iters = iters_per_step * args.steps
     value = total_iters / (dev_ms / 1e3)
@@ -329,8 +356,9 @@ def main():
                    "buckets": [geo["width"], geo["height"]],
                    "l2_policy": "histogram+accumulator (76.6 MB) are re-zeroed and rewritten "
                                 "every step; scatter addresses are random, no reuse across steps",
-                   "parallelism": "chains sharded over %d GPU(s), NCCL all-reduce of histograms"
-                                  % world if world > 1 else "single GPU"},
+                   "parallelism": ("chains sharded over %d GPUs, NCCL all-reduce of the histograms, "
+                                   "row-strip post-pass + NCCL all-gather of the image strips" % world)
+                   if world > 1 else "single GPU"},
         "frame_time_s": dev_ms / 1e3 / args.steps,
         "e2e": {"value": total_iters / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,

@@ -19,6 +19,8 @@ struct DevBuf {
    size_t cap = 0;
 };
 
+#define F3B_SIDE_STREAMS 3
+
 struct f3b_ctx {
    int device = 0;
    int sms = 0;
@@ -32,6 +34,8 @@ struct f3b_ctx {
    DevBuf blobs, jobs, groups, de_coefs, de_radius, filter, de_kidx, de_tiles;
    bool accum_zero_pending = false; /* accumulators are logically zero, memset not yet issued */
    unsigned long long *d_badvals = nullptr;
+   cudaStream_t side[F3B_SIDE_STREAMS] = {nullptr, nullptr, nullptr};
+   cudaEvent_t fork_ev = nullptr, join_ev[F3B_SIDE_STREAMS] = {nullptr, nullptr, nullptr};
 
    /* instrumentation */
    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -159,6 +163,11 @@ void f3b_ctx_destroy(f3b_ctx *ctx) {
       cudaEventDestroy(p.first);
       cudaEventDestroy(p.second);
    }
+   for (int i = 0; i < F3B_SIDE_STREAMS; i++) {
+      if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+      if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
+   }
+   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
    if (ctx->timer0) cudaEventDestroy(ctx->timer0);
    if (ctx->timer1) cudaEventDestroy(ctx->timer1);
    if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -257,6 +266,20 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    /* plan chains and groups */
    std::vector<uint32_t> group_job;
    size_t max_blob = 0;
+   uint64_t total_chains = 0;
+   for (int j = 0; j < n_jobs; j++) {
+      f3b_job &jb = jobs[j];
+      if (jb.n_chains == 0) jb.n_chains = f3b_plan_chains(ctx, jb.n_iters, max_chain_len, n_jobs);
+      total_chains += jb.n_chains;
+   }
+   /* Chains per group (= threads per CTA): 256 when there is plenty of work; small batches
+    * (draft quality, or the 1000 short temporal samples of an animation frame, where a
+    * sample may have a single chain) use narrower groups so that the groups of all samples
+    * are resident together and the serial walks overlap instead of queueing. */
+   int group_size = F3B_CHAINS_PER_GROUP;
+   while (group_size > 32 &&
+          total_chains / (uint64_t)group_size + (uint64_t)n_jobs < 2ull * (uint64_t)ctx->sms * 8ull)
+      group_size /= 2;
    for (int j = 0; j < n_jobs; j++) {
       f3b_job &jb = jobs[j];
       if (jb.blob_offset % 16 || jb.blob_offset + F3B_H_SIZE * 4 > blob_bytes)
@@ -267,9 +290,8 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          return fail(ctx, "f3b_iterate: job %d blob of %u words does not fit (max %u)", j, words,
                      F3B_MAX_BLOB_WORDS);
       if ((size_t)words * 4 > max_blob) max_blob = (size_t)words * 4;
-      if (jb.n_chains == 0) jb.n_chains = f3b_plan_chains(ctx, jb.n_iters, max_chain_len, n_jobs);
       jb.first_group = (uint32_t)group_job.size();
-      const uint32_t ng = (jb.n_chains + F3B_CHAINS_PER_GROUP - 1) / F3B_CHAINS_PER_GROUP;
+      const uint32_t ng = (jb.n_chains + (uint32_t)group_size - 1) / (uint32_t)group_size;
       for (uint32_t g = 0; g < ng; g++) group_job.push_back((uint32_t)j);
    }
    const uint32_t n_groups = (uint32_t)group_job.size();
@@ -303,7 +325,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    P.seed = seed;
    P.badvals = ctx->d_badvals;
 
-   const int bps = f3b_iterate_max_blocks_per_sm(max_blob);
+   const int bps = f3b_iterate_blocks_per_sm(group_size, max_blob);
    if (bps <= 0) return fail(ctx, "f3b_iterate: kernel does not fit with %zu bytes of shared memory", max_blob);
 
    /* One launch per `cap` temporal samples (their warp-uniform camera and chooser constants
@@ -312,7 +334,20 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    std::vector<F3ConstSample> consts((size_t)(n_jobs < cap ? n_jobs : cap));
    int launches = 0;
    if (stage_begin(ctx, F3B_STAGE_ITERATE)) return 1;
-   for (int j0 = 0; j0 < n_jobs; j0 += cap) {
+   /* several launches (more temporal samples than fit the parameter space) are independent:
+    * they go to side streams so that their CTAs can be resident together */
+   const bool fork = n_jobs > cap;
+   if (fork) {
+      for (int i = 0; i < F3B_SIDE_STREAMS; i++)
+         if (!ctx->side[i]) CK(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+      if (!ctx->fork_ev) CK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+      for (int i = 0; i < F3B_SIDE_STREAMS; i++)
+         if (!ctx->join_ev[i]) CK(cudaEventCreateWithFlags(&ctx->join_ev[i], cudaEventDisableTiming));
+      CK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+      for (int i = 0; i < F3B_SIDE_STREAMS; i++) CK(cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0));
+   }
+   int chunk = 0;
+   for (int j0 = 0; j0 < n_jobs; j0 += cap, chunk++) {
       const int j1 = (j0 + cap < n_jobs) ? j0 + cap : n_jobs;
       for (int j = j0; j < j1; j++) {
          const uint32_t *w = (const uint32_t *)((const char *)blobs + jobs[j].blob_offset);
@@ -342,11 +377,17 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       if (span == 0) continue;
       int grid = ctx->sms * bps;
       if ((uint32_t)grid > local_groups) grid = (int)local_groups;
+      cudaStream_t st = fork ? ctx->side[chunk % F3B_SIDE_STREAMS] : ctx->stream;
       const int nl = f3b_launch_iterate(P, consts.data(), j1 - j0, ctx->count_channel != 0, grid,
-                                        max_blob, ctx->stream);
+                                        group_size, max_blob, st);
       if (!nl) return fail(ctx, "chaos-game launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       launches += nl;
    }
+   if (fork)
+      for (int i = 0; i < F3B_SIDE_STREAMS; i++) {
+         CK(cudaEventRecord(ctx->join_ev[i], ctx->side[i]));
+         CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
+      }
    return stage_end(ctx, launches);
 }
 

@@ -13,7 +13,9 @@
 
 typedef f3b_job f3b_sample_job;
 
-#define F3B_CHAINS_PER_GROUP 256 /* = threads per block of the chaos-game kernel */
+#define F3B_CHAINS_PER_GROUP 256 /* largest chain group = threads per block of the chaos-game
+                                    kernel; batches with few chains per temporal sample use
+                                    smaller groups (32..256) so that more of them are resident */
 
 /* Warp-uniform per-sample values served from the kernel parameters (constant bank 0). */
 struct F3ConstSample {
@@ -55,7 +57,9 @@ struct F3IterateParams {
 /* returns the number of kernel launches made (0 on error; see cudaGetLastError). `consts`
  * holds the constants of jobs [p.job_base, p.job_base + n_consts), n_consts <= capacity */
 int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_consts,
-                       bool count_channel, int grid_blocks, size_t smem_bytes, cudaStream_t stream);
+                       bool count_channel, int grid_blocks, int group_size, size_t smem_bytes,
+                       cudaStream_t stream);
+int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes);
 int f3b_iterate_const_capacity(void);
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes);
 int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_index, const float *in,

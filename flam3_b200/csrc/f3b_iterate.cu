@@ -93,12 +93,12 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
          __syncthreads(); /* everyone is done with the previous blob */
          const uint32_t *src = reinterpret_cast<const uint32_t *>(P.blobs + job.blob_offset);
          const uint32_t words = src[F3B_H_WORDS];
-         for (uint32_t i = tid; i < words; i += F3B_BLOCK) smem[i] = src[i];
+         for (uint32_t i = tid; i < words; i += blockDim.x) smem[i] = src[i];
          __syncthreads();
          loaded_job = ji;
       }
 
-      const uint32_t chain = (g - job.first_group) * F3B_BLOCK + tid;
+      const uint32_t chain = (g - job.first_group) * blockDim.x + tid; /* blockDim.x chains per group */
       if (chain >= job.n_chains) continue;
 
       /* stored iterations of this chain */
@@ -292,24 +292,30 @@ int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_in
 int f3b_iterate_const_capacity(void) { return F3B_PARAM_SAMPLES; }
 
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes) {
+   return f3b_iterate_blocks_per_sm(F3B_BLOCK, smem_bytes);
+}
+
+int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes) {
    int nb = 0;
    cudaFuncSetAttribute(f3b_iterate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                         (int)(F3B_MAX_BLOB_WORDS * 4));
    cudaFuncSetAttribute(f3b_iterate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                         (int)(F3B_MAX_BLOB_WORDS * 4));
-   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true>, F3B_BLOCK,
+   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true>, group_size,
                                                      smem_bytes) != cudaSuccess)
       return 0;
    return nb;
 }
 
 int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_consts,
-                       bool count_channel, int grid_blocks, size_t smem_bytes, cudaStream_t stream) {
+                       bool count_channel, int grid_blocks, int group_size, size_t smem_bytes,
+                       cudaStream_t stream) {
    if (grid_blocks <= 0 || n_consts <= 0 || n_consts > F3B_PARAM_SAMPLES) return 0;
+   if (group_size < 32 || group_size > F3B_BLOCK || (group_size & 31)) return 0;
    for (int i = 0; i < n_consts; i++) p.samp[i] = consts[i];
    if (count_channel)
-      f3b_iterate_kernel<true><<<grid_blocks, F3B_BLOCK, smem_bytes, stream>>>(p);
+      f3b_iterate_kernel<true><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
    else
-      f3b_iterate_kernel<false><<<grid_blocks, F3B_BLOCK, smem_bytes, stream>>>(p);
+      f3b_iterate_kernel<false><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
 }

@@ -109,6 +109,13 @@ double flam3_render_memory_required(flam3_frame *spec) {
           cps[0].height * (real_bits / 8) * 9.0;
 }
 
+/* F3B_TIMING=1: host-side phase times of every flam3_render call on stderr */
+static double now_ms(void) {
+   struct timespec ts;
+   clock_gettime(CLOCK_MONOTONIC, &ts);
+   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int poll_progress(flam3_frame *spec, double percent, int stage) {
    /* 0 continue, 1 abort, 2 pause (rect.c:324-373) */
    if (!spec->progress) return 0;
@@ -224,7 +231,7 @@ static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *
    if (nts >= 32) {
       const char *e = getenv("F3B_HOST_THREADS");
       long nproc = sysconf(_SC_NPROCESSORS_ONLN);
-      nthreads = e ? atoi(e) : (int)(nproc > 8 ? 8 : nproc);
+      nthreads = e ? atoi(e) : (int)(nproc > 16 ? 16 : nproc);
       if (nthreads > nts / 8) nthreads = nts / 8;
       if (nthreads < 1) nthreads = 1;
    }
@@ -241,6 +248,8 @@ static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *
 static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, int nchan,
                          int transp, stat_struct *stats, int force_count_plane) {
    const time_t tstart = time(NULL);
+   const int timing = getenv("F3B_TIMING") != NULL;
+   double t_setup = now_ms(), t_pack = 0, t_serial = 0, t_iter = 0, t_dens = 0, t_fin = 0, t0;
    int rv = 1;
    int verbose = spec->verbose;
    const int nthreads = spec->nthreads > 0 ? spec->nthreads : 1;
@@ -394,11 +403,15 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
        * (flam3-animate: 1000 per frame) it is spread over a few host threads. ---- */
       blobs.used = 0;
       uint64_t seed = 0x243f6a8885a308d3ull;
+      if (batch_num == 0) t_setup = now_ms() - t_setup;
+      t0 = now_ms();
       if (pack_batch(spec, &g, temporal_filter, temporal_deltas, batch_num, ntemporal_samples,
                      cmap_size, spec->bits != 64, &packed)) {
          fprintf(stderr, "flam3_render (B200): out of memory packing temporal samples\n");
          goto done;
       }
+      t_pack += now_ms() - t0;
+      t0 = now_ms();
       for (int ts = 0; ts < ntemporal_samples; ts++) {
          const int fi = batch_num * ntemporal_samples + ts;
          const double color_scalar = temporal_filter[fi];
@@ -471,6 +484,8 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          goto done;
       }
 
+      t_serial += now_ms() - t0;
+      t0 = now_ms();
       /* ---- chaos game: one launch for the whole batch ---- */
       const uint32_t max_chain = spec->sub_batch_size > 0 ? (uint32_t)spec->sub_batch_size : 10000u;
       if (g_inject) {
@@ -488,6 +503,8 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          (*g_exchange)(ctx, g_exchange_user);
       }
 
+      t_iter += now_ms() - t0;
+      t0 = now_ms();
       /* ---- log scale + density estimation (rect.c:933-1058); cp/cam are those of the
        * batch's LAST temporal sample, as in the reference ---- */
       f3b_density_desc dd;
@@ -523,7 +540,9 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          f3b_de_filters_free(&de);
          de_alive = 0;
       }
+      t_dens += now_ms() - t0;
    }
+   t0 = now_ms();
 
    if (verbose) {
       fprintf(stderr, "\rchaos: 100.0%%  took: %ld seconds   \n", (long)(time(NULL) - progress_began));
@@ -579,6 +598,11 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
             for (int k = 0; k < 3; k++) p[k] = (unsigned char)last_dmap[i * 256 / g.image_width][k];
          }
    }
+   t_fin = now_ms() - t0;
+   if (timing)
+      fprintf(stderr, "f3b timing (host ms): setup %.2f pack %.2f jobs %.2f iterate-submit %.2f "
+                      "density-submit %.2f finish+download %.2f\n", t_setup, t_pack, t_serial, t_iter,
+              t_dens, t_fin);
    rv = 0;
    goto done;
 

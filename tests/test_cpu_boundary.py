@@ -176,3 +176,24 @@ def test_strip_rows_tile_the_image(height, nranks):
         assert per == -(-height // nranks) and 0 <= r0 <= r1 <= height and r1 - r0 <= per
         seen += list(range(r0, r1))
     assert seen == list(range(height))
+
+
+@pytest.mark.parametrize("first,last,dtime,n", [(0, 99, 1, 8), (10, 12, 1, 8), (0, 20, 3, 4), (5, 5, 1, 2)])
+def test_animate_frame_plan_covers_every_frame_once(first, last, dtime, n):
+    """flam3_b200.animate: worker r renders first + r*dtime, then every n*dtime — together
+    exactly flam3-animate's own frame list (flam3-animate.c:225)."""
+    from flam3_b200.animate import frames_of, plan_frames
+    per_worker = frames_of(plan_frames(first, last, dtime, n), last)
+    flat = sorted(t for w in per_worker for t in w)
+    assert flat == list(range(first, last + 1, dtime))
+    assert max(len(w) for w in per_worker) - min(len(w) for w in per_worker) <= 1
+
+
+def test_animate_frame_range_follows_flam3_animate():
+    from flam3_b200.animate import frame_range
+    xml = '<flames><flame time="0" size="1 1"/><flame time="100" size="1 1"/></flames>'
+    assert frame_range({}, xml) == (0, 99)
+    assert frame_range({"begin": "5"}, xml) == (5, 99)
+    assert frame_range({"begin": "5", "end": "7"}, xml) == (5, 7)
+    assert frame_range({"frame": "42"}, xml) == (42, 42)
+    assert frame_range({"time": "17"}, xml) == (17, 17)

@@ -77,3 +77,25 @@ def test_flam3_animate_cli_frames(tmp_path):
         assert f.shape == (480, 640, 3) and f.mean() > 5
     # consecutive frames of a smooth interpolation are close but not identical
     assert 20.0 < psnr(frames[0], frames[1]) < 60.0
+
+
+def test_animate_frame_scheduler_round_robin(tmp_path):
+    """flam3_b200.animate deals the frames of one flam3-animate job
+    round-robin to worker processes (one per GPU; here two workers on the one GPU). Every
+    frame appears once under the reference's file name and matches the single-process
+    frame up to Monte-Carlo noise (the seeds differ, see flam3_b200/animate.py)."""
+    import sys
+    tmp = str(tmp_path)
+    run_cli(os.path.join(ROOT, "dropin", "_build", "flam3-animate"), tmp, "one_",
+            {"begin": "30", "end": "34"})
+    env = dict(os.environ)
+    env.update({"format": "ppm", "isaac_seed": "flam3b200", "prefix": os.path.join(tmp, "rr_"),
+                "verbose": "0", "in": FIXTURE, "begin": "30", "end": "34", "PYTHONPATH": ROOT})
+    p = subprocess.run([sys.executable, "-m", "flam3_b200.animate", "--gpus", "2", "--devices", "0,0"],
+                       env=env, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    for t in range(30, 35):
+        a = read_ppm(os.path.join(tmp, "one_%05d.ppm" % t))
+        b = read_ppm(os.path.join(tmp, "rr_%05d.ppm" % t))
+        assert a.shape == b.shape == (480, 640, 3)
+        assert psnr(a, b) > 28.0, (t, psnr(a, b))
