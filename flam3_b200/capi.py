@@ -269,7 +269,7 @@ CORE_SYMBOLS = [
     "f3b_sync", "f3b_frame_begin", "f3b_hist_clear", "f3b_accum_clear", "f3b_plan_chains",
     "f3b_iterate", "f3b_badvals", "f3b_density", "f3b_density_rows", "f3b_finish",
     "f3b_finish_device", "f3b_finish_device_rows", "f3b_image_download", "f3b_hist_upload_u32", "f3b_hist_download_u32", "f3b_accum_upload",
-    "f3b_accum_download", "f3b_hist_color_ptr", "f3b_hist_count_ptr", "f3b_accum_ptr",
+    "f3b_accum_download", "f3b_hist_color_ptr", "f3b_hist_count_ptr", "f3b_hist_elems", "f3b_accum_ptr",
     "f3b_stream_ptr", "f3b_stage_stats", "f3b_stats_reset", "f3b_xfer_stats", "f3b_timer_start",
     "f3b_timer_stop",
 ]
@@ -309,7 +309,7 @@ class CoreLib:
         d.f3b_hist_download_u32.argtypes = [vp, vp]
         d.f3b_accum_upload.argtypes = [vp, vp]
         d.f3b_accum_download.argtypes = [vp, vp]
-        for n in ("f3b_hist_color_ptr", "f3b_hist_count_ptr", "f3b_accum_ptr", "f3b_stream_ptr"):
+        for n in ("f3b_hist_color_ptr", "f3b_hist_count_ptr", "f3b_hist_elems", "f3b_accum_ptr", "f3b_stream_ptr"):
             getattr(d, n).restype = vp
             getattr(d, n).argtypes = [vp]
         d.f3b_stage_stats.argtypes = [vp, ci, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]

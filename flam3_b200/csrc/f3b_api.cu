@@ -29,6 +29,8 @@ struct f3b_ctx {
    char err[512] = {0};
 
    int width = 0, height = 0;
+   F3HistLayout lay = {0, 0, 0}; /* histogram addressing */
+   size_t hist_elems = 0;        /* buckets in a histogram plane */
    int count_channel = 1;
    DevBuf hist_color, hist_count, accum, image;
    DevBuf blobs, jobs, groups, de_coefs, de_radius, filter, de_kidx, de_tiles;
@@ -190,14 +192,48 @@ int f3b_sync(f3b_ctx *ctx) {
    return 0;
 }
 
+/* Layout of the histogram planes. Buckets are plain row-major (F3B_HIST_PITCH=n pads the
+ * rows, for experiments). What matters for speed is how evenly the chaos game's reductions
+ * load the L2 slices: an attractor has a few very hot buckets (test.flam3's first flame at
+ * 1080p: one bucket takes 0.27% of all hits, the top 16 take 1.9%, against 0.5% for a whole
+ * average slice), so the slices that happen to hold them saturate while the rest idle
+ * (ncu: lts__t_tag_requests 45% avg, 81% max), and which buckets share a slice changes with
+ * every layout detail (measured 21.6 to 34.2 ms for the same frame over row pitches,
+ * profiles/r01_pitch_sweep.txt). While the chaos game runs the planes are therefore
+ * replicated: CTA b adds into copy b % replicas, which divides every hot bucket's load over
+ * `replicas` different slices; the copies are summed before anything reads them. Replicas
+ * are used as long as they all stay L2-resident (F3B_HIST_REPLICAS overrides). */
+static F3HistLayout hist_layout_for(int width, int height, int count_channel, size_t *elems) {
+   F3HistLayout L = {width, 1u, 0};
+   const char *e = getenv("F3B_HIST_PITCH");
+   if (e && atoi(e) >= width) L.pitch = atoi(e);
+   const size_t buckets = (size_t)L.pitch * height;
+   L.replica_stride = (buckets + 63) & ~(size_t)63;
+   const size_t plane_bytes = L.replica_stride * (sizeof(float4) + (count_channel ? sizeof(float) : 0));
+   /* all copies must stay in the 126 MB L2: 3 copies at 1080p (102 MB), 4 below ~26 MB */
+   size_t k = (104u << 20) / (plane_bytes ? plane_bytes : 1);
+   if (k > 4) k = 4;
+   if (k < 1) k = 1;
+   const char *r = getenv("F3B_HIST_REPLICAS");
+   if (r && atoi(r) >= 1 && atoi(r) <= 16) k = (size_t)atoi(r);
+   L.replicas = (uint32_t)k;
+   *elems = buckets;
+   return L;
+}
+
 int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel) {
    if (!ctx) return 1;
    if (width <= 0 || height <= 0) return fail(ctx, "bad buffer size %dx%d", width, height);
    CK(cudaSetDevice(ctx->device));
    const size_t n = (size_t)width * height;
-   if (ensure(ctx, ctx->hist_color, n * sizeof(float4))) return 1;
+   size_t nh = 0;
+   const F3HistLayout lay = hist_layout_for(width, height, count_channel, &nh);
+   const size_t nalloc = lay.replica_stride * lay.replicas;
+   if (ensure(ctx, ctx->hist_color, nalloc * sizeof(float4))) return 1;
    if (ensure(ctx, ctx->accum, n * sizeof(float4))) return 1;
-   if (count_channel && ensure(ctx, ctx->hist_count, n * sizeof(float))) return 1;
+   if (count_channel && ensure(ctx, ctx->hist_count, nalloc * sizeof(float))) return 1;
+   ctx->lay = lay;
+   ctx->hist_elems = nh;
    ctx->width = width;
    ctx->height = height;
    ctx->count_channel = count_channel ? 1 : 0;
@@ -207,7 +243,7 @@ int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel) {
 }
 
 int f3b_hist_clear(f3b_ctx *ctx) {
-   const size_t n = (size_t)ctx->width * ctx->height;
+   const size_t n = ctx->lay.replica_stride * ctx->lay.replicas;
    CK(cudaSetDevice(ctx->device));
    CK(cudaMemsetAsync(ctx->hist_color.p, 0, n * sizeof(float4), ctx->stream));
    if (ctx->count_channel) CK(cudaMemsetAsync(ctx->hist_count.p, 0, n * sizeof(float), ctx->stream));
@@ -277,9 +313,13 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
     * sample may have a single chain) use narrower groups so that the groups of all samples
     * are resident together and the serial walks overlap instead of queueing. */
    int group_size = F3B_CHAINS_PER_GROUP;
-   while (group_size > 32 &&
-          total_chains / (uint64_t)group_size + (uint64_t)n_jobs < 2ull * (uint64_t)ctx->sms * 8ull)
-      group_size /= 2;
+   for (; group_size > 32; group_size /= 2) {
+      uint64_t groups = 0;
+      for (int j = 0; j < n_jobs; j++) groups += (jobs[j].n_chains + group_size - 1) / group_size;
+      const bool fills_gpu = groups >= 3ull * (uint64_t)ctx->sms;
+      const bool lanes_used = 2 * total_chains >= groups * (uint64_t)group_size;
+      if (fills_gpu && lanes_used) break;
+   }
    for (int j = 0; j < n_jobs; j++) {
       f3b_job &jb = jobs[j];
       if (jb.blob_offset % 16 || jb.blob_offset + F3B_H_SIZE * 4 > blob_bytes)
@@ -321,6 +361,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    P.hist_count = ctx->count_channel ? (float *)ctx->hist_count.p : nullptr;
    P.width = ctx->width;
    P.height = ctx->height;
+   P.lay = ctx->lay;
    P.floor_adds = floor_adds;
    P.seed = seed;
    P.badvals = ctx->d_badvals;
@@ -349,6 +390,9 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    int chunk = 0;
    for (int j0 = 0; j0 < n_jobs; j0 += cap, chunk++) {
       const int j1 = (j0 + cap < n_jobs) ? j0 + cap : n_jobs;
+      /* every sample of the launch qualifies for the SIMPLE kernel (F3B_NO_SIMPLE=1 forces
+       * the generic kernel, for A/B timing) */
+      bool simple = getenv("F3B_NO_SIMPLE") == nullptr;
       for (int j = j0; j < j1; j++) {
          const uint32_t *w = (const uint32_t *)((const char *)blobs + jobs[j].blob_offset);
          const float *f = (const float *)w;
@@ -368,6 +412,20 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
              (int)w[F3B_H_FINAL] >= 0 ? w[F3B_H_XF_BASE] + w[F3B_H_FINAL] * w[F3B_H_XF_STRIDE] : 0u;
          c.lay = make_uint4(hf, w[F3B_H_XF_BASE] | (w[F3B_H_XF_STRIDE] << 16),
                             w[F3B_H_OFF_PALETTE] | (w[F3B_H_OFF_CHOOSER] << 16), final_off);
+         /* packed pick table of the SIMPLE kernel: the walk takes the first entry whose
+          * (count << 18 | offset) exceeds (k << 18 | 0x3ffff), else the last */
+         uint32_t pk[4];
+         const uint32_t nstd = w[F3B_H_NSTD];
+         for (uint32_t q = 0; q < 4; q++) {
+            const uint32_t xi = (nstd == 0) ? 0 : (q < nstd ? q : nstd - 1);
+            const uint32_t off = w[F3B_H_XF_BASE] + xi * w[F3B_H_XF_STRIDE];
+            const uint32_t cnt = cum[q < nstd ? q : (nstd ? nstd - 1 : 0)];
+            pk[q] = (cnt >= 16384u ? 0xfffc0000u : (cnt << 18)) | off;
+         }
+         c.pick = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+         if ((hf & (F3B_HF_CHOOSER_CONST | F3B_HF_PLOT_READY | F3B_HF_FINAL | F3B_HF_XAOS |
+                    F3B_HF_PAL_LINEAR)) != (F3B_HF_CHOOSER_CONST | F3B_HF_PLOT_READY))
+            simple = false;
       }
       P.job_base = (uint32_t)j0;
       P.group_begin = jobs[j0].first_group;
@@ -378,8 +436,8 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       int grid = ctx->sms * bps;
       if ((uint32_t)grid > local_groups) grid = (int)local_groups;
       cudaStream_t st = fork ? ctx->side[chunk % F3B_SIDE_STREAMS] : ctx->stream;
-      const int nl = f3b_launch_iterate(P, consts.data(), j1 - j0, ctx->count_channel != 0, grid,
-                                        group_size, max_blob, st);
+      const int nl = f3b_launch_iterate(P, consts.data(), j1 - j0, ctx->count_channel != 0, simple,
+                                        grid, group_size, max_blob, st);
       if (!nl) return fail(ctx, "chaos-game launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       launches += nl;
    }
@@ -388,6 +446,11 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          CK(cudaEventRecord(ctx->join_ev[i], ctx->side[i]));
          CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
       }
+   const int nm = f3b_launch_hist_merge((float4 *)ctx->hist_color.p,
+                                        ctx->count_channel ? (float *)ctx->hist_count.p : nullptr,
+                                        ctx->hist_elems, ctx->lay, ctx->stream);
+   if (nm < 0) return fail(ctx, "histogram merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+   launches += nm;
    return stage_end(ctx, launches);
 }
 
@@ -447,6 +510,7 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
    P.accum = (float4 *)ctx->accum.p;
    P.width = ctx->width;
    P.height = ctx->height;
+   P.lay = ctx->lay;
    P.row_begin = row0;
    P.row_end = row1;
    P.oversample = d->oversample;
@@ -610,8 +674,8 @@ int f3b_hist_upload_u32(f3b_ctx *ctx, const uint32_t *buckets5) {
                                    ctx->stream);
    if (e == cudaSuccess)
       f3b_launch_hist_from_u32(tmp, (float4 *)ctx->hist_color.p,
-                               ctx->count_channel ? (float *)ctx->hist_count.p : nullptr, n,
-                               ctx->stream);
+                               ctx->count_channel ? (float *)ctx->hist_count.p : nullptr, ctx->width,
+                               ctx->height, ctx->lay, ctx->stream);
    e = cudaStreamSynchronize(ctx->stream);
    cudaFree(tmp);
    if (e != cudaSuccess) return fail(ctx, "hist upload failed: %s", cudaGetErrorString(e));
@@ -625,8 +689,8 @@ int f3b_hist_download_u32(f3b_ctx *ctx, uint32_t *buckets5) {
    uint32_t *tmp = nullptr;
    CK(cudaMalloc(&tmp, n * 5 * sizeof(uint32_t)));
    f3b_launch_hist_to_u32((const float4 *)ctx->hist_color.p,
-                          ctx->count_channel ? (const float *)ctx->hist_count.p : nullptr, tmp, n,
-                          ctx->stream);
+                          ctx->count_channel ? (const float *)ctx->hist_count.p : nullptr, tmp,
+                          ctx->width, ctx->height, ctx->lay, ctx->stream);
    cudaError_t e = cudaMemcpyAsync(buckets5, tmp, n * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                    ctx->stream);
    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -656,6 +720,7 @@ int f3b_accum_download(f3b_ctx *ctx, float *acc4) {
 }
 
 void *f3b_hist_color_ptr(f3b_ctx *ctx) { return ctx ? ctx->hist_color.p : nullptr; }
+size_t f3b_hist_elems(f3b_ctx *ctx) { return ctx ? ctx->hist_elems : 0; }
 void *f3b_hist_count_ptr(f3b_ctx *ctx) {
    return (ctx && ctx->count_channel) ? ctx->hist_count.p : nullptr;
 }

@@ -13,6 +13,21 @@
 
 typedef f3b_job f3b_sample_job;
 
+/* Where bucket (x, y) lives in the histogram planes: rows are `pitch` buckets apart. While
+ * the chaos game runs there are `replicas` copies of every plane, `replica_stride` buckets
+ * apart, and a CTA adds into copy blockIdx.x % replicas; they are summed into copy 0 before
+ * anything reads the histogram (f3b_api.cu: hist_layout_for says why). */
+struct F3HistLayout {
+   int pitch;
+   uint32_t replicas;
+   size_t replica_stride;
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ size_t f3b_hist_index(const F3HistLayout &L, int x, int y) {
+   return (size_t)x + (size_t)L.pitch * (size_t)y;
+}
+#endif
+
 #define F3B_CHAINS_PER_GROUP 256 /* largest chain group = threads per block of the chaos-game
                                     kernel; batches with few chains per temporal sample use
                                     smaller groups (32..256) so that more of them are resident */
@@ -26,6 +41,8 @@ struct F3ConstSample {
    uint4 lay;     /* F3B_HF_* flags | chooser stride << 8 | cmap_size << 20;
                      xform base | stride << 16;  palette offset | chooser offset << 16;
                      offset of the final xform's record (all in blob words) */
+   uint4 pick;    /* <= 4 xforms, no xaos: (cumulative count << 18 | record offset) per xform,
+                     saturated and padded with the last xform (f3b_iterate.cu, SIMPLE) */
 };
 #define F3B_HF_XAOS 1u
 #define F3B_HF_ROTATE 2u
@@ -33,9 +50,10 @@ struct F3ConstSample {
 #define F3B_HF_PAL_LINEAR 8u
 #define F3B_HF_FINAL 16u
 #define F3B_HF_CHOOSER_CONST 32u /* <= 4 xforms, no xaos: thresholds come from samp[].cum */
-/* temporal samples per launch: 352 x 80 B = 27.5 KB of the 32 KB parameter space that CUDA
- * 12.1+ gives sm_70+ kernels. An animation frame with 1000 temporal samples is 3 launches. */
-#define F3B_PARAM_SAMPLES 352
+/* temporal samples per launch: 296 x 96 B = 27.75 KB of the 32 KB parameter space that CUDA
+ * 12.1+ gives sm_70+ kernels. An animation frame with 1000 temporal samples is 4 launches
+ * (on side streams, so they overlap). */
+#define F3B_PARAM_SAMPLES 296
 
 struct F3IterateParams {
    const uint8_t *blobs;         /* device: packed temporal samples */
@@ -48,6 +66,7 @@ struct F3IterateParams {
    float4 *hist_color;           /* [height*width] r,g,b,a sums */
    float *hist_count;            /* [height*width] 255*logvis sums; may alias nothing when !count */
    int width, height;
+   F3HistLayout lay;             /* bucket (x,y) -> element of the histogram planes */
    int floor_adds;               /* bits 32/33: add floor(value) like the integer buckets */
    uint64_t seed;
    unsigned long long *badvals;  /* device counter */
@@ -57,11 +76,14 @@ struct F3IterateParams {
 /* returns the number of kernel launches made (0 on error; see cudaGetLastError). `consts`
  * holds the constants of jobs [p.job_base, p.job_base + n_consts), n_consts <= capacity */
 int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_consts,
-                       bool count_channel, int grid_blocks, int group_size, size_t smem_bytes,
-                       cudaStream_t stream);
+                       bool count_channel, bool simple, int grid_blocks, int group_size,
+                       size_t smem_bytes, cudaStream_t stream);
 int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes);
 int f3b_iterate_const_capacity(void);
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes);
+/* copy 0 += copies 1..replicas-1 of the colour (and count) planes */
+int f3b_launch_hist_merge(float4 *color, float *count, size_t elems, F3HistLayout lay,
+                          cudaStream_t stream);
 int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_index, const float *in,
                            int n, float *out, uint64_t seed, cudaStream_t stream);
 
@@ -70,6 +92,7 @@ struct F3DensityParams {
    const float *hist_count; /* == nullptr -> use hist_color[].w as the count channel */
    float4 *accum;
    int width, height;
+   F3HistLayout lay;          /* histogram addressing; accum / de_kidx are plain [height][width] */
    int row_begin, row_end;    /* target bucket rows written by this launch */
    int oversample;
    float k1, k2;
@@ -104,9 +127,9 @@ struct F3FinalParams {
 };
 int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream);
 
-int f3b_launch_hist_from_u32(const uint32_t *src5, float4 *color, float *count, size_t n,
-                             cudaStream_t stream);
-int f3b_launch_hist_to_u32(const float4 *color, const float *count, uint32_t *dst5, size_t n,
-                           cudaStream_t stream);
+int f3b_launch_hist_from_u32(const uint32_t *src5, float4 *color, float *count, int width,
+                             int height, F3HistLayout lay, cudaStream_t stream);
+int f3b_launch_hist_to_u32(const float4 *color, const float *count, uint32_t *dst5, int width,
+                           int height, F3HistLayout lay, cudaStream_t stream);
 
 #endif

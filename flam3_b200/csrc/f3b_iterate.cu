@@ -69,12 +69,16 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
  * depended on the module loading mode (31 ms lazy vs 23 ms eager for the same code). */
 #define c_samp(ci) P.samp[ci]
 
-template <bool COUNT>
+/* SIMPLE: every temporal sample of the launch has <= 4 xforms, no xaos, no final xform, a
+ * step palette and fully visible xforms (the classic flame): the flag tests fold away and
+ * the xform pick is three compares on a packed table from the constant bank. */
+template <bool COUNT, bool SIMPLE>
 __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
    extern __shared__ __align__(16) uint32_t smem[];
    const float *sf = reinterpret_cast<const float *>(smem);
 
    const uint32_t tid = threadIdx.x;
+   const size_t rep_off = (size_t)(blockIdx.x % P.lay.replicas) * P.lay.replica_stride;
    uint32_t loaded_job = 0xffffffffu;
    unsigned int bad = 0;
 
@@ -127,13 +131,22 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
 
       for (int i = -(int)job.fuse; i < n_store; i++) {
          float qx, qy, qc, qv;
-         uint32_t fn;
+         uint32_t fn = 0;
          /* flam3.c:249-270: pick + apply, retrying a bad value up to 4 times in place */
          for (int consec = 0;;) {
-            const uint32_t k = rng.next() & (F3B_CHOOSER_GRAIN - 1u);
+            const uint32_t rnd = rng.next();
+            const uint32_t k = rnd & (F3B_CHOOSER_GRAIN - 1u);
             /* `ci` is redefined opaquely so the constant loads below stay in the loop; hoisted,
              * they would occupy a dozen registers across the variation code */
             asm volatile("" : "+r"(ci));
+            uint32_t xo;
+            if (SIMPLE) {
+               /* (k << 18 | 0x3ffff) against (count << 18 | record offset) */
+               const uint32_t key = __funnelshift_l(0xffffffffu, rnd, 18);
+               const uint4 e = c_samp(ci).pick;
+               const uint32_t sel = key < e.x ? e.x : (key < e.y ? e.y : (key < e.z ? e.z : e.w));
+               xo = sel & 0x3ffffu;
+            } else {
             /* fn = number of cumulative thresholds <= k; rows are padded with 16384 */
             if (hf & HF_CHOOSER_CONST) {
                const uint4 c = c_samp(ci).cum;
@@ -149,8 +162,9 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
                }
             }
             const uint32_t xfl = c_samp(ci).lay.y; /* base | stride << 16 */
-            const bool isbad = f3b_apply_xform(sf, (xfl & 0xffffu) + fn * (xfl >> 16), px, py, pc, qx,
-                                               qy, qc, qv, rng);
+            xo = (xfl & 0xffffu) + fn * (xfl >> 16);
+            }
+            const bool isbad = f3b_apply_xform(sf, xo, px, py, pc, qx, qy, qc, qv, rng);
             if (!isbad) break;
             bad++;
             if (++consec >= 5) break;
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
          pc = qc;
 
          /* flam3.c:280-287: final xform does not feed back into the orbit */
-         if (hf & HF_FINAL) {
+         if (!SIMPLE && (hf & HF_FINAL)) {
             const float final_opacity = sf[F3B_H_FINAL_OPACITY];
             bool apply = (final_opacity == 1.0f);
             if (!apply) apply = rng.u01() < final_opacity;
@@ -192,11 +206,11 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
             x = dx * rot.x + dy * rot.y + cs.z;
             y = dx * rot.z + dy * rot.w + cs.w;
          }
-         if (!(x >= bb.x && y >= bb.y && x <= bb.z && y <= bb.w) || qv == 0.0f) continue;
+         if (!(x >= bb.x && y >= bb.y && x <= bb.z && y <= bb.w) || (!SIMPLE && qv == 0.0f)) continue;
          const int ix = (int)((x - bb.x) * cs.x);
          const int iy = (int)((y - bb.y) * cs.y);
          if (ix >= P.width || iy >= P.height) continue;
-         const size_t bidx = (size_t)ix + (size_t)P.width * (size_t)iy;
+         const size_t bidx = rep_off + f3b_hist_index(P.lay, ix, iy);
 
          /* rect.c:465-498: palette lookup */
          const int cmap_size = (int)(hf >> 20);
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
          int pi = (int)findex;
          const float4 *dmap = reinterpret_cast<const float4 *>(sf + (c_samp(ci).lay.z & 0xffffu));
          float4 col;
-         if (hf & HF_PLOT_READY) {
+         if (SIMPLE || (hf & HF_PLOT_READY)) {
             /* step lookup, every xform fully visible, dmap truncated on the host */
             pi = pi < 0 ? 0 : (pi >= cmap_size - 1 ? cmap_size - 1 : pi);
             col = dmap[pi];
@@ -297,25 +311,33 @@ int f3b_iterate_max_blocks_per_sm(size_t smem_bytes) {
 
 int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes) {
    int nb = 0;
-   cudaFuncSetAttribute(f3b_iterate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+   cudaFuncSetAttribute(f3b_iterate_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                         (int)(F3B_MAX_BLOB_WORDS * 4));
-   cudaFuncSetAttribute(f3b_iterate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+   cudaFuncSetAttribute(f3b_iterate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                         (int)(F3B_MAX_BLOB_WORDS * 4));
-   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true>, group_size,
+   cudaFuncSetAttribute(f3b_iterate_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)(F3B_MAX_BLOB_WORDS * 4));
+   cudaFuncSetAttribute(f3b_iterate_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)(F3B_MAX_BLOB_WORDS * 4));
+   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false>, group_size,
                                                      smem_bytes) != cudaSuccess)
       return 0;
    return nb;
 }
 
 int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_consts,
-                       bool count_channel, int grid_blocks, int group_size, size_t smem_bytes,
-                       cudaStream_t stream) {
+                       bool count_channel, bool simple, int grid_blocks, int group_size,
+                       size_t smem_bytes, cudaStream_t stream) {
    if (grid_blocks <= 0 || n_consts <= 0 || n_consts > F3B_PARAM_SAMPLES) return 0;
    if (group_size < 32 || group_size > F3B_BLOCK || (group_size & 31)) return 0;
    for (int i = 0; i < n_consts; i++) p.samp[i] = consts[i];
-   if (count_channel)
-      f3b_iterate_kernel<true><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
+   if (count_channel && simple)
+      f3b_iterate_kernel<true, true><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
+   else if (count_channel)
+      f3b_iterate_kernel<true, false><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
+   else if (simple)
+      f3b_iterate_kernel<false, true><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
    else
-      f3b_iterate_kernel<false><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
+      f3b_iterate_kernel<false, false><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
 }

@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(256) f3b_logscale_kernel(const F3DensityParams
    size_t i = i0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
    const size_t stride = (size_t)gridDim.x * blockDim.x;
    for (; i < n; i += stride) {
-      const float4 c = P.hist_color[i];
+      const size_t y = i / (size_t)P.width, x = i - y * (size_t)P.width;
+      const float4 c = P.hist_color[f3b_hist_index(P.lay, (int)x, (int)y)];
       if (c.w == 0.0f) continue;
       const float ls = (P.k1 * log1pf(c.w * P.k2)) / c.w;
       float4 a = P.accum[i];
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256) f3b_logscale_kernel(const F3DensityParams
  */
 __device__ __forceinline__ float f3b_de_count(const F3DensityParams &P, int x, int y) {
    if (x < 0 || x >= P.width || y < 0 || y >= P.height) return 0.0f;
-   const size_t gi = (size_t)x + (size_t)P.width * y;
+   const size_t gi = f3b_hist_index(P.lay, x, y);
    return P.hist_count ? __ldg(P.hist_count + gi) : __ldg(&P.hist_color[gi].w);
 }
 
@@ -86,13 +87,13 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(cons
       gy[q] = tile_y * DE_TILE + threadIdx.y + q * DE_ROWS;
       live[q] = gx < P.width && gy[q] >= P.class_row_begin && gy[q] < P.class_row_end;
       c[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live[q]) c[q] = P.hist_color[(size_t)gx + (size_t)P.width * gy[q]];
+      if (live[q]) c[q] = P.hist_color[f3b_hist_index(P.lay, gx, gy[q])];
    }
 #pragma unroll
    for (int q = 0; q < DE_PER_THREAD; q++) {
       if (!live[q]) continue;
       const size_t gi = (size_t)gx + (size_t)P.width * gy[q];
-      const float cnt = P.hist_count ? P.hist_count[gi] : c[q].w;
+      const float cnt = P.hist_count ? P.hist_count[f3b_hist_index(P.lay, gx, gy[q])] : c[q].w;
       unsigned kidx = DE_NO_SOURCE;
       float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
       bool has_self = false;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_kernel(const 
          if (k != DE_NO_SOURCE) {
             const unsigned rad = __ldg(P.de_radius + k);
             if (rad) {
-               const float4 c = P.hist_color[gi];
+               const float4 c = P.hist_color[f3b_hist_index(P.lay, gx, gy)];
                const float ls = (P.k1 * log1pf(c.w * P.k2)) / c.w;
                col = make_float4(c.x * ls, c.y * ls, c.z * ls, c.w * ls);
                meta = k | (rad << 16);
@@ -483,36 +484,71 @@ int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream) {
 /* histogram import/export in the reference's bits=33 bucket layout (uint32[5])        */
 /* ---------------------------------------------------------------------------------- */
 __global__ void f3b_hist_from_u32_kernel(const uint32_t *src, float4 *color, float *count,
-                                         size_t n) {
+                                         int width, int height, F3HistLayout lay) {
+   const size_t n = (size_t)width * height;
    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
    const size_t stride = (size_t)gridDim.x * blockDim.x;
    for (; i < n; i += stride) {
       const uint32_t *b = src + i * 5;
-      color[i] = make_float4((float)b[0], (float)b[1], (float)b[2], (float)b[3]);
-      if (count) count[i] = (float)b[4];
+      const size_t y = i / (size_t)width, o = f3b_hist_index(lay, (int)(i - y * (size_t)width), (int)y);
+      color[o] = make_float4((float)b[0], (float)b[1], (float)b[2], (float)b[3]);
+      if (count) count[o] = (float)b[4];
    }
 }
 __global__ void f3b_hist_to_u32_kernel(const float4 *color, const float *count, uint32_t *dst,
-                                       size_t n) {
+                                       int width, int height, F3HistLayout lay) {
+   const size_t n = (size_t)width * height;
    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
    const size_t stride = (size_t)gridDim.x * blockDim.x;
    for (; i < n; i += stride) {
-      const float4 c = color[i];
+      const size_t y = i / (size_t)width, o = f3b_hist_index(lay, (int)(i - y * (size_t)width), (int)y);
+      const float4 c = color[o];
       uint32_t *b = dst + i * 5;
       b[0] = (uint32_t)fminf(c.x, 4294967040.0f);
       b[1] = (uint32_t)fminf(c.y, 4294967040.0f);
       b[2] = (uint32_t)fminf(c.z, 4294967040.0f);
       b[3] = (uint32_t)fminf(c.w, 4294967040.0f);
-      b[4] = count ? (uint32_t)fminf(count[i], 4294967040.0f) : b[3];
+      b[4] = count ? (uint32_t)fminf(count[o], 4294967040.0f) : b[3];
    }
 }
-int f3b_launch_hist_from_u32(const uint32_t *src5, float4 *color, float *count, size_t n,
-                             cudaStream_t stream) {
-   f3b_hist_from_u32_kernel<<<148 * 8, 256, 0, stream>>>(src5, color, count, n);
+int f3b_launch_hist_from_u32(const uint32_t *src5, float4 *color, float *count, int width,
+                             int height, F3HistLayout lay, cudaStream_t stream) {
+   f3b_hist_from_u32_kernel<<<148 * 8, 256, 0, stream>>>(src5, color, count, width, height, lay);
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
 }
-int f3b_launch_hist_to_u32(const float4 *color, const float *count, uint32_t *dst5, size_t n,
-                           cudaStream_t stream) {
-   f3b_hist_to_u32_kernel<<<148 * 8, 256, 0, stream>>>(color, count, dst5, n);
+int f3b_launch_hist_to_u32(const float4 *color, const float *count, uint32_t *dst5, int width,
+                           int height, F3HistLayout lay, cudaStream_t stream) {
+   f3b_hist_to_u32_kernel<<<148 * 8, 256, 0, stream>>>(color, count, dst5, width, height, lay);
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
+}
+
+/* ---------------------------------------------------------------------------------- */
+/* sum of the histogram replicas the chaos game wrote (f3b_api.cu: hist_layout_for)    */
+/* ---------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) f3b_hist_merge_kernel(float4 *color, float *count, size_t n,
+                                                             F3HistLayout lay) {
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const size_t stride = (size_t)gridDim.x * blockDim.x;
+   for (; i < n; i += stride) {
+      float4 a = color[i];
+      float c = count ? count[i] : 0.0f;
+      for (uint32_t r = 1; r < lay.replicas; r++) {
+         const float4 b = color[i + r * lay.replica_stride];
+         a.x += b.x;
+         a.y += b.y;
+         a.z += b.z;
+         a.w += b.w;
+         if (count) c += count[i + r * lay.replica_stride];
+      }
+      color[i] = a;
+      if (count) count[i] = c;
+   }
+}
+int f3b_launch_hist_merge(float4 *color, float *count, size_t elems, F3HistLayout lay,
+                          cudaStream_t stream) {
+   if (lay.replicas <= 1) return 0;
+   int blocks = (int)((elems + 255) / 256);
+   if (blocks > 148 * 8) blocks = 148 * 8;
+   f3b_hist_merge_kernel<<<blocks, 256, 0, stream>>>(color, count, elems, lay);
+   return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

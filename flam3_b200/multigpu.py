@@ -48,11 +48,14 @@ def make_allreduce_exchange(core, nbuckets, dist=None):
     if dist is None:
         import torch.distributed as dist
     d = core._dll
+    d.f3b_hist_elems.restype = C.c_size_t
+    d.f3b_hist_elems.argtypes = [C.c_void_p]
 
     def exchange(ctx_ptr):
         ctx = C.c_void_p(ctx_ptr)
         color = d.f3b_hist_color_ptr(ctx)
         count = d.f3b_hist_count_ptr(ctx)
+        nbuckets = int(d.f3b_hist_elems(ctx))  # height * row pitch (>= height * width)
         t = device_tensor(color, nbuckets * 4)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         if count:

@@ -140,8 +140,12 @@ int f3b_hist_download_u32(f3b_ctx *ctx, uint32_t *buckets5);
 /* accumulator: float[4] per bucket (abucket_float, flam3.c:3825) */
 int f3b_accum_upload(f3b_ctx *ctx, const float *acc4);
 int f3b_accum_download(f3b_ctx *ctx, float *acc4);
-void *f3b_hist_color_ptr(f3b_ctx *ctx); /* device float4[height*width] */
-void *f3b_hist_count_ptr(f3b_ctx *ctx); /* device float[height*width] or NULL */
+void *f3b_hist_color_ptr(f3b_ctx *ctx); /* device float4[f3b_hist_elems] */
+void *f3b_hist_count_ptr(f3b_ctx *ctx); /* device float[f3b_hist_elems] or NULL */
+/* buckets in a histogram plane = height * row pitch (the pitch may exceed the width; padding
+ * buckets stay zero): the number of elements an exchange between GPUs must cover. Use
+ * f3b_hist_download_u32 / f3b_hist_upload_u32 for the reference's [height][width] layout. */
+size_t f3b_hist_elems(f3b_ctx *ctx);
 void *f3b_accum_ptr(f3b_ctx *ctx);      /* device float4[height*width] */
 void *f3b_stream_ptr(f3b_ctx *ctx);     /* cudaStream_t the context launches on */
 
