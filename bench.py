@@ -306,18 +306,21 @@ def main():
     hist = ctx.hist_download_u32()
     hits_total = float(hist[..., 4].astype(np.float64).sum() / 255.0)
     peak, peak_src = load_peaks()
-    launches_iter = max(1, it_n)
+    # one chaos-game launch per step at this workload (+ the 40 us merge of the histogram
+    # copies, which the stage time includes): per-launch figures are per step
+    launches_iter = max(1, args.steps)
     iter_s_per_launch = (it_ms / 1e3) / launches_iter
     hits_per_launch = hits_total / 1.0 / world  # per rank and frame == per launch
     alg_bytes = 20.0 * hits_per_launch
     achieved = alg_bytes / iter_s_per_launch / 1e9
     roofline = {
-        "kernel": "f3b_iterate_kernel<COUNT=false> (chaos game + red.global.add.v4.f32 histogram)",
+        "kernel": "f3b_iterate_kernel<COUNT=false, SIMPLE=true> (chaos game + red.global.add.v4.f32 "
+                  "histogram; time includes f3b_hist_merge_kernel)",
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": load_ncu_traffic(),
         "peak_source": peak_src,
-        "note": ("atomic/L2-bound scatter, not an HBM stream: 20 B algorithmic RMW per in-bounds "
-                 "hit; the 42.6 MB histogram is L2-resident. See DESIGN.md §5."),
+        "note": ("L2-reduction / L1TEX-bound scatter, not an HBM stream: 20 B algorithmic RMW per "
+                 "in-bounds hit; the histogram copies are L2-resident. See DESIGN.md section 5."),
         "avg_launch_ms": 1e3 * iter_s_per_launch,
         "iters_per_s_kernel_only": iters_per_step / world / iter_s_per_launch * world,
         "in_bounds_fraction": hits_total / iters_per_step,
