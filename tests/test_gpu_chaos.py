@@ -220,3 +220,44 @@ def test_xaos_final_xform_opacity_palette_linear(flame0):
                 for i in range(256))
     a, b, g, *_ = three_way(xml)
     assert_statistically_equal(a, b, g)
+
+
+def test_full_size_c2_statistics_match_the_reference(flame0):
+    """BASELINE.json's headline configuration at FULL size (1920x1080, quality 2000,
+    4.147e9 iterations) against the reference at quality 60 on the same frame (the CPU
+    needs seconds for that, minutes for q2000). Quality only changes the Monte-Carlo noise, so:
+      * the iteration count is the reference's formula (quality * width * height);
+      * the fraction of iterations that land in the frame equals the reference's;
+      * block-averaged (16x16) images agree to a high PSNR;
+      * the share of the hits taken by each third of the image rows matches the
+        reference's histogram within its sampling noise."""
+    import os
+    ref, gpu, core = libs()
+    xml_hi = resize(flame0, 1920, 1080, scale=540, quality=2000, oversample=1, temporal_samples=1)
+    xml_lo = resize(flame0, 1920, 1080, scale=540, quality=60, oversample=1, temporal_samples=1)
+    gg = gpu.parse(xml_hi)
+    geo = gpu.buffer_geometry(gg)
+    ctx = gpu.render_context(core)
+    ctx.width, ctx.height = geo["width"], geo["height"]
+    g_img, g_st, _ = gpu.render(gg, isaac_seed="c2")
+    assert g_st["rv"] == 0 and g_st["num_iters"] == 2000.0 * 1920 * 1080
+    g_hist = ctx.hist_download_u32()[..., 4].astype(np.float64) / 255.0
+
+    r_img, r_st, r_buckets, _, _, _ = ref_render_capture(ref, ref.parse(xml_lo), isaac_seed="c2",
+                                                         nthreads=os.cpu_count() or 1)
+    r_hist = r_buckets[..., 4].astype(np.float64) / 255.0
+    assert r_st["num_iters"] == 60.0 * 1920 * 1080
+
+    g_frac, r_frac = g_hist.sum() / g_st["num_iters"], r_hist.sum() / r_st["num_iters"]
+    assert abs(g_frac - r_frac) < 2e-3, (g_frac, r_frac)
+
+    h = r_hist.shape[0] // 3
+    for k in range(3):
+        gs = g_hist[k * h:(k + 1) * h].sum() / g_hist.sum()
+        rs = r_hist[k * h:(k + 1) * h].sum() / r_hist.sum()
+        assert abs(gs - rs) < 6 * np.sqrt(rs * (1 - rs) / r_hist.sum()) + 1e-4, (k, gs, rs)
+
+    def blocks(img):
+        a = img[:1072, :1920].astype(np.float64)
+        return a.reshape(67, 16, 120, 16, 3).mean(axis=(1, 3))
+    assert psnr(blocks(g_img), blocks(r_img)) > 36.0, psnr(blocks(g_img), blocks(r_img))
