@@ -316,7 +316,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    for (; group_size > 32; group_size /= 2) {
       uint64_t groups = 0;
       for (int j = 0; j < n_jobs; j++) groups += (jobs[j].n_chains + group_size - 1) / group_size;
-      const bool fills_gpu = groups >= 3ull * (uint64_t)ctx->sms;
+      const bool fills_gpu = groups / (uint64_t)nranks >= 3ull * (uint64_t)ctx->sms; /* this rank's share */
       const bool lanes_used = 2 * total_chains >= groups * (uint64_t)group_size;
       if (fills_gpu && lanes_used) break;
    }

@@ -219,9 +219,22 @@ static void *pack_worker(void *arg) {
    return NULL;
 }
 
+/* The reference seeds one ISAAC context per worker thread from the frame's context, 16 words
+ * each, for every temporal sample (rect.c:858-865). Draw the same words, so that spec->rc
+ * ends in the same state, and fold them into the seed of the sample's random streams. */
+static uint64_t draw_sample_seed(flam3_frame *spec, int fi, int nthreads) {
+   uint64_t h = 0x9e3779b97f4a7c15ull ^ (uint64_t)fi;
+   for (int k = 0; k < 16 * nthreads; k++) {
+      h ^= (uint64_t)f3b_isaac_next(&spec->rc) & 0xffffffffull;
+      h *= 0x100000001b3ull;
+      h ^= h >> 29;
+   }
+   return h;
+}
+
 static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *tfilter,
                       const double *tdeltas, int batch_num, int nts, int cmap_size, int floor_adds,
-                      packed_batch *out) {
+                      packed_batch *out, uint64_t *seeds, int rc_threads) {
    packed_free(out);
    out->s = (packed_sample *)calloc((size_t)nts, sizeof(packed_sample));
    if (!out->s) return 1;
@@ -240,6 +253,8 @@ static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *
    int started = 0;
    for (int i = 1; i < nthreads; i++)
       if (pthread_create(&th[started], NULL, pack_worker, &job) == 0) started++;
+   /* the ISAAC draws are serial by nature: do them while the workers pack */
+   for (int ts = 0; ts < nts; ts++) seeds[ts] = draw_sample_seed(spec, batch_num * nts + ts, rc_threads);
    pack_worker(&job);
    for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
    return 0;
@@ -260,6 +275,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
    double *filter = NULL, *temporal_filter = NULL, *temporal_deltas = NULL;
    blob_buf blobs = {NULL, 0, 0};
    f3b_job *jobs = NULL;
+   uint64_t *sample_seeds = NULL;
    packed_batch packed = {NULL, 0};
    packed_sample last;
    memset(&last, 0, sizeof(last));
@@ -370,7 +386,8 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
    f3b_camera cam;
    memset(&cam, 0, sizeof(cam));
    jobs = (f3b_job *)calloc((size_t)ntemporal_samples, sizeof(f3b_job));
-   if (!jobs) goto done;
+   sample_seeds = (uint64_t *)calloc((size_t)ntemporal_samples, sizeof(uint64_t));
+   if (!jobs || !sample_seeds) goto done;
 
    for (int batch_num = 0; batch_num < nbatches; batch_num++) {
       const double de_time = spec->time + temporal_deltas[batch_num * ntemporal_samples];
@@ -406,7 +423,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       if (batch_num == 0) t_setup = now_ms() - t_setup;
       t0 = now_ms();
       if (pack_batch(spec, &g, temporal_filter, temporal_deltas, batch_num, ntemporal_samples,
-                     cmap_size, spec->bits != 64, &packed)) {
+                     cmap_size, spec->bits != 64, &packed, sample_seeds, nthreads)) {
          fprintf(stderr, "flam3_render (B200): out of memory packing temporal samples\n");
          goto done;
       }
@@ -439,15 +456,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          const double batch_size = nsamples / (nbatches * ntemporal_samples);
          stats->num_iters += batch_size;
 
-         /* The reference seeds one ISAAC context per worker thread from the frame's
-          * context, 16 words each (rect.c:858-865). Draw the same words, so spec->rc
-          * ends in the same state, and fold them into the seed of this sample's streams. */
-         uint64_t h = 0x9e3779b97f4a7c15ull ^ (uint64_t)fi;
-         for (int k = 0; k < 16 * nthreads; k++) {
-            h ^= (uint64_t)f3b_isaac_next(&spec->rc) & 0xffffffffull;
-            h *= 0x100000001b3ull;
-            h ^= h >> 29;
-         }
+         const uint64_t h = sample_seeds[ts]; /* drawn from spec->rc in pack_batch */
          if (ts == 0) seed ^= h;
 
          f3b_job *jb = &jobs[ts];
@@ -617,6 +626,7 @@ done:
    free(filter);
    free(blobs.words);
    free(jobs);
+   free(sample_seeds);
    packed_free(&packed);
    clear_cp(&cp, 0);
    stats->render_seconds = (int)(time(NULL) - tstart);

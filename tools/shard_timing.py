@@ -25,3 +25,5 @@ run("q2000 shard 0/4", 2000, (0, 4))
 run("q2000 full again", 2000)
 run("q2000 full sub_batch 5000", 2000, sub_batch_size=5000)
 run("q2000 full sub_batch 20000", 2000, sub_batch_size=20000)
+run("q2000 shard 0/8", 2000, (0, 8))
+run("q2000 shard 3/8", 2000, (3, 8))
