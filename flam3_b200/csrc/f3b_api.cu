@@ -267,27 +267,45 @@ static int accum_materialize(f3b_ctx *ctx) {
 }
 
 /* Chain planning. The reference gives each of its `nthreads` workers batch_size/nthreads
- * iterations cut into sub-batches of sub_batch_size (rect.c:279-284, 840); here the
- * "workers" are the resident GPU threads. */
-uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len, uint32_t n_jobs) {
+ * iterations and cuts them into sub-batches of at most sub_batch_size (rect.c:840, 279-284);
+ * a sub-batch is a chain: random start, `fuse` discarded iterations, then stored ones. So
+ * the reference runs  nthreads * ceil((n / nthreads) / sub_batch_size)  chains, and that is
+ * the MINIMUM used here, with `workers` = the caller's nthreads.
+ *
+ * Chain length is an observable: only `fuse` (15) iterations are discarded after a restart,
+ * so for slowly converging systems the image depends on how often the orbit restarts
+ * (measured: the reference's own output moves by 10+ dB of PSNR between sub_batch_size 10000
+ * and 2048 on such genomes, tests/test_gpu_variations.py). Beyond the minimum the count is
+ * therefore only rounded up, never by more than 2.5x (chains stay >= 0.4 sub_batch_size
+ * unless the caller's own nthreads says otherwise):
+ *   - to whole rounds of a node's worth of resident threads (F3B_PLAN_GPUS GPUs), when the
+ *     minimum is within 2.5x of that: the plan - and with it the image for a given seed -
+ *     then does not depend on how many GPUs of the node share the frame, and each of them
+ *     gets whole rounds of its resident threads (at 8 GPUs a 1080p q2000 frame would
+ *     otherwise leave every GPU half empty and latency bound);
+ *   - else to whole rounds of one GPU's resident threads when there are more chains than
+ *     that, so no tail wave is left. */
+#define F3B_PLAN_GPUS 8
+uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len, uint32_t n_jobs,
+                         uint32_t workers) {
    if (!ctx || n_iters == 0) return 0;
    if (max_chain_len == 0) max_chain_len = 10000;
    if (n_jobs == 0) n_jobs = 1;
+   if (workers == 0) workers = 1;
    const uint64_t T = (uint64_t)ctx->sms * ctx->iter_blocks_per_sm * F3B_CHAINS_PER_GROUP;
    uint64_t Ts = T / n_jobs;
    if (Ts < 32) Ts = 32;
    if (Ts >= F3B_CHAINS_PER_GROUP) Ts -= Ts % F3B_CHAINS_PER_GROUP;
-   /* Chain length is an observable of the reference: every chain starts at a random point
-    * and only `fuse` (15) iterations are discarded, so for slowly converging systems the
-    * image depends on how often the orbit is restarted (measured: the reference's own
-    * output moves by 10+ dB of PSNR between sub_batch_size 10000 and 2048 on such genomes,
-    * tests/test_gpu_variations.py). Chains are therefore sub_batch_size long, as in
-    * iter_thread (rect.c:279-284): as few chains as that allows, and once there are more
-    * chains than resident threads their number is rounded up to whole rounds of threads so
-    * no tail wave is left (the chains get marginally shorter, never longer). */
-   uint64_t chains = (n_iters + max_chain_len - 1) / max_chain_len;
+   const uint64_t Tv = Ts * F3B_PLAN_GPUS;
+
+   const uint64_t per_worker = (n_iters + workers - 1) / workers;
+   uint64_t chains = (uint64_t)workers * ((per_worker + max_chain_len - 1) / max_chain_len);
+   if (chains > n_iters) chains = n_iters;
    if (chains == 0) chains = 1;
-   if (chains > Ts) chains = ((chains + Ts - 1) / Ts) * Ts;
+   if (2 * Tv <= 5 * chains)
+      chains = ((chains + Tv - 1) / Tv) * Tv;
+   else if (chains > Ts)
+      chains = ((chains + Ts - 1) / Ts) * Ts;
    if (chains > 0xfffffff0ull) chains = 0xfffffff0ull;
    return (uint32_t)chains;
 }
@@ -305,7 +323,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    uint64_t total_chains = 0;
    for (int j = 0; j < n_jobs; j++) {
       f3b_job &jb = jobs[j];
-      if (jb.n_chains == 0) jb.n_chains = f3b_plan_chains(ctx, jb.n_iters, max_chain_len, n_jobs);
+      if (jb.n_chains == 0) jb.n_chains = f3b_plan_chains(ctx, jb.n_iters, max_chain_len, n_jobs, 1);
       total_chains += jb.n_chains;
    }
    /* Chains per group (= threads per CTA): 256 when there is plenty of work; small batches

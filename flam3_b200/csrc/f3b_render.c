@@ -419,6 +419,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
        * packing a sample is independent host work (~45 us), so with many temporal samples
        * (flam3-animate: 1000 per frame) it is spread over a few host threads. ---- */
       blobs.used = 0;
+      const uint32_t max_chain = spec->sub_batch_size > 0 ? (uint32_t)spec->sub_batch_size : 10000u;
       uint64_t seed = 0x243f6a8885a308d3ull;
       if (batch_num == 0) t_setup = now_ms() - t_setup;
       t0 = now_ms();
@@ -462,7 +463,8 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          f3b_job *jb = &jobs[ts];
          jb->blob_offset = (uint64_t)blobs.used * 4;
          jb->n_iters = batch_size > 0 ? (uint64_t)batch_size : 0;
-         jb->n_chains = 0;
+         jb->n_chains = f3b_plan_chains(ctx, jb->n_iters, max_chain, (uint32_t)ntemporal_samples,
+                                        (uint32_t)nthreads);
          jb->fuse = spec->earlyclip ? 100 : 15; /* FUSE_28 : FUSE_27, rect.c:39-40,266 */
          jb->first_group = 0;
          jb->sample_id = (uint32_t)(h ^ (h >> 32));
@@ -496,7 +498,6 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       t_serial += now_ms() - t0;
       t0 = now_ms();
       /* ---- chaos game: one launch for the whole batch ---- */
-      const uint32_t max_chain = spec->sub_batch_size > 0 ? (uint32_t)spec->sub_batch_size : 10000u;
       if (g_inject) {
          if (g_inject_n != (size_t)g.width * g.height) {
             fprintf(stderr, "flam3_render (B200): injected histogram has %zu buckets, frame needs "

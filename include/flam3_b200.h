@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define F3B_ABI_VERSION 1
+#define F3B_ABI_VERSION 2
 
 typedef struct f3b_ctx f3b_ctx;
 
@@ -72,10 +72,13 @@ typedef struct {
    uint32_t sample_id;   /* RNG stream id of this temporal sample */
 } f3b_job;
 
-/* Number of chains the library would use for n_iters stored iterations when the launch
- * holds n_jobs temporal samples and no chain may store more than max_chain_len iterations
- * (= flam3_frame.sub_batch_size, rect.c:279). */
-uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len, uint32_t n_jobs);
+/* Number of chains the library uses for n_iters stored iterations when the launch holds
+ * n_jobs temporal samples, no chain may store more than max_chain_len iterations
+ * (= flam3_frame.sub_batch_size, rect.c:279) and the caller asked for `workers` threads
+ * (= flam3_frame.nthreads: the reference runs workers * ceil(n / workers / sub_batch_size)
+ * sub-batches, rect.c:840 + 279-284; that is the minimum, see f3b_api.cu for the rounding). */
+uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len, uint32_t n_jobs,
+                         uint32_t workers);
 
 /* Runs the jobs' chains with chain-group index g where g % nranks == rank and adds the
  * hits into this context's histogram. floor_adds=1 reproduces the integer bucket

@@ -33,5 +33,6 @@ two = "<flames>" + resize(f0, 3840, 2160, scale=1080, quality=500, oversample=2,
 run("C3 4K os2 q500 ts=1000 (1 GPU)", two, reps=2, ngenomes=2, time=50.0)
 two = "<flames>" + f0 + f1 + "</flames>"
 run("C4 animate frame 640x480 q10 ts=1000", two, reps=5, ngenomes=2, time=50.0)
+run("C4 same, nthreads=16 (flam3-animate default)", two, reps=5, ngenomes=2, time=50.0, nthreads=16)
 for p in sorted(glob.glob(os.path.join(ROOT, "tests/golden/c5_*.flam3")))[:12]:
     run("C5 " + os.path.basename(p), resize(open(p).read(), 1024, 1024, quality=1000, temporal_samples=1), reps=2)
