@@ -4,6 +4,7 @@
  * (rect.c:685-1247). Host-side glue only; the kernels are in f3b_iterate.cu / f3b_post.cu.
  */
 #include <cuda_runtime.h>
+#include <time.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -514,8 +515,17 @@ int f3b_badvals(f3b_ctx *ctx, double *out) {
    return 0;
 }
 
+static double host_ms() {
+   struct timespec ts;
+   clock_gettime(CLOCK_MONOTONIC, &ts);
+   return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1) {
    if (!ctx || !d) return 1;
+   const bool timing = getenv("F3B_TIMING") != nullptr;
+   const double tt0 = host_ms();
+   double tt1 = tt0, tt2 = tt0;
    if (!ctx->accum.p) return fail(ctx, "f3b_density: f3b_frame_begin not called");
    CK(cudaSetDevice(ctx->device));
    if (row0 < 0) row0 = 0;
@@ -566,7 +576,9 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
       CK(cudaMemcpyAsync(ctx->de_radius.p, radius.data(), (size_t)d->n_kernels,
                          cudaMemcpyHostToDevice, ctx->stream));
       ctx->h2d_bytes += nc * sizeof(float) + (size_t)d->n_kernels;
+      tt1 = host_ms();
       CK(cudaStreamSynchronize(ctx->stream));
+      tt2 = host_ms();
       P.de_coefs = (const float *)ctx->de_coefs.p;
       P.de_radius = (const uint8_t *)ctx->de_radius.p;
       P.n_kernels = d->n_kernels;
@@ -592,6 +604,9 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
    if (stage_begin(ctx, F3B_STAGE_DENSITY)) return 1;
    const int nl = f3b_launch_density(P, ctx->stream);
    if (!nl) return fail(ctx, "density launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+   if (timing)
+      fprintf(stderr, "f3b timing (density host ms): tables+copies %.3f  wait for the stream %.3f  launch %.3f\n",
+              tt1 - tt0, tt2 - tt1, host_ms() - tt2);
    return stage_end(ctx, nl);
 }
 

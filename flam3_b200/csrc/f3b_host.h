@@ -42,6 +42,11 @@ int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_
                     int cmap_size, int floor_adds, uint32_t *words, size_t cap_words,
                     size_t *used_words, int *count_is_alpha);
 
+/* test hook: first index i with r_i >= thr[k] of the reference's running sum r += dr, by the
+ * packer's closed form (closed_form=1) or by the plain loop (0) */
+int f3b_debug_chooser_counts(double dr, unsigned n, const double *thr, int nthr, uint32_t *first,
+                             int closed_form);
+
 /* ISAAC as the reference runs it on LP64 (isaac.c + isaac.h): next 32-bit draw from ctx. */
 unsigned long f3b_isaac_next(randctx *ctx);
 void f3b_isaac_refill(randctx *ctx);

@@ -242,6 +242,72 @@ static int pack_var_params(const flam3_xform *x, int id, double *p) {
  * reference's 16384-entry table whose value is <= j. Walks the same double-precision
  * accumulation as flam3_create_chaos_distrib (flam3.c:165-224), so the step positions
  * are identical. xi < 0 -> plain weights; else weights scaled by chaos[xi][.] */
+/* First index i in [0, n] with r_i >= T for every T of thr[0..nthr) (non-decreasing), where
+ * r_0 = 0 and r_{i+1} = fl(r_i + dr) in double arithmetic, exactly as the reference's loop
+ * accumulates it (flam3.c:197-218). The 16384 dependent additions cost ~20 us per row, too
+ * much when a frame packs 1000 temporal samples, so the sequence is evaluated in closed form
+ * binade by binade: while r stays in [2^k, 2^(k+1)) every r_i is a multiple of ulp = 2^(k-52)
+ * and fl(r + dr) = r + rn(dr / ulp) * ulp, a constant step (round-to-nearest-even ties are
+ * walked one by one; they need dr's lowest set bit to sit exactly half an ulp below, which
+ * only one binade can have). Binade crossings are done with real additions.
+ * tests/test_cpu_boundary.py checks it against the plain loop on random and adversarial weights. */
+static void first_crossings(double dr, unsigned n, const double *thr, int nthr, uint32_t *first) {
+   int j = 0;
+   double r = 0.0;
+   unsigned i = 0;
+   while (j < nthr && r >= thr[j]) first[j++] = 0; /* thresholds <= 0 */
+   while (j < nthr && i < n) {
+      /* one real step: also how a binade is entered */
+      r += dr;
+      i++;
+      while (j < nthr && r >= thr[j]) first[j++] = i;
+      if (j >= nthr || i >= n) break;
+      int e;
+      (void)frexp(r, &e); /* r in [2^(e-1), 2^e) */
+      const int sh = 53 - e; /* r * 2^sh is an integer below 2^53 */
+      const double dq = ldexp(dr, sh);
+      if (!(dq >= 1.0) || dq >= 9007199254740992.0) continue; /* step below an ulp or huge: walk */
+      const double fl = floor(dq);
+      const double frac = dq - fl;
+      if (frac == 0.5) { /* tie binade: walk it with real additions */
+         const double top = ldexp(1.0, e);
+         while (j < nthr && i < n && r < top) {
+            r += dr;
+            i++;
+            while (j < nthr && r >= thr[j]) first[j++] = i;
+         }
+         continue;
+      }
+      const uint64_t d_int = (uint64_t)fl + (frac > 0.5 ? 1u : 0u);
+      uint64_t s_int = (uint64_t)ldexp(r, sh);
+      const uint64_t lim = 1ull << 53;
+      /* steps that stay inside the binade and inside the table */
+      uint64_t m_max = (lim - 1 - s_int) / d_int;
+      if (m_max > (uint64_t)(n - i)) m_max = n - i;
+      while (j < nthr) {
+         /* does thr[j] fall inside this linear stretch? */
+         int te;
+         (void)frexp(thr[j], &te);
+         uint64_t m_need;
+         if (thr[j] <= 0.0 || te < e) m_need = 0; /* already passed (cannot happen: handled above) */
+         else if (te > e) break;                    /* beyond this binade */
+         else {
+            const uint64_t t_int = (uint64_t)ldexp(thr[j], sh);
+            if (t_int <= s_int) m_need = 0;
+            else m_need = (t_int - s_int + d_int - 1) / d_int;
+         }
+         if (m_need > m_max) break;
+         first[j++] = i + (uint32_t)m_need;
+      }
+      if (m_max > 0) {
+         s_int += m_max * d_int;
+         i += (unsigned)m_max;
+         r = ldexp((double)s_int, -sh);
+      }
+   }
+   while (j < nthr) first[j++] = n; /* never reached inside the table */
+}
+
 static int chooser_row(const flam3_genome *cp, int nstd, int xi, uint32_t *cum) {
    double dr = 0.0;
    for (int i = 0; i < nstd; i++) {
@@ -259,20 +325,35 @@ static int chooser_row(const flam3_genome *cp, int nstd, int xi, uint32_t *cum) 
    }
    dr /= (double)F3B_CHOOSER_GRAIN;
 
-   for (int i = 0; i < nstd; i++) cum[i] = 0;
+   /* The reference's loop (flam3.c:197-218): table[i] = j where j advances while r >= t,
+    * t being the running sum of the weights and r the running sum of dr. Entry i therefore
+    * holds the number of running sums t_k <= r_i (capped at nstd-1), and the cumulative
+    * count of xform k is the first i with r_i >= t_k. */
+   double thr[nstd > 1 ? nstd : 1];
+   double t = 0.0;
+   for (int k = 0; k < nstd - 1; k++) {
+      t += (xi >= 0) ? cp->xform[k].density * cp->chaos[xi][k] : cp->xform[k].density;
+      thr[k] = t;
+   }
+   first_crossings(dr, F3B_CHOOSER_GRAIN, thr, nstd - 1, cum);
+   cum[nstd - 1] = F3B_CHOOSER_GRAIN;
+   return 0;
+}
+
+/* the plain loop, kept for the tests that pin the closed form above to it */
+int f3b_debug_chooser_counts(double dr, unsigned n, const double *thr, int nthr, uint32_t *first,
+                             int closed_form) {
+   if (closed_form) {
+      first_crossings(dr, n, thr, nthr, first);
+      return 0;
+   }
    int j = 0;
-   double t = cp->xform[0].density;
-   if (xi >= 0) t *= cp->chaos[xi][0];
    double r = 0.0;
-   for (unsigned i = 0; i < F3B_CHOOSER_GRAIN; i++) {
-      while (r >= t && j < nstd - 1) {
-         j++;
-         t += (xi >= 0) ? cp->xform[j].density * cp->chaos[xi][j] : cp->xform[j].density;
-      }
-      cum[j]++; /* histogram of picked xforms, made cumulative below */
+   for (unsigned i = 0; i <= n && j < nthr; i++) {
+      while (j < nthr && r >= thr[j]) first[j++] = i;
       r += dr;
    }
-   for (int i = 1; i < nstd; i++) cum[i] += cum[i - 1];
+   while (j < nthr) first[j++] = n;
    return 0;
 }
 

@@ -197,3 +197,52 @@ def test_animate_frame_range_follows_flam3_animate():
     assert frame_range({"begin": "5", "end": "7"}, xml) == (5, 7)
     assert frame_range({"frame": "42"}, xml) == (42, 42)
     assert frame_range({"time": "17"}, xml) == (17, 17)
+
+
+def test_chooser_closed_form_equals_the_reference_loop():
+    """The packer finds where the reference's 16384-step running sum (flam3.c:197-218,
+    r += dr in double) crosses the cumulative weights in closed form, binade by binade
+    (f3b_pack.c: first_crossings). It must give the very indices the plain loop gives:
+    random weights, weights with short mantissas (round-to-even ties), tiny and zero
+    weights, many xforms."""
+    import flam3_b200 as fb
+    gpu = fb.load_dropin()
+    f = gpu._dll.f3b_debug_chooser_counts
+    f.argtypes = [C.c_double, C.c_uint, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_uint32), C.c_int]
+    rs = np.random.RandomState(2024)
+    cases = []
+    for _ in range(1500):
+        n = rs.randint(2, 9)
+        kind = rs.randint(6)
+        if kind == 0:
+            w = rs.uniform(0.0, 1.0, n)
+        elif kind == 1:
+            w = rs.randint(1, 9, n) / 8.0                    # short mantissas: ties
+        elif kind == 2:
+            w = 2.0 ** rs.randint(-12, 4, n)                 # powers of two
+        elif kind == 3:
+            w = rs.uniform(0.0, 1.0, n) * (rs.uniform(0, 1, n) < 0.7)   # some zero weights
+            w[0] = max(w[0], 1e-3)
+        elif kind == 4:
+            w = rs.uniform(0.0, 1.0, n) * 10.0 ** rs.randint(-8, 3, n)  # wildly different scales
+        else:
+            w = rs.randint(1, 4, n) * 3.0 / 16384.0          # steps of a few grains
+        cases.append(w)
+    cases.append(np.full(40, 0.37))
+    cases.append(np.array([1.0, 1e-12, 1.0]))
+    cases.append(np.array([0.5, 0.5]))
+    for w in cases:
+        total = 0.0
+        for d in w:
+            total += float(d)
+        dr = total / 16384.0
+        thr, t = [], 0.0
+        for d in w[:-1]:
+            t += float(d)
+            thr.append(t)
+        thr_c = (C.c_double * len(thr))(*thr)
+        a = (C.c_uint32 * len(thr))()
+        b = (C.c_uint32 * len(thr))()
+        f(dr, 16384, thr_c, len(thr), a, 1)
+        f(dr, 16384, thr_c, len(thr), b, 0)
+        assert list(a) == list(b), (w, list(a), list(b))

@@ -10,4 +10,4 @@ f0 = open(os.path.join(ROOT, "tests/golden/test_flame0.flam3")).read()
 f1 = open(os.path.join(ROOT, "tests/golden/test_flame1.flam3")).read()
 g = gpu.parse("<flames>" + f0 + f1 + "</flames>")
 for _ in range(4):
-    gpu.render(g, ngenomes=2, time=50.0)
+    gpu.render(g, ngenomes=2, time=50.0, nthreads=16)  # flam3-animate passes the core count
