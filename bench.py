@@ -49,7 +49,9 @@ def workload_xml(quality=QUALITY):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks
+    line). NVML is polled from a thread every few milliseconds (the timed region can be
+    shorter than one nvidia-smi polling period); nvidia-smi -lms is the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -57,8 +59,30 @@ class ClockSampler:
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu_index = [], None, gpu_index
+        self.nvml, self.handle, self.thread, self.stop_flag = None, None, None, False
+        self.sm, self.mx, self.reasons = [], [], set()
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu_index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu_index])
+                except Exception:
+                    idx = self.gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
@@ -68,11 +92,34 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        names = {n.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 n.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 n.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 n.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None,
+                    "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc:
             self.proc.terminate()
             try:
@@ -92,7 +139,7 @@ class ClockSampler:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def load_peaks():
