@@ -31,3 +31,16 @@ def resize(xml, width, height, scale=None, quality=None, oversample=None, **extr
         attrs["supersample"] = str(int(oversample))
     attrs.update(extra)
     return set_flame_attrs(xml, **attrs)
+
+
+def flame_attr(xml, name, default=None):
+    """Value of attribute `name` on the first <flame ...> tag."""
+    m = re.search(r"<flame\b[^>]*?\s%s=\"([^\"]*)\"" % re.escape(name), xml)
+    return m.group(1) if m else default
+
+
+def rescale(xml, width, height, quality=None, **extra):
+    """Resize keeping the field of view: `scale` (pixels per unit) follows the width."""
+    w0 = float(flame_attr(xml, "size", "%d %d" % (width, height)).split()[0])
+    s0 = float(flame_attr(xml, "scale", "1"))
+    return resize(xml, width, height, scale=s0 * width / w0, quality=quality, **extra)
