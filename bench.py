@@ -285,9 +285,11 @@ def main():
     if world > 1:
         from flam3_b200.multigpu import make_allreduce_exchange, make_strip_gather
 
-        gpu.set_exchange(make_allreduce_exchange(core, nb))
+        ordered = not os.environ.get("F3B_HOST_SYNC_COLLECTIVES")
+        gpu.set_stream_ordered(ordered)
+        gpu.set_exchange(make_allreduce_exchange(core, nb, stream_ordered=ordered))
         if not os.environ.get("F3B_NO_STRIPS"):
-            gpu.set_strip_gather(make_strip_gather(rank, world))
+            gpu.set_strip_gather(make_strip_gather(rank, world, core=core, stream_ordered=ordered))
 
     ctx = gpu.render_context(core)
     ctx.width, ctx.height = geo["width"], geo["height"]

@@ -160,6 +160,10 @@ class Flam3Lib:
         self._exchange_keep = cb
         f(C.cast(cb, C.c_void_p), None)
 
+    def set_stream_ordered(self, on):
+        """Callbacks enqueue on the render stream instead of being bracketed by host syncs."""
+        self._dll.f3b_render_set_stream_ordered(int(bool(on)))
+
     def set_strip_gather(self, fn):
         """fn(ctx_ptr, image_ptr, row_bytes, rows_per) assembles the per-rank image strips
         (include/flam3_b200_dropin.h: f3b_render_set_strip_gather). None = whole-frame

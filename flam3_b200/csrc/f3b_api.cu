@@ -35,6 +35,9 @@ struct f3b_ctx {
    int count_channel = 1;
    DevBuf hist_color, hist_count, accum, image;
    DevBuf blobs, jobs, groups, de_coefs, de_radius, filter, de_kidx, de_tiles;
+   std::vector<float> de_coefs_host;    /* what de_coefs / de_radius / filter hold on the device */
+   std::vector<uint8_t> de_radius_host;
+   std::vector<double> filter_host;
    bool accum_zero_pending = false; /* accumulators are logically zero, memset not yet issued */
    unsigned long long *d_badvals = nullptr;
    cudaStream_t side[F3B_SIDE_STREAMS] = {nullptr, nullptr, nullptr};
@@ -569,15 +572,22 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
          radius[k] = (uint8_t)r;
          if (k <= d->max_filter_index && r > maxr) maxr = r;
       }
-      if (ensure(ctx, ctx->de_coefs, nc * sizeof(float))) return 1;
-      if (ensure(ctx, ctx->de_radius, (size_t)d->n_kernels)) return 1;
-      CK(cudaMemcpyAsync(ctx->de_coefs.p, coefs.data(), nc * sizeof(float), cudaMemcpyHostToDevice,
-                         ctx->stream));
-      CK(cudaMemcpyAsync(ctx->de_radius.p, radius.data(), (size_t)d->n_kernels,
-                         cudaMemcpyHostToDevice, ctx->stream));
-      ctx->h2d_bytes += nc * sizeof(float) + (size_t)d->n_kernels;
-      tt1 = host_ms();
-      CK(cudaStreamSynchronize(ctx->stream));
+      /* the tables only change with the estimator parameters: upload (and wait, the host
+       * vectors are temporaries) only when they differ from what the device already holds */
+      if (coefs != ctx->de_coefs_host || radius != ctx->de_radius_host) {
+         if (ensure(ctx, ctx->de_coefs, nc * sizeof(float))) return 1;
+         if (ensure(ctx, ctx->de_radius, (size_t)d->n_kernels)) return 1;
+         CK(cudaMemcpyAsync(ctx->de_coefs.p, coefs.data(), nc * sizeof(float), cudaMemcpyHostToDevice,
+                            ctx->stream));
+         CK(cudaMemcpyAsync(ctx->de_radius.p, radius.data(), (size_t)d->n_kernels,
+                            cudaMemcpyHostToDevice, ctx->stream));
+         ctx->h2d_bytes += nc * sizeof(float) + (size_t)d->n_kernels;
+         tt1 = host_ms();
+         CK(cudaStreamSynchronize(ctx->stream));
+         ctx->de_coefs_host.swap(coefs);
+         ctx->de_radius_host.swap(radius);
+      } else
+         tt1 = host_ms();
       tt2 = host_ms();
       P.de_coefs = (const float *)ctx->de_coefs.p;
       P.de_radius = (const uint8_t *)ctx->de_radius.p;
@@ -639,11 +649,19 @@ int f3b_finish_device_rows(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int 
    if (row1 > d->image_height) row1 = d->image_height;
    if (alloc_rows < d->image_height) alloc_rows = d->image_height;
    const size_t ibytes = (size_t)d->image_width * alloc_rows * d->nchan * d->bytes_per_channel;
-   if (ensure(ctx, ctx->filter, fbytes)) return 1;
    if (ensure(ctx, ctx->image, ibytes)) return 1;
-   CK(cudaMemcpyAsync(ctx->filter.p, d->filter, fbytes, cudaMemcpyHostToDevice, ctx->stream));
-   ctx->h2d_bytes += fbytes;
-   CK(cudaStreamSynchronize(ctx->stream));
+   {
+      const size_t nf = (size_t)d->filter_width * d->filter_width;
+      if (ctx->filter_host.size() != nf || memcmp(ctx->filter_host.data(), d->filter, fbytes) != 0) {
+         if (ensure(ctx, ctx->filter, fbytes)) return 1;
+         ctx->filter_host.assign(d->filter, d->filter + nf);
+         /* from the context's own copy, which outlives the call */
+         CK(cudaMemcpyAsync(ctx->filter.p, ctx->filter_host.data(), fbytes, cudaMemcpyHostToDevice,
+                            ctx->stream));
+         ctx->h2d_bytes += fbytes;
+         CK(cudaStreamSynchronize(ctx->stream));
+      }
+   }
 
    F3FinalParams P;
    memset(&P, 0, sizeof(P));

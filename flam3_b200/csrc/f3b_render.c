@@ -80,6 +80,7 @@ static void *g_exchange_user = NULL;
 /*  - strip gather: see include/flam3_b200_dropin.h (row-strip post-pass across ranks) */
 typedef void (*f3b_gather_fn)(f3b_ctx *, void *image, size_t row_bytes, int rows_per, void *user);
 static f3b_gather_fn g_gather = NULL;
+static int g_stream_ordered = 0;
 static void *g_gather_user = NULL;
 void f3b_render_set_device_only(int on) { g_device_only = on; }
 void f3b_render_set_shard(int rank, int nranks) {
@@ -90,6 +91,7 @@ void f3b_render_set_shard(int rank, int nranks) {
    g_rank = rank;
    g_nranks = nranks;
 }
+void f3b_render_set_stream_ordered(int on) { g_stream_ordered = on; }
 void f3b_render_set_strip_gather(f3b_gather_fn cb, void *user) {
    g_gather = cb;
    g_gather_user = user;
@@ -114,6 +116,33 @@ static double now_ms(void) {
    struct timespec ts;
    clock_gettime(CLOCK_MONOTONIC, &ts);
    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+/* The DE filter bank depends only on (estimator, estimator_minimum, estimator_curve,
+ * oversample): the last one built is kept (under g_lock), since animations and repeated
+ * renders ask for the same bank every batch and building it costs ~0.15 ms of idle GPU. */
+static struct {
+   int valid;
+   double max_rad, min_rad, curve;
+   int oversample;
+   f3b_de_filters de;
+} g_de_cache;
+
+static int de_filters_cached(double max_rad, double min_rad, double curve, int oversample,
+                             f3b_de_filters *out) {
+   if (!(g_de_cache.valid && g_de_cache.max_rad == max_rad && g_de_cache.min_rad == min_rad &&
+         g_de_cache.curve == curve && g_de_cache.oversample == oversample)) {
+      if (g_de_cache.valid) f3b_de_filters_free(&g_de_cache.de);
+      g_de_cache.valid = 0;
+      if (f3b_de_filters_create(max_rad, min_rad, curve, oversample, &g_de_cache.de)) return 1;
+      g_de_cache.valid = 1;
+      g_de_cache.max_rad = max_rad;
+      g_de_cache.min_rad = min_rad;
+      g_de_cache.curve = curve;
+      g_de_cache.oversample = oversample;
+   }
+   *out = g_de_cache.de; /* borrowed: owned by the cache */
+   return 0;
 }
 
 static int poll_progress(flam3_frame *spec, double percent, int stage) {
@@ -407,8 +436,8 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       memset(&de, 0, sizeof(de));
       de_alive = 0;
       if (cp.estimator > 0.0) {
-         if (f3b_de_filters_create(cp.estimator, cp.estimator_minimum, cp.estimator_curve,
-                                   oversample, &de)) {
+         if (de_filters_cached(cp.estimator, cp.estimator_minimum, cp.estimator_curve, oversample,
+                               &de)) {
             fprintf(stderr, "de.kernel_size returned 0 - aborting.\n");
             goto done;
          }
@@ -509,7 +538,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
                              spec->bits != 64, max_chain, g_rank, g_nranks))
          goto gpu_error;
       if (g_exchange) {
-         if (f3b_sync(ctx)) goto gpu_error;
+         if (!g_stream_ordered && f3b_sync(ctx)) goto gpu_error;
          (*g_exchange)(ctx, g_exchange_user);
       }
 
@@ -546,10 +575,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          if (strip_row1 > strip_row0 && f3b_density_rows(ctx, &dd, a0, a1)) goto gpu_error;
       } else if (f3b_density(ctx, &dd))
          goto gpu_error;
-      if (de_alive) {
-         f3b_de_filters_free(&de);
-         de_alive = 0;
-      }
+      de_alive = 0; /* the bank belongs to the cache */
       t_dens += now_ms() - t0;
    }
    t0 = now_ms();
@@ -582,7 +608,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       if (strips) {
          void *image = NULL;
          if (f3b_finish_device_rows(ctx, &fd, strip_row0, strip_row1, strip_rows_per * g_nranks, &image) ||
-             f3b_sync(ctx))
+             (!g_stream_ordered && f3b_sync(ctx)))
             goto gpu_error;
          (*g_gather)(ctx, image, (size_t)g.image_width * nchan * bytes_per_channel, strip_rows_per,
                      g_gather_user);
@@ -621,7 +647,6 @@ gpu_error:
    rv = 1;
 
 done:
-   if (de_alive) f3b_de_filters_free(&de);
    free(temporal_filter);
    free(temporal_deltas);
    free(filter);

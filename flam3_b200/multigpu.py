@@ -39,10 +39,21 @@ def shard_groups(n_groups, rank, nranks):
     return list(range(rank, n_groups, nranks))
 
 
-def make_allreduce_exchange(core, nbuckets, dist=None):
+def _render_stream(d, ctx):
+    """torch view of the drop-in's render stream, so that collectives are ordered with the
+    kernels by the stream and not by host synchronisation."""
+    import torch
+
+    d.f3b_stream_ptr.restype = C.c_void_p
+    d.f3b_stream_ptr.argtypes = [C.c_void_p]
+    return torch.cuda.ExternalStream(int(d.f3b_stream_ptr(ctx)))
+
+
+def make_allreduce_exchange(core, nbuckets=None, dist=None, stream_ordered=False):
     """Returns the callback for Flam3Lib.set_exchange: sums the per-rank histograms in
     place with one all-reduce per plane (float32; the adds are integer valued, so the sum
-    is exact below 2^24 per channel and order independent)."""
+    is exact below 2^24 per channel and order independent). stream_ordered=True issues the
+    collective on the render stream and returns at once (pair with set_stream_ordered(True))."""
     import torch
 
     if dist is None:
@@ -50,23 +61,34 @@ def make_allreduce_exchange(core, nbuckets, dist=None):
     d = core._dll
     d.f3b_hist_elems.restype = C.c_size_t
     d.f3b_hist_elems.argtypes = [C.c_void_p]
+    cache = {}
 
     def exchange(ctx_ptr):
         ctx = C.c_void_p(ctx_ptr)
         color = d.f3b_hist_color_ptr(ctx)
         count = d.f3b_hist_count_ptr(ctx)
-        nbuckets = int(d.f3b_hist_elems(ctx))  # height * row pitch (>= height * width)
-        t = device_tensor(color, nbuckets * 4)
+        n = int(d.f3b_hist_elems(ctx))  # height * row pitch (>= height * width)
+        key = (color, count, n)
+        if key not in cache:
+            cache.clear()
+            cache[key] = (device_tensor(color, n * 4), device_tensor(count, n) if count else None,
+                          _render_stream(d, ctx) if stream_ordered else None)
+        t, t2, stream = cache[key]
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                if t2 is not None:
+                    dist.all_reduce(t2, op=dist.ReduceOp.SUM)
+            return
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        if count:
-            t2 = device_tensor(count, nbuckets)
+        if t2 is not None:
             dist.all_reduce(t2, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
 
     return exchange
 
 
-def make_strip_gather(rank, nranks, dist=None):
+def make_strip_gather(rank, nranks, dist=None, core=None, stream_ordered=False):
     """Returns the callback for Flam3Lib.set_strip_gather: an in-place all-gather of the
     ranks' image strips (rows_per * row_bytes bytes each) so that every rank ends up with
     the whole image."""
@@ -74,10 +96,20 @@ def make_strip_gather(rank, nranks, dist=None):
 
     if dist is None:
         import torch.distributed as dist
+    cache = {}
 
     def gather(ctx_ptr, image_ptr, row_bytes, rows_per):
         chunk = int(row_bytes) * int(rows_per)
-        t = device_tensor(image_ptr, chunk * nranks, "|u1")
+        key = (image_ptr, chunk)
+        if key not in cache:
+            cache.clear()
+            stream = _render_stream(core._dll, C.c_void_p(ctx_ptr)) if (stream_ordered and core is not None) else None
+            cache[key] = (device_tensor(image_ptr, chunk * nranks, "|u1"), stream)
+        t, stream = cache[key]
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(t, t[rank * chunk:(rank + 1) * chunk])
+            return
         dist.all_gather_into_tensor(t, t[rank * chunk:(rank + 1) * chunk])
         torch.cuda.synchronize()
 

@@ -63,6 +63,11 @@ void f3b_render_set_exchange(void (*cb)(struct f3b_ctx *, void *), void *user);
  * device image of nranks*rows_per rows of row_bytes bytes; gather must fill in the other
  * ranks' strips (an in-place all-gather of rows_per*row_bytes bytes per rank). NULL = off:
  * every rank post-processes the whole frame. */
+/* By default both callbacks are called with the render stream idle and must have finished
+ * their device work when they return. With stream_ordered = 1 they are called without any
+ * host synchronisation and must enqueue their work on the render stream (f3b_stream_ptr of
+ * include/flam3_b200.h), e.g. an NCCL collective issued on that stream. */
+void f3b_render_set_stream_ordered(int on);
 typedef void (*f3b_gather_fn)(struct f3b_ctx *, void *image, size_t row_bytes, int rows_per,
                               void *user);
 void f3b_render_set_strip_gather(f3b_gather_fn cb, void *user);

@@ -31,16 +31,26 @@ for name, xml, kw in [("os1", resize(f0, 640, 363, scale=160, quality=50, tempor
     gpu.set_strip_gather(None)
     alone, st, _ = gpu.render(g, isaac_seed="mg", sub_batch_size=200)
     gpu.set_shard(rank, world)
-    gpu.set_exchange(make_allreduce_exchange(core, geo["width"] * geo["height"]))
+    gpu.set_stream_ordered(False)
+    gpu.set_exchange(make_allreduce_exchange(core))
     whole, st, _ = gpu.render(g, isaac_seed="mg", sub_batch_size=200)
     gpu.set_strip_gather(make_strip_gather(rank, world))
     strips, st, _ = gpu.render(g, isaac_seed="mg", sub_batch_size=200)
-    same = np.array_equal(alone, whole) and np.array_equal(alone, strips)
+    # the same with the collectives issued on the render stream (no host synchronisation)
+    gpu.set_stream_ordered(True)
+    gpu.set_exchange(make_allreduce_exchange(core, stream_ordered=True))
+    gpu.set_strip_gather(make_strip_gather(rank, world, core=core, stream_ordered=True))
+    ordered, st, _ = gpu.render(g, isaac_seed="mg", sub_batch_size=200)
+    ordered2, st, _ = gpu.render(g, isaac_seed="mg", sub_batch_size=200)
+    gpu.set_stream_ordered(False)
+    same = (np.array_equal(alone, whole) and np.array_equal(alone, strips) and
+            np.array_equal(alone, ordered) and np.array_equal(alone, ordered2))
     t = torch.tensor([1 if same else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("%s: N=%d sharded+allreduce %s, +strips %s (mean %.2f)" % (
-            name, world, np.array_equal(alone, whole), np.array_equal(alone, strips), alone.mean()), flush=True)
+        print("%s: N=%d sharded+allreduce %s, +strips %s, stream-ordered %s (mean %.2f)" % (
+            name, world, np.array_equal(alone, whole), np.array_equal(alone, strips),
+            np.array_equal(alone, ordered) and np.array_equal(alone, ordered2), alone.mean()), flush=True)
     ok = ok and bool(t.item())
 dist.barrier()
 dist.destroy_process_group()
