@@ -118,6 +118,66 @@ __device__ __forceinline__ float f3b_cos(float x) {
    return c;
 }
 
+
+/* Fast transcendental helpers for the variation code. The chaos game is compared with the
+ * reference statistically (image PSNR, visit frequencies), and per application to ~1e-5
+ * relative (tests/test_gpu_variations.py); the SFU approximations (ex2/lg2/rcp, ~1e-6) are
+ * well inside that, and a random genome spends most of its instructions in libm's slow
+ * paths otherwise (profiles/r01_c5_*: powf 94, atan2f 44 per call site, sinh/cosh 20 each). */
+__device__ __forceinline__ float f3b_pow(float x, float y) { /* x >= 0 */
+   if (y == 0.0f) return 1.0f;
+   return exp2f(y * __log2f(x));
+}
+__device__ __forceinline__ float f3b_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float f3b_log(float x) { return __logf(x); }
+/* atan2 from a degree-15 odd least-squares polynomial on [0,1] (max error 4e-8 rad before
+ * fp32 rounding) */
+__device__ __forceinline__ float f3b_atan2(float y, float x) {
+   const float ax = fabsf(x), ay = fabsf(y);
+   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+   if (mx == 0.0f) return 0.0f;
+   const float a = __fdividef(mn, mx);
+   const float s = a * a;
+   float r = fmaf(s, -0.00407331f, 0.02194661f);
+   r = fmaf(r, s, -0.05606318f);
+   r = fmaf(r, s, 0.09656256f);
+   r = fmaf(r, s, -0.13915802f);
+   r = fmaf(r, s, 0.19948509f);
+   r = fmaf(r, s, -0.33330107f);
+   r = fmaf(r, s, 0.99999944f);
+   r *= a;
+   if (ay > ax) r = 1.57079632679f - r;
+   if (x < 0.0f) r = 3.14159265359f - r;
+   return copysignf(r, y);
+}
+/* sinh and cosh together from one exponential; the series keeps sinh accurate near 0 */
+__device__ __forceinline__ void f3b_sinhcosh(float x, float *sh, float *ch) {
+   const float ax = fabsf(x);
+   const float e = __expf(ax), ei = __fdividef(1.0f, e);
+   *ch = 0.5f * (e + ei);
+   float s = 0.5f * (e - ei);
+   if (ax < 0.25f) {
+      const float x2 = ax * ax;
+      s = ax * fmaf(x2, fmaf(x2, fmaf(x2, 1.98412698e-4f, 8.33333333e-3f), 0.16666667f), 1.0f);
+   }
+   *sh = copysignf(s, x);
+}
+__device__ __forceinline__ float f3b_sinh(float x) {
+   float s, c;
+   f3b_sinhcosh(x, &s, &c);
+   return s;
+}
+__device__ __forceinline__ float f3b_cosh(float x) {
+   float s, c;
+   f3b_sinhcosh(x, &s, &c);
+   return c;
+}
+__device__ __forceinline__ float f3b_tan(float x) {
+   float s, c;
+   f3b_sincos(x, &s, &c);
+   return __fdividef(s, c);
+}
+
 /* per-point quantities shared by the variations (flam3_iter_helper, private.h:102-119) */
 struct F3Pt {
    float tx, ty, sumsq, rad, atan_xy, atan_yx, sina, cosa;
@@ -132,27 +192,27 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
    float p0 = 0.0f, p1 = 0.0f;
    switch (id) {
       case 17: { /* popcorn: p = {c20, c21} */
-         float dx = tanf(3.0f * ty);
-         float dy = tanf(3.0f * tx);
+         float dx = f3b_tan(3.0f * ty);
+         float dy = f3b_tan(3.0f * tx);
          p0 += w * (tx + p[0] * f3b_sin(dx));
          p1 += w * (ty + p[1] * f3b_sin(dy));
       } break;
       case 18: { /* exponential */
-         float dx = w * expf(tx - 1.0f), s, c;
+         float dx = w * f3b_exp(tx - 1.0f), s, c;
          f3b_sincos(F3B_PI * ty, &s, &c);
          p0 += dx * c;
          p1 += dx * s;
       } break;
       case 19: { /* power */
-         float r = w * powf(rad, sina);
+         float r = w * f3b_pow(rad, sina);
          p0 += r * cosa;
          p1 += r * sina;
       } break;
       case 20: { /* cosine */
          float s, c;
          f3b_sincos(tx * F3B_PI, &s, &c);
-         p0 += w * (c * coshf(ty));
-         p1 -= w * (s * sinhf(ty));
+         p0 += w * (c * f3b_cosh(ty));
+         p1 -= w * (s * f3b_sinh(ty));
       } break;
       case 21: { /* rings: p = {dx} */
          float dx = p[0];
@@ -200,7 +260,7 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
       case 32: { /* julian: p = {power, cn, rN} */
          float t_rnd = truncf(p[2] * rng.u01());
          float a = (atan_yx + 2.0f * F3B_PI * t_rnd) / p[0], s, c;
-         float r = w * powf(sumsq, p[1]);
+         float r = w * f3b_pow(sumsq, p[1]);
          f3b_sincos(a, &s, &c);
          p0 += r * c;
          p1 += r * s;
@@ -211,7 +271,7 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          if ((t_rnd & 1) == 0) a = (2.0f * F3B_PI * (float)t_rnd + atan_yx) / p[0];
          else a = (2.0f * F3B_PI * (float)t_rnd - atan_yx) / p[0];
          f3b_sincos(a, &s, &c);
-         float r = w * powf(sumsq, p[1]);
+         float r = w * f3b_pow(sumsq, p[1]);
          p0 += r * c;
          p1 += r * s;
       } break;
@@ -245,7 +305,7 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          p1 += r * s;
       } break;
       case 38: { /* ngon: p = {power/2, b=2pi/sides, corners, circle} */
-         float r_factor = powf(sumsq, p[0]);
+         float r_factor = f3b_pow(sumsq, p[0]);
          float b = p[1];
          float phi = atan_yx - b * floorf(atan_yx / b);
          if (phi > 0.5f * b) phi -= b;
@@ -262,12 +322,12 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
       } break;
       case 42: /* tangent */
          p0 += w * f3b_sin(tx) / f3b_cos(ty);
-         p1 += w * tanf(ty);
+         p1 += w * f3b_tan(ty);
          break;
       case 44: { /* rays */
          float ang = w * rng.u01() * F3B_PI;
          float r = w / (sumsq + F3B_EPS);
-         float tanr = w * tanf(ang) * r;
+         float tanr = w * f3b_tan(ang) * r;
          p0 += tanr * f3b_cos(tx);
          p1 += tanr * f3b_sin(ty);
       } break;
@@ -301,9 +361,9 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
       case 50: { /* super_shape: p = {pm_4, n2, n3, rnd, holes, pneg1_n1} */
          float st, ct;
          f3b_sincos(p[0] * atan_yx + F3B_PI_4, &st, &ct);
-         float t1 = powf(fabsf(ct), p[1]);
-         float t2 = powf(fabsf(st), p[2]);
-         float r = w * ((p[3] * rng.u01() + (1.0f - p[3]) * rad) - p[4]) * powf(t1 + t2, p[5]) /
+         float t1 = f3b_pow(fabsf(ct), p[1]);
+         float t2 = f3b_pow(fabsf(st), p[2]);
+         float r = w * ((p[3] * rng.u01() + (1.0f - p[3]) * rad) - p[4]) * f3b_pow(t1 + t2, p[5]) /
                    rad;
          p0 += r * tx;
          p1 += r * ty;
@@ -330,10 +390,10 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
       case 55: { /* bipolar: p = {ps = -pi/2 * shift} */
          float t = sumsq + 1.0f;
          float x2 = 2.0f * tx;
-         float y = 0.5f * atan2f(2.0f * ty, sumsq - 1.0f) + p[0];
+         float y = 0.5f * f3b_atan2(2.0f * ty, sumsq - 1.0f) + p[0];
          if (y > F3B_PI_2) y = -F3B_PI_2 + fmodf(y + F3B_PI_2, F3B_PI);
          else if (y < -F3B_PI_2) y = F3B_PI_2 - fmodf(F3B_PI_2 - y, F3B_PI);
-         p0 += w * 0.25f * F3B_2_PI * logf((t + x2) / (t - x2));
+         p0 += w * 0.25f * F3B_2_PI * f3b_log((t + x2) / (t - x2));
          p1 += w * F3B_2_PI * y;
       } break;
       case 56: { /* boarders */
@@ -376,26 +436,26 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          p1 -= w * (dy + (float)y * p[0]);
       } break;
       case 59: { /* cpow: p = {va, vc, vd, power} */
-         float lnr = 0.5f * logf(sumsq), s, c;
+         float lnr = 0.5f * f3b_log(sumsq), s, c;
          float ang = p[1] * atan_yx + p[2] * lnr + p[0] * floorf(p[3] * rng.u01());
-         float m = w * expf(p[1] * lnr - p[2] * atan_yx);
+         float m = w * f3b_exp(p[1] * lnr - p[2] * atan_yx);
          f3b_sincos(ang, &s, &c);
          p0 += m * c;
          p1 += m * s;
       } break;
       case 60: { /* curve: p = {xamp, yamp, 1/xlen^2, 1/ylen^2} */
-         p0 += w * (tx + p[0] * expf(-ty * ty * p[2]));
-         p1 += w * (ty + p[1] * expf(-tx * tx * p[3]));
+         p0 += w * (tx + p[0] * f3b_exp(-ty * ty * p[2]));
+         p1 += w * (ty + p[1] * f3b_exp(-tx * tx * p[3]));
       } break;
       case 61: { /* edisc */
          float tmp = sumsq + 1.0f;
          float tmp2 = 2.0f * tx;
          float xmax = (sqrtf(tmp + tmp2) + sqrtf(tmp - tmp2)) * 0.5f;
-         float a1 = logf(xmax + sqrtf(xmax - 1.0f));
+         float a1 = f3b_log(xmax + sqrtf(xmax - 1.0f));
          float a2 = -acosf(tx / xmax);
          float ww = w / 11.57034632f, snv, csv;
          f3b_sincos(a1, &snv, &csv);
-         float snhu = sinhf(a2), cshu = coshf(a2);
+         float snhu = f3b_sinh(a2), cshu = f3b_cosh(a2);
          if (ty > 0.0f) snv = -snv;
          p0 += ww * cshu * csv;
          p1 += ww * snhu * snv;
@@ -410,20 +470,20 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          float ww = w / F3B_PI_2;
          b = b < 0.0f ? 0.0f : sqrtf(b);
          ssx = ssx < 0.0f ? 0.0f : sqrtf(ssx);
-         p0 += ww * atan2f(a, b);
-         if (ty > 0.0f) p1 += ww * logf(xmax + ssx);
-         else p1 -= ww * logf(xmax + ssx);
+         p0 += ww * f3b_atan2(a, b);
+         if (ty > 0.0f) p1 += ww * f3b_log(xmax + ssx);
+         else p1 -= ww * f3b_log(xmax + ssx);
       } break;
       case 63: { /* escher: p = {vc, vd} */
-         float lnr = 0.5f * logf(sumsq), s, c;
-         float m = w * expf(p[0] * lnr - p[1] * atan_yx);
+         float lnr = 0.5f * f3b_log(sumsq), s, c;
+         float m = w * f3b_exp(p[0] * lnr - p[1] * atan_yx);
          float n = p[0] * atan_yx + p[1] * lnr;
          f3b_sincos(n, &s, &c);
          p0 += m * c;
          p1 += m * s;
       } break;
       case 64: { /* foci */
-         float expx = expf(tx) * 0.5f;
+         float expx = f3b_exp(tx) * 0.5f;
          float expnx = 0.25f / expx, s, c;
          f3b_sincos(ty, &s, &c);
          float t = w / (expx + expnx - c);
@@ -435,7 +495,7 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          float y = ty + p[4];
          float r = sqrtf(x * x + y * y);
          if (r < w) {
-            float a = atan2f(y, x) + p[0] + p[2] * (w - r), s, c;
+            float a = f3b_atan2(y, x) + p[0] + p[2] * (w - r), s, c;
             f3b_sincos(a, &s, &c);
             r = w * r;
             p0 += r * c + p[3];
@@ -458,7 +518,7 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
       case 69: { /* oscilloscope: p = {2*pi*freq, amplitude, separation, damping} */
          float t;
          if (p[3] == 0.0f) t = p[1] * f3b_cos(p[0] * tx) + p[2];
-         else t = p[1] * expf(-fabsf(tx) * p[3]) * f3b_cos(p[0] * tx) + p[2];
+         else t = p[1] * f3b_exp(-fabsf(tx) * p[3]) * f3b_cos(p[0] * tx) + p[2];
          p0 += w * tx;
          if (fabsf(ty) <= t) p1 -= w * ty;
          else p1 += w * ty;
@@ -466,11 +526,11 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
       case 70: { /* polar2 */
          float p2v = w * F3B_1_PI;
          p0 += p2v * atan_xy;
-         p1 += p2v * 0.5f * logf(sumsq);
+         p1 += p2v * 0.5f * f3b_log(sumsq);
       } break;
       case 71: { /* popcorn2: p = {x, y, c} */
-         p0 += w * (tx + p[0] * f3b_sin(tanf(ty * p[2])));
-         p1 += w * (ty + p[1] * f3b_sin(tanf(tx * p[2])));
+         p0 += w * (tx + p[0] * f3b_sin(f3b_tan(ty * p[2])));
+         p1 += w * (ty + p[1] * f3b_sin(f3b_tan(tx * p[2])));
       } break;
       case 74: { /* split: p = {xsize*pi, ysize*pi} */
          if (f3b_cos(tx * p[0]) >= 0.0f) p1 += w * ty;
@@ -488,7 +548,7 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          p1 += r * s;
       } break;
       case 78: { /* wedge_julia: p = {cn, rN, power, count, cf, angle} */
-         float r = w * powf(sumsq, p[0]), s, c;
+         float r = w * f3b_pow(sumsq, p[0]), s, c;
          int t_rnd = (int)(p[1] * rng.u01());
          float a = (atan_yx + 2.0f * F3B_PI * (float)t_rnd) / p[2];
          float cc = floorf((p[3] * a + F3B_PI) * F3B_1_PI * 0.5f);
@@ -520,93 +580,93 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          p1 += w * (ty + p[3] * f3b_sin(tx * p[2]));
       } break;
       case 82: { /* exp */
-         float e = expf(tx), s, c;
+         float e = f3b_exp(tx), s, c;
          f3b_sincos(ty, &s, &c);
          p0 += w * e * c;
          p1 += w * e * s;
       } break;
       case 83: /* log */
-         p0 += w * 0.5f * logf(sumsq);
+         p0 += w * 0.5f * f3b_log(sumsq);
          p1 += w * atan_yx;
          break;
       case 84: { /* sin */
          float s, c;
          f3b_sincos(tx, &s, &c);
-         p0 += w * s * coshf(ty);
-         p1 += w * c * sinhf(ty);
+         p0 += w * s * f3b_cosh(ty);
+         p1 += w * c * f3b_sinh(ty);
       } break;
       case 85: { /* cos */
          float s, c;
          f3b_sincos(tx, &s, &c);
-         p0 += w * c * coshf(ty);
-         p1 -= w * s * sinhf(ty);
+         p0 += w * c * f3b_cosh(ty);
+         p1 -= w * s * f3b_sinh(ty);
       } break;
       case 86: { /* tan */
          float s, c;
          f3b_sincos(2.0f * tx, &s, &c);
-         float den = 1.0f / (c + coshf(2.0f * ty));
+         float den = 1.0f / (c + f3b_cosh(2.0f * ty));
          p0 += w * den * s;
-         p1 += w * den * sinhf(2.0f * ty);
+         p1 += w * den * f3b_sinh(2.0f * ty);
       } break;
       case 87: { /* sec */
          float s, c;
          f3b_sincos(tx, &s, &c);
-         float den = 2.0f / (f3b_cos(2.0f * tx) + coshf(2.0f * ty));
-         p0 += w * den * c * coshf(ty);
-         p1 += w * den * s * sinhf(ty);
+         float den = 2.0f / (f3b_cos(2.0f * tx) + f3b_cosh(2.0f * ty));
+         p0 += w * den * c * f3b_cosh(ty);
+         p1 += w * den * s * f3b_sinh(ty);
       } break;
       case 88: { /* csc */
          float s, c;
          f3b_sincos(tx, &s, &c);
-         float den = 2.0f / (coshf(2.0f * ty) - f3b_cos(2.0f * tx));
-         p0 += w * den * s * coshf(ty);
-         p1 -= w * den * c * sinhf(ty);
+         float den = 2.0f / (f3b_cosh(2.0f * ty) - f3b_cos(2.0f * tx));
+         p0 += w * den * s * f3b_cosh(ty);
+         p1 -= w * den * c * f3b_sinh(ty);
       } break;
       case 89: { /* cot */
          float s, c;
          f3b_sincos(2.0f * tx, &s, &c);
-         float den = 1.0f / (coshf(2.0f * ty) - c);
+         float den = 1.0f / (f3b_cosh(2.0f * ty) - c);
          p0 += w * den * s;
-         p1 -= w * den * sinhf(2.0f * ty);
+         p1 -= w * den * f3b_sinh(2.0f * ty);
       } break;
       case 90: { /* sinh */
          float s, c;
          f3b_sincos(ty, &s, &c);
-         p0 += w * sinhf(tx) * c;
-         p1 += w * coshf(tx) * s;
+         p0 += w * f3b_sinh(tx) * c;
+         p1 += w * f3b_cosh(tx) * s;
       } break;
       case 91: { /* cosh */
          float s, c;
          f3b_sincos(ty, &s, &c);
-         p0 += w * coshf(tx) * c;
-         p1 += w * sinhf(tx) * s;
+         p0 += w * f3b_cosh(tx) * c;
+         p1 += w * f3b_sinh(tx) * s;
       } break;
       case 92: { /* tanh */
          float s, c;
          f3b_sincos(2.0f * ty, &s, &c);
-         float den = 1.0f / (c + coshf(2.0f * tx));
-         p0 += w * den * sinhf(2.0f * tx);
+         float den = 1.0f / (c + f3b_cosh(2.0f * tx));
+         p0 += w * den * f3b_sinh(2.0f * tx);
          p1 += w * den * s;
       } break;
       case 93: { /* sech */
          float s, c;
          f3b_sincos(ty, &s, &c);
-         float den = 2.0f / (f3b_cos(2.0f * ty) + coshf(2.0f * tx));
-         p0 += w * den * c * coshf(tx);
-         p1 -= w * den * s * sinhf(tx);
+         float den = 2.0f / (f3b_cos(2.0f * ty) + f3b_cosh(2.0f * tx));
+         p0 += w * den * c * f3b_cosh(tx);
+         p1 -= w * den * s * f3b_sinh(tx);
       } break;
       case 94: { /* csch */
          float s, c;
          f3b_sincos(ty, &s, &c);
-         float den = 2.0f / (coshf(2.0f * tx) - f3b_cos(2.0f * ty));
-         p0 += w * den * sinhf(tx) * c;
-         p1 -= w * den * coshf(tx) * s;
+         float den = 2.0f / (f3b_cosh(2.0f * tx) - f3b_cos(2.0f * ty));
+         p0 += w * den * f3b_sinh(tx) * c;
+         p1 -= w * den * f3b_cosh(tx) * s;
       } break;
       case 95: { /* coth */
          float s, c;
          f3b_sincos(2.0f * ty, &s, &c);
-         float den = 1.0f / (coshf(2.0f * tx) - c);
-         p0 += w * den * sinhf(2.0f * tx);
+         float den = 1.0f / (f3b_cosh(2.0f * tx) - c);
+         p0 += w * den * f3b_sinh(2.0f * tx);
          p1 += w * den * s;
       } break;
       case 96: { /* auger: p = {sym, weight, freq, scale} */
@@ -620,7 +680,7 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
       case 97: { /* flux: p = {2 + spread} */
          float xpw = tx + w, xmw = tx - w;
          float avgr = w * p[0] * sqrtf(sqrtf(ty * ty + xpw * xpw) / sqrtf(ty * ty + xmw * xmw));
-         float avga = (atan2f(ty, xmw) - atan2f(ty, xpw)) * 0.5f, s, c;
+         float avga = (f3b_atan2(ty, xmw) - f3b_atan2(ty, xpw)) * 0.5f, s, c;
          f3b_sincos(avga, &s, &c);
          p0 += avgr * c;
          p1 += avgr * s;
@@ -652,12 +712,12 @@ __device__ __noinline__ void f3b_precalc(const float *sf, uint32_t xo, uint32_t 
       *rngp = rng;
    }
    if (flags & F3B_XF_NEED_SQRT) pt.rad = sqrtf(pt.tx * pt.tx + pt.ty * pt.ty);
-   if (flags & F3B_XF_ATAN_XY) pt.atan_xy = atan2f(pt.tx, pt.ty);
+   if (flags & F3B_XF_ATAN_XY) pt.atan_xy = f3b_atan2(pt.tx, pt.ty);
    if (flags & F3B_XF_ANGLES) {
       pt.sina = pt.tx / pt.rad;
       pt.cosa = pt.ty / pt.rad;
    }
-   if (flags & F3B_XF_ATAN_YX) pt.atan_yx = atan2f(pt.ty, pt.tx);
+   if (flags & F3B_XF_ATAN_YX) pt.atan_yx = f3b_atan2(pt.ty, pt.tx);
    *ptp = pt;
 }
 
