@@ -183,12 +183,19 @@ struct F3Pt {
    float tx, ty, sumsq, rad, atan_xy, atan_yx, sina, cosa;
 };
 
-/* The heavyweight variations. `p` points at the packed parameters in shared memory. */
-__device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p, F3Pt pt,
-                                            F3Rng *rngp) {
+/* variations of the out-of-line set that draw random numbers (bit i of word i/32) */
+__device__ __forceinline__ bool f3b_var_is_random(uint32_t id) {
+   const uint32_t m = id < 32u ? 0x80000000u : (id < 64u ? 0x093cb23fu : (id < 96u ? 0x00004000u : 0x00000000u));
+   return (m >> (id & 31u)) & 1u;
+}
+
+/* The heavyweight variations, out of line. `p` points at the packed parameters in shared
+ * memory. Two functions: the ones that draw random numbers carry the generator state in and
+ * out (through local memory, the price of an out-of-line call); the deterministic majority
+ * does not pay for that. */
+__device__ __noinline__ float2 f3b_var_slow_det(uint32_t id, float w, const float *p, F3Pt pt) {
    const float tx = pt.tx, ty = pt.ty, sumsq = pt.sumsq, rad = pt.rad;
    const float atan_xy = pt.atan_xy, atan_yx = pt.atan_yx, sina = pt.sina, cosa = pt.cosa;
-   F3Rng rng = *rngp;
    float p0 = 0.0f, p1 = 0.0f;
    switch (id) {
       case 17: { /* popcorn: p = {c20, c21} */
@@ -250,60 +257,6 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          p0 += r * s;
          p1 += r * c;
       } break;
-      case 31: { /* noise */
-         float s, c;
-         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &s, &c);
-         float r = w * rng.u01();
-         p0 += tx * r * c;
-         p1 += ty * r * s;
-      } break;
-      case 32: { /* julian: p = {power, cn, rN} */
-         float t_rnd = truncf(p[2] * rng.u01());
-         float a = (atan_yx + 2.0f * F3B_PI * t_rnd) / p[0], s, c;
-         float r = w * f3b_pow(sumsq, p[1]);
-         f3b_sincos(a, &s, &c);
-         p0 += r * c;
-         p1 += r * s;
-      } break;
-      case 33: { /* juliascope: p = {power, cn, rN} */
-         int t_rnd = (int)truncf(p[2] * rng.u01());
-         float a, s, c;
-         if ((t_rnd & 1) == 0) a = (2.0f * F3B_PI * (float)t_rnd + atan_yx) / p[0];
-         else a = (2.0f * F3B_PI * (float)t_rnd - atan_yx) / p[0];
-         f3b_sincos(a, &s, &c);
-         float r = w * f3b_pow(sumsq, p[1]);
-         p0 += r * c;
-         p1 += r * s;
-      } break;
-      case 34: { /* blur */
-         float s, c;
-         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &s, &c);
-         float r = w * rng.u01();
-         p0 += r * c;
-         p1 += r * s;
-      } break;
-      case 35: { /* gaussian_blur */
-         float s, c;
-         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &s, &c);
-         float r = w * f3b_gauss4(rng);
-         p0 += r * c;
-         p1 += r * s;
-      } break;
-      case 36: { /* radial_blur: p = {spinvar, zoomvar} */
-         float g = w * f3b_gauss4(rng), s, c;
-         f3b_sincos(atan_yx + p[0] * g, &s, &c);
-         float rz = p[1] * g - 1.0f;
-         p0 += rad * c + rz * tx;
-         p1 += rad * s + rz * ty;
-      } break;
-      case 37: { /* pie: p = {slices, rotation, thickness} */
-         int sl = (int)(rng.u01() * p[0] + 0.5f);
-         float a = p[1] + 2.0f * F3B_PI * ((float)sl + rng.u01() * p[2]) / p[0], s, c;
-         float r = w * rng.u01();
-         f3b_sincos(a, &s, &c);
-         p0 += r * c;
-         p1 += r * s;
-      } break;
       case 38: { /* ngon: p = {power/2, b=2pi/sides, corners, circle} */
          float r_factor = f3b_pow(sumsq, p[0]);
          float b = p[1];
@@ -314,42 +267,15 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          p0 += w * tx * amp;
          p1 += w * ty * amp;
       } break;
-      case 41: { /* arch (weight used non-linearly, as in the reference) */
-         float s, c;
-         f3b_sincos(rng.u01() * w * F3B_PI, &s, &c);
-         p0 += w * s;
-         p1 += w * (s * s) / c;
-      } break;
       case 42: /* tangent */
          p0 += w * f3b_sin(tx) / f3b_cos(ty);
          p1 += w * f3b_tan(ty);
          break;
-      case 44: { /* rays */
-         float ang = w * rng.u01() * F3B_PI;
-         float r = w / (sumsq + F3B_EPS);
-         float tanr = w * f3b_tan(ang) * r;
-         p0 += tanr * f3b_cos(tx);
-         p1 += tanr * f3b_sin(ty);
-      } break;
-      case 45: { /* blade */
-         float r = rng.u01() * w * rad, s, c;
-         f3b_sincos(r, &s, &c);
-         p0 += w * tx * (c + s);
-         p1 += w * tx * (c - s);
-      } break;
       case 46: { /* secant2 */
          float cr = f3b_cos(w * rad);
          float icr = 1.0f / cr;
          p0 += w * tx;
          p1 += (cr < 0.0f) ? w * (icr + 1.0f) : w * (icr - 1.0f);
-      } break;
-      case 47: { /* twintrian */
-         float r = rng.u01() * w * rad, s, c;
-         f3b_sincos(r, &s, &c);
-         float diff = log10f(s * s) + c;
-         if (f3b_bad(diff)) diff = -30.0f;
-         p0 += w * tx * diff;
-         p1 += w * tx * (diff - s * F3B_PI);
       } break;
       case 49: { /* disc2: p = {timespi, sinadd, cosadd} */
          float s, c;
@@ -357,35 +283,6 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          float r = w * atan_xy * F3B_1_PI;
          p0 += (s + p[2]) * r;
          p1 += (c + p[1]) * r;
-      } break;
-      case 50: { /* super_shape: p = {pm_4, n2, n3, rnd, holes, pneg1_n1} */
-         float st, ct;
-         f3b_sincos(p[0] * atan_yx + F3B_PI_4, &st, &ct);
-         float t1 = f3b_pow(fabsf(ct), p[1]);
-         float t2 = f3b_pow(fabsf(st), p[2]);
-         float r = w * ((p[3] * rng.u01() + (1.0f - p[3]) * rad) - p[4]) * f3b_pow(t1 + t2, p[5]) /
-                   rad;
-         p0 += r * tx;
-         p1 += r * ty;
-      } break;
-      case 51: { /* flower: p = {petals, holes} */
-         float r = w * (rng.u01() - p[1]) * f3b_cos(p[0] * atan_yx) / rad;
-         p0 += r * tx;
-         p1 += r * ty;
-      } break;
-      case 52: { /* conic: p = {eccentricity, holes} */
-         float ct = tx / rad;
-         float r = w * (rng.u01() - p[1]) * p[0] / (1.0f + p[0] * ct) / rad;
-         p0 += r * tx;
-         p1 += r * ty;
-      } break;
-      case 53: { /* parabola: p = {height, width} */
-         float s, c;
-         f3b_sincos(rad, &s, &c);
-         float a = rng.u01();
-         float b = rng.u01();
-         p0 += p[0] * w * s * s * a;
-         p1 += p[1] * w * c * b;
       } break;
       case 55: { /* bipolar: p = {ps = -pi/2 * shift} */
          float t = sumsq + 1.0f;
@@ -395,30 +292,6 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          else if (y < -F3B_PI_2) y = F3B_PI_2 - fmodf(F3B_PI_2 - y, F3B_PI);
          p0 += w * 0.25f * F3B_2_PI * f3b_log((t + x2) / (t - x2));
          p1 += w * F3B_2_PI * y;
-      } break;
-      case 56: { /* boarders */
-         float rx = rintf(tx), ry = rintf(ty);
-         float ox = tx - rx, oy = ty - ry;
-         if (rng.u01() >= 0.75f) {
-            p0 += w * (ox * 0.5f + rx);
-            p1 += w * (oy * 0.5f + ry);
-         } else if (fabsf(ox) >= fabsf(oy)) {
-            if (ox >= 0.0f) {
-               p0 += w * (ox * 0.5f + rx + 0.25f);
-               p1 += w * (oy * 0.5f + ry + 0.25f * oy / ox);
-            } else {
-               p0 += w * (ox * 0.5f + rx - 0.25f);
-               p1 += w * (oy * 0.5f + ry - 0.25f * oy / ox);
-            }
-         } else {
-            if (oy >= 0.0f) {
-               p1 += w * (oy * 0.5f + ry + 0.25f);
-               p0 += w * (ox * 0.5f + rx + ox / oy * 0.25f);
-            } else {
-               p1 += w * (oy * 0.5f + ry - 0.25f);
-               p0 += w * (ox * 0.5f + rx - ox / oy * 0.25f);
-            }
-         }
       } break;
       case 58: { /* cell: p = {size, 1/size} */
          int x = (int)floorf(tx * p[1]);
@@ -434,14 +307,6 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          }
          p0 += w * (dx + (float)x * p[0]);
          p1 -= w * (dy + (float)y * p[0]);
-      } break;
-      case 59: { /* cpow: p = {va, vc, vd, power} */
-         float lnr = 0.5f * f3b_log(sumsq), s, c;
-         float ang = p[1] * atan_yx + p[2] * lnr + p[0] * floorf(p[3] * rng.u01());
-         float m = w * f3b_exp(p[1] * lnr - p[2] * atan_yx);
-         f3b_sincos(ang, &s, &c);
-         p0 += m * c;
-         p1 += m * s;
       } break;
       case 60: { /* curve: p = {xamp, yamp, 1/xlen^2, 1/ylen^2} */
          p0 += w * (tx + p[0] * f3b_exp(-ty * ty * p[2]));
@@ -544,16 +409,6 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          a = a * p[4] + cc * p[0];
          f3b_sincos(a, &s, &c);
          float r = w * (rad + p[1]);
-         p0 += r * c;
-         p1 += r * s;
-      } break;
-      case 78: { /* wedge_julia: p = {cn, rN, power, count, cf, angle} */
-         float r = w * f3b_pow(sumsq, p[0]), s, c;
-         int t_rnd = (int)(p[1] * rng.u01());
-         float a = (atan_yx + 2.0f * F3B_PI * (float)t_rnd) / p[2];
-         float cc = floorf((p[3] * a + F3B_PI) * F3B_1_PI * 0.5f);
-         a = a * p[4] + cc * p[5];
-         f3b_sincos(a, &s, &c);
          p0 += r * c;
          p1 += r * s;
       } break;
@@ -684,6 +539,172 @@ __device__ __noinline__ float2 f3b_var_slow(uint32_t id, float w, const float *p
          f3b_sincos(avga, &s, &c);
          p0 += avgr * c;
          p1 += avgr * s;
+      } break;
+   default:
+      break;
+   }
+   return make_float2(p0, p1);
+}
+
+__device__ __noinline__ float2 f3b_var_slow_rnd(uint32_t id, float w, const float *p, F3Pt pt,
+                                            F3Rng *rngp) {
+   const float tx = pt.tx, ty = pt.ty, sumsq = pt.sumsq, rad = pt.rad;
+   const float atan_xy = pt.atan_xy, atan_yx = pt.atan_yx, sina = pt.sina, cosa = pt.cosa;
+   (void)atan_xy, (void)sina, (void)cosa; /* not every set of cases uses all of them */
+   F3Rng rng = *rngp;
+   float p0 = 0.0f, p1 = 0.0f;
+   switch (id) {
+      case 31: { /* noise */
+         float s, c;
+         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &s, &c);
+         float r = w * rng.u01();
+         p0 += tx * r * c;
+         p1 += ty * r * s;
+      } break;
+      case 32: { /* julian: p = {power, cn, rN} */
+         float t_rnd = truncf(p[2] * rng.u01());
+         float a = (atan_yx + 2.0f * F3B_PI * t_rnd) / p[0], s, c;
+         float r = w * f3b_pow(sumsq, p[1]);
+         f3b_sincos(a, &s, &c);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 33: { /* juliascope: p = {power, cn, rN} */
+         int t_rnd = (int)truncf(p[2] * rng.u01());
+         float a, s, c;
+         if ((t_rnd & 1) == 0) a = (2.0f * F3B_PI * (float)t_rnd + atan_yx) / p[0];
+         else a = (2.0f * F3B_PI * (float)t_rnd - atan_yx) / p[0];
+         f3b_sincos(a, &s, &c);
+         float r = w * f3b_pow(sumsq, p[1]);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 34: { /* blur */
+         float s, c;
+         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &s, &c);
+         float r = w * rng.u01();
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 35: { /* gaussian_blur */
+         float s, c;
+         f3b_sincos(rng.u01() * 2.0f * F3B_PI, &s, &c);
+         float r = w * f3b_gauss4(rng);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 36: { /* radial_blur: p = {spinvar, zoomvar} */
+         float g = w * f3b_gauss4(rng), s, c;
+         f3b_sincos(atan_yx + p[0] * g, &s, &c);
+         float rz = p[1] * g - 1.0f;
+         p0 += rad * c + rz * tx;
+         p1 += rad * s + rz * ty;
+      } break;
+      case 37: { /* pie: p = {slices, rotation, thickness} */
+         int sl = (int)(rng.u01() * p[0] + 0.5f);
+         float a = p[1] + 2.0f * F3B_PI * ((float)sl + rng.u01() * p[2]) / p[0], s, c;
+         float r = w * rng.u01();
+         f3b_sincos(a, &s, &c);
+         p0 += r * c;
+         p1 += r * s;
+      } break;
+      case 41: { /* arch (weight used non-linearly, as in the reference) */
+         float s, c;
+         f3b_sincos(rng.u01() * w * F3B_PI, &s, &c);
+         p0 += w * s;
+         p1 += w * (s * s) / c;
+      } break;
+      case 44: { /* rays */
+         float ang = w * rng.u01() * F3B_PI;
+         float r = w / (sumsq + F3B_EPS);
+         float tanr = w * f3b_tan(ang) * r;
+         p0 += tanr * f3b_cos(tx);
+         p1 += tanr * f3b_sin(ty);
+      } break;
+      case 45: { /* blade */
+         float r = rng.u01() * w * rad, s, c;
+         f3b_sincos(r, &s, &c);
+         p0 += w * tx * (c + s);
+         p1 += w * tx * (c - s);
+      } break;
+      case 47: { /* twintrian */
+         float r = rng.u01() * w * rad, s, c;
+         f3b_sincos(r, &s, &c);
+         float diff = log10f(s * s) + c;
+         if (f3b_bad(diff)) diff = -30.0f;
+         p0 += w * tx * diff;
+         p1 += w * tx * (diff - s * F3B_PI);
+      } break;
+      case 50: { /* super_shape: p = {pm_4, n2, n3, rnd, holes, pneg1_n1} */
+         float st, ct;
+         f3b_sincos(p[0] * atan_yx + F3B_PI_4, &st, &ct);
+         float t1 = f3b_pow(fabsf(ct), p[1]);
+         float t2 = f3b_pow(fabsf(st), p[2]);
+         float r = w * ((p[3] * rng.u01() + (1.0f - p[3]) * rad) - p[4]) * f3b_pow(t1 + t2, p[5]) /
+                   rad;
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 51: { /* flower: p = {petals, holes} */
+         float r = w * (rng.u01() - p[1]) * f3b_cos(p[0] * atan_yx) / rad;
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 52: { /* conic: p = {eccentricity, holes} */
+         float ct = tx / rad;
+         float r = w * (rng.u01() - p[1]) * p[0] / (1.0f + p[0] * ct) / rad;
+         p0 += r * tx;
+         p1 += r * ty;
+      } break;
+      case 53: { /* parabola: p = {height, width} */
+         float s, c;
+         f3b_sincos(rad, &s, &c);
+         float a = rng.u01();
+         float b = rng.u01();
+         p0 += p[0] * w * s * s * a;
+         p1 += p[1] * w * c * b;
+      } break;
+      case 56: { /* boarders */
+         float rx = rintf(tx), ry = rintf(ty);
+         float ox = tx - rx, oy = ty - ry;
+         if (rng.u01() >= 0.75f) {
+            p0 += w * (ox * 0.5f + rx);
+            p1 += w * (oy * 0.5f + ry);
+         } else if (fabsf(ox) >= fabsf(oy)) {
+            if (ox >= 0.0f) {
+               p0 += w * (ox * 0.5f + rx + 0.25f);
+               p1 += w * (oy * 0.5f + ry + 0.25f * oy / ox);
+            } else {
+               p0 += w * (ox * 0.5f + rx - 0.25f);
+               p1 += w * (oy * 0.5f + ry - 0.25f * oy / ox);
+            }
+         } else {
+            if (oy >= 0.0f) {
+               p1 += w * (oy * 0.5f + ry + 0.25f);
+               p0 += w * (ox * 0.5f + rx + ox / oy * 0.25f);
+            } else {
+               p1 += w * (oy * 0.5f + ry - 0.25f);
+               p0 += w * (ox * 0.5f + rx - ox / oy * 0.25f);
+            }
+         }
+      } break;
+      case 59: { /* cpow: p = {va, vc, vd, power} */
+         float lnr = 0.5f * f3b_log(sumsq), s, c;
+         float ang = p[1] * atan_yx + p[2] * lnr + p[0] * floorf(p[3] * rng.u01());
+         float m = w * f3b_exp(p[1] * lnr - p[2] * atan_yx);
+         f3b_sincos(ang, &s, &c);
+         p0 += m * c;
+         p1 += m * s;
+      } break;
+      case 78: { /* wedge_julia: p = {cn, rN, power, count, cf, angle} */
+         float r = w * f3b_pow(sumsq, p[0]), s, c;
+         int t_rnd = (int)(p[1] * rng.u01());
+         float a = (atan_yx + 2.0f * F3B_PI * (float)t_rnd) / p[2];
+         float cc = floorf((p[3] * a + F3B_PI) * F3B_1_PI * 0.5f);
+         a = a * p[4] + cc * p[5];
+         f3b_sincos(a, &s, &c);
+         p0 += r * c;
+         p1 += r * s;
       } break;
    default:
       break;
@@ -982,9 +1003,13 @@ __device__ __noinline__ float2 f3b_apply_varlist(const float *sf, uint32_t vi, u
          p1 += rv * (im_u * re_v - re_u * im_v);
       } break;
       default: {
-         F3Rng tmp = rng; /* only this copy has its address taken */
-         const float2 d = f3b_var_slow(id, w, p, pt, &tmp);
-         rng = tmp;
+         float2 d;
+         if (f3b_var_is_random(id)) {
+            F3Rng tmp = rng; /* only this copy has its address taken */
+            d = f3b_var_slow_rnd(id, w, p, pt, &tmp);
+            rng = tmp;
+         } else
+            d = f3b_var_slow_det(id, w, p, pt);
          p0 += d.x;
          p1 += d.y;
       } break;
