@@ -142,13 +142,13 @@ int f3b_ctx_create(int device, f3b_ctx **out) {
    }
    ctx->sms = prop.multiProcessorCount;
    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-       cudaMalloc(&ctx->d_badvals, sizeof(unsigned long long)) != cudaSuccess) {
+       cudaMalloc(&ctx->d_badvals, 4 * sizeof(unsigned long long)) != cudaSuccess) {
       fprintf(stderr, "flam3_b200: context setup failed: %s\n",
               cudaGetErrorString(cudaGetLastError()));
       delete ctx;
       return 1;
    }
-   cudaMemsetAsync(ctx->d_badvals, 0, sizeof(unsigned long long), ctx->stream);
+   cudaMemsetAsync(ctx->d_badvals, 0, 4 * sizeof(unsigned long long), ctx->stream);
    ctx->iter_blocks_per_sm = f3b_iterate_max_blocks_per_sm(16 * 1024);
    if (ctx->iter_blocks_per_sm <= 0) ctx->iter_blocks_per_sm = 1;
    *out = ctx;
@@ -241,7 +241,7 @@ int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel) {
    ctx->width = width;
    ctx->height = height;
    ctx->count_channel = count_channel ? 1 : 0;
-   CK(cudaMemsetAsync(ctx->d_badvals, 0, sizeof(unsigned long long), ctx->stream));
+   CK(cudaMemsetAsync(ctx->d_badvals, 0, 4 * sizeof(unsigned long long), ctx->stream));
    if (f3b_hist_clear(ctx)) return 1;
    return f3b_accum_clear(ctx);
 }
@@ -397,6 +397,9 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    std::vector<F3ConstSample> consts((size_t)(n_jobs < cap ? n_jobs : cap));
    int launches = 0;
    if (stage_begin(ctx, F3B_STAGE_ITERATE)) return 1;
+   P.probe_iters = 0;
+   P.probe_counts = ctx->d_badvals + 1; /* [1] lanes adding, [2] lanes sharing a bucket, [3] scratch */
+   bool aggregate = false;
    /* several launches (more temporal samples than fit the parameter space) are independent:
     * they go to side streams so that their CTAs can be resident together */
    const bool fork = n_jobs > cap;
@@ -458,8 +461,38 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       int grid = ctx->sms * bps;
       if ((uint32_t)grid > local_groups) grid = (int)local_groups;
       cudaStream_t st = fork ? ctx->side[chunk % F3B_SIDE_STREAMS] : ctx->stream;
+      if (chunk == 0) {
+         /* Does the attractor collapse onto a few buckets? Then the adds must be aggregated
+          * across the warp, or they serialise on a handful of L2 addresses. A spread-out flame
+          * pays ~5% for the aggregation check, so it is decided by measurement: the first
+          * 64 iterations of one group per SM run once without adding anything and count how
+          * many lanes share their bucket with another lane (~0.1 ms; frames too small to
+          * care are not probed). F3B_AGG=0/1 overrides. */
+         const char *e = getenv("F3B_AGG");
+         uint64_t total_iters = 0;
+         for (int j = 0; j < n_jobs; j++) total_iters += jobs[j].n_iters;
+         if (e) aggregate = atoi(e) != 0;
+         else if (total_iters / (uint64_t)nranks >= 50000000ull) {
+            F3IterateParams Q = P;
+            Q.probe_iters = 64;
+            Q.badvals = ctx->d_badvals + 3;
+            int pgrid = ctx->sms < grid ? ctx->sms : grid;
+            const uint64_t lim = (uint64_t)P.group_begin + (uint64_t)pgrid * (uint64_t)nranks;
+            if (lim < Q.n_groups) Q.n_groups = (uint32_t)lim;
+            /* the counters were zeroed by f3b_frame_begin / the previous probe's read-back */
+            if (!f3b_launch_iterate(Q, consts.data(), j1 - j0, ctx->count_channel != 0, simple, true, pgrid,
+                                    group_size, max_blob, ctx->stream))
+               return fail(ctx, "probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            launches++;
+            unsigned long long pc[2] = {0, 0};
+            CK(cudaMemcpyAsync(pc, ctx->d_badvals + 1, sizeof(pc), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            aggregate = pc[0] > 0 && pc[1] * 8 >= pc[0];
+            CK(cudaMemsetAsync(ctx->d_badvals + 1, 0, 3 * sizeof(unsigned long long), ctx->stream));
+         }
+      }
       const int nl = f3b_launch_iterate(P, consts.data(), j1 - j0, ctx->count_channel != 0, simple,
-                                        grid, group_size, max_blob, st);
+                                        aggregate, grid, group_size, max_blob, st);
       if (!nl) return fail(ctx, "chaos-game launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       launches += nl;
    }

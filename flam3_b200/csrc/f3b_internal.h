@@ -70,14 +70,19 @@ struct F3IterateParams {
    int floor_adds;               /* bits 32/33: add floor(value) like the integer buckets */
    uint64_t seed;
    unsigned long long *badvals;  /* device counter */
+   /* probe launch (AGG kernels only): every chain stores at most probe_iters iterations,
+    * nothing is added to the histogram, probe_counts[0] += lanes that reached an add,
+    * probe_counts[1] += those that shared their bucket with another lane of the warp */
+   uint32_t probe_iters;
+   unsigned long long *probe_counts;
    F3ConstSample samp[F3B_PARAM_SAMPLES]; /* parameter-space home of the per-sample constants */
 };
 
 /* returns the number of kernel launches made (0 on error; see cudaGetLastError). `consts`
  * holds the constants of jobs [p.job_base, p.job_base + n_consts), n_consts <= capacity */
 int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_consts,
-                       bool count_channel, bool simple, int grid_blocks, int group_size,
-                       size_t smem_bytes, cudaStream_t stream);
+                       bool count_channel, bool simple, bool aggregate, int grid_blocks,
+                       int group_size, size_t smem_bytes, cudaStream_t stream);
 int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes);
 int f3b_iterate_const_capacity(void);
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes);

@@ -42,6 +42,52 @@ __device__ __forceinline__ void f3b_red_f32(float *addr, float v) {
    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
+/* Warp-level aggregation of bucket adds, for attractors that collapse onto a few buckets:
+ * reductions to ONE address serialise in L2 (~2e9/s for the whole GPU), so a genome whose
+ * orbit sits on a fixed point or a short cycle ran 50x slower than a spread-out one
+ * (profiles/r01_c5_*: var76 267 -> 39 ms, var47 118 -> 22 ms, var58 175 -> 35 ms). In the AGG
+ * instantiations of the kernel the lanes that are about to add compare their buckets
+ * (match.any); lanes with the same bucket sum their colours through shuffles and the lowest
+ * one issues the reduction. The sums are of integer-valued floats, so they stay exact.
+ * Returns false for a lane whose add was folded into another lane's. The check costs ~5 % on
+ * a spread-out flame, so the host only launches the AGG kernels when a short probe launch of
+ * the same kernel (probe_counts != NULL: count, add nothing) found the lanes colliding.
+ * Every warp-synchronous operation below is executed by exactly the lanes named in its mask:
+ * match and ballot by all lanes that entered together (`act`), the shuffles by the lanes of
+ * one `peers` set, which all see the same set and so run the same number of rounds. */
+__device__ __noinline__ bool f3b_bump_aggregate(unsigned long long bidx, float4 *colp, float *cntp,
+                                                unsigned long long *probe_counts) {
+   const unsigned act = __activemask();
+   const unsigned lane = threadIdx.x & 31u;
+   const unsigned peers = __match_any_sync(act, bidx);
+   const bool dup = (peers & (peers - 1u)) != 0u;
+   const unsigned nd = __popc(__ballot_sync(act, dup));
+   if (probe_counts) { /* probe launch: measure, add nothing */
+      if ((int)lane == __ffs(act) - 1) {
+         atomicAdd(probe_counts, (unsigned long long)__popc(act));
+         atomicAdd(probe_counts + 1, (unsigned long long)nd);
+      }
+      return false;
+   }
+   if (!dup) return true;
+   const int leader = __ffs(peers) - 1;
+   const float4 a = *colp;
+   const float c = *cntp;
+   float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f, sc = 0.f;
+   for (unsigned rest = peers & ~(1u << leader); rest; rest &= rest - 1u) {
+      const int src = __ffs(rest) - 1;
+      sx += __shfl_sync(peers, a.x, src);
+      sy += __shfl_sync(peers, a.y, src);
+      sz += __shfl_sync(peers, a.z, src);
+      sw += __shfl_sync(peers, a.w, src);
+      sc += __shfl_sync(peers, c, src);
+   }
+   if ((int)lane != leader) return false;
+   *colp = make_float4(a.x + sx, a.y + sy, a.z + sz, a.w + sw);
+   *cntp = c + sc;
+   return true;
+}
+
 /* The final xform (flam3.c:280-287) is applied out of line: few genomes have one, and a
  * second inlined copy of the variation interpreter would double the hot loop's code. */
 __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, float px, float py,
@@ -72,7 +118,7 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
 /* SIMPLE: every temporal sample of the launch has <= 4 xforms, no xaos, no final xform, a
  * step palette and fully visible xforms (the classic flame): the flag tests fold away and
  * the xform pick is three compares on a packed table from the constant bank. */
-template <bool COUNT, bool SIMPLE>
+template <bool COUNT, bool SIMPLE, bool AGG>
 __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
    extern __shared__ __align__(16) uint32_t smem[];
    const float *sf = reinterpret_cast<const float *>(smem);
@@ -108,8 +154,9 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
       /* stored iterations of this chain */
       const uint64_t base = job.n_iters / job.n_chains;
       const uint32_t rem = (uint32_t)(job.n_iters % job.n_chains);
-      const int n_store = (int)(base + (chain < rem ? 1u : 0u));
+      int n_store = (int)(base + (chain < rem ? 1u : 0u));
       if (n_store == 0) continue;
+      if (AGG && P.probe_iters && n_store > (int)P.probe_iters) n_store = (int)P.probe_iters;
 
       /* Flags, chooser stride and palette size share one register (made opaque, or the
        * compiler splits it into a register per flag and spills them); the blob offsets are
@@ -222,8 +269,18 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
             /* step lookup, every xform fully visible, dmap truncated on the host */
             pi = pi < 0 ? 0 : (pi >= cmap_size - 1 ? cmap_size - 1 : pi);
             col = dmap[pi];
+            float cnt = 255.0f;
+            if (AGG) {
+               float4 tc = col;
+               float tn = cnt;
+               const bool mine = f3b_bump_aggregate((unsigned long long)bidx, &tc, &tn,
+                                                    P.probe_iters ? P.probe_counts : nullptr);
+               if (!mine) continue;
+               col = tc;
+               cnt = tn;
+            }
             f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
-            if (COUNT) f3b_red_f32(P.hist_count + bidx, 255.0f);
+            if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
             continue;
          }
          if (hf & HF_PAL_LINEAR) {
@@ -259,6 +316,15 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
             col.z = floorf(col.z);
             col.w = floorf(col.w);
             cnt = floorf(cnt);
+         }
+         if (AGG) {
+            float4 tc = col;
+            float tn = cnt;
+            const bool mine = f3b_bump_aggregate((unsigned long long)bidx, &tc, &tn,
+                                                 P.probe_iters ? P.probe_counts : nullptr);
+            if (!mine) continue;
+            col = tc;
+            cnt = tn;
          }
          f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
          if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
@@ -311,33 +377,40 @@ int f3b_iterate_max_blocks_per_sm(size_t smem_bytes) {
 
 int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes) {
    int nb = 0;
-   cudaFuncSetAttribute(f3b_iterate_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                        (int)(F3B_MAX_BLOB_WORDS * 4));
-   cudaFuncSetAttribute(f3b_iterate_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                        (int)(F3B_MAX_BLOB_WORDS * 4));
-   cudaFuncSetAttribute(f3b_iterate_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                        (int)(F3B_MAX_BLOB_WORDS * 4));
-   cudaFuncSetAttribute(f3b_iterate_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                        (int)(F3B_MAX_BLOB_WORDS * 4));
-   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false>, group_size,
+   const int smax = (int)(F3B_MAX_BLOB_WORDS * 4);
+   const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+   cudaFuncSetAttribute(f3b_iterate_kernel<true, false, false>, at, smax);
+   cudaFuncSetAttribute(f3b_iterate_kernel<false, false, false>, at, smax);
+   cudaFuncSetAttribute(f3b_iterate_kernel<true, true, false>, at, smax);
+   cudaFuncSetAttribute(f3b_iterate_kernel<false, true, false>, at, smax);
+   cudaFuncSetAttribute(f3b_iterate_kernel<true, false, true>, at, smax);
+   cudaFuncSetAttribute(f3b_iterate_kernel<false, false, true>, at, smax);
+   cudaFuncSetAttribute(f3b_iterate_kernel<true, true, true>, at, smax);
+   cudaFuncSetAttribute(f3b_iterate_kernel<false, true, true>, at, smax);
+   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, true>, group_size,
                                                      smem_bytes) != cudaSuccess)
       return 0;
    return nb;
 }
 
 int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_consts,
-                       bool count_channel, bool simple, int grid_blocks, int group_size,
-                       size_t smem_bytes, cudaStream_t stream) {
+                       bool count_channel, bool simple, bool aggregate, int grid_blocks,
+                       int group_size, size_t smem_bytes, cudaStream_t stream) {
    if (grid_blocks <= 0 || n_consts <= 0 || n_consts > F3B_PARAM_SAMPLES) return 0;
    if (group_size < 32 || group_size > F3B_BLOCK || (group_size & 31)) return 0;
    for (int i = 0; i < n_consts; i++) p.samp[i] = consts[i];
-   if (count_channel && simple)
-      f3b_iterate_kernel<true, true><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
-   else if (count_channel)
-      f3b_iterate_kernel<true, false><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
-   else if (simple)
-      f3b_iterate_kernel<false, true><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
-   else
-      f3b_iterate_kernel<false, false><<<grid_blocks, group_size, smem_bytes, stream>>>(p);
+#define F3B_LAUNCH(C, S, A) f3b_iterate_kernel<C, S, A><<<grid_blocks, group_size, smem_bytes, stream>>>(p)
+   const int which = (count_channel ? 4 : 0) | (simple ? 2 : 0) | (aggregate ? 1 : 0);
+   switch (which) {
+   case 0: F3B_LAUNCH(false, false, false); break;
+   case 1: F3B_LAUNCH(false, false, true); break;
+   case 2: F3B_LAUNCH(false, true, false); break;
+   case 3: F3B_LAUNCH(false, true, true); break;
+   case 4: F3B_LAUNCH(true, false, false); break;
+   case 5: F3B_LAUNCH(true, false, true); break;
+   case 6: F3B_LAUNCH(true, true, false); break;
+   default: F3B_LAUNCH(true, true, true); break;
+   }
+#undef F3B_LAUNCH
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
 }
