@@ -261,3 +261,32 @@ def test_full_size_c2_statistics_match_the_reference(flame0):
         a = img[:1072, :1920].astype(np.float64)
         return a.reshape(67, 16, 120, 16, 3).mean(axis=(1, 3))
     assert psnr(blocks(g_img), blocks(r_img)) > 36.0, psnr(blocks(g_img), blocks(r_img))
+
+
+def test_chain_plan_follows_the_reference_rule():
+    """f3b_plan_chains: never fewer chains than the reference's nthreads * ceil(n / nthreads /
+    sub_batch_size) sub-batches (rect.c:840 + 279-284), never more than 2.5x as many (chain
+    length is observable), whole rounds of the resident threads when there are more chains
+    than threads, and flam3-animate's small temporal samples exactly as on the CPU."""
+    ref, gpu, core = libs()
+    ctx = gpu.render_context(core)
+    info = ctx.device_info()
+    resident = info["sms"] * info["blocks_per_sm"] * info["threads"]
+    plan = lambda n, sbs, jobs, workers: core._dll.f3b_plan_chains(ctx.ptr, int(n), sbs, jobs, workers)
+
+    def reference(n, sbs, workers):
+        per = -(-n // workers)
+        return workers * (-(-per // sbs))
+
+    for n, sbs, jobs, workers in [(3_072_000, 10000, 1, 1), (3_072_000, 10000, 1, 16), (3072, 10000, 1000, 16),
+                                  (3072, 10000, 1000, 1), (4_147_200_000, 10000, 1, 1), (4_147_200_000, 10000, 1, 16),
+                                  (1_036_800_000, 10000, 1, 1), (41_472_000_000, 10000, 1, 8),
+                                  (819_200, 100, 1, 1), (50, 10000, 1, 4)]:
+        got, want = plan(n, sbs, jobs, workers), min(reference(n, sbs, workers), n)
+        assert want <= got <= max(2.5 * want, want + 1), (n, sbs, jobs, workers, got, want)
+        if jobs == 1 and got > resident:
+            assert got % resident == 0, (got, resident)
+    # an animation sample: 16 chains of 192, as with 16 CPU threads
+    assert plan(3072, 10000, 1000, 16) == 16
+    # the headline frame: planned for a node's worth of threads, whatever the number of GPUs
+    assert plan(4_147_200_000, 10000, 1, 1) == 8 * resident
