@@ -460,8 +460,6 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       t_pack += now_ms() - t0;
       t0 = now_ms();
       for (int ts = 0; ts < ntemporal_samples; ts++) {
-         const int fi = batch_num * ntemporal_samples + ts;
-         const double color_scalar = temporal_filter[fi];
          const packed_sample *ps = &packed.s[ts];
          const size_t used = ps->used;
          if (ps->rc == 3) goto done; /* camera error, message already printed */
@@ -515,7 +513,6 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
                   for (int k = 0; k < 3; k++) last_dmap[j][k] = pal[j * 4 + k];
             }
          }
-         (void)color_scalar;
       }
 
       if (poll_progress(spec, 100.0 * batch_num / nbatches, 0)) {
