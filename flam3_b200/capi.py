@@ -271,7 +271,7 @@ class DeFilters(C.Structure):
 CORE_SYMBOLS = [
     "f3b_abi_version", "f3b_ctx_create", "f3b_ctx_destroy", "f3b_last_error", "f3b_device_info",
     "f3b_sync", "f3b_frame_begin", "f3b_hist_clear", "f3b_accum_clear", "f3b_plan_chains",
-    "f3b_iterate", "f3b_badvals", "f3b_density", "f3b_density_rows", "f3b_finish",
+    "f3b_iterate", "f3b_pinned_alloc", "f3b_pinned_free", "f3b_inputs_consumed", "f3b_badvals", "f3b_density", "f3b_density_rows", "f3b_finish",
     "f3b_finish_device", "f3b_finish_device_rows", "f3b_image_download", "f3b_hist_upload_u32", "f3b_hist_download_u32", "f3b_accum_upload",
     "f3b_accum_download", "f3b_hist_color_ptr", "f3b_hist_count_ptr", "f3b_hist_elems", "f3b_accum_ptr",
     "f3b_stream_ptr", "f3b_stage_stats", "f3b_stats_reset", "f3b_xfer_stats", "f3b_timer_start",

@@ -41,6 +41,8 @@ struct f3b_ctx {
    bool accum_zero_pending = false; /* accumulators are logically zero, memset not yet issued */
    unsigned long long *d_badvals = nullptr;
    cudaStream_t side[F3B_SIDE_STREAMS] = {nullptr, nullptr, nullptr};
+   cudaEvent_t inputs_ev = nullptr; /* the last f3b_iterate's uploads have left the host buffers */
+   bool inputs_pending = false;
    cudaEvent_t fork_ev = nullptr, join_ev[F3B_SIDE_STREAMS] = {nullptr, nullptr, nullptr};
 
    /* instrumentation */
@@ -174,6 +176,7 @@ void f3b_ctx_destroy(f3b_ctx *ctx) {
       if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
    }
    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+   if (ctx->inputs_ev) cudaEventDestroy(ctx->inputs_ev);
    if (ctx->timer0) cudaEventDestroy(ctx->timer0);
    if (ctx->timer1) cudaEventDestroy(ctx->timer1);
    if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -314,6 +317,25 @@ uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len,
    return (uint32_t)chains;
 }
 
+void *f3b_pinned_alloc(size_t bytes) {
+   void *p = nullptr;
+   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+   }
+   return p;
+}
+void f3b_pinned_free(void *p) {
+   if (p) cudaFreeHost(p);
+}
+int f3b_inputs_consumed(f3b_ctx *ctx) {
+   if (!ctx || !ctx->inputs_pending) return 0;
+   CK(cudaSetDevice(ctx->device));
+   CK(cudaEventSynchronize(ctx->inputs_ev));
+   ctx->inputs_pending = false;
+   return 0;
+}
+
 int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *jobs, int n_jobs,
                 uint64_t seed, int floor_adds, uint32_t max_chain_len, int rank, int nranks) {
    if (!ctx || !blobs || !jobs || n_jobs <= 0) return fail(ctx, "f3b_iterate: bad arguments");
@@ -368,9 +390,18 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    CK(cudaMemcpyAsync(ctx->groups.p, group_job.data(), sizeof(uint32_t) * (size_t)n_groups,
                       cudaMemcpyHostToDevice, ctx->stream));
    ctx->h2d_bytes += blob_bytes + sizeof(f3b_job) * (size_t)n_jobs + sizeof(uint32_t) * (size_t)n_groups;
-   /* the three host buffers above are pageable: the async copies have staged them before
-    * returning, but keep it simple and make that explicit */
-   CK(cudaStreamSynchronize(ctx->stream));
+   {
+      /* jobs and groups are small and pageable: their copies are staged before the call
+       * returns. A page-locked blob buffer is read by DMA later: mark when it is free again;
+       * a pageable one is waited for here. */
+      cudaPointerAttributes pa;
+      const bool pinned = cudaPointerGetAttributes(&pa, blobs) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+      cudaGetLastError(); /* unregistered pageable memory may report an error on old drivers */
+      if (!ctx->inputs_ev) CK(cudaEventCreateWithFlags(&ctx->inputs_ev, cudaEventDisableTiming));
+      CK(cudaEventRecord(ctx->inputs_ev, ctx->stream));
+      ctx->inputs_pending = true;
+      if (!pinned && f3b_inputs_consumed(ctx)) return 1;
+   }
 
    F3IterateParams P;
    P.blobs = (const uint8_t *)ctx->blobs.p;

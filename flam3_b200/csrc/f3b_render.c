@@ -162,12 +162,21 @@ typedef struct {
    size_t cap, used; /* in words */
 } blob_buf;
 
+/* The buffer the packed samples of a batch are assembled in lives across frames (under
+ * g_lock) and is page-locked: fresh pageable memory costs a page fault per 4 KB and a
+ * staging copy per upload, which for an animation frame (1000 samples, 4.6 MB) was a
+ * quarter of the host time. f3b_iterate's upload from it is asynchronous, so
+ * f3b_inputs_consumed must be awaited before the buffer is written again. */
+static blob_buf g_blobs = {NULL, 0, 0};
+
 static int blob_reserve(blob_buf *b, size_t extra) {
    if (b->used + extra <= b->cap) return 0;
-   size_t ncap = b->cap ? b->cap * 2 : 1u << 16;
+   size_t ncap = b->cap ? b->cap * 2 : 1u << 18;
    while (ncap < b->used + extra) ncap *= 2;
-   uint32_t *n = (uint32_t *)realloc(b->words, ncap * 4);
+   uint32_t *n = (uint32_t *)f3b_pinned_alloc(ncap * 4);
    if (!n) return 1;
+   if (b->used) memcpy(n, b->words, b->used * 4);
+   f3b_pinned_free(b->words);
    b->words = n;
    b->cap = ncap;
    return 0;
@@ -177,7 +186,8 @@ static int blob_reserve(blob_buf *b, size_t extra) {
 typedef struct {
    int rc, alpha_ok; /* rc: 0 ok, 1 genome error, 2 too large, 3 camera error */
    size_t used;      /* words */
-   uint32_t *words;  /* malloc'd packed sample */
+   uint32_t *words;  /* the packed sample: in its slot of the batch buffer, or malloc'd */
+   int owned;        /* words was malloc'd (the sample did not fit its slot) */
    f3b_camera cam;
    double vibrancy, gamma, background[3];
    double contrast, brightness, estimator_curve, gam_lin_thresh;
@@ -186,6 +196,7 @@ typedef struct {
 typedef struct {
    packed_sample *s;
    int n;
+   size_t slot_words; /* samples that are not `owned` sit at ts * slot_words of the batch buffer */
 } packed_batch;
 
 typedef struct {
@@ -195,14 +206,56 @@ typedef struct {
    int batch_num, nts, cmap_size, floor_adds;
    volatile int next;
    packed_sample *out;
+   uint32_t *slots;   /* batch buffer: sample ts is packed at slots + ts * slot_words ... */
+   size_t slot_words; /* ... when it fits (0: no slots yet, sample 0 sizes them) */
 } pack_job;
 
 static void packed_free(packed_batch *b) {
    if (!b->s) return;
-   for (int i = 0; i < b->n; i++) free(b->s[i].words);
+   for (int i = 0; i < b->n; i++)
+      if (b->s[i].owned) free(b->s[i].words);
    free(b->s);
    b->s = NULL;
    b->n = 0;
+   b->slot_words = 0;
+}
+
+static void pack_one(pack_job *j, int ts, uint32_t *scratch, flam3_genome *cp) {
+   packed_sample *ps = &j->out[ts];
+   const int fi = j->batch_num * j->nts + ts;
+   if (!scratch) {
+      ps->rc = 2;
+      return;
+   }
+   flam3_interpolate(j->spec->genomes, j->spec->ngenomes, j->spec->time + j->tdeltas[fi], 0, cp);
+   if (f3b_camera_setup(cp, j->g, &ps->cam)) {
+      ps->rc = 3;
+      return;
+   }
+   ps->rc = f3b_pack_sample(cp, &ps->cam, j->tfilter[fi], j->cmap_size, j->floor_adds, scratch,
+                            F3B_MAX_BLOB_WORDS, &ps->used, &ps->alpha_ok);
+   if (ps->rc) return;
+   if (j->slot_words && ps->used <= j->slot_words) {
+      ps->words = j->slots + (size_t)ts * j->slot_words;
+      ps->owned = 0;
+   } else {
+      ps->words = (uint32_t *)malloc(ps->used * 4);
+      ps->owned = 1;
+      if (!ps->words) {
+         ps->rc = 2;
+         return;
+      }
+   }
+   memcpy(ps->words, scratch, ps->used * 4);
+   ps->vibrancy = cp->vibrancy;
+   ps->gamma = cp->gamma;
+   ps->background[0] = cp->background[0];
+   ps->background[1] = cp->background[1];
+   ps->background[2] = cp->background[2];
+   ps->contrast = cp->contrast;
+   ps->brightness = cp->brightness;
+   ps->estimator_curve = cp->estimator_curve;
+   ps->gam_lin_thresh = cp->gam_lin_thresh;
 }
 
 static void *pack_worker(void *arg) {
@@ -213,35 +266,7 @@ static void *pack_worker(void *arg) {
    for (;;) {
       const int ts = __sync_fetch_and_add(&j->next, 1);
       if (ts >= j->nts) break;
-      packed_sample *ps = &j->out[ts];
-      const int fi = j->batch_num * j->nts + ts;
-      if (!scratch) {
-         ps->rc = 2;
-         continue;
-      }
-      flam3_interpolate(j->spec->genomes, j->spec->ngenomes, j->spec->time + j->tdeltas[fi], 0, &cp);
-      if (f3b_camera_setup(&cp, j->g, &ps->cam)) {
-         ps->rc = 3;
-         continue;
-      }
-      ps->rc = f3b_pack_sample(&cp, &ps->cam, j->tfilter[fi], j->cmap_size, j->floor_adds, scratch,
-                               F3B_MAX_BLOB_WORDS, &ps->used, &ps->alpha_ok);
-      if (ps->rc) continue;
-      ps->words = (uint32_t *)malloc(ps->used * 4);
-      if (!ps->words) {
-         ps->rc = 2;
-         continue;
-      }
-      memcpy(ps->words, scratch, ps->used * 4);
-      ps->vibrancy = cp.vibrancy;
-      ps->gamma = cp.gamma;
-      ps->background[0] = cp.background[0];
-      ps->background[1] = cp.background[1];
-      ps->background[2] = cp.background[2];
-      ps->contrast = cp.contrast;
-      ps->brightness = cp.brightness;
-      ps->estimator_curve = cp.estimator_curve;
-      ps->gam_lin_thresh = cp.gam_lin_thresh;
+      pack_one(j, ts, scratch, &cp);
    }
    clear_cp(&cp, 0);
    free(scratch);
@@ -263,12 +288,37 @@ static uint64_t draw_sample_seed(flam3_frame *spec, int fi, int nthreads) {
 
 static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *tfilter,
                       const double *tdeltas, int batch_num, int nts, int cmap_size, int floor_adds,
-                      packed_batch *out, uint64_t *seeds, int rc_threads) {
+                      packed_batch *out, uint64_t *seeds, int rc_threads, blob_buf *blobs) {
    packed_free(out);
    out->s = (packed_sample *)calloc((size_t)nts, sizeof(packed_sample));
    if (!out->s) return 1;
    out->n = nts;
-   pack_job job = {spec, g, tfilter, tdeltas, batch_num, nts, cmap_size, floor_adds, 0, out->s};
+   pack_job job = {spec, g, tfilter, tdeltas, batch_num, nts, cmap_size, floor_adds, 0, out->s, NULL, 0};
+   {
+      /* Sample 0 sizes the slots of the batch buffer (the samples of a frame are the same
+       * genome at different times: same size, give or take padding); the others are then
+       * packed straight into the page-locked buffer by the workers. */
+      uint32_t *scratch = (uint32_t *)malloc(F3B_MAX_BLOB_WORDS * 4);
+      flam3_genome cp;
+      memset(&cp, 0, sizeof(cp));
+      pack_one(&job, 0, scratch, &cp);
+      clear_cp(&cp, 0);
+      free(scratch);
+      job.next = 1;
+      if (out->s[0].rc == 0) {
+         const size_t slot = ((out->s[0].used + 3) & ~(size_t)3) + 64;
+         blobs->used = 0;
+         if (blob_reserve(blobs, slot * (size_t)nts)) return 1;
+         memcpy(blobs->words, out->s[0].words, out->s[0].used * 4);
+         free(out->s[0].words);
+         out->s[0].words = blobs->words;
+         out->s[0].owned = 0;
+         job.slots = blobs->words;
+         job.slot_words = slot;
+         out->slot_words = slot;
+         blobs->used = slot * (size_t)nts;
+      }
+   }
    int nthreads = 1;
    if (nts >= 32) {
       const char *e = getenv("F3B_HOST_THREADS");
@@ -302,10 +352,10 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
    const int cmap_size = 256 - (ai ? atoi(ai) : 0);
 
    double *filter = NULL, *temporal_filter = NULL, *temporal_deltas = NULL;
-   blob_buf blobs = {NULL, 0, 0};
+   blob_buf blobs = g_blobs; /* handed back to g_blobs at the end */
    f3b_job *jobs = NULL;
    uint64_t *sample_seeds = NULL;
-   packed_batch packed = {NULL, 0};
+   packed_batch packed = {NULL, 0, 0};
    packed_sample last;
    memset(&last, 0, sizeof(last));
    f3b_de_filters de;
@@ -447,13 +497,14 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       /* ---- pack every temporal sample of this batch (rect.c:754-884). Interpolating and
        * packing a sample is independent host work (~45 us), so with many temporal samples
        * (flam3-animate: 1000 per frame) it is spread over a few host threads. ---- */
+      if (f3b_inputs_consumed(ctx)) goto gpu_error; /* the previous upload has left the buffer */
       blobs.used = 0;
       const uint32_t max_chain = spec->sub_batch_size > 0 ? (uint32_t)spec->sub_batch_size : 10000u;
       uint64_t seed = 0x243f6a8885a308d3ull;
       if (batch_num == 0) t_setup = now_ms() - t_setup;
       t0 = now_ms();
       if (pack_batch(spec, &g, temporal_filter, temporal_deltas, batch_num, ntemporal_samples,
-                     cmap_size, spec->bits != 64, &packed, sample_seeds, nthreads)) {
+                     cmap_size, spec->bits != 64, &packed, sample_seeds, nthreads, &blobs)) {
          fprintf(stderr, "flam3_render (B200): out of memory packing temporal samples\n");
          goto done;
       }
@@ -475,8 +526,14 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
             rv = -2; /* caller retries with a count plane */
             goto done;
          }
-         if (blob_reserve(&blobs, used + 4)) goto done;
-         memcpy(blobs.words + blobs.used, ps->words, used * 4);
+         size_t blob_word_offset;
+         if (ps->owned) { /* did not fit its slot: appended behind the slots */
+            if (blob_reserve(&blobs, used + 4)) goto done;
+            memcpy(blobs.words + blobs.used, ps->words, used * 4);
+            blob_word_offset = blobs.used;
+            blobs.used += (used + 3) & ~(size_t)3;
+         } else
+            blob_word_offset = (size_t)ts * packed.slot_words;
          cam = ps->cam;
 
          /* sample budget (rect.c:830-835) */
@@ -488,14 +545,13 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          if (ts == 0) seed ^= h;
 
          f3b_job *jb = &jobs[ts];
-         jb->blob_offset = (uint64_t)blobs.used * 4;
+         jb->blob_offset = (uint64_t)blob_word_offset * 4;
          jb->n_iters = batch_size > 0 ? (uint64_t)batch_size : 0;
          jb->n_chains = f3b_plan_chains(ctx, jb->n_iters, max_chain, (uint32_t)ntemporal_samples,
                                         (uint32_t)nthreads);
          jb->fuse = spec->earlyclip ? 100 : 15; /* FUSE_28 : FUSE_27, rect.c:39-40,266 */
          jb->first_group = 0;
          jb->sample_id = (uint32_t)(h ^ (h >> 32));
-         blobs.used += (used + 3) & ~(size_t)3;
 
          vibrancy += ps->vibrancy;
          gamma += ps->gamma;
@@ -508,7 +564,9 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
              * batch's last temporal sample (rect.c:933-937, 997, 1076) */
             last = *ps;
             if (batch_num == nbatches - 1) {
-               const float *pal = (const float *)(ps->words + ps->words[F3B_H_OFF_PALETTE]);
+               /* (through the batch buffer: an append above may have moved it) */
+               const uint32_t *pw = blobs.words + blob_word_offset;
+               const float *pal = (const float *)(pw + pw[F3B_H_OFF_PALETTE]);
                for (int j = 0; j < 256; j++)
                   for (int k = 0; k < 3; k++) last_dmap[j][k] = pal[j * 4 + k];
             }
@@ -647,7 +705,9 @@ done:
    free(temporal_filter);
    free(temporal_deltas);
    free(filter);
-   free(blobs.words);
+   if (f3b_inputs_consumed(ctx)) rv = 1;
+   blobs.used = 0;
+   g_blobs = blobs;
    free(jobs);
    free(sample_seeds);
    packed_free(&packed);

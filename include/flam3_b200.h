@@ -88,6 +88,14 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
 /* One application of xform `xform_index` of a packed sample to n caller-supplied points
  * (apply_xform, variations.c:2129-2399): in = {x, y, color} per point, out = {x, y, color,
  * vis_adjusted, bad} per point. For testing the variation maths in isolation. */
+/* `blobs` may be page-locked host memory from f3b_pinned_alloc; the upload is then
+ * asynchronous and f3b_iterate returns while it may still be reading `blobs`:
+ * f3b_inputs_consumed waits until the buffer may be rewritten. (Pageable buffers are
+ * consumed before f3b_iterate returns.) */
+void *f3b_pinned_alloc(size_t bytes);
+void f3b_pinned_free(void *p);
+int f3b_inputs_consumed(f3b_ctx *ctx);
+
 int f3b_debug_apply_xform(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int xform_index,
                           const float *in_xyc, int n, float *out_xycvb, uint64_t seed);
 /* bad values since f3b_frame_begin (stat_struct.badvals, rect.c:1251) */
