@@ -722,6 +722,8 @@ int flam3_render(flam3_frame *spec, void *out, int field, int nchan, int transp,
       fprintf(stderr, "flam3: bits must be 32, 33, or 64 not %d.\n", spec->bits);
       return 1;
    }
+   static double t_last_return = 0.0;
+   const double t_enter = now_ms();
    pthread_mutex_lock(&g_lock);
    f3b_ctx *ctx = get_ctx();
    int rv = 1;
@@ -734,6 +736,10 @@ int flam3_render(flam3_frame *spec, void *out, int field, int nchan, int transp,
       }
       if (rv < 0) rv = 1;
    }
+   if (getenv("F3B_TIMING"))
+      fprintf(stderr, "f3b timing: flam3_render %.2f ms, %.2f ms in the caller since the previous call\n",
+              now_ms() - t_enter, t_last_return > 0.0 ? t_enter - t_last_return : 0.0);
+   t_last_return = now_ms();
    pthread_mutex_unlock(&g_lock);
    return rv;
 }
