@@ -41,6 +41,11 @@ struct f3b_ctx {
    bool accum_zero_pending = false; /* accumulators are logically zero, memset not yet issued */
    unsigned long long *d_badvals = nullptr;
    cudaStream_t side[F3B_SIDE_STREAMS] = {nullptr, nullptr, nullptr};
+   /* fullest bucket's share of the frame's count plane, measured by the density pass of the
+    * last frame, and which genome it belongs to (f3b_iterate decides about aggregation) */
+   double hot_share = -1.0, hot_total = 0.0;
+   bool hot_measured = false; /* a whole-frame density pass has written the fullest bucket */
+   uint64_t hot_share_signature = 0, hot_signature = 0;
    cudaEvent_t inputs_ev = nullptr; /* the last f3b_iterate's uploads have left the host buffers */
    bool inputs_pending = false;
    cudaEvent_t fork_ev = nullptr, join_ev[F3B_SIDE_STREAMS] = {nullptr, nullptr, nullptr};
@@ -144,13 +149,13 @@ int f3b_ctx_create(int device, f3b_ctx **out) {
    }
    ctx->sms = prop.multiProcessorCount;
    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-       cudaMalloc(&ctx->d_badvals, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+       cudaMalloc(&ctx->d_badvals, 6 * sizeof(unsigned long long)) != cudaSuccess) {
       fprintf(stderr, "flam3_b200: context setup failed: %s\n",
               cudaGetErrorString(cudaGetLastError()));
       delete ctx;
       return 1;
    }
-   cudaMemsetAsync(ctx->d_badvals, 0, 4 * sizeof(unsigned long long), ctx->stream);
+   cudaMemsetAsync(ctx->d_badvals, 0, 6 * sizeof(unsigned long long), ctx->stream);
    ctx->iter_blocks_per_sm = f3b_iterate_max_blocks_per_sm(16 * 1024);
    if (ctx->iter_blocks_per_sm <= 0) ctx->iter_blocks_per_sm = 1;
    *out = ctx;
@@ -244,7 +249,9 @@ int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel) {
    ctx->width = width;
    ctx->height = height;
    ctx->count_channel = count_channel ? 1 : 0;
-   CK(cudaMemsetAsync(ctx->d_badvals, 0, 4 * sizeof(unsigned long long), ctx->stream));
+   ctx->hot_total = 0.0;
+   ctx->hot_measured = false;
+   CK(cudaMemsetAsync(ctx->d_badvals, 0, 6 * sizeof(unsigned long long), ctx->stream));
    if (f3b_hist_clear(ctx)) return 1;
    return f3b_accum_clear(ctx);
 }
@@ -429,7 +436,10 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    int launches = 0;
    if (stage_begin(ctx, F3B_STAGE_ITERATE)) return 1;
    P.probe_iters = 0;
-   P.probe_counts = ctx->d_badvals + 1; /* [1] lanes adding, [2] lanes sharing a bucket, [3] scratch */
+   /* device counters: [0] bad values, [1] fullest bucket of the frame (float bits, written by
+    * the density pass), [2] lanes adding / [3] lanes sharing a bucket in the probe, [4] the
+    * probe's own bad values (discarded) */
+   P.probe_counts = ctx->d_badvals + 2;
    bool aggregate = false;
    /* several launches (more temporal samples than fit the parameter space) are independent:
     * they go to side streams so that their CTAs can be resident together */
@@ -498,15 +508,40 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
           * pays ~5% for the aggregation check, so it is decided by measurement: the first
           * 64 iterations of one group per SM run once without adding anything and count how
           * many lanes share their bucket with another lane (~0.1 ms; frames too small to
-          * care are not probed). F3B_AGG=0/1 overrides. */
+          * care are not probed). When the previous frame of the same genome structure and size
+          * went through a whole-frame density pass, that pass has measured the share of the
+          * fullest bucket, and a clear-cut share decides without a probe. F3B_AGG=0/1
+          * overrides. */
          const char *e = getenv("F3B_AGG");
          uint64_t total_iters = 0;
          for (int j = 0; j < n_jobs; j++) total_iters += jobs[j].n_iters;
+         /* genome structure + frame size: frames of one animation, repeated renders */
+         uint64_t sig = 0xcbf29ce484222325ull ^ ((uint64_t)ctx->width << 32) ^ (uint64_t)ctx->height;
+         {
+            const uint32_t *w0 = (const uint32_t *)((const char *)blobs + jobs[0].blob_offset);
+            const uint32_t nx = w0[F3B_H_NXF];
+            sig = (sig ^ nx ^ ((uint64_t)w0[F3B_H_XAOS] << 8) ^ ((uint64_t)w0[F3B_H_FINAL] << 16)) * 0x100000001b3ull;
+            for (uint32_t q = 0; q < nx; q++) {
+               const uint32_t rec = w0[F3B_H_XF_BASE] + q * w0[F3B_H_XF_STRIDE];
+               sig = (sig ^ w0[rec + F3B_X_FLAGS]) * 0x100000001b3ull;
+               for (uint32_t pv = rec + F3B_X_VARS; pv < rec + F3B_X_VARS + (w0[rec + F3B_X_FLAGS] >> 8);) {
+                  sig = (sig ^ (w0[pv] & 0xffu)) * 0x100000001b3ull;
+                  pv += 2 + (w0[pv] >> 8);
+               }
+            }
+         }
+         ctx->hot_signature = sig;
+         ctx->hot_total = 255.0 * (double)total_iters; /* of one batch, like the bucket maximum */
+         const bool known = ctx->hot_share >= 0.0 && ctx->hot_share_signature == sig;
          if (e) aggregate = atoi(e) != 0;
+         /* one bucket with share s of the hits gives a lane a duplicate among its 31 peers with
+          * probability ~31 s: the probe's 1/8 criterion corresponds to s ~ 0.4% */
+         else if (known && ctx->hot_share < 0.0035) aggregate = false; /* spread out last time */
+         else if (known && ctx->hot_share > 0.02) aggregate = true;   /* one bucket took > 2% */
          else if (total_iters / (uint64_t)nranks >= 50000000ull) {
             F3IterateParams Q = P;
             Q.probe_iters = 64;
-            Q.badvals = ctx->d_badvals + 3;
+            Q.badvals = ctx->d_badvals + 4;
             int pgrid = ctx->sms < grid ? ctx->sms : grid;
             const uint64_t lim = (uint64_t)P.group_begin + (uint64_t)pgrid * (uint64_t)nranks;
             if (lim < Q.n_groups) Q.n_groups = (uint32_t)lim;
@@ -516,10 +551,10 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
                return fail(ctx, "probe launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             launches++;
             unsigned long long pc[2] = {0, 0};
-            CK(cudaMemcpyAsync(pc, ctx->d_badvals + 1, sizeof(pc), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(pc, ctx->d_badvals + 2, sizeof(pc), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             aggregate = pc[0] > 0 && pc[1] * 8 >= pc[0];
-            CK(cudaMemsetAsync(ctx->d_badvals + 1, 0, 3 * sizeof(unsigned long long), ctx->stream));
+            CK(cudaMemsetAsync(ctx->d_badvals + 2, 0, 3 * sizeof(unsigned long long), ctx->stream));
          }
       }
       const int nl = f3b_launch_iterate(P, consts.data(), j1 - j0, ctx->count_channel != 0, simple,
@@ -573,12 +608,20 @@ int f3b_debug_apply_xform(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int
 }
 
 int f3b_badvals(f3b_ctx *ctx, double *out) {
-   unsigned long long v = 0;
+   unsigned long long v[2] = {0, 0};
    CK(cudaSetDevice(ctx->device));
-   CK(cudaMemcpyAsync(&v, ctx->d_badvals, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+   CK(cudaMemcpyAsync(v, ctx->d_badvals, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
    ctx->d2h_bytes += sizeof(v);
    CK(cudaStreamSynchronize(ctx->stream));
-   *out = (double)v;
+   *out = (double)v[0];
+   /* end of frame: remember how concentrated this genome's histogram was (see f3b_iterate) */
+   if (ctx->hot_total > 0.0 && ctx->hot_measured) {
+      float mx;
+      const uint32_t bits = (uint32_t)v[1];
+      memcpy(&mx, &bits, sizeof(mx));
+      ctx->hot_share = (double)mx / ctx->hot_total;
+      ctx->hot_share_signature = ctx->hot_signature;
+   }
    return 0;
 }
 
@@ -668,6 +711,9 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
       if (ensure(ctx, ctx->de_tiles, tiles * sizeof(int))) return 1;
       P.de_kidx = (uint16_t *)ctx->de_kidx.p;
       P.tile_maxrad = (int *)ctx->de_tiles.p;
+      /* whole-frame passes only: a strip sees a part of the histogram */
+      P.hot_max = (row0 == 0 && row1 == ctx->height) ? (int *)(ctx->d_badvals + 1) : nullptr;
+      if (P.hot_max) ctx->hot_measured = true;
    }
    if (ctx->accum_zero_pending && P.n_kernels > 0 && row0 == 0 && row1 == ctx->height) {
       P.overwrite_accum = 1;

@@ -112,6 +112,7 @@ struct F3DensityParams {
    uint16_t *de_kidx;         /* [height*width] kernel index per bucket, 0xffff = not a source */
    int *tile_maxrad;          /* [tiles_y*tiles_x] largest radius >= 1 in each 32x32 tile */
    int overwrite_accum;       /* first batch of a frame: write the accumulators, do not add */
+   int *hot_max;              /* device: max over buckets of the count plane, as float bits */
    /* filled by f3b_launch_density */
    int class_row_begin, class_row_end; /* rows classified: the target rows +- max_radius */
    int class_tile_y0, class_tile_y1, gather_tile_y0;

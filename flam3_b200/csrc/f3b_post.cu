@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(cons
    const int gx = blockIdx.x * DE_TILE + threadIdx.x;
    const int tile_y = P.class_tile_y0 + blockIdx.y;
    int my_maxrad = 0;
+   float maxcnt = 0.0f;
 
    float4 c[DE_PER_THREAD];
    int gy[DE_PER_THREAD];
@@ -94,6 +95,7 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(cons
       if (!live[q]) continue;
       const size_t gi = (size_t)gx + (size_t)P.width * gy[q];
       const float cnt = P.hist_count ? P.hist_count[f3b_hist_index(P.lay, gx, gy[q])] : c[q].w;
+      maxcnt = fmaxf(maxcnt, cnt);
       unsigned kidx = DE_NO_SOURCE;
       float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
       bool has_self = false;
@@ -139,15 +141,27 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(cons
          }
       }
    }
-   /* largest wide-kernel radius of this tile */
-   for (int o = 16; o > 0; o >>= 1) my_maxrad = max(my_maxrad, __shfl_xor_sync(0xffffffffu, my_maxrad, o));
-   __shared__ int s_rad[DE_ROWS];
-   if (threadIdx.x == 0) s_rad[threadIdx.y] = my_maxrad;
+   /* largest wide-kernel radius of this tile, and the fullest bucket seen (counts are
+    * non-negative floats, so their bit patterns order like integers) */
+   int my_maxcnt = __float_as_int(maxcnt);
+   for (int o = 16; o > 0; o >>= 1) {
+      my_maxrad = max(my_maxrad, __shfl_xor_sync(0xffffffffu, my_maxrad, o));
+      my_maxcnt = max(my_maxcnt, __shfl_xor_sync(0xffffffffu, my_maxcnt, o));
+   }
+   __shared__ int s_rad[DE_ROWS], s_cnt[DE_ROWS];
+   if (threadIdx.x == 0) {
+      s_rad[threadIdx.y] = my_maxrad;
+      s_cnt[threadIdx.y] = my_maxcnt;
+   }
    __syncthreads();
    if (threadIdx.x == 0 && threadIdx.y == 0) {
-      int m = 0;
-      for (int i = 0; i < DE_ROWS; i++) m = max(m, s_rad[i]);
+      int m = 0, c = 0;
+      for (int i = 0; i < DE_ROWS; i++) {
+         m = max(m, s_rad[i]);
+         c = max(c, s_cnt[i]);
+      }
       P.tile_maxrad[(size_t)tile_y * gridDim.x + blockIdx.x] = m;
+      if (P.hot_max && c > 0) atomicMax(P.hot_max, c);
    }
 }
 
