@@ -6,16 +6,21 @@
  *
  *  - one persistent walker per thread; a thread runs whole "chains" (= the reference's
  *    sub-batches: random start point, `fuse` discarded iterations, then stored ones);
- *  - a block (256 threads) works on a "chain group": 256 chains of the SAME temporal
- *    sample, whose packed genome/chooser/palette/camera blob is staged once in shared
- *    memory; blocks walk the group list with a grid stride (persistent CTAs);
+ *  - a block works on a "chain group": up to 256 chains (32..256, = blockDim.x) of the SAME
+ *    temporal sample, whose packed genome/chooser/palette blob is staged once in shared
+ *    memory; blocks walk the group list with a grid stride (persistent CTAs). What is
+ *    warp-uniform per sample (camera, flags, offsets, the xform pick table) comes from the
+ *    kernel parameters through the constant bank instead;
  *  - xform selection reproduces the 16384-grain table exactly through per-row cumulative
- *    counts held in shared memory (flam3.c:165-224), including xaos rows;
+ *    counts (flam3.c:165-224), including xaos rows;
  *  - the 5-channel bucket bump (rect.c:500-512) becomes ONE 16-byte vector reduction
- *    `red.global.add.v4.f32` into L2-resident float4 colour buckets, plus a scalar
+ *    `red.global.add.v4.f32` into L2-resident float4 colour buckets (K copies of them, a CTA
+ *    adds into copy blockIdx.x % K, see f3b_api.cu: hist_layout_for), plus a scalar
  *    `red.global.add.f32` into the count plane only when the count channel is not
  *    identical to the alpha channel (COUNT=false: palette alpha == 1 and temporal filter
- *    weight == 1 everywhere, the common case, where b[3] == b[4] bucket by bucket).
+ *    weight == 1 everywhere, the common case, where b[3] == b[4] bucket by bucket);
+ *  - instantiations: SIMPLE (classic flames: packed pick, folded flag tests) and AGG
+ *    (collapsed attractors: equal buckets of a warp aggregated before the reduction).
  *
  * Adds are integer valued (floor, like bump_no_overflow with unsigned buckets,
  * flam3.c:3838-3854), so float accumulation is exact up to 2^24 per channel.
