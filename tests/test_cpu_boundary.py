@@ -246,3 +246,62 @@ def test_chooser_closed_form_equals_the_reference_loop():
         f(dr, 16384, thr_c, len(thr), a, 1)
         f(dr, 16384, thr_c, len(thr), b, 0)
         assert list(a) == list(b), (w, list(a), list(b))
+
+
+XAOS_GENOME = """
+<flame time="0" size="64 64" center="0 0" scale="16" quality="5">
+   <xform weight="0.31" color="0" linear="1" coefs="0.5 0 0 0.5 -0.5 0" chaos="1 0.25 3"/>
+   <xform weight="0.07" color="0.5" spherical="1" coefs="0.5 0 0 0.5 0.5 0" chaos="0 1 1"/>
+   <xform weight="1.7" color="1" swirl="0.5" linear="0.5" coefs="0.4 0.2 -0.2 0.4 0 0.5" chaos="2 2 0.01"/>
+   <finalxform color="0" linear="1" coefs="1 0 0 1 0 0"/>
+   <color index="0" rgb="255 0 0"/>
+</flame>
+"""
+
+
+def _chooser_from_pack(gpu, genomes, idx=0):
+    """Expands the packed cumulative counts of a sample back into the 16384-entry rows."""
+    f = gpu._dll.f3b_debug_pack_genome
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    w = np.zeros(12288, dtype=np.uint32)
+    used = C.c_size_t()
+    assert f(genomes.ptr, idx, 1, w.ctypes.data, w.size, C.byref(used)) == 0
+    nstd, xaos, stride, off = int(w[1]), int(w[3]), int(w[25]), int(w[20])
+    rows = nstd + 1 if xaos else 1
+    out = np.empty((rows, 16384), dtype=np.uint16)
+    k = np.arange(16384)
+    for r in range(rows):
+        cum = w[off + r * stride: off + r * stride + nstd].astype(np.int64)
+        assert np.all(np.diff(cum) >= 0) and cum[-1] == 16384
+        assert np.all(w[off + r * stride + nstd: off + (r + 1) * stride] == 16384)   # padding
+        out[r] = np.searchsorted(cum, k, side="right")   # number of thresholds <= k
+    return out
+
+
+def _reference_chooser(lib, genomes, idx=0):
+    f = lib._dll.h_xform_distrib
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    buf = np.zeros(64 * 16384, dtype=np.uint16)
+    rows = C.c_int()
+    assert f(genomes.ptr, idx, buf.ctypes.data, C.byref(rows)) == 0
+    return buf[: rows.value * 16384].reshape(rows.value, 16384)
+
+
+def test_chooser_tables_equal_the_reference_entry_for_entry(gpu, ref, flame0):
+    """flam3_create_xform_distrib / flam3_create_chaos_distrib (flam3.c:76-224) against the
+    packed cumulative counts the kernel compares its 14-bit draw with: every one of the 16384
+    entries of every row, for test.flam3, an xaos + final-xform genome and all 122 random
+    genomes of config C5."""
+    import glob
+    cases = [flame0, XAOS_GENOME]
+    cases += [open(p).read() for p in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "c5", "c5_*.flam3")))]
+    assert len(cases) == 124
+    n_xaos = 0
+    for xml in cases:
+        gr, gg = ref.parse(xml), gpu.parse(xml)
+        want = _reference_chooser(ref, gr)
+        got = _chooser_from_pack(gpu, gg)
+        n_xaos += want.shape[0] > 1
+        assert got.shape == want.shape
+        assert np.array_equal(got, want), int((got != want).sum())
+    assert n_xaos >= 1
