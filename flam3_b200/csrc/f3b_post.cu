@@ -403,9 +403,14 @@ __device__ __forceinline__ void f3b_tonemap(double *t, const F3FinalParams &P) {
    }
    double newrgb[3];
    f3b_calc_newrgb(t, ls, P.highpow, newrgb);
+   /* the reference always evaluates (1 - vibrancy) * 256 * pow(t/255, g) (rect.c:1195); with
+    * the default vibrancy of exactly 1 the product is an exact zero whenever t >= 0 (pow is
+    * finite), and three of the four double-precision pows per pixel can be skipped; a
+    * negative t (filters with negative lobes) keeps the reference's NaN */
+   const double inv_vib = 1.0 - P.vibrancy;
    for (int i = 0; i < 3; i++) {
       double a = newrgb[i];
-      a += (1.0 - P.vibrancy) * 256.0 * pow(t[i] / 255.0, P.g);
+      if (inv_vib != 0.0 || t[i] < 0.0) a += inv_vib * 256.0 * pow(t[i] / 255.0, P.g);
       if (P.nchan <= 3 || P.transp == 0) a += (1.0 - alpha) * P.background[i];
       else a = (alpha > 0.0) ? a / alpha : 0.0;
       if (a > 255.0) a = 255.0;
