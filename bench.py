@@ -406,8 +406,10 @@ def main():
         "data": "synthetic (genome fixture tests/golden/test_flame0.flam3, random walk seeds)",
         "config": {"workload": WORKLOAD, "iters_per_step": iters_per_step,
                    "buckets": [geo["width"], geo["height"]],
-                   "l2_policy": "histogram+accumulator (76.6 MB) are re-zeroed and rewritten "
-                                "every step; scatter addresses are random, no reuse across steps",
+                   "l2_policy": "every step clears and rewrites its whole working set: 3 histogram "
+                                "copies (102 MB) + accumulator (34 MB) + DE index plane (4 MB) = 140 MB, "
+                                "larger than the 126 MB L2; scatter addresses are random, nothing is "
+                                "reused across steps",
                    "parallelism": ("chains sharded over %d GPUs, NCCL all-reduce of the histograms, "
                                    "row-strip post-pass + NCCL all-gather of the image strips" % world)
                    if world > 1 else "single GPU"},
