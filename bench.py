@@ -10,7 +10,8 @@ log-scale + density estimation, spatial filter + tone map.
 Workload at every N: config C2 of SURVEY.md §8(d) — test.flam3's first flame at 1920x1080,
 quality 2000, oversample 1, estimator_radius 9 (4.147e9 stored iterations per frame). With
 N > 1 the frame's chains are split over the ranks (strong scaling), the private
-histograms are summed with one NCCL all-reduce and rank 0 delivers the image.
+histograms are summed with one NCCL all-reduce, every rank post-processes a strip of image
+rows and an NCCL all-gather assembles the image (flam3_b200/multigpu.py).
 
  value : whole-job iterations/s from CUDA events on the render stream around the K
          steps, images left on the device (inputs are a few KB of packed genome).
