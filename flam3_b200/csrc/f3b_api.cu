@@ -44,7 +44,9 @@ struct f3b_ctx {
    /* fullest bucket's share of the frame's count plane, measured by the density pass of the
     * last frame, and which genome it belongs to (f3b_iterate decides about aggregation) */
    double hot_share = -1.0, hot_total = 0.0;
-   bool hot_measured = false; /* a whole-frame density pass has written the fullest bucket */
+   bool hot_measured = false;   /* a pass over the whole histogram has written the fullest bucket */
+   bool hot_from_merge = false; /* ... the merge of the histogram copies (this rank's share) */
+   uint64_t hot_iters = 0;
    uint64_t hot_share_signature = 0, hot_signature = 0;
    cudaEvent_t inputs_ev = nullptr; /* the last f3b_iterate's uploads have left the host buffers */
    bool inputs_pending = false;
@@ -251,6 +253,7 @@ int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel) {
    ctx->count_channel = count_channel ? 1 : 0;
    ctx->hot_total = 0.0;
    ctx->hot_measured = false;
+   ctx->hot_from_merge = false;
    CK(cudaMemsetAsync(ctx->d_badvals, 0, 6 * sizeof(unsigned long long), ctx->stream));
    if (f3b_hist_clear(ctx)) return 1;
    return f3b_accum_clear(ctx);
@@ -531,6 +534,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
             }
          }
          ctx->hot_signature = sig;
+         ctx->hot_iters = total_iters;
          ctx->hot_total = 255.0 * (double)total_iters; /* of one batch, like the bucket maximum */
          const bool known = ctx->hot_share >= 0.0 && ctx->hot_share_signature == sig;
          if (e) aggregate = atoi(e) != 0;
@@ -567,9 +571,16 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          CK(cudaEventRecord(ctx->join_ev[i], ctx->side[i]));
          CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
       }
+   /* the merge of the copies sees this rank's whole histogram (1/nranks of the hits): it also
+    * records the fullest bucket */
    const int nm = f3b_launch_hist_merge((float4 *)ctx->hist_color.p,
                                         ctx->count_channel ? (float *)ctx->hist_count.p : nullptr,
-                                        ctx->hist_elems, ctx->lay, ctx->stream);
+                                        ctx->hist_elems, ctx->lay, (int *)(ctx->d_badvals + 1), ctx->stream);
+   if (nm > 0) {
+      ctx->hot_measured = true;
+      ctx->hot_from_merge = true;
+      ctx->hot_total = 255.0 * (double)ctx->hot_iters / (double)nranks;
+   }
    if (nm < 0) return fail(ctx, "histogram merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
    launches += nm;
    return stage_end(ctx, launches);
@@ -711,8 +722,9 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
       if (ensure(ctx, ctx->de_tiles, tiles * sizeof(int))) return 1;
       P.de_kidx = (uint16_t *)ctx->de_kidx.p;
       P.tile_maxrad = (int *)ctx->de_tiles.p;
-      /* whole-frame passes only: a strip sees a part of the histogram */
-      P.hot_max = (row0 == 0 && row1 == ctx->height) ? (int *)(ctx->d_badvals + 1) : nullptr;
+      /* whole-frame passes only (a strip sees a part of the histogram), and only when the
+       * merge of the histogram copies has not measured it already */
+      P.hot_max = (!ctx->hot_from_merge && row0 == 0 && row1 == ctx->height) ? (int *)(ctx->d_badvals + 1) : nullptr;
       if (P.hot_max) ctx->hot_measured = true;
    }
    if (ctx->accum_zero_pending && P.n_kernels > 0 && row0 == 0 && row1 == ctx->height) {

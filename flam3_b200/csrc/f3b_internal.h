@@ -87,7 +87,7 @@ int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes);
 int f3b_iterate_const_capacity(void);
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes);
 /* copy 0 += copies 1..replicas-1 of the colour (and count) planes */
-int f3b_launch_hist_merge(float4 *color, float *count, size_t elems, F3HistLayout lay,
+int f3b_launch_hist_merge(float4 *color, float *count, size_t elems, F3HistLayout lay, int *hot_max,
                           cudaStream_t stream);
 int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_index, const float *in,
                            int n, float *out, uint64_t seed, cudaStream_t stream);

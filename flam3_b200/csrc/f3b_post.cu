@@ -545,9 +545,10 @@ int f3b_launch_hist_to_u32(const float4 *color, const float *count, uint32_t *ds
 /* sum of the histogram replicas the chaos game wrote (f3b_api.cu: hist_layout_for)    */
 /* ---------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(256) f3b_hist_merge_kernel(float4 *color, float *count, size_t n,
-                                                             F3HistLayout lay) {
+                                                             F3HistLayout lay, int *hot_max) {
    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
    const size_t stride = (size_t)gridDim.x * blockDim.x;
+   float mx = 0.0f;
    for (; i < n; i += stride) {
       float4 a = color[i];
       float c = count ? count[i] : 0.0f;
@@ -561,13 +562,19 @@ __global__ void __launch_bounds__(256) f3b_hist_merge_kernel(float4 *color, floa
       }
       color[i] = a;
       if (count) count[i] = c;
+      mx = fmaxf(mx, count ? c : a.w);
    }
+   /* the fullest bucket of this rank's histogram (non-negative floats order like their bits):
+    * f3b_iterate's aggregation decision for the next frame of this genome */
+   int m = __float_as_int(mx);
+   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+   if (hot_max && (threadIdx.x & 31) == 0 && m > 0) atomicMax(hot_max, m);
 }
-int f3b_launch_hist_merge(float4 *color, float *count, size_t elems, F3HistLayout lay,
+int f3b_launch_hist_merge(float4 *color, float *count, size_t elems, F3HistLayout lay, int *hot_max,
                           cudaStream_t stream) {
    if (lay.replicas <= 1) return 0;
    int blocks = (int)((elems + 255) / 256);
    if (blocks > 148 * 8) blocks = 148 * 8;
-   f3b_hist_merge_kernel<<<blocks, 256, 0, stream>>>(color, count, elems, lay);
+   f3b_hist_merge_kernel<<<blocks, 256, 0, stream>>>(color, count, elems, lay, hot_max);
    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
