@@ -290,3 +290,42 @@ def test_chain_plan_follows_the_reference_rule():
     assert plan(3072, 10000, 1000, 16) == 16
     # the headline frame: planned for a node's worth of threads, whatever the number of GPUs
     assert plan(4_147_200_000, 10000, 1, 1) == 8 * resident
+
+
+@pytest.mark.parametrize("variant", ["alpha_is_count", "count_plane", "collapsed"])
+def test_warp_aggregated_adds_give_the_same_histogram(flame0, variant):
+    """The AGG kernels (collapsed attractors: lanes of a warp that hit the same bucket sum
+    their colours and one of them adds) must produce the very histogram the plain kernels
+    produce: the adds are integer valued, so regrouping them is exact. Forced on and off
+    with F3B_AGG; `collapsed` is a genome whose orbit falls onto a handful of buckets, where
+    nearly every add is aggregated."""
+    import os
+    ref, gpu, core = libs()
+    if variant == "collapsed":
+        xml = """<flame time="0" size="128 128" center="0 0" scale="32" quality="3" temporal_samples="1"
+                 estimator_radius="0">
+                 <xform weight="1" color="0" linear="1" coefs="0.2 0 0 0.2 0.4 0.1"/>
+                 <xform weight="1" color="1" linear="1" coefs="0.1 0.05 -0.05 0.1 0.38 0.12"/>
+                 <color index="0" rgb="255 128 64"/><color index="255" rgb="32 64 255"/></flame>"""
+    else:
+        xml = resize(flame0, 160, 120, scale=60, quality=30, temporal_samples=1)
+        if variant == "count_plane":
+            xml = set_flame_attrs(xml, palette_mode="linear")
+    gg = gpu.parse(xml)
+    geo = gpu.buffer_geometry(gg)
+    ctx = gpu.render_context(core)
+    ctx.width, ctx.height = geo["width"], geo["height"]
+    hists = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["F3B_AGG"] = mode
+            _, st, _ = gpu.render(gg, isaac_seed="agg", sub_batch_size=500)
+            assert st["rv"] == 0
+            hists[mode] = ctx.hist_download_u32().astype(np.int64)
+    finally:
+        os.environ.pop("F3B_AGG", None)
+    assert hists["0"].sum() > 0 and hists["0"].max() < 2 ** 24
+    assert np.array_equal(hists["0"], hists["1"]), int((hists["0"] != hists["1"]).any(axis=-1).sum())
+    if variant == "collapsed":
+        h = hists["0"][..., 4]
+        assert np.sort(h.ravel())[-8:].sum() > 0.9 * h.sum()   # really collapsed
