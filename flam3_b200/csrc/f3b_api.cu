@@ -327,6 +327,24 @@ uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len,
    return (uint32_t)chains;
 }
 
+/* What stays the same between the frames of an animation or between repeated renders of a
+ * genome: its structure (xform count, xaos, final xform, each xform's flags and variation
+ * ids - not the coefficients) and the frame size. Keys the hot-bucket feedback below. */
+static uint64_t genome_signature(const uint32_t *w0, int width, int height) {
+   uint64_t sig = 0xcbf29ce484222325ull ^ ((uint64_t)width << 32) ^ (uint64_t)height;
+   const uint32_t nx = w0[F3B_H_NXF];
+   sig = (sig ^ nx ^ ((uint64_t)w0[F3B_H_XAOS] << 8) ^ ((uint64_t)w0[F3B_H_FINAL] << 16)) * 0x100000001b3ull;
+   for (uint32_t q = 0; q < nx; q++) {
+      const uint32_t rec = w0[F3B_H_XF_BASE] + q * w0[F3B_H_XF_STRIDE];
+      sig = (sig ^ w0[rec + F3B_X_FLAGS]) * 0x100000001b3ull;
+      for (uint32_t pv = rec + F3B_X_VARS; pv < rec + F3B_X_VARS + (w0[rec + F3B_X_FLAGS] >> 8);) {
+         sig = (sig ^ (w0[pv] & 0xffu)) * 0x100000001b3ull;
+         pv += 2 + (w0[pv] >> 8);
+      }
+   }
+   return sig;
+}
+
 void *f3b_pinned_alloc(size_t bytes) {
    void *p = nullptr;
    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -511,28 +529,15 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
           * pays ~5% for the aggregation check, so it is decided by measurement: the first
           * 64 iterations of one group per SM run once without adding anything and count how
           * many lanes share their bucket with another lane (~0.1 ms; frames too small to
-          * care are not probed). When the previous frame of the same genome structure and size
-          * went through a whole-frame density pass, that pass has measured the share of the
-          * fullest bucket, and a clear-cut share decides without a probe. F3B_AGG=0/1
-          * overrides. */
+          * care are not probed). When the previous frame had the same genome structure and
+          * size, the merge of its histogram copies (or its whole-frame density pass) has
+          * measured the share of the fullest bucket, and a clear-cut share decides without a
+          * probe. F3B_AGG=0/1 overrides. */
          const char *e = getenv("F3B_AGG");
          uint64_t total_iters = 0;
          for (int j = 0; j < n_jobs; j++) total_iters += jobs[j].n_iters;
-         /* genome structure + frame size: frames of one animation, repeated renders */
-         uint64_t sig = 0xcbf29ce484222325ull ^ ((uint64_t)ctx->width << 32) ^ (uint64_t)ctx->height;
-         {
-            const uint32_t *w0 = (const uint32_t *)((const char *)blobs + jobs[0].blob_offset);
-            const uint32_t nx = w0[F3B_H_NXF];
-            sig = (sig ^ nx ^ ((uint64_t)w0[F3B_H_XAOS] << 8) ^ ((uint64_t)w0[F3B_H_FINAL] << 16)) * 0x100000001b3ull;
-            for (uint32_t q = 0; q < nx; q++) {
-               const uint32_t rec = w0[F3B_H_XF_BASE] + q * w0[F3B_H_XF_STRIDE];
-               sig = (sig ^ w0[rec + F3B_X_FLAGS]) * 0x100000001b3ull;
-               for (uint32_t pv = rec + F3B_X_VARS; pv < rec + F3B_X_VARS + (w0[rec + F3B_X_FLAGS] >> 8);) {
-                  sig = (sig ^ (w0[pv] & 0xffu)) * 0x100000001b3ull;
-                  pv += 2 + (w0[pv] >> 8);
-               }
-            }
-         }
+         const uint64_t sig = genome_signature(
+             (const uint32_t *)((const char *)blobs + jobs[0].blob_offset), ctx->width, ctx->height);
          ctx->hot_signature = sig;
          ctx->hot_iters = total_iters;
          ctx->hot_total = 255.0 * (double)total_iters; /* of one batch, like the bucket maximum */
