@@ -50,10 +50,10 @@ REF_CFLAGS = -g -O3 -std=gnu99 -ffast-math -fPIC -w -I$(SHIMS) -I$(F3_REF) \
 HOST_SRCS  = variations.c filters.c isaac.c interpolation.c palettes.c parser.c
 HOST_OBJS  = $(addprefix $(DROP)/host_,$(HOST_SRCS:.c=.o))
 GLUE_OBJS  = $(DROP)/f3b_render.o $(DROP)/f3b_pack.o $(DROP)/f3b_isaac.o $(DROP)/f3b_debug.o
-MISC_OBJS  = $(DROP)/xmlshim.o $(DROP)/imgshim.o $(DROP)/harness.o
+MISC_OBJS  = $(DROP)/xmlshim.o $(DROP)/imgshim.o
 CLIS       = $(DROP)/flam3-render $(DROP)/flam3-animate $(DROP)/flam3-genome
 
-dropin: lib $(DROP)/libflam3.so $(CLIS)
+dropin: lib $(DROP)/libflam3.so $(CLIS) $(DROP)/libf3harness.so
 
 $(DROP):
 	mkdir -p $(DROP)
@@ -77,6 +77,12 @@ $(DROP)/imgshim.o: $(SHIMS)/imgshim.c | $(DROP)
 $(DROP)/harness.o: tests/harness/f3_harness.c | $(DROP)
 	$(CC) -O2 -fPIC -std=gnu99 -w -I$(SHIMS) -I$(F3_REF) -c $< -o $@
 
+# test infrastructure, NOT part of the product: the ctypes harness over flam3.h as its own
+# library, linked against the drop-in like any other libflam3 client
+$(DROP)/libf3harness.so: $(DROP)/harness.o $(DROP)/libflam3.so
+	$(CC) -shared -o $@ $(DROP)/harness.o -L$(DROP) -lflam3 -L$(LIBDIR) -lflam3_b200 \
+	   -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' -lm
+
 $(DROP)/libflam3.so: $(HOST_OBJS) $(DROP)/host_flam3.o $(GLUE_OBJS) $(MISC_OBJS) $(LIBDIR)/libflam3_b200.so
 	$(CC) -shared -Wl,-Bsymbolic -o $@ $(HOST_OBJS) $(DROP)/host_flam3.o $(GLUE_OBJS) $(MISC_OBJS) \
 	   -L$(LIBDIR) -lflam3_b200 -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' -lm -lpthread -lz
@@ -96,6 +102,10 @@ oracle:
 	@echo "reference tree $(F3_REF) not present: using prebuilt oracle/_ref artefacts"
 endif
 
+# microbenchmark of the scattered-reduction ceiling (profiles/r01_red_peak_microbench.txt)
+tools/micro/red_peak: tools/micro/red_peak.cu
+	$(NVCC) $(ARCH) -O3 -o $@ $<
+
 clean:
-	rm -rf $(LIBDIR) $(DROP) oracle/_ref
+	rm -rf $(LIBDIR) $(DROP) oracle/_ref tools/micro/red_peak
 .PHONY: all lib dropin oracle clean

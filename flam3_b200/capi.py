@@ -28,6 +28,12 @@ def dropin_lib_path():
     return os.path.join(repo_root(), "dropin", "_build", "libflam3.so")
 
 
+def dropin_harness_path():
+    """The test harness over flam3.h (tests/harness/f3_harness.c) built as its own library
+    against the drop-in libflam3.so — the product library itself holds no test code."""
+    return os.path.join(repo_root(), "dropin", "_build", "libf3harness.so")
+
+
 class RenderArgs(C.Structure):
     """Mirror of h_render_args (tests/harness/f3_harness.c)."""
 
@@ -101,7 +107,7 @@ class Flam3Lib:
     """A libflam3 build (flam3.h API + harness). Default: the B200 drop-in."""
 
     def __init__(self, path=None):
-        path = path or dropin_lib_path()
+        path = path or dropin_harness_path()
         if not os.path.exists(path):
             raise RuntimeError(
                 "native library %s is missing: run `make` (or __graft_entry__.build()) first; "
@@ -130,6 +136,19 @@ class Flam3Lib:
         """Make the following flam3_render calls skip the chaos game and use `buckets5`
         (uint32[h, w, 5], the reference's bits=33 bucket layout). None switches back."""
         f = self._dll.f3b_render_inject_histogram
+        f.argtypes = [C.c_void_p, C.c_size_t]
+        f.restype = None
+        if buckets5 is None:
+            self._inject_keep = None
+            f(None, 0)
+            return
+        b = np.ascontiguousarray(buckets5, dtype=np.uint32)
+        self._inject_keep = b
+        f(b.ctypes.data_as(C.c_void_p), b.size // 5)
+
+    def preload_histogram(self, buckets5):
+        """Like inject_histogram, but the chaos game still runs and adds on top."""
+        f = self._dll.f3b_render_preload_histogram
         f.argtypes = [C.c_void_p, C.c_size_t]
         f.restype = None
         if buckets5 is None:
@@ -271,7 +290,7 @@ class DeFilters(C.Structure):
 CORE_SYMBOLS = [
     "f3b_abi_version", "f3b_ctx_create", "f3b_ctx_destroy", "f3b_last_error", "f3b_device_info",
     "f3b_sync", "f3b_frame_begin", "f3b_hist_clear", "f3b_accum_clear", "f3b_plan_chains",
-    "f3b_iterate", "f3b_pinned_alloc", "f3b_pinned_free", "f3b_inputs_consumed", "f3b_badvals", "f3b_density", "f3b_density_rows", "f3b_finish",
+    "f3b_iterate", "f3b_pinned_alloc", "f3b_pinned_free", "f3b_inputs_consumed", "f3b_badvals", "f3b_exactness", "f3b_density", "f3b_density_rows", "f3b_finish",
     "f3b_finish_device", "f3b_finish_device_rows", "f3b_image_download", "f3b_hist_upload_u32", "f3b_hist_download_u32", "f3b_accum_upload",
     "f3b_accum_download", "f3b_hist_color_ptr", "f3b_hist_count_ptr", "f3b_hist_elems", "f3b_accum_ptr",
     "f3b_stream_ptr", "f3b_stage_stats", "f3b_stats_reset", "f3b_xfer_stats", "f3b_timer_start",
@@ -297,7 +316,7 @@ class CoreLib:
         d.f3b_last_error.argtypes = [vp]
         d.f3b_device_info.argtypes = [vp, C.POINTER(ci)]
         d.f3b_sync.argtypes = [vp]
-        d.f3b_frame_begin.argtypes = [vp, ci, ci, ci]
+        d.f3b_frame_begin.argtypes = [vp, ci, ci, ci, ci]
         d.f3b_hist_clear.argtypes = [vp]
         d.f3b_accum_clear.argtypes = [vp]
         d.f3b_plan_chains.restype = C.c_uint32
@@ -394,8 +413,8 @@ class Context:
         self._ck(self.lib._dll.f3b_device_info(self.ptr, info), "device_info")
         return dict(sms=info[0], blocks_per_sm=info[1], threads=info[2])
 
-    def frame_begin(self, width, height, count_channel=True):
-        self._ck(self.lib._dll.f3b_frame_begin(self.ptr, width, height, int(count_channel)),
+    def frame_begin(self, width, height, count_channel=True, bits=33):
+        self._ck(self.lib._dll.f3b_frame_begin(self.ptr, width, height, int(count_channel), bits),
                  "frame_begin")
         self.width, self.height = width, height
 
@@ -463,6 +482,15 @@ class Context:
         self._ck(self.lib._dll.f3b_finish(self.ptr, C.byref(f), out.ctypes.data_as(C.c_void_p),
                                           image_width * nchan * bytes_per_channel), "finish")
         return out
+
+    def exactness(self):
+        """(lost, saturated) of the last frame: staged sums that reached 2^24 before they were
+        moved into the integer buckets, and uint32 sums pinned at UINT_MAX."""
+        a, b = C.c_uint64(), C.c_uint64()
+        f = self.lib._dll.f3b_exactness
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        self._ck(f(self.ptr, C.byref(a), C.byref(b)), "exactness")
+        return a.value, b.value
 
     def stage_stats(self, stage):
         ms, n = C.c_double(), C.c_uint64()

@@ -21,6 +21,13 @@ struct DevBuf {
 };
 
 #define F3B_SIDE_STREAMS 3
+/* device counters (unsigned long long each): [0] bad values, [1] fullest bucket's count,
+ * [2] lanes adding / [3] lanes sharing a bucket in the aggregation probe, [4] the probe's own
+ * bad values (discarded), [5] spare, [6] staged values that reached 2^24 (exactness lost),
+ * [7] entries of the saturation list, [8] the sweepers' ticket counter (low 32 bits) */
+#define F3B_NCOUNTERS 16
+#define F3B_CTR_LOST 6
+#define F3B_CTR_TICKET 8
 
 struct f3b_ctx {
    int device = 0;
@@ -33,7 +40,13 @@ struct f3b_ctx {
    F3HistLayout lay = {0, 0, 0}; /* histogram addressing */
    size_t hist_elems = 0;        /* buckets in a histogram plane */
    int count_channel = 1;
-   DevBuf hist_color, hist_count, accum, image;
+   DevBuf hist_color, hist_count, accum, image; /* hist_*: the float STAGING copies */
+   DevBuf exact_color, exact_count, sat_list;   /* the buckets proper (f3b_internal.h) */
+   DevBuf xfer;                 /* staging of f3b_hist_upload/download_u32 (kept across calls) */
+   int f64 = 0;                 /* bits 64: double buckets */
+   bool staging_dirty = true;   /* staging copies may hold something (cleared by the merge) */
+   bool swept = false;          /* sweepers have run since the last hist_clear */
+   uint64_t lost_exact = 0, saturated = 0; /* as of the last f3b_badvals */
    DevBuf blobs, jobs, groups, de_coefs, de_radius, filter, de_kidx, de_tiles;
    std::vector<float> de_coefs_host;    /* what de_coefs / de_radius / filter hold on the device */
    std::vector<uint8_t> de_radius_host;
@@ -151,13 +164,13 @@ int f3b_ctx_create(int device, f3b_ctx **out) {
    }
    ctx->sms = prop.multiProcessorCount;
    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-       cudaMalloc(&ctx->d_badvals, 6 * sizeof(unsigned long long)) != cudaSuccess) {
+       cudaMalloc(&ctx->d_badvals, F3B_NCOUNTERS * sizeof(unsigned long long)) != cudaSuccess) {
       fprintf(stderr, "flam3_b200: context setup failed: %s\n",
               cudaGetErrorString(cudaGetLastError()));
       delete ctx;
       return 1;
    }
-   cudaMemsetAsync(ctx->d_badvals, 0, 6 * sizeof(unsigned long long), ctx->stream);
+   cudaMemsetAsync(ctx->d_badvals, 0, F3B_NCOUNTERS * sizeof(unsigned long long), ctx->stream);
    ctx->iter_blocks_per_sm = f3b_iterate_max_blocks_per_sm(16 * 1024);
    if (ctx->iter_blocks_per_sm <= 0) ctx->iter_blocks_per_sm = 1;
    *out = ctx;
@@ -168,7 +181,8 @@ void f3b_ctx_destroy(f3b_ctx *ctx) {
    if (!ctx) return;
    cudaSetDevice(ctx->device);
    cudaStreamSynchronize(ctx->stream);
-   DevBuf *bufs[] = {&ctx->hist_color, &ctx->hist_count, &ctx->accum,    &ctx->image,
+   DevBuf *bufs[] = {&ctx->exact_color, &ctx->exact_count, &ctx->sat_list, &ctx->xfer,
+                     &ctx->hist_color, &ctx->hist_count, &ctx->accum,    &ctx->image,
                      &ctx->blobs,      &ctx->jobs,       &ctx->groups,   &ctx->de_coefs,
                      &ctx->de_radius,  &ctx->filter,     &ctx->de_kidx,  &ctx->de_tiles};
    for (DevBuf *b : bufs)
@@ -235,35 +249,58 @@ static F3HistLayout hist_layout_for(int width, int height, int count_channel, si
    return L;
 }
 
-int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel) {
+int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel, int bits) {
    if (!ctx) return 1;
    if (width <= 0 || height <= 0) return fail(ctx, "bad buffer size %dx%d", width, height);
+   if (bits != 32 && bits != 33 && bits != 64) return fail(ctx, "bits must be 32, 33 or 64, not %d", bits);
    CK(cudaSetDevice(ctx->device));
    const size_t n = (size_t)width * height;
    size_t nh = 0;
    const F3HistLayout lay = hist_layout_for(width, height, count_channel, &nh);
    const size_t nalloc = lay.replica_stride * lay.replicas;
+   const int f64 = bits == 64;
+   const void *before[2] = {ctx->hist_color.p, ctx->hist_count.p};
    if (ensure(ctx, ctx->hist_color, nalloc * sizeof(float4))) return 1;
    if (ensure(ctx, ctx->accum, n * sizeof(float4))) return 1;
    if (count_channel && ensure(ctx, ctx->hist_count, nalloc * sizeof(float))) return 1;
+   if (ensure(ctx, ctx->exact_color, nh * (f64 ? sizeof(double4) : sizeof(uint4)))) return 1;
+   if (count_channel && ensure(ctx, ctx->exact_count, nh * (f64 ? sizeof(double) : sizeof(uint32_t)))) return 1;
+   if (ensure(ctx, ctx->sat_list, F3B_SAT_LIST_CAP * sizeof(uint32_t))) return 1;
+   /* the staging copies are zero between a merge and the next launch: clear them only when
+    * they are new, were left behind by a failed frame, or the layout changed under them */
+   if (before[0] != ctx->hist_color.p || (count_channel && before[1] != ctx->hist_count.p) ||
+       ctx->lay.replica_stride != lay.replica_stride || ctx->lay.replicas != lay.replicas ||
+       ctx->count_channel != (count_channel ? 1 : 0))
+      ctx->staging_dirty = true;
    ctx->lay = lay;
    ctx->hist_elems = nh;
    ctx->width = width;
    ctx->height = height;
    ctx->count_channel = count_channel ? 1 : 0;
+   ctx->f64 = f64;
    ctx->hot_total = 0.0;
    ctx->hot_measured = false;
    ctx->hot_from_merge = false;
-   CK(cudaMemsetAsync(ctx->d_badvals, 0, 6 * sizeof(unsigned long long), ctx->stream));
+   /* everything but the sweepers' ticket counter, which just keeps counting */
+   CK(cudaMemsetAsync(ctx->d_badvals, 0, F3B_CTR_TICKET * sizeof(unsigned long long), ctx->stream));
+   if (ctx->staging_dirty) {
+      CK(cudaMemsetAsync(ctx->hist_color.p, 0, nalloc * sizeof(float4), ctx->stream));
+      if (count_channel) CK(cudaMemsetAsync(ctx->hist_count.p, 0, nalloc * sizeof(float), ctx->stream));
+      ctx->staging_dirty = false;
+   }
    if (f3b_hist_clear(ctx)) return 1;
    return f3b_accum_clear(ctx);
 }
 
 int f3b_hist_clear(f3b_ctx *ctx) {
-   const size_t n = ctx->lay.replica_stride * ctx->lay.replicas;
+   const size_t n = ctx->hist_elems;
    CK(cudaSetDevice(ctx->device));
-   CK(cudaMemsetAsync(ctx->hist_color.p, 0, n * sizeof(float4), ctx->stream));
-   if (ctx->count_channel) CK(cudaMemsetAsync(ctx->hist_count.p, 0, n * sizeof(float), ctx->stream));
+   CK(cudaMemsetAsync(ctx->exact_color.p, 0, n * (ctx->f64 ? sizeof(double4) : sizeof(uint4)), ctx->stream));
+   if (ctx->count_channel)
+      CK(cudaMemsetAsync(ctx->exact_count.p, 0, n * (ctx->f64 ? sizeof(double) : sizeof(uint32_t)), ctx->stream));
+   if (ctx->swept) /* the saturation list belongs to the histogram being discarded */
+      CK(cudaMemsetAsync(ctx->d_badvals + F3B_CTR_LOST + 1, 0, sizeof(unsigned long long), ctx->stream));
+   ctx->swept = false;
    return 0;
 }
 
@@ -368,7 +405,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
                 uint64_t seed, int floor_adds, uint32_t max_chain_len, int rank, int nranks) {
    if (!ctx || !blobs || !jobs || n_jobs <= 0) return fail(ctx, "f3b_iterate: bad arguments");
    if (nranks <= 0 || rank < 0 || rank >= nranks) return fail(ctx, "f3b_iterate: bad rank");
-   if (!ctx->hist_color.p) return fail(ctx, "f3b_iterate: f3b_frame_begin not called");
+   if (!ctx->hist_color.p || !ctx->exact_color.p) return fail(ctx, "f3b_iterate: f3b_frame_begin not called");
    CK(cudaSetDevice(ctx->device));
 
    /* plan chains and groups */
@@ -446,9 +483,34 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    P.floor_adds = floor_adds;
    P.seed = seed;
    P.badvals = ctx->d_badvals;
+   P.exact_color = ctx->exact_color.p;
+   P.exact_count = ctx->count_channel ? ctx->exact_count.p : nullptr;
+   P.exact_f64 = (uint32_t)ctx->f64;
+   P.sweep_ticket = (unsigned int *)(ctx->d_badvals + F3B_CTR_TICKET);
+   P.exact_flags = ctx->d_badvals + F3B_CTR_LOST;
+   P.sat_list = (uint32_t *)ctx->sat_list.p;
+   P.chain_threads = (uint32_t)group_size;
+   {
+      /* Sweepers (f3b_iterate.cu) run unless no staged sum can reach the carry threshold at
+       * all. Their pace: flat out, unless the share of the fullest bucket is known from the
+       * previous frame of this genome; then a pass over the staging planes may take half the
+       * time that bucket needs to grow from the carry threshold to 2^24 at the highest
+       * iteration rate the GPU reaches. F3B_SWEEP=0/1, F3B_SWEEP_NS override. */
+      uint64_t it = 0;
+      for (int j = 0; j < n_jobs; j++) it += jobs[j].n_iters;
+      double carry = ctx->f64 ? (double)F3B_CARRY_F64 : (double)F3B_CARRY_U32;
+      const char *ce = getenv("F3B_CARRY"); /* test hook: a lower threshold exercises the carries */
+      if (ce && atof(ce) >= 1.0 && atof(ce) < carry) carry = atof(ce);
+      P.carry_thresh = (float)carry;
+      P.sweep_on = ((double)it / nranks) * 255.0 >= carry ? 1u : 0u;
+      P.sweep_sleep_ns = 0;
+      const char *e = getenv("F3B_SWEEP");
+      if (e) P.sweep_on = atoi(e) ? 1u : 0u;
+   }
 
    const int bps = f3b_iterate_blocks_per_sm(group_size, max_blob);
    if (bps <= 0) return fail(ctx, "f3b_iterate: kernel does not fit with %zu bytes of shared memory", max_blob);
+   ctx->staging_dirty = true;
 
    /* One launch per `cap` temporal samples (their warp-uniform camera and chooser constants
     * travel through the constant cache); a still frame is one launch. */
@@ -509,6 +571,16 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
             const uint32_t cnt = cum[q < nstd ? q : (nstd ? nstd - 1 : 0)];
             pk[q] = (cnt >= 16384u ? 0xfffc0000u : (cnt << 18)) | off;
          }
+         /* k = 16383 compares below no entry (a count of 16384 saturates to the same 14 bits)
+          * and falls through to the last slot: that slot must be the FIRST xform whose
+          * cumulative count reaches 16384, which is what the reference's table holds at
+          * [16383] when trailing xforms have zero weight (flam3.c:196-216). Every smaller k
+          * already stops at or before that xform's own slot. */
+         for (uint32_t q = 0; q < 4 && q < nstd; q++)
+            if (cum[q] >= 16384u) {
+               pk[3] = 0xfffc0000u | (w[F3B_H_XF_BASE] + q * w[F3B_H_XF_STRIDE]);
+               break;
+            }
          c.pick = make_uint4(pk[0], pk[1], pk[2], pk[3]);
          if ((hf & (F3B_HF_CHOOSER_CONST | F3B_HF_PLOT_READY | F3B_HF_FINAL | F3B_HF_XAOS |
                     F3B_HF_PAL_LINEAR)) != (F3B_HF_CHOOSER_CONST | F3B_HF_PLOT_READY))
@@ -542,6 +614,19 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          ctx->hot_iters = total_iters;
          ctx->hot_total = 255.0 * (double)total_iters; /* of one batch, like the bucket maximum */
          const bool known = ctx->hot_share >= 0.0 && ctx->hot_share_signature == sig;
+         if (P.sweep_on) {
+            const char *ns = getenv("F3B_SWEEP_NS");
+            if (ns) P.sweep_sleep_ns = (uint32_t)atoi(ns);
+            else if (known && !ctx->f64) {
+               const double share = ctx->hot_share > 1e-7 ? ctx->hot_share : 1e-7;
+               const double growth = share * 2.2e11 * 255.0 / (double)ctx->lay.replicas; /* per second */
+               const double allowed_us = 0.5e6 * ((double)F3B_EXACT_LIMIT - (double)F3B_CARRY_U32) / growth;
+               const double tickets = (double)(ctx->lay.replica_stride * ctx->lay.replicas) / F3B_SWEEP_ENTRIES;
+               const double per_sweeper = tickets / (double)(grid > 0 ? grid : 1);
+               const double pause_us = allowed_us / (per_sweeper > 1.0 ? per_sweeper : 1.0) - 1.5;
+               P.sweep_sleep_ns = pause_us <= 0.0 ? 0u : (pause_us > 100.0 ? 100000u : (uint32_t)(pause_us * 1e3));
+            }
+         }
          if (e) aggregate = atoi(e) != 0;
          /* one bucket with share s of the hits gives a lane a duplicate among its 31 peers with
           * probability ~31 s: the probe's 1/8 criterion corresponds to s ~ 0.4% */
@@ -550,6 +635,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          else if (total_iters / (uint64_t)nranks >= 50000000ull) {
             F3IterateParams Q = P;
             Q.probe_iters = 64;
+            Q.sweep_on = 0;
             Q.badvals = ctx->d_badvals + 4;
             int pgrid = ctx->sms < grid ? ctx->sms : grid;
             const uint64_t lim = (uint64_t)P.group_begin + (uint64_t)pgrid * (uint64_t)nranks;
@@ -576,17 +662,27 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          CK(cudaEventRecord(ctx->join_ev[i], ctx->side[i]));
          CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
       }
-   /* the merge of the copies sees this rank's whole histogram (1/nranks of the hits): it also
-    * records the fullest bucket */
-   const int nm = f3b_launch_hist_merge((float4 *)ctx->hist_color.p,
-                                        ctx->count_channel ? (float *)ctx->hist_count.p : nullptr,
-                                        ctx->hist_elems, ctx->lay, (int *)(ctx->d_badvals + 1), ctx->stream);
-   if (nm > 0) {
-      ctx->hot_measured = true;
-      ctx->hot_from_merge = true;
-      ctx->hot_total = 255.0 * (double)ctx->hot_iters / (double)nranks;
-   }
+   /* staging copies -> exact buckets; the merge sees this rank's whole histogram (1/nranks of
+    * the hits) and also records the fullest bucket */
+   F3MergeParams M;
+   M.color = (float4 *)ctx->hist_color.p;
+   M.count = ctx->count_channel ? (float *)ctx->hist_count.p : nullptr;
+   M.exact_color = ctx->exact_color.p;
+   M.exact_count = ctx->count_channel ? ctx->exact_count.p : nullptr;
+   M.f64 = ctx->f64;
+   M.elems = ctx->hist_elems;
+   M.lay = ctx->lay;
+   M.hot_max = (unsigned int *)(ctx->d_badvals + 1);
+   M.exact_flags = ctx->d_badvals + F3B_CTR_LOST;
+   M.sat_list = (const uint32_t *)ctx->sat_list.p;
+   if (P.sweep_on) ctx->swept = true;
+   M.sat_check = ctx->swept ? 1 : 0;
+   const int nm = f3b_launch_hist_merge(M, ctx->stream);
    if (nm < 0) return fail(ctx, "histogram merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+   ctx->staging_dirty = false;
+   ctx->hot_measured = true;
+   ctx->hot_from_merge = true;
+   ctx->hot_total = 255.0 * (double)ctx->hot_iters / (double)nranks;
    launches += nm;
    return stage_end(ctx, launches);
 }
@@ -624,20 +720,26 @@ int f3b_debug_apply_xform(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int
 }
 
 int f3b_badvals(f3b_ctx *ctx, double *out) {
-   unsigned long long v[2] = {0, 0};
+   unsigned long long v[F3B_CTR_TICKET] = {0};
    CK(cudaSetDevice(ctx->device));
    CK(cudaMemcpyAsync(v, ctx->d_badvals, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
    ctx->d2h_bytes += sizeof(v);
    CK(cudaStreamSynchronize(ctx->stream));
    *out = (double)v[0];
+   ctx->lost_exact = v[F3B_CTR_LOST];
+   ctx->saturated = v[F3B_CTR_LOST + 1];
    /* end of frame: remember how concentrated this genome's histogram was (see f3b_iterate) */
    if (ctx->hot_total > 0.0 && ctx->hot_measured) {
-      float mx;
-      const uint32_t bits = (uint32_t)v[1];
-      memcpy(&mx, &bits, sizeof(mx));
-      ctx->hot_share = (double)mx / ctx->hot_total;
+      ctx->hot_share = (double)(uint32_t)v[1] / ctx->hot_total;
       ctx->hot_share_signature = ctx->hot_signature;
    }
+   return 0;
+}
+
+int f3b_exactness(f3b_ctx *ctx, uint64_t *lost, uint64_t *saturated) {
+   if (!ctx) return 1;
+   if (lost) *lost = ctx->lost_exact;
+   if (saturated) *saturated = ctx->saturated;
    return 0;
 }
 
@@ -659,12 +761,14 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
 
    F3DensityParams P;
    memset(&P, 0, sizeof(P));
-   P.hist_color = (const float4 *)ctx->hist_color.p;
-   P.hist_count = ctx->count_channel ? (const float *)ctx->hist_count.p : nullptr;
+   P.hist.color = ctx->exact_color.p;
+   P.hist.count = ctx->count_channel ? ctx->exact_count.p : nullptr;
+   P.hist.f64 = ctx->f64;
+   P.hist.pitch = ctx->lay.pitch;
+   P.hist.row0 = 0;
    P.accum = (float4 *)ctx->accum.p;
    P.width = ctx->width;
    P.height = ctx->height;
-   P.lay = ctx->lay;
    P.row_begin = row0;
    P.row_end = row1;
    P.oversample = d->oversample;
@@ -729,7 +833,7 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
       P.tile_maxrad = (int *)ctx->de_tiles.p;
       /* whole-frame passes only (a strip sees a part of the histogram), and only when the
        * merge of the histogram copies has not measured it already */
-      P.hot_max = (!ctx->hot_from_merge && row0 == 0 && row1 == ctx->height) ? (int *)(ctx->d_badvals + 1) : nullptr;
+      P.hot_max = (!ctx->hot_from_merge && row0 == 0 && row1 == ctx->height) ? (unsigned int *)(ctx->d_badvals + 1) : nullptr;
       if (P.hot_max) ctx->hot_measured = true;
    }
    if (ctx->accum_zero_pending && P.n_kernels > 0 && row0 == 0 && row1 == ctx->height) {
@@ -843,37 +947,31 @@ int f3b_image_download(f3b_ctx *ctx, const f3b_final_desc *d, void *out, size_t 
 }
 
 int f3b_hist_upload_u32(f3b_ctx *ctx, const uint32_t *buckets5) {
-   if (!ctx || !ctx->hist_color.p) return 1;
+   if (!ctx || !ctx->exact_color.p) return 1;
    CK(cudaSetDevice(ctx->device));
    const size_t n = (size_t)ctx->width * ctx->height;
-   uint32_t *tmp = nullptr;
-   CK(cudaMalloc(&tmp, n * 5 * sizeof(uint32_t)));
-   cudaError_t e = cudaMemcpyAsync(tmp, buckets5, n * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                                   ctx->stream);
-   if (e == cudaSuccess)
-      f3b_launch_hist_from_u32(tmp, (float4 *)ctx->hist_color.p,
-                               ctx->count_channel ? (float *)ctx->hist_count.p : nullptr, ctx->width,
-                               ctx->height, ctx->lay, ctx->stream);
-   e = cudaStreamSynchronize(ctx->stream);
-   cudaFree(tmp);
-   if (e != cudaSuccess) return fail(ctx, "hist upload failed: %s", cudaGetErrorString(e));
+   if (ensure(ctx, ctx->xfer, n * 5 * sizeof(uint32_t))) return 1;
+   CK(cudaMemcpyAsync(ctx->xfer.p, buckets5, n * 5 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+   ctx->h2d_bytes += n * 5 * sizeof(uint32_t);
+   if (!f3b_launch_hist_from_u32((const uint32_t *)ctx->xfer.p, ctx->exact_color.p,
+                                 ctx->count_channel ? ctx->exact_count.p : nullptr, ctx->f64, ctx->width,
+                                 ctx->height, ctx->lay.pitch, ctx->stream))
+      return fail(ctx, "hist upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+   CK(cudaStreamSynchronize(ctx->stream)); /* the caller's buffer is free again */
    return 0;
 }
 
 int f3b_hist_download_u32(f3b_ctx *ctx, uint32_t *buckets5) {
-   if (!ctx || !ctx->hist_color.p) return 1;
+   if (!ctx || !ctx->exact_color.p) return 1;
    CK(cudaSetDevice(ctx->device));
    const size_t n = (size_t)ctx->width * ctx->height;
-   uint32_t *tmp = nullptr;
-   CK(cudaMalloc(&tmp, n * 5 * sizeof(uint32_t)));
-   f3b_launch_hist_to_u32((const float4 *)ctx->hist_color.p,
-                          ctx->count_channel ? (const float *)ctx->hist_count.p : nullptr, tmp,
-                          ctx->width, ctx->height, ctx->lay, ctx->stream);
-   cudaError_t e = cudaMemcpyAsync(buckets5, tmp, n * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                   ctx->stream);
-   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-   cudaFree(tmp);
-   if (e != cudaSuccess) return fail(ctx, "hist download failed: %s", cudaGetErrorString(e));
+   if (ensure(ctx, ctx->xfer, n * 5 * sizeof(uint32_t))) return 1;
+   if (!f3b_launch_hist_to_u32(ctx->exact_color.p, ctx->count_channel ? ctx->exact_count.p : nullptr, ctx->f64,
+                               (uint32_t *)ctx->xfer.p, ctx->width, ctx->height, ctx->lay.pitch, ctx->stream))
+      return fail(ctx, "hist download failed: %s", cudaGetErrorString(cudaGetLastError()));
+   CK(cudaMemcpyAsync(buckets5, ctx->xfer.p, n * 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+   ctx->d2h_bytes += n * 5 * sizeof(uint32_t);
+   CK(cudaStreamSynchronize(ctx->stream));
    return 0;
 }
 
@@ -897,10 +995,10 @@ int f3b_accum_download(f3b_ctx *ctx, float *acc4) {
    return 0;
 }
 
-void *f3b_hist_color_ptr(f3b_ctx *ctx) { return ctx ? ctx->hist_color.p : nullptr; }
+void *f3b_hist_color_ptr(f3b_ctx *ctx) { return ctx ? ctx->exact_color.p : nullptr; }
 size_t f3b_hist_elems(f3b_ctx *ctx) { return ctx ? ctx->hist_elems : 0; }
 void *f3b_hist_count_ptr(f3b_ctx *ctx) {
-   return (ctx && ctx->count_channel) ? ctx->hist_count.p : nullptr;
+   return (ctx && ctx->count_channel) ? ctx->exact_count.p : nullptr;
 }
 void *f3b_accum_ptr(f3b_ctx *ctx) {
    if (!ctx || accum_materialize(ctx)) return nullptr;

@@ -28,6 +28,49 @@ __device__ __forceinline__ size_t f3b_hist_index(const F3HistLayout &L, int x, i
 }
 #endif
 
+/* The buckets proper (what the post-pass, the exchange between GPUs and the tests see) are
+ * EXACT: uint32[4] colour sums + uint32 count per bucket for bits 32/33 (the reference's
+ * `bucket_int`, flam3.c:3772, 3824; adds are truncated and saturate at UINT_MAX,
+ * flam3.c:3838-3854), double[4] + double for bits 64 (`bucket_double`, flam3.c:3724). The
+ * chaos game does not add into them directly: it adds into float4 staging replicas with one
+ * vector reduction per hit, which are exact only below 2^24, so a sweeper warp in every CTA
+ * keeps moving whatever has grown past F3B_CARRY_* out of the staging planes into the exact
+ * planes while the walkers run, and f3b_hist_merge_kernel moves the rest (f3b_iterate.cu). */
+struct F3HistView {
+   const void *color; /* uint4[...] or double[4][...] */
+   const void *count; /* uint32[...] or double[...]; nullptr: colour channel 3 is the count */
+   int f64;           /* bits 64 */
+   int pitch;         /* buckets per row */
+   int row0;          /* bucket row held at element 0 (strips of a frame reduced over GPUs) */
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ size_t f3b_view_index(const F3HistView &V, int x, int y) {
+   return (size_t)x + (size_t)V.pitch * (size_t)(y - V.row0);
+}
+__device__ __forceinline__ float4 f3b_view_color(const F3HistView &V, size_t i) {
+   if (V.f64) {
+      const double4 *p = reinterpret_cast<const double4 *>(V.color);
+      const double4 d = p[i];
+      return make_float4((float)d.x, (float)d.y, (float)d.z, (float)d.w);
+   }
+   const uint4 u = reinterpret_cast<const uint4 *>(V.color)[i];
+   return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+}
+__device__ __forceinline__ float f3b_view_count(const F3HistView &V, size_t i) {
+   if (V.f64) {
+      if (V.count) return (float)reinterpret_cast<const double *>(V.count)[i];
+      return (float)reinterpret_cast<const double4 *>(V.color)[i].w;
+   }
+   if (V.count) return (float)reinterpret_cast<const uint32_t *>(V.count)[i];
+   return (float)reinterpret_cast<const uint4 *>(V.color)[i].w;
+}
+#endif
+#define F3B_CARRY_U32 4194304.0f /* 2^22: staged integer sums are moved out at this size ... */
+#define F3B_EXACT_LIMIT 16777216.0f /* ... and must never reach 2^24 */
+#define F3B_CARRY_F64 262144.0f  /* 2^18: bits 64, keeps the float rounding of an add <= 2^-6 */
+#define F3B_SWEEP_ENTRIES 128u   /* staging entries a sweeper warp examines per ticket */
+#define F3B_SAT_LIST_CAP 65536u
+
 #define F3B_CHAINS_PER_GROUP 256 /* largest chain group = threads per block of the chaos-game
                                     kernel; batches with few chains per temporal sample use
                                     smaller groups (32..256) so that more of them are resident */
@@ -70,6 +113,18 @@ struct F3IterateParams {
    int floor_adds;               /* bits 32/33: add floor(value) like the integer buckets */
    uint64_t seed;
    unsigned long long *badvals;  /* device counter */
+   /* exact planes and the sweeper warp (threads >= chain_threads of every CTA) */
+   void *exact_color;            /* uint4[elems] or double4[elems] */
+   void *exact_count;            /* uint32[elems] or double[elems]; nullptr without a count plane */
+   uint32_t chain_threads;       /* walkers per CTA = chains per group */
+   uint32_t sweep_on;            /* blockDim.x == chain_threads + 32 */
+   uint32_t sweep_sleep_ns;      /* pause between two tickets of a sweeper warp */
+   uint32_t exact_f64;
+   float carry_thresh;           /* F3B_CARRY_U32 / F3B_CARRY_F64 (F3B_CARRY lowers it, for tests) */
+   unsigned int *sweep_ticket;   /* device: next segment of the staging planes to examine */
+   unsigned long long *exact_flags; /* device: [0] staged values seen at >= 2^24 (exactness
+                                       lost), [1] entries in sat_list */
+   uint32_t *sat_list;           /* device: bucket * 8 + channel of exact sums that wrapped */
    /* probe launch (AGG kernels only): every chain stores at most probe_iters iterations,
     * nothing is added to the histogram, probe_counts[0] += lanes that reached an add,
     * probe_counts[1] += those that shared their bucket with another lane of the warp */
@@ -86,18 +141,28 @@ int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_co
 int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes);
 int f3b_iterate_const_capacity(void);
 int f3b_iterate_max_blocks_per_sm(size_t smem_bytes);
-/* copy 0 += copies 1..replicas-1 of the colour (and count) planes */
-int f3b_launch_hist_merge(float4 *color, float *count, size_t elems, F3HistLayout lay, int *hot_max,
-                          cudaStream_t stream);
+/* exact planes += all staging copies (saturating for the integer buckets); the staging
+ * copies are left zeroed. hot_max receives the fullest bucket's count (uint32, atomicMax). */
+struct F3MergeParams {
+   float4 *color;
+   float *count; /* nullptr without a count plane */
+   void *exact_color, *exact_count;
+   int f64;
+   size_t elems;
+   F3HistLayout lay;
+   unsigned int *hot_max;
+   unsigned long long *exact_flags;
+   const uint32_t *sat_list;
+   int sat_check; /* sweepers ran: uint32 sums may have wrapped */
+};
+int f3b_launch_hist_merge(const F3MergeParams &m, cudaStream_t stream);
 int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_index, const float *in,
                            int n, float *out, uint64_t seed, cudaStream_t stream);
 
 struct F3DensityParams {
-   const float4 *hist_color;
-   const float *hist_count; /* == nullptr -> use hist_color[].w as the count channel */
+   F3HistView hist;           /* the exact buckets */
    float4 *accum;
-   int width, height;
-   F3HistLayout lay;          /* histogram addressing; accum / de_kidx are plain [height][width] */
+   int width, height;         /* accum / de_kidx are plain [height][width] */
    int row_begin, row_end;    /* target bucket rows written by this launch */
    int oversample;
    float k1, k2;
@@ -112,7 +177,7 @@ struct F3DensityParams {
    uint16_t *de_kidx;         /* [height*width] kernel index per bucket, 0xffff = not a source */
    int *tile_maxrad;          /* [tiles_y*tiles_x] largest radius >= 1 in each 32x32 tile */
    int overwrite_accum;       /* first batch of a frame: write the accumulators, do not add */
-   int *hot_max;              /* device: max over buckets of the count plane, as float bits */
+   unsigned int *hot_max;     /* device: max over buckets of the count plane */
    /* filled by f3b_launch_density */
    int class_row_begin, class_row_end; /* rows classified: the target rows +- max_radius */
    int class_tile_y0, class_tile_y1, gather_tile_y0;
@@ -133,9 +198,10 @@ struct F3FinalParams {
 };
 int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream);
 
-int f3b_launch_hist_from_u32(const uint32_t *src5, float4 *color, float *count, int width,
-                             int height, F3HistLayout lay, cudaStream_t stream);
-int f3b_launch_hist_to_u32(const float4 *color, const float *count, uint32_t *dst5, int width,
-                           int height, F3HistLayout lay, cudaStream_t stream);
+/* reference bucket layout uint32[5] per bucket <-> the exact planes */
+int f3b_launch_hist_from_u32(const uint32_t *src5, void *exact_color, void *exact_count, int f64,
+                             int width, int height, int pitch, cudaStream_t stream);
+int f3b_launch_hist_to_u32(const void *exact_color, const void *exact_count, int f64, uint32_t *dst5,
+                           int width, int height, int pitch, cudaStream_t stream);
 
 #endif

@@ -93,6 +93,101 @@ __device__ __noinline__ bool f3b_bump_aggregate(unsigned long long bidx, float4 
    return true;
 }
 
+/* ---- the sweeper warp: exact buckets behind float staging planes -------------------- */
+/* A float sum of integers is exact only below 2^24 (65 793 hits of 255), and a 1080p
+ * quality-2000 frame puts 8e6 hits into its fullest bucket. So the float4 planes the walkers
+ * add into are only a STAGING area: the last warp of every CTA runs no chains but keeps
+ * walking over the staging planes (all copies, segment after segment from a global ticket
+ * counter, so the live sweepers of a launch always cover everything), and whatever has
+ * grown to F3B_CARRY_* is moved into the exact planes: an atomic exchange with zero takes a
+ * channel out of the staging bucket (what comes back is an exact integer below 2^24 and
+ * exactly what left, whatever adds land in between), an integer atomic adds it to the
+ * uint32 bucket. A uint32 sum that wraps is recorded and pinned to UINT_MAX
+ * after the merge, which is the reference's saturation (flam3.c:3838-3854). A staged value
+ * seen at >= 2^24 means the sweep came too late: counted in exact_flags[0], reported by
+ * f3b_exactness. Costs no instruction in the walkers' loop. */
+__device__ __forceinline__ float4 f3b_ld_staged4(const float4 *p) {
+   float4 v;
+   asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                : "l"(p));
+   return v;
+}
+__device__ __forceinline__ float f3b_ld_staged1(const float *p) {
+   float v;
+   asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+   return v;
+}
+__device__ __noinline__ void f3b_carry_channel(const F3IterateParams &P, size_t bucket, int ch, float v) {
+   if (v == 0.0f) return;
+   if (P.exact_f64) {
+      double *d = ch < 4 ? reinterpret_cast<double *>(P.exact_color) + bucket * 4 + ch
+                         : reinterpret_cast<double *>(P.exact_count) + bucket;
+      atomicAdd(d, (double)v);
+      return;
+   }
+   unsigned int *u = ch < 4 ? reinterpret_cast<unsigned int *>(P.exact_color) + bucket * 4 + ch
+                            : reinterpret_cast<unsigned int *>(P.exact_count) + bucket;
+   const unsigned int add = (unsigned int)v; /* integer valued, >= 0 */
+   const unsigned int old = atomicAdd(u, add);
+   if (old + add < old) { /* wrapped: saturate after the merge */
+      const unsigned long long slot = atomicAdd(P.exact_flags + 1, 1ull);
+      if (slot < F3B_SAT_LIST_CAP) P.sat_list[slot] = (uint32_t)(bucket * 8 + (size_t)ch);
+   }
+}
+__device__ __noinline__ void f3b_sweeper(const F3IterateParams &P, volatile int *s_done) {
+   const unsigned lane = threadIdx.x & 31u;
+   const size_t n_entries = P.lay.replica_stride * P.lay.replicas;
+   const unsigned nseg = (unsigned)((n_entries + F3B_SWEEP_ENTRIES - 1) / F3B_SWEEP_ENTRIES);
+   const float thr = P.carry_thresh;
+   constexpr int U = F3B_SWEEP_ENTRIES / 32;
+   while (!*s_done) {
+      unsigned t = 0;
+      if (lane == 0) t = atomicAdd(P.sweep_ticket, 1u);
+      t = __shfl_sync(0xffffffffu, t, 0);
+      const size_t base = (size_t)(t % nseg) * F3B_SWEEP_ENTRIES;
+      float4 v[U];
+      float c[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+         const size_t e = base + (size_t)u * 32 + lane;
+         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+         c[u] = 0.f;
+         if (e < n_entries) {
+            v[u] = f3b_ld_staged4(P.hist_color + e);
+            if (P.hist_count) c[u] = f3b_ld_staged1(P.hist_count + e);
+         }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+         const size_t e = base + (size_t)u * 32 + lane;
+         const float m = fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+         const size_t bucket = e % P.lay.replica_stride;
+         if (m >= thr) {
+            /* take the channels out one by one with an exchange: what comes back is exactly
+             * what left the staging bucket, whatever lands there meanwhile */
+            float *f = reinterpret_cast<float *>(P.hist_color + e);
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+               const float take = atomicExch(f + ch, 0.0f);
+               if (!P.exact_f64 && fabsf(take) >= F3B_EXACT_LIMIT) atomicAdd(P.exact_flags, 1ull);
+               f3b_carry_channel(P, bucket, ch, take);
+            }
+         }
+         if (fabsf(c[u]) >= thr) {
+            const float take = atomicExch(P.hist_count + e, 0.0f);
+            if (!P.exact_f64 && fabsf(take) >= F3B_EXACT_LIMIT) atomicAdd(P.exact_flags, 1ull);
+            f3b_carry_channel(P, bucket, 4, take);
+         }
+      }
+      if (P.sweep_sleep_ns) __nanosleep(P.sweep_sleep_ns);
+   }
+}
+/* barrier among the walkers only (the sweeper warp never joins it) */
+__device__ __forceinline__ void f3b_chain_barrier(uint32_t nthreads) {
+   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
 /* The final xform (flam3.c:280-287) is applied out of line: few genomes have one, and a
  * second inlined copy of the variation interpreter would double the hot loop's code. */
 __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, float px, float py,
@@ -124,11 +219,21 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
  * step palette and fully visible xforms (the classic flame): the flag tests fold away and
  * the xform pick is three compares on a packed table from the constant bank. */
 template <bool COUNT, bool SIMPLE, bool AGG>
-__global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
+__global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
    extern __shared__ __align__(16) uint32_t smem[];
    const float *sf = reinterpret_cast<const float *>(smem);
+   __shared__ int s_done;
 
    const uint32_t tid = threadIdx.x;
+   const uint32_t nct = P.chain_threads; /* walkers; one more warp sweeps when P.sweep_on */
+   if (P.sweep_on) {
+      if (tid == 0) s_done = 0;
+      __syncthreads();
+      if (tid >= nct) {
+         f3b_sweeper(P, &s_done);
+         return;
+      }
+   }
    const size_t rep_off = (size_t)(blockIdx.x % P.lay.replicas) * P.lay.replica_stride;
    uint32_t loaded_job = 0xffffffffu;
    unsigned int bad = 0;
@@ -145,15 +250,15 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
       const f3b_sample_job job = P.jobs[ji];
 
       if (ji != loaded_job) {
-         __syncthreads(); /* everyone is done with the previous blob */
+         f3b_chain_barrier(nct); /* everyone is done with the previous blob */
          const uint32_t *src = reinterpret_cast<const uint32_t *>(P.blobs + job.blob_offset);
          const uint32_t words = src[F3B_H_WORDS];
-         for (uint32_t i = tid; i < words; i += blockDim.x) smem[i] = src[i];
-         __syncthreads();
+         for (uint32_t i = tid; i < words; i += nct) smem[i] = src[i];
+         f3b_chain_barrier(nct);
          loaded_job = ji;
       }
 
-      const uint32_t chain = (g - job.first_group) * blockDim.x + tid; /* blockDim.x chains per group */
+      const uint32_t chain = (g - job.first_group) * nct + tid; /* nct chains per group */
       if (chain >= job.n_chains) continue;
 
       /* stored iterations of this chain */
@@ -339,6 +444,10 @@ __global__ void __launch_bounds__(F3B_BLOCK, F3B_ITER_MIN_BLOCKS) f3b_iterate_ke
    /* fic.badvals += badcount (rect.c:408) */
    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
    if ((tid & 31u) == 0 && bad) atomicAdd(P.badvals, (unsigned long long)bad);
+   if (P.sweep_on) { /* all walkers of the CTA are through: release its sweeper warp */
+      f3b_chain_barrier(nct);
+      if (tid == 0) *(volatile int *)&s_done = 1;
+   }
 }
 
 /* One application of one xform to caller-supplied points (parity tests of the variation
@@ -392,8 +501,9 @@ int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes) {
    cudaFuncSetAttribute(f3b_iterate_kernel<false, false, true>, at, smax);
    cudaFuncSetAttribute(f3b_iterate_kernel<true, true, true>, at, smax);
    cudaFuncSetAttribute(f3b_iterate_kernel<false, true, true>, at, smax);
-   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, true>, group_size,
-                                                     smem_bytes) != cudaSuccess)
+   /* group_size counts the walkers; the CTA has one more warp (the sweeper) */
+   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, true>,
+                                                     group_size + 32, smem_bytes) != cudaSuccess)
       return 0;
    return nb;
 }
@@ -404,7 +514,9 @@ int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_co
    if (grid_blocks <= 0 || n_consts <= 0 || n_consts > F3B_PARAM_SAMPLES) return 0;
    if (group_size < 32 || group_size > F3B_BLOCK || (group_size & 31)) return 0;
    for (int i = 0; i < n_consts; i++) p.samp[i] = consts[i];
-#define F3B_LAUNCH(C, S, A) f3b_iterate_kernel<C, S, A><<<grid_blocks, group_size, smem_bytes, stream>>>(p)
+   p.chain_threads = (uint32_t)group_size;
+   const int threads = group_size + (p.sweep_on ? 32 : 0);
+#define F3B_LAUNCH(C, S, A) f3b_iterate_kernel<C, S, A><<<grid_blocks, threads, smem_bytes, stream>>>(p)
    const int which = (count_channel ? 4 : 0) | (simple ? 2 : 0) | (aggregate ? 1 : 0);
    switch (which) {
    case 0: F3B_LAUNCH(false, false, false); break;

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) f3b_logscale_kernel(const F3DensityParams
    const size_t stride = (size_t)gridDim.x * blockDim.x;
    for (; i < n; i += stride) {
       const size_t y = i / (size_t)P.width, x = i - y * (size_t)P.width;
-      const float4 c = P.hist_color[f3b_hist_index(P.lay, (int)x, (int)y)];
+      const float4 c = f3b_view_color(P.hist, f3b_view_index(P.hist, (int)x, (int)y));
       if (c.w == 0.0f) continue;
       const float ls = (P.k1 * log1pf(c.w * P.k2)) / c.w;
       float4 a = P.accum[i];
@@ -67,8 +67,7 @@ __global__ void __launch_bounds__(256) f3b_logscale_kernel(const F3DensityParams
  */
 __device__ __forceinline__ float f3b_de_count(const F3DensityParams &P, int x, int y) {
    if (x < 0 || x >= P.width || y < 0 || y >= P.height) return 0.0f;
-   const size_t gi = f3b_hist_index(P.lay, x, y);
-   return P.hist_count ? __ldg(P.hist_count + gi) : __ldg(&P.hist_color[gi].w);
+   return f3b_view_count(P.hist, f3b_view_index(P.hist, x, y));
 }
 
 __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(const F3DensityParams P) {
@@ -88,13 +87,13 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(cons
       gy[q] = tile_y * DE_TILE + threadIdx.y + q * DE_ROWS;
       live[q] = gx < P.width && gy[q] >= P.class_row_begin && gy[q] < P.class_row_end;
       c[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live[q]) c[q] = P.hist_color[f3b_hist_index(P.lay, gx, gy[q])];
+      if (live[q]) c[q] = f3b_view_color(P.hist, f3b_view_index(P.hist, gx, gy[q]));
    }
 #pragma unroll
    for (int q = 0; q < DE_PER_THREAD; q++) {
       if (!live[q]) continue;
       const size_t gi = (size_t)gx + (size_t)P.width * gy[q];
-      const float cnt = P.hist_count ? P.hist_count[f3b_hist_index(P.lay, gx, gy[q])] : c[q].w;
+      const float cnt = P.hist.count ? f3b_view_count(P.hist, f3b_view_index(P.hist, gx, gy[q])) : c[q].w;
       maxcnt = fmaxf(maxcnt, cnt);
       unsigned kidx = DE_NO_SOURCE;
       float4 self = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -141,9 +140,9 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(cons
          }
       }
    }
-   /* largest wide-kernel radius of this tile, and the fullest bucket seen (counts are
-    * non-negative floats, so their bit patterns order like integers) */
-   int my_maxcnt = __float_as_int(maxcnt);
+   /* largest wide-kernel radius of this tile, and the fullest bucket seen (as an integer:
+    * the counts are whole numbers, or close enough for bits 64) */
+   int my_maxcnt = (int)fminf(maxcnt, 2147483520.0f);
    for (int o = 16; o > 0; o >>= 1) {
       my_maxrad = max(my_maxrad, __shfl_xor_sync(0xffffffffu, my_maxrad, o));
       my_maxcnt = max(my_maxcnt, __shfl_xor_sync(0xffffffffu, my_maxcnt, o));
@@ -161,7 +160,7 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(cons
          c = max(c, s_cnt[i]);
       }
       P.tile_maxrad[(size_t)tile_y * gridDim.x + blockIdx.x] = m;
-      if (P.hot_max && c > 0) atomicMax(P.hot_max, c);
+      if (P.hot_max && c > 0) atomicMax(P.hot_max, (unsigned int)c);
    }
 }
 
@@ -208,7 +207,7 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_kernel(const 
          if (k != DE_NO_SOURCE) {
             const unsigned rad = __ldg(P.de_radius + k);
             if (rad) {
-               const float4 c = P.hist_color[f3b_hist_index(P.lay, gx, gy)];
+               const float4 c = f3b_view_color(P.hist, f3b_view_index(P.hist, gx, gy));
                const float ls = (P.k1 * log1pf(c.w * P.k2)) / c.w;
                col = make_float4(c.x * ls, c.y * ls, c.z * ls, c.w * ls);
                meta = k | (rad << 16);
@@ -267,6 +266,74 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_kernel(const 
    }
 }
 
+/* Same gather without the shared-memory staging, for kernels too wide for it: a tile plus a
+ * halo of R buckets on every side needs (32 + 2R)^2 * 20 B, which passes the 227 KB a CTA can
+ * have at R = 38 (estimator 9 at oversample 5, 20 at oversample 2, ...). The sources are then
+ * read where they lie (the index plane is 2 B per bucket and L2-resident; colours are fetched
+ * only for sources that do reach the target). Same summation order as the staged kernel, so
+ * the two give identical accumulators. */
+__global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_global_kernel(const F3DensityParams P) {
+   __shared__ int s_reach;
+   const int tiles_x = gridDim.x;
+   const int tile_y = P.gather_tile_y0 + blockIdx.y;
+   const int tid = threadIdx.y * DE_TILE + threadIdx.x;
+   if (tid == 0) s_reach = 0;
+   __syncthreads();
+   {
+      const int nt = (P.max_radius + DE_TILE - 1) / DE_TILE, span = 2 * nt + 1;
+      int m = 0;
+      for (int i = tid; i < span * span; i += DE_TILE * DE_ROWS) {
+         const int tx = (int)blockIdx.x + (i % span) - nt, ty = tile_y + (i / span) - nt;
+         if (tx >= 0 && tx < tiles_x && ty >= P.class_tile_y0 && ty < P.class_tile_y1)
+            m = max(m, P.tile_maxrad[(size_t)ty * tiles_x + tx]);
+      }
+      if (m) atomicMax(&s_reach, m);
+   }
+   __syncthreads();
+   const int R = s_reach;
+   if (R == 0) return;
+   const int gx = blockIdx.x * DE_TILE + threadIdx.x;
+   if (gx >= P.width) return;
+#pragma unroll 1
+   for (int q = 0; q < DE_PER_THREAD; q++) {
+      const int gy = tile_y * DE_TILE + threadIdx.y + q * DE_ROWS;
+      if (gy < P.row_begin || gy >= P.row_end) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool any = false;
+      for (int dy = -R; dy <= R; dy++) {
+         const int sy = gy + dy;
+         if (sy < P.class_row_begin || sy >= P.class_row_end) continue;
+         const int ady = abs(dy);
+         for (int dx = -R; dx <= R; dx++) {
+            const int sx = gx + dx;
+            if (sx < 0 || sx >= P.width) continue;
+            const unsigned k = P.de_kidx[(size_t)sx + (size_t)P.width * sy];
+            if (k == DE_NO_SOURCE) continue;
+            const int rn = (int)__ldg(P.de_radius + k);
+            const int adx = abs(dx);
+            const int hi = max(adx, ady), lo = min(adx, ady);
+            if (hi > rn || rn == 0) continue;
+            const float4 c = f3b_view_color(P.hist, f3b_view_index(P.hist, sx, sy));
+            const float ls = (P.k1 * log1pf(c.w * P.k2)) / c.w;
+            const float coef = __ldg(P.de_coefs + (size_t)k * P.kernel_size + (hi * (hi + 1)) / 2 + lo);
+            acc.x += coef * (c.x * ls);
+            acc.y += coef * (c.y * ls);
+            acc.z += coef * (c.z * ls);
+            acc.w += coef * (c.w * ls);
+            any = true;
+         }
+      }
+      if (!any) continue;
+      const size_t gi = (size_t)gx + (size_t)P.width * gy;
+      float4 a = P.accum[gi];
+      a.x += acc.x;
+      a.y += acc.y;
+      a.z += acc.z;
+      a.w += acc.w;
+      P.accum[gi] = a;
+   }
+}
+
 int f3b_launch_density(const F3DensityParams &p_in, cudaStream_t stream) {
    if (p_in.row_end <= p_in.row_begin) return 1;
    if (p_in.n_kernels <= 0) {
@@ -290,14 +357,17 @@ int f3b_launch_density(const F3DensityParams &p_in, cudaStream_t stream) {
    const size_t SW = DE_TILE + 2 * R;
    size_t smem = SW * SW * (sizeof(float4) + sizeof(uint32_t)) + SW * sizeof(int);
    smem = (smem + 15) & ~(size_t)15;
-   if (smem > 220 * 1024) return 0;
-   if (cudaFuncSetAttribute(f3b_de_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)smem) != cudaSuccess)
+   const bool staged = smem <= 220 * 1024;
+   if (staged && cudaFuncSetAttribute(f3b_de_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem) != cudaSuccess)
       return 0;
    dim3 block(DE_TILE, DE_ROWS);
    f3b_de_classify_kernel<<<dim3(tiles_x, p.class_tile_y1 - p.class_tile_y0), block, 0, stream>>>(p);
    if (cudaGetLastError() != cudaSuccess) return 0;
-   f3b_de_gather_kernel<<<dim3(tiles_x, gather_tile_y1 - p.gather_tile_y0), block, smem, stream>>>(p);
+   if (staged)
+      f3b_de_gather_kernel<<<dim3(tiles_x, gather_tile_y1 - p.gather_tile_y0), block, smem, stream>>>(p);
+   else
+      f3b_de_gather_global_kernel<<<dim3(tiles_x, gather_tile_y1 - p.gather_tile_y0), block, 0, stream>>>(p);
    return cudaGetLastError() == cudaSuccess ? 2 : 0;
 }
 
@@ -502,79 +572,184 @@ int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream) {
 /* ---------------------------------------------------------------------------------- */
 /* histogram import/export in the reference's bits=33 bucket layout (uint32[5])        */
 /* ---------------------------------------------------------------------------------- */
-__global__ void f3b_hist_from_u32_kernel(const uint32_t *src, float4 *color, float *count,
-                                         int width, int height, F3HistLayout lay) {
+__global__ void f3b_hist_from_u32_kernel(const uint32_t *src, void *exact_color, void *exact_count,
+                                         int f64, int width, int height, int pitch) {
    const size_t n = (size_t)width * height;
    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
    const size_t stride = (size_t)gridDim.x * blockDim.x;
    for (; i < n; i += stride) {
       const uint32_t *b = src + i * 5;
-      const size_t y = i / (size_t)width, o = f3b_hist_index(lay, (int)(i - y * (size_t)width), (int)y);
-      color[o] = make_float4((float)b[0], (float)b[1], (float)b[2], (float)b[3]);
-      if (count) count[o] = (float)b[4];
+      const size_t y = i / (size_t)width, o = (i - y * (size_t)width) + y * (size_t)pitch;
+      if (f64) {
+         reinterpret_cast<double4 *>(exact_color)[o] =
+             make_double4((double)b[0], (double)b[1], (double)b[2], (double)b[3]);
+         if (exact_count) reinterpret_cast<double *>(exact_count)[o] = (double)b[4];
+      } else {
+         reinterpret_cast<uint4 *>(exact_color)[o] = make_uint4(b[0], b[1], b[2], b[3]);
+         if (exact_count) reinterpret_cast<uint32_t *>(exact_count)[o] = b[4];
+      }
    }
 }
-__global__ void f3b_hist_to_u32_kernel(const float4 *color, const float *count, uint32_t *dst,
-                                       int width, int height, F3HistLayout lay) {
+__device__ __forceinline__ uint32_t f3b_sat_u32(double v) {
+   return v <= 0.0 ? 0u : (v >= 4294967295.0 ? 0xffffffffu : (uint32_t)v);
+}
+__global__ void f3b_hist_to_u32_kernel(const void *exact_color, const void *exact_count, int f64,
+                                       uint32_t *dst, int width, int height, int pitch) {
    const size_t n = (size_t)width * height;
    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
    const size_t stride = (size_t)gridDim.x * blockDim.x;
    for (; i < n; i += stride) {
-      const size_t y = i / (size_t)width, o = f3b_hist_index(lay, (int)(i - y * (size_t)width), (int)y);
-      const float4 c = color[o];
+      const size_t y = i / (size_t)width, o = (i - y * (size_t)width) + y * (size_t)pitch;
       uint32_t *b = dst + i * 5;
-      b[0] = (uint32_t)fminf(c.x, 4294967040.0f);
-      b[1] = (uint32_t)fminf(c.y, 4294967040.0f);
-      b[2] = (uint32_t)fminf(c.z, 4294967040.0f);
-      b[3] = (uint32_t)fminf(c.w, 4294967040.0f);
-      b[4] = count ? (uint32_t)fminf(count[o], 4294967040.0f) : b[3];
+      if (f64) {
+         const double4 c = reinterpret_cast<const double4 *>(exact_color)[o];
+         b[0] = f3b_sat_u32(c.x);
+         b[1] = f3b_sat_u32(c.y);
+         b[2] = f3b_sat_u32(c.z);
+         b[3] = f3b_sat_u32(c.w);
+         b[4] = exact_count ? f3b_sat_u32(reinterpret_cast<const double *>(exact_count)[o]) : b[3];
+      } else {
+         const uint4 c = reinterpret_cast<const uint4 *>(exact_color)[o];
+         b[0] = c.x;
+         b[1] = c.y;
+         b[2] = c.z;
+         b[3] = c.w;
+         b[4] = exact_count ? reinterpret_cast<const uint32_t *>(exact_count)[o] : c.w;
+      }
    }
 }
-int f3b_launch_hist_from_u32(const uint32_t *src5, float4 *color, float *count, int width,
-                             int height, F3HistLayout lay, cudaStream_t stream) {
-   f3b_hist_from_u32_kernel<<<148 * 8, 256, 0, stream>>>(src5, color, count, width, height, lay);
+int f3b_launch_hist_from_u32(const uint32_t *src5, void *exact_color, void *exact_count, int f64,
+                             int width, int height, int pitch, cudaStream_t stream) {
+   f3b_hist_from_u32_kernel<<<148 * 8, 256, 0, stream>>>(src5, exact_color, exact_count, f64, width,
+                                                         height, pitch);
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
 }
-int f3b_launch_hist_to_u32(const float4 *color, const float *count, uint32_t *dst5, int width,
-                           int height, F3HistLayout lay, cudaStream_t stream) {
-   f3b_hist_to_u32_kernel<<<148 * 8, 256, 0, stream>>>(color, count, dst5, width, height, lay);
+int f3b_launch_hist_to_u32(const void *exact_color, const void *exact_count, int f64, uint32_t *dst5,
+                           int width, int height, int pitch, cudaStream_t stream) {
+   f3b_hist_to_u32_kernel<<<148 * 8, 256, 0, stream>>>(exact_color, exact_count, f64, dst5, width,
+                                                       height, pitch);
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
 }
 
 /* ---------------------------------------------------------------------------------- */
-/* sum of the histogram replicas the chaos game wrote (f3b_api.cu: hist_layout_for)    */
+/* staging copies -> exact buckets (f3b_iterate.cu: the sweeper warp)                  */
 /* ---------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256) f3b_hist_merge_kernel(float4 *color, float *count, size_t n,
-                                                             F3HistLayout lay, int *hot_max) {
+/* exact += every staging copy, which is left zeroed for the next launch (so the staging
+ * planes are never cleared separately). Integer buckets saturate at UINT_MAX like
+ * bump_no_overflow (flam3.c:3838-3854); a staged value found at >= 2^24 is counted as a loss
+ * of exactness. Also records the fullest bucket (aggregation decision of the next frame). */
+__device__ __forceinline__ uint32_t f3b_merge_u32(uint32_t base, long long staged) {
+   const long long s = (long long)base + staged;
+   return s <= 0 ? 0u : (s >= 0xffffffffll ? 0xffffffffu : (uint32_t)s);
+}
+__global__ void __launch_bounds__(256) f3b_hist_merge_kernel(const F3MergeParams M) {
    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
    const size_t stride = (size_t)gridDim.x * blockDim.x;
-   float mx = 0.0f;
-   for (; i < n; i += stride) {
-      float4 a = color[i];
-      float c = count ? count[i] : 0.0f;
-      for (uint32_t r = 1; r < lay.replicas; r++) {
-         const float4 b = color[i + r * lay.replica_stride];
-         a.x += b.x;
-         a.y += b.y;
-         a.z += b.z;
-         a.w += b.w;
-         if (count) c += count[i + r * lay.replica_stride];
+   unsigned int mx = 0;
+   unsigned int lost = 0;
+   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+   for (; i < M.elems; i += stride) {
+      if (M.f64) {
+         double ax = 0.0, ay = 0.0, az = 0.0, aw = 0.0, ac = 0.0;
+         for (uint32_t r = 0; r < M.lay.replicas; r++) {
+            const size_t e = i + r * M.lay.replica_stride;
+            const float4 b = M.color[e];
+            ax += (double)b.x;
+            ay += (double)b.y;
+            az += (double)b.z;
+            aw += (double)b.w;
+            M.color[e] = zero4;
+            if (M.count) {
+               ac += (double)M.count[e];
+               M.count[e] = 0.0f;
+            }
+         }
+         double4 *ec = reinterpret_cast<double4 *>(M.exact_color) + i;
+         double4 v = *ec;
+         v.x += ax;
+         v.y += ay;
+         v.z += az;
+         v.w += aw;
+         *ec = v;
+         double cnt = v.w;
+         if (M.count) {
+            double *en = reinterpret_cast<double *>(M.exact_count) + i;
+            cnt = *en + ac;
+            *en = cnt;
+         }
+         mx = max(mx, (unsigned int)fmin(cnt, 4294967295.0));
+      } else {
+         long long ax = 0, ay = 0, az = 0, aw = 0, ac = 0;
+         for (uint32_t r = 0; r < M.lay.replicas; r++) {
+            const size_t e = i + r * M.lay.replica_stride;
+            const float4 b = M.color[e];
+            const float m = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
+            if (m >= F3B_EXACT_LIMIT) lost++;
+            if (m != 0.0f) {
+               ax += (long long)b.x;
+               ay += (long long)b.y;
+               az += (long long)b.z;
+               aw += (long long)b.w;
+               M.color[e] = zero4;
+            }
+            if (M.count) {
+               const float c = M.count[e];
+               if (fabsf(c) >= F3B_EXACT_LIMIT) lost++;
+               if (c != 0.0f) {
+                  ac += (long long)c;
+                  M.count[e] = 0.0f;
+               }
+            }
+         }
+         uint4 *ec = reinterpret_cast<uint4 *>(M.exact_color) + i;
+         uint4 v = *ec;
+         if (ax | ay | az | aw) {
+            v.x = f3b_merge_u32(v.x, ax);
+            v.y = f3b_merge_u32(v.y, ay);
+            v.z = f3b_merge_u32(v.z, az);
+            v.w = f3b_merge_u32(v.w, aw);
+            *ec = v;
+         }
+         unsigned int cnt = v.w;
+         if (M.count) {
+            uint32_t *en = reinterpret_cast<uint32_t *>(M.exact_count) + i;
+            cnt = *en;
+            if (ac) {
+               cnt = f3b_merge_u32(cnt, ac);
+               *en = cnt;
+            }
+         }
+         mx = max(mx, cnt);
       }
-      color[i] = a;
-      if (count) count[i] = c;
-      mx = fmaxf(mx, count ? c : a.w);
    }
-   /* the fullest bucket of this rank's histogram (non-negative floats order like their bits):
-    * f3b_iterate's aggregation decision for the next frame of this genome */
-   int m = __float_as_int(mx);
-   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-   if (hot_max && (threadIdx.x & 31) == 0 && m > 0) atomicMax(hot_max, m);
+   for (int o = 16; o > 0; o >>= 1) {
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      lost += __shfl_xor_sync(0xffffffffu, lost, o);
+   }
+   if ((threadIdx.x & 31) == 0) {
+      if (M.hot_max && mx > 0) atomicMax(M.hot_max, mx);
+      if (lost) atomicAdd(M.exact_flags, (unsigned long long)lost);
+   }
 }
-int f3b_launch_hist_merge(float4 *color, float *count, size_t elems, F3HistLayout lay, int *hot_max,
-                          cudaStream_t stream) {
-   if (lay.replicas <= 1) return 0;
-   int blocks = (int)((elems + 255) / 256);
+/* uint32 sums that wrapped while the sweepers were adding to them are pinned to UINT_MAX */
+__global__ void f3b_hist_saturate_kernel(const F3MergeParams M) {
+   unsigned long long n = M.exact_flags[1];
+   if (n > F3B_SAT_LIST_CAP) n = F3B_SAT_LIST_CAP;
+   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+        i += (unsigned long long)gridDim.x * blockDim.x) {
+      const uint32_t e = M.sat_list[i];
+      const size_t bucket = e >> 3;
+      const int ch = (int)(e & 7u);
+      if (ch < 4) reinterpret_cast<uint32_t *>(M.exact_color)[bucket * 4 + ch] = 0xffffffffu;
+      else if (M.exact_count) reinterpret_cast<uint32_t *>(M.exact_count)[bucket] = 0xffffffffu;
+   }
+}
+int f3b_launch_hist_merge(const F3MergeParams &m, cudaStream_t stream) {
+   int blocks = (int)((m.elems + 255) / 256);
    if (blocks > 148 * 8) blocks = 148 * 8;
-   f3b_hist_merge_kernel<<<blocks, 256, 0, stream>>>(color, count, elems, lay, hot_max);
-   return cudaGetLastError() == cudaSuccess ? 1 : -1;
+   f3b_hist_merge_kernel<<<blocks, 256, 0, stream>>>(m);
+   if (cudaGetLastError() != cudaSuccess) return -1;
+   if (m.f64 || !m.sat_check) return 1;
+   f3b_hist_saturate_kernel<<<1, 256, 0, stream>>>(m);
+   return cudaGetLastError() == cudaSuccess ? 2 : -1;
 }

@@ -57,10 +57,21 @@ f3b_ctx *f3b_render_context(void) {
  * (another GPU, or the reference itself in the parity tests). */
 static const uint32_t *g_inject = NULL;
 static size_t g_inject_n = 0;
+static int g_inject_preload = 0;
 void f3b_render_inject_histogram(const uint32_t *buckets5, size_t nbuckets) {
    pthread_mutex_lock(&g_lock);
    g_inject = buckets5;
    g_inject_n = nbuckets;
+   g_inject_preload = 0;
+   pthread_mutex_unlock(&g_lock);
+}
+/* Same, but the chaos game still runs and adds on top of the supplied buckets (tests of the
+ * saturating integer adds start from buckets close to UINT_MAX). */
+void f3b_render_preload_histogram(const uint32_t *buckets5, size_t nbuckets) {
+   pthread_mutex_lock(&g_lock);
+   g_inject = buckets5;
+   g_inject_n = nbuckets;
+   g_inject_preload = buckets5 != NULL;
    pthread_mutex_unlock(&g_lock);
 }
 
@@ -451,7 +462,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          if (spec->genomes[i].palette[j].color[3] != 1.0) count_plane = 1;
    }
 
-   if (f3b_frame_begin(ctx, g.width, g.height, count_plane)) {
+   if (f3b_frame_begin(ctx, g.width, g.height, count_plane, spec->bits)) {
       fprintf(stderr, "render_rectangle (B200): cannot allocate %dx%d buckets: %s\n", g.width,
               g.height, f3b_last_error(ctx));
       goto done;
@@ -589,6 +600,9 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
             goto done;
          }
          if (f3b_hist_upload_u32(ctx, g_inject)) goto gpu_error;
+      }
+      if (g_inject && !g_inject_preload) {
+         /* post-pass only */
       } else if (f3b_iterate(ctx, blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
                              spec->bits != 64, max_chain, g_rank, g_nranks))
          goto gpu_error;
@@ -680,7 +694,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       stats->badvals = bv;
    }
 
-   if (getenv("insert_palette")) { /* debug aid of the reference, rect.c:1267-1279 */
+   if (getenv("insert_palette") && out && !g_device_only) { /* debug aid of the reference, rect.c:1267-1279 */
       int ph = 100;
       if (ph >= g.image_height) ph = g.image_height;
       for (int j = 0; j < ph; j++)

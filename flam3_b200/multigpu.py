@@ -51,8 +51,8 @@ def _render_stream(d, ctx):
 
 def make_allreduce_exchange(core, nbuckets=None, dist=None, stream_ordered=False):
     """Returns the callback for Flam3Lib.set_exchange: sums the per-rank histograms in
-    place with one all-reduce per plane (float32; the adds are integer valued, so the sum
-    is exact below 2^24 per channel and order independent). stream_ordered=True issues the
+    place with one all-reduce per plane (the buckets are uint32, summed as int32: exact and
+    order independent; no saturation across ranks on this path). stream_ordered=True issues the
     collective on the render stream and returns at once (pair with set_stream_ordered(True))."""
     import torch
 
@@ -71,7 +71,8 @@ def make_allreduce_exchange(core, nbuckets=None, dist=None, stream_ordered=False
         key = (color, count, n)
         if key not in cache:
             cache.clear()
-            cache[key] = (device_tensor(color, n * 4), device_tensor(count, n) if count else None,
+            # the buckets are uint32 (exact integer sums): summed as int32, same bits
+            cache[key] = (device_tensor(color, n * 4, "<i4"), device_tensor(count, n, "<i4") if count else None,
                           _render_stream(d, ctx) if stream_ordered else None)
         t, t2, stream = cache[key]
         if stream is not None:

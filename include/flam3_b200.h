@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define F3B_ABI_VERSION 2
+#define F3B_ABI_VERSION 3
 
 typedef struct f3b_ctx f3b_ctx;
 
@@ -55,9 +55,12 @@ int f3b_sync(f3b_ctx *ctx);
 
 /* ---- frame buffers (rect.c:685-710) ---------------------------------------------- */
 /* width/height are the BUCKET grid (oversample*image + 2*gutter). count_channel=0 lets
- * the alpha plane double as the hit-count plane (valid when every palette alpha is 1 and
- * every temporal-filter weight is 1; f3b_render.c decides). Clears both buffers. */
-int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel);
+ * the alpha channel double as the hit-count channel (valid when every palette alpha is 1 and
+ * every temporal-filter weight is 1; f3b_render.c decides). `bits` is flam3_frame.bits and
+ * selects the bucket type like flam3.c:3894-3932 does: 32 / 33 -> uint32[5] per bucket, adds
+ * truncated, saturating at UINT_MAX (flam3.c:3772, 3824, 3838-3854); 64 -> double[5]
+ * (flam3.c:3724). Clears buckets and accumulators. */
+int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel, int bits);
 int f3b_hist_clear(f3b_ctx *ctx);
 int f3b_accum_clear(f3b_ctx *ctx);
 
@@ -98,8 +101,13 @@ int f3b_inputs_consumed(f3b_ctx *ctx);
 
 int f3b_debug_apply_xform(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int xform_index,
                           const float *in_xyc, int n, float *out_xycvb, uint64_t seed);
-/* bad values since f3b_frame_begin (stat_struct.badvals, rect.c:1251) */
+/* bad values since f3b_frame_begin (stat_struct.badvals, rect.c:1251); waits for the stream */
 int f3b_badvals(f3b_ctx *ctx, double *out);
+/* Integer-bucket bookkeeping of the frame, as of the last f3b_badvals: *lost = staged float
+ * sums that were found at >= 2^24 before they could be moved into the uint32 buckets (0 = the
+ * histogram is exactly the integer histogram the reference's adds would give); *saturated =
+ * uint32 sums that passed UINT_MAX and were pinned there (flam3.c:3838-3854). */
+int f3b_exactness(f3b_ctx *ctx, uint64_t *lost, uint64_t *saturated);
 
 /* ---- log scale + density estimation (rect.c:933-1058, de_thread rect.c:57-251) ---- */
 typedef struct {
@@ -151,8 +159,8 @@ int f3b_hist_download_u32(f3b_ctx *ctx, uint32_t *buckets5);
 /* accumulator: float[4] per bucket (abucket_float, flam3.c:3825) */
 int f3b_accum_upload(f3b_ctx *ctx, const float *acc4);
 int f3b_accum_download(f3b_ctx *ctx, float *acc4);
-void *f3b_hist_color_ptr(f3b_ctx *ctx); /* device float4[f3b_hist_elems] */
-void *f3b_hist_count_ptr(f3b_ctx *ctx); /* device float[f3b_hist_elems] or NULL */
+void *f3b_hist_color_ptr(f3b_ctx *ctx); /* device uint32[4][f3b_hist_elems] (double[4] for bits 64) */
+void *f3b_hist_count_ptr(f3b_ctx *ctx); /* device uint32[f3b_hist_elems] (double) or NULL */
 /* buckets in a histogram plane = height * row pitch (the pitch may exceed the width; padding
  * buckets stay zero): the number of elements an exchange between GPUs must cover. Use
  * f3b_hist_download_u32 / f3b_hist_upload_u32 for the reference's [height][width] layout. */

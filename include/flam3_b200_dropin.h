@@ -50,6 +50,8 @@ struct f3b_ctx *f3b_render_context(void);
 /* Post-pass only: the next renders take this histogram (reference bits=33 layout,
  * uint32[5] per bucket, flam3.c:3824) instead of running the chaos game. NULL = off. */
 void f3b_render_inject_histogram(const uint32_t *buckets5, size_t nbuckets);
+/* Same, but the chaos game still runs and adds on top of the supplied buckets. */
+void f3b_render_preload_histogram(const uint32_t *buckets5, size_t nbuckets);
 /* Leave the finished image in device memory; `out` is not written. */
 void f3b_render_set_device_only(int on);
 /* This process runs chain groups g with g % nranks == rank (one process per GPU). */

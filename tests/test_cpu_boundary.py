@@ -28,7 +28,7 @@ def test_core_library_exports_every_declared_symbol(core):
     from flam3_b200.capi import CORE_SYMBOLS
 
     assert set(CORE_SYMBOLS) <= set(names)
-    assert core._dll.f3b_abi_version() == 2
+    assert core._dll.f3b_abi_version() == 3
 
 
 def test_dropin_exports_the_reference_entry_points(gpu):
