@@ -199,6 +199,43 @@ class Flam3Lib:
         self._gather_keep = cb
         f(C.cast(cb, C.c_void_p), None)
 
+    def set_peers(self, peers, image0):
+        """Ranks in separate processes: peers = [(color_ptr, count_ptr or None)] per rank, as
+        device pointers valid in THIS process (CUDA IPC), image0 = rank 0's device image.
+        None switches the peer path off (include/flam3_b200_dropin.h)."""
+        f = self._dll.f3b_render_set_peers
+        f.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        f.restype = None
+        if not peers:
+            f(0, None, None)
+            return
+        arr = (PeerHist * len(peers))()
+        for i, (c, n) in enumerate(peers):
+            arr[i].color, arr[i].count = c, n
+        f(len(peers), C.cast(arr, C.c_void_p), image0)
+
+    def set_barrier(self, fn):
+        """fn(ctx_ptr) must enqueue a barrier over all ranks on the render stream."""
+        proto = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+        f = self._dll.f3b_render_set_barrier
+        f.argtypes = [C.c_void_p, C.c_void_p]
+        f.restype = None
+        if fn is None:
+            self._barrier_keep = None
+            f(None, None)
+            return
+        cb = proto(lambda ctx, user: fn(ctx))
+        self._barrier_keep = cb
+        f(C.cast(cb, C.c_void_p), None)
+
+    def render_context_at(self, core, i):
+        """The i-th GPU context of this process (F3B_DEVICES), or None."""
+        f = self._dll.f3b_render_context_at
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_int]
+        p = f(i)
+        return Context(core, C.c_void_p(p)) if p else None
+
     def render_context(self, core):
         """The f3b_ctx the drop-in renders with, wrapped for stage stats / buffer access."""
         f = self._dll.f3b_render_context
@@ -256,6 +293,12 @@ class Flam3Lib:
         return out, st, rc.raw
 
 
+class PeerHist(C.Structure):
+    """f3b_peer_hist (include/flam3_b200.h)."""
+
+    _fields_ = [("color", C.c_void_p), ("count", C.c_void_p)]
+
+
 class F3Job(C.Structure):
     _fields_ = [("blob_offset", C.c_uint64), ("n_iters", C.c_uint64), ("n_chains", C.c_uint32),
                 ("fuse", C.c_uint32), ("first_group", C.c_uint32), ("sample_id", C.c_uint32)]
@@ -294,7 +337,9 @@ CORE_SYMBOLS = [
     "f3b_finish_device", "f3b_finish_device_rows", "f3b_image_download", "f3b_hist_upload_u32", "f3b_hist_download_u32", "f3b_accum_upload",
     "f3b_accum_download", "f3b_hist_color_ptr", "f3b_hist_count_ptr", "f3b_hist_elems", "f3b_accum_ptr",
     "f3b_stream_ptr", "f3b_stage_stats", "f3b_stats_reset", "f3b_xfer_stats", "f3b_timer_start",
-    "f3b_timer_stop",
+    "f3b_timer_stop", "f3b_peer_enable", "f3b_hist_reduce_rows", "f3b_group_barrier",
+    "f3b_image_reserve", "f3b_image_ptr", "f3b_finish_rows_into", "f3b_ipc_export", "f3b_ipc_open",
+    "f3b_ipc_close", "f3b_device_index",
 ]
 
 
@@ -522,6 +567,27 @@ class Context:
 
     def sync(self):
         self._ck(self.lib._dll.f3b_sync(self.ptr), "sync")
+
+    def image_ptr(self):
+        f = self.lib._dll.f3b_image_ptr
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p]
+        return f(self.ptr)
+
+    def ipc_export(self, dev_ptr):
+        buf = (C.c_ubyte * 64)()
+        f = self.lib._dll.f3b_ipc_export
+        f.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_ubyte)]
+        self._ck(f(self.ptr, dev_ptr, buf), "ipc_export")
+        return bytes(buf)
+
+    def ipc_open(self, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        out = C.c_void_p()
+        f = self.lib._dll.f3b_ipc_open
+        f.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+        self._ck(f(self.ptr, buf, C.byref(out)), "ipc_open")
+        return out.value
 
     def hist_ptrs(self):
         d = self.lib._dll

@@ -24,7 +24,8 @@ struct DevBuf {
 /* device counters (unsigned long long each): [0] bad values, [1] fullest bucket's count,
  * [2] lanes adding / [3] lanes sharing a bucket in the aggregation probe, [4] the probe's own
  * bad values (discarded), [5] spare, [6] staged values that reached 2^24 (exactness lost),
- * [7] entries of the saturation list, [8] the sweepers' ticket counter (low 32 bits) */
+ * [7] entries of the saturation list, [8..9] the sweepers' state (three uint32: cold ticket,
+ * hot entries, hot ticket; cleared before every launch) */
 #define F3B_NCOUNTERS 16
 #define F3B_CTR_LOST 6
 #define F3B_CTR_TICKET 8
@@ -43,6 +44,12 @@ struct f3b_ctx {
    DevBuf hist_color, hist_count, accum, image; /* hist_*: the float STAGING copies */
    DevBuf exact_color, exact_count, sat_list;   /* the buckets proper (f3b_internal.h) */
    DevBuf xfer;                 /* staging of f3b_hist_upload/download_u32 (kept across calls) */
+   DevBuf hot_list, hot_bitmap; /* the sweepers' list of fast-growing staging entries */
+   /* several GPUs on one frame: the strip of rows this context owns, summed over all ranks */
+   DevBuf reduced_color, reduced_count;
+   bool view_reduced = false;
+   int view_row0 = 0, view_rows = 0;
+   cudaEvent_t bar_ev = nullptr; /* f3b_group_barrier */
    int f64 = 0;                 /* bits 64: double buckets */
    bool staging_dirty = true;   /* staging copies may hold something (cleared by the merge) */
    bool swept = false;          /* sweepers have run since the last hist_clear */
@@ -73,9 +80,9 @@ struct f3b_ctx {
    };
    std::vector<Rec> recs;
    size_t ev_used = 0;
-   double stage_ms[F3B_NSTAGES] = {0, 0, 0};
-   uint64_t stage_launches[F3B_NSTAGES] = {0, 0, 0};
-   uint64_t h2d_bytes = 0, d2h_bytes = 0;
+   double stage_ms[F3B_NSTAGES] = {0};
+   uint64_t stage_launches[F3B_NSTAGES] = {0};
+   uint64_t h2d_bytes = 0, d2h_bytes = 0, peer_bytes = 0;
    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
 };
 
@@ -182,6 +189,8 @@ void f3b_ctx_destroy(f3b_ctx *ctx) {
    cudaSetDevice(ctx->device);
    cudaStreamSynchronize(ctx->stream);
    DevBuf *bufs[] = {&ctx->exact_color, &ctx->exact_count, &ctx->sat_list, &ctx->xfer,
+                     &ctx->reduced_color, &ctx->reduced_count,
+                     &ctx->hot_list, &ctx->hot_bitmap,
                      &ctx->hist_color, &ctx->hist_count, &ctx->accum,    &ctx->image,
                      &ctx->blobs,      &ctx->jobs,       &ctx->groups,   &ctx->de_coefs,
                      &ctx->de_radius,  &ctx->filter,     &ctx->de_kidx,  &ctx->de_tiles};
@@ -197,6 +206,7 @@ void f3b_ctx_destroy(f3b_ctx *ctx) {
       if (ctx->join_ev[i]) cudaEventDestroy(ctx->join_ev[i]);
    }
    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+   if (ctx->bar_ev) cudaEventDestroy(ctx->bar_ev);
    if (ctx->inputs_ev) cudaEventDestroy(ctx->inputs_ev);
    if (ctx->timer0) cudaEventDestroy(ctx->timer0);
    if (ctx->timer1) cudaEventDestroy(ctx->timer1);
@@ -266,6 +276,8 @@ int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel, int 
    if (ensure(ctx, ctx->exact_color, nh * (f64 ? sizeof(double4) : sizeof(uint4)))) return 1;
    if (count_channel && ensure(ctx, ctx->exact_count, nh * (f64 ? sizeof(double) : sizeof(uint32_t)))) return 1;
    if (ensure(ctx, ctx->sat_list, F3B_SAT_LIST_CAP * sizeof(uint32_t))) return 1;
+   if (ensure(ctx, ctx->hot_list, F3B_HOT_LIST_CAP * sizeof(uint32_t))) return 1;
+   if (ensure(ctx, ctx->hot_bitmap, (nalloc + 31) / 32 * sizeof(uint32_t))) return 1;
    /* the staging copies are zero between a merge and the next launch: clear them only when
     * they are new, were left behind by a failed frame, or the layout changed under them */
    if (before[0] != ctx->hist_color.p || (count_channel && before[1] != ctx->hist_count.p) ||
@@ -281,8 +293,7 @@ int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel, int 
    ctx->hot_total = 0.0;
    ctx->hot_measured = false;
    ctx->hot_from_merge = false;
-   /* everything but the sweepers' ticket counter, which just keeps counting */
-   CK(cudaMemsetAsync(ctx->d_badvals, 0, F3B_CTR_TICKET * sizeof(unsigned long long), ctx->stream));
+   CK(cudaMemsetAsync(ctx->d_badvals, 0, F3B_NCOUNTERS * sizeof(unsigned long long), ctx->stream));
    if (ctx->staging_dirty) {
       CK(cudaMemsetAsync(ctx->hist_color.p, 0, nalloc * sizeof(float4), ctx->stream));
       if (count_channel) CK(cudaMemsetAsync(ctx->hist_count.p, 0, nalloc * sizeof(float), ctx->stream));
@@ -301,6 +312,7 @@ int f3b_hist_clear(f3b_ctx *ctx) {
    if (ctx->swept) /* the saturation list belongs to the histogram being discarded */
       CK(cudaMemsetAsync(ctx->d_badvals + F3B_CTR_LOST + 1, 0, sizeof(unsigned long long), ctx->stream));
    ctx->swept = false;
+   ctx->view_reduced = false; /* the post-pass reads this context's own buckets again */
    return 0;
 }
 
@@ -384,7 +396,8 @@ static uint64_t genome_signature(const uint32_t *w0, int width, int height) {
 
 void *f3b_pinned_alloc(size_t bytes) {
    void *p = nullptr;
-   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+   /* portable: a frame spread over several GPUs uploads the same packed samples to each */
+   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
       cudaGetLastError();
       return nullptr;
    }
@@ -486,16 +499,17 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    P.exact_color = ctx->exact_color.p;
    P.exact_count = ctx->count_channel ? ctx->exact_count.p : nullptr;
    P.exact_f64 = (uint32_t)ctx->f64;
-   P.sweep_ticket = (unsigned int *)(ctx->d_badvals + F3B_CTR_TICKET);
+   P.sweep_state = (unsigned int *)(ctx->d_badvals + F3B_CTR_TICKET);
+   P.sweep_hot_list = (uint32_t *)ctx->hot_list.p;
+   P.sweep_hot_bitmap = (unsigned int *)ctx->hot_bitmap.p;
    P.exact_flags = ctx->d_badvals + F3B_CTR_LOST;
    P.sat_list = (uint32_t *)ctx->sat_list.p;
    P.chain_threads = (uint32_t)group_size;
    {
       /* Sweepers (f3b_iterate.cu) run unless no staged sum can reach the carry threshold at
-       * all. Their pace: flat out, unless the share of the fullest bucket is known from the
-       * previous frame of this genome; then a pass over the staging planes may take half the
-       * time that bucket needs to grow from the carry threshold to 2^24 at the highest
-       * iteration rate the GPU reaches. F3B_SWEEP=0/1, F3B_SWEEP_NS override. */
+       * all. After the first passes a cold pass over all staging entries is due once per
+       * sweep_gap: 2 ms, or longer for big histograms so that the passes stay below
+       * ~100 GB/s of reads. F3B_SWEEP=0/1, F3B_SWEEP_GAP_US override. */
       uint64_t it = 0;
       for (int j = 0; j < n_jobs; j++) it += jobs[j].n_iters;
       double carry = ctx->f64 ? (double)F3B_CARRY_F64 : (double)F3B_CARRY_U32;
@@ -503,11 +517,22 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       if (ce && atof(ce) >= 1.0 && atof(ce) < carry) carry = atof(ce);
       P.carry_thresh = (float)carry;
       P.sweep_on = ((double)it / nranks) * 255.0 >= carry ? 1u : 0u;
-      P.sweep_sleep_ns = 0;
       const char *e = getenv("F3B_SWEEP");
       if (e) P.sweep_on = atoi(e) ? 1u : 0u;
+      const double plane_bytes = (double)(ctx->lay.replica_stride * ctx->lay.replicas) * (ctx->count_channel ? 20.0 : 16.0);
+      double gap_us = plane_bytes / 100e9 * 1e6;
+      if (gap_us < 2000.0) gap_us = 2000.0;
+      const char *ge = getenv("F3B_SWEEP_GAP_US");
+      if (ge && atof(ge) > 0.0) gap_us = atof(ge);
+      P.sweep_gap_ns = gap_us * 1e3 > 4e9 ? 4000000000u : (uint32_t)(gap_us * 1e3);
+      const char *me = getenv("F3B_SWEEP_MODE");
+      P.sweep_mode = me ? (uint32_t)atoi(me) : 3u;
+      if (P.sweep_on) {
+         CK(cudaMemsetAsync(P.sweep_state, 0, 4 * sizeof(unsigned int), ctx->stream));
+         CK(cudaMemsetAsync(ctx->hot_bitmap.p, 0,
+                            (ctx->lay.replica_stride * ctx->lay.replicas + 31) / 32 * sizeof(uint32_t), ctx->stream));
+      }
    }
-
    const int bps = f3b_iterate_blocks_per_sm(group_size, max_blob);
    if (bps <= 0) return fail(ctx, "f3b_iterate: kernel does not fit with %zu bytes of shared memory", max_blob);
    ctx->staging_dirty = true;
@@ -614,25 +639,14 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          ctx->hot_iters = total_iters;
          ctx->hot_total = 255.0 * (double)total_iters; /* of one batch, like the bucket maximum */
          const bool known = ctx->hot_share >= 0.0 && ctx->hot_share_signature == sig;
-         if (P.sweep_on) {
-            const char *ns = getenv("F3B_SWEEP_NS");
-            if (ns) P.sweep_sleep_ns = (uint32_t)atoi(ns);
-            else if (known && !ctx->f64) {
-               const double share = ctx->hot_share > 1e-7 ? ctx->hot_share : 1e-7;
-               const double growth = share * 2.2e11 * 255.0 / (double)ctx->lay.replicas; /* per second */
-               const double allowed_us = 0.5e6 * ((double)F3B_EXACT_LIMIT - (double)F3B_CARRY_U32) / growth;
-               const double tickets = (double)(ctx->lay.replica_stride * ctx->lay.replicas) / F3B_SWEEP_ENTRIES;
-               const double per_sweeper = tickets / (double)(grid > 0 ? grid : 1);
-               const double pause_us = allowed_us / (per_sweeper > 1.0 ? per_sweeper : 1.0) - 1.5;
-               P.sweep_sleep_ns = pause_us <= 0.0 ? 0u : (pause_us > 100.0 ? 100000u : (uint32_t)(pause_us * 1e3));
-            }
-         }
          if (e) aggregate = atoi(e) != 0;
          /* one bucket with share s of the hits gives a lane a duplicate among its 31 peers with
           * probability ~31 s: the probe's 1/8 criterion corresponds to s ~ 0.4% */
          else if (known && ctx->hot_share < 0.0035) aggregate = false; /* spread out last time */
          else if (known && ctx->hot_share > 0.02) aggregate = true;   /* one bucket took > 2% */
-         else if (total_iters / (uint64_t)nranks >= 50000000ull) {
+         else if (total_iters / (uint64_t)nranks >= (P.sweep_on ? 1000000ull : 50000000ull)) {
+            /* (with integer buckets the answer also decides whether hot buckets get their
+             * aggregated sums added exactly, so smaller frames are worth the probe too) */
             F3IterateParams Q = P;
             Q.probe_iters = 64;
             Q.sweep_on = 0;
@@ -675,7 +689,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    M.hot_max = (unsigned int *)(ctx->d_badvals + 1);
    M.exact_flags = ctx->d_badvals + F3B_CTR_LOST;
    M.sat_list = (const uint32_t *)ctx->sat_list.p;
-   if (P.sweep_on) ctx->swept = true;
+   if (P.sweep_on || aggregate) ctx->swept = true; /* integer atomics may have wrapped */
    M.sat_check = ctx->swept ? 1 : 0;
    const int nm = f3b_launch_hist_merge(M, ctx->stream);
    if (nm < 0) return fail(ctx, "histogram merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -736,6 +750,17 @@ int f3b_badvals(f3b_ctx *ctx, double *out) {
    return 0;
 }
 
+/* all device counters as of now (waits for the stream); for tools */
+int f3b_debug_counters(f3b_ctx *ctx, uint64_t out[16]) {
+   if (!ctx || !out) return 1;
+   CK(cudaSetDevice(ctx->device));
+   unsigned long long v[F3B_NCOUNTERS];
+   CK(cudaMemcpyAsync(v, ctx->d_badvals, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+   CK(cudaStreamSynchronize(ctx->stream));
+   for (int i = 0; i < F3B_NCOUNTERS; i++) out[i] = v[i];
+   return 0;
+}
+
 int f3b_exactness(f3b_ctx *ctx, uint64_t *lost, uint64_t *saturated) {
    if (!ctx) return 1;
    if (lost) *lost = ctx->lost_exact;
@@ -766,6 +791,13 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
    P.hist.f64 = ctx->f64;
    P.hist.pitch = ctx->lay.pitch;
    P.hist.row0 = 0;
+   P.hist.rows = ctx->height;
+   if (ctx->view_reduced) {
+      P.hist.color = ctx->reduced_color.p;
+      P.hist.count = ctx->count_channel ? ctx->reduced_count.p : nullptr;
+      P.hist.row0 = ctx->view_row0;
+      P.hist.rows = ctx->view_rows;
+   }
    P.accum = (float4 *)ctx->accum.p;
    P.width = ctx->width;
    P.height = ctx->height;
@@ -825,6 +857,15 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
       P.max_filter_index = d->max_filter_index;
       P.curve = (float)d->curve;
    }
+   if (ctx->view_reduced) {
+      /* sources up to max_radius rows beyond the targets, each looking oversample/2 further */
+      const int reach = P.n_kernels > 0 ? P.max_radius + d->oversample / 2 : 0;
+      const int need0 = row0 - reach < 0 ? 0 : row0 - reach;
+      const int need1 = row1 + reach > ctx->height ? ctx->height : row1 + reach;
+      if (need0 < ctx->view_row0 || need1 > ctx->view_row0 + ctx->view_rows)
+         return fail(ctx, "f3b_density_rows: rows [%d,%d) need buckets [%d,%d), the reduced strip holds [%d,%d)",
+                     row0, row1, need0, need1, ctx->view_row0, ctx->view_row0 + ctx->view_rows);
+   }
    if (P.n_kernels > 0) {
       const size_t tiles = (size_t)((ctx->width + 31) / 32) * ((ctx->height + 31) / 32);
       if (ensure(ctx, ctx->de_kidx, (size_t)ctx->width * ctx->height * sizeof(uint16_t))) return 1;
@@ -859,8 +900,30 @@ int f3b_finish_device(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_out) {
    return f3b_finish_device_rows(ctx, d, 0, d ? d->image_height : 0, 0, dev_out);
 }
 
+static int finish_rows_impl(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int row1, int alloc_rows,
+                            void *dst_image, void **dev_out);
+
 int f3b_finish_device_rows(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int row1, int alloc_rows,
                            void **dev_out) {
+   return finish_rows_impl(ctx, d, row0, row1, alloc_rows, nullptr, dev_out);
+}
+
+int f3b_finish_rows_into(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int row1, void *dst_image) {
+   if (!dst_image) return fail(ctx, "f3b_finish_rows_into: null image");
+   return finish_rows_impl(ctx, d, row0, row1, 0, dst_image, nullptr);
+}
+
+int f3b_image_reserve(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_image) {
+   if (!ctx || !d || !dev_image) return 1;
+   CK(cudaSetDevice(ctx->device));
+   const size_t ibytes = (size_t)d->image_width * d->image_height * d->nchan * d->bytes_per_channel;
+   if (ensure(ctx, ctx->image, ibytes)) return 1;
+   *dev_image = ctx->image.p;
+   return 0;
+}
+
+static int finish_rows_impl(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int row1, int alloc_rows,
+                            void *dst_image, void **dev_out) {
    if (!ctx || !d) return 1;
    if (!ctx->accum.p) return fail(ctx, "f3b_finish: f3b_frame_begin not called");
    CK(cudaSetDevice(ctx->device));
@@ -880,7 +943,7 @@ int f3b_finish_device_rows(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int 
    if (row1 > d->image_height) row1 = d->image_height;
    if (alloc_rows < d->image_height) alloc_rows = d->image_height;
    const size_t ibytes = (size_t)d->image_width * alloc_rows * d->nchan * d->bytes_per_channel;
-   if (ensure(ctx, ctx->image, ibytes)) return 1;
+   if (!dst_image && ensure(ctx, ctx->image, ibytes)) return 1;
    {
       const size_t nf = (size_t)d->filter_width * d->filter_width;
       if (ctx->filter_host.size() != nf || memcmp(ctx->filter_host.data(), d->filter, fbytes) != 0) {
@@ -914,7 +977,7 @@ int f3b_finish_device_rows(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int 
    P.vibrancy = d->vibrancy;
    P.highpow = d->highlight_power;
    for (int i = 0; i < 3; i++) P.background[i] = d->background[i];
-   P.out = ctx->image.p;
+   P.out = dst_image ? dst_image : ctx->image.p;
    P.out_row_begin = row0;
    P.out_row_end = row1;
 
@@ -1006,6 +1069,101 @@ void *f3b_accum_ptr(f3b_ctx *ctx) {
 }
 void *f3b_stream_ptr(f3b_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
+/* ---- several GPUs on one frame ------------------------------------------------------ */
+int f3b_peer_enable(f3b_ctx *ctx, f3b_ctx *peer) {
+   if (!ctx || !peer) return 1;
+   if (ctx->device == peer->device) return 0;
+   CK(cudaSetDevice(ctx->device));
+   int can = 0;
+   CK(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+   if (!can) return fail(ctx, "device %d cannot access device %d directly", ctx->device, peer->device);
+   cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+   if (e == cudaErrorPeerAccessAlreadyEnabled) {
+      cudaGetLastError();
+      e = cudaSuccess;
+   }
+   if (e != cudaSuccess) return fail(ctx, "cudaDeviceEnablePeerAccess(%d) failed: %s", peer->device, cudaGetErrorString(e));
+   return 0;
+}
+
+int f3b_hist_reduce_rows(f3b_ctx *ctx, const f3b_peer_hist *peers, int npeers, int row0, int row1) {
+   if (!ctx || !peers || npeers < 1 || npeers > F3B_MAX_RANKS) return fail(ctx, "f3b_hist_reduce_rows: bad arguments");
+   if (!ctx->exact_color.p) return fail(ctx, "f3b_hist_reduce_rows: f3b_frame_begin not called");
+   CK(cudaSetDevice(ctx->device));
+   if (row0 < 0) row0 = 0;
+   if (row1 > ctx->height) row1 = ctx->height;
+   if (row1 <= row0) return fail(ctx, "f3b_hist_reduce_rows: empty row range");
+   F3ReduceParams R;
+   memset(&R, 0, sizeof(R));
+   R.npeers = npeers;
+   R.f64 = ctx->f64;
+   for (int p = 0; p < npeers; p++) {
+      if (!peers[p].color || (ctx->count_channel && !peers[p].count))
+         return fail(ctx, "f3b_hist_reduce_rows: peer %d has no buckets", p);
+      R.color[p] = peers[p].color;
+      R.count[p] = ctx->count_channel ? peers[p].count : nullptr;
+   }
+   R.first = (size_t)row0 * ctx->lay.pitch;
+   R.n = (size_t)(row1 - row0) * ctx->lay.pitch;
+   if (ensure(ctx, ctx->reduced_color, R.n * (ctx->f64 ? sizeof(double4) : sizeof(uint4)))) return 1;
+   if (ctx->count_channel && ensure(ctx, ctx->reduced_count, R.n * (ctx->f64 ? sizeof(double) : sizeof(uint32_t)))) return 1;
+   R.out_color = ctx->reduced_color.p;
+   R.out_count = ctx->count_channel ? ctx->reduced_count.p : nullptr;
+   if (stage_begin(ctx, F3B_STAGE_EXCHANGE)) return 1;
+   if (!f3b_launch_hist_reduce(R, ctx->stream))
+      return fail(ctx, "strip reduction launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+   if (stage_end(ctx, 1)) return 1;
+   ctx->view_reduced = true;
+   ctx->view_row0 = row0;
+   ctx->view_rows = row1 - row0;
+   ctx->peer_bytes += (uint64_t)R.n * (uint64_t)(npeers - 1) * (ctx->f64 ? 2 : 1) * (ctx->count_channel ? 20 : 16);
+   return 0;
+}
+
+int f3b_group_barrier(f3b_ctx *const *ctxs, int n) {
+   if (!ctxs || n < 1) return 1;
+   for (int i = 0; i < n; i++) {
+      f3b_ctx *ctx = ctxs[i];
+      if (!ctx) return 1;
+      CK(cudaSetDevice(ctx->device));
+      if (!ctx->bar_ev) CK(cudaEventCreateWithFlags(&ctx->bar_ev, cudaEventDisableTiming));
+      CK(cudaEventRecord(ctx->bar_ev, ctx->stream));
+   }
+   for (int i = 0; i < n; i++) {
+      f3b_ctx *ctx = ctxs[i];
+      CK(cudaSetDevice(ctx->device));
+      for (int j = 0; j < n; j++)
+         if (j != i) CK(cudaStreamWaitEvent(ctx->stream, ctxs[j]->bar_ev, 0));
+   }
+   return 0;
+}
+
+int f3b_ipc_export(f3b_ctx *ctx, const void *dev_ptr, unsigned char handle[64]) {
+   if (!ctx || !dev_ptr || !handle) return 1;
+   CK(cudaSetDevice(ctx->device));
+   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+   cudaIpcMemHandle_t h;
+   CK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+   memcpy(handle, &h, 64);
+   return 0;
+}
+int f3b_ipc_open(f3b_ctx *ctx, const unsigned char handle[64], void **dev_ptr) {
+   if (!ctx || !handle || !dev_ptr) return 1;
+   CK(cudaSetDevice(ctx->device));
+   cudaIpcMemHandle_t h;
+   memcpy(&h, handle, 64);
+   CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+   return 0;
+}
+int f3b_ipc_close(f3b_ctx *ctx, void *dev_ptr) {
+   if (!ctx || !dev_ptr) return 1;
+   CK(cudaSetDevice(ctx->device));
+   CK(cudaIpcCloseMemHandle(dev_ptr));
+   return 0;
+}
+void *f3b_image_ptr(f3b_ctx *ctx) { return ctx ? ctx->image.p : nullptr; }
+int f3b_device_index(f3b_ctx *ctx) { return ctx ? ctx->device : -1; }
+
 int f3b_stage_stats(f3b_ctx *ctx, int stage, double *ms, uint64_t *launches) {
    if (!ctx || stage < 0 || stage >= F3B_NSTAGES) return 1;
    CK(cudaSetDevice(ctx->device));
@@ -1048,7 +1206,7 @@ void f3b_stats_reset(f3b_ctx *ctx) {
    if (!ctx) return;
    cudaSetDevice(ctx->device);
    stats_collect(ctx);
-   ctx->h2d_bytes = ctx->d2h_bytes = 0;
+   ctx->h2d_bytes = ctx->d2h_bytes = ctx->peer_bytes = 0;
    for (int i = 0; i < F3B_NSTAGES; i++) {
       ctx->stage_ms[i] = 0.0;
       ctx->stage_launches[i] = 0;

@@ -41,7 +41,8 @@ struct F3HistView {
    const void *count; /* uint32[...] or double[...]; nullptr: colour channel 3 is the count */
    int f64;           /* bits 64 */
    int pitch;         /* buckets per row */
-   int row0;          /* bucket row held at element 0 (strips of a frame reduced over GPUs) */
+   int row0, rows;    /* bucket rows [row0, row0 + rows) are held, row0 at element 0 (a strip
+                         of the frame reduced over several GPUs; else 0, height) */
 };
 #ifdef __CUDACC__
 __device__ __forceinline__ size_t f3b_view_index(const F3HistView &V, int x, int y) {
@@ -68,8 +69,9 @@ __device__ __forceinline__ float f3b_view_count(const F3HistView &V, size_t i) {
 #define F3B_CARRY_U32 4194304.0f /* 2^22: staged integer sums are moved out at this size ... */
 #define F3B_EXACT_LIMIT 16777216.0f /* ... and must never reach 2^24 */
 #define F3B_CARRY_F64 262144.0f  /* 2^18: bits 64, keeps the float rounding of an add <= 2^-6 */
-#define F3B_SWEEP_ENTRIES 128u   /* staging entries a sweeper warp examines per ticket */
+#define F3B_SWEEP_ENTRIES 256u   /* staging entries a sweeper warp examines per ticket */
 #define F3B_SAT_LIST_CAP 65536u
+#define F3B_HOT_LIST_CAP 262144u
 
 #define F3B_CHAINS_PER_GROUP 256 /* largest chain group = threads per block of the chaos-game
                                     kernel; batches with few chains per temporal sample use
@@ -118,12 +120,16 @@ struct F3IterateParams {
    void *exact_count;            /* uint32[elems] or double[elems]; nullptr without a count plane */
    uint32_t chain_threads;       /* walkers per CTA = chains per group */
    uint32_t sweep_on;            /* blockDim.x == chain_threads + 32 */
-   uint32_t sweep_sleep_ns;      /* pause between two tickets of a sweeper warp */
+   uint32_t sweep_gap_ns;        /* a cold pass over the staging planes is due this often */
+   uint32_t sweep_mode;          /* 1 cold passes | 2 hot list (3 = normal; F3B_SWEEP_MODE for experiments) */
    uint32_t exact_f64;
    float carry_thresh;           /* F3B_CARRY_U32 / F3B_CARRY_F64 (F3B_CARRY lowers it, for tests) */
-   unsigned int *sweep_ticket;   /* device: next segment of the staging planes to examine */
+   unsigned int *sweep_state;    /* device: [0] cold ticket, [1] hot entries, [2] hot ticket */
+   uint32_t *sweep_hot_list;     /* device: staging entries that grow fast */
+   unsigned int *sweep_hot_bitmap; /* device: one bit per staging entry: on the hot list */
    unsigned long long *exact_flags; /* device: [0] staged values seen at >= 2^24 (exactness
-                                       lost), [1] entries in sat_list */
+                                       lost), [1] entries in sat_list, [4..6] diagnostics: where
+                                       the losses were seen (cold pass, hot list, merge) */
    uint32_t *sat_list;           /* device: bucket * 8 + channel of exact sums that wrapped */
    /* probe launch (AGG kernels only): every chain stores at most probe_iters iterations,
     * nothing is added to the histogram, probe_counts[0] += lanes that reached an add,
@@ -197,6 +203,21 @@ struct F3FinalParams {
    int out_row_begin, out_row_end; /* image rows produced by this launch */
 };
 int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream);
+
+/* Several GPUs on one frame: rank r owns a strip of bucket rows and sums every rank's
+ * buckets of those rows straight out of the peers' memory (NVLink loads), saturating like
+ * the buckets themselves. This is the reduce-scatter by image strip, halo rows included
+ * (overlapping strips are simply fetched by both neighbours). */
+#define F3B_MAX_RANKS 16
+struct F3ReduceParams {
+   const void *color[F3B_MAX_RANKS];
+   const void *count[F3B_MAX_RANKS]; /* all nullptr without a count plane */
+   int npeers, f64;
+   void *out_color, *out_count;
+   size_t first; /* element of the peers' planes that becomes element 0 of the output */
+   size_t n;     /* elements to reduce */
+};
+int f3b_launch_hist_reduce(const F3ReduceParams &r, cudaStream_t stream);
 
 /* reference bucket layout uint32[5] per bucket <-> the exact planes */
 int f3b_launch_hist_from_u32(const uint32_t *src5, void *exact_color, void *exact_count, int f64,

@@ -47,52 +47,6 @@ __device__ __forceinline__ void f3b_red_f32(float *addr, float v) {
    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
-/* Warp-level aggregation of bucket adds, for attractors that collapse onto a few buckets:
- * reductions to ONE address serialise in L2 (~2e9/s for the whole GPU), so a genome whose
- * orbit sits on a fixed point or a short cycle ran 50x slower than a spread-out one
- * (profiles/r01_c5_*: var76 267 -> 39 ms, var47 118 -> 22 ms, var58 175 -> 35 ms). In the AGG
- * instantiations of the kernel the lanes that are about to add compare their buckets
- * (match.any); lanes with the same bucket sum their colours through shuffles and the lowest
- * one issues the reduction. The sums are of integer-valued floats, so they stay exact.
- * Returns false for a lane whose add was folded into another lane's. The check costs ~5 % on
- * a spread-out flame, so the host only launches the AGG kernels when a short probe launch of
- * the same kernel (probe_counts != NULL: count, add nothing) found the lanes colliding.
- * Every warp-synchronous operation below is executed by exactly the lanes named in its mask:
- * match and ballot by all lanes that entered together (`act`), the shuffles by the lanes of
- * one `peers` set, which all see the same set and so run the same number of rounds. */
-__device__ __noinline__ bool f3b_bump_aggregate(unsigned long long bidx, float4 *colp, float *cntp,
-                                                unsigned long long *probe_counts) {
-   const unsigned act = __activemask();
-   const unsigned lane = threadIdx.x & 31u;
-   const unsigned peers = __match_any_sync(act, bidx);
-   const bool dup = (peers & (peers - 1u)) != 0u;
-   const unsigned nd = __popc(__ballot_sync(act, dup));
-   if (probe_counts) { /* probe launch: measure, add nothing */
-      if ((int)lane == __ffs(act) - 1) {
-         atomicAdd(probe_counts, (unsigned long long)__popc(act));
-         atomicAdd(probe_counts + 1, (unsigned long long)nd);
-      }
-      return false;
-   }
-   if (!dup) return true;
-   const int leader = __ffs(peers) - 1;
-   const float4 a = *colp;
-   const float c = *cntp;
-   float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f, sc = 0.f;
-   for (unsigned rest = peers & ~(1u << leader); rest; rest &= rest - 1u) {
-      const int src = __ffs(rest) - 1;
-      sx += __shfl_sync(peers, a.x, src);
-      sy += __shfl_sync(peers, a.y, src);
-      sz += __shfl_sync(peers, a.z, src);
-      sw += __shfl_sync(peers, a.w, src);
-      sc += __shfl_sync(peers, c, src);
-   }
-   if ((int)lane != leader) return false;
-   *colp = make_float4(a.x + sx, a.y + sy, a.z + sz, a.w + sw);
-   *cntp = c + sc;
-   return true;
-}
-
 /* ---- the sweeper warp: exact buckets behind float staging planes -------------------- */
 /* A float sum of integers is exact only below 2^24 (65 793 hits of 255), and a 1080p
  * quality-2000 frame puts 8e6 hits into its fullest bucket. So the float4 planes the walkers
@@ -135,52 +89,202 @@ __device__ __noinline__ void f3b_carry_channel(const F3IterateParams &P, size_t 
       if (slot < F3B_SAT_LIST_CAP) P.sat_list[slot] = (uint32_t)(bucket * 8 + (size_t)ch);
    }
 }
+/* Warp-level aggregation of bucket adds, for attractors that collapse onto a few buckets:
+ * reductions to ONE address serialise in L2 (~2e9/s for the whole GPU), so a genome whose
+ * orbit sits on a fixed point or a short cycle ran 50x slower than a spread-out one
+ * (profiles/r01_c5_*: var76 267 -> 39 ms, var47 118 -> 22 ms, var58 175 -> 35 ms). In the AGG
+ * instantiations of the kernel the lanes that are about to add compare their buckets
+ * (match.any); lanes with the same bucket sum their colours through shuffles and the lowest
+ * one adds the sum, with integer atomics, directly to the exact bucket. The sums are of
+ * integer-valued floats, so they stay exact. Returns false for a lane whose add has been
+ * taken care of (folded into another lane's, or made by this function). The check costs ~5 % on
+ * a spread-out flame, so the host only launches the AGG kernels when a short probe launch of
+ * the same kernel (probe_counts != NULL: count, add nothing) found the lanes colliding.
+ * Every warp-synchronous operation below is executed by exactly the lanes named in its mask:
+ * match and ballot by all lanes that entered together (`act`), the shuffles by the lanes of
+ * one `peers` set, which all see the same set and so run the same number of rounds. */
+__device__ __noinline__ bool f3b_bump_aggregate(const F3IterateParams &P, size_t bucket,
+                                                unsigned long long bidx, float4 *colp, float *cntp,
+                                                unsigned long long *probe_counts) {
+   const unsigned act = __activemask();
+   const unsigned lane = threadIdx.x & 31u;
+   const unsigned peers = __match_any_sync(act, bidx);
+   const bool dup = (peers & (peers - 1u)) != 0u;
+   const unsigned nd = __popc(__ballot_sync(act, dup));
+   if (probe_counts) { /* probe launch: measure, add nothing */
+      if ((int)lane == __ffs(act) - 1) {
+         atomicAdd(probe_counts, (unsigned long long)__popc(act));
+         atomicAdd(probe_counts + 1, (unsigned long long)nd);
+      }
+      return false;
+   }
+   if (!dup) return true;
+   const int leader = __ffs(peers) - 1;
+   const float4 a = *colp;
+   const float c = *cntp;
+   float sx = 0.f, sy = 0.f, sz = 0.f, sw = 0.f, sc = 0.f;
+   for (unsigned rest = peers & ~(1u << leader); rest; rest &= rest - 1u) {
+      const int src = __ffs(rest) - 1;
+      sx += __shfl_sync(peers, a.x, src);
+      sy += __shfl_sync(peers, a.y, src);
+      sz += __shfl_sync(peers, a.z, src);
+      sw += __shfl_sync(peers, a.w, src);
+      sc += __shfl_sync(peers, c, src);
+   }
+   if ((int)lane != leader) return false;
+   /* A bucket that several lanes of one warp hit at once is a bucket that fills faster than
+    * any sweeper could empty its staging copy (a collapsed attractor adds 1e12 per second to
+    * one address): the aggregated sum goes straight into the exact bucket. Lone hits of the
+    * same bucket still take the staged path, at a rate the sweepers handle. */
+   f3b_carry_channel(P, bucket, 0, a.x + sx);
+   f3b_carry_channel(P, bucket, 1, a.y + sy);
+   f3b_carry_channel(P, bucket, 2, a.z + sz);
+   f3b_carry_channel(P, bucket, 3, a.w + sw);
+   if (P.hist_count) f3b_carry_channel(P, bucket, 4, c + sc);
+   return false;
+}
+
+/* examine one staging entry: carry what has reached the threshold; returns the largest
+ * channel seen (before the carry) */
+__device__ __forceinline__ float f3b_sweep_entry(const F3IterateParams &P, size_t e, float4 v, float c,
+                                                 int where) {
+   const float thr = P.carry_thresh;
+   const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+   const size_t bucket = e % P.lay.replica_stride;
+   if (m >= thr) {
+      /* take the channels out one by one with an exchange: what comes back is exactly what
+       * left the staging bucket, whatever lands there meanwhile */
+      float *f = reinterpret_cast<float *>(P.hist_color + e);
+#pragma unroll
+      for (int ch = 0; ch < 4; ch++) {
+         const float take = atomicExch(f + ch, 0.0f);
+         if (!P.exact_f64 && fabsf(take) >= F3B_EXACT_LIMIT) {
+            atomicAdd(P.exact_flags, 1ull);
+            atomicAdd(P.exact_flags + 4 + where, 1ull); /* diagnostics: seen by a cold pass / hot service */
+         }
+         f3b_carry_channel(P, bucket, ch, take);
+      }
+   }
+   if (fabsf(c) >= thr) {
+      const float take = atomicExch(P.hist_count + e, 0.0f);
+      if (!P.exact_f64 && fabsf(take) >= F3B_EXACT_LIMIT) {
+         atomicAdd(P.exact_flags, 1ull);
+         atomicAdd(P.exact_flags + 4 + where, 1ull);
+      }
+      f3b_carry_channel(P, bucket, 4, take);
+   }
+   return fmaxf(m, fabsf(c));
+}
+__device__ __forceinline__ unsigned long long f3b_now_ns() {
+   unsigned long long t;
+   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+   return t;
+}
+/* Two kinds of work, so that exactness costs (almost) no L2 bandwidth:
+ *  - COLD passes over all staging entries, 128 per ticket from a global counter (whichever
+ *    sweepers are alive share a pass). Passes 0 and 1 run flat out from the start of the
+ *    launch (~70 us each for a 1080p frame: the fullest bucket of a flame that does not
+ *    qualify for warp aggregation needs >= 200 us to reach 2^24), the later ones are due 4x
+ *    later each up to one per P.sweep_gap_ns: an entry that was still small when last seen
+ *    needs proportionally long to become large.
+ *  - Entries that fill fast enough to reach the carry threshold within one such gap go on the
+ *    HOT list (once: a bitmap), and between cold tickets every sweeper keeps servicing 32
+ *    hot entries at a time. A 1080p
+ *    quality-2000 flame has ~6000 hot entries among 6.4 million; they are what actually needs
+ *    carrying, every ~100 us for the fullest. */
 __device__ __noinline__ void f3b_sweeper(const F3IterateParams &P, volatile int *s_done) {
    const unsigned lane = threadIdx.x & 31u;
    const size_t n_entries = P.lay.replica_stride * P.lay.replicas;
    const unsigned nseg = (unsigned)((n_entries + F3B_SWEEP_ENTRIES - 1) / F3B_SWEEP_ENTRIES);
-   const float thr = P.carry_thresh;
+   const float gap_inv = 1.0f / (float)P.sweep_gap_ns;
    constexpr int U = F3B_SWEEP_ENTRIES / 32;
-   while (!*s_done) {
-      unsigned t = 0;
-      if (lane == 0) t = atomicAdd(P.sweep_ticket, 1u);
-      t = __shfl_sync(0xffffffffu, t, 0);
-      const size_t base = (size_t)(t % nseg) * F3B_SWEEP_ENTRIES;
-      float4 v[U];
-      float c[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-         const size_t e = base + (size_t)u * 32 + lane;
-         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-         c[u] = 0.f;
-         if (e < n_entries) {
-            v[u] = f3b_ld_staged4(P.hist_color + e);
-            if (P.hist_count) c[u] = f3b_ld_staged1(P.hist_count + e);
-         }
+   unsigned int *const S = P.sweep_state; /* [0] cold ticket, [1] hot entries, [2] hot ticket */
+   const unsigned long long t0 = f3b_now_ns();
+   if (!(P.sweep_mode & 3u)) return; /* experiments: idle sweepers */
+   /* the ticket after the one in hand is requested before the one in hand is worked on */
+   unsigned next = 0;
+   if (lane == 0) next = atomicAdd(S, 1u);
+   unsigned ticket = 0;
+   bool have_ticket = false;
+   for (unsigned round = 0; !*s_done; round++) {
+      bool worked = false;
+      if (!have_ticket) {
+         ticket = __shfl_sync(0xffffffffu, next, 0);
+         if (lane == 0) next = atomicAdd(S, 1u);
+         have_ticket = true;
       }
+      const unsigned pass = ticket / nseg;
+      /* due times: 0, 0, 100 us, 400 us, then one pass per sweep_gap_ns */
+      unsigned long long due = 0;
+      if (pass == 2) due = 100000ull;
+      else if (pass == 3) due = 400000ull;
+      else if (pass > 3) due = 400000ull + (unsigned long long)(pass - 3) * P.sweep_gap_ns;
+      const unsigned long long elapsed = f3b_now_ns() - t0;
+      if ((P.sweep_mode & 1u) && (pass < 2 || elapsed >= due)) {
+         /* HOT means: fills at a rate that reaches the carry threshold within one gap between
+          * cold passes. Whatever is below that rate cannot get from the threshold of this visit
+          * past twice the carry threshold before the next one. */
+         const float frac = (float)elapsed * gap_inv;
+         const float hot_mark = P.carry_thresh * (frac < 1.0f ? fmaxf(frac, 1.0f / 4096.0f) : 1.0f);
+         const size_t base = (size_t)(ticket % nseg) * F3B_SWEEP_ENTRIES;
+         float4 v[U];
+         float c[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-         const size_t e = base + (size_t)u * 32 + lane;
-         const float m = fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
-         const size_t bucket = e % P.lay.replica_stride;
-         if (m >= thr) {
-            /* take the channels out one by one with an exchange: what comes back is exactly
-             * what left the staging bucket, whatever lands there meanwhile */
-            float *f = reinterpret_cast<float *>(P.hist_color + e);
-#pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
-               const float take = atomicExch(f + ch, 0.0f);
-               if (!P.exact_f64 && fabsf(take) >= F3B_EXACT_LIMIT) atomicAdd(P.exact_flags, 1ull);
-               f3b_carry_channel(P, bucket, ch, take);
+         for (int u = 0; u < U; u++) {
+            const size_t e = base + (size_t)u * 32 + lane;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            c[u] = 0.f;
+            if (e < n_entries) {
+               v[u] = f3b_ld_staged4(P.hist_color + e);
+               if (P.hist_count) c[u] = f3b_ld_staged1(P.hist_count + e);
             }
          }
-         if (fabsf(c[u]) >= thr) {
-            const float take = atomicExch(P.hist_count + e, 0.0f);
-            if (!P.exact_f64 && fabsf(take) >= F3B_EXACT_LIMIT) atomicAdd(P.exact_flags, 1ull);
-            f3b_carry_channel(P, bucket, 4, take);
+#pragma unroll
+         for (int u = 0; u < U; u++) {
+            const size_t e = base + (size_t)u * 32 + lane;
+            const float m = fmaxf(fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))),
+                                  fabsf(c[u]));
+            if (m >= hot_mark) {
+               f3b_sweep_entry(P, e, v[u], c[u], 0);
+               const unsigned bit = 1u << (e & 31u);
+               const unsigned old = atomicOr(P.sweep_hot_bitmap + (e >> 5), bit);
+               if (!(old & bit)) {
+                  const unsigned slot = atomicAdd(S + 1, 1u);
+                  if (slot < F3B_HOT_LIST_CAP) P.sweep_hot_list[slot] = (uint32_t)e;
+               }
+            }
+         }
+         have_ticket = false;
+         worked = true;
+         if (pass < 2 && (round & 3u)) continue; /* first passes: as fast as possible */
+      }
+      /* hot entries */
+      unsigned nhot = 0;
+      if (lane == 0) nhot = *(volatile unsigned int *)(S + 1);
+      nhot = __shfl_sync(0xffffffffu, nhot, 0);
+      if (nhot > F3B_HOT_LIST_CAP) nhot = F3B_HOT_LIST_CAP;
+      if (!(P.sweep_mode & 2u)) nhot = 0;
+      if (nhot) {
+         unsigned h = 0;
+         if (lane == 0) h = atomicAdd(S + 2, 1u);
+         h = __shfl_sync(0xffffffffu, h, 0);
+         const unsigned groups = (nhot + 31u) / 32u;
+         const unsigned idx = (h % groups) * 32u + lane;
+         if (idx < nhot) {
+            const size_t e = *(volatile uint32_t *)(P.sweep_hot_list + idx);
+            if (e < n_entries) { /* a slot may be claimed but not written yet */
+               const float4 v = f3b_ld_staged4(P.hist_color + e);
+               const float c = P.hist_count ? f3b_ld_staged1(P.hist_count + e) : 0.0f;
+               f3b_sweep_entry(P, e, v, c, 1);
+            }
          }
       }
-      if (P.sweep_sleep_ns) __nanosleep(P.sweep_sleep_ns);
+      /* every hot entry is looked at about every 20 us by the sweepers of the launch together */
+      if (!worked) {
+         const unsigned groups = (nhot + 31u) / 32u;
+         unsigned ns = groups ? 20000u * gridDim.x / groups : 20000u;
+         __nanosleep(ns < 1000u ? 1000u : (ns > 50000u ? 50000u : ns));
+      }
    }
 }
 /* barrier among the walkers only (the sweeper warp never joins it) */
@@ -383,7 +487,7 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
             if (AGG) {
                float4 tc = col;
                float tn = cnt;
-               const bool mine = f3b_bump_aggregate((unsigned long long)bidx, &tc, &tn,
+               const bool mine = f3b_bump_aggregate(P, bidx - rep_off, (unsigned long long)bidx, &tc, &tn,
                                                     P.probe_iters ? P.probe_counts : nullptr);
                if (!mine) continue;
                col = tc;
@@ -430,7 +534,7 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
          if (AGG) {
             float4 tc = col;
             float tn = cnt;
-            const bool mine = f3b_bump_aggregate((unsigned long long)bidx, &tc, &tn,
+            const bool mine = f3b_bump_aggregate(P, bidx - rep_off, (unsigned long long)bidx, &tc, &tn,
                                                  P.probe_iters ? P.probe_counts : nullptr);
             if (!mine) continue;
             col = tc;

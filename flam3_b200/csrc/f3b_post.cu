@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) f3b_logscale_kernel(const F3DensityParams
  */
 __device__ __forceinline__ float f3b_de_count(const F3DensityParams &P, int x, int y) {
    if (x < 0 || x >= P.width || y < 0 || y >= P.height) return 0.0f;
+   if (y < P.hist.row0 || y >= P.hist.row0 + P.hist.rows) return 0.0f; /* outside the strip held */
    return f3b_view_count(P.hist, f3b_view_index(P.hist, x, y));
 }
 
@@ -728,7 +729,10 @@ __global__ void __launch_bounds__(256) f3b_hist_merge_kernel(const F3MergeParams
    }
    if ((threadIdx.x & 31) == 0) {
       if (M.hot_max && mx > 0) atomicMax(M.hot_max, mx);
-      if (lost) atomicAdd(M.exact_flags, (unsigned long long)lost);
+      if (lost) {
+         atomicAdd(M.exact_flags, (unsigned long long)lost);
+         atomicAdd(M.exact_flags + 6, (unsigned long long)lost);
+      }
    }
 }
 /* uint32 sums that wrapped while the sweepers were adding to them are pinned to UINT_MAX */
@@ -752,4 +756,53 @@ int f3b_launch_hist_merge(const F3MergeParams &m, cudaStream_t stream) {
    if (m.f64 || !m.sat_check) return 1;
    f3b_hist_saturate_kernel<<<1, 256, 0, stream>>>(m);
    return cudaGetLastError() == cudaSuccess ? 2 : -1;
+}
+
+/* ---------------------------------------------------------------------------------- */
+/* strip reduction over peer memory (several GPUs on one frame)                        */
+/* ---------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) f3b_hist_reduce_kernel(const F3ReduceParams R) {
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const size_t stride = (size_t)gridDim.x * blockDim.x;
+   for (; i < R.n; i += stride) {
+      const size_t e = R.first + i;
+      if (R.f64) {
+         double4 a = make_double4(0.0, 0.0, 0.0, 0.0);
+         double c = 0.0;
+#pragma unroll 4
+         for (int p = 0; p < R.npeers; p++) {
+            const double4 b = reinterpret_cast<const double4 *>(R.color[p])[e];
+            a.x += b.x;
+            a.y += b.y;
+            a.z += b.z;
+            a.w += b.w;
+            if (R.out_count) c += reinterpret_cast<const double *>(R.count[p])[e];
+         }
+         reinterpret_cast<double4 *>(R.out_color)[i] = a;
+         if (R.out_count) reinterpret_cast<double *>(R.out_count)[i] = c;
+      } else {
+         unsigned long long ax = 0, ay = 0, az = 0, aw = 0, ac = 0;
+#pragma unroll 4
+         for (int p = 0; p < R.npeers; p++) {
+            const uint4 b = reinterpret_cast<const uint4 *>(R.color[p])[e];
+            ax += b.x;
+            ay += b.y;
+            az += b.z;
+            aw += b.w;
+            if (R.out_count) ac += reinterpret_cast<const uint32_t *>(R.count[p])[e];
+         }
+         const unsigned long long top = 0xffffffffull;
+         reinterpret_cast<uint4 *>(R.out_color)[i] =
+             make_uint4((uint32_t)min(ax, top), (uint32_t)min(ay, top), (uint32_t)min(az, top),
+                        (uint32_t)min(aw, top));
+         if (R.out_count) reinterpret_cast<uint32_t *>(R.out_count)[i] = (uint32_t)min(ac, top);
+      }
+   }
+}
+int f3b_launch_hist_reduce(const F3ReduceParams &r, cudaStream_t stream) {
+   if (r.n == 0) return 1;
+   int blocks = (int)((r.n + 255) / 256);
+   if (blocks > 148 * 8) blocks = 148 * 8;
+   f3b_hist_reduce_kernel<<<blocks, 256, 0, stream>>>(r);
+   return cudaGetLastError() == cudaSuccess ? 1 : 0;
 }

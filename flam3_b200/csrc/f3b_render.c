@@ -26,19 +26,64 @@
 #include "f3b_host.h"
 
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
-static f3b_ctx *g_ctx = NULL;
+
+/* The GPUs of this process. F3B_DEVICES ("0-7", "0,2,4", ...) spreads every frame over several
+ * GPUs inside this one call: the unmodified flam3-render / flam3-animate then use the whole
+ * node. Default: the single device F3B_DEVICE (0). An entry may repeat ("0,0": two contexts
+ * on one GPU, which is how the multi-GPU path is tested on a one-GPU box). */
+#define F3B_MAX_LOCAL 16
+static struct {
+   int n;
+   f3b_ctx *ctx[F3B_MAX_LOCAL];
+} g_group;
+
+static int parse_devices(const char *e, int *dev, int cap) {
+   int n = 0;
+   while (*e && n < cap) {
+      char *end;
+      long a = strtol(e, &end, 10);
+      if (end == e) break;
+      long b = a;
+      if (*end == '-') {
+         const char *q = end + 1;
+         b = strtol(q, &end, 10);
+         if (end == q) b = a;
+      }
+      for (long d = a; d <= b && n < cap; d++) dev[n++] = (int)d;
+      e = end;
+      while (*e == ',' || *e == ' ') e++;
+   }
+   return n;
+}
 
 static f3b_ctx *get_ctx(void) {
-   if (!g_ctx) {
-      const char *e = getenv("F3B_DEVICE");
-      int dev = e ? atoi(e) : 0;
-      if (f3b_ctx_create(dev, &g_ctx)) {
-         fprintf(stderr, "flam3_render (B200): cannot create a GPU context on device %d; "
-                         "this build has no CPU path.\n", dev);
-         g_ctx = NULL;
+   if (!g_group.n) {
+      int dev[F3B_MAX_LOCAL], n = 0;
+      const char *e = getenv("F3B_DEVICES");
+      if (e) n = parse_devices(e, dev, F3B_MAX_LOCAL);
+      if (n == 0) {
+         e = getenv("F3B_DEVICE");
+         dev[0] = e ? atoi(e) : 0;
+         n = 1;
       }
+      for (int i = 0; i < n; i++) {
+         if (f3b_ctx_create(dev[i], &g_group.ctx[i])) {
+            fprintf(stderr, "flam3_render (B200): cannot create a GPU context on device %d; "
+                            "this build has no CPU path.\n", dev[i]);
+            for (int j = 0; j < i; j++) f3b_ctx_destroy(g_group.ctx[j]);
+            return NULL;
+         }
+      }
+      for (int i = 0; i < n; i++)
+         for (int j = 0; j < n; j++)
+            if (i != j && f3b_peer_enable(g_group.ctx[i], g_group.ctx[j])) {
+               fprintf(stderr, "flam3_render (B200): %s\n", f3b_last_error(g_group.ctx[i]));
+               for (int k = 0; k < n; k++) f3b_ctx_destroy(g_group.ctx[k]);
+               return NULL;
+            }
+      g_group.n = n;
    }
-   return g_ctx;
+   return g_group.ctx[0];
 }
 
 /* Exposed so hosts embedding the library (and the tests / bench) can reach the context
@@ -46,6 +91,14 @@ static f3b_ctx *get_ctx(void) {
 f3b_ctx *f3b_render_context(void) {
    pthread_mutex_lock(&g_lock);
    f3b_ctx *c = get_ctx();
+   pthread_mutex_unlock(&g_lock);
+   return c;
+}
+/* the i-th GPU context of this process (F3B_DEVICES), NULL beyond the last */
+f3b_ctx *f3b_render_context_at(int i) {
+   pthread_mutex_lock(&g_lock);
+   f3b_ctx *c = get_ctx();
+   c = (c && i >= 0 && i < g_group.n) ? g_group.ctx[i] : NULL;
    pthread_mutex_unlock(&g_lock);
    return c;
 }
@@ -93,6 +146,35 @@ typedef void (*f3b_gather_fn)(f3b_ctx *, void *image, size_t row_bytes, int rows
 static f3b_gather_fn g_gather = NULL;
 static int g_stream_ordered = 0;
 static void *g_gather_user = NULL;
+/*  - peers (ranks in separate processes, one GPU each): where every rank's buckets and rank
+ *    0's image are, as pointers valid on this process's device (CUDA IPC), and a callback that
+ *    enqueues a barrier over all ranks on the render stream. With them set, rank r sums its
+ *    strip of the frame out of the peers' memory and writes its image rows into rank 0's
+ *    image (include/flam3_b200.h, "several GPUs on one frame"). */
+static f3b_peer_hist g_peers[16];
+static int g_npeers = 0;
+static void *g_peer_image0 = NULL;
+static void *g_peer_own_color = NULL; /* what this rank exported: checked against reallocation */
+static void (*g_barrier)(f3b_ctx *, void *) = NULL;
+static void *g_barrier_user = NULL;
+void f3b_render_set_peers(int nranks, const f3b_peer_hist *peers, void *image0) {
+   pthread_mutex_lock(&g_lock);
+   g_npeers = 0;
+   g_peer_image0 = NULL;
+   g_peer_own_color = NULL;
+   if (peers && nranks > 1 && nranks <= 16) {
+      for (int i = 0; i < nranks; i++) g_peers[i] = peers[i];
+      g_npeers = nranks;
+      g_peer_image0 = image0;
+   }
+   pthread_mutex_unlock(&g_lock);
+}
+void f3b_render_set_barrier(void (*cb)(f3b_ctx *, void *), void *user) {
+   pthread_mutex_lock(&g_lock);
+   g_barrier = cb;
+   g_barrier_user = user;
+   pthread_mutex_unlock(&g_lock);
+}
 void f3b_render_set_device_only(int on) { g_device_only = on; }
 void f3b_render_set_shard(int rank, int nranks) {
    if (nranks < 1 || rank < 0 || rank >= nranks) {
@@ -356,6 +438,9 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
    const int timing = getenv("F3B_TIMING") != NULL;
    double t_setup = now_ms(), t_pack = 0, t_serial = 0, t_iter = 0, t_dens = 0, t_fin = 0, t0;
    int rv = 1;
+   enum { MODE_SINGLE, MODE_PEER_LOCAL, MODE_PEER_IPC, MODE_CALLBACKS } mode = MODE_SINGLE;
+   int NR = 1, nlocal = 1, rank0 = 0; /* ranks sharing the frame, contexts of this process, first rank here */
+   f3b_ctx **lc = g_group.ctx;
    int verbose = spec->verbose;
    const int nthreads = spec->nthreads > 0 ? spec->nthreads : 1;
    const int bytes_per_channel = spec->bytes_per_channel;
@@ -445,10 +530,28 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
    g.height = oversample * g.image_height + 2 * g.gutter_width;
    g.width = oversample * g.image_width + 2 * g.gutter_width;
 
-   /* multi-GPU row strips of the post-pass (f3b_render_set_strip_gather) */
-   const int strips = (g_gather != NULL && g_nranks > 1 && g_exchange != NULL);
-   const int strip_rows_per = (g.image_height + g_nranks - 1) / (g_nranks > 0 ? g_nranks : 1);
-   int strip_row0 = g_rank * strip_rows_per, strip_row1 = strip_row0 + strip_rows_per;
+   /* ---- how many GPUs share this frame, and how ----
+    * PEER_LOCAL: the contexts of this process (F3B_DEVICES), rank i = context i.
+    * PEER_IPC:   one context here, the other ranks in other processes (f3b_render_set_peers).
+    * legacy:     one context, host callbacks sum the histograms and gather the strips
+    *             (f3b_render_set_exchange / f3b_render_set_strip_gather). */
+   if (g_group.n > 1 && !g_inject) {
+      mode = MODE_PEER_LOCAL;
+      NR = nlocal = g_group.n;
+   } else if (g_npeers > 1 && g_nranks == g_npeers && g_barrier && !g_inject) {
+      mode = MODE_PEER_IPC;
+      NR = g_nranks;
+      rank0 = g_rank;
+   } else if (g_nranks > 1) {
+      mode = MODE_CALLBACKS;
+      NR = g_nranks;
+      rank0 = g_rank;
+   }
+   const int peer_mode = (mode == MODE_PEER_LOCAL || mode == MODE_PEER_IPC);
+   /* row strips of the post-pass: rank r handles image rows [r*per, (r+1)*per) */
+   const int strips = peer_mode || (mode == MODE_CALLBACKS && g_gather != NULL && g_exchange != NULL);
+   const int strip_rows_per = (g.image_height + NR - 1) / NR;
+   int strip_row0 = rank0 * strip_rows_per, strip_row1 = strip_row0 + strip_rows_per;
    if (strip_row0 > g.image_height) strip_row0 = g.image_height;
    if (strip_row1 > g.image_height) strip_row1 = g.image_height;
 
@@ -462,10 +565,20 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          if (spec->genomes[i].palette[j].color[3] != 1.0) count_plane = 1;
    }
 
-   if (f3b_frame_begin(ctx, g.width, g.height, count_plane, spec->bits)) {
-      fprintf(stderr, "render_rectangle (B200): cannot allocate %dx%d buckets: %s\n", g.width,
-              g.height, f3b_last_error(ctx));
-      goto done;
+   for (int i = 0; i < nlocal; i++)
+      if (f3b_frame_begin(lc[i], g.width, g.height, count_plane, spec->bits)) {
+         fprintf(stderr, "render_rectangle (B200): cannot allocate %dx%d buckets: %s\n", g.width,
+                 g.height, f3b_last_error(lc[i]));
+         goto done;
+      }
+   if (mode == MODE_PEER_IPC) {
+      /* the peers were told where this rank's buckets are: they must still be there */
+      if (!g_peer_own_color) g_peer_own_color = f3b_hist_color_ptr(ctx);
+      if (g_peer_own_color != f3b_hist_color_ptr(ctx)) {
+         fprintf(stderr, "flam3_render (B200): the bucket planes moved (the frame grew) after their "
+                         "address was given to the other ranks; exchange the addresses again.\n");
+         goto done;
+      }
    }
 
    if (verbose) fprintf(stderr, "chaos: ");
@@ -482,7 +595,12 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
    for (int batch_num = 0; batch_num < nbatches; batch_num++) {
       const double de_time = spec->time + temporal_deltas[batch_num * ntemporal_samples];
 
-      if (batch_num > 0 && f3b_hist_clear(ctx)) goto gpu_error;
+      if (batch_num > 0)
+         for (int i = 0; i < nlocal; i++)
+            if (f3b_hist_clear(lc[i])) {
+               ctx = lc[i];
+               goto gpu_error;
+            }
 
       /* DE parameters come from the genome at the batch's first time (rect.c:726-751) */
       flam3_interpolate(spec->genomes, spec->ngenomes, de_time, 0, &cp);
@@ -508,7 +626,11 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       /* ---- pack every temporal sample of this batch (rect.c:754-884). Interpolating and
        * packing a sample is independent host work (~45 us), so with many temporal samples
        * (flam3-animate: 1000 per frame) it is spread over a few host threads. ---- */
-      if (f3b_inputs_consumed(ctx)) goto gpu_error; /* the previous upload has left the buffer */
+      for (int i = 0; i < nlocal; i++) /* the previous upload has left the buffer */
+         if (f3b_inputs_consumed(lc[i])) {
+            ctx = lc[i];
+            goto gpu_error;
+         }
       blobs.used = 0;
       const uint32_t max_chain = spec->sub_batch_size > 0 ? (uint32_t)spec->sub_batch_size : 10000u;
       uint64_t seed = 0x243f6a8885a308d3ull;
@@ -603,10 +725,18 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       }
       if (g_inject && !g_inject_preload) {
          /* post-pass only */
-      } else if (f3b_iterate(ctx, blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
-                             spec->bits != 64, max_chain, g_rank, g_nranks))
-         goto gpu_error;
-      if (g_exchange) {
+      } else {
+         for (int i = 0; i < nlocal; i++) {
+            if (i > 0) /* the plan is the same for every rank: only first_group is filled in */
+               for (int ts = 0; ts < ntemporal_samples; ts++) jobs[ts].first_group = 0;
+            if (f3b_iterate(lc[i], blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
+                            spec->bits != 64, max_chain, rank0 + i, NR)) {
+               ctx = lc[i];
+               goto gpu_error;
+            }
+         }
+      }
+      if (mode == MODE_CALLBACKS && g_exchange) {
          if (!g_stream_ordered && f3b_sync(ctx)) goto gpu_error;
          (*g_exchange)(ctx, g_exchange_user);
       }
@@ -637,7 +767,49 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          rv = 0;
          goto done;
       }
-      if (strips) {
+      if (peer_mode) {
+         /* Reduce-scatter by image strip, fused: when every rank's chaos game is through,
+          * rank r sums all ranks' buckets of the rows its strip needs - the accumulator rows
+          * under its pixels' filter footprints plus the reach of the widest DE kernel -
+          * straight out of the peers' memory, and nobody clears buckets before all have read. */
+         if (mode == MODE_PEER_LOCAL ? f3b_group_barrier(lc, nlocal) : ((*g_barrier)(ctx, g_barrier_user), 0))
+            goto gpu_error;
+         f3b_peer_hist peers[F3B_MAX_LOCAL];
+         for (int r = 0; r < NR; r++) {
+            if (mode == MODE_PEER_LOCAL) {
+               peers[r].color = f3b_hist_color_ptr(lc[r]);
+               peers[r].count = f3b_hist_count_ptr(lc[r]);
+            } else
+               peers[r] = g_peers[r];
+         }
+         const int halo = max_de + oversample;
+         for (int i = 0; i < nlocal; i++) {
+            int s0 = (rank0 + i) * strip_rows_per, s1 = s0 + strip_rows_per;
+            if (s0 > g.image_height) s0 = g.image_height;
+            if (s1 > g.image_height) s1 = g.image_height;
+            if (s1 <= s0) continue;
+            const int a0 = g.de_offset + s0 * oversample;
+            const int a1 = g.de_offset + (s1 - 1) * oversample + g.filter_width;
+            if (f3b_hist_reduce_rows(lc[i], peers, NR, a0 - halo, a1 + halo)) {
+               ctx = lc[i];
+               goto gpu_error;
+            }
+         }
+         if (mode == MODE_PEER_LOCAL ? f3b_group_barrier(lc, nlocal) : ((*g_barrier)(ctx, g_barrier_user), 0))
+            goto gpu_error;
+         for (int i = 0; i < nlocal; i++) {
+            int s0 = (rank0 + i) * strip_rows_per, s1 = s0 + strip_rows_per;
+            if (s0 > g.image_height) s0 = g.image_height;
+            if (s1 > g.image_height) s1 = g.image_height;
+            if (s1 <= s0) continue;
+            const int a0 = g.de_offset + s0 * oversample;
+            const int a1 = g.de_offset + (s1 - 1) * oversample + g.filter_width;
+            if (f3b_density_rows(lc[i], &dd, a0, a1)) {
+               ctx = lc[i];
+               goto gpu_error;
+            }
+         }
+      } else if (strips) {
          /* accumulator rows under the filter footprints of this rank's image rows */
          const int a0 = g.de_offset + strip_row0 * oversample;
          const int a1 = g.de_offset + (strip_row1 - 1) * oversample + g.filter_width;
@@ -674,7 +846,30 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       fd.highlight_power = highpow;
       fd.gam_lin_thresh = last.gam_lin_thresh;
       const size_t stride = (size_t)g.out_width * nchan * bytes_per_channel;
-      if (strips) {
+      if (peer_mode) {
+         /* every rank's image rows go straight into the image of the rank that owns `out` */
+         void *image = g_peer_image0;
+         const int owner_here = (rank0 == 0);
+         if (owner_here && f3b_image_reserve(lc[0], &fd, &image)) goto gpu_error;
+         if (mode == MODE_PEER_IPC && owner_here && g_peer_image0 && image != g_peer_image0) {
+            fprintf(stderr, "flam3_render (B200): the image buffer moved after its address was given "
+                            "to the other ranks; exchange the addresses again.\n");
+            goto done;
+         }
+         for (int i = 0; i < nlocal; i++) {
+            int s0 = (rank0 + i) * strip_rows_per, s1 = s0 + strip_rows_per;
+            if (s0 > g.image_height) s0 = g.image_height;
+            if (s1 > g.image_height) s1 = g.image_height;
+            if (s1 <= s0) continue;
+            if (f3b_finish_rows_into(lc[i], &fd, s0, s1, image)) {
+               ctx = lc[i];
+               goto gpu_error;
+            }
+         }
+         if (mode == MODE_PEER_LOCAL ? f3b_group_barrier(lc, nlocal) : ((*g_barrier)(ctx, g_barrier_user), 0))
+            goto gpu_error;
+         if (owner_here && !g_device_only && f3b_image_download(lc[0], &fd, out, stride)) goto gpu_error;
+      } else if (strips) {
          void *image = NULL;
          if (f3b_finish_device_rows(ctx, &fd, strip_row0, strip_row1, strip_rows_per * g_nranks, &image) ||
              (!g_stream_ordered && f3b_sync(ctx)))
@@ -688,10 +883,13 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          goto gpu_error;
    }
 
-   {
+   for (int i = 0; i < nlocal; i++) {
       double bv = 0.0;
-      if (f3b_badvals(ctx, &bv)) goto gpu_error;
-      stats->badvals = bv;
+      if (f3b_badvals(lc[i], &bv)) {
+         ctx = lc[i];
+         goto gpu_error;
+      }
+      stats->badvals += bv;
    }
 
    if (getenv("insert_palette") && out && !g_device_only) { /* debug aid of the reference, rect.c:1267-1279 */
@@ -719,7 +917,8 @@ done:
    free(temporal_filter);
    free(temporal_deltas);
    free(filter);
-   if (f3b_inputs_consumed(ctx)) rv = 1;
+   for (int i = 0; i < nlocal; i++)
+      if (f3b_inputs_consumed(lc[i])) rv = 1;
    blobs.used = 0;
    g_blobs = blobs;
    free(jobs);

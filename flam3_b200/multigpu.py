@@ -115,3 +115,60 @@ def make_strip_gather(rank, nranks, dist=None, core=None, stream_ordered=False):
         torch.cuda.synchronize()
 
     return gather
+
+
+def setup_peer_strips(gpu, core, rank, nranks, genomes, dist=None, **render_kw):
+    """One process per GPU, strips reduced over peer memory (include/flam3_b200.h, "several
+    GPUs on one frame"): every rank renders once on its own so that its bucket planes and image
+    exist, their CUDA IPC handles go round with an all-gather, and the drop-in is told where
+    every rank's buckets and rank 0's image are. From then on a flam3_render call on every
+    rank renders ONE frame together: rank r runs its share of the chains, sums the buckets of
+    its strip of rows out of the peers' memory over NVLink and writes its image rows into rank
+    0's image; only rank 0's `out` receives the picture. The barriers between the steps are
+    one-element NCCL all-reduces issued on the render stream (no host synchronisation).
+    Must be called again if a later frame is larger (the planes are reallocated)."""
+    import torch
+
+    if dist is None:
+        import torch.distributed as dist
+    gpu.set_peers(None, None)
+    gpu.set_exchange(None)
+    gpu.set_strip_gather(None)
+    gpu.set_shard(rank, nranks)
+    gpu.set_device_only(True)
+    _, st, _ = gpu.render(genomes, **render_kw)  # allocates buckets, count plane, image
+    gpu.set_device_only(False)
+    assert st["rv"] == 0, st
+    ctx = gpu.render_context(core)
+    ctx.sync()
+    color, count, _ = ctx.hist_ptrs()
+    image = ctx.image_ptr()
+    mine = [ctx.ipc_export(color), ctx.ipc_export(count) if count else bytes(64), ctx.ipc_export(image)]
+    t = torch.tensor(list(b"".join(mine)), dtype=torch.uint8, device="cuda")
+    allh = torch.empty(nranks * t.numel(), dtype=torch.uint8, device="cuda")
+    dist.all_gather_into_tensor(allh, t)
+    allh = bytes(allh.cpu().tolist())
+    peers, image0 = [], None
+    for r in range(nranks):
+        h = allh[r * 192:(r + 1) * 192]
+        if r == rank:
+            peers.append((color, count))
+            if r == 0:
+                image0 = image
+            continue
+        c = ctx.ipc_open(h[:64])
+        n = ctx.ipc_open(h[64:128]) if count else None
+        peers.append((c, n))
+        if r == 0:
+            image0 = ctx.ipc_open(h[128:192])
+    gpu.set_peers(peers, image0)
+    stream = _render_stream(core._dll, ctx.ptr)
+    token = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def barrier(_ctx_ptr):
+        with torch.cuda.stream(stream):
+            dist.all_reduce(token, op=dist.ReduceOp.SUM)
+
+    gpu.set_barrier(barrier)
+    gpu.set_stream_ordered(True)
+    return peers

@@ -168,8 +168,45 @@ size_t f3b_hist_elems(f3b_ctx *ctx);
 void *f3b_accum_ptr(f3b_ctx *ctx);      /* device float4[height*width] */
 void *f3b_stream_ptr(f3b_ctx *ctx);     /* cudaStream_t the context launches on */
 
+/* ---- several GPUs on one frame (rect.c:840 splits the sample budget over threads the
+ * same way) ---------------------------------------------------------
+ * Every rank runs its share of the chains into its own buckets (f3b_iterate's rank/nranks).
+ * Then rank r owns the image rows of strip r: it sums, straight out of the peers' memory
+ * over NVLink, all ranks' buckets of the bucket rows that strip needs (its rows plus the
+ * halo the widest density-estimation kernel and the spatial filter reach: overlapping rows
+ * are simply fetched by both neighbours), saturating like the buckets do, and the post-pass
+ * of those rows reads the sum: a reduce-scatter by image strip fused into one kernel. Its
+ * image rows go straight into the image of the rank that owns `out` (f3b_finish_rows_into
+ * with a peer pointer). The caller orders the steps: all ranks' f3b_iterate before any
+ * f3b_hist_reduce_rows, every reduce before any rank clears its buckets again
+ * (f3b_group_barrier for contexts of one process; ranks in separate processes exchange
+ * pointers with f3b_ipc_* and synchronise their streams themselves). */
+typedef struct {
+   void *color; /* f3b_hist_color_ptr of that rank, valid on this context's device */
+   void *count; /* f3b_hist_count_ptr, NULL without a count plane */
+} f3b_peer_hist;
+/* lets this context's device read and write `peer`'s memory (same process) */
+int f3b_peer_enable(f3b_ctx *ctx, f3b_ctx *peer);
+/* buckets of rows [row0,row1) summed over peers[0..npeers) (this rank included) become what
+ * f3b_density_rows / f3b_density read until the next f3b_hist_clear / f3b_frame_begin */
+int f3b_hist_reduce_rows(f3b_ctx *ctx, const f3b_peer_hist *peers, int npeers, int row0, int row1);
+/* every context's stream waits until all n streams have reached this point (one process) */
+int f3b_group_barrier(f3b_ctx *const *ctxs, int n);
+/* device image of d->image_height rows, allocated now so that peers can be told where it is */
+int f3b_image_reserve(f3b_ctx *ctx, const f3b_final_desc *d, void **dev_image);
+void *f3b_image_ptr(f3b_ctx *ctx);
+/* like f3b_finish_device_rows, but the rows go into `dev_image` (own or a peer's) */
+int f3b_finish_rows_into(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int row1, void *dev_image);
+/* CUDA IPC for ranks in separate processes: 64-byte handles of device allocations (the
+ * pointers returned by f3b_hist_color_ptr / f3b_hist_count_ptr / f3b_image_ptr) */
+int f3b_ipc_export(f3b_ctx *ctx, const void *dev_ptr, unsigned char handle[64]);
+int f3b_ipc_open(f3b_ctx *ctx, const unsigned char handle[64], void **dev_ptr);
+int f3b_ipc_close(f3b_ctx *ctx, void *dev_ptr);
+int f3b_device_index(f3b_ctx *ctx);
+
 /* ---- instrumentation ------------------------------------------------------------- */
-enum { F3B_STAGE_ITERATE = 0, F3B_STAGE_DENSITY = 1, F3B_STAGE_FINAL = 2, F3B_NSTAGES = 3 };
+enum { F3B_STAGE_ITERATE = 0, F3B_STAGE_DENSITY = 1, F3B_STAGE_FINAL = 2, F3B_STAGE_EXCHANGE = 3,
+       F3B_NSTAGES = 4 };
 /* GPU milliseconds (CUDA events on the context stream) and launch count of a stage since
  * f3b_stats_reset; synchronises the stream. */
 int f3b_stage_stats(f3b_ctx *ctx, int stage, double *ms, uint64_t *launches);

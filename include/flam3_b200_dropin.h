@@ -18,6 +18,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "flam3_b200.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -27,7 +29,6 @@ struct flam3_frame_s;
 typedef struct flam3_frame_opaque flam3_frame;
 typedef struct stat_struct_opaque stat_struct;
 #endif
-struct f3b_ctx;
 
 /* Replaces flam3.c:3894-3932 (dispatch on bits / nthreads) and the six instantiations of
  * rect.c:render_rectangle behind it. Same arguments, same return convention (0 ok, 1 error
@@ -73,6 +74,19 @@ void f3b_render_set_stream_ordered(int on);
 typedef void (*f3b_gather_fn)(struct f3b_ctx *, void *image, size_t row_bytes, int rows_per,
                               void *user);
 void f3b_render_set_strip_gather(f3b_gather_fn cb, void *user);
+
+/* ---- several GPUs on one frame (see include/flam3_b200.h) ---------------------------
+ * In ONE process: set F3B_DEVICES ("0-7", "0,2", ...) before the first call; every
+ * flam3_render then spreads its frame over those devices and `out` receives the whole image.
+ * f3b_render_context_at(i) is the i-th of them.
+ * In SEPARATE processes (one GPU each, e.g. under torchrun): f3b_render_set_shard(rank, n),
+ * then tell every rank where all ranks' buckets and rank 0's image are (device pointers valid
+ * in the calling process: CUDA IPC, f3b_ipc_export / f3b_ipc_open) and give a callback that
+ * enqueues a barrier over all ranks on the render stream. Only rank 0's `out` is written.
+ */
+struct f3b_ctx *f3b_render_context_at(int i);
+void f3b_render_set_peers(int nranks, const f3b_peer_hist *peers /* [nranks] */, void *image0);
+void f3b_render_set_barrier(void (*cb)(struct f3b_ctx *, void *), void *user);
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,24 @@ def test_flam3_animate_cli_frames(tmp_path):
     assert 20.0 < psnr(frames[0], frames[1]) < 60.0
 
 
+def test_flam3_animate_cli_matches_the_reference_cli(tmp_path):
+    """Config C4's two sides, frame by frame: the unmodified flam3-animate linked against the
+    drop-in against the same program linked against the unmodified library (1000 temporal
+    samples per frame, motion blur). Bound as everywhere: as close to a reference render as a
+    second reference render with another seed is, less 1.5 dB."""
+    tmp = str(tmp_path)
+    times = {"begin": "20", "end": "21"}
+    run_cli(os.path.join(ROOT, "dropin", "_build", "flam3-animate"), tmp, "g_", times)
+    run_cli(os.path.join(ROOT, "oracle", "_ref", "flam3-animate-ref"), tmp, "ra_", dict(times, nthreads="8"))
+    run_cli(os.path.join(ROOT, "oracle", "_ref", "flam3-animate-ref"), tmp, "rb_",
+            dict(times, nthreads="8", isaac_seed="another"))
+    for t in (20, 21):
+        g, a, b = (read_ppm(os.path.join(tmp, "%s%05d.ppm" % (p, t))) for p in ("g_", "ra_", "rb_"))
+        assert g.shape == a.shape == (480, 640, 3)
+        assert min(psnr(g, a), psnr(g, b)) >= psnr(a, b) - 1.5, (t, psnr(g, a), psnr(g, b), psnr(a, b))
+        assert abs(g.mean() - a.mean()) <= max(0.5, 0.02 * a.mean())
+
+
 def test_animate_frame_scheduler_round_robin(tmp_path):
     """flam3_b200.animate deals the frames of one flam3-animate job
     round-robin to worker processes (one per GPU; here two workers on the one GPU). Every

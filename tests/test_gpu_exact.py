@@ -68,13 +68,15 @@ def test_carries_leave_the_histogram_unchanged(flame0, variant):
 
 
 def test_sums_above_2_pow_24_are_exact():
-    """A collapsed attractor at a quality that puts ~1e8 into single uint32 channels: with and
-    without warp aggregation, and as three shards against one, the buckets are identical and
-    the bookkeeping reports no staged value at 2^24."""
+    """A collapsed attractor at a quality that puts ~1e8 into single uint32 channels. Such a
+    bucket fills faster than a staging copy can be emptied, so the library must pick the
+    aggregating kernels by itself (probe), whose multi-lane sums go straight into the integer
+    buckets. Regrouping the adds - three shards against one - gives identical buckets (rounded
+    float sums would not), and the bookkeeping reports no staged value at 2^24."""
     _, gpu, core = libs()
     gg = gpu.parse(COLLAPSED % 400.0)
     ctx = _ctx(gpu, core, gg)
-    a, (lost_a, _) = _hist(gpu, ctx, gg, {"F3B_AGG": "0"}, isaac_seed="big", sub_batch_size=500)
+    a, (lost_a, _) = _hist(gpu, ctx, gg, {}, isaac_seed="big", sub_batch_size=500)
     b, (lost_b, _) = _hist(gpu, ctx, gg, {"F3B_AGG": "1"}, isaac_seed="big", sub_batch_size=500)
     assert a.max() > 4 * 2 ** 24, a.max()
     assert lost_a == 0 and lost_b == 0
@@ -91,6 +93,23 @@ def test_sums_above_2_pow_24_are_exact():
     finally:
         gpu.set_shard(0, 1)
     assert np.array_equal(parts[0] + parts[1] + parts[2], a)
+
+
+def test_headline_frame_is_exact(flame0):
+    """C2 (1080p, quality 2000): the fullest bucket collects 2.1e9 per channel, 125x what a
+    float sum holds exactly. No staged value may be seen at 2^24, the count channel must be a
+    whole number of hits everywhere (every add is 255), and its total must be the number of
+    in-frame iterations."""
+    _, gpu, core = libs()
+    gg = gpu.parse(resize(flame0, 1920, 1080, scale=540, quality=2000, oversample=1, temporal_samples=1))
+    ctx = _ctx(gpu, core, gg)
+    h, (lost, sat) = _hist(gpu, ctx, gg, {}, isaac_seed="c2-exact")
+    assert h[..., 4].max() > 50 * 2 ** 24
+    assert lost == 0 and sat == 0
+    assert (h[..., 4] % 255 == 0).all()
+    assert (h[..., 3] == h[..., 4]).all()   # alpha doubles as the count for this genome
+    hits = int(h[..., 4].sum() // 255)
+    assert 0.74 * 4147200000 < hits < 0.76 * 4147200000
 
 
 @pytest.mark.parametrize("through", ["merge", "sweepers"])
