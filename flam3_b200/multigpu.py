@@ -117,6 +117,15 @@ def make_strip_gather(rank, nranks, dist=None, core=None, stream_ordered=False):
     return gather
 
 
+_opened = {}  # CUDA IPC handle -> device pointer in this process (a handle is opened once)
+
+
+def _ipc_open(ctx, handle):
+    if handle not in _opened:
+        _opened[handle] = ctx.ipc_open(handle)
+    return _opened[handle]
+
+
 def setup_peer_strips(gpu, core, rank, nranks, genomes, dist=None, **render_kw):
     """One process per GPU, strips reduced over peer memory (include/flam3_b200.h, "several
     GPUs on one frame"): every rank renders once on its own so that its bucket planes and image
@@ -156,11 +165,11 @@ def setup_peer_strips(gpu, core, rank, nranks, genomes, dist=None, **render_kw):
             if r == 0:
                 image0 = image
             continue
-        c = ctx.ipc_open(h[:64])
-        n = ctx.ipc_open(h[64:128]) if count else None
+        c = _ipc_open(ctx, h[:64])
+        n = _ipc_open(ctx, h[64:128]) if count else None
         peers.append((c, n))
         if r == 0:
-            image0 = ctx.ipc_open(h[128:192])
+            image0 = _ipc_open(ctx, h[128:192])
     gpu.set_peers(peers, image0)
     stream = _render_stream(core._dll, ctx.ptr)
     token = torch.zeros(1, dtype=torch.int32, device="cuda")
