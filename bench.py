@@ -352,6 +352,7 @@ def main():
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    barrier()  # starting the sampler takes rank 0 a while: everybody enters the timed region together
     ctx.timer_start()
     for i in range(args.steps):
         render(out, i)

@@ -45,6 +45,17 @@ struct f3b_ctx {
    DevBuf exact_color, exact_count, sat_list;   /* the buckets proper (f3b_internal.h) */
    DevBuf xfer;                 /* staging of f3b_hist_upload/download_u32 (kept across calls) */
    DevBuf hot_list, hot_bitmap; /* the sweepers' list of fast-growing staging entries */
+   /* binned scatter (f3b_iterate.cu): the staging planes are ONE L2-sized tile, hits travel
+    * as records through per-region queues */
+   bool binned = false;
+   int bin_regions = 0, bin_region_rows = 0;
+   uint32_t bin_magic = 0;
+   size_t bin_cap = 0, bin_tile_elems = 0;
+   DevBuf bin_records, bin_pos, bin_table;
+   bool bin_forced = false;     /* F3B_BINNED=1: always, else only when f3b_iterate finds it safe */
+   bool bin_batch_open = false;
+   uint64_t bin_batch_iters = 0;
+   unsigned bin_launch_seq = 0;
    /* several GPUs on one frame: the strip of rows this context owns, summed over all ranks */
    DevBuf reduced_color, reduced_count;
    bool view_reduced = false;
@@ -189,7 +200,7 @@ void f3b_ctx_destroy(f3b_ctx *ctx) {
    cudaSetDevice(ctx->device);
    cudaStreamSynchronize(ctx->stream);
    DevBuf *bufs[] = {&ctx->exact_color, &ctx->exact_count, &ctx->sat_list, &ctx->xfer,
-                     &ctx->reduced_color, &ctx->reduced_count,
+                     &ctx->reduced_color, &ctx->reduced_count, &ctx->bin_records, &ctx->bin_pos, &ctx->bin_table,
                      &ctx->hot_list, &ctx->hot_bitmap,
                      &ctx->hist_color, &ctx->hist_count, &ctx->accum,    &ctx->image,
                      &ctx->blobs,      &ctx->jobs,       &ctx->groups,   &ctx->de_coefs,
@@ -266,9 +277,46 @@ int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel, int 
    CK(cudaSetDevice(ctx->device));
    const size_t n = (size_t)width * height;
    size_t nh = 0;
-   const F3HistLayout lay = hist_layout_for(width, height, count_channel, &nh);
-   const size_t nalloc = lay.replica_stride * lay.replicas;
+   const F3HistLayout lay0 = hist_layout_for(width, height, count_channel, &nh);
    const int f64 = bits == 64;
+   /* Histograms that do not fit L2 are filled through binned records (f3b_iterate.cu): bands
+    * of rows whose float4 tile is F3B_BIN_REGION_MB (48) big, a record pool of F3B_BIN_MEM_MB
+    * (12288). Integer buckets only (a record carries whole numbers <= 255). F3B_BINNED=0/1
+    * overrides the size rule. */
+   F3HistLayout lay = lay0;
+   bool binned = false;
+   int bin_regions = 0, bin_rows = 0;
+   uint32_t bin_magic = 0;
+   size_t bin_cap = 0;
+   {
+      const double plane_mb = (double)lay0.replica_stride * (count_channel ? 20.0 : 16.0) / 1048576.0;
+      const char *be = getenv("F3B_BINNED");
+      bool want = !f64 && (be ? atoi(be) != 0 : plane_mb > 110.0);
+      if (want) {
+         const char *re = getenv("F3B_BIN_REGION_MB");
+         double region_mb = re && atof(re) > 0.0 ? atof(re) : 48.0;
+         int R = (int)ceil(plane_mb / region_mb);
+         if (R < 1) R = 1;
+         if (R > F3B_BIN_MAX_REGIONS) R = F3B_BIN_MAX_REGIONS;
+         bin_rows = (height + R - 1) / R;
+         bin_regions = (height + bin_rows - 1) / bin_rows;
+         bin_magic = (uint32_t)((0x100000000ull + (uint64_t)bin_rows - 1) / (uint64_t)bin_rows);
+         bool ok = (size_t)bin_rows * lay0.pitch <= 0xffffffull;
+         for (int y = 0; y < height && ok; y++)
+            ok = (uint32_t)(((uint64_t)(uint32_t)y * bin_magic) >> 32) == (uint32_t)(y / bin_rows);
+         const char *me = getenv("F3B_BIN_MEM_MB");
+         const double mem_mb = me && atof(me) > 0.0 ? atof(me) : 12288.0;
+         bin_cap = (size_t)(mem_mb * 1048576.0 / 256.0); /* blocks of 32 records */
+         if (bin_cap > 0x7ffffff0ull) bin_cap = 0x7ffffff0ull;
+         if (bin_cap < (1u << 15)) ok = false;
+         binned = ok;
+      }
+      /* the staging planes keep their full size: f3b_iterate decides per frame which path
+       * fills them (the tile of the binned path is their first bin_rows rows) */
+      if (binned) lay.replicas = 1;
+      ctx->bin_forced = binned && be != nullptr;
+   }
+   const size_t nalloc = lay.replica_stride * lay.replicas;
    const void *before[2] = {ctx->hist_color.p, ctx->hist_count.p};
    if (ensure(ctx, ctx->hist_color, nalloc * sizeof(float4))) return 1;
    if (ensure(ctx, ctx->accum, n * sizeof(float4))) return 1;
@@ -284,6 +332,17 @@ int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel, int 
        ctx->lay.replica_stride != lay.replica_stride || ctx->lay.replicas != lay.replicas ||
        ctx->count_channel != (count_channel ? 1 : 0))
       ctx->staging_dirty = true;
+   if (binned) {
+      if (ensure(ctx, ctx->bin_records, bin_cap * 32 * sizeof(uint2))) return 1;
+      if (ensure(ctx, ctx->bin_table, bin_cap)) return 1;
+      if (ensure(ctx, ctx->bin_pos, 4 * sizeof(unsigned int))) return 1;
+   }
+   ctx->binned = binned;
+   ctx->bin_regions = bin_regions;
+   ctx->bin_region_rows = bin_rows;
+   ctx->bin_magic = bin_magic;
+   ctx->bin_cap = bin_cap;
+   ctx->bin_tile_elems = binned ? (size_t)bin_rows * lay.pitch : 0;
    ctx->lay = lay;
    ctx->hist_elems = nh;
    ctx->width = width;
@@ -496,6 +555,24 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    P.floor_adds = floor_adds;
    P.seed = seed;
    P.badvals = ctx->d_badvals;
+   /* Binned scatter or direct reductions? (only a question when the planes exceed L2.) The
+    * tile of the binned path collects a whole batch - up to the record pool's worth of
+    * iterations - before it is merged into the integer buckets, so its fullest bucket must
+    * stay below 2^24 over a batch: known only from the previous frame of the same genome
+    * structure and size (the merge records the fullest bucket's share). Spread-out histograms
+    * (motion blur over many temporal samples) qualify and gain ~20 %; a still with hot buckets
+    * is both exact and faster through the direct path with its sweepers. */
+   bool binned = false;
+   double bin_safe_iters = 0.0;
+   if (ctx->binned && floor_adds) {
+      const uint64_t sig = genome_signature((const uint32_t *)((const char *)blobs + jobs[0].blob_offset),
+                                            ctx->width, ctx->height);
+      const bool known = ctx->hot_share >= 0.0 && ctx->hot_share_signature == sig;
+      /* iterations a batch may hold so that the fullest bucket gains < 2^23 in it */
+      const double safe_iters = known ? 8388608.0 / (255.0 * (ctx->hot_share > 1e-12 ? ctx->hot_share : 1e-12)) : 0.0;
+      binned = ctx->bin_forced || safe_iters >= 2e8; /* smaller batches are latency bound */
+      bin_safe_iters = ctx->bin_forced ? 1e18 : safe_iters;
+   }
    P.exact_color = ctx->exact_color.p;
    P.exact_count = ctx->count_channel ? ctx->exact_count.p : nullptr;
    P.exact_f64 = (uint32_t)ctx->f64;
@@ -519,6 +596,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       P.sweep_on = ((double)it / nranks) * 255.0 >= carry ? 1u : 0u;
       const char *e = getenv("F3B_SWEEP");
       if (e) P.sweep_on = atoi(e) ? 1u : 0u;
+      if (binned) P.sweep_on = 0; /* the tile is merged into the exact buckets after every batch */
       const double plane_bytes = (double)(ctx->lay.replica_stride * ctx->lay.replicas) * (ctx->count_channel ? 20.0 : 16.0);
       double gap_us = plane_bytes / 100e9 * 1e6;
       if (gap_us < 2000.0) gap_us = 2000.0;
@@ -533,8 +611,23 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
                             (ctx->lay.replica_stride * ctx->lay.replicas + 31) / 32 * sizeof(uint32_t), ctx->stream));
       }
    }
-   const int bps = f3b_iterate_blocks_per_sm(group_size, max_blob);
-   if (bps <= 0) return fail(ctx, "f3b_iterate: kernel does not fit with %zu bytes of shared memory", max_blob);
+   /* binned scatter: per-warp region queues behind the blob in shared memory */
+   P.bin_regions = 0;
+   size_t smem_bytes = max_blob;
+   if (binned) {
+      P.bin_regions = (uint32_t)ctx->bin_regions;
+      P.bin_region_rows = (uint32_t)ctx->bin_region_rows;
+      P.bin_row_magic = ctx->bin_magic;
+      P.bin_cap = (uint32_t)ctx->bin_cap;
+      P.bin_smem_off = (uint32_t)((max_blob + 15) / 16 * 4);
+      P.bin_warp_words = (uint32_t)(32 + ctx->bin_regions * 130); /* 65 records per region: queues start in different banks */
+      P.bin_records = (uint2 *)ctx->bin_records.p;
+      P.bin_block_region = (uint8_t *)ctx->bin_table.p;
+      P.bin_pos = (unsigned int *)ctx->bin_pos.p;
+      smem_bytes = (size_t)P.bin_smem_off * 4 + (size_t)(group_size / 32) * P.bin_warp_words * 4;
+   }
+   const int bps = f3b_iterate_blocks_per_sm(group_size, smem_bytes);
+   if (bps <= 0) return fail(ctx, "f3b_iterate: kernel does not fit with %zu bytes of shared memory", smem_bytes);
    ctx->staging_dirty = true;
 
    /* One launch per `cap` temporal samples (their warp-uniform camera and chooser constants
@@ -620,6 +713,109 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       int grid = ctx->sms * bps;
       if ((uint32_t)grid > local_groups) grid = (int)local_groups;
       cudaStream_t st = fork ? ctx->side[chunk % F3B_SIDE_STREAMS] : ctx->stream;
+      if (binned) {
+         /* A BATCH is as many of this rank's chain groups as the record pool holds for certain
+          * (one record per iteration in the worst case). Its launches - one per group of
+          * temporal samples that share a parameter block - run side by side on the side
+          * streams; then the pool is applied region by region to the L2-resident tile and the
+          * tile merged into the region's exact buckets; repeat. */
+         if (chunk == 0) {
+            uint64_t total_iters = 0;
+            for (int j = 0; j < n_jobs; j++) total_iters += jobs[j].n_iters;
+            ctx->hot_signature = genome_signature(
+                (const uint32_t *)((const char *)blobs + jobs[0].blob_offset), ctx->width, ctx->height);
+            ctx->hot_iters = total_iters;
+         }
+         /* pool blocks that may stay unfilled: the last hand-out of 32 and one padded block per
+          * region for every warp of every launch that can be in flight */
+         const uint64_t slack = (uint64_t)(F3B_SIDE_STREAMS + 1) * ctx->sms * bps * (group_size / 32) *
+                                (uint64_t)(ctx->bin_regions + 33);
+         if (ctx->bin_cap <= slack + 1024) return fail(ctx, "f3b_iterate: record pool too small; raise F3B_BIN_MEM_MB");
+         uint64_t room = (ctx->bin_cap - slack) * 32;
+         if ((double)room > bin_safe_iters) room = (uint64_t)bin_safe_iters;
+         auto batch_begin = [&]() -> int {
+            CK(cudaMemsetAsync(ctx->bin_pos.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+            CK(cudaMemsetAsync(ctx->bin_table.p, 0xff, ctx->bin_cap, ctx->stream));
+            if (fork) {
+               CK(cudaEventRecord(ctx->fork_ev, ctx->stream));
+               for (int i = 0; i < F3B_SIDE_STREAMS; i++) CK(cudaStreamWaitEvent(ctx->side[i], ctx->fork_ev, 0));
+            }
+            ctx->bin_batch_open = true;
+            ctx->bin_batch_iters = 0;
+            return 0;
+         };
+         auto batch_end = [&]() -> int {
+            if (fork)
+               for (int i = 0; i < F3B_SIDE_STREAMS; i++) {
+                  CK(cudaEventRecord(ctx->join_ev[i], ctx->side[i]));
+                  CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
+               }
+            for (int r = 0; r < ctx->bin_regions; r++) {
+               if (!f3b_launch_bin_apply((const uint2 *)ctx->bin_records.p, (const uint8_t *)ctx->bin_table.p,
+                                         (const unsigned int *)ctx->bin_pos.p, (uint32_t)ctx->bin_cap, (uint32_t)r,
+                                         (float4 *)ctx->hist_color.p,
+                                         ctx->count_channel ? (float *)ctx->hist_count.p : nullptr, ctx->stream))
+                  return fail(ctx, "record apply launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+               const size_t off = (size_t)r * ctx->bin_tile_elems;
+               F3MergeParams M;
+               M.color = (float4 *)ctx->hist_color.p;
+               M.count = ctx->count_channel ? (float *)ctx->hist_count.p : nullptr;
+               M.exact_color = (char *)ctx->exact_color.p + off * sizeof(uint4);
+               M.exact_count = ctx->count_channel ? (char *)ctx->exact_count.p + off * sizeof(uint32_t) : nullptr;
+               M.f64 = 0;
+               M.elems = ctx->hist_elems - off < ctx->bin_tile_elems ? ctx->hist_elems - off : ctx->bin_tile_elems;
+               M.lay = ctx->lay;
+               M.hot_max = (unsigned int *)(ctx->d_badvals + 1);
+               M.exact_flags = ctx->d_badvals + F3B_CTR_LOST;
+               M.sat_list = (const uint32_t *)ctx->sat_list.p;
+               M.sat_check = 0;
+               if (f3b_launch_hist_merge(M, ctx->stream) < 0)
+                  return fail(ctx, "tile merge launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+               launches += 2;
+            }
+            ctx->bin_batch_open = false;
+            return 0;
+         };
+         auto launch_range = [&](uint32_t ga, uint32_t gb, uint32_t mine) -> int {
+            F3IterateParams Q = P;
+            Q.group_begin = ga;
+            Q.n_groups = gb;
+            int qgrid = ctx->sms * bps;
+            if ((uint32_t)qgrid > mine) qgrid = (int)mine;
+            cudaStream_t qs = fork ? ctx->side[(ctx->bin_launch_seq++) % F3B_SIDE_STREAMS] : ctx->stream;
+            if (!f3b_launch_iterate(Q, consts.data(), j1 - j0, ctx->count_channel != 0, simple, true, qgrid,
+                                    group_size, smem_bytes, qs))
+               return fail(ctx, "chaos-game launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            launches++;
+            return 0;
+         };
+         if (chunk == 0) ctx->bin_batch_open = false;
+         const uint32_t g_first = P.group_begin + ((uint32_t)rank + (uint32_t)nranks - P.group_begin % (uint32_t)nranks) % (uint32_t)nranks;
+         const uint32_t g_end = P.n_groups;
+         uint32_t ga = P.group_begin, mine = 0;
+         for (uint32_t g = g_first; g < g_end; g += (uint32_t)nranks) {
+            const f3b_job &jb = jobs[group_job[g]];
+            const uint64_t first_chain = (uint64_t)(g - jb.first_group) * group_size;
+            uint64_t nch = jb.n_chains > first_chain ? jb.n_chains - first_chain : 0;
+            if (nch > (uint64_t)group_size) nch = group_size;
+            const uint64_t gi = nch * (jb.n_iters / jb.n_chains + 1);
+            if (gi > room)
+               return fail(ctx, "f3b_iterate: one chain group (%llu iterations) exceeds the record pool (%llu records); raise F3B_BIN_MEM_MB",
+                           (unsigned long long)gi, (unsigned long long)room);
+            if (ctx->bin_batch_open && ctx->bin_batch_iters + gi > room) { /* the pool is full: close the batch */
+               if (mine && launch_range(ga, g, mine)) return 1;
+               if (batch_end()) return 1;
+               ga = g;
+               mine = 0;
+            }
+            if (!ctx->bin_batch_open && batch_begin()) return 1;
+            ctx->bin_batch_iters += gi;
+            mine++;
+         }
+         if (mine && launch_range(ga, g_end, mine)) return 1;
+         if (j1 >= n_jobs && ctx->bin_batch_open && batch_end()) return 1; /* last parameter block */
+         continue;
+      }
       if (chunk == 0) {
          /* Does the attractor collapse onto a few buckets? Then the adds must be aggregated
           * across the warp, or they serialise on a handful of L2 addresses. A spread-out flame
@@ -667,15 +863,22 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          }
       }
       const int nl = f3b_launch_iterate(P, consts.data(), j1 - j0, ctx->count_channel != 0, simple,
-                                        aggregate, grid, group_size, max_blob, st);
+                                        aggregate, grid, group_size, smem_bytes, st);
       if (!nl) return fail(ctx, "chaos-game launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       launches += nl;
    }
-   if (fork)
+   if (fork && !binned)
       for (int i = 0; i < F3B_SIDE_STREAMS; i++) {
          CK(cudaEventRecord(ctx->join_ev[i], ctx->side[i]));
          CK(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
       }
+   if (binned) { /* every tile has been merged already */
+      ctx->staging_dirty = false;
+      ctx->hot_measured = true;
+      ctx->hot_from_merge = true;
+      ctx->hot_total = 255.0 * (double)ctx->hot_iters / (double)nranks;
+      return stage_end(ctx, launches);
+   }
    /* staging copies -> exact buckets; the merge sees this rank's whole histogram (1/nranks of
     * the hits) and also records the fullest bucket */
    F3MergeParams M;

@@ -131,6 +131,15 @@ struct F3IterateParams {
                                        lost), [1] entries in sat_list, [4..6] diagnostics: where
                                        the losses were seen (cold pass, hot list, merge) */
    uint32_t *sat_list;           /* device: bucket * 8 + channel of exact sums that wrapped */
+   /* binned scatter (histograms that do not fit L2; AGG kernels only, see f3b_iterate.cu):
+    * hits become 8-byte records in per-region queues instead of reductions */
+   uint32_t bin_regions;         /* 0 = off; else regions of bin_region_rows bucket rows each */
+   uint32_t bin_region_rows, bin_row_magic; /* region of row y = umulhi(y, magic) */
+   uint32_t bin_cap;             /* blocks of 32 records in the pool */
+   uint32_t bin_smem_off, bin_warp_words; /* per-warp queues in shared memory, in words */
+   uint2 *bin_records;           /* device: the pool, [bin_cap][32] */
+   uint8_t *bin_block_region;    /* device: [bin_cap] region of every block, 0xff = not used */
+   unsigned int *bin_pos;        /* device: blocks handed out */
    /* probe launch (AGG kernels only): every chain stores at most probe_iters iterations,
     * nothing is added to the histogram, probe_counts[0] += lanes that reached an add,
     * probe_counts[1] += those that shared their bucket with another lane of the warp */
@@ -203,6 +212,12 @@ struct F3FinalParams {
    int out_row_begin, out_row_end; /* image rows produced by this launch */
 };
 int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream);
+
+#define F3B_BIN_MAX_REGIONS 16
+#define F3B_BIN_NULL 0xffffffffu
+/* region queue -> reductions into the L2-resident staging tile of that region */
+int f3b_launch_bin_apply(const uint2 *records, const uint8_t *block_region, const unsigned int *pos, uint32_t cap,
+                         uint32_t region, float4 *tile_color, float *tile_count, cudaStream_t stream);
 
 /* Several GPUs on one frame: rank r owns a strip of bucket rows and sums every rank's
  * buckets of those rows straight out of the peers' memory (NVLink loads), saturating like

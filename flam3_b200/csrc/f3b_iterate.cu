@@ -144,6 +144,125 @@ __device__ __noinline__ bool f3b_bump_aggregate(const F3IterateParams &P, size_t
    return false;
 }
 
+/* ---- binned scatter: histograms larger than L2 --------------------------------------- */
+/* A 4K frame at oversample 2 has 33.6 million buckets (538 MB of float4): scattered
+ * reductions into it are DRAM read-modify-writes of a 32-byte sector per hit and run 3.7x
+ * slower than into an L2-resident plane. So the hit is not applied where it is produced: it
+ * becomes an 8-byte record {bucket within its region | count << 24, r g b a bytes} (the adds
+ * of the integer buckets are whole numbers <= 255) destined for its REGION, a band of bucket
+ * rows whose float4 staging tile fits L2. Every warp keeps a 64-record queue per region in
+ * shared memory; whenever one holds 32 records they go out as one 256-byte block of a global
+ * pool (blocks are handed to warps 32 at a time from one counter; a byte per block says
+ * which region it belongs to): 8 B per hit of sequential DRAM writes instead of 64 B of
+ * scattered sector traffic, and the pool only needs one record per iteration of the launch,
+ * however the hits spread over the regions. After the launch the regions are applied one
+ * after the other (f3b_bin_apply_kernel: the blocks of region r, one vector reduction per
+ * record into the tile, which stays in L2) and each tile is merged into the exact buckets of
+ * its region.
+ * f3b_bin_commit is called by the whole warp at a converged point of the iteration loop (the
+ * queues are warp-private state: lanes arriving in separate groups would race on them). */
+#define F3B_BIN_HDR 32u /* words before the queues: [0..16) records queued per region */
+/* next block of the pool for this warp (warp-uniform state in registers: blocks are handed
+ * out 32 at a time from the global counter) */
+__device__ __forceinline__ uint32_t f3b_bin_block(unsigned int *bin_pos, uint32_t &blk_next, uint32_t &blk_end,
+                                                  unsigned lane) {
+   if (blk_next == blk_end) {
+      uint32_t n = 0;
+      if (lane == 0) n = atomicAdd(bin_pos, 32u);
+      blk_next = __shfl_sync(0xffffffffu, n, 0);
+      blk_end = blk_next + 32u;
+   }
+   return blk_next++;
+}
+/* inlined into the kernel: P's fields then come straight from the constant bank */
+__device__ __forceinline__ void f3b_bin_commit(const F3IterateParams &P, uint32_t *wq, uint32_t a, uint32_t c,
+                                               uint32_t r, uint32_t &blk_next, uint32_t &blk_end) {
+   const unsigned lane = threadIdx.x & 31u;
+   const bool has = a != F3B_BIN_NULL;
+   const unsigned valid = __ballot_sync(0xffffffffu, has);
+   if (!valid) return;
+   uint2 *q = reinterpret_cast<uint2 *>(wq + F3B_BIN_HDR);
+   uint32_t newc = 0;
+   bool full = false;
+   if (has) {
+      const unsigned peers = __match_any_sync(valid, r);
+      const uint32_t base = *(volatile uint32_t *)(wq + r);
+      q[r * 65u + base + __popc(peers & ((1u << lane) - 1u))] = make_uint2(a, c);
+      if ((int)lane == __ffs(peers) - 1) {
+         newc = base + __popc(peers);
+         full = newc >= 32u;
+      }
+   }
+   __syncwarp();
+   if (newc && !full) wq[r] = newc;
+   for (unsigned fm = __ballot_sync(0xffffffffu, full); fm; fm &= fm - 1u) {
+      const int src = __ffs(fm) - 1;
+      const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+      const uint32_t nc = __shfl_sync(0xffffffffu, newc, src);
+      const uint32_t blk = f3b_bin_block(P.bin_pos, blk_next, blk_end, lane);
+      uint2 *qq = q + rr * 65u;
+      const uint2 out = qq[lane];
+      const uint2 rest = qq[32u + lane];
+      if (blk < P.bin_cap) {
+         P.bin_records[(size_t)blk * 32u + lane] = out;
+         if (lane == 0) P.bin_block_region[blk] = (uint8_t)rr;
+      } else if (lane == 0)
+         atomicAdd(P.exact_flags, 32ull); /* cannot happen with the host's sizing; never silent */
+      __syncwarp();
+      if (lane < nc - 32u) qq[lane] = rest;
+      if (lane == 0) wq[rr] = nc - 32u;
+      __syncwarp();
+   }
+}
+/* end of a CTA's work: what is left in the warp's queues goes out, padded to 32 records */
+__device__ __noinline__ void f3b_bin_flush(const F3IterateParams &P, uint32_t *wq, uint32_t blk_next,
+                                           uint32_t blk_end) {
+   const unsigned lane = threadIdx.x & 31u;
+   const uint2 *q = reinterpret_cast<const uint2 *>(wq + F3B_BIN_HDR);
+   __syncwarp();
+   for (uint32_t r = 0; r < P.bin_regions; r++) {
+      const uint32_t c = *(volatile uint32_t *)(wq + r);
+      if (c == 0) continue;
+      const uint32_t blk = f3b_bin_block(P.bin_pos, blk_next, blk_end, lane);
+      const uint2 rec = lane < c ? q[r * 65u + lane] : make_uint2(F3B_BIN_NULL, 0u);
+      if (blk < P.bin_cap) {
+         P.bin_records[(size_t)blk * 32u + lane] = rec;
+         if (lane == 0) P.bin_block_region[blk] = (uint8_t)r;
+      } else if (lane == 0)
+         atomicAdd(P.exact_flags, 32ull);
+      __syncwarp();
+      if (lane == 0) wq[r] = 0;
+   }
+   __syncwarp();
+}
+
+/* the blocks of one region -> reductions into the region's L2-resident tile: a warp looks at
+ * 32 table entries at a time and handles the blocks that are the region's */
+__global__ void __launch_bounds__(256) f3b_bin_apply_kernel(const uint2 *records, const uint8_t *block_region,
+                                                            const unsigned int *pos, uint32_t cap, uint32_t region,
+                                                            float4 *tile_color, float *tile_count) {
+   uint32_t nblk = *pos;
+   if (nblk > cap) nblk = cap;
+   const unsigned lane = threadIdx.x & 31u;
+   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+   for (uint32_t b0 = warp * 32u; b0 < nblk; b0 += nwarps * 32u) {
+      const bool is_mine = b0 + lane < nblk && block_region[b0 + lane] == region;
+      for (unsigned m = __ballot_sync(0xffffffffu, is_mine); m; m &= m - 1u) {
+         const uint2 rec = records[(size_t)(b0 + (uint32_t)__ffs(m) - 1u) * 32u + lane];
+         if (rec.x == F3B_BIN_NULL) continue;
+         const uint32_t idx = rec.x & 0xffffffu, c = rec.y;
+         f3b_red_v4(tile_color + idx, (float)(c & 255u), (float)((c >> 8) & 255u), (float)((c >> 16) & 255u),
+                    (float)(c >> 24));
+         if (tile_count) f3b_red_f32(tile_count + idx, (float)(rec.x >> 24));
+      }
+   }
+}
+int f3b_launch_bin_apply(const uint2 *records, const uint8_t *block_region, const unsigned int *pos, uint32_t cap,
+                         uint32_t region, float4 *tile_color, float *tile_count, cudaStream_t stream) {
+   f3b_bin_apply_kernel<<<148 * 8, 256, 0, stream>>>(records, block_region, pos, cap, region, tile_color, tile_count);
+   return cudaGetLastError() == cudaSuccess ? 1 : 0;
+}
+
 /* examine one staging entry: carry what has reached the threshold; returns the largest
  * channel seen (before the carry) */
 __device__ __forceinline__ float f3b_sweep_entry(const F3IterateParams &P, size_t e, float4 v, float c,
@@ -339,6 +458,12 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
       }
    }
    const size_t rep_off = (size_t)(blockIdx.x % P.lay.replicas) * P.lay.replica_stride;
+   uint32_t *const wq = smem + P.bin_smem_off + (tid >> 5) * P.bin_warp_words; /* binned scatter only */
+   uint32_t blk_next = 0, blk_end = 0; /* no pool blocks in hand */
+   if (AGG && P.bin_regions) { /* this warp's region queues start empty */
+      wq[tid & 31u] = 0u;
+      __syncwarp();
+   }
    uint32_t loaded_job = 0xffffffffu;
    unsigned int bad = 0;
 
@@ -363,14 +488,22 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
       }
 
       const uint32_t chain = (g - job.first_group) * nct + tid; /* nct chains per group */
-      if (chain >= job.n_chains) continue;
+      const bool binned = AGG && P.bin_regions != 0;
+      if (chain >= job.n_chains && !binned) continue;
 
       /* stored iterations of this chain */
       const uint64_t base = job.n_iters / job.n_chains;
       const uint32_t rem = (uint32_t)(job.n_iters % job.n_chains);
-      int n_store = (int)(base + (chain < rem ? 1u : 0u));
-      if (n_store == 0) continue;
+      int n_store = chain < job.n_chains ? (int)(base + (chain < rem ? 1u : 0u)) : 0;
+      if (n_store == 0 && !binned) continue;
       if (AGG && P.probe_iters && n_store > (int)P.probe_iters) n_store = (int)P.probe_iters;
+      /* binned scatter: the lanes of a warp stay together through the loop (the records are
+       * committed by the whole warp), a lane with fewer iterations idles at the end */
+      int n_loop = n_store;
+      if (binned) {
+         n_loop = __reduce_max_sync(0xffffffffu, n_store);
+         if (n_loop == 0) continue;
+      }
 
       /* Flags, chooser stride and palette size share one register (made opaque, or the
        * compiler splits it into a register per flag and spills them); the blob offsets are
@@ -390,7 +523,10 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
       (void)rng.u01();
       uint32_t lastxf = 0;
 
-      for (int i = -(int)job.fuse; i < n_store; i++) {
+      for (int i = -(int)job.fuse; i < n_loop; i++) {
+         uint32_t bin_a = F3B_BIN_NULL, bin_c = 0, bin_r = 0;
+         do { /* `continue` below ends the iteration's work and falls through to the commit */
+         if (binned && (n_store == 0 || i >= n_store)) continue;
          float qx, qy, qc, qv;
          uint32_t fn = 0;
          /* flam3.c:249-270: pick + apply, retrying a bad value up to 4 times in place */
@@ -485,6 +621,12 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
             col = dmap[pi];
             float cnt = 255.0f;
             if (AGG) {
+               if (P.bin_regions) {
+                  bin_r = __umulhi((uint32_t)iy, P.bin_row_magic);
+                  bin_a = (((uint32_t)iy - bin_r * P.bin_region_rows) * (uint32_t)P.lay.pitch + (uint32_t)ix) | (255u << 24);
+                  bin_c = (uint32_t)col.x | ((uint32_t)col.y << 8) | ((uint32_t)col.z << 16) | ((uint32_t)col.w << 24);
+                  continue;
+               }
                float4 tc = col;
                float tn = cnt;
                const bool mine = f3b_bump_aggregate(P, bidx - rep_off, (unsigned long long)bidx, &tc, &tn,
@@ -532,6 +674,12 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
             cnt = floorf(cnt);
          }
          if (AGG) {
+            if (P.bin_regions) { /* floor_adds: whole numbers <= 255 */
+               bin_r = __umulhi((uint32_t)iy, P.bin_row_magic);
+               bin_a = (((uint32_t)iy - bin_r * P.bin_region_rows) * (uint32_t)P.lay.pitch + (uint32_t)ix) | ((uint32_t)cnt << 24);
+               bin_c = (uint32_t)col.x | ((uint32_t)col.y << 8) | ((uint32_t)col.z << 16) | ((uint32_t)col.w << 24);
+               continue;
+            }
             float4 tc = col;
             float tn = cnt;
             const bool mine = f3b_bump_aggregate(P, bidx - rep_off, (unsigned long long)bidx, &tc, &tn,
@@ -542,8 +690,14 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
          }
          f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
          if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
+         } while (0);
+         if (binned) {
+            __syncwarp();
+            f3b_bin_commit(P, wq, bin_a, bin_c, bin_r, blk_next, blk_end);
+         }
       }
    }
+   if (AGG && P.bin_regions) f3b_bin_flush(P, wq, blk_next, blk_end);
 
    /* fic.badvals += badcount (rect.c:408) */
    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
@@ -595,7 +749,8 @@ int f3b_iterate_max_blocks_per_sm(size_t smem_bytes) {
 
 int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes) {
    int nb = 0;
-   const int smax = (int)(F3B_MAX_BLOB_WORDS * 4);
+   /* the blob, plus the per-warp region queues of the binned scatter (AGG kernels) */
+   const int smax = (int)(F3B_MAX_BLOB_WORDS * 4) + 8 * (32 + F3B_BIN_MAX_REGIONS * 130) * 4;
    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
    cudaFuncSetAttribute(f3b_iterate_kernel<true, false, false>, at, smax);
    cudaFuncSetAttribute(f3b_iterate_kernel<false, false, false>, at, smax);

@@ -155,3 +155,41 @@ def test_bits_64_double_buckets(flame0):
     s33, s64, s64c = (h[..., :4].sum(dtype=np.float64) for h in (h33, h64, h64c))
     assert s64 > s33 * 1.0005          # truncation removed a visible amount
     assert abs(s64 - s64c) <= 2e-4 * s64  # downloads truncate per bucket; sums agree
+
+
+@pytest.mark.parametrize("variant", ["alpha_is_count", "count_plane", "opacity_xaos_final", "temporal_samples",
+                                     "one_region"])
+def test_binned_scatter_gives_the_same_histogram(flame0, flame1, variant):
+    """Histograms larger than L2 are filled through per-region record queues and an
+    L2-resident tile (f3b_iterate.cu, binned scatter). Forced here on small frames, with
+    regions of 0.25 MB and queues so small that a frame needs many launches: the buckets must
+    equal those of the direct path bit for bit, also for one shard of three."""
+    _, gpu, core = libs()
+    kw = {}
+    xml = resize(flame0, 320, 240, scale=120, quality=60, temporal_samples=1)
+    if variant == "count_plane":
+        xml = set_flame_attrs(xml, palette_mode="linear")
+    elif variant == "opacity_xaos_final":
+        xml = xml.replace("<xform ", '<xform opacity="0.6" chaos="1 0.3 1" ', 1)
+        xml = xml.replace("</flame>", '<finalxform color="0" symmetry="1" linear="0.9" spherical="0.1" '
+                          'coefs="1 0 0 1 0.05 0"/></flame>')
+    elif variant == "temporal_samples":
+        xml = "<flames>" + resize(flame0, 320, 240, scale=120, quality=60, temporal_samples=700) + \
+              resize(flame1, 320, 240, scale=120, quality=60, temporal_samples=700).replace('time="0"', 'time="100"', 1) + "</flames>"
+        kw = {"ngenomes": 2, "time": 50.0}
+    gg = gpu.parse(xml)
+    ctx = _ctx(gpu, core, gg, **kw)
+    binned_env = {"F3B_BINNED": "1", "F3B_BIN_REGION_MB": "64" if variant == "one_region" else "0.25",
+                  "F3B_BIN_MEM_MB": "160"}
+    direct, _ = _hist(gpu, ctx, gg, {"F3B_BINNED": "0"}, isaac_seed="bin", sub_batch_size=400, **kw)
+    binned, (lost, _) = _hist(gpu, ctx, gg, binned_env, isaac_seed="bin", sub_batch_size=400, **kw)
+    assert direct.sum() > 0 and lost == 0
+    assert np.array_equal(direct, binned), int((direct != binned).any(axis=-1).sum())
+    try:
+        gpu.set_shard(1, 3)
+        d1, _ = _hist(gpu, ctx, gg, {"F3B_BINNED": "0"}, isaac_seed="bin", sub_batch_size=400, **kw)
+        b1, _ = _hist(gpu, ctx, gg, binned_env, isaac_seed="bin", sub_batch_size=400, **kw)
+    finally:
+        gpu.set_shard(0, 1)
+    assert 0 < d1.sum() < direct.sum()
+    assert np.array_equal(d1, b1)
