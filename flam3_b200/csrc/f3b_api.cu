@@ -45,6 +45,7 @@ struct f3b_ctx {
    DevBuf exact_color, exact_count, sat_list;   /* the buckets proper (f3b_internal.h) */
    DevBuf xfer;                 /* staging of f3b_hist_upload/download_u32 (kept across calls) */
    DevBuf hot_list, hot_bitmap; /* the sweepers' list of fast-growing staging entries */
+   DevBuf fixup;                /* final pass: [0] count, [4..] pixels to redo in double */
    /* binned scatter (f3b_iterate.cu): the staging planes are ONE L2-sized tile, hits travel
     * as records through per-region queues */
    bool binned = false;
@@ -65,7 +66,7 @@ struct f3b_ctx {
    bool staging_dirty = true;   /* staging copies may hold something (cleared by the merge) */
    bool swept = false;          /* sweepers have run since the last hist_clear */
    uint64_t lost_exact = 0, saturated = 0; /* as of the last f3b_badvals */
-   DevBuf blobs, jobs, groups, de_coefs, de_radius, filter, de_kidx, de_tiles;
+   DevBuf blobs, jobs, groups, de_coefs, de_radius, de_kparam, de_d2max, filter, de_kidx, de_tiles;
    std::vector<float> de_coefs_host;    /* what de_coefs / de_radius / filter hold on the device */
    std::vector<uint8_t> de_radius_host;
    std::vector<double> filter_host;
@@ -201,10 +202,11 @@ void f3b_ctx_destroy(f3b_ctx *ctx) {
    cudaStreamSynchronize(ctx->stream);
    DevBuf *bufs[] = {&ctx->exact_color, &ctx->exact_count, &ctx->sat_list, &ctx->xfer,
                      &ctx->reduced_color, &ctx->reduced_count, &ctx->bin_records, &ctx->bin_pos, &ctx->bin_table,
-                     &ctx->hot_list, &ctx->hot_bitmap,
+                     &ctx->hot_list, &ctx->hot_bitmap, &ctx->fixup,
                      &ctx->hist_color, &ctx->hist_count, &ctx->accum,    &ctx->image,
                      &ctx->blobs,      &ctx->jobs,       &ctx->groups,   &ctx->de_coefs,
-                     &ctx->de_radius,  &ctx->filter,     &ctx->de_kidx,  &ctx->de_tiles};
+                     &ctx->de_radius,  &ctx->filter,     &ctx->de_kidx,  &ctx->de_tiles,
+                     &ctx->de_kparam,  &ctx->de_d2max};
    for (DevBuf *b : bufs)
       if (b->p) cudaFree(b->p);
    if (ctx->d_badvals) cudaFree(ctx->d_badvals);
@@ -1026,6 +1028,8 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
       /* largest half-width the octant table can address: kernel_size = (h+1)(h+2)/2 */
       int half = 0;
       while ((half + 2) * (half + 3) / 2 <= d->kernel_size) half++;
+      std::vector<float> kparam(2 * (size_t)d->n_kernels);
+      std::vector<uint16_t> d2max(d->n_kernels);
       for (int k = 0; k < d->n_kernels; k++) {
          int r = (int)ceil(d->widths[k]) - 1; /* arr_filt_width, rect.c:123 */
          if (r < 0) r = 0;
@@ -1033,12 +1037,28 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
          if (r > 254) return fail(ctx, "f3b_density: kernel radius %d too large", r);
          radius[k] = (uint8_t)r;
          if (k <= d->max_filter_index && r > maxr) maxr = r;
+         /* closed form of the kernel for the staged gather (f3b_post.cu) */
+         const double h = d->widths[k];
+         kparam[2 * k] = h > 0.0 ? (float)(4.5 * 1.4426950408889634 / (h * h)) : 0.0f;
+         kparam[2 * k + 1] = (float)d->coefs[(size_t)k * d->kernel_size];
+         int m = 0;
+         for (int j = 0; j <= r; j++)
+            for (int i = 0; i <= j; i++)
+               if (d->coefs[(size_t)k * d->kernel_size + (size_t)j * (j + 1) / 2 + i] != 0.0 && j * j + i * i > m)
+                  m = j * j + i * i;
+         d2max[k] = (uint16_t)(m > 65535 ? 65535 : m);
       }
       /* the tables only change with the estimator parameters: upload (and wait, the host
        * vectors are temporaries) only when they differ from what the device already holds */
       if (coefs != ctx->de_coefs_host || radius != ctx->de_radius_host) {
          if (ensure(ctx, ctx->de_coefs, nc * sizeof(float))) return 1;
          if (ensure(ctx, ctx->de_radius, (size_t)d->n_kernels)) return 1;
+         if (ensure(ctx, ctx->de_kparam, (size_t)d->n_kernels * 2 * sizeof(float))) return 1;
+         if (ensure(ctx, ctx->de_d2max, (size_t)d->n_kernels * sizeof(uint16_t))) return 1;
+         CK(cudaMemcpyAsync(ctx->de_kparam.p, kparam.data(), kparam.size() * sizeof(float), cudaMemcpyHostToDevice,
+                            ctx->stream));
+         CK(cudaMemcpyAsync(ctx->de_d2max.p, d2max.data(), d2max.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                            ctx->stream));
          CK(cudaMemcpyAsync(ctx->de_coefs.p, coefs.data(), nc * sizeof(float), cudaMemcpyHostToDevice,
                             ctx->stream));
          CK(cudaMemcpyAsync(ctx->de_radius.p, radius.data(), (size_t)d->n_kernels,
@@ -1053,6 +1073,9 @@ int f3b_density_rows(f3b_ctx *ctx, const f3b_density_desc *d, int row0, int row1
       tt2 = host_ms();
       P.de_coefs = (const float *)ctx->de_coefs.p;
       P.de_radius = (const uint8_t *)ctx->de_radius.p;
+      P.de_kparam = (const float2 *)ctx->de_kparam.p;
+      P.de_d2max = (const uint16_t *)ctx->de_d2max.p;
+      P.de_table_only = getenv("F3B_DE_TABLE") != nullptr;
       P.n_kernels = d->n_kernels;
       P.kernel_size = d->kernel_size;
       P.max_radius = maxr;
@@ -1181,6 +1204,18 @@ static int finish_rows_impl(f3b_ctx *ctx, const f3b_final_desc *d, int row0, int
    P.highpow = d->highlight_power;
    for (int i = 0; i < 3; i++) P.background[i] = d->background[i];
    P.out = dst_image ? dst_image : ctx->image.p;
+   /* 8-bit images of up to 65535 x 65535 pixels: float pass + double fix-up of the listed
+    * pixels (F3B_FINAL_DOUBLE=1: everything in double, for A/B) */
+   P.fixup_list = nullptr;
+   P.fixup_count = nullptr;
+   if (d->bytes_per_channel == 1 && d->image_width < 65536 && d->image_height < 65536 &&
+       !getenv("F3B_FINAL_DOUBLE")) {
+      const size_t rows = (size_t)(row1 > row0 ? row1 - row0 : 0);
+      if (ensure(ctx, ctx->fixup, (rows * d->image_width + 4) * sizeof(uint32_t))) return 1;
+      P.fixup_count = (unsigned int *)ctx->fixup.p;
+      P.fixup_list = (uint32_t *)ctx->fixup.p + 4;
+      CK(cudaMemsetAsync(ctx->fixup.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+   }
    P.out_row_begin = row0;
    P.out_row_end = row1;
 

@@ -185,6 +185,9 @@ struct F3DensityParams {
    /* density estimation tables (device); n_kernels == 0 -> plain log scale (rect.c:947-974) */
    const float *de_coefs;     /* [n_kernels * kernel_size] octant-packed, filters.c:322-384 */
    const uint8_t *de_radius;  /* [n_kernels] ceil(width)-1, rect.c:123 */
+   const float2 *de_kparam;   /* [n_kernels] {4.5 log2(e) / h_k^2, centre coefficient N_k} */
+   const uint16_t *de_d2max;  /* [n_kernels] largest dx^2+dy^2 with a non-zero coefficient */
+   int de_table_only;         /* F3B_DE_TABLE=1: gather from the coefficient table (A/B, tests) */
    int n_kernels, kernel_size, max_radius;
    int max_filtered_counts, max_filter_index;
    float curve;
@@ -210,6 +213,9 @@ struct F3FinalParams {
    double background[3];
    void *out;          /* device image, tightly packed image_width*nchan*bpc per row */
    int out_row_begin, out_row_end; /* image rows produced by this launch */
+   /* float first, double where it matters (f3b_post.cu): pixels to redo; nullptr = all double */
+   uint32_t *fixup_list;
+   unsigned int *fixup_count;
 };
 int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream);
 

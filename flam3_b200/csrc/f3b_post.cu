@@ -113,7 +113,14 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(cons
          int k;
          if (f > (double)P.max_filtered_counts) k = P.max_filter_index;
          else if (f <= 100.0) k = (int)ceil(f) - 1;
-         else k = 100 + (int)floor(pow(f - 100.0, (double)P.curve));
+         else {
+            /* 100 + floor((f - 100)^curve) (rect.c:112): in float first; the double pow only
+             * when the float power is too close to a whole number to be trusted (its relative
+             * error is ~1e-6; the margin is 1e-4) */
+            const float pf = exp2f(P.curve * log2f((float)(f - 100.0)));
+            if (fabsf(pf - rintf(pf)) > 1e-4f * fmaxf(pf, 1.0f) + 1e-5f) k = 100 + (int)floorf(pf);
+            else k = 100 + (int)floor(pow(f - 100.0, (double)P.curve));
+         }
          if (k > P.max_filter_index) k = P.max_filter_index;
          if (k < 0) k = 0;
          kidx = (unsigned)k;
@@ -165,6 +172,14 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_classify_kernel(cons
    }
 }
 
+/* A kernel's coefficients are N_k * exp(-4.5 d^2 / h_k^2) inside the disc d <= h_k (Gaussian
+ * with support 1.5 sampled at 1.5 d / h, filters.c:356-372), zero outside, and the reference
+ * only visits |dx|,|dy| <= ceil(h_k) - 1 (rect.c:123). The staged gather evaluates that
+ * instead of fetching the octant table: per staged source the colour already carries
+ * ls * N_k, and a tap costs a compare against the largest d^2 inside the disc, one ex2 and
+ * four FMAs - no dependent global load per tap, which is what held the table version back
+ * (L1TEX 38 %, profiles/r01_v6_postpass). P.de_kparam[k] = {4.5 log2(e) / h_k^2, N_k}, P.de_d2max[k]
+ * the largest d^2 the table holds a non-zero coefficient for. */
 __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_kernel(const F3DensityParams P) {
    extern __shared__ __align__(16) unsigned char de_smem[];
    __shared__ int s_reach;
@@ -190,9 +205,10 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_kernel(const 
    if (R == 0) return;
 
    const int SW = DE_TILE + 2 * R;
-   float4 *s_col = reinterpret_cast<float4 *>(de_smem);
-   uint32_t *s_meta = reinterpret_cast<uint32_t *>(s_col + (size_t)SW * SW); /* kidx | radius<<16 */
-   int *s_rowmax = reinterpret_cast<int *>(s_meta + (size_t)SW * SW); /* widest kernel per staged row */
+   float4 *s_col = reinterpret_cast<float4 *>(de_smem);                  /* colour * ls * N_k */
+   float *s_c = reinterpret_cast<float *>(s_col + (size_t)SW * SW);       /* exponent scale */
+   uint32_t *s_meta = reinterpret_cast<uint32_t *>(s_c + (size_t)SW * SW); /* d2max | radius << 16 */
+   int *s_rowmax = reinterpret_cast<int *>(s_meta + (size_t)SW * SW);     /* widest kernel per staged row */
    const int x0 = blockIdx.x * DE_TILE - R, y0 = tile_y * DE_TILE - R;
 
    for (int i = tid; i < SW; i += DE_TILE * DE_ROWS) s_rowmax[i] = 0;
@@ -202,6 +218,7 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_kernel(const 
       const int gx = x0 + lx, gy = y0 + ly;
       uint32_t meta = 0; /* radius 0 = nothing to gather from here */
       float4 col = make_float4(0.f, 0.f, 0.f, 0.f);
+      float cc = 0.f;
       if (gx >= 0 && gx < P.width && gy >= P.class_row_begin && gy < P.class_row_end) {
          const size_t gi = (size_t)gx + (size_t)P.width * gy;
          const unsigned k = P.de_kidx[gi];
@@ -209,14 +226,17 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_kernel(const 
             const unsigned rad = __ldg(P.de_radius + k);
             if (rad) {
                const float4 c = f3b_view_color(P.hist, f3b_view_index(P.hist, gx, gy));
-               const float ls = (P.k1 * log1pf(c.w * P.k2)) / c.w;
+               const float2 kp = __ldg(P.de_kparam + k);
+               const float ls = (P.k1 * log1pf(c.w * P.k2)) / c.w * kp.y;
                col = make_float4(c.x * ls, c.y * ls, c.z * ls, c.w * ls);
-               meta = k | (rad << 16);
+               cc = kp.x;
+               meta = (uint32_t)__ldg(P.de_d2max + k) | (rad << 16);
                if ((int)rad > s_rowmax[ly]) atomicMax(&s_rowmax[ly], (int)rad);
             }
          }
       }
       s_col[i] = col;
+      s_c[i] = cc;
       s_meta[i] = meta;
    }
    __syncthreads();
@@ -238,21 +258,19 @@ __global__ void __launch_bounds__(DE_TILE * DE_ROWS) f3b_de_gather_kernel(const 
          const int rm = s_rowmax[cy + dy];
          if (rm < ady) continue;
          const int rowbase = (cy + dy) * SW + cx;
+         const int dy2 = dy * dy;
          for (int dx = -rm; dx <= rm; dx++) {
             const int n = rowbase + dx;
             const uint32_t meta = s_meta[n];
             const int rn = (int)(meta >> 16);
-            const int adx = abs(dx);
-            const int hi = max(adx, ady), lo = min(adx, ady);
-            if (hi > rn || rn == 0) continue;
-            /* octant-packed coefficient: index jj*(jj+1)/2 + ii with jj >= ii (filters.c:362) */
-            const float coef = __ldg(P.de_coefs + (size_t)(meta & 0xffffu) * P.kernel_size +
-                                     (hi * (hi + 1)) / 2 + lo);
+            const int d2 = dx * dx + dy2;
+            if (max(abs(dx), ady) > rn || d2 > (int)(meta & 0xffffu) || rn == 0) continue;
+            const float w = exp2f(-s_c[n] * (float)d2);
             const float4 c = s_col[n];
-            acc.x += coef * c.x;
-            acc.y += coef * c.y;
-            acc.z += coef * c.z;
-            acc.w += coef * c.w;
+            acc.x = fmaf(w, c.x, acc.x);
+            acc.y = fmaf(w, c.y, acc.y);
+            acc.z = fmaf(w, c.z, acc.z);
+            acc.w = fmaf(w, c.w, acc.w);
             any = true;
          }
       }
@@ -356,9 +374,10 @@ int f3b_launch_density(const F3DensityParams &p_in, cudaStream_t stream) {
    const int tiles_x = (p.width + DE_TILE - 1) / DE_TILE;
 
    const size_t SW = DE_TILE + 2 * R;
-   size_t smem = SW * SW * (sizeof(float4) + sizeof(uint32_t)) + SW * sizeof(int);
+   size_t smem = SW * SW * (sizeof(float4) + sizeof(float) + sizeof(uint32_t)) + SW * sizeof(int);
    smem = (smem + 15) & ~(size_t)15;
-   const bool staged = smem <= 220 * 1024;
+   /* the staged kernel packs d2max into 16 bits: R <= 181; shared memory stops it long before */
+   const bool staged = smem <= 220 * 1024 && !p.de_table_only;
    if (staged && cudaFuncSetAttribute(f3b_de_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem) != cudaSuccess)
       return 0;
@@ -373,45 +392,56 @@ int f3b_launch_density(const F3DensityParams &p_in, cudaStream_t stream) {
 }
 
 /* ---------------------------------------------------------------------------------- */
-/* tone map helpers (palettes.c:199-349), double precision                             */
+/* tone map helpers (palettes.c:199-349)                                               */
 /* ---------------------------------------------------------------------------------- */
-__device__ __forceinline__ double f3b_calc_alpha(double dens, double g, double linrange) {
-   if (!(dens > 0.0)) return 0.0;
+/* Written once for T = double and T = float. The image is defined by the double version (the
+ * reference computes this pass in double and truncates to 8 or 16 bits; the <= 1 LSB gate is
+ * met with < 0.1 % of the bytes differing). The float version is a FILTER in front of it: it
+ * is ~10x cheaper (the double version keeps the FP64 pipe busy), and a pixel all of whose
+ * channels land further than F3B_FIXUP_EPS from a truncation boundary gets the same bytes
+ * from both; the others (a few %) are listed and redone in double by a second kernel. */
+#define F3B_FIXUP_EPS 0.01f
+template <typename T> __device__ __forceinline__ T f3b_pow(T a, T b);
+template <> __device__ __forceinline__ double f3b_pow<double>(double a, double b) { return pow(a, b); }
+template <> __device__ __forceinline__ float f3b_pow<float>(float a, float b) { return powf(a, b); }
+
+template <typename T> __device__ __forceinline__ T f3b_calc_alpha(T dens, T g, T linrange) {
+   if (!(dens > T(0))) return T(0);
    if (dens < linrange) {
-      const double funcval = pow(linrange, g);
-      const double frac = dens / linrange;
-      return (1.0 - frac) * dens * (funcval / linrange) + frac * pow(dens, g);
+      const T funcval = f3b_pow<T>(linrange, g);
+      const T frac = dens / linrange;
+      return (T(1) - frac) * dens * (funcval / linrange) + frac * f3b_pow<T>(dens, g);
    }
-   return pow(dens, g);
+   return f3b_pow<T>(dens, g);
 }
 
-__device__ void f3b_rgb2hsv(const double *rgb, double *hsv) {
-   const double r = rgb[0], g = rgb[1], b = rgb[2];
-   const double mx = fmax(r, fmax(g, b)), mn = fmin(r, fmin(g, b));
-   const double del = mx - mn;
-   const double s = (mx != 0.0) ? del / mx : 0.0;
-   double h = 0.0;
-   if (s != 0.0) {
-      const double rc = (mx - r) / del, gc = (mx - g) / del, bc = (mx - b) / del;
+template <typename T> __device__ void f3b_rgb2hsv(const T *rgb, T *hsv) {
+   const T r = rgb[0], g = rgb[1], b = rgb[2];
+   const T mx = fmax(r, fmax(g, b)), mn = fmin(r, fmin(g, b));
+   const T del = mx - mn;
+   const T s = (mx != T(0)) ? del / mx : T(0);
+   T h = T(0);
+   if (s != T(0)) {
+      const T rc = (mx - r) / del, gc = (mx - g) / del, bc = (mx - b) / del;
       if (r == mx) h = bc - gc;
-      else if (g == mx) h = 2.0 + rc - bc;
-      else if (b == mx) h = 4.0 + gc - rc;
-      if (h < 0.0) h += 6.0;
+      else if (g == mx) h = T(2) + rc - bc;
+      else if (b == mx) h = T(4) + gc - rc;
+      if (h < T(0)) h += T(6);
    }
    hsv[0] = h;
    hsv[1] = s;
    hsv[2] = mx;
 }
 
-__device__ void f3b_hsv2rgb(const double *hsv, double *rgb) {
-   double h = hsv[0];
-   const double s = hsv[1], v = hsv[2];
-   while (h >= 6.0) h -= 6.0;
-   while (h < 0.0) h += 6.0;
+template <typename T> __device__ void f3b_hsv2rgb(const T *hsv, T *rgb) {
+   T h = hsv[0];
+   const T s = hsv[1], v = hsv[2];
+   while (h >= T(6)) h -= T(6);
+   while (h < T(0)) h += T(6);
    const int j = (int)floor(h);
-   const double f = h - j;
-   const double p = v * (1.0 - s), q = v * (1.0 - s * f), t = v * (1.0 - s * (1.0 - f));
-   double r, g, b;
+   const T f = h - j;
+   const T p = v * (T(1) - s), q = v * (T(1) - s * f), t = v * (T(1) - s * (T(1) - f));
+   T r, g, b;
    switch (j) {
    case 1: r = q; g = v; b = p; break;
    case 2: r = p; g = v; b = t; break;
@@ -425,70 +455,73 @@ __device__ void f3b_hsv2rgb(const double *hsv, double *rgb) {
    rgb[2] = b;
 }
 
-__device__ void f3b_calc_newrgb(const double *cbuf, double ls, double highpow, double *newrgb) {
-   if (ls == 0.0 || (cbuf[0] == 0.0 && cbuf[1] == 0.0 && cbuf[2] == 0.0)) {
-      newrgb[0] = newrgb[1] = newrgb[2] = 0.0;
-      return;
+/* returns true when the hue-preserving clip (hsv round trip) was taken: the float filter does
+ * not trust itself there */
+template <typename T> __device__ bool f3b_calc_newrgb(const T *cbuf, T ls, T highpow, T *newrgb) {
+   if (ls == T(0) || (cbuf[0] == T(0) && cbuf[1] == T(0) && cbuf[2] == T(0))) {
+      newrgb[0] = newrgb[1] = newrgb[2] = T(0);
+      return false;
    }
    /* most saturated channel */
-   double maxa = -1.0, maxc = 0.0;
+   T maxa = T(-1), maxc = T(0);
    for (int i = 0; i < 3; i++) {
-      const double a = ls * (cbuf[i] / 255.0);
+      const T a = ls * (cbuf[i] / T(255));
       if (a > maxa) {
          maxa = a;
-         maxc = cbuf[i] / 255.0;
+         maxc = cbuf[i] / T(255);
       }
    }
-   const double newls = 255.0 / maxc;
-   if (maxa > 255.0 && highpow >= 0.0) {
+   const T newls = T(255) / maxc;
+   if (maxa > T(255) && highpow >= T(0)) {
       /* clip to full scale and desaturate instead of shifting hue */
-      const double lsratio = pow(newls / ls, highpow);
-      double hsv[3];
-      for (int i = 0; i < 3; i++) newrgb[i] = newls * (cbuf[i] / 255.0) / 255.0;
-      f3b_rgb2hsv(newrgb, hsv);
+      const T lsratio = f3b_pow<T>(newls / ls, highpow);
+      T hsv[3];
+      for (int i = 0; i < 3; i++) newrgb[i] = newls * (cbuf[i] / T(255)) / T(255);
+      f3b_rgb2hsv<T>(newrgb, hsv);
       hsv[1] *= lsratio;
-      f3b_hsv2rgb(hsv, newrgb);
-      for (int i = 0; i < 3; i++) newrgb[i] *= 255.0;
-   } else {
-      double adj = -highpow;
-      if (adj > 1.0) adj = 1.0;
-      if (maxa <= 255.0) adj = 1.0;
-      for (int i = 0; i < 3; i++)
-         newrgb[i] = ((1.0 - adj) * newls + adj * ls) * (cbuf[i] / 255.0);
+      f3b_hsv2rgb<T>(hsv, newrgb);
+      for (int i = 0; i < 3; i++) newrgb[i] *= T(255);
+      return true;
    }
+   T adj = -highpow;
+   if (adj > T(1)) adj = T(1);
+   if (maxa <= T(255)) adj = T(1);
+   for (int i = 0; i < 3; i++) newrgb[i] = ((T(1) - adj) * newls + adj * ls) * (cbuf[i] / T(255));
+   return false;
 }
 
 /* gamma / vibrancy / highlight / background for one 4-vector t (rect.c:1100-1130 and
  * rect.c:1172-1210). On return t[0..2] are clamped to [0,255] and t[3] is alpha. */
-__device__ __forceinline__ void f3b_tonemap(double *t, const F3FinalParams &P) {
-   double alpha, ls;
-   if (t[3] <= 0.0) {
-      alpha = 0.0;
-      ls = 0.0;
+template <typename T> __device__ __forceinline__ bool f3b_tonemap(T *t, const F3FinalParams &P) {
+   T alpha, ls;
+   if (t[3] <= T(0)) {
+      alpha = T(0);
+      ls = T(0);
    } else {
-      const double tmp = t[3] / 255.0;
-      alpha = f3b_calc_alpha(tmp, P.g, P.linrange);
-      ls = P.vibrancy * 256.0 * alpha / tmp;
-      if (alpha < 0.0) alpha = 0.0;
-      if (alpha > 1.0) alpha = 1.0;
+      const T tmp = t[3] / T(255);
+      alpha = f3b_calc_alpha<T>(tmp, (T)P.g, (T)P.linrange);
+      ls = (T)P.vibrancy * T(256) * alpha / tmp;
+      if (alpha < T(0)) alpha = T(0);
+      if (alpha > T(1)) alpha = T(1);
    }
-   double newrgb[3];
-   f3b_calc_newrgb(t, ls, P.highpow, newrgb);
+   T newrgb[3];
+   const bool hard = f3b_calc_newrgb<T>(t, ls, (T)P.highpow, newrgb);
    /* the reference always evaluates (1 - vibrancy) * 256 * pow(t/255, g) (rect.c:1195); with
     * the default vibrancy of exactly 1 the product is an exact zero whenever t >= 0 (pow is
-    * finite), and three of the four double-precision pows per pixel can be skipped; a
-    * negative t (filters with negative lobes) keeps the reference's NaN */
-   const double inv_vib = 1.0 - P.vibrancy;
+    * finite), and three of the four pows per pixel can be skipped; a negative t (filters
+    * with negative lobes) keeps the reference's NaN */
+   const T inv_vib = T(1) - (T)P.vibrancy;
    for (int i = 0; i < 3; i++) {
-      double a = newrgb[i];
-      if (inv_vib != 0.0 || t[i] < 0.0) a += inv_vib * 256.0 * pow(t[i] / 255.0, P.g);
-      if (P.nchan <= 3 || P.transp == 0) a += (1.0 - alpha) * P.background[i];
-      else a = (alpha > 0.0) ? a / alpha : 0.0;
-      if (a > 255.0) a = 255.0;
-      if (a < 0.0) a = 0.0;
+      T a = newrgb[i];
+      if (inv_vib != T(0) || t[i] < T(0)) a += inv_vib * T(256) * f3b_pow<T>(t[i] / T(255), (T)P.g);
+      if (P.nchan <= 3 || P.transp == 0) a += (T(1) - alpha) * (T)P.background[i];
+      else a = (alpha > T(0)) ? a / alpha : T(0);
+      if (a > T(255)) a = T(255);
+      if (a < T(0)) a = T(0);
       t[i] = a;
    }
    t[3] = alpha;
+   return hard;
 }
 
 __global__ void __launch_bounds__(256) f3b_earlyclip_kernel(const F3FinalParams P, size_t i0, size_t n) {
@@ -497,55 +530,101 @@ __global__ void __launch_bounds__(256) f3b_earlyclip_kernel(const F3FinalParams 
    for (; i < n; i += stride) {
       const float4 a = P.accum[i];
       double t[4] = {(double)a.x, (double)a.y, (double)a.z, (double)a.w};
-      f3b_tonemap(t, P);
+      f3b_tonemap<double>(t, P);
       P.accum[i] = make_float4((float)t[0], (float)t[1], (float)t[2], (float)t[3]);
    }
 }
 
-__global__ void __launch_bounds__(256) f3b_final_kernel(const F3FinalParams P) {
-   const int i = blockIdx.x * blockDim.x + threadIdx.x; /* output column */
-   const int j = P.out_row_begin + blockIdx.y * blockDim.y + threadIdx.y; /* output row */
-   if (i >= P.image_width || j >= P.out_row_end) return;
+/* one output pixel: filter_width^2 taps in the reference's order (rect.c:1146-1160, ii outer,
+ * jj inner), tone map, quantise. Returns true (float version only) when some channel is too
+ * close to a truncation boundary for the float result to be trusted. */
+template <typename T> __device__ __forceinline__ bool f3b_final_pixel(const F3FinalParams &P, int i, int j) {
    const int x = P.de_offset + i * P.oversample;
    const int y = P.de_offset + j * P.oversample;
    const int fw = P.filter_width;
-
-   double t[4] = {0.0, 0.0, 0.0, 0.0};
-   /* same tap order as rect.c:1146-1160 (ii outer, jj inner) so the double sums agree */
+   T t[4] = {T(0), T(0), T(0), T(0)};
    for (int ii = 0; ii < fw; ii++) {
       for (int jj = 0; jj < fw; jj++) {
-         const double k = __ldg(P.filter + ii + jj * fw);
+         const T k = (T)__ldg(P.filter + ii + jj * fw);
          const float4 a = __ldg(P.accum + (size_t)(x + ii) + (size_t)(y + jj) * P.width);
-         t[0] += k * (double)a.x;
-         t[1] += k * (double)a.y;
-         t[2] += k * (double)a.z;
-         t[3] += k * (double)a.w;
+         t[0] += k * (T)a.x;
+         t[1] += k * (T)a.y;
+         t[2] += k * (T)a.z;
+         t[3] += k * (T)a.w;
       }
    }
-   if (!P.earlyclip) f3b_tonemap(t, P);
-
-   double alpha = t[3];
-   if (alpha > 1.0) alpha = 1.0;
-   if (alpha < 0.0) alpha = 0.0;
+   bool unsure = false;
+   if (sizeof(T) == 4 && t[0] == T(0) && t[1] == T(0) && t[2] == T(0) && t[3] == T(0)) {
+      /* nothing under the filter (most of a sparse frame): the pixel is the background, which
+       * sits ON a truncation boundary when it is a whole number (black). Exact zeros need no
+       * filtering: take the double formula directly, it costs nothing here. */
+      double td[4] = {0.0, 0.0, 0.0, 0.0};
+      if (!P.earlyclip) f3b_tonemap<double>(td, P);
+      unsigned char *o = reinterpret_cast<unsigned char *>(P.out) + ((size_t)i + (size_t)j * P.image_width) * P.nchan;
+      for (int c = 0; c < 3; c++) o[c] = (unsigned char)fmin(fmax(td[c], 0.0), 255.0);
+      if (P.nchan > 3) o[3] = P.transp ? (unsigned char)(fmin(fmax(td[3], 0.0), 1.0) * 255.0) : 255;
+      return false;
+   }
+   if (!P.earlyclip) unsure = f3b_tonemap<T>(t, P);
+   T alpha = t[3];
+   if (alpha > T(1)) alpha = T(1);
+   if (alpha < T(0)) alpha = T(0);
    const size_t pix = (size_t)i + (size_t)j * P.image_width;
    if (P.bytes_per_channel == 2) {
       unsigned short *o = reinterpret_cast<unsigned short *>(P.out) + pix * P.nchan;
       for (int c = 0; c < 3; c++) {
-         double a = t[c];
-         if (a > 255.0) a = 255.0;
-         if (a < 0.0) a = 0.0;
-         o[c] = (unsigned short)(a * 256.0);
+         T a = t[c];
+         if (a > T(255)) a = T(255);
+         if (a < T(0)) a = T(0);
+         o[c] = (unsigned short)(a * T(256));
       }
-      if (P.nchan > 3) o[3] = P.transp ? (unsigned short)(alpha * 65535.0) : 65535;
-   } else {
-      unsigned char *o = reinterpret_cast<unsigned char *>(P.out) + pix * P.nchan;
-      for (int c = 0; c < 3; c++) {
-         double a = t[c];
-         if (a > 255.0) a = 255.0;
-         if (a < 0.0) a = 0.0;
-         o[c] = (unsigned char)a;
+      if (P.nchan > 3) o[3] = P.transp ? (unsigned short)(alpha * T(65535)) : 65535;
+      return false; /* 16 bit is always rendered by the double version */
+   }
+   unsigned char *o = reinterpret_cast<unsigned char *>(P.out) + pix * P.nchan;
+   for (int c = 0; c < 3; c++) {
+      T a = t[c];
+      if (!(a == a)) unsure = true; /* NaN: let the double version decide */
+      if (a > T(255)) a = T(255);
+      if (a < T(0)) a = T(0);
+      /* distance to the nearest integer; values clamped at 0 or 255 sit ON a boundary unless
+       * the unclamped value was clearly beyond it */
+      if (sizeof(T) == 4) {
+         const float v = (float)t[c];
+         if (fabsf(v - rintf(v)) < F3B_FIXUP_EPS && v > -F3B_FIXUP_EPS && v < 255.0f + F3B_FIXUP_EPS) unsure = true;
       }
-      if (P.nchan > 3) o[3] = P.transp ? (unsigned char)(alpha * 255.0) : 255;
+      o[c] = (unsigned char)a;
+   }
+   if (P.nchan > 3) {
+      if (sizeof(T) == 4 && P.transp) {
+         const float v = (float)alpha * 255.0f;
+         if (fabsf(v - rintf(v)) < F3B_FIXUP_EPS) unsure = true;
+      }
+      o[3] = P.transp ? (unsigned char)(alpha * T(255)) : 255;
+   }
+   return unsure;
+}
+
+/* pass 1: every pixel in float; pixels the float result cannot be trusted for are listed */
+__global__ void __launch_bounds__(256) f3b_final_kernel(const F3FinalParams P) {
+   const int i = blockIdx.x * blockDim.x + threadIdx.x; /* output column */
+   const int j = P.out_row_begin + blockIdx.y * blockDim.y + threadIdx.y; /* output row */
+   if (i >= P.image_width || j >= P.out_row_end) return;
+   if (!P.fixup_list) { /* 16 bit output, or the filter switched off: all in double */
+      f3b_final_pixel<double>(P, i, j);
+      return;
+   }
+   if (f3b_final_pixel<float>(P, i, j)) {
+      const unsigned slot = atomicAdd(P.fixup_count, 1u);
+      P.fixup_list[slot] = (uint32_t)i | ((uint32_t)j << 16);
+   }
+}
+/* pass 2: the listed pixels again, in double */
+__global__ void __launch_bounds__(128) f3b_final_fixup_kernel(const F3FinalParams P) {
+   const unsigned n = *P.fixup_count;
+   for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+      const uint32_t e = P.fixup_list[k];
+      f3b_final_pixel<double>(P, (int)(e & 0xffffu), (int)(e >> 16));
    }
 }
 
@@ -567,7 +646,13 @@ int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream) {
    dim3 grid((p.image_width + 31) / 32, (p.out_row_end - p.out_row_begin + 7) / 8);
    f3b_final_kernel<<<grid, block, 0, stream>>>(p);
    if (cudaGetLastError() != cudaSuccess) return 0;
-   return launches + 1;
+   launches++;
+   if (p.fixup_list) {
+      f3b_final_fixup_kernel<<<148 * 4, 128, 0, stream>>>(p);
+      if (cudaGetLastError() != cudaSuccess) return 0;
+      launches++;
+   }
+   return launches;
 }
 
 /* ---------------------------------------------------------------------------------- */

@@ -118,7 +118,9 @@ def test_c5_at_1024(name):
     b, _, _ = ref.render(gr, isaac_seed="c5-b", nthreads=8)
     g, sg, _ = gpu.render(gg, isaac_seed="c5-a", nthreads=8)
     assert sa["rv"] == 0 and sg["rv"] == 0 and sg["num_iters"] == sa["num_iters"]
-    noise, got = psnr(a, b), min(psnr(g, a), psnr(g, b))
+    # a collapsed attractor gives (nearly) the same image whatever the seed: beyond 60 dB the
+    # images are equal for every purpose (psnr() itself reports identical images as 99)
+    noise, got = min(psnr(a, b), 60.0), min(psnr(g, a), psnr(g, b))
     assert got >= noise - 1.5, "%s: gpu-vs-ref %.2f dB, ref-vs-ref %.2f dB" % (name, got, noise)
 
 

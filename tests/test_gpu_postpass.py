@@ -162,3 +162,33 @@ def test_row_strip_postpass_equals_whole_frame(flame0, variant):
         gpu.set_strip_gather(None)
     assert len(calls) == nranks and calls[0] == (whole.shape[1] * whole.shape[2], (H + 2) // 3)
     assert np.array_equal(tiled, whole), "%d bytes differ" % int((tiled != whole).sum())
+
+
+@pytest.mark.parametrize("variant", ["default", "tone", "rgba", "earlyclip", "os2"])
+def test_float_first_final_pass_gives_the_double_bytes(flame0, variant):
+    """The final pass computes every pixel in float and redoes in double the few % whose
+    channels land within 0.01 of a truncation boundary (f3b_post.cu). The image must be the
+    one the all-double pass (F3B_FINAL_DOUBLE=1) produces, byte for byte."""
+    import os
+    _, gpu, _ = libs()
+    kw = {}
+    if variant == "tone":
+        xml = small(flame0, quality=100, vibrancy=0.6, highlight_power=1.5, background="0.2 0.1 0.3",
+                    gamma=2.5, gamma_threshold=0.05, brightness=12)
+    elif variant == "os2":
+        xml = resize(flame0, 640, 480, scale=240, quality=100, oversample=2, temporal_samples=1)
+    else:
+        xml = resize(flame0, 640, 480, scale=240, quality=100, temporal_samples=1)
+    if variant == "rgba":
+        kw = dict(nchan=4, transp=1)
+    if variant == "earlyclip":
+        kw = dict(earlyclip=1)
+    gg = gpu.parse(xml)
+    try:
+        os.environ["F3B_FINAL_DOUBLE"] = "1"
+        a, sa, _ = gpu.render(gg, isaac_seed="ff", **kw)
+    finally:
+        os.environ.pop("F3B_FINAL_DOUBLE", None)
+    b, sb, _ = gpu.render(gg, isaac_seed="ff", **kw)
+    assert sa["rv"] == 0 and sb["rv"] == 0 and a.mean() > 1.0
+    assert np.array_equal(a, b), "%d bytes differ" % int((a != b).sum())
