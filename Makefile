@@ -49,7 +49,7 @@ REF_CFLAGS = -g -O3 -std=gnu99 -ffast-math -fPIC -w -I$(SHIMS) -I$(F3_REF) \
              -DPACKAGE_DATA_DIR='"$(F3_REF)"' -DGIT_REV='""'
 HOST_SRCS  = variations.c filters.c isaac.c interpolation.c palettes.c parser.c
 HOST_OBJS  = $(addprefix $(DROP)/host_,$(HOST_SRCS:.c=.o))
-GLUE_OBJS  = $(DROP)/f3b_render.o $(DROP)/f3b_pack.o $(DROP)/f3b_isaac.o $(DROP)/f3b_debug.o
+GLUE_OBJS  = $(DROP)/f3b_render.o $(DROP)/f3b_pack.o $(DROP)/f3b_isaac.o $(DROP)/f3b_debug.o $(DROP)/f3b_analysis.o
 MISC_OBJS  = $(DROP)/xmlshim.o $(DROP)/imgshim.o
 CLIS       = $(DROP)/flam3-render $(DROP)/flam3-animate $(DROP)/flam3-genome
 
@@ -65,7 +65,9 @@ $(DROP)/host_%.o: $(F3_REF)/%.c | $(DROP)
 # flam3.c also holds the CPU flam3_render this library replaces: rename it out of the way
 $(DROP)/host_flam3.o: $(F3_REF)/flam3.c $(F3_REF)/rect.c | $(DROP)
 	$(CC) $(REF_CFLAGS) -Dflam3_render=flam3_render_cpu_unused \
-	   -Dflam3_render_memory_required=flam3_render_memory_required_cpu_unused -c $< -o $@
+	   -Dflam3_render_memory_required=flam3_render_memory_required_cpu_unused \
+	   -Dflam3_estimate_bounding_box=flam3_estimate_bounding_box_cpu_unused \
+	   -Dflam3_colorhist=flam3_colorhist_cpu_unused -c $< -o $@
 
 $(DROP)/f3b_%.o: $(CSRC)/f3b_%.c $(CSRC)/f3b_host.h $(CSRC)/f3b_pack.h include/flam3_b200.h | $(DROP)
 	$(CC) -O2 -std=gnu99 -fPIC -Wall -Wno-unused-function -I$(SHIMS) -I$(F3_REF) -c $< -o $@

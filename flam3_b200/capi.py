@@ -276,6 +276,22 @@ class Flam3Lib:
         s = C.string_at(p).decode()
         return s
 
+    def bounding_box(self, genomes, idx=0, eps=0.01, nsamples=100000, seed="flam3b200"):
+        """flam3_estimate_bounding_box: (rv, (xmin, ymin, xmax, ymax))."""
+        f = self._dll.h_bounding_box
+        f.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
+        out = (C.c_double * 4)()
+        rv = f(genomes.ptr, idx, eps, nsamples, seed.encode(), out)
+        return rv, tuple(out)
+
+    def colorhist(self, genomes, idx=0, num_batches=10, seed="flam3b200"):
+        """flam3_colorhist: (rv, hist[256])."""
+        f = self._dll.h_colorhist
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_double)]
+        out = (C.c_double * 256)()
+        rv = f(genomes.ptr, idx, num_batches, seed.encode(), out)
+        return rv, np.array(out[:])
+
     def render(self, genomes, out=None, **kw):
         """flam3_render of genomes[first_genome:first_genome+ngenomes].
 
@@ -339,7 +355,7 @@ CORE_SYMBOLS = [
     "f3b_stream_ptr", "f3b_stage_stats", "f3b_stats_reset", "f3b_xfer_stats", "f3b_timer_start",
     "f3b_timer_stop", "f3b_peer_enable", "f3b_hist_reduce_rows", "f3b_group_barrier",
     "f3b_image_reserve", "f3b_image_ptr", "f3b_finish_rows_into", "f3b_ipc_export", "f3b_ipc_open",
-    "f3b_ipc_close", "f3b_device_index",
+    "f3b_ipc_close", "f3b_device_index", "f3b_orbits", "f3b_debug_counters",
 ]
 
 

@@ -906,6 +906,35 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    return stage_end(ctx, launches);
 }
 
+int f3b_orbits(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int n_chains, int n_per_chain, int fuse,
+               uint64_t seed, const float *start_xy, float *out_xycv, uint64_t *badvals) {
+   if (!ctx || !blob || !out_xycv || n_chains <= 0 || n_per_chain <= 0 || fuse < 0)
+      return fail(ctx, "f3b_orbits: bad arguments");
+   CK(cudaSetDevice(ctx->device));
+   const uint32_t *w = (const uint32_t *)blob;
+   if (blob_bytes < F3B_H_SIZE * 4 || (size_t)w[F3B_H_WORDS] * 4 > blob_bytes || w[F3B_H_WORDS] > F3B_MAX_BLOB_WORDS)
+      return fail(ctx, "f3b_orbits: malformed blob");
+   const size_t nout = (size_t)n_chains * n_per_chain;
+   const size_t bb = ((size_t)w[F3B_H_WORDS] * 4 + 15) & ~(size_t)15;
+   const size_t sb = start_xy ? (((size_t)n_chains * 2 * sizeof(float) + 15) & ~(size_t)15) : 0;
+   if (ensure(ctx, ctx->xfer, bb + sb + 16 + nout * sizeof(float4))) return 1;
+   char *base = (char *)ctx->xfer.p;
+   unsigned long long *d_bad = (unsigned long long *)(base + bb + sb);
+   float4 *d_out = (float4 *)(base + bb + sb + 16);
+   CK(cudaMemcpyAsync(base, blob, (size_t)w[F3B_H_WORDS] * 4, cudaMemcpyHostToDevice, ctx->stream));
+   if (start_xy) CK(cudaMemcpyAsync(base + bb, start_xy, (size_t)n_chains * 2 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+   CK(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), ctx->stream));
+   if (!f3b_launch_orbits((const uint32_t *)base, (size_t)w[F3B_H_WORDS] * 4, n_chains, n_per_chain, fuse, seed,
+                          start_xy ? (const float *)(base + bb) : nullptr, d_out, d_bad, ctx->stream))
+      return fail(ctx, "orbit launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+   CK(cudaMemcpyAsync(out_xycv, d_out, nout * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+   unsigned long long bad = 0;
+   CK(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream));
+   CK(cudaStreamSynchronize(ctx->stream));
+   if (badvals) *badvals = bad;
+   return 0;
+}
+
 int f3b_debug_apply_xform(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int xform_index,
                           const float *in_xyc, int n, float *out_xycvb, uint64_t seed) {
    if (!ctx || !blob || !in_xyc || !out_xycvb || n <= 0) return fail(ctx, "debug_apply: bad arguments");

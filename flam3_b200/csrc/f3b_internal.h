@@ -171,6 +171,9 @@ struct F3MergeParams {
    int sat_check; /* sweepers ran: uint32 sums may have wrapped */
 };
 int f3b_launch_hist_merge(const F3MergeParams &m, cudaStream_t stream);
+int f3b_launch_orbits(const uint32_t *blob, size_t blob_bytes, int n_chains, int n_per_chain, int fuse,
+                      uint64_t seed, const float *start, float4 *out, unsigned long long *badvals,
+                      cudaStream_t stream);
 int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_index, const float *in,
                            int n, float *out, uint64_t seed, cudaStream_t stream);
 

@@ -732,6 +732,79 @@ __global__ void f3b_debug_apply_kernel(const uint32_t *blob, int xform_index, co
    out[5 * i + 4] = bad ? 1.0f : 0.0f;
 }
 
+/* flam3_iterate (flam3.c:232-299) for many independent chains at once: thread t is a chain
+ * that starts at start[t] (or a random point of [-1,1]^2) with colour 0, discards `fuse`
+ * iterations and stores n_per_chain samples {x, y, colour, vis_adjusted} - the final xform
+ * applied to the stored sample but not fed back, a bad value retried up to 4 times - exactly
+ * the loop the render kernel runs, without camera and buckets. out[i * n_chains + t]. For
+ * the analysis helpers either side of the render (flam3_estimate_bounding_box,
+ * flam3_colorhist): one chain is latency bound on a GPU, a few hundred are not. */
+__global__ void __launch_bounds__(128) f3b_orbit_kernel(const uint32_t *blob, int n_chains, int n_per_chain,
+                                                        int fuse, uint64_t seed, const float *start,
+                                                        float4 *out, unsigned long long *badvals) {
+   extern __shared__ __align__(16) uint32_t smem[];
+   const float *sf = reinterpret_cast<const float *>(smem);
+   const uint32_t words = blob[F3B_H_WORDS];
+   for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) smem[i] = blob[i];
+   __syncthreads();
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= n_chains) return;
+   const uint32_t cstride = smem[F3B_H_CHOOSER_STRIDE], choff = smem[F3B_H_OFF_CHOOSER];
+   const uint32_t xaos = smem[F3B_H_XAOS], xb = smem[F3B_H_XF_BASE], xs = smem[F3B_H_XF_STRIDE];
+   const int fin = (int)smem[F3B_H_FINAL];
+   const float final_opacity = sf[F3B_H_FINAL_OPACITY];
+   F3Rng rng;
+   f3b_rng_seed(rng, seed, 0x0b17u, (uint32_t)t);
+   float px = start ? start[2 * t] : rng.u11();
+   float py = start ? start[2 * t + 1] : rng.u11();
+   float pc = 0.0f;
+   uint32_t lastxf = 0;
+   unsigned int bad = 0;
+   for (int i = -fuse; i < n_per_chain; i++) {
+      float qx, qy, qc, qv;
+      uint32_t fn = 0;
+      for (int consec = 0;;) {
+         const uint32_t k = rng.next() & (F3B_CHOOSER_GRAIN - 1u);
+         const uint32_t ro = choff + (xaos ? lastxf * cstride : 0u);
+         fn = 0;
+         for (uint32_t j = 0; j < cstride; j++) fn += k >= smem[ro + j] ? 1u : 0u;
+         const bool isbad = f3b_apply_xform(sf, xb + fn * xs, px, py, pc, qx, qy, qc, qv, rng);
+         if (!isbad) break;
+         bad++;
+         if (++consec >= 5) break;
+         px = qx;
+         py = qy;
+         pc = qc;
+      }
+      lastxf = fn + 1;
+      px = qx;
+      py = qy;
+      pc = qc;
+      if (fin >= 0) {
+         bool apply = final_opacity == 1.0f;
+         if (!apply) apply = rng.u01() < final_opacity;
+         if (apply) {
+            float fx, fy, fc, fv;
+            f3b_apply_xform(sf, xb + (uint32_t)fin * xs, px, py, pc, fx, fy, fc, fv, rng);
+            qx = fx;
+            qy = fy;
+            qc = fc;
+         }
+      }
+      if (i >= 0) out[(size_t)i * n_chains + t] = make_float4(qx, qy, qc, qv);
+   }
+   if (bad) atomicAdd(badvals, (unsigned long long)bad);
+}
+int f3b_launch_orbits(const uint32_t *blob, size_t blob_bytes, int n_chains, int n_per_chain, int fuse,
+                      uint64_t seed, const float *start, float4 *out, unsigned long long *badvals,
+                      cudaStream_t stream) {
+   cudaFuncSetAttribute(f3b_orbit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)(F3B_MAX_BLOB_WORDS * 4));
+   f3b_orbit_kernel<<<(n_chains + 127) / 128, 128, blob_bytes, stream>>>(blob, n_chains, n_per_chain, fuse, seed,
+                                                                          start, out, badvals);
+   return cudaGetLastError() == cudaSuccess ? 1 : 0;
+}
+
 int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_index, const float *in,
                            int n, float *out, uint64_t seed, cudaStream_t stream) {
    cudaFuncSetAttribute(f3b_debug_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -538,15 +538,17 @@ __global__ void __launch_bounds__(256) f3b_earlyclip_kernel(const F3FinalParams 
 /* one output pixel: filter_width^2 taps in the reference's order (rect.c:1146-1160, ii outer,
  * jj inner), tone map, quantise. Returns true (float version only) when some channel is too
  * close to a truncation boundary for the float result to be trusted. */
-template <typename T> __device__ __forceinline__ bool f3b_final_pixel(const F3FinalParams &P, int i, int j) {
-   const int x = P.de_offset + i * P.oversample;
-   const int y = P.de_offset + j * P.oversample;
+template <typename T, typename FT>
+__device__ __forceinline__ bool f3b_final_pixel(const F3FinalParams &P, int i, int j, const float4 *src,
+                                                size_t spitch, const FT *filt) {
+   /* src: the accumulator value under the pixel's first tap, rows spitch apart (the
+    * accumulator itself, or the CTA's tile of it in shared memory); filt: the filter */
    const int fw = P.filter_width;
    T t[4] = {T(0), T(0), T(0), T(0)};
    for (int ii = 0; ii < fw; ii++) {
       for (int jj = 0; jj < fw; jj++) {
-         const T k = (T)__ldg(P.filter + ii + jj * fw);
-         const float4 a = __ldg(P.accum + (size_t)(x + ii) + (size_t)(y + jj) * P.width);
+         const T k = (T)filt[ii + jj * fw];
+         const float4 a = src[(size_t)ii + (size_t)jj * spitch];
          t[0] += k * (T)a.x;
          t[1] += k * (T)a.y;
          t[2] += k * (T)a.z;
@@ -605,26 +607,61 @@ template <typename T> __device__ __forceinline__ bool f3b_final_pixel(const F3Fi
    return unsure;
 }
 
-/* pass 1: every pixel in float; pixels the float result cannot be trusted for are listed */
-__global__ void __launch_bounds__(256) f3b_final_kernel(const F3FinalParams P) {
+__device__ __forceinline__ const float4 *f3b_final_origin(const F3FinalParams &P, int i, int j) {
+   return P.accum + (size_t)(P.de_offset + i * P.oversample) + (size_t)(P.de_offset + j * P.oversample) * P.width;
+}
+/* pass 1: every pixel in float; pixels the float result cannot be trusted for are listed. A CTA
+ * renders 32x8 pixels from a shared-memory tile of the accumulator (each value is a tap of up
+ * to filter_width^2 pixels: the tile turns 25-64 L2 loads per pixel into ~2) and a float copy
+ * of the filter. tile_w == 0: no tile (it would not fit), taps come from global memory. */
+__global__ void __launch_bounds__(256) f3b_final_kernel(const F3FinalParams P, int tile_w, int tile_h) {
+   extern __shared__ __align__(16) unsigned char fin_smem[];
    const int i = blockIdx.x * blockDim.x + threadIdx.x; /* output column */
    const int j = P.out_row_begin + blockIdx.y * blockDim.y + threadIdx.y; /* output row */
-   if (i >= P.image_width || j >= P.out_row_end) return;
+   const bool inside = i < P.image_width && j < P.out_row_end;
    if (!P.fixup_list) { /* 16 bit output, or the filter switched off: all in double */
-      f3b_final_pixel<double>(P, i, j);
+      if (inside) f3b_final_pixel<double, double>(P, i, j, f3b_final_origin(P, i, j), (size_t)P.width, P.filter);
       return;
    }
-   if (f3b_final_pixel<float>(P, i, j)) {
-      const unsigned slot = atomicAdd(P.fixup_count, 1u);
-      P.fixup_list[slot] = (uint32_t)i | ((uint32_t)j << 16);
+   float *s_filt = reinterpret_cast<float *>(fin_smem);
+   const int nf = P.filter_width * P.filter_width;
+   float4 *s_tile = reinterpret_cast<float4 *>(fin_smem + (((size_t)nf * 4 + 15) & ~(size_t)15));
+   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+   for (int k = tid; k < nf; k += 256) s_filt[k] = (float)__ldg(P.filter + k);
+   if (tile_w) {
+      const int bx = P.de_offset + (int)(blockIdx.x * blockDim.x) * P.oversample;
+      const int by = P.de_offset + (P.out_row_begin + (int)(blockIdx.y * blockDim.y)) * P.oversample;
+      for (int k = tid; k < tile_w * tile_h; k += 256) {
+         const int lx = k % tile_w, ly = k / tile_w;
+         const int gx = bx + lx, gy = by + ly;
+         s_tile[k] = (gx < P.width && gy < P.height) ? __ldg(P.accum + (size_t)gx + (size_t)gy * P.width)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
    }
+   __shared__ unsigned int s_n, s_base;
+   if (tid == 0) s_n = 0;
+   __syncthreads();
+   bool unsure = false;
+   if (inside) {
+      const float4 *src = tile_w ? s_tile + (size_t)threadIdx.x * P.oversample + (size_t)threadIdx.y * P.oversample * tile_w
+                                 : f3b_final_origin(P, i, j);
+      unsure = f3b_final_pixel<float, float>(P, i, j, src, tile_w ? (size_t)tile_w : (size_t)P.width, s_filt);
+   }
+   /* one global atomic per CTA, not per pixel: 10^5 atomics on one address cost more than the pass */
+   unsigned int slot = 0;
+   if (unsure) slot = atomicAdd(&s_n, 1u);
+   __syncthreads();
+   if (tid == 0 && s_n) s_base = atomicAdd(P.fixup_count, s_n);
+   __syncthreads();
+   if (unsure) P.fixup_list[s_base + slot] = (uint32_t)i | ((uint32_t)j << 16);
 }
 /* pass 2: the listed pixels again, in double */
 __global__ void __launch_bounds__(128) f3b_final_fixup_kernel(const F3FinalParams P) {
    const unsigned n = *P.fixup_count;
    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
       const uint32_t e = P.fixup_list[k];
-      f3b_final_pixel<double>(P, (int)(e & 0xffffu), (int)(e >> 16));
+      const int i = (int)(e & 0xffffu), j = (int)(e >> 16);
+      f3b_final_pixel<double, double>(P, i, j, f3b_final_origin(P, i, j), (size_t)P.width, P.filter);
    }
 }
 
@@ -644,7 +681,20 @@ int f3b_launch_final(const F3FinalParams &p, cudaStream_t stream) {
    }
    dim3 block(32, 8);
    dim3 grid((p.image_width + 31) / 32, (p.out_row_end - p.out_row_begin + 7) / 8);
-   f3b_final_kernel<<<grid, block, 0, stream>>>(p);
+   int tile_w = 31 * p.oversample + p.filter_width, tile_h = 7 * p.oversample + p.filter_width;
+   size_t smem = 0;
+   if (p.fixup_list) {
+      const size_t fbytes = ((size_t)p.filter_width * p.filter_width * 4 + 15) & ~(size_t)15;
+      smem = fbytes + (size_t)tile_w * tile_h * sizeof(float4);
+      if (smem > 96 * 1024) { /* very wide filters: taps straight from the accumulator */
+         tile_w = tile_h = 0;
+         smem = fbytes;
+      }
+      if (smem > 200 * 1024) return 0;
+      if (cudaFuncSetAttribute(f3b_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+         return 0;
+   }
+   f3b_final_kernel<<<grid, block, smem, stream>>>(p, tile_w, tile_h);
    if (cudaGetLastError() != cudaSuccess) return 0;
    launches++;
    if (p.fixup_list) {

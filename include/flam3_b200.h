@@ -99,6 +99,15 @@ void *f3b_pinned_alloc(size_t bytes);
 void f3b_pinned_free(void *p);
 int f3b_inputs_consumed(f3b_ctx *ctx);
 
+/* flam3_iterate (flam3.h:555, flam3.c:232-299) for n_chains independent chains at once: each
+ * starts at start_xy[2 t .. 2 t + 1] (NULL: a random point of [-1,1]^2) with colour 0, discards
+ * `fuse` iterations and stores n_per_chain samples. out_xycv (host) receives
+ * {x, y, colour, vis_adjusted} of sample i of chain t at [(i * n_chains + t) * 4]; *badvals the
+ * number of bad values met. `blob` is ONE packed sample (f3b_pack.h). What the analysis helpers
+ * either side of the render need (flam3_estimate_bounding_box flam3.c:3574, flam3_colorhist
+ * flam3.c:351; both provided by the drop-in on top of this). */
+int f3b_orbits(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int n_chains, int n_per_chain, int fuse,
+               uint64_t seed, const float *start_xy, float *out_xycv, uint64_t *badvals);
 int f3b_debug_apply_xform(f3b_ctx *ctx, const void *blob, size_t blob_bytes, int xform_index,
                           const float *in_xyc, int n, float *out_xycvb, uint64_t seed);
 /* bad values since f3b_frame_begin (stat_struct.badvals, rect.c:1251); waits for the stream */
@@ -213,6 +222,10 @@ int f3b_stage_stats(f3b_ctx *ctx, int stage, double *ms, uint64_t *launches);
 void f3b_stats_reset(f3b_ctx *ctx);
 /* Bytes copied host->device / device->host by this context since f3b_stats_reset. */
 int f3b_xfer_stats(f3b_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
+/* The context's 16 device counters as of now (waits for the stream): [0] bad values, [1] fullest
+ * bucket's count, [6] staged sums seen at >= 2^24, [7] saturated sums, [10..12] where the former
+ * were seen (cold sweep, hot list, merge). For tools. */
+int f3b_debug_counters(f3b_ctx *ctx, uint64_t out[16]);
 /* A CUDA-event stopwatch on the context's stream: start records an event, stop records a
  * second one, waits for it and returns the elapsed GPU milliseconds. */
 int f3b_timer_start(f3b_ctx *ctx);

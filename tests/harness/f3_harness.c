@@ -218,3 +218,23 @@ int h_iterate(void *cps, int idx, int n, int fuse, const double *p0, double *sam
    free(d);
    return bad;
 }
+
+/* the analysis helpers either side of the render (flam3.h:587-589), seeded like a frame */
+int h_bounding_box(void *cps, int idx, double eps, int nsamples, const char *seed, double *out4) {
+   flam3_frame f;
+   memset(&f, 0, sizeof(f));
+   seed_frame(&f, seed);
+   double bmin[2] = {0, 0}, bmax[2] = {0, 0};
+   int rv = flam3_estimate_bounding_box((flam3_genome *)cps + idx, eps, nsamples, bmin, bmax, &f.rc);
+   out4[0] = bmin[0];
+   out4[1] = bmin[1];
+   out4[2] = bmax[0];
+   out4[3] = bmax[1];
+   return rv;
+}
+int h_colorhist(void *cps, int idx, int num_batches, const char *seed, double *hist256) {
+   flam3_frame f;
+   memset(&f, 0, sizeof(f));
+   seed_frame(&f, seed);
+   return flam3_colorhist((flam3_genome *)cps + idx, num_batches, &f.rc, hist256);
+}

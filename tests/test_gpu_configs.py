@@ -100,7 +100,7 @@ def test_c3_shape_gate2(flame0, flame1):
 
 
 C5_SUBSET = ["mix107", "mix116", "mix123", "mix101", "var76", "var58", "var47", "var33", "var13", "var50",
-             "var98", "var0"]
+             "var98", "var00"]
 
 
 @pytest.mark.parametrize("name", C5_SUBSET)
