@@ -276,6 +276,21 @@ class Flam3Lib:
         s = C.string_at(p).decode()
         return s
 
+    def render_with_progress(self, genomes, abort_at=0, **kw):
+        """flam3_render with a progress callback installed (flam3_frame.progress): returns
+        (image, stats, dict(calls, max_percent, last_eta))."""
+        a = make_args(**kw)
+        w, h, _ = genomes.dims(a.first_genome)
+        out = np.zeros((h, w, a.nchan), dtype=np.uint8 if a.bytes_per_channel == 1 else np.uint16)
+        stats, prog = (C.c_double * 3)(), (C.c_double * 3)()
+        f = self._dll.h_render_progress
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.POINTER(RenderArgs), C.c_void_p, C.POINTER(C.c_double), C.c_int,
+                      C.POINTER(C.c_double)]
+        rv = f(genomes.ptr, C.byref(a), out.ctypes.data_as(C.c_void_p), stats, abort_at, prog)
+        st = dict(rv=rv, badvals=stats[0], num_iters=stats[1], render_seconds=stats[2])
+        return out, st, dict(calls=int(prog[0]), max_percent=prog[1], last_eta=prog[2])
+
     def bounding_box(self, genomes, idx=0, eps=0.01, nsamples=100000, seed="flam3b200"):
         """flam3_estimate_bounding_box: (rv, (xmin, ymin, xmax, ymax))."""
         f = self._dll.h_bounding_box

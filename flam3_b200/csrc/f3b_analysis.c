@@ -20,7 +20,8 @@
 
 #include "f3b_host.h"
 
-struct f3b_ctx *f3b_render_context(void);
+struct f3b_ctx *f3b_render_acquire(void); /* a free GPU context of the drop-in ... */
+void f3b_render_release(void);             /* ... and back */
 
 static int pack_for_orbits(flam3_genome *cp, uint32_t **words, size_t *used) {
    f3b_camera cam;
@@ -55,11 +56,14 @@ static int cmp_double(const void *a, const void *b) {
 int flam3_estimate_bounding_box(flam3_genome *cp, double eps, int nsamples, double *bmin, double *bmax,
                                 randctx *rc) {
    if (nsamples <= 0) nsamples = 10000;
-   struct f3b_ctx *ctx = f3b_render_context();
-   if (!ctx) return -1;
    uint32_t *words = NULL;
    size_t used = 0;
    if (pack_for_orbits(cp, &words, &used)) return -1; /* message printed, as by the reference */
+   struct f3b_ctx *ctx = f3b_render_acquire();
+   if (!ctx) {
+      free(words);
+      return -1;
+   }
    /* chains of ~200 samples: enough of them to fill the GPU's latency, long enough that the
     * 20 fused iterations stay a small share */
    int n_chains = nsamples / 200;
@@ -97,6 +101,7 @@ int flam3_estimate_bounding_box(flam3_genome *cp, double eps, int nsamples, doub
       rv = bv;
    } else if (pts && xs)
       fprintf(stderr, "flam3_estimate_bounding_box (B200): %s\n", f3b_last_error(ctx));
+   f3b_render_release();
    free(pts);
    free(xs);
    free(words);
@@ -107,11 +112,14 @@ int flam3_colorhist(flam3_genome *cp, int num_batches, randctx *rc, double *hist
    const int sbs = 10000;
    memset(hist, 0, 256 * sizeof(double));
    if (num_batches <= 0) return 0;
-   struct f3b_ctx *ctx = f3b_render_context();
-   if (!ctx) return 1;
    uint32_t *words = NULL;
    size_t used = 0;
    if (pack_for_orbits(cp, &words, &used)) return 1;
+   struct f3b_ctx *ctx = f3b_render_acquire();
+   if (!ctx) {
+      free(words);
+      return 1;
+   }
    /* the reference's batches are independent chains already (random start, 20 fused, 10000
     * stored): each becomes 50 chains of 200 */
    const int per = 200, n_chains = num_batches * (sbs / per);
@@ -128,6 +136,7 @@ int flam3_colorhist(flam3_genome *cp, int num_batches, randctx *rc, double *hist
       rv = 0;
    } else if (pts)
       fprintf(stderr, "flam3_colorhist (B200): %s\n", f3b_last_error(ctx));
+   f3b_render_release();
    free(pts);
    free(words);
    return rv;

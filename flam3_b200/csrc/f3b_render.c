@@ -32,10 +32,43 @@ static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
  * node. Default: the single device F3B_DEVICE (0). An entry may repeat ("0,0": two contexts
  * on one GPU, which is how the multi-GPU path is tested on a one-GPU box). */
 #define F3B_MAX_LOCAL 16
-static struct {
+typedef struct {
    int n;
    f3b_ctx *ctx[F3B_MAX_LOCAL];
-} g_group;
+} f3b_group_t;
+
+/* Independent frames may be rendered concurrently from different host threads (SURVEY §8(b)
+ * Threading; README.txt:336-338: GUIs call flam3_render from worker threads). A SLOT is
+ * everything one flam3_render call needs for itself: its GPU context(s), the page-locked batch
+ * buffer, the cached DE filter bank. F3B_CONTEXTS=n (default 1, at most 8) slots exist; a call
+ * takes a free one and waits when all are busy. g_lock guards the slot table and the
+ * configuration knobs below, which must be set before rendering starts, not during. */
+typedef struct {
+   uint32_t *words;
+   size_t cap, used; /* in words */
+} blob_buf;
+typedef struct {
+   int valid;
+   double max_rad, min_rad, curve;
+   int oversample;
+   f3b_de_filters de;
+} de_cache_t;
+typedef struct {
+   f3b_group_t group;
+   de_cache_t de;
+   blob_buf blobs;
+   double t0; /* start of the frame being rendered */
+   int busy;
+} f3b_slot;
+#define F3B_MAX_SLOTS 8
+static f3b_slot g_slots[F3B_MAX_SLOTS];
+static int g_nslots = 0;
+static pthread_cond_t g_slot_free = PTHREAD_COND_INITIALIZER;
+static __thread f3b_slot *t_slot = NULL; /* the slot the calling thread holds */
+#define g_group (t_slot->group)
+#define g_de_cache (t_slot->de)
+#define g_blobs (t_slot->blobs)
+#define g_progress_t0 (t_slot->t0)
 
 static int parse_devices(const char *e, int *dev, int cap) {
    int n = 0;
@@ -86,19 +119,58 @@ static f3b_ctx *get_ctx(void) {
    return g_group.ctx[0];
 }
 
-/* Exposed so hosts embedding the library (and the tests / bench) can reach the context
- * the drop-in renders with, e.g. for per-stage GPU timings. */
-f3b_ctx *f3b_render_context(void) {
+/* take a free slot (creating its contexts on first use); NULL when no GPU is usable */
+static f3b_ctx *slot_acquire(void) {
    pthread_mutex_lock(&g_lock);
-   f3b_ctx *c = get_ctx();
+   if (!g_nslots) {
+      const char *e = getenv("F3B_CONTEXTS");
+      g_nslots = e ? atoi(e) : 1;
+      if (g_nslots < 1) g_nslots = 1;
+      if (g_nslots > F3B_MAX_SLOTS) g_nslots = F3B_MAX_SLOTS;
+   }
+   f3b_slot *sl = NULL;
+   for (;;) {
+      for (int i = 0; i < g_nslots && !sl; i++)
+         if (!g_slots[i].busy) sl = &g_slots[i];
+      if (sl) break;
+      pthread_cond_wait(&g_slot_free, &g_lock);
+   }
+   sl->busy = 1;
+   t_slot = sl;
+   f3b_ctx *c = get_ctx(); /* context creation is serialised by g_lock */
+   if (!c) {
+      sl->busy = 0;
+      t_slot = NULL;
+      pthread_cond_signal(&g_slot_free);
+   }
    pthread_mutex_unlock(&g_lock);
    return c;
 }
-/* the i-th GPU context of this process (F3B_DEVICES), NULL beyond the last */
+static void slot_release(void) {
+   pthread_mutex_lock(&g_lock);
+   if (t_slot) t_slot->busy = 0;
+   t_slot = NULL;
+   pthread_cond_signal(&g_slot_free);
+   pthread_mutex_unlock(&g_lock);
+}
+/* for the other entry points of the drop-in that use a GPU context (f3b_analysis.c) */
+f3b_ctx *f3b_render_acquire(void) { return slot_acquire(); }
+void f3b_render_release(void) { slot_release(); }
+
+/* Exposed so hosts embedding the library (and the tests / bench) can reach the context
+ * the drop-in renders with (the first slot's), e.g. for per-stage GPU timings. Not to be used
+ * while another thread renders. */
+f3b_ctx *f3b_render_context_at(int i);
+f3b_ctx *f3b_render_context(void) { return f3b_render_context_at(0); }
+/* the i-th GPU context of the first slot (F3B_DEVICES), NULL beyond the last */
 f3b_ctx *f3b_render_context_at(int i) {
    pthread_mutex_lock(&g_lock);
+   if (!g_nslots) g_nslots = 1;
+   f3b_slot *saved = t_slot;
+   t_slot = &g_slots[0];
    f3b_ctx *c = get_ctx();
    c = (c && i >= 0 && i < g_group.n) ? g_group.ctx[i] : NULL;
+   t_slot = saved;
    pthread_mutex_unlock(&g_lock);
    return c;
 }
@@ -214,12 +286,6 @@ static double now_ms(void) {
 /* The DE filter bank depends only on (estimator, estimator_minimum, estimator_curve,
  * oversample): the last one built is kept (under g_lock), since animations and repeated
  * renders ask for the same bank every batch and building it costs ~0.15 ms of idle GPU. */
-static struct {
-   int valid;
-   double max_rad, min_rad, curve;
-   int oversample;
-   f3b_de_filters de;
-} g_de_cache;
 
 static int de_filters_cached(double max_rad, double min_rad, double curve, int oversample,
                              f3b_de_filters *out) {
@@ -239,28 +305,26 @@ static int de_filters_cached(double max_rad, double min_rad, double curve, int o
 }
 
 static int poll_progress(flam3_frame *spec, double percent, int stage) {
-   /* 0 continue, 1 abort, 2 pause (rect.c:324-373) */
+   /* 0 continue, 1 abort, 2 pause (rect.c:324-373); the 4th argument is the estimated time
+    * to completion in seconds, like rect.c:338-343 */
    if (!spec->progress) return 0;
-   int rv = (*spec->progress)(spec->progress_parameter, percent, stage, 0.0);
+   double eta = 0.0;
+   if (percent > 0.0 && g_progress_t0 > 0.0) eta = (now_ms() - g_progress_t0) * 1e-3 * (100.0 - percent) / percent;
+   int rv = (*spec->progress)(spec->progress_parameter, percent, stage, eta);
    while (rv == 2) {
       struct timespec ts = {0, 100000000};
       nanosleep(&ts, NULL);
-      rv = (*spec->progress)(spec->progress_parameter, percent, stage, 0.0);
+      rv = (*spec->progress)(spec->progress_parameter, percent, stage, eta);
    }
    return rv == 1;
 }
 
-typedef struct {
-   uint32_t *words;
-   size_t cap, used; /* in words */
-} blob_buf;
 
 /* The buffer the packed samples of a batch are assembled in lives across frames (under
  * g_lock) and is page-locked: fresh pageable memory costs a page fault per 4 KB and a
  * staging copy per upload, which for an animation frame (1000 samples, 4.6 MB) was a
  * quarter of the host time. f3b_iterate's upload from it is asynchronous, so
  * f3b_inputs_consumed must be awaited before the buffer is written again. */
-static blob_buf g_blobs = {NULL, 0, 0};
 
 static int blob_reserve(blob_buf *b, size_t extra) {
    if (b->used + extra <= b->cap) return 0;
@@ -435,6 +499,7 @@ static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *
 static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, int nchan,
                          int transp, stat_struct *stats, int force_count_plane) {
    const time_t tstart = time(NULL);
+   g_progress_t0 = now_ms();
    const int timing = getenv("F3B_TIMING") != NULL;
    double t_setup = now_ms(), t_pack = 0, t_serial = 0, t_iter = 0, t_dens = 0, t_fin = 0, t0;
    int rv = 1;
@@ -726,13 +791,40 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
       if (g_inject && !g_inject_preload) {
          /* post-pass only */
       } else {
-         for (int i = 0; i < nlocal; i++) {
-            if (i > 0) /* the plan is the same for every rank: only first_group is filled in */
+         /* With a progress callback installed (GUIs; the CLIs have none) a long batch is cut
+          * into slices of >= 2.5e8 iterations per GPU - slice s of S is "rank r + s N of S N"
+          * of the same chain-group sharding, so the image does not change - and the callback
+          * is polled between them (percent, ETA, abort, pause: rect.c:324-373). Without a
+          * callback the batch is one launch sequence and nothing waits on the host. */
+         int nslices = 1;
+         if (spec->progress) {
+            double total = 0.0;
+            for (int ts = 0; ts < ntemporal_samples; ts++) total += (double)jobs[ts].n_iters;
+            nslices = (int)(total / (2.5e8 * NR));
+            if (nslices < 1) nslices = 1;
+            if (nslices > 64) nslices = 64;
+         }
+         for (int sl = 0; sl < nslices; sl++) {
+            for (int i = 0; i < nlocal; i++) {
+               /* the plan is the same for every call: only first_group is filled in */
                for (int ts = 0; ts < ntemporal_samples; ts++) jobs[ts].first_group = 0;
-            if (f3b_iterate(lc[i], blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
-                            spec->bits != 64, max_chain, rank0 + i, NR)) {
-               ctx = lc[i];
-               goto gpu_error;
+               if (f3b_iterate(lc[i], blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
+                               spec->bits != 64, max_chain, rank0 + i + sl * NR, NR * nslices)) {
+                  ctx = lc[i];
+                  goto gpu_error;
+               }
+            }
+            if (nslices > 1) {
+               for (int i = 0; i < nlocal; i++)
+                  if (f3b_sync(lc[i])) {
+                     ctx = lc[i];
+                     goto gpu_error;
+                  }
+               if (poll_progress(spec, 100.0 * (batch_num + (sl + 1.0) / nslices) / nbatches, 0)) {
+                  if (verbose) fprintf(stderr, "\naborted!\n");
+                  rv = 0;
+                  goto done;
+               }
             }
          }
       }
@@ -935,10 +1027,9 @@ int flam3_render(flam3_frame *spec, void *out, int field, int nchan, int transp,
       fprintf(stderr, "flam3: bits must be 32, 33, or 64 not %d.\n", spec->bits);
       return 1;
    }
-   static double t_last_return = 0.0;
+   static __thread double t_last_return = 0.0;
    const double t_enter = now_ms();
-   pthread_mutex_lock(&g_lock);
-   f3b_ctx *ctx = get_ctx();
+   f3b_ctx *ctx = slot_acquire(); /* waits while all F3B_CONTEXTS slots are rendering */
    int rv = 1;
    if (ctx) {
       const randctx rc0 = spec->rc;
@@ -948,11 +1039,11 @@ int flam3_render(flam3_frame *spec, void *out, int field, int nchan, int transp,
          rv = render_locked(ctx, spec, out, field, nchan, transp, stats, 1);
       }
       if (rv < 0) rv = 1;
+      slot_release();
    }
    if (getenv("F3B_TIMING"))
       fprintf(stderr, "f3b timing: flam3_render %.2f ms, %.2f ms in the caller since the previous call\n",
               now_ms() - t_enter, t_last_return > 0.0 ? t_enter - t_last_return : 0.0);
    t_last_return = now_ms();
-   pthread_mutex_unlock(&g_lock);
    return rv;
 }

@@ -238,3 +238,50 @@ int h_colorhist(void *cps, int idx, int num_batches, const char *seed, double *h
    seed_frame(&f, seed);
    return flam3_colorhist((flam3_genome *)cps + idx, num_batches, &f.rc, hist256);
 }
+
+/* a progress callback like a GUI's (flam3.h:599-614, rect.c:324-373): counts its calls,
+ * remembers the last percentage and ETA, asks for an abort at call number abort_at (0 = never) */
+static struct { int calls, abort_at; double last_percent, last_eta, max_percent; } g_prog;
+static int harness_progress(void *param, double percent, int stage, double eta) {
+   (void)param;
+   (void)stage;
+   g_prog.calls++;
+   g_prog.last_percent = percent;
+   g_prog.last_eta = eta;
+   if (percent > g_prog.max_percent) g_prog.max_percent = percent;
+   return (g_prog.abort_at && g_prog.calls >= g_prog.abort_at) ? 1 : 0;
+}
+/* h_render with the callback installed; prog_out = {calls, max percent, last eta} */
+int h_render_progress(void *cps, const h_render_args *a, void *out, double *stats_out, int abort_at,
+                      double *prog_out) {
+   flam3_genome *g = (flam3_genome *)cps;
+   flam3_frame f;
+   stat_struct st;
+   memset(&f, 0, sizeof(f));
+   memset(&st, 0, sizeof(st));
+   memset(&g_prog, 0, sizeof(g_prog));
+   g_prog.abort_at = abort_at;
+   f.pixel_aspect_ratio = a->pixel_aspect_ratio;
+   f.genomes = g + a->first_genome;
+   f.ngenomes = a->ngenomes;
+   f.verbose = a->verbose;
+   f.bits = a->bits;
+   f.bytes_per_channel = a->bytes_per_channel;
+   f.earlyclip = a->earlyclip;
+   f.time = a->time;
+   f.progress = harness_progress;
+   f.progress_parameter = 0;
+   f.nthreads = a->nthreads;
+   f.sub_batch_size = a->sub_batch_size;
+   seed_frame(&f, a->isaac_seed);
+   int rv = flam3_render(&f, out, a->field, a->nchan, a->transp, &st);
+   if (stats_out) {
+      stats_out[0] = st.badvals;
+      stats_out[1] = (double)st.num_iters;
+      stats_out[2] = (double)st.render_seconds;
+   }
+   prog_out[0] = g_prog.calls;
+   prog_out[1] = g_prog.max_percent;
+   prog_out[2] = g_prog.last_eta;
+   return rv;
+}

@@ -329,3 +329,20 @@ def test_warp_aggregated_adds_give_the_same_histogram(flame0, variant):
     if variant == "collapsed":
         h = hists["0"][..., 4]
         assert np.sort(h.ravel())[-8:].sum() > 0.9 * h.sum()   # really collapsed
+
+
+def test_progress_callback_between_slices(flame0):
+    """flam3_frame.progress (rect.c:324-373): GUIs get a percentage, an ETA and the chance to
+    abort while a long frame renders. The drop-in cuts a long batch into slices of the same
+    chain-group sharding and polls between them: same image as without a callback, rising
+    percentages, and an abort returns 0 early like the reference's `goto done`."""
+    _, gpu, _ = libs()
+    gg = gpu.parse(resize(flame0, 640, 480, scale=240, quality=4000, temporal_samples=1))
+    plain, st0, _ = gpu.render(gg, isaac_seed="prog")
+    img, st, pr = gpu.render_with_progress(gg, isaac_seed="prog")
+    assert st0["rv"] == 0 and st["rv"] == 0
+    assert pr["calls"] >= 5 and 99.0 <= pr["max_percent"] <= 100.0
+    assert np.array_equal(plain, img)
+    part, st2, pr2 = gpu.render_with_progress(gg, abort_at=2, isaac_seed="prog")
+    assert st2["rv"] == 0 and pr2["calls"] == 2 and pr2["max_percent"] < 60.0
+    assert not np.array_equal(part, plain)

@@ -95,3 +95,44 @@ def test_unmodified_flam3_render_uses_f3b_devices(tmp_path):
         imgs.append([open(tmp_path / ("%s%05d.ppm" % (tag, i)), "rb").read() for i in range(2)])
     for a, b in zip(*imgs):
         assert len(a) > 640 * 480 * 3 and a == b
+
+
+THREADS_SCRIPT = r"""
+import os, sys, threading, numpy as np
+sys.path.insert(0, %(root)r)
+import flam3_b200 as fb
+from flam3_b200.genome_xml import resize
+gpu = fb.load_dropin()
+f0 = open(os.path.join(%(root)r, "tests/golden/test_flame0.flam3")).read()
+f1 = open(os.path.join(%(root)r, "tests/golden/test_flame1.flam3")).read()
+jobs = [(resize(f0, 400, 300, scale=100, quality=300, temporal_samples=1), "t0"),
+        (resize(f1, 320, 240, scale=80, quality=400, temporal_samples=1), "t1"),
+        (resize(f0, 256, 256, scale=64, quality=200, oversample=2, temporal_samples=1), "t2"),
+        (resize(f1, 500, 200, scale=120, quality=300, temporal_samples=3), "t3")]
+genomes = [gpu.parse(x) for x, _ in jobs]
+seq = [gpu.render(g, isaac_seed=s)[0] for g, (_, s) in zip(genomes, jobs)]
+par = [None] * len(jobs)
+def work(i):
+    for _ in range(3):
+        par[i] = gpu.render(genomes[i], isaac_seed=jobs[i][1])[0]
+th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+[t.start() for t in th]
+[t.join() for t in th]
+ok = all(np.array_equal(a, b) and a.max() > 0 for a, b in zip(seq, par))
+print("concurrent == sequential:", ok)
+sys.exit(0 if ok else 1)
+"""
+
+
+@pytest.mark.parametrize("contexts", ["1", "3"])
+def test_concurrent_frames_from_several_host_threads(contexts):
+    """SURVEY §8(b) Threading: independent frames may be rendered concurrently from different
+    host threads. Four threads render four different frames three times each; with
+    F3B_CONTEXTS=3 three of them are on the GPU at once (each call takes a free slot: context,
+    batch buffer, filter cache), with 1 they take turns. Either way every image equals the one
+    rendered alone."""
+    env = dict(os.environ, F3B_CONTEXTS=contexts)
+    env.pop("F3B_DEVICES", None)
+    r = subprocess.run([sys.executable, "-c", THREADS_SCRIPT % {"root": ROOT}], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-1500:])
