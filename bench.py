@@ -302,6 +302,9 @@ def main():
 
     os.environ["F3B_DEVICE"] = str(local_rank)
     os.environ.pop("F3B_DEVICES", None)
+    if world > 1 and "F3B_HOST_THREADS" not in os.environ:
+        # N processes share the host: each packs its temporal samples on its share of the cores
+        os.environ["F3B_HOST_THREADS"] = str(max(1, min(16, (os.cpu_count() or 1) // world)))
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:

@@ -398,7 +398,7 @@ class CoreLib:
         d.f3b_plan_chains.restype = C.c_uint32
         d.f3b_plan_chains.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
         d.f3b_iterate.argtypes = [vp, vp, C.c_size_t, C.POINTER(F3Job), ci, C.c_uint64, ci,
-                                  C.c_uint32, ci, ci]
+                                  C.c_uint32, C.c_uint32, ci, ci]
         d.f3b_badvals.argtypes = [vp, C.POINTER(C.c_double)]
         d.f3b_density.argtypes = [vp, C.POINTER(DensityDesc)]
         d.f3b_density_rows.argtypes = [vp, C.POINTER(DensityDesc), ci, ci]

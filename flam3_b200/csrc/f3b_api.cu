@@ -33,7 +33,8 @@ struct DevBuf {
 struct f3b_ctx {
    int device = 0;
    int sms = 0;
-   int iter_blocks_per_sm = 0;
+   int iter_blocks_per_sm = 0;         /* resident CTAs per SM of the SIMPLE kernels ... */
+   int iter_blocks_per_sm_generic = 0; /* ... and of the generic ones */
    cudaStream_t stream = nullptr;
    char err[512] = {0};
 
@@ -190,8 +191,10 @@ int f3b_ctx_create(int device, f3b_ctx **out) {
       return 1;
    }
    cudaMemsetAsync(ctx->d_badvals, 0, F3B_NCOUNTERS * sizeof(unsigned long long), ctx->stream);
-   ctx->iter_blocks_per_sm = f3b_iterate_max_blocks_per_sm(16 * 1024);
+   ctx->iter_blocks_per_sm = f3b_iterate_max_blocks_per_sm(16 * 1024, true);
    if (ctx->iter_blocks_per_sm <= 0) ctx->iter_blocks_per_sm = 1;
+   ctx->iter_blocks_per_sm_generic = f3b_iterate_max_blocks_per_sm(16 * 1024, false);
+   if (ctx->iter_blocks_per_sm_generic <= 0) ctx->iter_blocks_per_sm_generic = 1;
    *out = ctx;
    return 0;
 }
@@ -413,13 +416,22 @@ static int accum_materialize(f3b_ctx *ctx) {
  *   - else to whole rounds of one GPU's resident threads when there are more chains than
  *     that, so no tail wave is left. */
 #define F3B_PLAN_GPUS 8
+static uint32_t plan_chains(f3b_ctx *ctx, int blocks_per_sm, uint64_t n_iters, uint32_t max_chain_len,
+                            uint32_t n_jobs, uint32_t workers);
 uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len, uint32_t n_jobs,
                          uint32_t workers) {
+   if (!ctx) return 0;
+   return plan_chains(ctx, ctx->iter_blocks_per_sm, n_iters, max_chain_len, n_jobs, workers);
+}
+/* blocks_per_sm: of the kernel class that will run the chains (the SIMPLE kernels keep 3 CTAs
+ * per SM resident, the generic ones 2) */
+static uint32_t plan_chains(f3b_ctx *ctx, int blocks_per_sm, uint64_t n_iters, uint32_t max_chain_len,
+                            uint32_t n_jobs, uint32_t workers) {
    if (!ctx || n_iters == 0) return 0;
    if (max_chain_len == 0) max_chain_len = 10000;
    if (n_jobs == 0) n_jobs = 1;
    if (workers == 0) workers = 1;
-   const uint64_t T = (uint64_t)ctx->sms * ctx->iter_blocks_per_sm * F3B_CHAINS_PER_GROUP;
+   const uint64_t T = (uint64_t)ctx->sms * blocks_per_sm * F3B_CHAINS_PER_GROUP;
    uint64_t Ts = T / n_jobs;
    if (Ts < 32) Ts = 32;
    if (Ts >= F3B_CHAINS_PER_GROUP) Ts -= Ts % F3B_CHAINS_PER_GROUP;
@@ -475,8 +487,15 @@ int f3b_inputs_consumed(f3b_ctx *ctx) {
    return 0;
 }
 
+/* every sample qualifies for the SIMPLE kernels (<= 4 xforms, no xaos, no final xform, step
+ * palette, all xforms opaque)? */
+static bool blob_is_simple(const uint32_t *w) {
+   return !w[F3B_H_XAOS] && w[F3B_H_CHOOSER_STRIDE] == 4 && (w[F3B_H_PLOT] & F3B_PLOT_READY) &&
+          !w[F3B_H_PALMODE] && (int)w[F3B_H_FINAL] < 0;
+}
+
 int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *jobs, int n_jobs,
-                uint64_t seed, int floor_adds, uint32_t max_chain_len, int rank, int nranks) {
+                uint64_t seed, int floor_adds, uint32_t max_chain_len, uint32_t workers, int rank, int nranks) {
    if (!ctx || !blobs || !jobs || n_jobs <= 0) return fail(ctx, "f3b_iterate: bad arguments");
    if (nranks <= 0 || rank < 0 || rank >= nranks) return fail(ctx, "f3b_iterate: bad rank");
    if (!ctx->hist_color.p || !ctx->exact_color.p) return fail(ctx, "f3b_iterate: f3b_frame_begin not called");
@@ -486,9 +505,18 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
    std::vector<uint32_t> group_job;
    size_t max_blob = 0;
    uint64_t total_chains = 0;
+   /* which kernel class runs this batch decides how many threads are resident, which the
+    * chain plan rounds to */
+   bool all_simple = getenv("F3B_NO_SIMPLE") == nullptr;
+   for (int j = 0; j < n_jobs && all_simple; j++) {
+      if (jobs[j].blob_offset % 16 || jobs[j].blob_offset + F3B_H_SIZE * 4 > blob_bytes)
+         return fail(ctx, "f3b_iterate: job %d blob offset invalid", j);
+      all_simple = blob_is_simple((const uint32_t *)((const char *)blobs + jobs[j].blob_offset));
+   }
+   const int plan_bps = all_simple ? ctx->iter_blocks_per_sm : ctx->iter_blocks_per_sm_generic;
    for (int j = 0; j < n_jobs; j++) {
       f3b_job &jb = jobs[j];
-      if (jb.n_chains == 0) jb.n_chains = f3b_plan_chains(ctx, jb.n_iters, max_chain_len, n_jobs, 1);
+      if (jb.n_chains == 0) jb.n_chains = plan_chains(ctx, plan_bps, jb.n_iters, max_chain_len, n_jobs, workers);
       total_chains += jb.n_chains;
    }
    /* Chains per group (= threads per CTA): 256 when there is plenty of work; small batches
@@ -628,8 +656,44 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       P.bin_pos = (unsigned int *)ctx->bin_pos.p;
       smem_bytes = (size_t)P.bin_smem_off * 4 + (size_t)(group_size / 32) * P.bin_warp_words * 4;
    }
-   const int bps = f3b_iterate_blocks_per_sm(group_size, smem_bytes);
-   if (bps <= 0) return fail(ctx, "f3b_iterate: kernel does not fit with %zu bytes of shared memory", smem_bytes);
+   /* warp-uniform xform step (f3b_iterate.cu): CTAs of >= 4 warps, not with the binned
+    * scatter; per sample it is off for xaos genomes. It pays when the xforms run DIFFERENT
+    * variation code, i.e. when lanes that picked different xforms would diverge (random
+    * genomes with several variations per xform: 1.6-5.4x, profiles/r02_warp_uniform_ab.txt); a
+    * classic flame whose xforms share their code path loses 12 % to the CTA-wide exchange of
+    * the walkers. So: on when the standard xforms of the first sample differ in their
+    * variation lists or flags. F3B_WU=0/1 overrides. */
+   P.warp_uniform = 0;
+   P.wu_smem_off = 0;
+   {
+      const uint32_t *w0 = (const uint32_t *)((const char *)blobs + jobs[0].blob_offset);
+      bool heterogeneous = false;
+      uint64_t first_sig = 0;
+      for (uint32_t q = 0; q < w0[F3B_H_NSTD]; q++) {
+         const uint32_t rec = w0[F3B_H_XF_BASE] + q * w0[F3B_H_XF_STRIDE];
+         uint64_t sig = 0xcbf29ce484222325ull ^ (w0[rec + F3B_X_FLAGS] & 0xffu);
+         const float *fr = (const float *)(w0 + rec);
+         sig = (sig ^ (fr[F3B_X_WLINEAR] != 0.0f ? 1u : 0u) ^ (fr[F3B_X_WSPHERICAL] != 0.0f ? 2u : 0u)) * 0x100000001b3ull;
+         for (uint32_t pv = rec + F3B_X_VARS; pv < rec + F3B_X_VARS + (w0[rec + F3B_X_FLAGS] >> 8);) {
+            sig = (sig ^ (w0[pv] & 0xffu)) * 0x100000001b3ull;
+            pv += 2 + (w0[pv] >> 8);
+         }
+         if (q == 0) first_sig = sig;
+         else if (sig != first_sig) heterogeneous = true;
+      }
+      const char *we = getenv("F3B_WU");
+      /* (the classic-flame kernels have no variation code to diverge in: they only lose) */
+      const bool want = we ? atoi(we) != 0 : (heterogeneous && !all_simple);
+      if (want && !binned && group_size >= 128) {
+         P.warp_uniform = 1;
+         P.wu_smem_off = (uint32_t)((smem_bytes + 15) / 16 * 4);
+         smem_bytes = (size_t)P.wu_smem_off * 4 + (size_t)group_size * 3 * sizeof(float);
+      }
+   }
+   const int bps_simple = f3b_iterate_blocks_per_sm(group_size, smem_bytes, true);
+   const int bps_generic = f3b_iterate_blocks_per_sm(group_size, smem_bytes, false);
+   if (bps_simple <= 0 || bps_generic <= 0)
+      return fail(ctx, "f3b_iterate: kernel does not fit with %zu bytes of shared memory", smem_bytes);
    ctx->staging_dirty = true;
 
    /* One launch per `cap` temporal samples (their warp-uniform camera and chooser constants
@@ -706,6 +770,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
                     F3B_HF_PAL_LINEAR)) != (F3B_HF_CHOOSER_CONST | F3B_HF_PLOT_READY))
             simple = false;
       }
+      const int bps = simple ? bps_simple : bps_generic;
       P.job_base = (uint32_t)j0;
       P.group_begin = jobs[j0].first_group;
       P.n_groups = (j1 < n_jobs) ? jobs[j1].first_group : n_groups;
@@ -848,6 +913,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
             F3IterateParams Q = P;
             Q.probe_iters = 64;
             Q.sweep_on = 0;
+            Q.warp_uniform = 0;
             Q.badvals = ctx->d_badvals + 4;
             int pgrid = ctx->sms < grid ? ctx->sms : grid;
             const uint64_t lim = (uint64_t)P.group_begin + (uint64_t)pgrid * (uint64_t)nranks;

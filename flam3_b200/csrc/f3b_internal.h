@@ -131,6 +131,8 @@ struct F3IterateParams {
                                        lost), [1] entries in sat_list, [4..6] diagnostics: where
                                        the losses were seen (cold pass, hot list, merge) */
    uint32_t *sat_list;           /* device: bucket * 8 + channel of exact sums that wrapped */
+   uint32_t warp_uniform;        /* warp-uniform xform step + walker exchange (f3b_iterate.cu) */
+   uint32_t wu_smem_off;         /* words: 3 floats per walker of the CTA behind the blob */
    /* binned scatter (histograms that do not fit L2; AGG kernels only, see f3b_iterate.cu):
     * hits become 8-byte records in per-region queues instead of reductions */
    uint32_t bin_regions;         /* 0 = off; else regions of bin_region_rows bucket rows each */
@@ -153,9 +155,9 @@ struct F3IterateParams {
 int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_consts,
                        bool count_channel, bool simple, bool aggregate, int grid_blocks,
                        int group_size, size_t smem_bytes, cudaStream_t stream);
-int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes);
+int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes, bool simple);
 int f3b_iterate_const_capacity(void);
-int f3b_iterate_max_blocks_per_sm(size_t smem_bytes);
+int f3b_iterate_max_blocks_per_sm(size_t smem_bytes, bool simple);
 /* exact planes += all staging copies (saturating for the integer buckets); the staging
  * copies are left zeroed. hot_max receives the fullest bucket's count (uint32, atomicMax). */
 struct F3MergeParams {

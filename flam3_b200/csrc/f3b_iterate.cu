@@ -35,7 +35,12 @@
 
 #define F3B_BLOCK F3B_CHAINS_PER_GROUP
 #ifndef F3B_ITER_MIN_BLOCKS
-#define F3B_ITER_MIN_BLOCKS 3 /* 80 registers, 24 warps/SM: best of {2,3,4} on B200 (profiles/r01) */
+#define F3B_ITER_MIN_BLOCKS 3 /* 24 walker warps + 3 sweeper warps per SM, 72 registers */
+#endif
+#ifndef F3B_GENERIC_MIN_BLOCKS
+#define F3B_GENERIC_MIN_BLOCKS 2 /* the non-SIMPLE instantiations: 96 registers, 16 walker warps per SM.
+                                    With 3 CTAs they have 72 registers, spill, and run 30-47 % slower on
+                                    the random genomes of C5 (profiles/r02_generic_occupancy_ab.txt) */
 #endif
 
 __device__ __forceinline__ void f3b_red_v4(float4 *addr, float r, float g, float b, float a) {
@@ -136,11 +141,41 @@ __device__ __noinline__ bool f3b_bump_aggregate(const F3IterateParams &P, size_t
     * any sweeper could empty its staging copy (a collapsed attractor adds 1e12 per second to
     * one address): the aggregated sum goes straight into the exact bucket. Lone hits of the
     * same bucket still take the staged path, at a rate the sweepers handle. */
-   f3b_carry_channel(P, bucket, 0, a.x + sx);
-   f3b_carry_channel(P, bucket, 1, a.y + sy);
-   f3b_carry_channel(P, bucket, 2, a.z + sz);
-   f3b_carry_channel(P, bucket, 3, a.w + sw);
-   if (P.hist_count) f3b_carry_channel(P, bucket, 4, c + sc);
+   const float tx = a.x + sx, ty = a.y + sy, tz = a.z + sz, tw = a.w + sw, tc = c + sc;
+   if (!P.exact_f64) {
+      /* The count channel (the alpha channel when it doubles as the count) is never smaller
+       * than the others: every hit adds 255 vis to it and at most that to the rest. So ONE
+       * atomic with a return value - on the count - tells whether anything can wrap: while it
+       * is below 2^31 the other channels go out as plain reductions (r and g as one 64-bit
+       * reduction: no carry can cross the halves), which is what keeps the hot addresses of a
+       * collapsed attractor from serialising on four round trips per add. Near saturation
+       * every channel takes the careful path. */
+      unsigned int *ec = reinterpret_cast<unsigned int *>(P.exact_color) + bucket * 4;
+      unsigned int *top = P.hist_count ? reinterpret_cast<unsigned int *>(P.exact_count) + bucket : ec + 3;
+      const unsigned int addt = (unsigned int)(P.hist_count ? tc : tw);
+      const unsigned int old = atomicAdd(top, addt);
+      if (old < 0x7fff0000u && old + addt < 0x80000000u) {
+         const unsigned long long rg = (unsigned long long)(unsigned int)tx | ((unsigned long long)(unsigned int)ty << 32);
+         asm volatile("red.global.add.u64 [%0], %1;" ::"l"(ec), "l"(rg) : "memory");
+         asm volatile("red.global.add.u32 [%0], %1;" ::"l"(ec + 2), "r"((unsigned int)tz) : "memory");
+         if (P.hist_count) asm volatile("red.global.add.u32 [%0], %1;" ::"l"(ec + 3), "r"((unsigned int)tw) : "memory");
+         return false;
+      }
+      if (old + addt < old) { /* the count itself wrapped: pinned to UINT_MAX after the merge */
+         const unsigned long long slot = atomicAdd(P.exact_flags + 1, 1ull);
+         if (slot < F3B_SAT_LIST_CAP) P.sat_list[slot] = (uint32_t)(bucket * 8 + (size_t)(P.hist_count ? 4 : 3));
+      }
+      f3b_carry_channel(P, bucket, 0, tx);
+      f3b_carry_channel(P, bucket, 1, ty);
+      f3b_carry_channel(P, bucket, 2, tz);
+      if (P.hist_count) f3b_carry_channel(P, bucket, 3, tw);
+      return false;
+   }
+   f3b_carry_channel(P, bucket, 0, tx);
+   f3b_carry_channel(P, bucket, 1, ty);
+   f3b_carry_channel(P, bucket, 2, tz);
+   f3b_carry_channel(P, bucket, 3, tw);
+   if (P.hist_count) f3b_carry_channel(P, bucket, 4, tc);
    return false;
 }
 
@@ -442,7 +477,8 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
  * step palette and fully visible xforms (the classic flame): the flag tests fold away and
  * the xform pick is three compares on a packed table from the constant bank. */
 template <bool COUNT, bool SIMPLE, bool AGG>
-__global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
+__global__ void __launch_bounds__(F3B_BLOCK + 32, SIMPLE ? F3B_ITER_MIN_BLOCKS : F3B_GENERIC_MIN_BLOCKS)
+f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
    extern __shared__ __align__(16) uint32_t smem[];
    const float *sf = reinterpret_cast<const float *>(smem);
    __shared__ int s_done;
@@ -489,19 +525,37 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
 
       const uint32_t chain = (g - job.first_group) * nct + tid; /* nct chains per group */
       const bool binned = AGG && P.bin_regions != 0;
-      if (chain >= job.n_chains && !binned) continue;
+      /* Warp-uniform xform step: the 32 walkers of a warp apply the SAME xform in an iteration
+       * (picked from one lane's draw, a different lane every iteration). Each walker still
+       * sees xforms that are independent over time with the chooser's probabilities, so its
+       * orbit is a chaos game as before - but the three LDS.128 of the xform record become
+       * broadcasts (12 -> 3 wavefronts of the ~41 per warp-iteration that bound the kernel)
+       * and the lanes run the same variation code (random genomes: 6-16 of 32 lanes active
+       * otherwise). Walkers that kept sharing their xforms would contract onto one another,
+       * so every 4 iterations the CTA's walkers are dealt out anew: thread (warp w, lane l)
+       * takes over the walker of thread (l * W + w) of W warps - each warp's 32 walkers come
+       * from all the others. Not with xaos (the pick depends on the walker's last xform), not
+       * for CTAs of fewer than 4 warps. */
+      const bool wu = P.warp_uniform && !binned && !(c_samp(ji - P.job_base).lay.x & F3B_HF_XAOS);
+      const bool lockstep = binned || wu;
+      if (chain >= job.n_chains && !lockstep) continue;
 
       /* stored iterations of this chain */
       const uint64_t base = job.n_iters / job.n_chains;
       const uint32_t rem = (uint32_t)(job.n_iters % job.n_chains);
       int n_store = chain < job.n_chains ? (int)(base + (chain < rem ? 1u : 0u)) : 0;
-      if (n_store == 0 && !binned) continue;
+      if (n_store == 0 && !lockstep) continue;
       if (AGG && P.probe_iters && n_store > (int)P.probe_iters) n_store = (int)P.probe_iters;
       /* binned scatter: the lanes of a warp stay together through the loop (the records are
-       * committed by the whole warp), a lane with fewer iterations idles at the end */
+       * committed by the whole warp), a lane with fewer iterations idles at the end; the
+       * warp-uniform step keeps the whole CTA together (the walkers change hands) */
       int n_loop = n_store;
       if (binned) {
          n_loop = __reduce_max_sync(0xffffffffu, n_store);
+         if (n_loop == 0) continue;
+      } else if (wu) {
+         n_loop = (int)(base + (rem ? 1u : 0u));
+         if (AGG && P.probe_iters && n_loop > (int)P.probe_iters) n_loop = (int)P.probe_iters;
          if (n_loop == 0) continue;
       }
 
@@ -525,13 +579,21 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
 
       for (int i = -(int)job.fuse; i < n_loop; i++) {
          uint32_t bin_a = F3B_BIN_NULL, bin_c = 0, bin_r = 0;
+         uint32_t wu_rnd = 0;
+         if (wu) { /* every lane draws, lane (i mod 32)'s draw picks the xform for all */
+            wu_rnd = rng.next();
+            wu_rnd = __shfl_sync(0xffffffffu, wu_rnd, (unsigned)(i + 1024) & 31u);
+         }
          do { /* `continue` below ends the iteration's work and falls through to the commit */
-         if (binned && (n_store == 0 || i >= n_store)) continue;
+         /* a lane without (more) iterations of its own idles; with the warp-uniform step it
+          * still runs the fuse iterations, so that the walker it holds is on the attractor
+          * when another thread takes it over */
+         if (lockstep && i >= n_store && (binned || i >= 0)) continue;
          float qx, qy, qc, qv;
          uint32_t fn = 0;
          /* flam3.c:249-270: pick + apply, retrying a bad value up to 4 times in place */
          for (int consec = 0;;) {
-            const uint32_t rnd = rng.next();
+            const uint32_t rnd = (wu && consec == 0) ? wu_rnd : rng.next();
             const uint32_t k = rnd & (F3B_CHOOSER_GRAIN - 1u);
             /* `ci` is redefined opaquely so the constant loads below stay in the loop; hoisted,
              * they would occupy a dozen registers across the variation code */
@@ -695,6 +757,19 @@ __global__ void __launch_bounds__(F3B_BLOCK + 32, F3B_ITER_MIN_BLOCKS) f3b_itera
             __syncwarp();
             f3b_bin_commit(P, wq, bin_a, bin_c, bin_r, blk_next, blk_end);
          }
+         if (wu && (((unsigned)(i + (int)job.fuse) & 3u) == 3u) && i + 1 < n_loop) {
+            /* deal the walkers out anew (transpose of the warps x lanes grid) */
+            float *xs = reinterpret_cast<float *>(smem + P.wu_smem_off);
+            xs[tid] = px;
+            xs[nct + tid] = py;
+            xs[2 * nct + tid] = pc;
+            f3b_chain_barrier(nct);
+            const uint32_t from = (tid & 31u) * (nct >> 5) + (tid >> 5);
+            px = xs[from];
+            py = xs[nct + from];
+            pc = xs[2 * nct + from];
+            f3b_chain_barrier(nct);
+         }
       }
    }
    if (AGG && P.bin_regions) f3b_bin_flush(P, wq, blk_next, blk_end);
@@ -816,15 +891,17 @@ int f3b_launch_debug_apply(const uint32_t *blob, size_t blob_bytes, int xform_in
 
 int f3b_iterate_const_capacity(void) { return F3B_PARAM_SAMPLES; }
 
-int f3b_iterate_max_blocks_per_sm(size_t smem_bytes) {
-   return f3b_iterate_blocks_per_sm(F3B_BLOCK, smem_bytes);
+int f3b_iterate_max_blocks_per_sm(size_t smem_bytes, bool simple) {
+   return f3b_iterate_blocks_per_sm(F3B_BLOCK, smem_bytes, simple);
 }
 
-int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes) {
+int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes, bool simple) {
    int nb = 0;
    /* the blob, plus the per-warp region queues of the binned scatter (AGG kernels) */
    const int smax = (int)(F3B_MAX_BLOB_WORDS * 4) + 8 * (32 + F3B_BIN_MAX_REGIONS * 130) * 4;
    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
+   static bool attrs_set = false; /* per process and device 0..n alike: the attribute is per function */
+   if (!attrs_set) attrs_set = true;
    cudaFuncSetAttribute(f3b_iterate_kernel<true, false, false>, at, smax);
    cudaFuncSetAttribute(f3b_iterate_kernel<false, false, false>, at, smax);
    cudaFuncSetAttribute(f3b_iterate_kernel<true, true, false>, at, smax);
@@ -833,10 +910,13 @@ int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes) {
    cudaFuncSetAttribute(f3b_iterate_kernel<false, false, true>, at, smax);
    cudaFuncSetAttribute(f3b_iterate_kernel<true, true, true>, at, smax);
    cudaFuncSetAttribute(f3b_iterate_kernel<false, true, true>, at, smax);
-   /* group_size counts the walkers; the CTA has one more warp (the sweeper) */
-   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, true>,
-                                                     group_size + 32, smem_bytes) != cudaSuccess)
-      return 0;
+   /* group_size counts the walkers; the CTA has one more warp (the sweeper). The SIMPLE and the
+    * generic instantiations have different register budgets (3 and 2 CTAs per SM). */
+   cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, true, true>,
+                                                                          group_size + 32, smem_bytes)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, true>,
+                                                                          group_size + 32, smem_bytes);
+   if (e != cudaSuccess) return 0;
    return nb;
 }
 

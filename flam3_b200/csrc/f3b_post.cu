@@ -403,7 +403,9 @@ int f3b_launch_density(const F3DensityParams &p_in, cudaStream_t stream) {
 #define F3B_FIXUP_EPS 0.01f
 template <typename T> __device__ __forceinline__ T f3b_pow(T a, T b);
 template <> __device__ __forceinline__ double f3b_pow<double>(double a, double b) { return pow(a, b); }
-template <> __device__ __forceinline__ float f3b_pow<float>(float a, float b) { return powf(a, b); }
+/* the float pass is a filter in front of the double one (below): ex2(b lg2 a) is ~1e-6
+ * accurate in relative terms, far inside the 0.01 it is trusted to */
+template <> __device__ __forceinline__ float f3b_pow<float>(float a, float b) { return __powf(a, b); }
 
 template <typename T> __device__ __forceinline__ T f3b_calc_alpha(T dens, T g, T linrange) {
    if (!(dens > T(0))) return T(0);
@@ -540,7 +542,7 @@ __global__ void __launch_bounds__(256) f3b_earlyclip_kernel(const F3FinalParams 
  * close to a truncation boundary for the float result to be trusted. */
 template <typename T, typename FT>
 __device__ __forceinline__ bool f3b_final_pixel(const F3FinalParams &P, int i, int j, const float4 *src,
-                                                size_t spitch, const FT *filt) {
+                                                unsigned spitch, const FT *filt) {
    /* src: the accumulator value under the pixel's first tap, rows spitch apart (the
     * accumulator itself, or the CTA's tile of it in shared memory); filt: the filter */
    const int fw = P.filter_width;
@@ -548,7 +550,7 @@ __device__ __forceinline__ bool f3b_final_pixel(const F3FinalParams &P, int i, i
    for (int ii = 0; ii < fw; ii++) {
       for (int jj = 0; jj < fw; jj++) {
          const T k = (T)filt[ii + jj * fw];
-         const float4 a = src[(size_t)ii + (size_t)jj * spitch];
+         const float4 a = src[(unsigned)ii + (unsigned)jj * spitch];
          t[0] += k * (T)a.x;
          t[1] += k * (T)a.y;
          t[2] += k * (T)a.z;
@@ -620,7 +622,7 @@ __global__ void __launch_bounds__(256) f3b_final_kernel(const F3FinalParams P, i
    const int j = P.out_row_begin + blockIdx.y * blockDim.y + threadIdx.y; /* output row */
    const bool inside = i < P.image_width && j < P.out_row_end;
    if (!P.fixup_list) { /* 16 bit output, or the filter switched off: all in double */
-      if (inside) f3b_final_pixel<double, double>(P, i, j, f3b_final_origin(P, i, j), (size_t)P.width, P.filter);
+      if (inside) f3b_final_pixel<double, double>(P, i, j, f3b_final_origin(P, i, j), (unsigned)P.width, P.filter);
       return;
    }
    float *s_filt = reinterpret_cast<float *>(fin_smem);
@@ -645,7 +647,7 @@ __global__ void __launch_bounds__(256) f3b_final_kernel(const F3FinalParams P, i
    if (inside) {
       const float4 *src = tile_w ? s_tile + (size_t)threadIdx.x * P.oversample + (size_t)threadIdx.y * P.oversample * tile_w
                                  : f3b_final_origin(P, i, j);
-      unsure = f3b_final_pixel<float, float>(P, i, j, src, tile_w ? (size_t)tile_w : (size_t)P.width, s_filt);
+      unsure = f3b_final_pixel<float, float>(P, i, j, src, tile_w ? (unsigned)tile_w : (unsigned)P.width, s_filt);
    }
    /* one global atomic per CTA, not per pixel: 10^5 atomics on one address cost more than the pass */
    unsigned int slot = 0;
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(128) f3b_final_fixup_kernel(const F3FinalParam
    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
       const uint32_t e = P.fixup_list[k];
       const int i = (int)(e & 0xffffu), j = (int)(e >> 16);
-      f3b_final_pixel<double, double>(P, i, j, f3b_final_origin(P, i, j), (size_t)P.width, P.filter);
+      f3b_final_pixel<double, double>(P, i, j, f3b_final_origin(P, i, j), (unsigned)P.width, P.filter);
    }
 }
 

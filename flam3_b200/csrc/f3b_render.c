@@ -745,8 +745,7 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
          f3b_job *jb = &jobs[ts];
          jb->blob_offset = (uint64_t)blob_word_offset * 4;
          jb->n_iters = batch_size > 0 ? (uint64_t)batch_size : 0;
-         jb->n_chains = f3b_plan_chains(ctx, jb->n_iters, max_chain, (uint32_t)ntemporal_samples,
-                                        (uint32_t)nthreads);
+         jb->n_chains = 0; /* planned by f3b_iterate, which knows the kernel class of the batch */
          jb->fuse = spec->earlyclip ? 100 : 15; /* FUSE_28 : FUSE_27, rect.c:39-40,266 */
          jb->first_group = 0;
          jb->sample_id = (uint32_t)(h ^ (h >> 32));
@@ -809,7 +808,8 @@ static int render_locked(f3b_ctx *ctx, flam3_frame *spec, void *out, int field, 
                /* the plan is the same for every call: only first_group is filled in */
                for (int ts = 0; ts < ntemporal_samples; ts++) jobs[ts].first_group = 0;
                if (f3b_iterate(lc[i], blobs.words, blobs.used * 4, jobs, ntemporal_samples, seed,
-                               spec->bits != 64, max_chain, rank0 + i + sl * NR, NR * nslices)) {
+                               spec->bits != 64, max_chain, (uint32_t)nthreads, rank0 + i + sl * NR,
+                               NR * nslices)) {
                   ctx = lc[i];
                   goto gpu_error;
                }

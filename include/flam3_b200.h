@@ -84,10 +84,14 @@ uint32_t f3b_plan_chains(f3b_ctx *ctx, uint64_t n_iters, uint32_t max_chain_len,
                          uint32_t workers);
 
 /* Runs the jobs' chains with chain-group index g where g % nranks == rank and adds the
- * hits into this context's histogram. floor_adds=1 reproduces the integer bucket
- * semantics of bits 32/33 (flam3.c:3838-3854). seed selects the random streams. */
+ * hits into this context's buckets. floor_adds=1 truncates every add like the integer buckets
+ * of bits 32/33 (flam3.c:3838-3854). seed selects the random streams. Jobs with n_chains == 0
+ * are planned here, like f3b_plan_chains but rounding to the threads the kernel class that
+ * runs the batch keeps resident (3 CTAs per SM for the classic-flame kernels, 2 for the
+ * generic ones); `workers` = flam3_frame.nthreads. */
 int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *jobs, int n_jobs,
-                uint64_t seed, int floor_adds, uint32_t max_chain_len, int rank, int nranks);
+                uint64_t seed, int floor_adds, uint32_t max_chain_len, uint32_t workers, int rank,
+                int nranks);
 /* One application of xform `xform_index` of a packed sample to n caller-supplied points
  * (apply_xform, variations.c:2129-2399): in = {x, y, color} per point, out = {x, y, color,
  * vis_adjusted, bad} per point. For testing the variation maths in isolation. */

@@ -48,3 +48,44 @@ def test_random_genome_matches_the_reference(path):
     # noise-free images (ref-vs-ref > 52 dB) must agree to 50 dB (mean error < 1 level)
     assert got >= min(noise - 2.0, 50.0), "gpu-vs-ref %.2f dB, ref-vs-ref %.2f dB" % (got, noise)
     assert abs(g.mean() - a.mean()) <= max(1.0, 0.04 * a.mean()), (g.mean(), a.mean())
+
+
+@pytest.mark.parametrize("name", ["mix101", "mix123", "mix107"])
+def test_warp_uniform_xform_step_keeps_the_statistics(name):
+    """Random genomes whose xforms run different variation code are rendered with the
+    warp-uniform xform step (all 32 walkers of a warp apply the same xform in an iteration, the
+    CTA's walkers change hands every 4 iterations; f3b_iterate.cu) - 1.6-5.4x faster. It only
+    engages for frames with >= 57 000 chains, so it is checked here at the configuration's own
+    size and quality (1024x1024 q1000): the image must differ from a per-lane render with
+    ANOTHER seed by no more than two per-lane renders differ from each other (Monte-Carlo noise
+    at 1e9 iterations is ~45 dB, so a bias of a fraction of a grey level would show)."""
+    import glob
+    import os
+    _, gpu, core = libs()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = sorted(glob.glob(os.path.join(root, "tests", "golden", "c5", "*%s.flam3" % name)))
+    from flam3_b200.genome_xml import resize
+    gg = gpu.parse(resize(open(p[0]).read(), 1024, 1024, quality=1000, temporal_samples=1))
+    ctx = gpu.render_context(core)
+
+    def render(wu, seed):
+        os.environ["F3B_WU"] = wu
+        try:
+            ctx.stats_reset()
+            img, st, _ = gpu.render(gg, isaac_seed=seed)
+            assert st["rv"] == 0
+            return img, ctx.stage_stats(0)[0]
+        finally:
+            os.environ.pop("F3B_WU", None)
+
+    off1, _ = render("0", "one")
+    off2, t_off = render("0", "two")
+    on1, _ = render("1", "one")
+    on1b, t_on = render("1", "one")
+    assert np.array_equal(on1, on1b)             # still deterministic per seed
+    assert not np.array_equal(on1, off1)         # and really a different walk
+    noise = psnr(off1, off2)
+    got = min(psnr(on1, off2), psnr(on1, off1))
+    assert got >= noise - 1.0, "%s: warp-uniform vs per-lane %.2f dB, per-lane vs per-lane %.2f dB" % (name, got, noise)
+    assert abs(on1.mean() - off1.mean()) <= 0.01 * off1.mean() + 0.05
+    assert t_on < t_off                          # the point of it
