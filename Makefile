@@ -49,11 +49,12 @@ REF_CFLAGS = -g -O3 -std=gnu99 -ffast-math -fPIC -w -I$(SHIMS) -I$(F3_REF) \
              -DPACKAGE_DATA_DIR='"$(F3_REF)"' -DGIT_REV='""'
 HOST_SRCS  = variations.c filters.c isaac.c interpolation.c palettes.c parser.c
 HOST_OBJS  = $(addprefix $(DROP)/host_,$(HOST_SRCS:.c=.o))
-GLUE_OBJS  = $(DROP)/f3b_render.o $(DROP)/f3b_pack.o $(DROP)/f3b_isaac.o $(DROP)/f3b_debug.o $(DROP)/f3b_analysis.o
+GLUE_OBJS  = $(DROP)/f3b_render.o $(DROP)/f3b_pack.o $(DROP)/f3b_isaac.o $(DROP)/f3b_debug.o $(DROP)/f3b_analysis.o \
+             $(DROP)/f3b_frontend.o
 MISC_OBJS  = $(DROP)/xmlshim.o $(DROP)/imgshim.o
 CLIS       = $(DROP)/flam3-render $(DROP)/flam3-animate $(DROP)/flam3-genome
 
-dropin: lib $(DROP)/libflam3.so $(CLIS) $(DROP)/libf3harness.so
+dropin: lib $(DROP)/libflam3.so $(CLIS) $(DROP)/libf3harness.so $(DROP)/f3b-render
 
 $(DROP):
 	mkdir -p $(DROP)
@@ -87,6 +88,14 @@ $(DROP)/libf3harness.so: $(DROP)/harness.o $(DROP)/libflam3.so
 
 $(DROP)/libflam3.so: $(HOST_OBJS) $(DROP)/host_flam3.o $(GLUE_OBJS) $(MISC_OBJS) $(LIBDIR)/libflam3_b200.so
 	$(CC) -shared -Wl,-Bsymbolic -o $@ $(HOST_OBJS) $(DROP)/host_flam3.o $(GLUE_OBJS) $(MISC_OBJS) \
+	   -L$(LIBDIR) -lflam3_b200 -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' -lm -lpthread -lz
+
+# a renderer made of this repository's code only: own front end, the
+# flam3_render drop-in, libflam3_b200.so - NO reference object (flam3.h is the public header)
+STANDALONE_OBJS = $(DROP)/f3b_frontend.o $(DROP)/f3b_standalone.o $(DROP)/f3b_render.o $(DROP)/f3b_pack.o \
+                  $(DROP)/f3b_isaac.o $(DROP)/xmlshim.o $(DROP)/imgshim.o
+$(DROP)/f3b-render: tools/f3b-render.c $(STANDALONE_OBJS) $(LIBDIR)/libflam3_b200.so
+	$(CC) -O2 -std=gnu99 -Wall -I$(SHIMS) -I$(F3_REF) -o $@ $< $(STANDALONE_OBJS) \
 	   -L$(LIBDIR) -lflam3_b200 -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' -lm -lpthread -lz
 
 # the reference's own command-line programs, unmodified, linked against the drop-in

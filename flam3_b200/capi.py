@@ -255,6 +255,19 @@ class Flam3Lib:
             raise ValueError("flam3_parse_xml2 found no genomes")
         return Genomes(self, p, n.value)
 
+    def parse_own(self, xml):
+        """Parse with the repository's own front end (f3b_parse_flam3; drop-in library only)."""
+        if isinstance(xml, str):
+            xml = xml.encode()
+        f = self._dll.h_parse_own
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+        n = C.c_int(0)
+        p = f(xml, C.byref(n))
+        if not p or n.value <= 0:
+            raise ValueError("f3b_parse_flam3 found no genomes")
+        return Genomes(self, p, n.value)
+
     def abi_sizes(self):
         out = (C.c_int * 4)()
         self._dll.h_abi_sizes(out)

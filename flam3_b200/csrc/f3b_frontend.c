@@ -1,0 +1,1007 @@
+/*
+ * f3b_frontend.c — a self-contained front end for the render path:
+ * reads .flam3 genome files and the palette library and writes images WITHOUT the reference's
+ * parser.c / palettes.c / png.c, so that a program can render flames with nothing but this
+ * repository's code (tools/f3b-render.c does).
+ *
+ *   f3b_parse_flam3        flam3_parse_xml2 + scan_for_flame_nodes + parse_flame_element +
+ *                          parse_xform_xml, parser.c:220-1257
+ *   f3b_get_palette        flam3_get_palette, palettes.c:25-195 (flam3-palettes.xml)
+ *   f3b_genome_*           clear_cp flam3.c:1270, flam3_add_xforms flam3.c:1033 with
+ *                          initialize_xforms variations.c:2401, flam3_copy flam3.c:1171
+ *   f3b_write_ppm          the "ppm" branch of flam3-render.c:384-390
+ *
+ * It fills the reference's own `flam3_genome` (flam3.h is the public header every libflam3
+ * client includes), so the genomes go straight into flam3_render. Written table-driven: one
+ * table of <flame> attributes, one of <xform> parameters (attribute name = field of
+ * `flam3_xform`), one of variation names. The XML reader underneath is shims/libxml/xmlshim.c
+ * (this repository's mini-DOM behind the libxml2 entry points the reference uses; a real
+ * libxml2 works the same).
+ *
+ * Deliberately NOT read (an error says so instead of guessing): <symmetry kind="0"> (a random
+ * symmetry), motion elements, the pre-2008 two-palette <palette index0= ...> blend, <edit> history (skipped
+ * silently: it does not affect rendering). Parity: for every fixture genome the reference's
+ * own printer (flam3_print_to_string) gives the same text for the genome parsed here as for
+ * the one parsed by the reference (tests/test_cpu_frontend.py).
+ */
+#include <ctype.h>
+#include <errno.h>
+#include <math.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "flam3.h"
+
+#include "../../include/flam3_b200_frontend.h"
+
+/* ---- tables --------------------------------------------------------------------------- */
+static const char *const k_variation_names[flam3_nvariations] = {
+   "linear", "sinusoidal", "spherical", "swirl", "horseshoe", "polar", "handkerchief", "heart",
+   "disc", "spiral", "hyperbolic", "diamond", "ex", "julia", "bent", "waves", "fisheye", "popcorn",
+   "exponential", "power", "cosine", "rings", "fan", "blob", "pdj", "fan2", "rings2", "eyefish",
+   "bubble", "cylinder", "perspective", "noise", "julian", "juliascope", "blur", "gaussian_blur",
+   "radial_blur", "pie", "ngon", "curl", "rectangles", "arch", "tangent", "square", "rays", "blade",
+   "secant2", "twintrian", "cross", "disc2", "super_shape", "flower", "conic", "parabola", "bent2",
+   "bipolar", "boarders", "butterfly", "cell", "cpow", "curve", "edisc", "elliptic", "escher", "foci",
+   "lazysusan", "loonie", "pre_blur", "modulus", "oscilloscope", "polar2", "popcorn2", "scry",
+   "separation", "split", "splits", "stripes", "wedge", "wedge_julia", "wedge_sph", "whorl", "waves2",
+   "exp", "log", "sin", "cos", "tan", "sec", "csc", "cot", "sinh", "cosh", "tanh", "sech", "csch",
+   "coth", "auger", "flux", "mobius"};
+
+/* variation parameters: XML attribute = field name; value of a fresh xform (variations.c:2401) */
+#define XP(field, dflt) {#field, offsetof(flam3_xform, field), dflt}
+static const struct {
+   const char *name;
+   size_t off;
+   double dflt;
+} k_xform_params[] = {
+   XP(blob_low, 0), XP(blob_high, 1), XP(blob_waves, 1), XP(pdj_a, 0), XP(pdj_b, 0), XP(pdj_c, 0), XP(pdj_d, 0),
+   XP(fan2_x, 0), XP(fan2_y, 0), XP(rings2_val, 0), XP(perspective_angle, 0), XP(perspective_dist, 0),
+   XP(julian_power, 1), XP(julian_dist, 1), XP(juliascope_power, 1), XP(juliascope_dist, 1),
+   XP(radial_blur_angle, 0), XP(pie_slices, 6), XP(pie_rotation, 0), XP(pie_thickness, 0.5),
+   XP(ngon_sides, 5), XP(ngon_power, 3), XP(ngon_circle, 1), XP(ngon_corners, 2), XP(curl_c1, 1), XP(curl_c2, 0),
+   XP(rectangles_x, 1), XP(rectangles_y, 1), XP(amw_amp, 1), XP(disc2_rot, 0), XP(disc2_twist, 0),
+   XP(super_shape_rnd, 0), XP(super_shape_m, 0), XP(super_shape_n1, 1), XP(super_shape_n2, 1),
+   XP(super_shape_n3, 1), XP(super_shape_holes, 0), XP(flower_petals, 0), XP(flower_holes, 0),
+   XP(conic_eccentricity, 1), XP(conic_holes, 0), XP(parabola_height, 0), XP(parabola_width, 0),
+   XP(bent2_x, 1), XP(bent2_y, 1), XP(bipolar_shift, 0), XP(cell_size, 1), XP(cpow_r, 1), XP(cpow_i, 0),
+   XP(cpow_power, 1), XP(curve_xamp, 0), XP(curve_yamp, 0), XP(curve_xlength, 1), XP(curve_ylength, 1),
+   XP(escher_beta, 0), XP(lazysusan_space, 0), XP(lazysusan_twist, 0), XP(lazysusan_spin, 0),
+   XP(lazysusan_x, 0), XP(lazysusan_y, 0), XP(modulus_x, 0), XP(modulus_y, 0), XP(oscope_separation, 1),
+   XP(oscope_frequency, M_PI), XP(oscope_amplitude, 1), XP(oscope_damping, 0), XP(popcorn2_x, 0),
+   XP(popcorn2_y, 0), XP(popcorn2_c, 0), XP(separation_x, 0), XP(separation_xinside, 0), XP(separation_y, 0),
+   XP(separation_yinside, 0), XP(split_xsize, 0), XP(split_ysize, 0), XP(splits_x, 0), XP(splits_y, 0),
+   XP(stripes_space, 0), XP(stripes_warp, 0), XP(wedge_angle, 0), XP(wedge_hole, 0), XP(wedge_count, 1),
+   XP(wedge_swirl, 0), XP(wedge_julia_angle, 0), XP(wedge_julia_count, 1), XP(wedge_julia_power, 1),
+   XP(wedge_julia_dist, 0), XP(wedge_sph_angle, 0), XP(wedge_sph_hole, 0), XP(wedge_sph_count, 1),
+   XP(wedge_sph_swirl, 0), XP(whorl_inside, 0), XP(whorl_outside, 0), XP(waves2_scalex, 0),
+   XP(waves2_scaley, 0), XP(waves2_freqx, 0), XP(waves2_freqy, 0), XP(auger_freq, 1), XP(auger_weight, 0.5),
+   XP(auger_sym, 0), XP(auger_scale, 1), XP(flux_spread, 0), XP(mobius_re_a, 0), XP(mobius_re_b, 0),
+   XP(mobius_re_c, 0), XP(mobius_re_d, 0), XP(mobius_im_a, 0), XP(mobius_im_b, 0), XP(mobius_im_c, 0),
+   XP(mobius_im_d, 0),
+};
+/* other spellings some writers use (parser.c:1141-1156, 1229-1243) */
+static const struct {
+   const char *alias, *name;
+} k_xform_aliases[] = {
+   {"oscilloscope_separation", "oscope_separation"}, {"oscilloscope_frequency", "oscope_frequency"},
+   {"oscilloscope_amplitude", "oscope_amplitude"},   {"oscilloscope_damping", "oscope_damping"},
+   {"Re_A", "mobius_re_a"}, {"Re_B", "mobius_re_b"}, {"Re_C", "mobius_re_c"}, {"Re_D", "mobius_re_d"},
+   {"Im_A", "mobius_im_a"}, {"Im_B", "mobius_im_b"}, {"Im_C", "mobius_im_c"}, {"Im_D", "mobius_im_d"},
+};
+/* derived constants of a fresh xform that the precalc step overwrites anyway */
+static void xform_derived_defaults(flam3_xform *x) {
+   x->julian_rN = 1.0;
+   x->julian_cn = 0.5;
+   x->juliascope_rN = 1.0;
+   x->juliascope_cn = 0.5;
+   x->radialBlur_zoomvar = 1.0;
+   x->wedgeJulia_cn = 0.5;
+   x->wedgeJulia_rN = 1.0;
+}
+
+/* <flame> attributes that are one number: name, kind (d double, i int), field */
+#define GA(attr, kind, field) {attr, kind, offsetof(flam3_genome, field)}
+static const struct {
+   const char *name;
+   char kind;
+   size_t off;
+} k_flame_numbers[] = {
+   GA("time", 'd', time), GA("hsv_rgb_palette_blend", 'd', hsv_rgb_palette_blend), GA("palette", 'i', palette_index),
+   GA("scale", 'd', pixels_per_unit), GA("rotate", 'd', rotate), GA("zoom", 'd', zoom),
+   GA("oversample", 'i', spatial_oversample), GA("supersample", 'i', spatial_oversample),
+   GA("filter", 'd', spatial_filter_radius), GA("temporal_filter_width", 'd', temporal_filter_width),
+   GA("temporal_filter_exp", 'd', temporal_filter_exp), GA("quality", 'd', sample_density),
+   GA("passes", 'i', nbatches), GA("temporal_samples", 'i', ntemporal_samples), GA("brightness", 'd', brightness),
+   GA("gamma", 'd', gamma), GA("vibrancy", 'd', vibrancy), GA("estimator_radius", 'd', estimator),
+   GA("estimator_minimum", 'd', estimator_minimum), GA("estimator_curve", 'd', estimator_curve),
+   GA("gamma_threshold", 'd', gam_lin_thresh),
+};
+/* <flame> attributes that are one word of a fixed set */
+typedef struct {
+   const char *word;
+   int value;
+} f3b_word;
+static const f3b_word k_filter_shapes[] = {
+   {"gaussian", flam3_gaussian_kernel}, {"hermite", flam3_hermite_kernel}, {"box", flam3_box_kernel},
+   {"triangle", flam3_triangle_kernel}, {"bell", flam3_bell_kernel}, {"bspline", flam3_b_spline_kernel},
+   {"mitchell", flam3_mitchell_kernel}, {"blackman", flam3_blackman_kernel}, {"catrom", flam3_catrom_kernel},
+   {"hanning", flam3_hanning_kernel}, {"hamming", flam3_hamming_kernel}, {"lanczos3", flam3_lanczos3_kernel},
+   {"lanczos2", flam3_lanczos2_kernel}, {"quadratic", flam3_quadratic_kernel}, {NULL, 0}};
+static const f3b_word k_interpolation[] = {{"linear", flam3_interpolation_linear}, {"smooth", flam3_interpolation_smooth}, {NULL, 0}};
+static const f3b_word k_palette_interp[] = {{"hsv", flam3_palette_interpolation_hsv}, {"sweep", flam3_palette_interpolation_sweep},
+                                            {"hsv_circular", flam3_palette_interpolation_hsv_circular},
+                                            {"rgb", flam3_palette_interpolation_rgb}, {NULL, 0}};
+static const f3b_word k_interp_type[] = {{"linear", flam3_inttype_linear}, {"log", flam3_inttype_log},
+                                         {"old", flam3_inttype_compat}, {"older", flam3_inttype_older}, {NULL, 0}};
+static const f3b_word k_temporal[] = {{"box", flam3_temporal_box}, {"gaussian", flam3_temporal_gaussian},
+                                      {"exp", flam3_temporal_exp}, {NULL, 0}};
+static const f3b_word k_palette_mode[] = {{"step", flam3_palette_mode_step}, {"linear", flam3_palette_mode_linear}, {NULL, 0}};
+static const struct {
+   const char *name;
+   const f3b_word *words;
+   size_t off;
+   const char *what;
+} k_flame_words[] = {
+   {"filter_shape", k_filter_shapes, offsetof(flam3_genome, spatial_filter_select), "kernel shape"},
+   {"interpolation", k_interpolation, offsetof(flam3_genome, interpolation), "interpolation type"},
+   {"palette_interpolation", k_palette_interp, offsetof(flam3_genome, palette_interpolation), "palette interpolation type"},
+   {"interpolation_space", k_interp_type, offsetof(flam3_genome, interpolation_type), "interpolation_type"},
+   {"interpolation_type", k_interp_type, offsetof(flam3_genome, interpolation_type), "interpolation_type"},
+   {"temporal_filter_type", k_temporal, offsetof(flam3_genome, temporal_filter_type), "temporal filter"},
+   {"palette_mode", k_palette_mode, offsetof(flam3_genome, palette_mode), "palette mode"},
+};
+
+/* ---- numbers (flam3_atof / flam3_atoi, parser.c:26-72: the whole string must convert) ---- */
+static int g_bad_number;
+static double to_double(const char *s) {
+   char *end;
+   errno = 0;
+   const double v = strtod(s, &end);
+   if (end != s + strlen(s) || errno) {
+      g_bad_number = 1;
+      fprintf(stderr, "f3b_parse_flam3: cannot convert '%s' to a number\n", s);
+   }
+   return v;
+}
+static int to_int(const char *s) {
+   char *end;
+   errno = 0;
+   const long v = strtol(s, &end, 10);
+   if (end != s + strlen(s) || errno) {
+      g_bad_number = 1;
+      fprintf(stderr, "f3b_parse_flam3: cannot convert '%s' to an integer\n", s);
+   }
+   return (int)v;
+}
+/* exactly n numbers and nothing else */
+static int to_doubles(const char *s, double *out, int n) {
+   const char *p = s;
+   for (int i = 0; i < n; i++) {
+      char *end;
+      errno = 0;
+      out[i] = strtod(p, &end);
+      if (errno || end == p) return 1;
+      p = end;
+   }
+   while (isspace((unsigned char)*p)) p++;
+   return *p != 0;
+}
+
+/* ---- genome housekeeping ------------------------------------------------------------------ */
+void f3b_genome_init(flam3_genome *cp, int defaults_on) {
+   /* clear_cp (flam3.c:1270-1370): the values a genome starts from */
+   f3b_genome_free_xforms(cp);
+   cp->palette_index = flam3_palette_random;
+   cp->center[0] = cp->center[1] = cp->rot_center[0] = cp->rot_center[1] = 0.0;
+   cp->gamma = 4.0;
+   cp->vibrancy = 1.0;
+   cp->contrast = 1.0;
+   cp->brightness = 4.0;
+   cp->symmetry = 0;
+   cp->hue_rotation = 0.0;
+   cp->rotate = 0.0;
+   cp->pixels_per_unit = 50;
+   cp->interpolation = flam3_interpolation_linear;
+   cp->palette_interpolation = flam3_palette_interpolation_hsv_circular;
+   cp->hsv_rgb_palette_blend = 0.0;
+   cp->genome_index = 0;
+   memset(cp->parent_fname, 0, flam3_parent_fn_len);
+   cp->highlight_power = -1.0;
+   if (defaults_on) {
+      cp->background[0] = cp->background[1] = cp->background[2] = 0.0;
+      cp->width = cp->height = 100;
+      cp->spatial_oversample = 1;
+      cp->spatial_filter_radius = 0.5;
+      cp->zoom = 0.0;
+      cp->sample_density = 1;
+      cp->estimator = 9.0;
+      cp->estimator_minimum = 0.0;
+      cp->estimator_curve = 0.4;
+      cp->gam_lin_thresh = 0.01;
+      cp->nbatches = 1;
+      cp->ntemporal_samples = 1000;
+      cp->spatial_filter_select = flam3_gaussian_kernel;
+      cp->interpolation_type = flam3_inttype_log;
+      cp->temporal_filter_type = flam3_temporal_box;
+      cp->temporal_filter_width = 1.0;
+      cp->temporal_filter_exp = 0.0;
+      cp->palette_mode = flam3_palette_mode_step;
+   } else {
+      cp->background[0] = cp->background[1] = cp->background[2] = -1.0;
+      cp->zoom = 999999999;
+      cp->spatial_oversample = -1;
+      cp->spatial_filter_radius = -1;
+      cp->width = cp->height = -1;
+      cp->sample_density = -1;
+      cp->estimator = cp->estimator_minimum = cp->estimator_curve = cp->gam_lin_thresh = -1;
+      cp->nbatches = 0;
+      cp->ntemporal_samples = 0;
+      cp->spatial_filter_select = -1;
+      cp->interpolation_type = -1;
+      cp->temporal_filter_type = -1;
+      cp->temporal_filter_width = -1;
+      cp->temporal_filter_exp = -999;
+      cp->palette_mode = -1;
+   }
+   cp->final_xform_enable = 0;
+   cp->final_xform_index = -1;
+}
+
+void f3b_genome_free_xforms(flam3_genome *cp) {
+   if (cp->xform && cp->num_xforms > 0) {
+      const int nstd = cp->num_xforms - (cp->final_xform_index >= 0);
+      if (cp->chaos) {
+         for (int i = 0; i < nstd; i++) free(cp->chaos[i]);
+         free(cp->chaos);
+      }
+      for (int i = 0; i < cp->num_xforms; i++)
+         if (cp->xform[i].num_motion > 0) free(cp->xform[i].motion);
+      free(cp->xform);
+   }
+   cp->xform = NULL;
+   cp->chaos = NULL;
+   cp->num_xforms = 0;
+   cp->final_xform_index = -1;
+}
+
+static void xform_defaults(flam3_xform *x, int position) {
+   memset(x, 0, sizeof(*x));
+   x->color_speed = 0.5;
+   x->animate = 1.0;
+   x->color = position & 1;
+   x->opacity = 1.0;
+   x->var[0] = 1.0;
+   x->c[0][0] = x->c[1][1] = 1.0;
+   x->post[0][0] = x->post[1][1] = 1.0;
+   for (size_t i = 0; i < sizeof(k_xform_params) / sizeof(k_xform_params[0]); i++)
+      *(double *)((char *)x + k_xform_params[i].off) = k_xform_params[i].dflt;
+   xform_derived_defaults(x);
+}
+
+/* one more xform: a standard one goes in front of the final xform (which stays last) and
+ * widens the chaos matrix with ones; the final xform has no row or column in it */
+int f3b_genome_add_xform(flam3_genome *cp, int is_final) {
+   const int had_final = cp->final_xform_index >= 0;
+   if (is_final && had_final) return -1;
+   const int old_std = cp->num_xforms - had_final;
+   flam3_xform *nx = (flam3_xform *)realloc(cp->xform, (size_t)(cp->num_xforms + 1) * sizeof(flam3_xform));
+   if (!nx) return -1;
+   cp->xform = nx;
+   int at = cp->num_xforms;
+   if (!is_final && had_final) { /* keep the final xform at the end */
+      cp->xform[cp->num_xforms] = cp->xform[cp->final_xform_index];
+      at = cp->final_xform_index;
+      cp->final_xform_index = cp->num_xforms;
+   }
+   cp->num_xforms++;
+   xform_defaults(&cp->xform[at], at);
+   if (is_final) {
+      cp->final_xform_enable = 1;
+      cp->final_xform_index = at;
+      return at;
+   }
+   const int nstd = old_std + 1;
+   double **rows = (double **)realloc(cp->chaos, (size_t)nstd * sizeof(double *));
+   if (!rows) return -1;
+   cp->chaos = rows;
+   cp->chaos[old_std] = NULL;
+   for (int i = 0; i < nstd; i++) {
+      double *r = (double *)realloc(cp->chaos[i], (size_t)nstd * sizeof(double));
+      if (!r) return -1;
+      cp->chaos[i] = r;
+      for (int j = (i < old_std ? old_std : 0); j < nstd; j++) r[j] = 1.0;
+   }
+   return at;
+}
+
+int f3b_genome_copy(flam3_genome *dest, const flam3_genome *src) {
+   f3b_genome_free_xforms(dest);
+   memcpy(dest, src, sizeof(*dest));
+   dest->xform = NULL;
+   dest->chaos = NULL;
+   dest->num_xforms = 0;
+   dest->final_xform_index = -1;
+   const int nstd = src->num_xforms - (src->final_xform_index >= 0);
+   for (int i = 0; i < src->num_xforms; i++) {
+      const int is_final = (i == src->final_xform_index);
+      const int at = f3b_genome_add_xform(dest, is_final);
+      if (at < 0) return 1;
+      dest->xform[at] = src->xform[i];
+      dest->xform[at].motion = NULL;
+      dest->xform[at].num_motion = 0;
+      if (src->xform[i].num_motion > 0) {
+         const size_t bytes = (size_t)src->xform[i].num_motion * sizeof(flam3_xform);
+         dest->xform[at].motion = (struct xform *)malloc(bytes);
+         if (!dest->xform[at].motion) return 1;
+         memcpy(dest->xform[at].motion, src->xform[i].motion, bytes);
+         dest->xform[at].num_motion = src->xform[i].num_motion;
+      }
+   }
+   dest->final_xform_enable = src->final_xform_enable;
+   for (int i = 0; i < nstd; i++) memcpy(dest->chaos[i], src->chaos[i], (size_t)nstd * sizeof(double));
+   return 0;
+}
+
+/* ---- <symmetry kind="n"/> (flam3_add_symmetry, flam3.c:2558-2641) ----------------------- */
+/* n >= 2: n-1 rotations by multiples of 2 pi / n; n <= -1: a reflection first, then the
+ * rotations of |n|. The added xforms have weight 1, colour speed 0, do not animate, and are
+ * put in order of their determinant (all colour speeds are 0; interpolation.c:117-147) by a
+ * stable sort - over the LAST `added` entries of the xform array, as the reference does. */
+static double round_6(double x) {
+   x *= 1e6;
+   if (x < 0) x -= 1.0;
+   return 1e-6 * (int)(x + 0.5);
+}
+static int symmetry_order(const flam3_xform *a, const flam3_xform *b) {
+   double ad = a->c[0][0] * a->c[1][1] - a->c[0][1] * a->c[1][0];
+   double bd = b->c[0][0] * b->c[1][1] - b->c[0][1] * b->c[1][0];
+   if (a->color_speed > b->color_speed) return 1;
+   if (a->color_speed < b->color_speed) return -1;
+   if (a->color_speed) {
+      if (ad < 0) return -1;
+      if (bd < 0) return 1;
+      ad = atan2(a->c[0][0], a->c[0][1]);
+      bd = atan2(b->c[0][0], b->c[0][1]);
+   }
+   return ad < bd ? -1 : (ad > bd ? 1 : 0);
+}
+static int add_symmetry(flam3_genome *cp, int kind) {
+   if (kind == 0) {
+      fprintf(stderr, "f3b_parse_flam3: <symmetry kind=\"0\"/> (a random symmetry) is not supported by this front end\n");
+      return -1;
+   }
+   if (kind == 1) return 0;
+   cp->symmetry = kind;
+   int added = 0;
+   for (int pass = (kind < 0 ? 0 : 1), n = kind < 0 ? -kind : kind, k = 1; pass < 2 || k < n;) {
+      const int at = f3b_genome_add_xform(cp, 0);
+      if (at < 0) return -1;
+      flam3_xform *x = &cp->xform[at];
+      x->density = 1.0;
+      x->color_speed = 0.0;
+      x->animate = 0.0;
+      memset(x->var, 0, sizeof(x->var));
+      x->var[0] = 1.0;
+      if (pass == 0) { /* the reflection of a negative kind */
+         x->color = 1.0;
+         x->c[0][0] = -1.0;
+         x->c[0][1] = x->c[1][0] = 0.0;
+         x->c[1][1] = 1.0;
+         pass = 2;
+      } else {
+         pass = 2;
+         const double a = 2 * M_PI / n;
+         x->color = n < 3 ? 0.0 : (k - 1.0) / (n - 2.0);
+         x->c[0][0] = round_6(cos(k * a));
+         x->c[0][1] = round_6(sin(k * a));
+         x->c[1][0] = round_6(-x->c[0][1]);
+         x->c[1][1] = x->c[0][0];
+         k++;
+      }
+      x->c[2][0] = x->c[2][1] = 0.0;
+      added++;
+   }
+   /* stable insertion sort of the last `added` entries */
+   flam3_xform *base = cp->xform + (cp->num_xforms - added);
+   for (int i = 1; i < added; i++) {
+      flam3_xform key = base[i];
+      int j = i - 1;
+      while (j >= 0 && symmetry_order(&base[j], &key) > 0) {
+         base[j + 1] = base[j];
+         j--;
+      }
+      base[j + 1] = key;
+   }
+   return added;
+}
+
+/* ---- colours ---------------------------------------------------------------------------- */
+/* `count` colours of 2 hex digits per channel (parser.c:83-133): chan 3 = RRGGBB, 4 = RRGGBBAA,
+ * -4 = 00RRGGBB; whitespace between colours */
+static int hex_colors(const char *s, flam3_genome *cp, int count, int chan) {
+   const int digits = 2 * (chan < 0 ? -chan : chan);
+   size_t at = 0;
+   while (isspace((unsigned char)s[at])) at++;
+   int n = 0;
+   do {
+      unsigned v[4] = {0, 0, 0, 255};
+      const int lead = chan == -4 ? 2 : 0, nch = chan == 4 ? 4 : 3;
+      if (lead && (s[at] != '0' || s[at + 1] != '0')) goto bad;
+      for (int c = 0; c < nch; c++) {
+         char two[3] = {s[at + lead + 2 * c], s[at + lead + 2 * c + 1], 0};
+         if (!isxdigit((unsigned char)two[0]) || !isxdigit((unsigned char)two[1])) goto bad;
+         v[c] = (unsigned)strtoul(two, NULL, 16);
+      }
+      at += (size_t)digits;
+      while (isspace((unsigned char)s[at])) at++;
+      if (n < 256) {
+         for (int c = 0; c < 4; c++) cp->palette[n].color[c] = v[c] / 255.0;
+         cp->palette[n].index = n;
+      }
+      n++;
+   } while (n < count);
+   if (s[at]) {
+      fprintf(stderr, "f3b_parse_flam3: extra data at the end of hex colour data '%.20s'\n", s + at);
+      return 1;
+   }
+   return 0;
+bad:
+   fprintf(stderr, "f3b_parse_flam3: problem reading hexadecimal colour data\n");
+   return 1;
+}
+
+/* palette entries that were not given are interpolated between their neighbours, wrapping
+ * around (parser.c:135-218) */
+static void fill_missing_colors(flam3_genome *cp) {
+   int first = -1, last = -1;
+   for (int i = 0; i < 256; i++)
+      if (cp->palette[i].index >= 0) {
+         if (first < 0) first = i;
+         last = i;
+      }
+   if (first < 0) {
+      for (int i = 0; i < 256; i++) cp->palette[i].index = i;
+      return;
+   }
+   for (int i = 0; i < 256;) {
+      if (cp->palette[i].index >= 0) {
+         i++;
+         continue;
+      }
+      int end = i;
+      while (end + 1 < 256 && cp->palette[end + 1].index < 0) end++;
+      /* neighbours of the gap [i, end]: positions for the weights, entries for the colours */
+      int lpos = i - 1, rpos = end + 1, lcol = lpos, rcol = rpos;
+      if (lpos < 0) {
+         lpos = last - 256;
+         lcol = last;
+      }
+      if (rpos > 255) {
+         rpos = first + 256;
+         rcol = first;
+      }
+      for (int j = i; j <= end; j++) {
+         const double t = (j - lpos) / (double)(rpos - lpos);
+         for (int k = 0; k < 4; k++)
+            cp->palette[j].color[k] = cp->palette[lcol].color[k] * (1.0 - t) + cp->palette[rcol].color[k] * t;
+         cp->palette[j].index = j;
+      }
+      i = end + 1;
+   }
+}
+
+/* hexcone model, h in [0,6) (palettes.c:199-272) */
+static void rgb_to_hsv(const double *rgb, double *hsv) {
+   const double r = rgb[0], g = rgb[1], b = rgb[2];
+   const double mx = fmax(r, fmax(g, b)), mn = fmin(r, fmin(g, b));
+   const double del = mx - mn;
+   const double s = mx != 0.0 ? del / mx : 0.0;
+   double h = 0.0;
+   if (s != 0.0) {
+      const double rc = (mx - r) / del, gc = (mx - g) / del, bc = (mx - b) / del;
+      if (r == mx) h = bc - gc;
+      else if (g == mx) h = 2 + rc - bc;
+      else if (b == mx) h = 4 + gc - rc;
+      if (h < 0) h += 6;
+   }
+   hsv[0] = h;
+   hsv[1] = s;
+   hsv[2] = mx;
+}
+static void hsv_to_rgb(const double *hsv, double *rgb) {
+   double h = hsv[0];
+   const double s = hsv[1], v = hsv[2];
+   while (h >= 6.0) h -= 6.0;
+   while (h < 0.0) h += 6.0;
+   const int j = (int)floor(h);
+   const double f = h - j, p = v * (1 - s), q = v * (1 - s * f), t = v * (1 - s * (1 - f));
+   const double tab[6][3] = {{v, t, p}, {q, v, p}, {p, v, t}, {p, q, v}, {t, p, v}, {v, p, q}};
+   memcpy(rgb, tab[j % 6], 3 * sizeof(double));
+}
+
+/* the palette library: <palette number="N" name="..." data="00RRGGBB x 256"/> */
+static struct {
+   int number;
+   unsigned char rgb[256][3];
+} *g_palettes;
+static int g_npalettes = -1; /* -1: not read yet */
+
+static void collect_palettes(xmlNode *n) {
+   for (; n; n = n->next) {
+      if (n->type == XML_ELEMENT_NODE && !xmlStrcmp(n->name, (const xmlChar *)"palette")) {
+         char *num = (char *)xmlGetProp(n, (const xmlChar *)"number");
+         char *data = (char *)xmlGetProp(n, (const xmlChar *)"data");
+         if (data) {
+            void *grown = realloc(g_palettes, (size_t)(g_npalettes + 1) * sizeof(*g_palettes));
+            if (grown) {
+               g_palettes = grown;
+               g_palettes[g_npalettes].number = num ? atoi(num) : 0;
+               size_t at = 0;
+               int ok = 1;
+               for (int c = 0; c < 256 && ok; c++) {
+                  unsigned r, g, b;
+                  if (sscanf(data + at, "00%2x%2x%2x", &r, &g, &b) != 3) ok = 0;
+                  at += 8;
+                  while (ok && isspace((unsigned char)data[at])) at++;
+                  g_palettes[g_npalettes].rgb[c][0] = (unsigned char)r;
+                  g_palettes[g_npalettes].rgb[c][1] = (unsigned char)g;
+                  g_palettes[g_npalettes].rgb[c][2] = (unsigned char)b;
+               }
+               if (ok) g_npalettes++;
+               else fprintf(stderr, "f3b_get_palette: problem reading hexadecimal colour data of palette %s\n", num ? num : "?");
+            }
+         }
+         if (num) xmlFree(num);
+         if (data) xmlFree(data);
+      } else
+         collect_palettes(n->children);
+   }
+}
+
+static char *read_file(const char *path) {
+   FILE *f = fopen(path, "rb");
+   if (!f) return NULL;
+   size_t cap = 1 << 16, n = 0;
+   char *s = (char *)malloc(cap);
+   for (size_t got; s && (got = fread(s + n, 1, cap - n - 1, f)) > 0;) {
+      n += got;
+      if (n + 1 >= cap) s = (char *)realloc(s, cap *= 2);
+   }
+   fclose(f);
+   if (s) s[n] = 0;
+   return s;
+}
+
+int f3b_get_palette(int number, flam3_palette pal, double hue_rotation) {
+   for (int i = 0; i < 256; i++) { /* all white in case of problems, like the reference */
+      pal[i].index = i;
+      for (int j = 0; j < 4; j++) pal[i].color[j] = 1.0;
+   }
+   if (g_npalettes < 0) {
+      const char *path = getenv("flam3_palettes");
+      if (!path) path = "flam3-palettes.xml";
+      char *text = read_file(path);
+      if (!text) {
+         fprintf(stderr, "f3b_get_palette: could not open palette file %s (set flam3_palettes)\n", path);
+         return -1;
+      }
+      xmlDocPtr doc = xmlReadMemory(text, (int)strlen(text), path, NULL, XML_PARSE_NONET);
+      free(text);
+      if (!doc) {
+         fprintf(stderr, "f3b_get_palette: error parsing %s\n", path);
+         return -1;
+      }
+      g_npalettes = 0;
+      collect_palettes(xmlDocGetRootElement(doc));
+      xmlFreeDoc(doc);
+   }
+   if (g_npalettes == 0) return -1;
+   if (number == flam3_palette_random) number = g_palettes[random() % g_npalettes].number;
+   for (int p = 0; p < g_npalettes; p++) {
+      if (g_palettes[p].number != number) continue;
+      for (int i = 0; i < 256; i++) {
+         double rgb[3], hsv[3];
+         for (int j = 0; j < 3; j++) rgb[j] = g_palettes[p].rgb[i][j] / 255.0;
+         rgb_to_hsv(rgb, hsv);
+         hsv[0] += hue_rotation * 6.0;
+         hsv_to_rgb(hsv, rgb);
+         for (int j = 0; j < 3; j++) pal[i].color[j] = rgb[j];
+         pal[i].color[3] = 1.0;
+      }
+      return number;
+   }
+   fprintf(stderr, "warning: palette number %d not found, using white.\n", number);
+   return -1;
+}
+
+/* ---- <xform> / <finalxform> ------------------------------------------------------------- */
+typedef struct {
+   int from, to;
+   double scalar;
+} xaos_entry;
+
+static int xform_from_xml(xmlNode *node, flam3_xform *x, int std_index, xaos_entry **xaos, int *nxaos) {
+   if (!node->properties) {
+      fprintf(stderr, "Error: No attributes for element.\n");
+      return 1;
+   }
+   for (xmlAttrPtr a = node->properties; a; a = a->next) {
+      const char *name = (const char *)a->name;
+      char *val = (char *)xmlGetProp(node, a->name);
+      int rc = 0;
+      if (!strcmp(name, "weight")) x->density = to_double(val);
+      else if (!strcmp(name, "symmetry")) { /* deprecated spelling of color_speed + animate */
+         const double s = to_double(val);
+         x->color_speed = (1.0 - s) / 2.0;
+         x->animate = s > 0 ? 0 : 1;
+      } else if (!strcmp(name, "color_speed")) x->color_speed = to_double(val);
+      else if (!strcmp(name, "animate")) x->animate = to_double(val);
+      else if (!strcmp(name, "opacity")) x->opacity = to_double(val);
+      else if (!strcmp(name, "plotmode")) {
+         if (!strcmp(val, "off")) x->opacity = 0.0;
+      } else if (!strcmp(name, "color")) { /* one coordinate; an old second one is read and dropped */
+         double two[2];
+         x->color = 0.0;
+         if (to_doubles(val, two, 2) == 0) x->color = two[0];
+         else if (to_doubles(val, two, 1) == 0) x->color = two[0];
+         else {
+            fprintf(stderr, "Error: malformed xform color attribute '%s'\n", val);
+            rc = 1;
+         }
+      } else if (!strcmp(name, "coefs") || !strcmp(name, "post")) {
+         double six[6];
+         if (to_doubles(val, six, 6)) {
+            fprintf(stderr, "error: bad value in %s attribute '%s'\n", name, val);
+            rc = 1;
+         } else {
+            double(*m)[2] = name[0] == 'c' ? x->c : x->post;
+            for (int k = 0; k < 3; k++)
+               for (int j = 0; j < 2; j++) m[k][j] = six[2 * k + j];
+         }
+      } else if (!strcmp(name, "var1")) {
+         const int v = to_int(val);
+         if (v < 0 || v >= flam3_nvariations) {
+            fprintf(stderr, "Error:  Bad variation (%d)\n", v);
+            rc = 1;
+         } else {
+            memset(x->var, 0, sizeof(x->var));
+            x->var[v] = 1.0;
+         }
+      } else if (!strcmp(name, "var")) {
+         if (to_doubles(val, x->var, flam3_nvariations)) {
+            fprintf(stderr, "error: bad value in var attribute '%s'\n", val);
+            rc = 1;
+         }
+      } else if (!strcmp(name, "chaos")) {
+         /* entries that are not 1 are remembered and applied when all xforms are known */
+         int to = 0;
+         for (char *tok = strtok(val, " "); tok && !rc; tok = strtok(NULL, " "), to++) {
+            const double s = to_double(tok);
+            if (s == 1.0) continue;
+            xaos_entry *grown = (xaos_entry *)realloc(*xaos, (size_t)(*nxaos + 1) * sizeof(xaos_entry));
+            if (!grown) rc = 1;
+            else {
+               *xaos = grown;
+               (*xaos)[*nxaos].from = std_index;
+               (*xaos)[*nxaos].to = to;
+               (*xaos)[*nxaos].scalar = s;
+               (*nxaos)++;
+            }
+         }
+      } else if (!strcmp(name, "motion_frequency") || !strcmp(name, "motion_function")) {
+         fprintf(stderr, "Error: Motion parameters should not be specified in xforms.\n");
+         rc = 1;
+      } else if (!strcmp(name, "super_shape_rnd")) {
+         const double v = to_double(val);
+         x->super_shape_rnd = v < 0 ? 0 : (v > 1 ? 1 : v);
+      } else {
+         const char *field = name;
+         for (size_t i = 0; i < sizeof(k_xform_aliases) / sizeof(k_xform_aliases[0]); i++)
+            if (!strcmp(name, k_xform_aliases[i].alias)) field = k_xform_aliases[i].name;
+         int done = 0;
+         for (size_t i = 0; i < sizeof(k_xform_params) / sizeof(k_xform_params[0]) && !done; i++)
+            if (!strcmp(field, k_xform_params[i].name)) {
+               *(double *)((char *)x + k_xform_params[i].off) = to_double(val);
+               done = 1;
+            }
+         for (int v = 0; v < flam3_nvariations && !done; v++)
+            if (!strcmp(name, k_variation_names[v])) {
+               x->var[v] = to_double(val);
+               done = 1;
+            }
+         if (!done) fprintf(stderr, "Warning: unrecognized variation %s.  Ignoring.\n", name);
+      }
+      xmlFree(val);
+      if (rc) return 1;
+   }
+   for (xmlNode *c = node->children; c; c = c->next)
+      if (c->type == XML_ELEMENT_NODE && !xmlStrcmp(c->name, (const xmlChar *)"motion")) {
+         fprintf(stderr, "f3b_parse_flam3: motion elements are not supported by this front end\n");
+         return 1;
+      }
+   return 0;
+}
+
+/* ---- <flame> ---------------------------------------------------------------------------- */
+static int flame_from_xml(xmlNode *flame, flam3_genome *cp) {
+   if (!flame->properties) {
+      fprintf(stderr, "Error : <flame> element has no attributes.\n");
+      return 1;
+   }
+   for (int i = 0; i < 256; i++) {
+      memset(cp->palette[i].color, 0, sizeof(cp->palette[i].color));
+      cp->palette[i].index = -1;
+   }
+   memset(cp->flame_name, 0, flam3_name_len + 1);
+   g_bad_number = 0;
+   int solo = -1;
+
+   for (xmlAttrPtr a = flame->properties; a; a = a->next) {
+      const char *name = (const char *)a->name;
+      char *val = (char *)xmlGetProp(flame, a->name);
+      int rc = 0, done = 0;
+      for (size_t i = 0; i < sizeof(k_flame_numbers) / sizeof(k_flame_numbers[0]) && !done; i++)
+         if (!strcmp(name, k_flame_numbers[i].name)) {
+            if (k_flame_numbers[i].kind == 'd') *(double *)((char *)cp + k_flame_numbers[i].off) = to_double(val);
+            else *(int *)((char *)cp + k_flame_numbers[i].off) = to_int(val);
+            done = 1;
+         }
+      for (size_t i = 0; i < sizeof(k_flame_words) / sizeof(k_flame_words[0]) && !done; i++)
+         if (!strcmp(name, k_flame_words[i].name)) {
+            const f3b_word *w = k_flame_words[i].words;
+            while (w->word && strcmp(w->word, val)) w++;
+            if (w->word) *(int *)((char *)cp + k_flame_words[i].off) = w->value;
+            else fprintf(stderr, "warning: unrecognized %s %s.\n", k_flame_words[i].what, val);
+            done = 1;
+         }
+      if (done) {
+      } else if (!strcmp(name, "name")) {
+         strncpy(cp->flame_name, val, flam3_name_len);
+         for (int i = (int)strlen(cp->flame_name) - 2; i >= 0; i--) /* as the reference: not the last one */
+            if (isspace((unsigned char)cp->flame_name[i])) cp->flame_name[i] = '_';
+      } else if (!strcmp(name, "size")) {
+         double wh[2];
+         if (to_doubles(val, wh, 2) || wh[0] != (int)wh[0] || wh[1] != (int)wh[1]) {
+            fprintf(stderr, "error: invalid size attribute '%s'\n", val);
+            rc = 1;
+         } else {
+            cp->width = (int)wh[0];
+            cp->height = (int)wh[1];
+         }
+      } else if (!strcmp(name, "center")) {
+         if (to_doubles(val, cp->center, 2)) {
+            fprintf(stderr, "error: invalid center attribute '%s'\n", val);
+            rc = 1;
+         } else {
+            cp->rot_center[0] = cp->center[0];
+            cp->rot_center[1] = cp->center[1];
+         }
+      } else if (!strcmp(name, "background")) {
+         if (to_doubles(val, cp->background, 3)) {
+            fprintf(stderr, "error: invalid background attribute '%s'\n", val);
+            rc = 1;
+         }
+      } else if (!strcmp(name, "highlight_power")) cp->highlight_power = atof(val);
+      else if (!strcmp(name, "hue")) cp->hue_rotation = fmod(to_double(val), 1.0);
+      else if (!strcmp(name, "soloxform")) solo = (int)to_double(val);
+      /* anything else (version, brightness aliases of other programs, ...) is ignored */
+      xmlFree(val);
+      if (rc) return 1;
+   }
+
+   xaos_entry *xaos = NULL;
+   int nxaos = 0, nstd = 0, rc = 0;
+   for (xmlNode *c = flame->children; c && !rc; c = c->next) {
+      if (c->type != XML_ELEMENT_NODE) continue;
+      const char *tag = (const char *)c->name;
+      if (!strcmp(tag, "color")) {
+         int index = -1;
+         double rgba[4] = {0, 0, 0, 255.0};
+         for (xmlAttrPtr a = c->properties; a && !rc; a = a->next) {
+            char *val = (char *)xmlGetProp(c, a->name);
+            const char *an = (const char *)a->name;
+            if (!strcmp(an, "index")) index = to_int(val);
+            else if (!strcmp(an, "rgb")) rc = to_doubles(val, rgba, 3);
+            else if (!strcmp(an, "rgba")) rc = to_doubles(val, rgba, 4);
+            else if (!strcmp(an, "a")) rc = to_doubles(val, rgba + 3, 1);
+            else {
+               fprintf(stderr, "Error:  Unknown color attribute '%s'\n", an);
+               rc = 1;
+            }
+            if (rc) fprintf(stderr, "error: invalid colour attribute '%s'\n", val);
+            xmlFree(val);
+         }
+         if (!rc && (index < 0 || index > 255)) {
+            fprintf(stderr, "Error:  Color element with bad/missing index attribute (%d)\n", index);
+            rc = 1;
+         }
+         if (!rc) { /* premultiplied by alpha */
+            const double alpha = rgba[3] / 255.0;
+            cp->palette[index].color[3] = alpha;
+            for (int k = 0; k < 3; k++) cp->palette[index].color[k] = alpha * rgba[k] / 255.0;
+            cp->palette[index].index = index;
+         }
+      } else if (!strcmp(tag, "colors")) {
+         int count = 0;
+         for (xmlAttrPtr a = c->properties; a && !rc; a = a->next) {
+            char *val = (char *)xmlGetProp(c, a->name);
+            if (!strcmp((const char *)a->name, "count")) count = to_int(val);
+            else if (!strcmp((const char *)a->name, "data")) rc = hex_colors(val, cp, count, -4);
+            else {
+               fprintf(stderr, "Error:  Unknown color attribute '%s'\n", (const char *)a->name);
+               rc = 1;
+            }
+            xmlFree(val);
+         }
+      } else if (!strcmp(tag, "palette")) {
+         int count = 0, bytes = 0;
+         for (xmlAttrPtr a = c->properties; a && !rc; a = a->next) {
+            char *val = (char *)xmlGetProp(c, a->name);
+            const char *an = (const char *)a->name;
+            if (!strcmp(an, "count")) count = to_int(val);
+            else if (!strcmp(an, "format")) {
+               bytes = !strcmp(val, "RGB") ? 3 : (!strcmp(val, "RGBA") ? 4 : 0);
+               if (!bytes) {
+                  fprintf(stderr, "Error: Unrecognized palette format string (%s)\n", val);
+                  rc = 1;
+               }
+            } else {
+               fprintf(stderr, "f3b_parse_flam3: palette attribute '%s' (the old two-palette blend) is not "
+                               "supported by this front end\n", an);
+               rc = 1;
+            }
+            xmlFree(val);
+         }
+         if (!rc) {
+            char *text = (char *)xmlNodeGetContent(c);
+            rc = hex_colors(text ? text : "", cp, count, bytes ? bytes : 3);
+            if (text) xmlFree(text);
+         }
+      } else if (!strcmp(tag, "xform") || !strcmp(tag, "finalxform")) {
+         const int is_final = tag[0] == 'f';
+         if (is_final && cp->final_xform_index >= 0) {
+            fprintf(stderr, "Error:  Cannot specify more than one final xform.\n");
+            rc = 1;
+            break;
+         }
+         const int at = f3b_genome_add_xform(cp, is_final);
+         if (at < 0) {
+            rc = 1;
+            break;
+         }
+         cp->xform[at].var[0] = 0.0;
+         rc = xform_from_xml(c, &cp->xform[at], is_final ? -1 : nstd, &xaos, &nxaos);
+         if (!rc && is_final && cp->xform[at].density != 0.0) {
+            fprintf(stderr, "Error: Final xforms should not have weight specified.\n");
+            rc = 1;
+         }
+         if (!is_final) nstd++;
+      } else if (!strcmp(tag, "symmetry")) {
+         int kind = 0;
+         for (xmlAttrPtr a = c->properties; a && !rc; a = a->next) {
+            char *val = (char *)xmlGetProp(c, a->name);
+            if (!strcmp((const char *)a->name, "kind")) kind = to_int(val);
+            else {
+               fprintf(stderr, "Error:  Unknown symmetry attribute '%s'\n", (const char *)a->name);
+               rc = 1;
+            }
+            xmlFree(val);
+         }
+         if (!rc) {
+            const int added = add_symmetry(cp, kind);
+            if (added < 0) rc = 1;
+            else nstd += added;
+         }
+      }
+      /* <edit> and unknown elements: no effect on rendering */
+   }
+   if (!rc) {
+      for (int i = 0; i < nstd; i++)
+         if (solo >= 0 && i != solo) cp->xform[i].opacity = 0.0;
+      for (int i = 0; i < nxaos; i++)
+         if (xaos[i].from >= 0 && xaos[i].from < nstd && xaos[i].to < nstd) cp->chaos[xaos[i].from][xaos[i].to] = xaos[i].scalar;
+      if (g_bad_number) {
+         fprintf(stderr, "error: parsing a double or int attribute's value.\n");
+         rc = 1;
+      }
+   }
+   free(xaos);
+   return rc;
+}
+
+static int collect_flames(xmlNode *n, int defaults_on, flam3_genome **all, int *count) {
+   for (; n; n = n->next) {
+      if (n->type == XML_ELEMENT_NODE && !xmlStrcmp(n->name, (const xmlChar *)"flame")) {
+         flam3_genome cp;
+         memset(&cp, 0, sizeof(cp));
+         f3b_genome_init(&cp, defaults_on);
+         if (flame_from_xml(n, &cp)) {
+            fprintf(stderr, "error parsing flame element\n");
+            f3b_genome_free_xforms(&cp);
+            return 1;
+         }
+         if (cp.palette_index != -1 && f3b_get_palette(cp.palette_index, cp.palette, cp.hue_rotation) < 0)
+            fprintf(stderr, "error retrieving palette %d, setting to all white\n", cp.palette_index);
+         fill_missing_colors(&cp);
+         cp.genome_index = *count;
+         flam3_genome *grown = (flam3_genome *)realloc(*all, (size_t)(*count + 1) * sizeof(flam3_genome));
+         if (!grown) {
+            f3b_genome_free_xforms(&cp);
+            return 1;
+         }
+         *all = grown;
+         (*all)[*count] = cp; /* the xform and chaos arrays move with it */
+         (*count)++;
+      } else if (collect_flames(n->children, defaults_on, all, count))
+         return 1;
+   }
+   return 0;
+}
+
+flam3_genome *f3b_parse_flam3(const char *xmltext, int defaults_on, int *ncps) {
+   *ncps = 0;
+   xmlDocPtr doc = xmlReadMemory(xmltext, (int)strlen(xmltext), "f3b.flam3", NULL, XML_PARSE_NONET);
+   if (!doc) {
+      fprintf(stderr, "f3b_parse_flam3: failed to parse the XML text\n");
+      return NULL;
+   }
+   flam3_genome *all = NULL;
+   int n = 0;
+   const int rc = collect_flames(xmlDocGetRootElement(doc), defaults_on, &all, &n);
+   xmlFreeDoc(doc);
+   if (rc) {
+      f3b_free_genomes(all, n);
+      return NULL;
+   }
+   /* what flam3_parse_xml2 does with the whole sequence (flam3.c:1477-1514): no smooth
+    * interpolation on the first and last segment, consecutive `rotate` values brought within
+    * 180 degrees of each other (not for the two oldest interpolation types) */
+   if (n >= 1 && all[0].interpolation == flam3_interpolation_smooth) {
+      fprintf(stderr, "Warning: smooth interpolation cannot be used for first segment.\n         switching to linear.\n");
+      all[0].interpolation = flam3_interpolation_linear;
+   }
+   if (n >= 2 && all[n - 2].interpolation == flam3_interpolation_smooth) {
+      fprintf(stderr, "Warning: smooth interpolation cannot be used for last segment.\n         switching to linear.\n");
+      all[n - 2].interpolation = flam3_interpolation_linear;
+   }
+   for (int i = 1; i < n; i++) {
+      if (all[i - 1].interpolation_type == flam3_inttype_compat || all[i - 1].interpolation_type == flam3_inttype_older)
+         continue;
+      while (all[i].rotate < all[i - 1].rotate - 180) all[i].rotate += 360;
+      while (all[i].rotate > all[i - 1].rotate + 180) all[i].rotate -= 360;
+   }
+   *ncps = n;
+   return all;
+}
+
+void f3b_free_genomes(flam3_genome *g, int n) {
+   if (!g) return;
+   for (int i = 0; i < n; i++) f3b_genome_free_xforms(&g[i]);
+   free(g);
+}
+
+/* ---- output ----------------------------------------------------------------------------- */
+int f3b_write_ppm(const char *path, const void *image, int width, int height, int nchan, int bytes_per_channel) {
+   FILE *f = fopen(path, "wb");
+   if (!f) {
+      perror(path);
+      return 1;
+   }
+   const int maxv = bytes_per_channel == 2 ? 65535 : 255;
+   fprintf(f, "P6\n%d %d\n%d\n", width, height, maxv);
+   const unsigned char *p = (const unsigned char *)image;
+   for (size_t i = 0; i < (size_t)width * height; i++) {
+      if (bytes_per_channel == 1) fwrite(p + i * nchan, 1, 3, f);
+      else { /* PPM wants the most significant byte first */
+         const unsigned short *q = (const unsigned short *)(p + i * nchan * 2);
+         for (int c = 0; c < 3; c++) {
+            const unsigned char be[2] = {(unsigned char)(q[c] >> 8), (unsigned char)(q[c] & 255)};
+            fwrite(be, 1, 2, f);
+         }
+      }
+   }
+   return fclose(f) != 0;
+}

@@ -285,3 +285,13 @@ int h_render_progress(void *cps, const h_render_args *a, void *out, double *stat
    prog_out[2] = g_prog.last_eta;
    return rv;
 }
+
+/* the repository's own front end (flam3_b200/csrc/f3b_frontend.c), present in the drop-in
+ * library only: parse with it, so that the tests can print the result with the REFERENCE's
+ * printer (h_print_genome) and compare with the reference's own parse */
+extern flam3_genome *f3b_parse_flam3(const char *xml, int defaults_on, int *ncps) __attribute__((weak));
+void *h_parse_own(const char *xml, int *ncps) {
+   *ncps = 0;
+   if (!f3b_parse_flam3) return NULL;
+   return f3b_parse_flam3(xml, flam3_defaults_on, ncps);
+}

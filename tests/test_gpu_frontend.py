@@ -1,0 +1,59 @@
+"""SURVEY §8(f) row 4, end to end: dropin/_build/f3b-render is a flame renderer made of this
+repository's code only - own genome/palette reader and image writers (f3b_frontend.c), the
+flam3_render drop-in, libflam3_b200.so - with NO reference object linked. For the same genome
+file and isaac_seed it must write the very bytes the reference's unmodified flam3-render writes
+when linked against the drop-in (same genomes in, same frame seeding, same render)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OWN = os.path.join(ROOT, "dropin", "_build", "f3b-render")
+REF_CLI = os.path.join(ROOT, "dropin", "_build", "flam3-render")
+
+
+def _run(exe, tmp, prefix, fixture, **env_extra):
+    env = dict(os.environ)
+    env.update({"format": "ppm", "isaac_seed": "frontend", "prefix": os.path.join(tmp, prefix), "verbose": "0"})
+    env.update(env_extra)
+    with open(fixture) as f:
+        p = subprocess.run([exe], stdin=f, env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+
+
+def test_standalone_renderer_links_no_reference_code():
+    syms = subprocess.run(["nm", "-D", "--defined-only", OWN], capture_output=True, text=True).stdout + \
+        subprocess.run(["nm", OWN], capture_output=True, text=True).stdout
+    for name in ("flam3_parse_xml2", "parse_flame_element", "flam3_get_palette", "flam3_interpolate_n",
+                 "flam3_align", "flam3_print", "iter_thread", "de_thread"):
+        assert (" " + name + "\n") not in syms and (" T " + name) not in syms, name
+    libs = subprocess.run(["ldd", OWN], capture_output=True, text=True).stdout
+    assert "libflam3_b200.so" in libs and "libflam3.so" not in libs and "flam3_ref" not in libs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture,extra", [("test_both.flam3", {}),
+                                           ("c5/c5_mix101.flam3", {"qs": "0.05"}),
+                                           ("c5/c5_var33.flam3", {"qs": "0.05", "ss": "0.5", "nthreads": "4"})])
+def test_standalone_renderer_writes_the_same_bytes(tmp_path, fixture, extra):
+    tmp = str(tmp_path)
+    path = os.path.join(ROOT, "tests", "golden", fixture)
+    _run(OWN, tmp, "own_", path, **extra)
+    _run(REF_CLI, tmp, "cli_", path, **extra)
+    own = sorted(f for f in os.listdir(tmp) if f.startswith("own_"))
+    cli = sorted(f for f in os.listdir(tmp) if f.startswith("cli_"))
+    assert own and len(own) == len(cli)
+    for a, b in zip(own, cli):
+        da, db = open(os.path.join(tmp, a), "rb").read(), open(os.path.join(tmp, b), "rb").read()
+        assert len(da) > 1000 and da == db, (a, b)
+
+
+@pytest.mark.gpu
+def test_standalone_renderer_png(tmp_path):
+    tmp = str(tmp_path)
+    _run(OWN, tmp, "p_", os.path.join(ROOT, "tests", "golden", "test_flame0.flam3"),
+         format="png", bpc="16", transparency="1", qs="0.5")
+    data = open(os.path.join(tmp, "p_00000.png"), "rb").read()
+    assert data[:8] == b"\\x89PNG\\r\\n\\x1a\\n"
+    assert data[16:26] == (640).to_bytes(4, "big") + (480).to_bytes(4, "big") + bytes([16, 6])

@@ -1,0 +1,143 @@
+/*
+ * f3b-render — a flame renderer made of this repository's code only: front end
+ * (f3b_frontend.c: genome XML, palette library, PPM/PNG), the flam3_render drop-in
+ * (f3b_render.c, f3b_pack.c, f3b_isaac.c) and libflam3_b200.so. No reference object is linked
+ * (SURVEY.md §8(f) row 4). It takes flam3-render's environment (README.txt:55-115, the subset
+ * that matters for stills):
+ *
+ *    in (default stdin), prefix, out, format (ppm | png), qs, ss, bits (33), bpc (8 | 16, 16 needs png),
+ *    nthreads, sub_batch_size, earlyclip, pixel_aspect, transparency, isaac_seed, verbose,
+ *    flam3_palettes, F3B_DEVICE / F3B_DEVICES
+ *
+ *    env format=ppm prefix=out/ tools/_build/f3b-render < some.flam3
+ *
+ * One image per <flame>, named <prefix>%05d.<format> like flam3-render.c:355. For the same
+ * genome file and isaac_seed the bytes equal those of the unmodified flam3-render linked
+ * against the drop-in (tests/test_gpu_frontend.py).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "flam3.h"
+
+#include "../include/flam3_b200_frontend.h"
+
+/* shims/imgshim.c: this repository's PNG writer behind the reference's write_png signature
+ * (img.h:29-40) */
+typedef struct {
+   char *genome, *badvals, *numiters, *rtime;
+} flam3_img_comments;
+void write_png(FILE *file, void *image, int width, int height, flam3_img_comments *fpc, int bpc);
+
+static const char *env_or(const char *name, const char *dflt) {
+   const char *v = getenv(name);
+   return v ? v : dflt;
+}
+
+int main(void) {
+   const char *inf = getenv("in"), *prefix = env_or("prefix", ""), *out = getenv("out");
+   const char *format = env_or("format", "ppm");
+   const double qs = atof(env_or("qs", "1")), ss = atof(env_or("ss", "1"));
+   const int bits = atoi(env_or("bits", "33")), bpc = atoi(env_or("bpc", "8"));
+   const int transp = atoi(env_or("transparency", "0")), verbose = atoi(env_or("verbose", "0"));
+   if (strcmp(format, "ppm") && strcmp(format, "png")) {
+      fprintf(stderr, "f3b-render: format must be ppm or png, not %s.\n", format);
+      return 1;
+   }
+   if (bpc != 8 && bpc != 16) {
+      fprintf(stderr, "Unexpected bpc specified (%d)\n", bpc);
+      return 1;
+   }
+   if (bpc == 16 && strcmp(format, "png")) {
+      fprintf(stderr, "Support for 16 bpc images is only present for the png format.\n");
+      return 1;
+   }
+   FILE *in = inf ? fopen(inf, "rb") : stdin;
+   if (!in) {
+      perror(inf);
+      return 1;
+   }
+   size_t cap = 1 << 16, n = 0;
+   char *text = (char *)malloc(cap);
+   for (size_t got; text && (got = fread(text + n, 1, cap - n - 1, in)) > 0;) {
+      n += got;
+      if (n + 1 >= cap) text = (char *)realloc(text, cap *= 2);
+   }
+   if (inf) fclose(in);
+   if (!text) return 1;
+   text[n] = 0;
+
+   int ncps = 0;
+   flam3_genome *cps = f3b_parse_flam3(text, flam3_defaults_on, &ncps);
+   free(text);
+   if (!cps || ncps == 0) {
+      fprintf(stderr, "error reading genomes from file\n");
+      return 1;
+   }
+   flam3_frame f;
+   memset(&f, 0, sizeof(f));
+   flam3_init_frame(&f);
+   const int channels = strcmp(format, "png") ? 3 : 4;
+   for (int i = 0; i < ncps; i++) {
+      cps[i].ntemporal_samples = 1; /* stills: flam3-render.c:235 */
+      cps[i].sample_density *= qs;
+      cps[i].height = (int)(cps[i].height * ss);
+      cps[i].width = (int)(cps[i].width * ss);
+      cps[i].pixels_per_unit *= ss;
+      if (cps[i].height <= 0 || cps[i].width <= 0) {
+         fprintf(stderr, "output image has dimension <=0, aborting.\n");
+         return 1;
+      }
+      f.genomes = &cps[i];
+      f.ngenomes = 1;
+      f.verbose = verbose;
+      f.bits = bits;
+      f.time = 0.0;
+      f.pixel_aspect_ratio = atof(env_or("pixel_aspect", "1"));
+      f.progress = 0;
+      f.nthreads = atoi(env_or("nthreads", "0"));
+      if (f.nthreads <= 0) f.nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN); /* flam3_count_nthreads, flam3.c:1415 */
+      if (f.nthreads < 1) f.nthreads = 1;
+      f.earlyclip = atoi(env_or("earlyclip", "0"));
+      f.sub_batch_size = atoi(env_or("sub_batch_size", "10000"));
+      f.bytes_per_channel = bpc == 16 ? 2 : 1;
+      const size_t bytes = (size_t)channels * cps[i].width * cps[i].height * f.bytes_per_channel;
+      void *image = calloc(bytes, 1);
+      stat_struct stats;
+      if (!image || flam3_render(&f, image, flam3_field_both, channels, transp, &stats)) {
+         fprintf(stderr, "error rendering image: aborting.\n");
+         return 1;
+      }
+      char name[4096];
+      if (out) snprintf(name, sizeof(name), "%s", out);
+      else snprintf(name, sizeof(name), "%s%05d.%s", prefix, i, format);
+      if (verbose) fprintf(stderr, "writing %s...", name);
+      if (!strcmp(format, "ppm")) {
+         if (f3b_write_ppm(name, image, cps[i].width, cps[i].height, channels, f.bytes_per_channel)) return 1;
+      } else {
+         FILE *fp = fopen(name, "wb");
+         if (!fp) {
+            perror(name);
+            return 1;
+         }
+         flam3_img_comments fpc;
+         memset(&fpc, 0, sizeof(fpc));
+         char badvals[64], iters[64], secs[64];
+         snprintf(badvals, sizeof(badvals), "%g", stats.badvals / (double)(stats.num_iters ? stats.num_iters : 1));
+         snprintf(iters, sizeof(iters), "%g", (double)stats.num_iters);
+         snprintf(secs, sizeof(secs), "%d", stats.render_seconds);
+         fpc.genome = (char *)"";
+         fpc.badvals = badvals;
+         fpc.numiters = iters;
+         fpc.rtime = secs;
+         write_png(fp, image, cps[i].width, cps[i].height, &fpc, f.bytes_per_channel);
+         fclose(fp);
+      }
+      if (verbose) fprintf(stderr, "done.\n");
+      free(image);
+   }
+   f3b_free_genomes(cps, ncps);
+   return 0;
+}
