@@ -154,6 +154,14 @@ static const struct {
    {"palette_mode", k_palette_mode, offsetof(flam3_genome, palette_mode), "palette mode"},
 };
 
+/* The reference is built with -ffast-math (Makefile.am:4), which turns every division by a
+ * constant into a multiplication by its rounded reciprocal. Colours are n / 255 all over the
+ * parser and n / 255 != n * (1 / 255) in the last bit for some n - enough to move a palette
+ * entry across a truncation boundary (132 / 255 * 255 = 132, 132 * (1 / 255) * 255 = 131.99...).
+ * The same arithmetic, spelled out, so that the genomes are bit-identical however this file is
+ * compiled: */
+static const double k_inv255 = 1.0 / 255.0;
+
 /* ---- numbers (flam3_atof / flam3_atoi, parser.c:26-72: the whole string must convert) ---- */
 static int g_bad_number;
 static double to_double(const char *s) {
@@ -438,7 +446,7 @@ static int hex_colors(const char *s, flam3_genome *cp, int count, int chan) {
       at += (size_t)digits;
       while (isspace((unsigned char)s[at])) at++;
       if (n < 256) {
-         for (int c = 0; c < 4; c++) cp->palette[n].color[c] = v[c] / 255.0;
+         for (int c = 0; c < 4; c++) cp->palette[n].color[c] = v[c] * k_inv255;
          cp->palette[n].index = n;
       }
       n++;
@@ -483,8 +491,10 @@ static void fill_missing_colors(flam3_genome *cp) {
          rpos = first + 256;
          rcol = first;
       }
+      /* one reciprocal per gap, as the reference's -ffast-math build hoists it (see k_inv255) */
+      const double inv_span = 1.0 / (double)(rpos - lpos);
       for (int j = i; j <= end; j++) {
-         const double t = (j - lpos) / (double)(rpos - lpos);
+         const double t = (j - lpos) * inv_span;
          for (int k = 0; k < 4; k++)
             cp->palette[j].color[k] = cp->palette[lcol].color[k] * (1.0 - t) + cp->palette[rcol].color[k] * t;
          cp->palette[j].index = j;
@@ -493,18 +503,20 @@ static void fill_missing_colors(flam3_genome *cp) {
    }
 }
 
-/* hexcone model, h in [0,6) (palettes.c:199-272) */
+/* hexcone model, h in [0,6) (palettes.c:199-272). The hue is the difference of two of
+ * (max - channel) / del; the reference's -ffast-math build folds that into ONE division of the
+ * channel difference, (g - b) / del and so on (see k_inv255) - the same here, to the bit. */
 static void rgb_to_hsv(const double *rgb, double *hsv) {
    const double r = rgb[0], g = rgb[1], b = rgb[2];
-   const double mx = fmax(r, fmax(g, b)), mn = fmin(r, fmin(g, b));
+   const double mx = r >= g ? (r >= b ? r : b) : (g >= b ? g : b);
+   const double mn = r <= g ? (r <= b ? r : b) : (g <= b ? g : b);
    const double del = mx - mn;
    const double s = mx != 0.0 ? del / mx : 0.0;
    double h = 0.0;
    if (s != 0.0) {
-      const double rc = (mx - r) / del, gc = (mx - g) / del, bc = (mx - b) / del;
-      if (r == mx) h = bc - gc;
-      else if (g == mx) h = 2 + rc - bc;
-      else if (b == mx) h = 4 + gc - rc;
+      if (r == mx) h = (g - b) / del;
+      else if (g == mx) h = (b - r) / del + 2.0;
+      else if (b == mx) h = (r - g) / del + 4.0;
       if (h < 0) h += 6;
    }
    hsv[0] = h;
@@ -604,7 +616,7 @@ int f3b_get_palette(int number, flam3_palette pal, double hue_rotation) {
       if (g_palettes[p].number != number) continue;
       for (int i = 0; i < 256; i++) {
          double rgb[3], hsv[3];
-         for (int j = 0; j < 3; j++) rgb[j] = g_palettes[p].rgb[i][j] / 255.0;
+         for (int j = 0; j < 3; j++) rgb[j] = g_palettes[p].rgb[i][j] * k_inv255;
          rgb_to_hsv(rgb, hsv);
          hsv[0] += hue_rotation * 6.0;
          hsv_to_rgb(hsv, rgb);
@@ -819,9 +831,9 @@ static int flame_from_xml(xmlNode *flame, flam3_genome *cp) {
             rc = 1;
          }
          if (!rc) { /* premultiplied by alpha */
-            const double alpha = rgba[3] / 255.0;
+            const double alpha = rgba[3] * k_inv255;
             cp->palette[index].color[3] = alpha;
-            for (int k = 0; k < 3; k++) cp->palette[index].color[k] = alpha * rgba[k] / 255.0;
+            for (int k = 0; k < 3; k++) cp->palette[index].color[k] = alpha * rgba[k] * k_inv255;
             cp->palette[index].index = index;
          }
       } else if (!strcmp(tag, "colors")) {

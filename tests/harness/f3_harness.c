@@ -7,6 +7,7 @@
  * Compiled once against each library; contains no rendering logic of its own.
  */
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -294,4 +295,40 @@ void *h_parse_own(const char *xml, int *ncps) {
    *ncps = 0;
    if (!f3b_parse_flam3) return NULL;
    return f3b_parse_flam3(xml, flam3_defaults_on, ncps);
+}
+
+/* byte ranges of flam3_genome that are not genome DATA (pointers, the name of the file it came
+ * from): {offset, length} pairs, for tests that compare parsed genomes byte for byte */
+int h_genome_nondata_ranges(int *out) {
+   flam3_genome *g = 0;
+   int n = 0;
+#define RANGE(field) out[n++] = (int)(size_t)&g->field, out[n++] = (int)sizeof(g->field)
+   RANGE(xform);
+   RANGE(chaos);
+   RANGE(edits);
+   RANGE(parent_fname);
+#undef RANGE
+   return n / 2;
+}
+/* the xform array and one chaos row of genome idx, raw */
+const void *h_genome_xforms(void *cps, int idx, int *num, int *final_index) {
+   flam3_genome *g = (flam3_genome *)cps + idx;
+   *num = g->num_xforms;
+   *final_index = g->final_xform_index;
+   return g->xform;
+}
+const double *h_genome_chaos_row(void *cps, int idx, int row) { return ((flam3_genome *)cps + idx)->chaos[row]; }
+/* the same for flam3_xform: padding holes, values derived at render time (precalc flags and
+ * values, the active-variation list) and the motion pointer */
+int h_xform_nondata_ranges(int *out) {
+   int n = 0;
+#define SPAN(from, to) out[n++] = (int)(from), out[n++] = (int)((to) - (from))
+   SPAN(offsetof(flam3_xform, vis_adjusted), offsetof(flam3_xform, padding));   /* variations.c:2034 */
+   SPAN(offsetof(flam3_xform, padding) + sizeof(int), offsetof(flam3_xform, wind));
+   SPAN(offsetof(flam3_xform, precalc_angles_flag), offsetof(flam3_xform, blob_low)); /* :2039-2102 */
+   SPAN(offsetof(flam3_xform, persp_vsin), offsetof(flam3_xform, motion_freq));
+   SPAN(offsetof(flam3_xform, motion_func) + sizeof(int), offsetof(flam3_xform, num_motion));
+   SPAN(offsetof(flam3_xform, num_motion) + sizeof(int), sizeof(flam3_xform));
+#undef SPAN
+   return n / 2;
 }

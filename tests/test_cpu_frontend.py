@@ -35,6 +35,58 @@ def test_own_parser_equals_the_reference_parser(gpu, path):
         assert x == y
 
 
+def _raw(lib, genomes):
+    """Every data byte a render can read: the genome structs without their pointer fields and
+    file name, the xform arrays (variation weights, affine parts, parameters, motion function;
+    not what flam3_render derives - precalc values, the active-variation list - nor padding)
+    and the chaos matrix."""
+    import ctypes as C
+    import numpy as np
+    d = lib._dll
+    ranges = (C.c_int * 16)()
+    nr = d.h_genome_nondata_ranges(ranges)
+    xranges = (C.c_int * 16)()
+    nx = d.h_xform_nondata_ranges(xranges)
+    d.h_genome_xforms.restype = C.c_void_p
+    d.h_genome_xforms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    d.h_genome_chaos_row.restype = C.POINTER(C.c_double)
+    d.h_genome_chaos_row.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    sizes = lib.abi_sizes()
+    out = []
+    for i in range(genomes.n):
+        g = bytearray(C.string_at(genomes.ptr + i * sizes["flam3_genome"], sizes["flam3_genome"]))
+        for k in range(nr):
+            g[ranges[2 * k]:ranges[2 * k] + ranges[2 * k + 1]] = bytes(ranges[2 * k + 1])
+        num, fin = C.c_int(), C.c_int()
+        xp = d.h_genome_xforms(genomes.ptr, i, C.byref(num), C.byref(fin))
+        xs = np.frombuffer(C.string_at(xp, num.value * sizes["flam3_xform"]), dtype=np.uint8).reshape(num.value, -1).copy()
+        for k in range(nx):
+            xs[:, xranges[2 * k]:xranges[2 * k] + xranges[2 * k + 1]] = 0
+        nstd = num.value - (1 if fin.value >= 0 else 0)
+        chaos = [[d.h_genome_chaos_row(genomes.ptr, i, r)[c] for c in range(nstd)] for r in range(nstd)]
+        out.append((bytes(g), xs, chaos))
+    return out
+
+
+@pytest.mark.parametrize("path", _fixtures(),
+                         ids=lambda p: os.path.basename(p))
+def test_own_parser_gives_bit_identical_genomes(gpu, path):
+    """Stronger than the printed text (which rounds to a few digits): the genome structs, xform
+    arrays and chaos matrices of both parsers are the same BYTES, so a render cannot tell them
+    apart. This is what catches, e.g., n / 255 against n * (1 / 255) in a palette entry (the
+    reference is built with -ffast-math)."""
+    import numpy as np
+    xml = open(path).read()
+    a, b = _raw(gpu, gpu.parse(xml)), _raw(gpu, gpu.parse_own(xml))
+    assert len(a) == len(b)
+    for (ga, xa, ca), (gb, xb, cb) in zip(a, b):
+        diff = [i for i in range(len(ga)) if ga[i] != gb[i]]
+        assert not diff, "genome bytes differ at offsets %s" % diff[:20]
+        assert ca == cb
+        assert xa.shape == xb.shape
+        assert np.array_equal(xa, xb), "xform bytes differ at offsets %s" % np.where((xa != xb).any(axis=0))[0][:20]
+
+
 EXTRA = """
 <flames>
 <flame name="two  words here" time="3" size="320 200" center="0.25 -0.5" scale="77.5" rotate="200" zoom="0.5"
@@ -83,6 +135,53 @@ def test_own_parser_on_every_attribute_it_reads(gpu):
     for x, y in zip(a, b):
         assert x == y
     assert 'rotate="260"' in b[1] or re.search(r'rotate="2[56]\d', b[1])
+    import numpy as np
+    for (ga, xa, ca), (gb, xb, cb) in zip(_raw(gpu, gpu.parse(EXTRA)), _raw(gpu, gpu.parse_own(EXTRA))):
+        assert ga == gb and ca == cb and np.array_equal(xa, xb)
+
+
+PALETTE_LIB_SCRIPT = r"""
+import sys
+sys.path.insert(0, %(tests)r)
+import numpy as np
+import flam3_b200 as fb
+import test_cpu_frontend as T
+lib = fb.load_dropin()
+xml = '<flames>' + ''.join(
+    '<flame time="%%d" size="32 32" palette="%%d" hue="%%s"><xform weight="1" color="0" coefs="1 0 0 1 0 0" linear="1"/></flame>'
+    %% (i, n, h) for i, (n, h) in enumerate([(3, "0"), (3, "0.37"), (11, "-0.2"), (42, "0.999"), (42, "2.5")])) + '</flames>'
+a, b = T._raw(lib, lib.parse(xml)), T._raw(lib, lib.parse_own(xml))
+assert len(a) == len(b) == 5
+for (ga, xa, ca), (gb, xb, cb) in zip(a, b):
+    diff = [i for i in range(len(ga)) if ga[i] != gb[i]]
+    assert not diff, diff[:20]
+    assert np.array_equal(xa, xb)
+pal = np.frombuffer(a[1][0], dtype=np.uint8)
+assert len(set(a[k][0] for k in range(5))) == 5      # the palettes were found and rotated
+print("ok")
+"""
+
+
+def test_palette_library_and_hue_rotation(tmp_path):
+    """palette="N" hue="h": the library file (the path comes from the environment variable the
+    reference reads, palettes.c:117) and the hexcone rotation, against the reference's parser on
+    a library written here. In a fresh process: both sides read the library once."""
+    import subprocess
+    import sys
+    import numpy as np
+    rng = np.random.default_rng(5)
+    rows = []
+    for number in (3, 11, 42):
+        cols = rng.integers(0, 256, size=(256, 3))
+        cols[:8] = [[0, 0, 0], [255, 255, 255], [7, 7, 7], [255, 0, 0], [0, 255, 0], [0, 0, 255], [255, 255, 0], [1, 2, 1]]
+        data = "\n".join("".join("00%02X%02X%02X" % tuple(c) for c in cols[i:i + 8]) for i in range(0, 256, 8))
+        rows.append('<palette number="%d" name="p%d" data="%s"/>' % (number, number, data))
+    path = tmp_path / "palettes.xml"
+    path.write_text("<palettes>\n" + "\n".join(rows) + "\n</palettes>\n")
+    env = dict(os.environ, flam3_palettes=str(path))
+    out = subprocess.run([sys.executable, "-c", PALETTE_LIB_SCRIPT % {"tests": os.path.join(ROOT, "tests")}],
+                         env=env, cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
 
 
 def test_own_parser_refuses_what_it_does_not_read(gpu):
