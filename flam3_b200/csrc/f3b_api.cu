@@ -634,7 +634,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       if (ge && atof(ge) > 0.0) gap_us = atof(ge);
       P.sweep_gap_ns = gap_us * 1e3 > 4e9 ? 4000000000u : (uint32_t)(gap_us * 1e3);
       const char *me = getenv("F3B_SWEEP_MODE");
-      P.sweep_mode = me ? (uint32_t)atoi(me) : 3u;
+      P.sweep_mode = me ? (uint32_t)atoi(me) : 11u;
       if (P.sweep_on) {
          CK(cudaMemsetAsync(P.sweep_state, 0, 4 * sizeof(unsigned int), ctx->stream));
          CK(cudaMemsetAsync(ctx->hot_bitmap.p, 0,
@@ -672,8 +672,6 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       for (uint32_t q = 0; q < w0[F3B_H_NSTD]; q++) {
          const uint32_t rec = w0[F3B_H_XF_BASE] + q * w0[F3B_H_XF_STRIDE];
          uint64_t sig = 0xcbf29ce484222325ull ^ (w0[rec + F3B_X_FLAGS] & 0xffu);
-         const float *fr = (const float *)(w0 + rec);
-         sig = (sig ^ (fr[F3B_X_WLINEAR] != 0.0f ? 1u : 0u) ^ (fr[F3B_X_WSPHERICAL] != 0.0f ? 2u : 0u)) * 0x100000001b3ull;
          for (uint32_t pv = rec + F3B_X_VARS; pv < rec + F3B_X_VARS + (w0[rec + F3B_X_FLAGS] >> 8);) {
             sig = (sig ^ (w0[pv] & 0xffu)) * 0x100000001b3ull;
             pv += 2 + (w0[pv] >> 8);
@@ -682,8 +680,9 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          else if (sig != first_sig) heterogeneous = true;
       }
       const char *we = getenv("F3B_WU");
-      /* (the classic-flame kernels have no variation code to diverge in: they only lose) */
-      const bool want = we ? atoi(we) != 0 : (heterogeneous && !all_simple);
+      /* (xforms that differ only in their linear / spherical weights - the fixed-function slots
+       * every xform runs - have no code to diverge in: the classic flames only lose, -12 %) */
+      const bool want = we ? atoi(we) != 0 : heterogeneous;
       if (want && !binned && group_size >= 128) {
          P.warp_uniform = 1;
          P.wu_smem_off = (uint32_t)((smem_bytes + 15) / 16 * 4);
@@ -738,6 +737,7 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          const uint32_t hf =
              (w[F3B_H_XAOS] ? F3B_HF_XAOS : 0u) | (w[F3B_H_ROTATE] ? F3B_HF_ROTATE : 0u) |
              ((w[F3B_H_PLOT] & F3B_PLOT_READY) ? F3B_HF_PLOT_READY : 0u) |
+             ((w[F3B_H_PLOT] & F3B_PLOT_PACKED) ? F3B_HF_PAL_PACKED : 0u) |
              (w[F3B_H_PALMODE] ? F3B_HF_PAL_LINEAR : 0u) | ((int)w[F3B_H_FINAL] >= 0 ? F3B_HF_FINAL : 0u) |
              ((!w[F3B_H_XAOS] && w[F3B_H_CHOOSER_STRIDE] == 4) ? F3B_HF_CHOOSER_CONST : 0u) |
              (w[F3B_H_CHOOSER_STRIDE] << 8) | (w[F3B_H_CMAPSIZE] << 20);

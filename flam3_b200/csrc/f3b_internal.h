@@ -95,6 +95,7 @@ struct F3ConstSample {
 #define F3B_HF_PAL_LINEAR 8u
 #define F3B_HF_FINAL 16u
 #define F3B_HF_CHOOSER_CONST 32u /* <= 4 xforms, no xaos: thresholds come from samp[].cum */
+#define F3B_HF_PAL_PACKED 64u    /* the rgba8 copy of the dmap may be used (F3B_PLOT_PACKED) */
 /* temporal samples per launch: 296 x 96 B = 27.75 KB of the 32 KB parameter space that CUDA
  * 12.1+ gives sm_70+ kernels. An animation frame with 1000 temporal samples is 4 launches
  * (on side streams, so they overlap). */
@@ -121,7 +122,7 @@ struct F3IterateParams {
    uint32_t chain_threads;       /* walkers per CTA = chains per group */
    uint32_t sweep_on;            /* blockDim.x == chain_threads + 32 */
    uint32_t sweep_gap_ns;        /* a cold pass over the staging planes is due this often */
-   uint32_t sweep_mode;          /* 1 cold passes | 2 hot list (3 = normal; F3B_SWEEP_MODE for experiments) */
+   uint32_t sweep_mode;          /* 1 cold passes | 2 hot list | 4 hot mark from the nominal gap only | 8 walkers report sampled entries (11 = normal; F3B_SWEEP_MODE for experiments) */
    uint32_t exact_f64;
    float carry_thresh;           /* F3B_CARRY_U32 / F3B_CARRY_F64 (F3B_CARRY lowers it, for tests) */
    unsigned int *sweep_state;    /* device: [0] cold ticket, [1] hot entries, [2] hot ticket */

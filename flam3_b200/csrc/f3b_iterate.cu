@@ -346,7 +346,15 @@ __device__ __forceinline__ unsigned long long f3b_now_ns() {
  *    hot entries at a time. A 1080p
  *    quality-2000 flame has ~6000 hot entries among 6.4 million; they are what actually needs
  *    carrying, every ~100 us for the fullest. */
-__device__ __noinline__ void f3b_sweeper(const F3IterateParams &P, volatile int *s_done) {
+/* ring of staging entries the walkers report (see the walkers' loop): written by them, read by
+ * the CTA's sweeper warp; a lost or repeated report is harmless */
+#define F3B_SAMPLE_RING 256u
+#define F3B_SAMPLE_EVERY 512 /* a walker reports the entry it just added to every so many iterations */
+struct F3SampleRing {
+   unsigned int head;
+   uint32_t entry[F3B_SAMPLE_RING];
+};
+__device__ __noinline__ void f3b_sweeper(const F3IterateParams &P, volatile int *s_done, volatile F3SampleRing *ring) {
    const unsigned lane = threadIdx.x & 31u;
    const size_t n_entries = P.lay.replica_stride * P.lay.replicas;
    const unsigned nseg = (unsigned)((n_entries + F3B_SWEEP_ENTRIES - 1) / F3B_SWEEP_ENTRIES);
@@ -360,6 +368,10 @@ __device__ __noinline__ void f3b_sweeper(const F3IterateParams &P, volatile int 
    if (lane == 0) next = atomicAdd(S, 1u);
    unsigned ticket = 0;
    bool have_ticket = false;
+   unsigned ring_tail = 0;
+   unsigned my_pass = 0; /* the last pass this warp held a ticket of, when, and the measured period */
+   unsigned long long my_pass_t = 0;
+   float period_ns = 0.0f;
    for (unsigned round = 0; !*s_done; round++) {
       bool worked = false;
       if (!have_ticket) {
@@ -378,7 +390,19 @@ __device__ __noinline__ void f3b_sweeper(const F3IterateParams &P, volatile int 
          /* HOT means: fills at a rate that reaches the carry threshold within one gap between
           * cold passes. Whatever is below that rate cannot get from the threshold of this visit
           * past twice the carry threshold before the next one. */
-         const float frac = (float)elapsed * gap_inv;
+         /* The gap is what the schedule asks for; what counts is how long the passes really
+          * take: with a histogram that lives in DRAM the walkers' scatter saturates the memory
+          * system and a pass over the staging planes can take several gaps. The time between
+          * this warp's first tickets of consecutive passes is that period. An entry left alone
+          * at this visit fills at less than thresh / T, so it stays below 2^24 = 4 thresh as long
+          * as the next visit comes within 3 T. */
+         if (pass != my_pass) {
+            period_ns = (float)(elapsed - my_pass_t) / (float)(pass - my_pass);
+            my_pass = pass;
+            my_pass_t = elapsed;
+         }
+         float frac = (float)elapsed * gap_inv;
+         if (!(P.sweep_mode & 4u) && period_ns * gap_inv > 1.0f) frac = (float)elapsed / period_ns;
          const float hot_mark = P.carry_thresh * (frac < 1.0f ? fmaxf(frac, 1.0f / 4096.0f) : 1.0f);
          const size_t base = (size_t)(ticket % nseg) * F3B_SWEEP_ENTRIES;
          float4 v[U];
@@ -411,6 +435,34 @@ __device__ __noinline__ void f3b_sweeper(const F3IterateParams &P, volatile int 
          have_ticket = false;
          worked = true;
          if (pass < 2 && (round & 3u)) continue; /* first passes: as fast as possible */
+      }
+      /* Entries the walkers have just added to, one in F3B_SAMPLE_EVERY adds: a sample of the
+       * buckets weighted by how fast they fill. Whatever is found at the carry threshold is
+       * carried now and goes on the hot list. This is what finds the fast fillers of a
+       * histogram that lives in DRAM, where a cold pass over the staging planes takes
+       * several ms beside the walkers' scatter (4K oversample 2: 7.7 ms, in which the fullest
+       * buckets of a still pass 2^24): such a bucket is reported ~100 times on its way from
+       * the threshold to 2^24, however long the cold passes take. */
+      if (P.sweep_mode & 8u) {
+         const unsigned head = ring->head;
+         if (head - ring_tail > F3B_SAMPLE_RING) ring_tail = head - F3B_SAMPLE_RING;
+         for (; ring_tail != head; ring_tail += (head - ring_tail < 32u ? head - ring_tail : 32u)) {
+            if (lane < head - ring_tail) {
+               const size_t e = ring->entry[(ring_tail + lane) % F3B_SAMPLE_RING];
+               if (e < n_entries) {
+                  const float4 v = f3b_ld_staged4(P.hist_color + e);
+                  const float c = P.hist_count ? f3b_ld_staged1(P.hist_count + e) : 0.0f;
+                  if (f3b_sweep_entry(P, e, v, c, 1) >= P.carry_thresh) {
+                     const unsigned bit = 1u << (e & 31u);
+                     const unsigned old = atomicOr(P.sweep_hot_bitmap + (e >> 5), bit);
+                     if (!(old & bit)) {
+                        const unsigned slot = atomicAdd(S + 1, 1u);
+                        if (slot < F3B_HOT_LIST_CAP) P.sweep_hot_list[slot] = (uint32_t)e;
+                     }
+                  }
+               }
+            }
+         }
       }
       /* hot entries */
       unsigned nhot = 0;
@@ -464,6 +516,7 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
 #define HF_PAL_LINEAR F3B_HF_PAL_LINEAR
 #define HF_FINAL F3B_HF_FINAL
 #define HF_CHOOSER_CONST F3B_HF_CHOOSER_CONST
+#define HF_PAL_PACKED F3B_HF_PAL_PACKED
 
 /* Warp-uniform per-sample values (camera, small chooser row) travel in the kernel
  * parameters and are served by the constant cache: every lane needs them every iteration,
@@ -476,23 +529,28 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
 /* SIMPLE: every temporal sample of the launch has <= 4 xforms, no xaos, no final xform, a
  * step palette and fully visible xforms (the classic flame): the flag tests fold away and
  * the xform pick is three compares on a packed table from the constant bank. */
-template <bool COUNT, bool SIMPLE, bool AGG>
+template <bool COUNT, bool SIMPLE, bool AGG, bool WU>
 __global__ void __launch_bounds__(F3B_BLOCK + 32, SIMPLE ? F3B_ITER_MIN_BLOCKS : F3B_GENERIC_MIN_BLOCKS)
 f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
    extern __shared__ __align__(16) uint32_t smem[];
    const float *sf = reinterpret_cast<const float *>(smem);
    __shared__ int s_done;
+   __shared__ F3SampleRing s_ring;
 
    const uint32_t tid = threadIdx.x;
    const uint32_t nct = P.chain_threads; /* walkers; one more warp sweeps when P.sweep_on */
    if (P.sweep_on) {
-      if (tid == 0) s_done = 0;
+      if (tid == 0) {
+         s_done = 0;
+         s_ring.head = 0;
+      }
       __syncthreads();
       if (tid >= nct) {
-         f3b_sweeper(P, &s_done);
+         f3b_sweeper(P, &s_done, &s_ring);
          return;
       }
    }
+   const bool report = P.sweep_on && (P.sweep_mode & 8u);
    const size_t rep_off = (size_t)(blockIdx.x % P.lay.replicas) * P.lay.replica_stride;
    uint32_t *const wq = smem + P.bin_smem_off + (tid >> 5) * P.bin_warp_words; /* binned scatter only */
    uint32_t blk_next = 0, blk_end = 0; /* no pool blocks in hand */
@@ -535,8 +593,9 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
        * so every 4 iterations the CTA's walkers are dealt out anew: thread (warp w, lane l)
        * takes over the walker of thread (l * W + w) of W warps - each warp's 32 walkers come
        * from all the others. Not with xaos (the pick depends on the walker's last xform), not
-       * for CTAs of fewer than 4 warps. */
-      const bool wu = P.warp_uniform && !binned && !(c_samp(ji - P.job_base).lay.x & F3B_HF_XAOS);
+       * for CTAs of fewer than 4 warps. A template parameter: merely carrying the code cost the
+       * kernels that do not use it 6 %. */
+      const bool wu = WU && !binned && !(c_samp(ji - P.job_base).lay.x & F3B_HF_XAOS);
       const bool lockstep = binned || wu;
       if (chain >= job.n_chains && !lockstep) continue;
 
@@ -680,15 +739,23 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
          if (SIMPLE || (hf & HF_PLOT_READY)) {
             /* step lookup, every xform fully visible, dmap truncated on the host */
             pi = pi < 0 ? 0 : (pi >= cmap_size - 1 ? cmap_size - 1 : pi);
+            if (AGG && P.bin_regions) {
+               /* a record carries the colour as four bytes: taken from the rgba8 copy of the
+                * table when the host made one (whole numbers <= 255) */
+               uint32_t rgba;
+               if (hf & HF_PAL_PACKED) rgba = reinterpret_cast<const uint32_t *>(dmap + 256)[pi];
+               else {
+                  col = dmap[pi];
+                  rgba = (uint32_t)col.x | ((uint32_t)col.y << 8) | ((uint32_t)col.z << 16) | ((uint32_t)col.w << 24);
+               }
+               bin_r = __umulhi((uint32_t)iy, P.bin_row_magic);
+               bin_a = (((uint32_t)iy - bin_r * P.bin_region_rows) * (uint32_t)P.lay.pitch + (uint32_t)ix) | (255u << 24);
+               bin_c = rgba;
+               continue;
+            }
             col = dmap[pi];
             float cnt = 255.0f;
             if (AGG) {
-               if (P.bin_regions) {
-                  bin_r = __umulhi((uint32_t)iy, P.bin_row_magic);
-                  bin_a = (((uint32_t)iy - bin_r * P.bin_region_rows) * (uint32_t)P.lay.pitch + (uint32_t)ix) | (255u << 24);
-                  bin_c = (uint32_t)col.x | ((uint32_t)col.y << 8) | ((uint32_t)col.z << 16) | ((uint32_t)col.w << 24);
-                  continue;
-               }
                float4 tc = col;
                float tn = cnt;
                const bool mine = f3b_bump_aggregate(P, bidx - rep_off, (unsigned long long)bidx, &tc, &tn,
@@ -699,6 +766,10 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
             }
             f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
             if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
+#ifndef F3B_NO_REPORT
+            if (!AGG && ((((uint32_t)i ^ tid) & (F3B_SAMPLE_EVERY - 1)) == 0) && report)
+               s_ring.entry[atomicAdd(&s_ring.head, 1u) % F3B_SAMPLE_RING] = (uint32_t)bidx;
+#endif
             continue;
          }
          if (hf & HF_PAL_LINEAR) {
@@ -752,6 +823,10 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
          }
          f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
          if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
+#ifndef F3B_NO_REPORT
+         if (!AGG && ((((uint32_t)i ^ tid) & (F3B_SAMPLE_EVERY - 1)) == 0) && report)
+            s_ring.entry[atomicAdd(&s_ring.head, 1u) % F3B_SAMPLE_RING] = (uint32_t)bidx;
+#endif
          } while (0);
          if (binned) {
             __syncwarp();
@@ -902,19 +977,23 @@ int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes, bool simple) {
    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
    static bool attrs_set = false; /* per process and device 0..n alike: the attribute is per function */
    if (!attrs_set) attrs_set = true;
-   cudaFuncSetAttribute(f3b_iterate_kernel<true, false, false>, at, smax);
-   cudaFuncSetAttribute(f3b_iterate_kernel<false, false, false>, at, smax);
-   cudaFuncSetAttribute(f3b_iterate_kernel<true, true, false>, at, smax);
-   cudaFuncSetAttribute(f3b_iterate_kernel<false, true, false>, at, smax);
-   cudaFuncSetAttribute(f3b_iterate_kernel<true, false, true>, at, smax);
-   cudaFuncSetAttribute(f3b_iterate_kernel<false, false, true>, at, smax);
-   cudaFuncSetAttribute(f3b_iterate_kernel<true, true, true>, at, smax);
-   cudaFuncSetAttribute(f3b_iterate_kernel<false, true, true>, at, smax);
+#define F3B_SET(C, S, A)                                                        \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, A, false>, at, smax);          \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, A, true>, at, smax)
+   F3B_SET(true, false, false);
+   F3B_SET(false, false, false);
+   F3B_SET(true, true, false);
+   F3B_SET(false, true, false);
+   F3B_SET(true, false, true);
+   F3B_SET(false, false, true);
+   F3B_SET(true, true, true);
+   F3B_SET(false, true, true);
+#undef F3B_SET
    /* group_size counts the walkers; the CTA has one more warp (the sweeper). The SIMPLE and the
     * generic instantiations have different register budgets (3 and 2 CTAs per SM). */
-   cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, true, true>,
+   cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, true, true, true>,
                                                                           group_size + 32, smem_bytes)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, true>,
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, true, true>,
                                                                           group_size + 32, smem_bytes);
    if (e != cudaSuccess) return 0;
    return nb;
@@ -928,7 +1007,11 @@ int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_co
    for (int i = 0; i < n_consts; i++) p.samp[i] = consts[i];
    p.chain_threads = (uint32_t)group_size;
    const int threads = group_size + (p.sweep_on ? 32 : 0);
-#define F3B_LAUNCH(C, S, A) f3b_iterate_kernel<C, S, A><<<grid_blocks, threads, smem_bytes, stream>>>(p)
+#define F3B_LAUNCH(C, S, A)                                                                          \
+   do {                                                                                              \
+      if (p.warp_uniform) f3b_iterate_kernel<C, S, A, true><<<grid_blocks, threads, smem_bytes, stream>>>(p); \
+      else f3b_iterate_kernel<C, S, A, false><<<grid_blocks, threads, smem_bytes, stream>>>(p);     \
+   } while (0)
    const int which = (count_channel ? 4 : 0) | (simple ? 2 : 0) | (aggregate ? 1 : 0);
    switch (which) {
    case 0: F3B_LAUNCH(false, false, false); break;

@@ -546,7 +546,7 @@ int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_
 
    /* dmap (rect.c:778-782): palette * WHITE_LEVEL * temporal filter weight */
    o = (o + 3) & ~(size_t)3;
-   if (o + 256 * 4 > cap) return 2;
+   if (o + 256 * 5 > cap) return 2;
    w[F3B_H_OFF_PALETTE] = (uint32_t)o;
    /* With step lookup, alpha == 1 and weight == 1 the alpha sum equals the count sum hit
     * by hit. Linear lookup blends alpha in floating point (rect.c:482-485), which the
@@ -557,16 +557,21 @@ int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_
    int plot_ready = (cp->palette_mode != flam3_palette_mode_linear);
    for (int i = 0; i < cp->num_xforms; i++)
       if (cp->xform[i].opacity != 1.0) plot_ready = 0;
-   w[F3B_H_PLOT] = plot_ready ? F3B_PLOT_READY : 0u;
+   int packed = plot_ready && floor_adds;
    for (int j = 0; j < 256; j++) {
+      uint32_t rgba = 0;
       for (int k = 0; k < 4; k++) {
          double c = cp->palette[j].color[k] * 255.0 * color_scalar;
          if (plot_ready && floor_adds) c = floor(c); /* what the integer bucket add keeps */
          w[o + j * 4 + k] = f2u(c);
+         if (!(c >= 0.0 && c <= 255.0)) packed = 0;
+         else rgba |= (uint32_t)c << (8 * k);
       }
+      w[o + 1024 + j] = rgba;
       if (cp->palette[j].color[3] * 255.0 * color_scalar != 255.0) alpha_ok = 0;
    }
-   o += 256 * 4;
+   w[F3B_H_PLOT] = (plot_ready ? F3B_PLOT_READY : 0u) | (packed ? F3B_PLOT_PACKED : 0u);
+   o += 256 * 5;
    w[F3B_H_WORDS] = (uint32_t)o;
    *used = o;
    if (count_is_alpha) *count_is_alpha = alpha_ok;

@@ -36,7 +36,7 @@ enum {
    F3B_H_RCX, F3B_H_RCY,                               /* f32 rot_center */
    F3B_H_OFF_CHOOSER,   /* u32 -> u32 cum[rows][nstd]: entries of the 16384 table <= j */
    F3B_H_OFF_XFTAB,     /* u32 -> u32 word offset of each xform record [nxf] */
-   F3B_H_OFF_PALETTE,   /* u32 -> float4 dmap[256] (16-byte aligned) */
+   F3B_H_OFF_PALETTE,   /* u32 -> float4 dmap[256] (16-byte aligned), then u32 rgba8[256] */
    F3B_H_NXF,           /* u32 number of xform records (nstd + 1 if final present) */
    F3B_H_PLOT,          /* u32 F3B_PLOT_*: what the bucket bump may skip */
    F3B_H_CHOOSER_STRIDE, /* u32 entries per chooser row: nstd rounded up to 4, pad = 16384 */
@@ -49,6 +49,12 @@ enum {
  * and the dmap entries were already truncated on the host when the buckets are integer
  * (bits 32/33), so a hit adds dmap[i] as is (rect.c:499-505 with p[3]==1). */
 #define F3B_PLOT_READY 1u
+/* PACKED (only with READY): every dmap entry is a whole number in [0, 255], and a second copy of
+ * the table follows the float4 one at F3B_H_OFF_PALETTE + 1024: 256 words r | g << 8 | b << 16 |
+ * a << 24: what a record of the binned scatter carries. (For the direct path the 4-byte lookup
+ * was measured and lost: fewer shared-memory wavefronts, but the eight instructions that turn
+ * bytes into floats cost the issue-bound loop 5 %, profiles/r02_palette_rgba8_ab.txt.) */
+#define F3B_PLOT_PACKED 2u
 
 /* xform record: word indices relative to the record start (all f32 unless noted) */
 /* Records start on a 16-byte boundary. The first 12 words are what every application of

@@ -98,7 +98,7 @@ def test_packed_sample_layout(gpu, flame0):
     assert f(g.ptr, 0, 1, w.ctypes.data, w.size, C.byref(used)) == 0
     fl = w.view(np.float32)
     assert w[1] == 4 and w[2] == 0xFFFFFFFF and w[3] == 0   # 4 xforms, no final, no xaos
-    assert w[23] == 4 and w[24] == 1 and w[25] == 4          # nxf, plot-ready, chooser stride
+    assert w[23] == 4 and w[24] == 3 and w[25] == 4          # nxf, plot-ready | packed, chooser stride
     xftab = w[w[21]: w[21] + 4]
     assert all(int(o) % 4 == 0 for o in xftab)
     # xform 0: spherical only -> fixed-function slot, empty variation list
@@ -107,6 +107,11 @@ def test_packed_sample_layout(gpu, flame0):
     assert abs(fl[rec + 0] - (-0.681206)) < 1e-6 and abs(fl[rec + 3] - (-0.0779465)) < 1e-6
     pal = fl[w[22]: w[22] + 1024].reshape(256, 4)
     assert np.all(pal == np.floor(pal)) and np.all(pal[:, 3] == 255.0)
+    # the rgba8 copy behind it (F3B_PLOT_PACKED): the same whole numbers, a byte each
+    rgba = w[w[22] + 1024: w[22] + 1280]
+    assert int(w[0]) == int(w[22]) + 1280
+    for k in range(4):
+        assert np.array_equal((rgba >> (8 * k)) & 0xFF, pal[:, k].astype(np.uint32))
     # the chooser row: four equal weights -> 4096 / 8192 / 12288 / 16384
     assert list(w[w[20]: w[20] + 4]) == [4096, 8192, 12288, 16384]
 

@@ -55,5 +55,5 @@ def test_standalone_renderer_png(tmp_path):
     _run(OWN, tmp, "p_", os.path.join(ROOT, "tests", "golden", "test_flame0.flam3"),
          format="png", bpc="16", transparency="1", qs="0.5")
     data = open(os.path.join(tmp, "p_00000.png"), "rb").read()
-    assert data[:8] == b"\\x89PNG\\r\\n\\x1a\\n"
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
     assert data[16:26] == (640).to_bytes(4, "big") + (480).to_bytes(4, "big") + bytes([16, 6])

@@ -26,7 +26,7 @@ def t(env, reps=5):
     return ms, ctx.exactness() + ("lost seen by cold/hot/merge", out[10], out[11], out[12], "hot entries", out[8] >> 32)
 hist = {}
 for rnd in range(2):
-    for name, env in (("off", {"F3B_SWEEP": "0"}), ("auto", {}), ("flat", {"F3B_SWEEP_GAP_US": "1"}),
+    for name, env in (("off", {"F3B_SWEEP": "0"}), ("auto", {}), ("norep", {"F3B_SWEEP_MODE": "3"}), ("flat", {"F3B_SWEEP_GAP_US": "1"}),
                       ("4ms", {"F3B_SWEEP_GAP_US": "4000"}), ("idle", {"F3B_SWEEP_MODE": "0"}),
                       ("cold", {"F3B_SWEEP_MODE": "1"}), ("hot", {"F3B_SWEEP_MODE": "2"})):
         ms, ex = t(env)
