@@ -634,7 +634,9 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
       if (ge && atof(ge) > 0.0) gap_us = atof(ge);
       P.sweep_gap_ns = gap_us * 1e3 > 4e9 ? 4000000000u : (uint32_t)(gap_us * 1e3);
       const char *me = getenv("F3B_SWEEP_MODE");
-      P.sweep_mode = me ? (uint32_t)atoi(me) : 11u;
+      /* histograms beyond L2: the cold passes are slow beside the walkers' DRAM scatter, the
+       * walkers report a sample of the entries they add to (kernel MODE 2) */
+      P.sweep_mode = me ? (uint32_t)atoi(me) : (plane_bytes > 112e6 ? 11u : 3u);
       if (P.sweep_on) {
          CK(cudaMemsetAsync(P.sweep_state, 0, 4 * sizeof(unsigned int), ctx->stream));
          CK(cudaMemsetAsync(ctx->hot_bitmap.p, 0,

@@ -50,5 +50,6 @@ int f3b_debug_chooser_counts(double dr, unsigned n, const double *thr, int nthr,
 /* ISAAC as the reference runs it on LP64 (isaac.c + isaac.h): next 32-bit draw from ctx. */
 unsigned long f3b_isaac_next(randctx *ctx);
 void f3b_isaac_refill(randctx *ctx);
+void f3b_isaac_skip(randctx *ctx, unsigned long n);
 
 #endif

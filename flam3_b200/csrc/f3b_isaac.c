@@ -49,3 +49,16 @@ unsigned long f3b_isaac_next(randctx *c) {
    }
    return c->randrsl[c->randcnt];
 }
+
+/* n calls of f3b_isaac_next whose results nobody looks at: whole pools at a time */
+void f3b_isaac_skip(randctx *c, unsigned long n) {
+   while (n > 0) {
+      if (c->randcnt == 0) {
+         f3b_isaac_refill(c);
+         c->randcnt = N;
+      }
+      const unsigned long take = n < (unsigned long)c->randcnt ? n : (unsigned long)c->randcnt;
+      c->randcnt -= (ub4)take;
+      n -= take;
+   }
+}

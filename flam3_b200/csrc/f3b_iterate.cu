@@ -529,9 +529,15 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
 /* SIMPLE: every temporal sample of the launch has <= 4 xforms, no xaos, no final xform, a
  * step palette and fully visible xforms (the classic flame): the flag tests fold away and
  * the xform pick is three compares on a packed table from the constant bank. */
-template <bool COUNT, bool SIMPLE, bool AGG, bool WU>
+template <bool COUNT, bool SIMPLE, int MODE, bool WU>
 __global__ void __launch_bounds__(F3B_BLOCK + 32, SIMPLE ? F3B_ITER_MIN_BLOCKS : F3B_GENERIC_MIN_BLOCKS)
 f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
+   /* MODE 0: one vector reduction per hit; 1 (AGG): lanes of a warp that hit the same bucket add
+    * once (also the binned scatter); 2 (REPORT): as 0, and the walkers report a sample of the
+    * entries they add to (histograms in DRAM). Instantiations, because merely carrying the few
+    * instructions of 2 costs the 72-register loop of 0 six per cent. */
+   constexpr bool AGG = MODE == 1;
+   constexpr bool REPORT = MODE == 2;
    extern __shared__ __align__(16) uint32_t smem[];
    const float *sf = reinterpret_cast<const float *>(smem);
    __shared__ int s_done;
@@ -550,7 +556,6 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
          return;
       }
    }
-   const bool report = P.sweep_on && (P.sweep_mode & 8u);
    const size_t rep_off = (size_t)(blockIdx.x % P.lay.replicas) * P.lay.replica_stride;
    uint32_t *const wq = smem + P.bin_smem_off + (tid >> 5) * P.bin_warp_words; /* binned scatter only */
    uint32_t blk_next = 0, blk_end = 0; /* no pool blocks in hand */
@@ -766,10 +771,8 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
             }
             f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
             if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
-#ifndef F3B_NO_REPORT
-            if (!AGG && ((((uint32_t)i ^ tid) & (F3B_SAMPLE_EVERY - 1)) == 0) && report)
+            if (REPORT && (((uint32_t)i ^ tid) & (F3B_SAMPLE_EVERY - 1)) == 0)
                s_ring.entry[atomicAdd(&s_ring.head, 1u) % F3B_SAMPLE_RING] = (uint32_t)bidx;
-#endif
             continue;
          }
          if (hf & HF_PAL_LINEAR) {
@@ -823,10 +826,8 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
          }
          f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
          if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
-#ifndef F3B_NO_REPORT
-         if (!AGG && ((((uint32_t)i ^ tid) & (F3B_SAMPLE_EVERY - 1)) == 0) && report)
+         if (REPORT && (((uint32_t)i ^ tid) & (F3B_SAMPLE_EVERY - 1)) == 0)
             s_ring.entry[atomicAdd(&s_ring.head, 1u) % F3B_SAMPLE_RING] = (uint32_t)bidx;
-#endif
          } while (0);
          if (binned) {
             __syncwarp();
@@ -977,23 +978,23 @@ int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes, bool simple) {
    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
    static bool attrs_set = false; /* per process and device 0..n alike: the attribute is per function */
    if (!attrs_set) attrs_set = true;
-#define F3B_SET(C, S, A)                                                        \
-   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, A, false>, at, smax);          \
-   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, A, true>, at, smax)
-   F3B_SET(true, false, false);
-   F3B_SET(false, false, false);
-   F3B_SET(true, true, false);
-   F3B_SET(false, true, false);
-   F3B_SET(true, false, true);
-   F3B_SET(false, false, true);
-   F3B_SET(true, true, true);
-   F3B_SET(false, true, true);
+#define F3B_SET(C, S)                                                           \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 0, false>, at, smax);          \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 0, true>, at, smax);           \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 1, false>, at, smax);          \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 1, true>, at, smax);           \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 2, false>, at, smax);          \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 2, true>, at, smax)
+   F3B_SET(true, false);
+   F3B_SET(false, false);
+   F3B_SET(true, true);
+   F3B_SET(false, true);
 #undef F3B_SET
    /* group_size counts the walkers; the CTA has one more warp (the sweeper). The SIMPLE and the
     * generic instantiations have different register budgets (3 and 2 CTAs per SM). */
-   cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, true, true, true>,
+   cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, true, 1, true>,
                                                                           group_size + 32, smem_bytes)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, true, true>,
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, 1, true>,
                                                                           group_size + 32, smem_bytes);
    if (e != cudaSuccess) return 0;
    return nb;
@@ -1007,22 +1008,30 @@ int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_co
    for (int i = 0; i < n_consts; i++) p.samp[i] = consts[i];
    p.chain_threads = (uint32_t)group_size;
    const int threads = group_size + (p.sweep_on ? 32 : 0);
-#define F3B_LAUNCH(C, S, A)                                                                          \
+   /* the sweeper drains the walkers' reports only where the walkers make them */
+   const int mode = aggregate ? 1 : ((p.sweep_on && (p.sweep_mode & 8u)) ? 2 : 0);
+   const uint32_t sweep_mode_asked = p.sweep_mode;
+   if (mode != 2) p.sweep_mode &= ~8u;
+#define F3B_LAUNCH_M(C, S, M)                                                                        \
    do {                                                                                              \
-      if (p.warp_uniform) f3b_iterate_kernel<C, S, A, true><<<grid_blocks, threads, smem_bytes, stream>>>(p); \
-      else f3b_iterate_kernel<C, S, A, false><<<grid_blocks, threads, smem_bytes, stream>>>(p);     \
+      if (p.warp_uniform) f3b_iterate_kernel<C, S, M, true><<<grid_blocks, threads, smem_bytes, stream>>>(p); \
+      else f3b_iterate_kernel<C, S, M, false><<<grid_blocks, threads, smem_bytes, stream>>>(p);     \
    } while (0)
-   const int which = (count_channel ? 4 : 0) | (simple ? 2 : 0) | (aggregate ? 1 : 0);
-   switch (which) {
-   case 0: F3B_LAUNCH(false, false, false); break;
-   case 1: F3B_LAUNCH(false, false, true); break;
-   case 2: F3B_LAUNCH(false, true, false); break;
-   case 3: F3B_LAUNCH(false, true, true); break;
-   case 4: F3B_LAUNCH(true, false, false); break;
-   case 5: F3B_LAUNCH(true, false, true); break;
-   case 6: F3B_LAUNCH(true, true, false); break;
-   default: F3B_LAUNCH(true, true, true); break;
+#define F3B_LAUNCH(C, S)                 \
+   do {                                  \
+      if (mode == 1) F3B_LAUNCH_M(C, S, 1);      \
+      else if (mode == 2) F3B_LAUNCH_M(C, S, 2); \
+      else F3B_LAUNCH_M(C, S, 0);                \
+   } while (0)
+   if (count_channel) {
+      if (simple) F3B_LAUNCH(true, true);
+      else F3B_LAUNCH(true, false);
+   } else {
+      if (simple) F3B_LAUNCH(false, true);
+      else F3B_LAUNCH(false, false);
    }
+#undef F3B_LAUNCH_M
+   p.sweep_mode = sweep_mode_asked;
 #undef F3B_LAUNCH
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
 }

@@ -377,14 +377,143 @@ static void packed_free(packed_batch *b) {
    b->slot_words = 0;
 }
 
-static void pack_one(pack_job *j, int ts, uint32_t *scratch, flam3_genome *cp) {
+/* ---- the genome of one temporal sample ---------------------------------------------------
+ * flam3_interpolate (flam3.c:717-802) for a time between two key frames: make aligned copies
+ * of the two genomes (flam3_align: pad to the same xforms), reset the result, and blend
+ * everything with flam3_interpolate_n (interpolation.c:373-708). An animation frame asks for
+ * 1000 such genomes, and that was its bottleneck: ~25 us each, 80 % of the host's work per
+ * temporal sample, against ~3000 iterations on the GPU. Two thirds of it does not depend on
+ * the time and is done once per worker and segment here:
+ *   - the aligned copies (5.6 us);
+ *   - the palettes' way into HSV: interpolate_n converts all 256 entries of both key frames
+ *     (three rgb2hsv per entry) for every sample. The copies are switched to the "sweep"
+ *     palette mode, which makes interpolate_n copy entries instead, and the blend is done
+ *     here from HSV values kept with the copies - the same operations on the same numbers,
+ *     with the reference's own rgb2hsv / hsv2rgb (bit-identical, tests/test_cpu_boundary.py).
+ * Smooth (Catmull-Rom) segments and single genomes go through flam3_interpolate as before.
+ * The symbols are weak: a program linked without libflam3's interpolation.c (tools/f3b-render)
+ * renders single key frames only and never gets here. */
+extern void flam3_align(flam3_genome *dst, flam3_genome *src, int nsrc) __attribute__((weak));
+extern void flam3_interpolate_n(flam3_genome *result, int ncp, flam3_genome *cpi, double *c, double stagger)
+    __attribute__((weak));
+extern void flam3_add_xforms(flam3_genome *cp, int num_to_add, int interp_padding, int final_flag)
+    __attribute__((weak));
+extern void rgb2hsv(double *rgb, double *hsv) __attribute__((weak));
+extern void hsv2rgb(double *hsv, double *rgb) __attribute__((weak));
+
+typedef struct {
+   int i1;       /* the copies are cps[i1], cps[i1 + 1] aligned; -1: none yet */
+   int pal_mode; /* palette_interpolation of the first one (the copy says sweep) */
+   flam3_genome cpi[2];
+   double hsv[2][256][3]; /* of the copies' palettes, the first one's hue moved next to the second's */
+} interp_cache;
+
+static void interp_cache_clear(interp_cache *ic) {
+   if (ic->i1 >= 0) {
+      clear_cp(&ic->cpi[0], 0);
+      clear_cp(&ic->cpi[1], 0);
+   }
+   ic->i1 = -1;
+}
+
+static void f3b_interpolate_cached(flam3_genome *cps, int ncps, double time, flam3_genome *result, interp_cache *ic) {
+   const int have = flam3_align && flam3_interpolate_n && flam3_add_xforms && rgb2hsv && hsv2rgb;
+   int i1 = 0;
+   if (ncps >= 2) { /* flam3.c:729-743 */
+      if (cps[0].time >= time) i1 = 0;
+      else if (cps[ncps - 1].time <= time) i1 = ncps - 2;
+      else {
+         while (cps[i1].time < time) i1++;
+         i1--;
+      }
+   }
+   if (!have || !ic || ncps < 2 || cps[i1].interpolation != flam3_interpolation_linear || getenv("F3B_INTERP_REF")) {
+      flam3_interpolate(cps, ncps, time, 0, result);
+      return;
+   }
+   const int i2 = i1 + 1;
+   if (ic->i1 != i1) {
+      interp_cache_clear(ic);
+      memset(ic->cpi, 0, sizeof(ic->cpi));
+      flam3_align(&ic->cpi[0], &cps[i1], 2);
+      ic->i1 = i1;
+      ic->pal_mode = ic->cpi[0].palette_interpolation;
+      if (ic->pal_mode != flam3_palette_interpolation_sweep) {
+         for (int i = 0; i < 256; i++) {
+            rgb2hsv(ic->cpi[0].palette[i].color, ic->hsv[0][i]);
+            rgb2hsv(ic->cpi[1].palette[i].color, ic->hsv[1][i]);
+            if (ic->pal_mode == flam3_palette_interpolation_hsv_circular) { /* the shorter way round */
+               const double dh = ic->hsv[1][i][0] - ic->hsv[0][i][0];
+               if (dh > 3.0) ic->hsv[0][i][0] += 6.0;
+               else if (dh < -3.0) ic->hsv[0][i][0] -= 6.0;
+            }
+         }
+         ic->cpi[0].palette_interpolation = flam3_palette_interpolation_sweep;
+      }
+   }
+   double c[2];
+   c[0] = (cps[i2].time - time) / (cps[i2].time - cps[i1].time);
+   c[1] = 1.0 - c[0];
+   clear_cp(result, 1);
+   if (ic->cpi[0].final_xform_index >= 0) {
+      flam3_add_xforms(result, ic->cpi[0].num_xforms - 1, 0, 0);
+      flam3_add_xforms(result, 1, 0, 1);
+   } else
+      flam3_add_xforms(result, ic->cpi[0].num_xforms, 0, 0);
+   result->time = time;
+   result->interpolation = flam3_interpolation_linear;
+   result->interpolation_type = ic->cpi[0].interpolation_type;
+   flam3_interpolate_n(result, 2, ic->cpi, c, 0.0);
+   result->palette_interpolation = ic->pal_mode;
+   if (ic->pal_mode == flam3_palette_interpolation_sweep) return;
+   /* interpolation.c:377-455 with the conversions taken out of the loop */
+   double rgb_fraction = 0.0;
+   if (ic->pal_mode == flam3_palette_interpolation_rgb) rgb_fraction = 1.0;
+   else if (ic->pal_mode == flam3_palette_interpolation_hsv_circular) rgb_fraction = ic->cpi[0].hsv_rgb_palette_blend;
+   for (int i = 0; i < 256; i++) {
+      const double *p0 = ic->cpi[0].palette[i].color, *p1 = ic->cpi[1].palette[i].color;
+      double new_rgb[3], new_hsv[3], back[3];
+      for (int k = 0; k < 3; k++) {
+         new_rgb[k] = c[0] * p0[k] + c[1] * p1[k];
+         new_hsv[k] = c[0] * ic->hsv[0][i][k] + c[1] * ic->hsv[1][i][k];
+      }
+      double count = c[0] * p0[3] + c[1] * p1[3];
+      if (p0[3] == 1.0 && p1[3] == 1.0) count = 1.0;
+      double index = c[0] * ic->cpi[0].palette[i].index + c[1] * ic->cpi[1].palette[i].index;
+      hsv2rgb(new_hsv, back);
+      double *out = result->palette[i].color;
+      for (int k = 0; k < 3; k++) out[k] = rgb_fraction * new_rgb[k] + (1.0 - rgb_fraction) * back[k];
+      out[3] = count;
+      for (int k = 0; k < 4; k++) {
+         if (out[k] < 0.0) out[k] = 0.0;
+         if (out[k] > 1.0) out[k] = 1.0;
+      }
+      if (index < 0.0) index = 0.0;
+      if (index > 255.0) index = 255.0;
+      result->palette[i].index = index;
+   }
+}
+
+/* for the parity test: the genome of one time, through the cached path */
+int f3b_debug_interpolate(void *cps, int ncps, double time, void *result) {
+   interp_cache *ic = (interp_cache *)calloc(1, sizeof(interp_cache));
+   if (!ic) return 1;
+   ic->i1 = -1;
+   f3b_interpolate_cached((flam3_genome *)cps, ncps, time, (flam3_genome *)result, ic);
+   const int fast = ic->i1 >= 0;
+   interp_cache_clear(ic);
+   free(ic);
+   return fast ? 0 : 2; /* 2: went through flam3_interpolate */
+}
+
+static void pack_one(pack_job *j, int ts, uint32_t *scratch, flam3_genome *cp, interp_cache *ic) {
    packed_sample *ps = &j->out[ts];
    const int fi = j->batch_num * j->nts + ts;
    if (!scratch) {
       ps->rc = 2;
       return;
    }
-   flam3_interpolate(j->spec->genomes, j->spec->ngenomes, j->spec->time + j->tdeltas[fi], 0, cp);
+   f3b_interpolate_cached(j->spec->genomes, j->spec->ngenomes, j->spec->time + j->tdeltas[fi], cp, ic);
    if (f3b_camera_setup(cp, j->g, &ps->cam)) {
       ps->rc = 3;
       return;
@@ -418,29 +547,67 @@ static void pack_one(pack_job *j, int ts, uint32_t *scratch, flam3_genome *cp) {
 static void *pack_worker(void *arg) {
    pack_job *j = (pack_job *)arg;
    uint32_t *scratch = (uint32_t *)malloc(F3B_MAX_BLOB_WORDS * 4);
+   interp_cache *ic = (interp_cache *)calloc(1, sizeof(interp_cache));
+   if (ic) ic->i1 = -1;
    flam3_genome cp;
    memset(&cp, 0, sizeof(cp));
    for (;;) {
       const int ts = __sync_fetch_and_add(&j->next, 1);
       if (ts >= j->nts) break;
-      pack_one(j, ts, scratch, &cp);
+      pack_one(j, ts, scratch, &cp, ic);
    }
    clear_cp(&cp, 0);
+   if (ic) interp_cache_clear(ic);
+   free(ic);
    free(scratch);
    return NULL;
 }
 
 /* The reference seeds one ISAAC context per worker thread from the frame's context, 16 words
- * each, for every temporal sample (rect.c:858-865). Draw the same words, so that spec->rc
- * ends in the same state, and fold them into the seed of the sample's random streams. */
-static uint64_t draw_sample_seed(flam3_frame *spec, int fi, int nthreads) {
-   uint64_t h = 0x9e3779b97f4a7c15ull ^ (uint64_t)fi;
-   for (int k = 0; k < 16 * nthreads; k++) {
-      h ^= (uint64_t)f3b_isaac_next(&spec->rc) & 0xffffffffull;
-      h *= 0x100000001b3ull;
-      h ^= h >> 29;
-   }
-   return h;
+ * each, for every temporal sample (rect.c:858-865): spec->rc ends 16 * nthreads * samples
+ * words further on, which is part of the call's contract. ISAAC cannot jump: a pool of 16
+ * words costs ~0.1 us of strictly serial work, 1.5 ms for a frame of 1000 temporal samples
+ * at nthreads = 16 - most of what an animation frame took on the host. So only the first 16
+ * words of a batch become seed material for the GPU streams (one thread's worth of the
+ * reference's seeding), and the rest of the advance runs in a thread of its own beside the
+ * packing, the launches and the GPU work; it is joined before the next batch draws and before
+ * flam3_render returns. */
+typedef struct {
+   pthread_t th;
+   int active;
+   randctx *rc;
+   unsigned long n;
+} rc_advance;
+static __thread rc_advance t_advance;
+
+static void *rc_advance_main(void *arg) {
+   rc_advance *a = (rc_advance *)arg;
+   f3b_isaac_skip(a->rc, a->n);
+   return NULL;
+}
+static void rc_advance_join(void) {
+   if (t_advance.active) pthread_join(t_advance.th, NULL);
+   t_advance.active = 0;
+}
+static void rc_advance_start(randctx *rc, unsigned long n) {
+   rc_advance_join();
+   t_advance.rc = rc;
+   t_advance.n = n;
+   if (n >= 16384 && pthread_create(&t_advance.th, NULL, rc_advance_main, &t_advance) == 0) t_advance.active = 1;
+   else f3b_isaac_skip(rc, n);
+}
+static uint64_t mix64(uint64_t z) { /* splitmix64 finaliser */
+   z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+   z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+   return z ^ (z >> 31);
+}
+/* seeds of the batch's temporal samples; spec->rc is final once rc_advance_join() has run */
+static void draw_sample_seeds(flam3_frame *spec, int first_sample, int nts, int nthreads, uint64_t *seeds) {
+   rc_advance_join();
+   uint64_t h = 0x9e3779b97f4a7c15ull;
+   for (int k = 0; k < 16; k++) h = mix64(h ^ ((uint64_t)f3b_isaac_next(&spec->rc) & 0xffffffffull));
+   for (int ts = 0; ts < nts; ts++) seeds[ts] = mix64(h + 0x9e3779b97f4a7c15ull * (uint64_t)(first_sample + ts + 1));
+   rc_advance_start(&spec->rc, 16ul * (unsigned long)nthreads * (unsigned long)nts - 16ul);
 }
 
 static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *tfilter,
@@ -458,7 +625,7 @@ static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *
       uint32_t *scratch = (uint32_t *)malloc(F3B_MAX_BLOB_WORDS * 4);
       flam3_genome cp;
       memset(&cp, 0, sizeof(cp));
-      pack_one(&job, 0, scratch, &cp);
+      pack_one(&job, 0, scratch, &cp, NULL);
       clear_cp(&cp, 0);
       free(scratch);
       job.next = 1;
@@ -489,8 +656,7 @@ static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *
    int started = 0;
    for (int i = 1; i < nthreads; i++)
       if (pthread_create(&th[started], NULL, pack_worker, &job) == 0) started++;
-   /* the ISAAC draws are serial by nature: do them while the workers pack */
-   for (int ts = 0; ts < nts; ts++) seeds[ts] = draw_sample_seed(spec, batch_num * nts + ts, rc_threads);
+   draw_sample_seeds(spec, batch_num * nts, nts, rc_threads, seeds);
    pack_worker(&job);
    for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
    return 0;
@@ -1034,9 +1200,11 @@ int flam3_render(flam3_frame *spec, void *out, int field, int nchan, int transp,
    if (ctx) {
       const randctx rc0 = spec->rc;
       rv = render_locked(ctx, spec, out, field, nchan, transp, stats, g_inject != NULL);
+      rc_advance_join(); /* spec->rc is where the reference would have left it */
       if (rv == -2) { /* a palette with alpha appeared mid-frame: redo with a count plane */
          spec->rc = rc0;
          rv = render_locked(ctx, spec, out, field, nchan, transp, stats, 1);
+         rc_advance_join();
       }
       if (rv < 0) rv = 1;
       slot_release();

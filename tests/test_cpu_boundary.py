@@ -116,6 +116,46 @@ def test_packed_sample_layout(gpu, flame0):
     assert list(w[w[20]: w[20] + 4]) == [4096, 8192, 12288, 16384]
 
 
+@pytest.mark.parametrize("mode", ["hsv_circular", "hsv", "rgb", "sweep", "blend"])
+def test_cached_interpolation_equals_flam3_interpolate(gpu, flame0, flame1, mode):
+    """The genome of a temporal sample (f3b_render.c, f3b_interpolate_cached: aligned copies and
+    the palettes' HSV values kept across the samples of a frame) is byte for byte what
+    flam3_interpolate makes for the same time: genome struct, xform arrays, chaos matrix -
+    inside a segment, on and beyond the key frames, with a final xform on one side only
+    (padding) and for every palette interpolation mode."""
+    from types import SimpleNamespace
+    from flam3_b200.genome_xml import set_flame_attrs
+    from test_cpu_frontend import _raw
+    a = flame0.replace("</flame>", '<finalxform color="0" symmetry="1" linear="0.9" spherical="0.1" '
+                       'coefs="1 0 0 1 0.05 0"/></flame>')
+    b = flame1.replace('time="0"', 'time="100"', 1)
+    extra = {"hsv_circular": {}, "hsv": {"palette_interpolation": "hsv"}, "rgb": {"palette_interpolation": "rgb"},
+             "sweep": {"palette_interpolation": "sweep"},
+             "blend": {"palette_interpolation": "hsv_circular", "hsv_rgb_palette_blend": "0.35"}}[mode]
+    if extra:
+        a, b = set_flame_attrs(a, **extra), set_flame_attrs(b, **extra)
+    c = set_flame_attrs(flame0, **extra).replace('time="0"', 'time="250"', 1) if extra else flame0.replace('time="0"', 'time="250"', 1)
+    g = gpu.parse("<flames>" + a + b + c + "</flames>")
+    assert g.n == 3
+    d = gpu._dll
+    size = gpu.abi_sizes()["flam3_genome"]
+    d.flam3_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
+    d.flam3_interpolate.restype = None
+    d.f3b_debug_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    d.clear_cp.argtypes = [C.c_void_p, C.c_int]
+    for t in (-3.0, 0.0, 0.001, 37.25, 50.0, 99.999, 100.0, 100.5, 180.0, 250.0, 260.0):
+        ra, rb = (C.c_char * size)(), (C.c_char * size)()
+        d.flam3_interpolate(g.ptr, 3, t, 0.0, ra)
+        assert d.f3b_debug_interpolate(g.ptr, 3, t, rb) == 0
+        (ga, xa, ca), = _raw(gpu, SimpleNamespace(ptr=C.addressof(ra), n=1))
+        (gb, xb, cb), = _raw(gpu, SimpleNamespace(ptr=C.addressof(rb), n=1))
+        diff = [i for i in range(len(ga)) if ga[i] != gb[i]]
+        assert not diff, "t=%g: genome bytes differ at %s" % (t, diff[:12])
+        assert ca == cb and np.array_equal(xa, xb), t
+        d.clear_cp(ra, 0)
+        d.clear_cp(rb, 0)
+
+
 def test_shard_rule_partitions_groups():
     from flam3_b200.multigpu import shard_groups
 

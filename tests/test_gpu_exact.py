@@ -112,6 +112,24 @@ def test_headline_frame_is_exact(flame0):
     assert 0.74 * 4147200000 < hits < 0.76 * 4147200000
 
 
+def test_histogram_in_dram_is_exact(flame0):
+    """A 4K oversample-2 still: 7718x4358 buckets, 538 MB of staging - the histogram lives in
+    DRAM, a cold pass of the sweepers over it takes ~8 ms beside the walkers' scatter, and the
+    fullest buckets pass 2^24 in less. What keeps them exact is the walkers' own reports (one in
+    512 of the entries they add to, examined by the CTA's sweeper): without them 13-18 staged
+    values were seen at 2^24 (profiles/r02_sweeper_big_histograms.txt)."""
+    _, gpu, core = libs()
+    gg = gpu.parse(resize(flame0, 3840, 2160, scale=1080, quality=500, oversample=2, temporal_samples=1))
+    ctx = _ctx(gpu, core, gg)
+    h, (lost, sat) = _hist(gpu, ctx, gg, {"F3B_BINNED": "0"}, isaac_seed="dram")
+    assert h.shape[:2] == (4358, 7718)
+    assert h[..., 4].max() > 4 * 2 ** 24
+    assert lost == 0 and sat == 0
+    assert (h[..., 4] % 255 == 0).all()
+    hits = int(h[..., 4].sum() // 255)
+    assert 0.70 * 4147200000 < hits < 0.80 * 4147200000
+
+
 @pytest.mark.parametrize("through", ["merge", "sweepers"])
 def test_uint32_buckets_saturate(flame0, through):
     """Start from buckets 300 below UINT_MAX: wherever the frame adds more than that the
