@@ -563,6 +563,70 @@ static void *pack_worker(void *arg) {
    return NULL;
 }
 
+/* The packers are threads that stay: an animation frame is 2 ms, creating and joining 15
+ * threads for each took a fifth of it. One pool per process; a flam3_render that finds it busy
+ * (several calls at once, F3B_CONTEXTS) packs on its own thread. */
+static struct {
+   pthread_mutex_t mu;
+   pthread_cond_t wake, done;
+   int nworkers;      /* threads created so far */
+   unsigned long gen; /* job generation */
+   pack_job *job;
+   int want, active;  /* helpers asked for / still packing */
+   int busy;          /* a job is posted and not waited for yet */
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, 0, 0, NULL, 0, 0, 0};
+
+static void *pool_main(void *arg) {
+   const int me = (int)(size_t)arg;
+   unsigned long seen = 0;
+   pthread_mutex_lock(&g_pool.mu);
+   for (;;) {
+      while (g_pool.gen == seen) pthread_cond_wait(&g_pool.wake, &g_pool.mu);
+      seen = g_pool.gen;
+      if (me >= g_pool.want) continue;
+      pack_job *job = g_pool.job;
+      pthread_mutex_unlock(&g_pool.mu);
+      pack_worker(job);
+      pthread_mutex_lock(&g_pool.mu);
+      if (--g_pool.active == 0) pthread_cond_signal(&g_pool.done);
+   }
+   return NULL;
+}
+/* hands the job to up to `helpers` pool threads; returns how many took it (0: pool busy) */
+static int pool_post(pack_job *job, int helpers) {
+   pthread_mutex_lock(&g_pool.mu);
+   if (g_pool.busy) {
+      pthread_mutex_unlock(&g_pool.mu);
+      return 0;
+   }
+   while (g_pool.nworkers < helpers) {
+      pthread_t th;
+      pthread_attr_t at;
+      pthread_attr_init(&at);
+      pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+      const int rc = pthread_create(&th, &at, pool_main, (void *)(size_t)g_pool.nworkers);
+      pthread_attr_destroy(&at);
+      if (rc) break;
+      g_pool.nworkers++;
+   }
+   if (helpers > g_pool.nworkers) helpers = g_pool.nworkers;
+   if (helpers > 0) {
+      g_pool.job = job;
+      g_pool.want = g_pool.active = helpers;
+      g_pool.busy = 1;
+      g_pool.gen++;
+      pthread_cond_broadcast(&g_pool.wake);
+   }
+   pthread_mutex_unlock(&g_pool.mu);
+   return helpers;
+}
+static void pool_wait(void) {
+   pthread_mutex_lock(&g_pool.mu);
+   while (g_pool.active) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+   g_pool.busy = 0;
+   pthread_mutex_unlock(&g_pool.mu);
+}
+
 /* The reference seeds one ISAAC context per worker thread from the frame's context, 16 words
  * each, for every temporal sample (rect.c:858-865): spec->rc ends 16 * nthreads * samples
  * words further on, which is part of the call's contract. ISAAC cannot jump: a pool of 16
@@ -651,14 +715,11 @@ static int pack_batch(flam3_frame *spec, const f3b_frame_geom *g, const double *
       if (nthreads > nts / 8) nthreads = nts / 8;
       if (nthreads < 1) nthreads = 1;
    }
-   pthread_t th[64];
    if (nthreads > 64) nthreads = 64;
-   int started = 0;
-   for (int i = 1; i < nthreads; i++)
-      if (pthread_create(&th[started], NULL, pack_worker, &job) == 0) started++;
+   const int helpers = nthreads > 1 ? pool_post(&job, nthreads - 1) : 0;
    draw_sample_seeds(spec, batch_num * nts, nts, rc_threads, seeds);
    pack_worker(&job);
-   for (int i = 0; i < started; i++) pthread_join(th[i], NULL);
+   if (helpers) pool_wait();
    return 0;
 }
 

@@ -111,23 +111,28 @@ def test_variation_image(vid):
     ref, gpu, _, _ = _ctx()
     xml = genome_xml(vid, size=96, quality=40)
     gr, gg = ref.parse(xml), gpu.parse(xml)
-    refs = []
-    for seed in ("va", "vb", "vc"):
-        img, sa, _ = ref.render(gr, isaac_seed=seed, nthreads=1)
+    # The PSNR of two renders of a 96x96 q40 frame is itself a noisy number, with a heavy tail:
+    # one stray hit in an empty region becomes a blob under the widest DE kernel. On the
+    # reference alone it scatters over seed pairs by 9 dB for lazysusan (33.2..42.1) and 14 dB
+    # for bipolar (34.3..48.0); the GPU's pairings scatter the same way around the same centre
+    # (profiles/r02_psnr_statistic_spread.txt, all 99 variations). So: six reference renders
+    # (15 pairs) and four GPU renders (24 GPU-reference pairs), compared through their medians
+    # - within 2 dB (measured: -1.0 dB at worst below 50 dB) - and through their worst pairings,
+    # within 5 dB. Attractors that collapse onto a handful of buckets have almost no
+    # Monte-Carlo noise (ref-vs-ref > 60 dB); there the fp32 walk can land a boundary point in
+    # the neighbouring bucket, which the wide low-density DE kernel turns into a faint blob:
+    # beyond 50 dB (mean error < 1 level) the images are equal for this test.
+    refs, gpus = [], []
+    for seed in "abcdef":
+        img, sa, _ = ref.render(gr, isaac_seed="v" + seed, nthreads=1)
         refs.append(img)
-    g, sg, _ = gpu.render(gg, isaac_seed="va")
-    assert sg["rv"] == 0 and sg["num_iters"] == sa["num_iters"]
-    # The PSNR of two renders of a 96x96 q40 frame is itself a noisy number: for one genome it
-    # scatters by +-3 dB over seed pairs on the reference alone (profiles/r02_psnr_statistic_spread.txt:
-    # eyefish 50.8..56.1 dB ref-vs-ref, 49.7..57.5 gpu-vs-ref, equal means). So three reference
-    # renders: the GPU image must be as close to them on average as they are to each other
-    # (within 2 dB), and its worst pairing within 2.5 dB of their worst. Attractors that
-    # collapse onto a handful of buckets have almost no Monte-Carlo noise (ref-vs-ref > 60 dB);
-    # there the fp32 walk can land a boundary point in the neighbouring bucket, which the wide
-    # low-density DE kernel turns into a faint blob: accept >= 50 dB (mean error < 1 level).
-    rr = [psnr(refs[i], refs[j]) for i in range(3) for j in range(i + 1, 3)]
-    gr_ = [psnr(g, r) for r in refs]
-    assert np.mean(gr_) >= min(np.mean(rr) - 2.0, 50.0), \
-        "%s: gpu-vs-ref %s dB, ref-vs-ref %s dB" % (VAR_NAMES[vid], np.round(gr_, 2), np.round(rr, 2))
-    assert min(gr_) >= min(min(rr) - 2.5, 48.0), \
-        "%s: gpu-vs-ref %s dB, ref-vs-ref %s dB" % (VAR_NAMES[vid], np.round(gr_, 2), np.round(rr, 2))
+    for seed in "abcd":
+        img, sg, _ = gpu.render(gg, isaac_seed="v" + seed)
+        assert sg["rv"] == 0 and sg["num_iters"] == sa["num_iters"]
+        gpus.append(img)
+    rr = [min(psnr(refs[i], refs[j]), 60.0) for i in range(6) for j in range(i + 1, 6)]
+    gv = [min(psnr(g, r), 60.0) for g in gpus for r in refs]
+    msg = "%s: gpu-vs-ref median %.2f min %.2f dB, ref-vs-ref median %.2f min %.2f dB" % (
+        VAR_NAMES[vid], np.median(gv), min(gv), np.median(rr), min(rr))
+    assert np.median(gv) >= min(np.median(rr) - 2.0, 50.0), msg
+    assert min(gv) >= min(min(rr) - 5.0, 46.0), msg
