@@ -529,7 +529,7 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
 /* SIMPLE: every temporal sample of the launch has <= 4 xforms, no xaos, no final xform, a
  * step palette and fully visible xforms (the classic flame): the flag tests fold away and
  * the xform pick is three compares on a packed table from the constant bank. */
-template <bool COUNT, bool SIMPLE, int MODE, bool WU>
+template <bool COUNT, bool SIMPLE, int MODE, bool WU, bool SINGLE>
 __global__ void __launch_bounds__(F3B_BLOCK + 32, SIMPLE ? F3B_ITER_MIN_BLOCKS : F3B_GENERIC_MIN_BLOCKS)
 f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
    /* MODE 0: one vector reduction per hit; 1 (AGG): lanes of a warp that hit the same bucket add
@@ -538,6 +538,10 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
     * instructions of 2 costs the 72-register loop of 0 six per cent. */
    constexpr bool AGG = MODE == 1;
    constexpr bool REPORT = MODE == 2;
+   /* SINGLE: the launch has one temporal sample (every still). Its camera, flags and pick table
+    * are then at fixed offsets of the parameter block and become constant-bank operands of the
+    * instructions that use them, instead of ~20 indexed constant loads and their address
+    * arithmetic per iteration (of ~143 instructions). */
    extern __shared__ __align__(16) uint32_t smem[];
    const float *sf = reinterpret_cast<const float *>(smem);
    __shared__ int s_done;
@@ -600,7 +604,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
        * from all the others. Not with xaos (the pick depends on the walker's last xform), not
        * for CTAs of fewer than 4 warps. A template parameter: merely carrying the code cost the
        * kernels that do not use it 6 %. */
-      const bool wu = WU && !binned && !(c_samp(ji - P.job_base).lay.x & F3B_HF_XAOS);
+      const bool wu = WU && !binned && !(c_samp(SINGLE ? 0u : ji - P.job_base).lay.x & F3B_HF_XAOS);
       const bool lockstep = binned || wu;
       if (chain >= job.n_chains && !lockstep) continue;
 
@@ -626,7 +630,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
       /* Flags, chooser stride and palette size share one register (made opaque, or the
        * compiler splits it into a register per flag and spills them); the blob offsets are
        * fetched from the constant bank where they are used. */
-      uint32_t ci = ji - P.job_base; /* index into c_samp[] */
+      uint32_t ci = SINGLE ? 0u : ji - P.job_base; /* index into c_samp[] */
       uint32_t hf = c_samp(ci).lay.x;
       asm volatile("" : "+r"(hf));
 
@@ -661,7 +665,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
             const uint32_t k = rnd & (F3B_CHOOSER_GRAIN - 1u);
             /* `ci` is redefined opaquely so the constant loads below stay in the loop; hoisted,
              * they would occupy a dozen registers across the variation code */
-            asm volatile("" : "+r"(ci));
+            if (!SINGLE) asm volatile("" : "+r"(ci));
             uint32_t xo;
             if (SIMPLE) {
                /* (k << 18 | 0x3ffff) against (count << 18 | record offset) */
@@ -719,7 +723,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
          if (i < 0) continue;
 
          /* rect.c:419-441: camera */
-         asm volatile("" : "+r"(ci));
+         if (!SINGLE) asm volatile("" : "+r"(ci));
          const float4 bb = c_samp(ci).bounds; /* b0 b1 b2 b3 */
          const float4 cs = c_samp(ci).cs;     /* ws0 hs1 rcx rcy */
          float x = qx, y = qy;
@@ -978,23 +982,27 @@ int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes, bool simple) {
    const cudaFuncAttribute at = cudaFuncAttributeMaxDynamicSharedMemorySize;
    static bool attrs_set = false; /* per process and device 0..n alike: the attribute is per function */
    if (!attrs_set) attrs_set = true;
-#define F3B_SET(C, S)                                                           \
-   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 0, false>, at, smax);          \
-   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 0, true>, at, smax);           \
-   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 1, false>, at, smax);          \
-   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 1, true>, at, smax);           \
-   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 2, false>, at, smax);          \
-   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, 2, true>, at, smax)
+#define F3B_SET1(C, S, M, W)                                                    \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, M, W, false>, at, smax);       \
+   cudaFuncSetAttribute(f3b_iterate_kernel<C, S, M, W, true>, at, smax)
+#define F3B_SET(C, S)          \
+   F3B_SET1(C, S, 0, false);   \
+   F3B_SET1(C, S, 0, true);    \
+   F3B_SET1(C, S, 1, false);   \
+   F3B_SET1(C, S, 1, true);    \
+   F3B_SET1(C, S, 2, false);   \
+   F3B_SET1(C, S, 2, true)
    F3B_SET(true, false);
    F3B_SET(false, false);
    F3B_SET(true, true);
    F3B_SET(false, true);
 #undef F3B_SET
+#undef F3B_SET1
    /* group_size counts the walkers; the CTA has one more warp (the sweeper). The SIMPLE and the
     * generic instantiations have different register budgets (3 and 2 CTAs per SM). */
-   cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, true, 1, true>,
+   cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, true, 1, true, false>,
                                                                           group_size + 32, smem_bytes)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, 1, true>,
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, 1, true, false>,
                                                                           group_size + 32, smem_bytes);
    if (e != cudaSuccess) return 0;
    return nb;
@@ -1012,10 +1020,15 @@ int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_co
    const int mode = aggregate ? 1 : ((p.sweep_on && (p.sweep_mode & 8u)) ? 2 : 0);
    const uint32_t sweep_mode_asked = p.sweep_mode;
    if (mode != 2) p.sweep_mode &= ~8u;
-#define F3B_LAUNCH_M(C, S, M)                                                                        \
+#define F3B_LAUNCH_W(C, S, M, W)                                                                     \
    do {                                                                                              \
-      if (p.warp_uniform) f3b_iterate_kernel<C, S, M, true><<<grid_blocks, threads, smem_bytes, stream>>>(p); \
-      else f3b_iterate_kernel<C, S, M, false><<<grid_blocks, threads, smem_bytes, stream>>>(p);     \
+      if (n_consts == 1) f3b_iterate_kernel<C, S, M, W, true><<<grid_blocks, threads, smem_bytes, stream>>>(p); \
+      else f3b_iterate_kernel<C, S, M, W, false><<<grid_blocks, threads, smem_bytes, stream>>>(p);  \
+   } while (0)
+#define F3B_LAUNCH_M(C, S, M)                    \
+   do {                                          \
+      if (p.warp_uniform) F3B_LAUNCH_W(C, S, M, true); \
+      else F3B_LAUNCH_W(C, S, M, false);         \
    } while (0)
 #define F3B_LAUNCH(C, S)                 \
    do {                                  \
@@ -1031,6 +1044,7 @@ int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_co
       else F3B_LAUNCH(false, false);
    }
 #undef F3B_LAUNCH_M
+#undef F3B_LAUNCH_W
    p.sweep_mode = sweep_mode_asked;
 #undef F3B_LAUNCH
    return cudaGetLastError() == cudaSuccess ? 1 : 0;
