@@ -258,11 +258,22 @@ int f3b_sync(f3b_ctx *ctx) {
  * `replicas` different slices; the copies are summed before anything reads them. Replicas
  * are used as long as they all stay L2-resident (F3B_HIST_REPLICAS overrides). */
 static F3HistLayout hist_layout_for(int width, int height, int count_channel, size_t *elems) {
-   F3HistLayout L = {width, 1u, 0};
+   F3HistLayout L = {width, 1u, 0, 0u, 1u, 1u};
    const char *e = getenv("F3B_HIST_PITCH");
    if (e && atoi(e) >= width) L.pitch = atoi(e);
    const size_t buckets = (size_t)L.pitch * height;
-   L.replica_stride = (buckets + 63) & ~(size_t)63;
+   L.replica_stride = (buckets + 4095) & ~(size_t)4095; /* whole scramble blocks (<= 2^12 entries) */
+   {
+      /* scrambled staging layout: blocks of 256 entries = 4 KB (F3B_HIST_SCRAMBLE=bits, 0: plain) */
+      int bits = 8;
+      const char *se = getenv("F3B_HIST_SCRAMBLE");
+      if (se && atoi(se) >= 0 && atoi(se) <= 12) bits = atoi(se);
+      L.smask = (1u << bits) - 1u;
+      L.smul = 0x9E3779B1u;
+      uint32_t inv = L.smul; /* Newton: inverse of an odd number modulo 2^32 */
+      for (int i = 0; i < 5; i++) inv *= 2u - L.smul * inv;
+      L.sinv = inv;
+   }
    const size_t plane_bytes = L.replica_stride * (sizeof(float4) + (count_channel ? sizeof(float) : 0));
    /* all copies must stay in the 126 MB L2: 3 copies at 1080p (102 MB), 4 below ~26 MB */
    size_t k = (104u << 20) / (plane_bytes ? plane_bytes : 1);
@@ -318,10 +329,16 @@ int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel, int 
       }
       /* the staging planes keep their full size: f3b_iterate decides per frame which path
        * fills them (the tile of the binned path is their first bin_rows rows) */
-      if (binned) lay.replicas = 1;
+      if (binned) {
+         lay.replicas = 1;
+         lay.smask = 0; /* the tile of the binned scatter is addressed by the records: plain layout */
+      }
       ctx->bin_forced = binned && be != nullptr;
    }
    const size_t nalloc = lay.replica_stride * lay.replicas;
+   /* staging entries are indexed in 32 bits by the walkers, the hot list and the binned records
+    * (2^32 buckets would be 64 GB of staging) */
+   if (nalloc >= 0xffffffffull) return fail(ctx, "bucket grid %dx%d too large", width, height);
    const void *before[2] = {ctx->hist_color.p, ctx->hist_count.p};
    if (ensure(ctx, ctx->hist_color, nalloc * sizeof(float4))) return 1;
    if (ensure(ctx, ctx->accum, n * sizeof(float4))) return 1;
@@ -736,8 +753,11 @@ int f3b_iterate(f3b_ctx *ctx, const void *blobs, size_t blob_bytes, f3b_job *job
          c.rot = make_float4(f[F3B_H_ROT00], f[F3B_H_ROT01], f[F3B_H_ROT10], f[F3B_H_ROT11]);
          const uint32_t *cum = w + w[F3B_H_OFF_CHOOSER];
          c.cum = make_uint4(cum[0], cum[1], cum[2], cum[3]);
+         bool any_post = false;
+         for (uint32_t q = 0; q < w[F3B_H_NXF]; q++)
+            if (w[w[F3B_H_XF_BASE] + q * w[F3B_H_XF_STRIDE] + F3B_X_FLAGS] & F3B_XF_HAS_POST) any_post = true;
          const uint32_t hf =
-             (w[F3B_H_XAOS] ? F3B_HF_XAOS : 0u) | (w[F3B_H_ROTATE] ? F3B_HF_ROTATE : 0u) |
+             (any_post ? F3B_HF_ANY_POST : 0u) | (w[F3B_H_XAOS] ? F3B_HF_XAOS : 0u) | (w[F3B_H_ROTATE] ? F3B_HF_ROTATE : 0u) |
              ((w[F3B_H_PLOT] & F3B_PLOT_READY) ? F3B_HF_PLOT_READY : 0u) |
              ((w[F3B_H_PLOT] & F3B_PLOT_PACKED) ? F3B_HF_PAL_PACKED : 0u) |
              (w[F3B_H_PALMODE] ? F3B_HF_PAL_LINEAR : 0u) | ((int)w[F3B_H_FINAL] >= 0 ? F3B_HF_FINAL : 0u) |

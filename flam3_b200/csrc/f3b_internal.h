@@ -21,10 +21,25 @@ struct F3HistLayout {
    int pitch;
    uint32_t replicas;
    size_t replica_stride;
+   /* Where bucket b (= x + pitch * y) sits inside a STAGING copy: its low bits are multiplied by
+    * an odd constant, a bijection of every aligned block of smask + 1 entries (replica_stride is
+    * a multiple of it). An attractor's hits cluster on neighbouring buckets; in the plain layout
+    * those are the same 32-byte sectors and 128-byte lines, whose reductions L2 serialises. The
+    * scrambled layout puts neighbours 2.8 KB apart: C2's chaos game 24.0 -> 18.2 ms for the same
+    * instruction stream (profiles/r02_staging_scramble_ab.txt). smask = 0: plain layout. The exact
+    * buckets, and everything after the chaos game, stay in the plain layout. */
+   uint32_t smask, smul, sinv;
 };
 #ifdef __CUDACC__
 __device__ __forceinline__ size_t f3b_hist_index(const F3HistLayout &L, int x, int y) {
    return (size_t)x + (size_t)L.pitch * (size_t)y;
+}
+/* bucket -> entry of a staging copy, and back */
+__device__ __forceinline__ uint32_t f3b_stage_index(const F3HistLayout &L, uint32_t b) {
+   return (b & ~L.smask) | ((b * L.smul) & L.smask);
+}
+__device__ __forceinline__ uint32_t f3b_stage_bucket(const F3HistLayout &L, uint32_t s) {
+   return (s & ~L.smask) | ((s * L.sinv) & L.smask);
 }
 #endif
 
@@ -96,6 +111,7 @@ struct F3ConstSample {
 #define F3B_HF_FINAL 16u
 #define F3B_HF_CHOOSER_CONST 32u /* <= 4 xforms, no xaos: thresholds come from samp[].cum */
 #define F3B_HF_PAL_PACKED 64u    /* the rgba8 copy of the dmap may be used (F3B_PLOT_PACKED) */
+#define F3B_HF_ANY_POST 128u     /* some xform of the sample has a post affine */
 /* temporal samples per launch: 296 x 96 B = 27.75 KB of the 32 KB parameter space that CUDA
  * 12.1+ gives sm_70+ kernels. An animation frame with 1000 temporal samples is 4 launches
  * (on side streams, so they overlap). */

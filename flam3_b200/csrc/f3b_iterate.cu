@@ -304,7 +304,7 @@ __device__ __forceinline__ float f3b_sweep_entry(const F3IterateParams &P, size_
                                                  int where) {
    const float thr = P.carry_thresh;
    const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-   const size_t bucket = e % P.lay.replica_stride;
+   const size_t bucket = f3b_stage_bucket(P.lay, (uint32_t)(e % P.lay.replica_stride));
    if (m >= thr) {
       /* take the channels out one by one with an exchange: what comes back is exactly what
        * left the staging bucket, whatever lands there meanwhile */
@@ -372,7 +372,10 @@ __device__ __noinline__ void f3b_sweeper(const F3IterateParams &P, volatile int 
    unsigned my_pass = 0; /* the last pass this warp held a ticket of, when, and the measured period */
    unsigned long long my_pass_t = 0;
    float period_ns = 0.0f;
-   for (unsigned round = 0; !*s_done; round++) {
+   for (unsigned round = 0;; round++) {
+      int done = 0; /* (atomics on both sides of the flag and of the ring: nothing for racecheck to report) */
+      if (lane == 0) done = atomicAdd((int *)s_done, 0);
+      if (__shfl_sync(0xffffffffu, done, 0)) break;
       bool worked = false;
       if (!have_ticket) {
          ticket = __shfl_sync(0xffffffffu, next, 0);
@@ -444,11 +447,11 @@ __device__ __noinline__ void f3b_sweeper(const F3IterateParams &P, volatile int 
        * buckets of a still pass 2^24): such a bucket is reported ~100 times on its way from
        * the threshold to 2^24, however long the cold passes take. */
       if (P.sweep_mode & 8u) {
-         const unsigned head = ring->head;
+         const unsigned head = atomicAdd((unsigned int *)&ring->head, 0u);
          if (head - ring_tail > F3B_SAMPLE_RING) ring_tail = head - F3B_SAMPLE_RING;
          for (; ring_tail != head; ring_tail += (head - ring_tail < 32u ? head - ring_tail : 32u)) {
             if (lane < head - ring_tail) {
-               const size_t e = ring->entry[(ring_tail + lane) % F3B_SAMPLE_RING];
+               const size_t e = atomicAdd((uint32_t *)&ring->entry[(ring_tail + lane) % F3B_SAMPLE_RING], 0u);
                if (e < n_entries) {
                   const float4 v = f3b_ld_staged4(P.hist_color + e);
                   const float c = P.hist_count ? f3b_ld_staged1(P.hist_count + e) : 0.0f;
@@ -525,17 +528,25 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
  * (profiles/r01_v2: 94% of peak). A __constant__ array was tried and dropped: its speed
  * depended on the module loading mode (31 ms lazy vs 23 ms eager for the same code). */
 #define c_samp(ci) P.samp[ci]
+#ifndef F3B_OPT_PICK
+#define F3B_OPT_PICK 1
+#endif
+
 
 /* SIMPLE: every temporal sample of the launch has <= 4 xforms, no xaos, no final xform, a
  * step palette and fully visible xforms (the classic flame): the flag tests fold away and
  * the xform pick is three compares on a packed table from the constant bank. */
-template <bool COUNT, bool SIMPLE, int MODE, bool WU, bool SINGLE>
-__global__ void __launch_bounds__(F3B_BLOCK + 32, SIMPLE ? F3B_ITER_MIN_BLOCKS : F3B_GENERIC_MIN_BLOCKS)
+template <bool COUNT, int KIND, int MODE, bool WU, bool SINGLE>
+__global__ void __launch_bounds__(F3B_BLOCK + 32, KIND ? F3B_ITER_MIN_BLOCKS : F3B_GENERIC_MIN_BLOCKS)
 f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
    /* MODE 0: one vector reduction per hit; 1 (AGG): lanes of a warp that hit the same bucket add
     * once (also the binned scatter); 2 (REPORT): as 0, and the walkers report a sample of the
     * entries they add to (histograms in DRAM). Instantiations, because merely carrying the few
     * instructions of 2 costs the 72-register loop of 0 six per cent. */
+   /* KIND 0: any genome; 1 (SIMPLE): the classic flame, see above; 2: SIMPLE and no xform has a
+    * post affine - if-converted, the post block costs every iteration 8 issue slots (-4 %) */
+   constexpr bool SIMPLE = KIND != 0;
+   constexpr bool NOPOST = KIND == 2;
    constexpr bool AGG = MODE == 1;
    constexpr bool REPORT = MODE == 2;
    /* SINGLE: the launch has one temporal sample (every still). Its camera, flags and pick table
@@ -560,7 +571,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
          return;
       }
    }
-   const size_t rep_off = (size_t)(blockIdx.x % P.lay.replicas) * P.lay.replica_stride;
+   const uint32_t rep_off = (blockIdx.x % P.lay.replicas) * (uint32_t)P.lay.replica_stride;
    uint32_t *const wq = smem + P.bin_smem_off + (tid >> 5) * P.bin_warp_words; /* binned scatter only */
    uint32_t blk_next = 0, blk_end = 0; /* no pool blocks in hand */
    if (AGG && P.bin_regions) { /* this warp's region queues start empty */
@@ -669,10 +680,22 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
             uint32_t xo;
             if (SIMPLE) {
                /* (k << 18 | 0x3ffff) against (count << 18 | record offset) */
+#if F3B_OPT_PICK
+               const uint32_t key = rnd * 262144u + 0x3ffffu; /* one multiply-add */
+               const uint4 e = c_samp(ci).pick;
+               /* the entries ascend: selects from the last to the first leave the first one
+                * that exceeds the key - no branches for the lanes to diverge on */
+               uint32_t sel = e.w;
+               sel = key < e.z ? e.z : sel;
+               sel = key < e.y ? e.y : sel;
+               sel = key < e.x ? e.x : sel;
+               xo = sel & 0x3ffffu;
+#else
                const uint32_t key = __funnelshift_l(0xffffffffu, rnd, 18);
                const uint4 e = c_samp(ci).pick;
                const uint32_t sel = key < e.x ? e.x : (key < e.y ? e.y : (key < e.z ? e.z : e.w));
                xo = sel & 0x3ffffu;
+#endif
             } else {
             /* fn = number of cumulative thresholds <= k; rows are padded with 16384 */
             if (hf & HF_CHOOSER_CONST) {
@@ -691,7 +714,8 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
             const uint32_t xfl = c_samp(ci).lay.y; /* base | stride << 16 */
             xo = (xfl & 0xffffu) + fn * (xfl >> 16);
             }
-            const bool isbad = f3b_apply_xform(sf, xo, px, py, pc, qx, qy, qc, qv, rng);
+            const bool isbad = f3b_apply_xform(sf, xo, px, py, pc, qx, qy, qc, qv, rng,
+                                               !NOPOST);
             if (!isbad) break;
             bad++;
             if (++consec >= 5) break;
@@ -737,7 +761,12 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
          const int ix = (int)((x - bb.x) * cs.x);
          const int iy = (int)((y - bb.y) * cs.y);
          if (ix >= P.width || iy >= P.height) continue;
-         const size_t bidx = rep_off + f3b_hist_index(P.lay, ix, iy);
+         /* staging entries are counted in 32 bits (f3b_frame_begin refuses more): one
+          * multiply-add, and one widening multiply-add for the address */
+         /* staging entries are counted in 32 bits (f3b_frame_begin refuses more); the bucket's
+          * place in the staging copy is scrambled (f3b_internal.h: F3HistLayout) */
+         const uint32_t lin = (uint32_t)iy * (uint32_t)P.lay.pitch + (uint32_t)ix;
+         const uint32_t bidx = rep_off + f3b_stage_index(P.lay, lin);
 
          /* rect.c:465-498: palette lookup */
          const int cmap_size = (int)(hf >> 20);
@@ -767,7 +796,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
             if (AGG) {
                float4 tc = col;
                float tn = cnt;
-               const bool mine = f3b_bump_aggregate(P, bidx - rep_off, (unsigned long long)bidx, &tc, &tn,
+               const bool mine = f3b_bump_aggregate(P, lin, (unsigned long long)bidx, &tc, &tn,
                                                     P.probe_iters ? P.probe_counts : nullptr);
                if (!mine) continue;
                col = tc;
@@ -776,7 +805,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
             f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
             if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
             if (REPORT && (((uint32_t)i ^ tid) & (F3B_SAMPLE_EVERY - 1)) == 0)
-               s_ring.entry[atomicAdd(&s_ring.head, 1u) % F3B_SAMPLE_RING] = (uint32_t)bidx;
+               atomicExch(&s_ring.entry[atomicAdd(&s_ring.head, 1u) % F3B_SAMPLE_RING], (uint32_t)bidx);
             continue;
          }
          if (hf & HF_PAL_LINEAR) {
@@ -822,7 +851,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
             }
             float4 tc = col;
             float tn = cnt;
-            const bool mine = f3b_bump_aggregate(P, bidx - rep_off, (unsigned long long)bidx, &tc, &tn,
+            const bool mine = f3b_bump_aggregate(P, lin, (unsigned long long)bidx, &tc, &tn,
                                                  P.probe_iters ? P.probe_counts : nullptr);
             if (!mine) continue;
             col = tc;
@@ -831,7 +860,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
          f3b_red_v4(P.hist_color + bidx, col.x, col.y, col.z, col.w);
          if (COUNT) f3b_red_f32(P.hist_count + bidx, cnt);
          if (REPORT && (((uint32_t)i ^ tid) & (F3B_SAMPLE_EVERY - 1)) == 0)
-            s_ring.entry[atomicAdd(&s_ring.head, 1u) % F3B_SAMPLE_RING] = (uint32_t)bidx;
+            atomicExch(&s_ring.entry[atomicAdd(&s_ring.head, 1u) % F3B_SAMPLE_RING], (uint32_t)bidx);
          } while (0);
          if (binned) {
             __syncwarp();
@@ -859,7 +888,7 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
    if ((tid & 31u) == 0 && bad) atomicAdd(P.badvals, (unsigned long long)bad);
    if (P.sweep_on) { /* all walkers of the CTA are through: release its sweeper warp */
       f3b_chain_barrier(nct);
-      if (tid == 0) *(volatile int *)&s_done = 1;
+      if (tid == 0) atomicExch(&s_done, 1);
    }
 }
 
@@ -992,17 +1021,19 @@ int f3b_iterate_blocks_per_sm(int group_size, size_t smem_bytes, bool simple) {
    F3B_SET1(C, S, 1, true);    \
    F3B_SET1(C, S, 2, false);   \
    F3B_SET1(C, S, 2, true)
-   F3B_SET(true, false);
-   F3B_SET(false, false);
-   F3B_SET(true, true);
-   F3B_SET(false, true);
+   F3B_SET(true, 0);
+   F3B_SET(false, 0);
+   F3B_SET(true, 1);
+   F3B_SET(false, 1);
+   F3B_SET(true, 2);
+   F3B_SET(false, 2);
 #undef F3B_SET
 #undef F3B_SET1
    /* group_size counts the walkers; the CTA has one more warp (the sweeper). The SIMPLE and the
     * generic instantiations have different register budgets (3 and 2 CTAs per SM). */
-   cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, true, 1, true, false>,
+   cudaError_t e = simple ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, 1, 1, true, false>,
                                                                           group_size + 32, smem_bytes)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, false, 1, true, false>,
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f3b_iterate_kernel<true, 0, 1, true, false>,
                                                                           group_size + 32, smem_bytes);
    if (e != cudaSuccess) return 0;
    return nb;
@@ -1036,12 +1067,17 @@ int f3b_launch_iterate(F3IterateParams &p, const F3ConstSample *consts, int n_co
       else if (mode == 2) F3B_LAUNCH_M(C, S, 2); \
       else F3B_LAUNCH_M(C, S, 0);                \
    } while (0)
+   int kind = simple ? 2 : 0;
+   for (int i = 0; i < n_consts && kind == 2; i++)
+      if (consts[i].lay.x & F3B_HF_ANY_POST) kind = 1;
    if (count_channel) {
-      if (simple) F3B_LAUNCH(true, true);
-      else F3B_LAUNCH(true, false);
+      if (kind == 2) F3B_LAUNCH(true, 2);
+      else if (kind == 1) F3B_LAUNCH(true, 1);
+      else F3B_LAUNCH(true, 0);
    } else {
-      if (simple) F3B_LAUNCH(false, true);
-      else F3B_LAUNCH(false, false);
+      if (kind == 2) F3B_LAUNCH(false, 2);
+      else if (kind == 1) F3B_LAUNCH(false, 1);
+      else F3B_LAUNCH(false, 0);
    }
 #undef F3B_LAUNCH_M
 #undef F3B_LAUNCH_W

@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(256) f3b_hist_merge_kernel(const F3MergeParams
       if (M.f64) {
          double ax = 0.0, ay = 0.0, az = 0.0, aw = 0.0, ac = 0.0;
          for (uint32_t r = 0; r < M.lay.replicas; r++) {
-            const size_t e = i + r * M.lay.replica_stride;
+            const size_t e = f3b_stage_index(M.lay, (uint32_t)i) + r * M.lay.replica_stride;
             const float4 b = M.color[e];
             ax += (double)b.x;
             ay += (double)b.y;
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(256) f3b_hist_merge_kernel(const F3MergeParams
       } else {
          long long ax = 0, ay = 0, az = 0, aw = 0, ac = 0;
          for (uint32_t r = 0; r < M.lay.replicas; r++) {
-            const size_t e = i + r * M.lay.replica_stride;
+            const size_t e = f3b_stage_index(M.lay, (uint32_t)i) + r * M.lay.replica_stride;
             const float4 b = M.color[e];
             const float m = fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)));
             if (m >= F3B_EXACT_LIMIT) lost++;

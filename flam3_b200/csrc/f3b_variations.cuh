@@ -1031,9 +1031,19 @@ __device__ __noinline__ float2 f3b_apply_varlist(const float *sf, uint32_t vi, u
  * tests and runs out of line, so the hot loop's registers and instruction footprint are
  * those of the common case.
  */
+#ifndef F3B_OPT_POST
+#define F3B_OPT_POST 2
+#endif
+/* the post affine (variations.c:2383-2390) */
+__device__ __noinline__ float2 f3b_apply_post(const float *sf, uint32_t xo, float p0, float p1) {
+   const float4 b0 = *reinterpret_cast<const float4 *>(sf + xo + F3B_X_P00);       /* p00 p10 p20 p01 */
+   const float2 b1 = *reinterpret_cast<const float2 *>(sf + xo + F3B_X_P11); /* p11 p21 */
+   return make_float2(fmaf(b0.x, p0, fmaf(b0.y, p1, b0.z)), fmaf(b0.w, p0, fmaf(b1.x, p1, b1.y)));
+}
+
 __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, uint32_t xo, float px,
                                                 float py, float pc, float &qx, float &qy, float &qc,
-                                                float &qvis, F3Rng &rng) {
+                                                float &qvis, F3Rng &rng, bool any_post = true) {
    const float4 *xf4 = reinterpret_cast<const float4 *>(sf + xo);
    const float4 a0 = xf4[0]; /* c00 c10 c20 c01 */
    const float4 a1 = xf4[1]; /* c11 c21 scolor 1-s */
@@ -1042,30 +1052,45 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, ui
    qvis = a2.x;
    const uint32_t flags = __float_as_uint(a2.y);
 
+   /* The common case needs tx, ty and their squares only; the point record with its angles and
+    * radius is built on the two out-of-line paths that read it. */
+   float tx = fmaf(a0.x, px, fmaf(a0.y, py, a0.z));
+   float ty = fmaf(a0.w, px, fmaf(a1.x, py, a1.y));
+   const uint32_t precalc = flags & (F3B_XF_PREBLUR | F3B_XF_NEED_SQRT | F3B_XF_ATAN_XY | F3B_XF_ANGLES | F3B_XF_ATAN_YX);
    F3Pt pt;
-   pt.tx = fmaf(a0.x, px, fmaf(a0.y, py, a0.z));
-   pt.ty = fmaf(a0.w, px, fmaf(a1.x, py, a1.y));
-   pt.rad = 0.0f;
-   pt.atan_xy = pt.atan_yx = pt.sina = pt.cosa = 0.0f;
-   if (flags & (F3B_XF_PREBLUR | F3B_XF_NEED_SQRT | F3B_XF_ATAN_XY | F3B_XF_ANGLES | F3B_XF_ATAN_YX)) {
-      /* only these copies have their address taken; `pt` and `rng` stay in registers */
+   if (precalc) {
+      /* only these copies have their address taken; `rng` stays in registers */
       F3Rng tmp = rng;
-      F3Pt tpt = pt;
+      F3Pt tpt;
+      tpt.tx = tx;
+      tpt.ty = ty;
+      tpt.rad = 0.0f;
+      tpt.atan_xy = tpt.atan_yx = tpt.sina = tpt.cosa = 0.0f;
+      tpt.sumsq = 0.0f;
       f3b_precalc(sf, xo, flags, &tpt, &tmp);
       rng = tmp;
       pt = tpt;
+      tx = tpt.tx; /* pre_blur moves the point */
+      ty = tpt.ty;
    }
-   pt.sumsq = pt.tx * pt.tx + pt.ty * pt.ty;
+   const float sumsq = tx * tx + ty * ty;
 
    /* fixed-function slots */
-   float p0 = a2.z * pt.tx, p1 = a2.z * pt.ty;
+   float p0 = a2.z * tx, p1 = a2.z * ty;
    if (a2.w != 0.0f) {
-      const float r2 = __fdividef(a2.w, pt.sumsq + F3B_EPS);
-      p0 = fmaf(r2, pt.tx, p0);
-      p1 = fmaf(r2, pt.ty, p1);
+      const float r2 = __fdividef(a2.w, sumsq + F3B_EPS);
+      p0 = fmaf(r2, tx, p0);
+      p1 = fmaf(r2, ty, p1);
    }
    /* the rest of the variation list, if any */
    if (flags >> 8) {
+      if (!precalc) {
+         pt.rad = 0.0f;
+         pt.atan_xy = pt.atan_yx = pt.sina = pt.cosa = 0.0f;
+      }
+      pt.tx = tx;
+      pt.ty = ty;
+      pt.sumsq = sumsq;
       F3Rng tmp = rng;
       const float2 d = f3b_apply_varlist(sf, xo + F3B_X_VARS, xo + F3B_X_VARS + (flags >> 8), pt, &tmp);
       rng = tmp;
@@ -1073,6 +1098,27 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, ui
       p1 += d.y;
    }
 
+#if F3B_OPT_POST == 2
+   qx = p0;
+   qy = p1;
+   /* any_post is a compile-time constant in the kernels (false where no xform of the launch has
+    * a post affine: most classic flames); if-converted, the block costs every iteration 8 issue
+    * slots */
+   if (any_post && (flags & F3B_XF_HAS_POST)) {
+      const float4 b0 = xf4[3];                                              /* p00 p10 p20 p01 */
+      const float2 b1 = *reinterpret_cast<const float2 *>(sf + xo + F3B_X_P11); /* p11 p21 */
+      qx = fmaf(b0.x, p0, fmaf(b0.y, p1, b0.z));
+      qy = fmaf(b0.w, p0, fmaf(b1.x, p1, b1.y));
+   }
+#elif F3B_OPT_POST
+   qx = p0;
+   qy = p1;
+   if (flags & F3B_XF_HAS_POST) { /* out of line: predicated in line it cost every iteration 8 issue slots */
+      const float2 q = f3b_apply_post(sf, xo, p0, p1);
+      qx = q.x;
+      qy = q.y;
+   }
+#else
    if (flags & F3B_XF_HAS_POST) {
       const float4 b0 = xf4[3];                                              /* p00 p10 p20 p01 */
       const float2 b1 = *reinterpret_cast<const float2 *>(sf + xo + F3B_X_P11); /* p11 p21 */
@@ -1082,6 +1128,7 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, ui
       qx = p0;
       qy = p1;
    }
+#endif
    if (f3b_bad(qx) || f3b_bad(qy)) {
       qx = rng.u11();
       qy = rng.u11();
