@@ -533,6 +533,7 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
 #endif
 
 
+
 /* SIMPLE: every temporal sample of the launch has <= 4 xforms, no xaos, no final xform, a
  * step palette and fully visible xforms (the classic flame): the flag tests fold away and
  * the xform pick is three compares on a packed table from the constant bank. */
@@ -791,6 +792,9 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
                bin_c = rgba;
                continue;
             }
+            /* (the 4-byte copy of the table was tried here twice - fewer shared-memory wavefronts,
+             * eight more instructions to turn bytes into floats: -5 % and -3.5 %,
+             * profiles/r02_palette_rgba8_ab.txt) */
             col = dmap[pi];
             float cnt = 255.0f;
             if (AGG) {
