@@ -528,9 +528,6 @@ __device__ __noinline__ float4 f3b_apply_final(const float *sf, uint32_t xo, flo
  * (profiles/r01_v2: 94% of peak). A __constant__ array was tried and dropped: its speed
  * depended on the module loading mode (31 ms lazy vs 23 ms eager for the same code). */
 #define c_samp(ci) P.samp[ci]
-#ifndef F3B_OPT_PICK
-#define F3B_OPT_PICK 1
-#endif
 
 
 
@@ -681,7 +678,6 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
             uint32_t xo;
             if (SIMPLE) {
                /* (k << 18 | 0x3ffff) against (count << 18 | record offset) */
-#if F3B_OPT_PICK
                const uint32_t key = rnd * 262144u + 0x3ffffu; /* one multiply-add */
                const uint4 e = c_samp(ci).pick;
                /* the entries ascend: selects from the last to the first leave the first one
@@ -691,12 +687,6 @@ f3b_iterate_kernel(const __grid_constant__ F3IterateParams P) {
                sel = key < e.y ? e.y : sel;
                sel = key < e.x ? e.x : sel;
                xo = sel & 0x3ffffu;
-#else
-               const uint32_t key = __funnelshift_l(0xffffffffu, rnd, 18);
-               const uint4 e = c_samp(ci).pick;
-               const uint32_t sel = key < e.x ? e.x : (key < e.y ? e.y : (key < e.z ? e.z : e.w));
-               xo = sel & 0x3ffffu;
-#endif
             } else {
             /* fn = number of cumulative thresholds <= k; rows are padded with 16384 */
             if (hf & HF_CHOOSER_CONST) {

@@ -1031,16 +1031,6 @@ __device__ __noinline__ float2 f3b_apply_varlist(const float *sf, uint32_t vi, u
  * tests and runs out of line, so the hot loop's registers and instruction footprint are
  * those of the common case.
  */
-#ifndef F3B_OPT_POST
-#define F3B_OPT_POST 2
-#endif
-/* the post affine (variations.c:2383-2390) */
-__device__ __noinline__ float2 f3b_apply_post(const float *sf, uint32_t xo, float p0, float p1) {
-   const float4 b0 = *reinterpret_cast<const float4 *>(sf + xo + F3B_X_P00);       /* p00 p10 p20 p01 */
-   const float2 b1 = *reinterpret_cast<const float2 *>(sf + xo + F3B_X_P11); /* p11 p21 */
-   return make_float2(fmaf(b0.x, p0, fmaf(b0.y, p1, b0.z)), fmaf(b0.w, p0, fmaf(b1.x, p1, b1.y)));
-}
-
 __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, uint32_t xo, float px,
                                                 float py, float pc, float &qx, float &qy, float &qc,
                                                 float &qvis, F3Rng &rng, bool any_post = true) {
@@ -1098,7 +1088,6 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, ui
       p1 += d.y;
    }
 
-#if F3B_OPT_POST == 2
    qx = p0;
    qy = p1;
    /* any_post is a compile-time constant in the kernels (false where no xform of the launch has
@@ -1110,25 +1099,6 @@ __device__ __forceinline__ bool f3b_apply_xform(const float *__restrict__ sf, ui
       qx = fmaf(b0.x, p0, fmaf(b0.y, p1, b0.z));
       qy = fmaf(b0.w, p0, fmaf(b1.x, p1, b1.y));
    }
-#elif F3B_OPT_POST
-   qx = p0;
-   qy = p1;
-   if (flags & F3B_XF_HAS_POST) { /* out of line: predicated in line it cost every iteration 8 issue slots */
-      const float2 q = f3b_apply_post(sf, xo, p0, p1);
-      qx = q.x;
-      qy = q.y;
-   }
-#else
-   if (flags & F3B_XF_HAS_POST) {
-      const float4 b0 = xf4[3];                                              /* p00 p10 p20 p01 */
-      const float2 b1 = *reinterpret_cast<const float2 *>(sf + xo + F3B_X_P11); /* p11 p21 */
-      qx = fmaf(b0.x, p0, fmaf(b0.y, p1, b0.z));
-      qy = fmaf(b0.w, p0, fmaf(b1.x, p1, b1.y));
-   } else {
-      qx = p0;
-      qy = p1;
-   }
-#endif
    if (f3b_bad(qx) || f3b_bad(qy)) {
       qx = rng.u11();
       qy = rng.u11();
