@@ -31,7 +31,9 @@ def dropin_lib_path():
 def dropin_harness_path():
     """The test harness over flam3.h (tests/harness/f3_harness.c) built as its own library
     against the drop-in libflam3.so — the product library itself holds no test code."""
-    return os.path.join(repo_root(), "dropin", "_build", "libf3harness.so")
+    # (F3B_HARNESS_LIB: another build of the same pair of libraries, e.g. one made with
+    # -fsanitize=address for the host-side tests)
+    return os.environ.get("F3B_HARNESS_LIB") or os.path.join(repo_root(), "dropin", "_build", "libf3harness.so")
 
 
 class RenderArgs(C.Structure):
