@@ -995,6 +995,416 @@ void f3b_free_genomes(flam3_genome *g, int n) {
    free(g);
 }
 
+
+/* ---- between key frames (flam3.c:717-802, interpolation.c) ------------------------------ */
+/* What flam3_interpolate gives flam3_render for a time between key frames: the key frames are
+ * padded to the same xforms (flam3_align), everything is blended with the segment's weights -
+ * two of them, or four Catmull-Rom weights on smooth segments - the affine parts in log-polar
+ * form. Motion elements are not read by this front end, so there are none to apply. Pinned
+ * against the reference byte for byte (tests/test_cpu_frontend.py). */
+
+/* which variation a parameter belongs to: its name is the variation's name + "_" + something;
+ * the longest such variation wins (wedge_julia_angle is wedge_julia's, not wedge's) */
+static int param_variation(const char *pname) {
+   int best = -1;
+   size_t best_len = 0;
+   for (int v = 0; v < flam3_nvariations; v++) {
+      const char *vn = v == VAR_OSCILLOSCOPE ? "oscope" : k_variation_names[v];
+      const size_t n = strlen(vn);
+      if (n > best_len && !strncmp(pname, vn, n) && pname[n] == '_') {
+         best = v;
+         best_len = n;
+      }
+   }
+   return best;
+}
+/* flam3_copy_params (flam3.c:804-1030): the parameters of variation `var`, with the derived
+ * values the reference copies along - and without flower_holes, which it forgets */
+static void copy_var_params(flam3_xform *dst, const flam3_xform *src, int var) {
+   for (size_t i = 0; i < sizeof(k_xform_params) / sizeof(k_xform_params[0]); i++) {
+      if (param_variation(k_xform_params[i].name) != var) continue;
+      if (!strcmp(k_xform_params[i].name, "flower_holes")) continue;
+      *(double *)((char *)dst + k_xform_params[i].off) = *(const double *)((const char *)src + k_xform_params[i].off);
+   }
+   if (var == VAR_JULIAN) {
+      dst->julian_rN = src->julian_rN;
+      dst->julian_cn = src->julian_cn;
+   } else if (var == VAR_JULIASCOPE) {
+      dst->juliascope_rN = src->juliascope_rN;
+      dst->juliascope_cn = src->juliascope_cn;
+   } else if (var == VAR_PERSPECTIVE) {
+      dst->persp_vsin = src->persp_vsin;
+      dst->persp_vfcos = src->persp_vfcos;
+   } else if (var == VAR_WEDGE_JULIA) {
+      dst->wedgeJulia_cf = src->wedgeJulia_cf;
+      dst->wedgeJulia_cn = src->wedgeJulia_cn;
+      dst->wedgeJulia_rN = src->wedgeJulia_rN;
+   }
+}
+
+/* flam3_copyx (flam3.c:1211-1268): a copy with nstd standard xforms (the missing ones are fresh
+ * xforms marked as padding) and a final xform if any key frame has one */
+static int copy_padded(flam3_genome *dst, const flam3_genome *src, int nstd, int want_final) {
+   f3b_genome_init(dst, 1);
+   memcpy(dst, src, sizeof(*dst));
+   dst->xform = NULL;
+   dst->chaos = NULL;
+   dst->num_xforms = 0;
+   dst->final_xform_index = -1;
+   const int src_std = src->num_xforms - (src->final_xform_index >= 0);
+   for (int i = 0; i < nstd; i++) {
+      const int at = f3b_genome_add_xform(dst, 0);
+      if (at < 0) return 1;
+      dst->xform[at].padding = 1;
+   }
+   for (int i = 0; i < src_std; i++) {
+      dst->xform[i] = src->xform[i]; /* (no motion elements in genomes of this front end) */
+      dst->xform[i].motion = NULL;
+      dst->xform[i].num_motion = 0;
+      memcpy(dst->chaos[i], src->chaos[i], (size_t)src_std * sizeof(double));
+   }
+   if (want_final > 0) {
+      const int at = f3b_genome_add_xform(dst, 1);
+      if (at < 0) return 1;
+      dst->xform[at].padding = 1;
+      if (src->final_xform_enable > 0) {
+         dst->xform[at] = src->xform[src->final_xform_index];
+         dst->xform[at].motion = NULL;
+         dst->xform[at].num_motion = 0;
+      } else { /* a final xform to interpolate against: it must not rotate or recolour */
+         dst->xform[at].animate = 0.0;
+         dst->xform[at].color_speed = 0.0;
+      }
+   } else {
+      dst->final_xform_index = -1;
+      dst->final_xform_enable = 0;
+   }
+   return 0;
+}
+
+/* the better 'identity' of a padding xform (interpolation.c:845-1025): what it is made of
+ * depends on what its neighbour in time uses */
+static const int k_holes[] = {VAR_SPHERICAL, VAR_NGON, VAR_JULIAN, VAR_JULIASCOPE, VAR_POLAR, VAR_WEDGE_SPH, VAR_WEDGE_JULIA};
+
+static void pad_like_neighbours(flam3_genome *g, int n, int i, int xf) {
+   flam3_xform *x = &g[i].xform[xf];
+   x->var[VAR_LINEAR] = 0.0;
+   int found = 0;
+   const int log_space = (i == 0 ? g[i].interpolation_type : g[i - 1].interpolation_type) == flam3_inttype_log;
+   if (log_space)
+      for (int d = -1; d <= 1; d += 2) {
+         if (i + d < 0 || i + d >= n || g[i + d].xform[xf].padding == 1) continue;
+         const flam3_xform *o = &g[i + d].xform[xf];
+         int holes = 0;
+         for (size_t k = 0; k < sizeof(k_holes) / sizeof(k_holes[0]); k++) holes |= o->var[k_holes[k]] > 0;
+         if (holes) { /* against a half turn with weight -1 */
+            x->var[VAR_LINEAR] = -1.0;
+            x->c[0][0] = -1.0; x->c[0][1] = 0.0;
+            x->c[1][0] = 0.0;  x->c[1][1] = -1.0;
+            x->c[2][0] = 0.0;  x->c[2][1] = 0.0;
+            found = -1;
+         }
+      }
+   if (found == 0)
+      for (int d = -1; d <= 1; d += 2) {
+         if (i + d < 0 || i + d >= n || g[i + d].xform[xf].padding == 1) continue;
+         const flam3_xform *o = &g[i + d].xform[xf];
+         if (o->var[VAR_RECTANGLES] > 0) { x->var[VAR_RECTANGLES] = 1.0; x->rectangles_x = 0.0; x->rectangles_y = 0.0; found++; }
+         if (o->var[VAR_RINGS2] > 0) { x->var[VAR_RINGS2] = 1.0; x->rings2_val = 0.0; found++; }
+         if (o->var[VAR_FAN2] > 0) { x->var[VAR_FAN2] = 1.0; x->fan2_x = 0.0; x->fan2_y = 0.0; found++; }
+         if (o->var[VAR_BLOB] > 0) { x->var[VAR_BLOB] = 1.0; x->blob_low = 1.0; x->blob_high = 1.0; x->blob_waves = 1.0; found++; }
+         if (o->var[VAR_PERSPECTIVE] > 0) { x->var[VAR_PERSPECTIVE] = 1.0; x->perspective_angle = 0.0; found++; }
+         if (o->var[VAR_CURL] > 0) { x->var[VAR_CURL] = 1.0; x->curl_c1 = 0.0; x->curl_c2 = 0.0; found++; }
+         if (o->var[VAR_SUPER_SHAPE] > 0) {
+            x->var[VAR_SUPER_SHAPE] = 1.0;
+            x->super_shape_n1 = x->super_shape_n2 = x->super_shape_n3 = 2.0;
+            x->super_shape_rnd = 0.0;
+            x->super_shape_holes = 0.0;
+            found++;
+         }
+      }
+   if (found == 0) { /* fan and rings work on the coefficients: against the swapped axes */
+      for (int d = -1; d <= 1; d += 2) {
+         if (i + d < 0 || i + d >= n || g[i + d].xform[xf].padding == 1) continue;
+         const flam3_xform *o = &g[i + d].xform[xf];
+         if (o->var[VAR_FAN] > 0) { x->var[VAR_FAN] = 1.0; found++; }
+         if (o->var[VAR_RINGS] > 0) { x->var[VAR_RINGS] = 1.0; found++; }
+      }
+      if (found > 0) {
+         x->c[0][0] = 0.0; x->c[0][1] = 1.0;
+         x->c[1][0] = 1.0; x->c[1][1] = 0.0;
+         x->c[2][0] = 0.0; x->c[2][1] = 0.0;
+      }
+   }
+   if (found == 0) x->var[VAR_LINEAR] = 1.0;
+   else if (found > 0) {
+      double sum = 0.0;
+      for (int j = 0; j < flam3_nvariations; j++) sum += x->var[j];
+      for (int j = 0; j < flam3_nvariations; j++) x->var[j] /= sum;
+   }
+}
+
+/* flam3_align (interpolation.c:768-1032) */
+static int align_genomes(flam3_genome *dst, const flam3_genome *src, int n) {
+   int nstd = src[0].num_xforms - (src[0].final_xform_index >= 0), nfinal = src[0].final_xform_enable;
+   int aligned = 1;
+   for (int i = 1; i < n; i++) {
+      const int t = src[i].num_xforms - (src[i].final_xform_index >= 0);
+      if (t != nstd) {
+         aligned = 0;
+         if (t > nstd) nstd = t;
+      }
+      if (src[i].final_xform_enable != nfinal) {
+         aligned = 0;
+         nfinal |= src[i].final_xform_enable;
+      }
+   }
+   for (int i = 0; i < n; i++)
+      if (copy_padded(&dst[i], &src[i], nstd, nfinal)) return 1;
+   const int lead = n / 2 - 1;
+   if (dst[lead].interpolation_type == flam3_inttype_compat || dst[lead].interpolation_type == flam3_inttype_older) return 0;
+   for (int i = 0; i < n; i++)
+      for (int xf = 0; xf < nstd + nfinal; xf++) {
+         /* a parametric variation that a neighbour in time uses and this xform does not: take
+          * the neighbour's parameters, so that the blend does not sweep them from defaults */
+         for (int j = 23; j < flam3_nvariations; j++) {
+            if (dst[i].xform[xf].var[j] != 0) continue;
+            if (i > 0) {
+               if (dst[i - 1].xform[xf].var[j] != 0) copy_var_params(&dst[i].xform[xf], &dst[i - 1].xform[xf], j);
+            } else if (i < n - 1) {
+               if (dst[i + 1].xform[xf].var[j] != 0) copy_var_params(&dst[i].xform[xf], &dst[i + 1].xform[xf], j);
+            }
+         }
+         if (dst[i].xform[xf].padding == 1 && !aligned) pad_like_neighbours(dst, n, i, xf);
+      }
+   return 0;
+}
+
+/* affine parts as two column vectors in polar form (interpolation.c:247-324) */
+static void affine_to_polar(const flam3_genome *g, int n, int xf, int post, double ang[4][2], double mag[4][2], double trn[4][2]) {
+   for (int k = 0; k < n; k++) {
+      const double(*m)[2] = post ? g[k].xform[xf].post : g[k].xform[xf].c;
+      int zero[2] = {0, 0};
+      for (int col = 0; col < 2; col++) {
+         ang[k][col] = atan2(m[col][1], m[col][0]);
+         mag[k][col] = sqrt(m[col][0] * m[col][0] + m[col][1] * m[col][1]);
+         if (mag[k][col] == 0.0) zero[col] = 1;
+         trn[k][col] = m[2][col];
+      }
+      if (zero[0] == 1 && zero[1] == 0) ang[k][0] = ang[k][1];
+      else if (zero[0] == 0 && zero[1] == 1) ang[k][1] = ang[k][0];
+   }
+   for (int col = 0; col < 2; col++)
+      for (int k = 1; k < n; k++) {
+         const double wind = g[k].xform[xf].wind[col];
+         if (wind > 0 && !post) { /* asymmetric case: both angles within [wind - 2 pi, wind] */
+            const double ref = wind - 2 * M_PI;
+            while (ang[k - 1][col] < ref) ang[k - 1][col] += 2 * M_PI;
+            while (ang[k - 1][col] > ref + 2 * M_PI) ang[k - 1][col] -= 2 * M_PI;
+            while (ang[k][col] < ref) ang[k][col] += 2 * M_PI;
+            while (ang[k][col] > ref + 2 * M_PI) ang[k][col] -= 2 * M_PI;
+         } else { /* the shorter way round, clockwise at exactly half a turn */
+            const double d = ang[k][col] - ang[k - 1][col];
+            if (d > M_PI + 1e-10) ang[k][col] -= 2 * M_PI;
+            else if (d < -(M_PI - 1e-10)) ang[k][col] += 2 * M_PI;
+         }
+      }
+}
+static void polar_blend(const double *c, int n, double ang[4][2], double mag[4][2], double trn[4][2], double out[3][2]) {
+   double a[2] = {0.0, 0.0}, m[2] = {0.0, 0.0};
+   int linear[2] = {0, 0};
+   for (int col = 0; col < 2; col++)
+      for (int i = 0; i < n; i++)
+         if (log(mag[i][col]) < -10) linear[col] = 1; /* near-zero columns blend their lengths linearly */
+   for (int i = 0; i < n; i++)
+      for (int col = 0; col < 2; col++) {
+         a[col] += c[i] * ang[i][col];
+         if (!linear[col]) m[col] += c[i] * log(mag[i][col]);
+         else m[col] += c[i] * mag[i][col];
+         out[2][col] += c[i] * trn[i][col];
+      }
+   for (int col = 0; col < 2; col++) {
+      const double len = linear[col] ? m[col] : exp(m[col]);
+      out[col][0] = len * cos(a[col]);
+      out[col][1] = len * sin(a[col]);
+   }
+}
+static int is_identity(const double m[3][2]) {
+   return m[0][0] == 1.0 && m[0][1] == 0.0 && m[1][0] == 0.0 && m[1][1] == 1.0 && m[2][0] == 0.0 && m[2][1] == 0.0;
+}
+
+/* flam3_interpolate_n (interpolation.c:373-708), stagger 0 */
+#define BLEND(field)                                                         \
+   do {                                                                      \
+      double acc_ = 0.0;                                                     \
+      for (int k_ = 0; k_ < n; k_++) acc_ += c[k_] * g[k_].field;            \
+      r->field = acc_;                                                       \
+   } while (0)
+#define BLEND_INT(field)                                                     \
+   do {                                                                      \
+      double acc_ = 0.0;                                                     \
+      for (int k_ = 0; k_ < n; k_++) acc_ += c[k_] * g[k_].field;            \
+      r->field = (int)rint(acc_);                                            \
+   } while (0)
+static void blend_genomes(flam3_genome *r, int n, flam3_genome *g, const double *c) {
+   if (g[0].palette_interpolation != flam3_palette_interpolation_sweep) {
+      double rgb_fraction = 0.0;
+      if (g[0].palette_interpolation == flam3_palette_interpolation_rgb) rgb_fraction = 1.0;
+      else if (g[0].palette_interpolation == flam3_palette_interpolation_hsv_circular) rgb_fraction = g[0].hsv_rgb_palette_blend;
+      for (int i = 0; i < 256; i++) {
+         double new_rgb[3] = {0, 0, 0}, new_hsv[3] = {0, 0, 0}, count = 0, index = 0;
+         int alpha1 = 1;
+         for (int k = 0; k < n; k++) {
+            double hsv[3];
+            rgb_to_hsv(g[k].palette[i].color, hsv);
+            if (n == 2 && k == 0 && g[0].palette_interpolation == flam3_palette_interpolation_hsv_circular) {
+               double second[3];
+               rgb_to_hsv(g[1].palette[i].color, second);
+               if (second[0] - hsv[0] > 3.0) hsv[0] += 6.0;
+               else if (second[0] - hsv[0] < -3.0) hsv[0] -= 6.0;
+            }
+            for (int j = 0; j < 3; j++) {
+               new_rgb[j] += c[k] * g[k].palette[i].color[j];
+               new_hsv[j] += c[k] * hsv[j];
+            }
+            count += c[k] * g[k].palette[i].color[3];
+            if (g[k].palette[i].color[3] != 1.0) alpha1 = 0;
+            index += c[k] * g[k].palette[i].index;
+         }
+         if (alpha1) count = 1.0;
+         double back[3];
+         hsv_to_rgb(new_hsv, back);
+         double *out = r->palette[i].color;
+         for (int j = 0; j < 3; j++) out[j] = rgb_fraction * new_rgb[j] + (1.0 - rgb_fraction) * back[j];
+         out[3] = count;
+         /* (the reference's -ffast-math build clips with max / min instructions: a -0.0 that
+          * comes out of the blend leaves as +0.0) */
+         for (int j = 0; j < 4; j++) {
+            out[j] = out[j] > 0.0 ? out[j] : 0.0;
+            out[j] = out[j] < 1.0 ? out[j] : 1.0;
+         }
+         index = index > 0.0 ? index : 0.0;
+         r->palette[i].index = index < 255.0 ? index : 255.0;
+      }
+   } else
+      for (int i = 0; i < 256; i++) r->palette[i] = g[i < 256 * c[0] ? 0 : 1].palette[i];
+
+   r->palette_index = flam3_palette_random;
+   r->symmetry = 0;
+   r->spatial_filter_select = g[0].spatial_filter_select;
+   r->temporal_filter_type = g[0].temporal_filter_type;
+   r->palette_mode = g[0].palette_mode;
+   r->interpolation_type = g[0].interpolation_type;
+   r->palette_interpolation = g[0].palette_interpolation;
+   r->hsv_rgb_palette_blend = g[0].hsv_rgb_palette_blend;
+   BLEND(brightness); BLEND(contrast); BLEND(highlight_power); BLEND(gamma); BLEND(vibrancy); BLEND(hue_rotation);
+   BLEND_INT(width); BLEND_INT(height); BLEND_INT(spatial_oversample);
+   BLEND(center[0]); BLEND(center[1]); BLEND(rot_center[0]); BLEND(rot_center[1]);
+   BLEND(background[0]); BLEND(background[1]); BLEND(background[2]);
+   BLEND(pixels_per_unit); BLEND(spatial_filter_radius); BLEND(temporal_filter_exp); BLEND(temporal_filter_width);
+   BLEND(sample_density); BLEND(zoom); BLEND(rotate);
+   BLEND_INT(nbatches); BLEND_INT(ntemporal_samples);
+   BLEND(estimator); BLEND(estimator_minimum); BLEND(estimator_curve); BLEND(gam_lin_thresh);
+
+   const int nstd = g[0].num_xforms - (g[0].final_xform_index >= 0);
+   for (int i = 0; i < nstd; i++)
+      for (int j = 0; j < nstd; j++) {
+         BLEND(chaos[i][j]);
+         if (r->chaos[i][j] < 0) r->chaos[i][j] = 0;
+      }
+   for (int i = 0; i < g[0].num_xforms; i++) {
+      BLEND(xform[i].density);
+      if (r->xform[i].density < 0.0) r->xform[i].density = 0.0;
+      BLEND(xform[i].color);
+      if (r->xform[i].color < 0) r->xform[i].color = 0;
+      if (r->xform[i].color > 1) r->xform[i].color = 1;
+      BLEND(xform[i].color_speed);
+      if (r->xform[i].color_speed < 0) r->xform[i].color_speed = 0;
+      if (r->xform[i].color_speed > 1) r->xform[i].color_speed = 1;
+      BLEND(xform[i].opacity);
+      BLEND(xform[i].animate);
+      for (size_t p = 0; p < sizeof(k_xform_params) / sizeof(k_xform_params[0]); p++) {
+         double acc = 0.0;
+         for (int k = 0; k < n; k++) acc += c[k] * *(const double *)((const char *)&g[k].xform[i] + k_xform_params[p].off);
+         *(double *)((char *)&r->xform[i] + k_xform_params[p].off) = acc;
+      }
+      for (int j = 0; j < flam3_nvariations; j++) BLEND(xform[i].var[j]);
+
+      int all_id = 1;
+      for (int k = 0; k < n; k++) all_id &= is_identity(g[k].xform[i].post);
+      memset(r->xform[i].c, 0, sizeof(r->xform[i].c));
+      memset(r->xform[i].post, 0, sizeof(r->xform[i].post));
+      if (g[0].interpolation_type == flam3_inttype_log) {
+         double ang[4][2], mag[4][2], trn[4][2];
+         affine_to_polar(g, n, i, 0, ang, mag, trn);
+         polar_blend(c, n, ang, mag, trn, r->xform[i].c);
+         if (!all_id) {
+            affine_to_polar(g, n, i, 1, ang, mag, trn);
+            polar_blend(c, n, ang, mag, trn, r->xform[i].post);
+         }
+      } else
+         for (int k = 0; k < n; k++)
+            for (int a = 0; a < 3; a++)
+               for (int b = 0; b < 2; b++) {
+                  r->xform[i].c[a][b] += c[k] * g[k].xform[i].c[a][b];
+                  r->xform[i].post[a][b] += c[k] * g[k].xform[i].post[a][b];
+               }
+      if (all_id) {
+         memset(r->xform[i].post, 0, sizeof(r->xform[i].post));
+         r->xform[i].post[0][0] = 1.0;
+         r->xform[i].post[1][1] = 1.0;
+      }
+   }
+}
+
+int f3b_interpolate(flam3_genome *cps, int ncps, double time, flam3_genome *result) {
+   if (ncps == 1) return f3b_genome_copy(result, &cps[0]);
+   int i1, i2;
+   if (cps[0].time >= time) { i1 = 0; i2 = 1; }
+   else if (cps[ncps - 1].time <= time) { i1 = ncps - 2; i2 = ncps - 1; }
+   else {
+      i1 = 0;
+      while (cps[i1].time < time) i1++;
+      i1--;
+      i2 = i1 + 1;
+   }
+   double c[4];
+   c[0] = (cps[i2].time - time) / (cps[i2].time - cps[i1].time);
+   c[1] = 1.0 - c[0];
+   flam3_genome g[4];
+   memset(g, 0, sizeof(g));
+   int n = 2, smooth = 0;
+   if (cps[i1].interpolation != flam3_interpolation_linear) {
+      if (i1 == 0) fprintf(stderr, "error: cannot use smooth interpolation on first segment.\nreverting to linear interpolation.\n");
+      else if (i2 == ncps - 1) fprintf(stderr, "error: cannot use smooth interpolation on last segment.\nreverting to linear interpolation.\n");
+      else smooth = 1;
+   }
+   if (smooth) {
+      n = 4;
+      if (align_genomes(g, &cps[i1 - 1], 4)) return 1;
+   } else if (align_genomes(g, &cps[i1], 2)) return 1;
+   f3b_genome_init(result, 1);
+   const int g_std = g[0].num_xforms - (g[0].final_xform_index >= 0);
+   for (int i = 0; i < g_std; i++)
+      if (f3b_genome_add_xform(result, 0) < 0) return 1;
+   if (g[0].final_xform_index >= 0 && f3b_genome_add_xform(result, 1) < 0) return 1;
+   result->time = time;
+   result->interpolation = flam3_interpolation_linear;
+   result->interpolation_type = g[0].interpolation_type;
+   result->palette_interpolation = flam3_palette_interpolation_hsv_circular;
+   result->hsv_rgb_palette_blend = 0.0;
+   if (smooth) { /* Catmull-Rom weights of the four key frames (interpolation.c:326-337) */
+      const double t = c[1], t2 = t * t, t3 = t2 * t;
+      c[0] = (2 * t2 - t - t3) / 2;
+      c[1] = (3 * t3 - 5 * t2 + 2) / 2;
+      c[2] = ((4 * t2 + t) - 3 * t3) / 2; /* in this order: the reference's -ffast-math build reassociates the sum */
+      c[3] = (t3 - t2) / 2;
+   }
+   blend_genomes(result, n, g, c);
+   for (int k = 0; k < n; k++) f3b_genome_free_xforms(&g[k]);
+   return 0;
+}
+
 /* ---- output ----------------------------------------------------------------------------- */
 int f3b_write_ppm(const char *path, const void *image, int width, int height, int nchan, int bytes_per_channel) {
    FILE *f = fopen(path, "wb");

@@ -484,13 +484,14 @@ static void f3b_interpolate_cached(flam3_genome *cps, int ncps, double time, fla
       double *out = result->palette[i].color;
       for (int k = 0; k < 3; k++) out[k] = rgb_fraction * new_rgb[k] + (1.0 - rgb_fraction) * back[k];
       out[3] = count;
+      /* (the reference's -ffast-math build clips with max / min instructions: a -0.0 that comes
+       * out of the blend leaves as +0.0) */
       for (int k = 0; k < 4; k++) {
-         if (out[k] < 0.0) out[k] = 0.0;
-         if (out[k] > 1.0) out[k] = 1.0;
+         out[k] = out[k] > 0.0 ? out[k] : 0.0;
+         out[k] = out[k] < 1.0 ? out[k] : 1.0;
       }
-      if (index < 0.0) index = 0.0;
-      if (index > 255.0) index = 255.0;
-      result->palette[i].index = index;
+      index = index > 0.0 ? index : 0.0;
+      result->palette[i].index = index < 255.0 ? index : 255.0;
    }
 }
 

@@ -2,10 +2,9 @@
  * f3b_standalone.c — the handful of libflam3 entry points f3b_render.c calls besides the ones
  * this repository replaces, for programs that link NO reference object at all (tools/f3b-render):
  *
- *   flam3_interpolate   flam3.c:717-802   for ONE key frame, which is all a still render needs
- *                                         (flam3-render passes ngenomes = 1, flam3-render.c:262):
- *                                         a copy of the genome. Several key frames need the
- *                                         reference's interpolation.c; that is said, not guessed.
+ *   flam3_interpolate   flam3.c:717-802   the front end's own f3b_interpolate (f3b_frontend.c):
+ *                                         a copy for one key frame, aligned and blended genomes
+ *                                         between several
  *   clear_cp            flam3.c:1270      reset a genome, free its xforms
  *   flam3_init_frame    flam3.c:2494      seed the frame's ISAAC context from $isaac_seed (or the
  *                                         clock), with irandinit exactly as the reference runs it
@@ -25,13 +24,8 @@
 void clear_cp(flam3_genome *cp, int default_flag) { f3b_genome_init(cp, default_flag == flam3_defaults_on); }
 
 void flam3_interpolate(flam3_genome *cps, int ncps, double time, double stagger, flam3_genome *result) {
-   (void)time;
-   (void)stagger;
-   if (ncps != 1) {
-      fprintf(stderr, "flam3_interpolate (standalone front end): %d key frames given; interpolating between key "
-                      "frames needs libflam3's interpolation.c. Rendering the first one.\n", ncps);
-   }
-   f3b_genome_copy(result, &cps[0]);
+   (void)stagger; /* flam3_render asks without stagger */
+   if (f3b_interpolate(cps, ncps, time, result)) fprintf(stderr, "flam3_interpolate: out of memory\n");
 }
 
 static void mix8(ub4 *v) { /* isaac.c:48-59, deliberately not masked to 32 bits */

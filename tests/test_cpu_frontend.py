@@ -184,6 +184,54 @@ def test_palette_library_and_hue_rotation(tmp_path):
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
 
 
+def _interp_pairs():
+    fx = [f for f in _fixtures() if os.sep + "c5" + os.sep in f]
+    # neighbours in the sorted list: unrelated random genomes with different numbers of xforms,
+    # final xforms on one side only, all 99 variations between them
+    return [(fx[i], fx[(i * 7 + 3) % len(fx)], fx[(i * 11 + 5) % len(fx)], fx[(i * 13 + 1) % len(fx)]) for i in range(0, len(fx), 3)]
+
+
+@pytest.mark.parametrize("quad", _interp_pairs(), ids=lambda q: os.path.basename(q[0])[:-6])
+def test_own_interpolation_equals_flam3_interpolate(gpu, quad):
+    """f3b_interpolate (f3b_frontend.c: own flam3_align / flam3_interpolate_n / Catmull-Rom) against
+    the reference's flam3_interpolate on four unrelated random genomes as key frames: padding
+    xforms and their 'better identities', parameters borrowed from the neighbour in time,
+    log-polar affine parts, palettes - linear segments and a smooth one, inside segments, on
+    and beyond the key frames. Byte for byte (genome struct, xform arrays, chaos matrix)."""
+    import ctypes as C
+    from types import SimpleNamespace
+    import numpy as np
+    from flam3_b200.genome_xml import set_flame_attrs
+    flames = []
+    for k, path in enumerate(quad):
+        x = open(path).read()
+        x = re.sub(r'\btime="[^"]*"', "", x, count=1).replace("<flame ", '<flame time="%d" ' % (k * 40), 1)
+        if k == 1:
+            x = set_flame_attrs(x, interpolation="smooth")
+        flames.append(x)
+    g = gpu.parse("<flames>" + "".join(flames) + "</flames>")
+    assert g.n == 4
+    d = gpu._dll
+    size = gpu.abi_sizes()["flam3_genome"]
+    d.flam3_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
+    d.flam3_interpolate.restype = None
+    d.f3b_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    d.clear_cp.argtypes = [C.c_void_p, C.c_int]
+    for t in (-5.0, 0.0, 13.5, 40.0, 47.25, 79.9, 80.0, 101.0, 120.0, 130.0):
+        ra, rb = (C.c_char * size)(), (C.c_char * size)()
+        d.flam3_interpolate(g.ptr, 4, t, 0.0, ra)
+        assert d.f3b_interpolate(g.ptr, 4, t, rb) == 0
+        (ga, xa, ca), = _raw(gpu, SimpleNamespace(ptr=C.addressof(ra), n=1))
+        (gb, xb, cb), = _raw(gpu, SimpleNamespace(ptr=C.addressof(rb), n=1))
+        diff = [i for i in range(len(ga)) if ga[i] != gb[i]]
+        assert not diff, "t=%g: genome bytes differ at %s" % (t, diff[:12])
+        assert ca == cb, t
+        bad = np.where((xa != xb).any(axis=0))[0]
+        assert bad.size == 0, "t=%g: xform bytes differ at offsets %s" % (t, bad[:16])
+        d.clear_cp(ra, 0)
+        d.clear_cp(rb, 0)
+
+
 def test_own_parser_refuses_what_it_does_not_read(gpu):
     for bad in ('<flame size="10 10"><symmetry kind="0"/><xform weight="1" coefs="1 0 0 1 0 0" linear="1"/></flame>',
                 '<flame size="10 10"><xform weight="1" coefs="1 0 0 1 0 0" linear="1"><motion linear="1"/></xform></flame>',

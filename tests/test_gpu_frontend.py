@@ -54,6 +54,30 @@ def test_standalone_renderer_writes_the_same_bytes(tmp_path, fixture, extra):
 
 
 @pytest.mark.gpu
+def test_standalone_animation_writes_the_same_bytes(tmp_path, flame0, flame1):
+    """Motion-blurred frames between two key frames: f3b-render in its flam3-animate mode (own
+    interpolation: f3b_interpolate for every temporal sample) against the unmodified
+    flam3-animate linked to the drop-in (the reference's flam3_align / flam3_interpolate_n through
+    the cached path). The interpolated genomes are equal byte for byte
+    (tests/test_cpu_frontend.py), so the images are."""
+    from flam3_b200.genome_xml import resize
+    tmp = str(tmp_path)
+    a = resize(flame0, 160, 120, scale=60, quality=20, temporal_samples=24)
+    b = resize(flame1, 160, 120, scale=60, quality=20, temporal_samples=24).replace('time="0"', 'time="10"', 1)
+    path = os.path.join(tmp, "anim.flam3")
+    with open(path, "w") as f:
+        f.write("<flames>" + a + b + "</flames>")
+    _run(OWN, tmp, "own_", path, begin="3", end="4")
+    _run(os.path.join(ROOT, "dropin", "_build", "flam3-animate"), tmp, "cli_", path, begin="3", end="4")
+    own = sorted(f for f in os.listdir(tmp) if f.startswith("own_"))
+    cli = sorted(f for f in os.listdir(tmp) if f.startswith("cli_"))
+    assert own == ["own_00003.ppm", "own_00004.ppm"] and len(cli) == 2
+    for x, y in zip(own, cli):
+        da, db = open(os.path.join(tmp, x), "rb").read(), open(os.path.join(tmp, y), "rb").read()
+        assert len(da) > 1000 and da == db, (x, y)
+
+
+@pytest.mark.gpu
 def test_standalone_renderer_png(tmp_path):
     tmp = str(tmp_path)
     _run(OWN, tmp, "p_", os.path.join(ROOT, "tests", "golden", "test_flame0.flam3"),

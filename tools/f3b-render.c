@@ -14,6 +14,12 @@
  * One image per <flame>, named <prefix>%05d.<format> like flam3-render.c:355. For the same
  * genome file and isaac_seed the bytes equal those of the unmodified flam3-render linked
  * against the drop-in (tests/test_gpu_frontend.py).
+ *
+ * With begin / end / time / frame / dtime in the environment it is flam3-animate instead
+ * (flam3-animate.c:160-290, without fields): the flames are key frames, one motion-blurred
+ * image per time step from `begin` (default: the first key frame's time) to `end` (default: the
+ * last one's - 1), named <prefix>%05d.<format> by time; the genomes between the key frames
+ * come from this front end's own interpolation (f3b_interpolate).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -34,6 +40,43 @@ void write_png(FILE *file, void *image, int width, int height, flam3_img_comment
 static const char *env_or(const char *name, const char *dflt) {
    const char *v = getenv(name);
    return v ? v : dflt;
+}
+
+/* one flam3_render call and its image file */
+static int render_and_write(flam3_frame *f, int width, int height, int channels, int transp, const char *format,
+                            const char *name, int verbose) {
+   const size_t bytes = (size_t)channels * width * height * f->bytes_per_channel;
+   void *image = calloc(bytes, 1);
+   stat_struct stats;
+   if (!image || flam3_render(f, image, flam3_field_both, channels, transp, &stats)) {
+      fprintf(stderr, "error rendering image: aborting.\n");
+      return 1;
+   }
+   if (verbose) fprintf(stderr, "writing %s...", name);
+   if (!strcmp(format, "ppm")) {
+      if (f3b_write_ppm(name, image, width, height, channels, f->bytes_per_channel)) return 1;
+   } else {
+      FILE *fp = fopen(name, "wb");
+      if (!fp) {
+         perror(name);
+         return 1;
+      }
+      flam3_img_comments fpc;
+      memset(&fpc, 0, sizeof(fpc));
+      char badvals[64], iters[64], secs[64];
+      snprintf(badvals, sizeof(badvals), "%g", stats.badvals / (double)(stats.num_iters ? stats.num_iters : 1));
+      snprintf(iters, sizeof(iters), "%g", (double)stats.num_iters);
+      snprintf(secs, sizeof(secs), "%d", stats.render_seconds);
+      fpc.genome = (char *)"";
+      fpc.badvals = badvals;
+      fpc.numiters = iters;
+      fpc.rtime = secs;
+      write_png(fp, image, width, height, &fpc, f->bytes_per_channel);
+      fclose(fp);
+   }
+   if (verbose) fprintf(stderr, "done.\n");
+   free(image);
+   return 0;
 }
 
 int main(void) {
@@ -80,6 +123,67 @@ int main(void) {
    memset(&f, 0, sizeof(f));
    flam3_init_frame(&f);
    const int channels = strcmp(format, "png") ? 3 : 4;
+   f.verbose = verbose;
+   f.bits = bits;
+   f.pixel_aspect_ratio = atof(env_or("pixel_aspect", "1"));
+   f.progress = 0;
+   f.nthreads = atoi(env_or("nthreads", "0"));
+   if (f.nthreads <= 0) f.nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN); /* flam3_count_nthreads, flam3.c:1415 */
+   if (f.nthreads < 1) f.nthreads = 1;
+   f.earlyclip = atoi(env_or("earlyclip", "0"));
+   f.sub_batch_size = atoi(env_or("sub_batch_size", "10000"));
+   f.bytes_per_channel = bpc == 16 ? 2 : 1;
+   if (getenv("begin") || getenv("end") || getenv("time") || getenv("frame") || getenv("dtime")) {
+      /* flam3-animate.c:153-290 */
+      for (int i = 0; i < ncps; i++) {
+         cps[i].sample_density *= qs;
+         cps[i].height = (int)(cps[i].height * ss);
+         cps[i].width = (int)(cps[i].width * ss);
+         cps[i].pixels_per_unit *= ss;
+         if (cps[i].height <= 0 || cps[i].width <= 0) {
+            fprintf(stderr, "output image has dimension <=0, aborting.\n");
+            return 1;
+         }
+         if (i > 0 && cps[i].time <= cps[i - 1].time) {
+            fprintf(stderr, "error: control points must be sorted by time, but %g <= %g, index %d.\n", cps[i].time,
+                    cps[i - 1].time, i);
+            return 1;
+         }
+         if (cps[i].width != cps[0].width || cps[i].height != cps[0].height) {
+            fprintf(stderr, "warning: flame %d at time %g size mismatch.  (%d,%d) should be (%d,%d).\n", i, cps[i].time,
+                    cps[i].width, cps[i].height, cps[0].width, cps[0].height);
+            cps[i].width = cps[0].width;
+            cps[i].height = cps[0].height;
+         }
+      }
+      const char *one = getenv("time") ? getenv("time") : getenv("frame");
+      int first = atoi(env_or("begin", "0")), last = atoi(env_or("end", "0"));
+      const int dtime = atoi(env_or("dtime", "1"));
+      if (one) first = last = atoi(one);
+      else {
+         if (!getenv("begin")) first = (int)cps[0].time;
+         if (!getenv("end")) {
+            last = (int)cps[ncps - 1].time - 1;
+            if (last < first) last = first;
+         }
+      }
+      if (dtime < 1) {
+         fprintf(stderr, "dtime must be positive, not %d.\n", dtime);
+         return 1;
+      }
+      f.genomes = cps;
+      f.ngenomes = ncps;
+      for (int t = first; t <= last; t += dtime) {
+         f.time = (double)t;
+         if (verbose && (last - first) / dtime >= 1) fprintf(stderr, "time = %d/%d/%d\n", t, last, dtime);
+         char name[4096];
+         if (out) snprintf(name, sizeof(name), "%s", out);
+         else snprintf(name, sizeof(name), "%s%05d.%s", prefix, t, format);
+         if (render_and_write(&f, cps[0].width, cps[0].height, channels, transp, format, name, verbose)) return 1;
+      }
+      f3b_free_genomes(cps, ncps);
+      return 0;
+   }
    for (int i = 0; i < ncps; i++) {
       cps[i].ntemporal_samples = 1; /* stills: flam3-render.c:235 */
       cps[i].sample_density *= qs;
@@ -92,51 +196,11 @@ int main(void) {
       }
       f.genomes = &cps[i];
       f.ngenomes = 1;
-      f.verbose = verbose;
-      f.bits = bits;
       f.time = 0.0;
-      f.pixel_aspect_ratio = atof(env_or("pixel_aspect", "1"));
-      f.progress = 0;
-      f.nthreads = atoi(env_or("nthreads", "0"));
-      if (f.nthreads <= 0) f.nthreads = (int)sysconf(_SC_NPROCESSORS_ONLN); /* flam3_count_nthreads, flam3.c:1415 */
-      if (f.nthreads < 1) f.nthreads = 1;
-      f.earlyclip = atoi(env_or("earlyclip", "0"));
-      f.sub_batch_size = atoi(env_or("sub_batch_size", "10000"));
-      f.bytes_per_channel = bpc == 16 ? 2 : 1;
-      const size_t bytes = (size_t)channels * cps[i].width * cps[i].height * f.bytes_per_channel;
-      void *image = calloc(bytes, 1);
-      stat_struct stats;
-      if (!image || flam3_render(&f, image, flam3_field_both, channels, transp, &stats)) {
-         fprintf(stderr, "error rendering image: aborting.\n");
-         return 1;
-      }
       char name[4096];
       if (out) snprintf(name, sizeof(name), "%s", out);
       else snprintf(name, sizeof(name), "%s%05d.%s", prefix, i, format);
-      if (verbose) fprintf(stderr, "writing %s...", name);
-      if (!strcmp(format, "ppm")) {
-         if (f3b_write_ppm(name, image, cps[i].width, cps[i].height, channels, f.bytes_per_channel)) return 1;
-      } else {
-         FILE *fp = fopen(name, "wb");
-         if (!fp) {
-            perror(name);
-            return 1;
-         }
-         flam3_img_comments fpc;
-         memset(&fpc, 0, sizeof(fpc));
-         char badvals[64], iters[64], secs[64];
-         snprintf(badvals, sizeof(badvals), "%g", stats.badvals / (double)(stats.num_iters ? stats.num_iters : 1));
-         snprintf(iters, sizeof(iters), "%g", (double)stats.num_iters);
-         snprintf(secs, sizeof(secs), "%d", stats.render_seconds);
-         fpc.genome = (char *)"";
-         fpc.badvals = badvals;
-         fpc.numiters = iters;
-         fpc.rtime = secs;
-         write_png(fp, image, cps[i].width, cps[i].height, &fpc, f.bytes_per_channel);
-         fclose(fp);
-      }
-      if (verbose) fprintf(stderr, "done.\n");
-      free(image);
+      if (render_and_write(&f, cps[i].width, cps[i].height, channels, transp, format, name, verbose)) return 1;
    }
    f3b_free_genomes(cps, ncps);
    return 0;
