@@ -385,7 +385,7 @@ CORE_SYMBOLS = [
     "f3b_stream_ptr", "f3b_stage_stats", "f3b_stats_reset", "f3b_xfer_stats", "f3b_timer_start",
     "f3b_timer_stop", "f3b_peer_enable", "f3b_hist_reduce_rows", "f3b_group_barrier",
     "f3b_image_reserve", "f3b_image_ptr", "f3b_finish_rows_into", "f3b_ipc_export", "f3b_ipc_open",
-    "f3b_ipc_close", "f3b_device_index", "f3b_orbits", "f3b_debug_counters",
+    "f3b_ipc_close", "f3b_device_index", "f3b_orbits", "f3b_debug_counters", "f3b_debug_stage_layout",
 ]
 
 

@@ -286,6 +286,20 @@ static F3HistLayout hist_layout_for(int width, int height, int count_channel, si
    return L;
 }
 
+/* the staging layout a width x height bucket grid gets (no GPU needed; for the tests):
+ * out = {entries per copy, copies, scramble mask, multiplier, inverse multiplier} */
+int f3b_debug_stage_layout(int width, int height, int count_channel, uint64_t out[5]) {
+   if (width <= 0 || height <= 0 || !out) return 1;
+   size_t elems = 0;
+   const F3HistLayout L = hist_layout_for(width, height, count_channel, &elems);
+   out[0] = L.replica_stride;
+   out[1] = L.replicas;
+   out[2] = L.smask;
+   out[3] = L.smul;
+   out[4] = L.sinv;
+   return 0;
+}
+
 int f3b_frame_begin(f3b_ctx *ctx, int width, int height, int count_channel, int bits) {
    if (!ctx) return 1;
    if (width <= 0 || height <= 0) return fail(ctx, "bad buffer size %dx%d", width, height);

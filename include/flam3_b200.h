@@ -230,6 +230,11 @@ int f3b_xfer_stats(f3b_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
  * bucket's count, [6] staged sums seen at >= 2^24, [7] saturated sums, [10..12] where the former
  * were seen (cold sweep, hot list, merge). For tools. */
 int f3b_debug_counters(f3b_ctx *ctx, uint64_t out[16]);
+/* The layout of the float staging copies in front of the exact buckets for a width x height
+ * grid: out = {entries per copy, copies, scramble mask m, multiplier a, its inverse}. Bucket
+ * b = x + width * y sits at entry (b & ~m) | ((b * a) & m) of a copy (DESIGN.md section 3:
+ * neighbouring buckets must not share L2 sectors). Needs no GPU. */
+int f3b_debug_stage_layout(int width, int height, int count_channel, uint64_t out[5]);
 /* A CUDA-event stopwatch on the context's stream: start records an event, stop records a
  * second one, waits for it and returns the elapsed GPU milliseconds. */
 int f3b_timer_start(f3b_ctx *ctx);

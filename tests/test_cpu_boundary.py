@@ -156,6 +156,29 @@ def test_cached_interpolation_equals_flam3_interpolate(gpu, flame0, flame1, mode
         d.clear_cp(rb, 0)
 
 
+@pytest.mark.parametrize("grid", [(1938, 1098), (658, 498), (1042, 1042), (97, 13)])
+def test_staging_layout_is_a_bijection(grid):
+    """Inside a staging copy bucket b sits at (b & ~m) | ((b * a) & m): a
+    bijection of every aligned block of m + 1 entries, undone with the inverse multiplier, the
+    copy a whole number of blocks, neighbouring buckets at least 128 bytes (8 entries) apart."""
+    import flam3_b200 as fb
+    core = fb.load_core()
+    out = (C.c_uint64 * 5)()
+    core._dll.f3b_debug_stage_layout.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
+    assert core._dll.f3b_debug_stage_layout(grid[0], grid[1], 0, out) == 0
+    stride, copies, m, a, inv = (int(v) for v in out)
+    assert stride >= grid[0] * grid[1] and 1 <= copies <= 4
+    assert m == 255 and stride % (m + 1) == 0
+    assert (a * inv) % 2 ** 32 == 1
+    b = np.arange(0, 4 * (m + 1), dtype=np.uint64) + 7 * (m + 1)
+    s = (b & ~np.uint64(m)) | ((b * np.uint64(a)) & np.uint64(m))
+    assert len(set(s.tolist())) == len(b) and (s >> 8 == b >> 8).all()
+    back = (s & ~np.uint64(m)) | (((s * np.uint64(inv)) & np.uint64(0xFFFFFFFF)) & np.uint64(m))
+    assert (back == b).all()
+    gap = np.abs(s[1:].astype(np.int64) - s[:-1].astype(np.int64))[(b[1:] >> 8) == (b[:-1] >> 8)]
+    assert gap.min() >= 8
+
+
 def test_shard_rule_partitions_groups():
     from flam3_b200.multigpu import shard_groups
 
