@@ -1000,7 +1000,8 @@ void f3b_free_genomes(flam3_genome *g, int n) {
 /* What flam3_interpolate gives flam3_render for a time between key frames: the key frames are
  * padded to the same xforms (flam3_align), everything is blended with the segment's weights -
  * two of them, or four Catmull-Rom weights on smooth segments - the affine parts in log-polar
- * form. Motion elements are not read by this front end, so there are none to apply. Pinned
+ * form; with stagger the xforms take their turns. Motion elements are not read by this front
+ * end, so there are none to apply. Pinned
  * against the reference byte for byte (tests/test_cpu_frontend.py). */
 
 /* which variation a parameter belongs to: its name is the variation's name + "_" + something;
@@ -1246,7 +1247,22 @@ static int is_identity(const double m[3][2]) {
       for (int k_ = 0; k_ < n; k_++) acc_ += c[k_] * g[k_].field;            \
       r->field = (int)rint(acc_);                                            \
    } while (0)
-static void blend_genomes(flam3_genome *r, int n, flam3_genome *g, const double *c) {
+/* get_stagger_coef (interpolation.c:343-367): with stagger the xforms do not blend together but
+ * one after the other, the first xform first; t is the weight of the first key frame */
+static double stagger_weight(double t, double stagger, int nxf, int xf) {
+   const double max_stag = (double)(nxf - 1) / nxf;
+   const double scaled = stagger * max_stag;
+   const double st = scaled * (nxf - 1 - xf) / (nxf - 1);
+   const double et = st + (1 - scaled);
+   if (t <= st) return 0;
+   if (t >= et) return 1;
+   const double u = (t - st) / (1 - scaled);
+   return (3.0 - (u + u)) * (u * u); /* 3u^2 - 2u^3 as the reference's -ffast-math build factors it */
+}
+
+static void blend_genomes(flam3_genome *r, int n, flam3_genome *g, const double *cw, double stagger) {
+   double c[4];
+   for (int k = 0; k < n; k++) c[k] = cw[k];
    if (g[0].palette_interpolation != flam3_palette_interpolation_sweep) {
       double rgb_fraction = 0.0;
       if (g[0].palette_interpolation == flam3_palette_interpolation_rgb) rgb_fraction = 1.0;
@@ -1313,6 +1329,13 @@ static void blend_genomes(flam3_genome *r, int n, flam3_genome *g, const double 
          if (r->chaos[i][j] < 0) r->chaos[i][j] = 0;
       }
    for (int i = 0; i < g[0].num_xforms; i++) {
+      if (n == 2 && stagger > 0 && i != g[0].final_xform_index) {
+         c[0] = stagger_weight(cw[0], stagger, nstd, i);
+         c[1] = 1.0 - c[0];
+      } else {
+         c[0] = cw[0];
+         c[1] = cw[1];
+      }
       BLEND(xform[i].density);
       if (r->xform[i].density < 0.0) r->xform[i].density = 0.0;
       BLEND(xform[i].color);
@@ -1357,7 +1380,7 @@ static void blend_genomes(flam3_genome *r, int n, flam3_genome *g, const double 
    }
 }
 
-int f3b_interpolate(flam3_genome *cps, int ncps, double time, flam3_genome *result) {
+int f3b_interpolate(flam3_genome *cps, int ncps, double time, double stagger, flam3_genome *result) {
    if (ncps == 1) return f3b_genome_copy(result, &cps[0]);
    int i1, i2;
    if (cps[0].time >= time) { i1 = 0; i2 = 1; }
@@ -1400,7 +1423,7 @@ int f3b_interpolate(flam3_genome *cps, int ncps, double time, flam3_genome *resu
       c[2] = ((4 * t2 + t) - 3 * t3) / 2; /* in this order: the reference's -ffast-math build reassociates the sum */
       c[3] = (t3 - t2) / 2;
    }
-   blend_genomes(result, n, g, c);
+   blend_genomes(result, n, g, c, smooth ? 0.0 : stagger);
    for (int k = 0; k < n; k++) f3b_genome_free_xforms(&g[k]);
    return 0;
 }

@@ -24,8 +24,7 @@
 void clear_cp(flam3_genome *cp, int default_flag) { f3b_genome_init(cp, default_flag == flam3_defaults_on); }
 
 void flam3_interpolate(flam3_genome *cps, int ncps, double time, double stagger, flam3_genome *result) {
-   (void)stagger; /* flam3_render asks without stagger */
-   if (f3b_interpolate(cps, ncps, time, result)) fprintf(stderr, "flam3_interpolate: out of memory\n");
+   if (f3b_interpolate(cps, ncps, time, stagger, result)) fprintf(stderr, "flam3_interpolate: out of memory\n");
 }
 
 static void mix8(ub4 *v) { /* isaac.c:48-59, deliberately not masked to 32 bits */

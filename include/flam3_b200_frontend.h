@@ -35,12 +35,13 @@ void f3b_genome_free_xforms(flam3_genome *cp);
 int f3b_genome_add_xform(flam3_genome *cp, int is_final);
 int f3b_genome_copy(flam3_genome *dest, const flam3_genome *src);
 
-/* flam3_interpolate (flam3.c:717-802) without stagger: the genome at `time` between the key
+/* flam3_interpolate (flam3.c:717-802): the genome at `time` between the key
  * frames cps[0..ncps) - aligned copies padded to the same xforms (flam3_align,
  * interpolation.c:768-1032), blended with two weights or, on smooth segments, four Catmull-Rom
- * weights (flam3_interpolate_n, interpolation.c:373-708); affine parts in log-polar form. The
+ * weights (flam3_interpolate_n, interpolation.c:373-708); affine parts in log-polar form; with
+ * stagger > 0 the xforms of a linear segment blend one after the other (get_stagger_coef). The
  * result is what the reference's function gives, byte for byte. Returns 0, or 1 out of memory. */
-int f3b_interpolate(flam3_genome *cps, int ncps, double time, flam3_genome *result);
+int f3b_interpolate(flam3_genome *cps, int ncps, double time, double stagger, flam3_genome *result);
 
 /* binary PPM like flam3-render's format=ppm (flam3-render.c:384-390); 16-bit samples are
  * written big-endian as the format requires */

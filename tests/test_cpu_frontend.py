@@ -197,7 +197,7 @@ def test_own_interpolation_equals_flam3_interpolate(gpu, quad):
     the reference's flam3_interpolate on four unrelated random genomes as key frames: padding
     xforms and their 'better identities', parameters borrowed from the neighbour in time,
     log-polar affine parts, palettes - linear segments and a smooth one, inside segments, on
-    and beyond the key frames. Byte for byte (genome struct, xform arrays, chaos matrix)."""
+    and beyond the key frames, with and without stagger. Byte for byte (genome struct, xform arrays, chaos matrix)."""
     import ctypes as C
     from types import SimpleNamespace
     import numpy as np
@@ -215,19 +215,20 @@ def test_own_interpolation_equals_flam3_interpolate(gpu, quad):
     size = gpu.abi_sizes()["flam3_genome"]
     d.flam3_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
     d.flam3_interpolate.restype = None
-    d.f3b_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+    d.f3b_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p]
     d.clear_cp.argtypes = [C.c_void_p, C.c_int]
-    for t in (-5.0, 0.0, 13.5, 40.0, 47.25, 79.9, 80.0, 101.0, 120.0, 130.0):
+    for t, stagger in ((-5.0, 0.0), (0.0, 0.0), (13.5, 0.0), (40.0, 0.0), (47.25, 0.0), (79.9, 0.0), (80.0, 0.0), (101.0, 0.0),
+                       (120.0, 0.0), (130.0, 0.0), (13.5, 0.3), (29.0, 1.0), (95.0, 0.65), (47.25, 0.5), (3.0, 0.9)):
         ra, rb = (C.c_char * size)(), (C.c_char * size)()
-        d.flam3_interpolate(g.ptr, 4, t, 0.0, ra)
-        assert d.f3b_interpolate(g.ptr, 4, t, rb) == 0
+        d.flam3_interpolate(g.ptr, 4, t, stagger, ra)
+        assert d.f3b_interpolate(g.ptr, 4, t, stagger, rb) == 0
         (ga, xa, ca), = _raw(gpu, SimpleNamespace(ptr=C.addressof(ra), n=1))
         (gb, xb, cb), = _raw(gpu, SimpleNamespace(ptr=C.addressof(rb), n=1))
         diff = [i for i in range(len(ga)) if ga[i] != gb[i]]
-        assert not diff, "t=%g: genome bytes differ at %s" % (t, diff[:12])
+        assert not diff, "t=%g stagger=%g: genome bytes differ at %s" % (t, stagger, diff[:12])
         assert ca == cb, t
         bad = np.where((xa != xb).any(axis=0))[0]
-        assert bad.size == 0, "t=%g: xform bytes differ at offsets %s" % (t, bad[:16])
+        assert bad.size == 0, "t=%g stagger=%g: xform bytes differ at offsets %s" % (t, stagger, bad[:16])
         d.clear_cp(ra, 0)
         d.clear_cp(rb, 0)
 
