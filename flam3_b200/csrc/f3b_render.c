@@ -406,14 +406,28 @@ typedef struct {
    int pal_mode; /* palette_interpolation of the first one (the copy says sweep) */
    flam3_genome cpi[2];
    double hsv[2][256][3]; /* of the copies' palettes, the first one's hue moved next to the second's */
+   /* what clear_cp + flam3_add_xforms leave for the copies' shape: a result that already has
+    * that shape is reset by copying this over it instead of freeing, allocating and
+    * initialising its xforms again for every temporal sample */
+   flam3_genome blank;
 } interp_cache;
 
 static void interp_cache_clear(interp_cache *ic) {
    if (ic->i1 >= 0) {
       clear_cp(&ic->cpi[0], 0);
       clear_cp(&ic->cpi[1], 0);
+      clear_cp(&ic->blank, 0);
    }
    ic->i1 = -1;
+}
+/* flam3.c:774-782: the result as flam3_interpolate prepares it before the blend */
+static void interp_blank(flam3_genome *g, const flam3_genome *shape) {
+   clear_cp(g, 1);
+   if (shape->final_xform_index >= 0) {
+      flam3_add_xforms(g, shape->num_xforms - 1, 0, 0);
+      flam3_add_xforms(g, 1, 0, 1);
+   } else
+      flam3_add_xforms(g, shape->num_xforms, 0, 0);
 }
 
 static void f3b_interpolate_cached(flam3_genome *cps, int ncps, double time, flam3_genome *result, interp_cache *ic) {
@@ -450,16 +464,31 @@ static void f3b_interpolate_cached(flam3_genome *cps, int ncps, double time, fla
          }
          ic->cpi[0].palette_interpolation = flam3_palette_interpolation_sweep;
       }
+      memset(&ic->blank, 0, sizeof(ic->blank));
+      interp_blank(&ic->blank, &ic->cpi[0]);
    }
    double c[2];
    c[0] = (cps[i2].time - time) / (cps[i2].time - cps[i1].time);
    c[1] = 1.0 - c[0];
-   clear_cp(result, 1);
-   if (ic->cpi[0].final_xform_index >= 0) {
-      flam3_add_xforms(result, ic->cpi[0].num_xforms - 1, 0, 0);
-      flam3_add_xforms(result, 1, 0, 1);
+   const flam3_genome *bl = &ic->blank;
+   if (result->xform && result->chaos && result->num_xforms == bl->num_xforms &&
+       result->final_xform_index == bl->final_xform_index) {
+      /* same shape as last time (the previous temporal sample): reset in place */
+      flam3_xform *xf = result->xform;
+      double **chaos = result->chaos;
+      int motion = 0;
+      for (int i = 0; i < result->num_xforms; i++) motion |= xf[i].num_motion;
+      if (motion) interp_blank(result, &ic->cpi[0]); /* (never the case for an interpolated genome) */
+      else {
+         *result = *bl;
+         result->xform = xf;
+         result->chaos = chaos;
+         memcpy(xf, bl->xform, (size_t)bl->num_xforms * sizeof(flam3_xform));
+         const int nstd = bl->num_xforms - (bl->final_xform_index >= 0);
+         for (int i = 0; i < nstd; i++) memcpy(chaos[i], bl->chaos[i], (size_t)nstd * sizeof(double));
+      }
    } else
-      flam3_add_xforms(result, ic->cpi[0].num_xforms, 0, 0);
+      interp_blank(result, &ic->cpi[0]);
    result->time = time;
    result->interpolation = flam3_interpolation_linear;
    result->interpolation_type = ic->cpi[0].interpolation_type;
@@ -500,6 +529,10 @@ int f3b_debug_interpolate(void *cps, int ncps, double time, void *result) {
    interp_cache *ic = (interp_cache *)calloc(1, sizeof(interp_cache));
    if (!ic) return 1;
    ic->i1 = -1;
+   /* twice, as a packer thread goes from one temporal sample to the next: the second call finds
+    * the cache filled and the result shaped (F3B_DEBUG_INTERP_COLD=1: once, from scratch) */
+   if (!getenv("F3B_DEBUG_INTERP_COLD"))
+      f3b_interpolate_cached((flam3_genome *)cps, ncps, time - 0.37, (flam3_genome *)result, ic);
    f3b_interpolate_cached((flam3_genome *)cps, ncps, time, (flam3_genome *)result, ic);
    const int fast = ic->i1 >= 0;
    interp_cache_clear(ic);

@@ -116,8 +116,9 @@ def test_packed_sample_layout(gpu, flame0):
     assert list(w[w[20]: w[20] + 4]) == [4096, 8192, 12288, 16384]
 
 
+@pytest.mark.parametrize("cold", [False, True])
 @pytest.mark.parametrize("mode", ["hsv_circular", "hsv", "rgb", "sweep", "blend"])
-def test_cached_interpolation_equals_flam3_interpolate(gpu, flame0, flame1, mode):
+def test_cached_interpolation_equals_flam3_interpolate(gpu, flame0, flame1, mode, cold, monkeypatch):
     """The genome of a temporal sample (f3b_render.c, f3b_interpolate_cached: aligned copies and
     the palettes' HSV values kept across the samples of a frame) is byte for byte what
     flam3_interpolate makes for the same time: genome struct, xform arrays, chaos matrix -
@@ -126,6 +127,11 @@ def test_cached_interpolation_equals_flam3_interpolate(gpu, flame0, flame1, mode
     from types import SimpleNamespace
     from flam3_b200.genome_xml import set_flame_attrs
     from test_cpu_frontend import _raw
+    # warm (default): the call under test follows another one on the same cache and result, as
+    # one temporal sample follows another in a packer thread (the result is reset in place);
+    # cold: a single call from scratch
+    if cold:
+        monkeypatch.setenv("F3B_DEBUG_INTERP_COLD", "1")
     a = flame0.replace("</flame>", '<finalxform color="0" symmetry="1" linear="0.9" spherical="0.1" '
                        'coefs="1 0 0 1 0.05 0"/></flame>')
     b = flame1.replace('time="0"', 'time="100"', 1)
