@@ -19,11 +19,20 @@
  *    `red.global.add.f32` into the count plane only when the count channel is not
  *    identical to the alpha channel (COUNT=false: palette alpha == 1 and temporal filter
  *    weight == 1 everywhere, the common case, where b[3] == b[4] bucket by bucket);
- *  - instantiations: SIMPLE (classic flames: packed pick, folded flag tests) and AGG
- *    (collapsed attractors: equal buckets of a warp aggregated before the reduction).
+ *  - inside a staging copy a bucket does not sit at x + pitch * y but at a scrambled place
+ *    (f3b_internal.h: F3HistLayout): the hits of an attractor cluster on neighbouring buckets,
+ *    and L2 serialises reductions that meet in the same sectors;
+ *  - instantiations f3b_iterate_kernel<COUNT, KIND, MODE, WU, SINGLE> instead of run-time
+ *    flags - the 72-register loop pays 3-6 % for a few instructions it merely carries:
+ *    KIND 1/2 (SIMPLE: classic flames, packed pick, folded flag tests; 2: and no post affine),
+ *    MODE 1 (AGG: collapsed attractors, equal buckets of a warp aggregated before the
+ *    reduction; also the binned scatter) and 2 (walkers report sampled entries to the sweeper:
+ *    histograms beyond L2), WU (warp-uniform xform step for genomes whose xforms run different
+ *    variation code), SINGLE (one temporal sample: constants as constant-bank operands).
  *
  * Adds are integer valued (floor, like bump_no_overflow with unsigned buckets,
- * flam3.c:3838-3854), so float accumulation is exact up to 2^24 per channel.
+ * flam3.c:3838-3854), so float accumulation is exact up to 2^24 per channel; sweeper warps move
+ * what grows large into the exact uint32 / double buckets while the walkers run (below).
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
