@@ -27,6 +27,7 @@
 #include <ctype.h>
 #include <errno.h>
 #include <math.h>
+#include <stdarg.h>
 #include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -833,7 +834,8 @@ static int flame_from_xml(xmlNode *flame, flam3_genome *cp) {
          if (!rc) { /* premultiplied by alpha */
             const double alpha = rgba[3] * k_inv255;
             cp->palette[index].color[3] = alpha;
-            for (int k = 0; k < 3; k++) cp->palette[index].color[k] = alpha * rgba[k] * k_inv255;
+            /* (r / 255) * alpha, in this order: what the reference's build makes of alpha * r / 255 */
+            for (int k = 0; k < 3; k++) cp->palette[index].color[k] = (rgba[k] * k_inv255) * alpha;
             cp->palette[index].index = index;
          }
       } else if (!strcmp(tag, "colors")) {
@@ -1426,6 +1428,169 @@ int f3b_interpolate(flam3_genome *cps, int ncps, double time, double stagger, fl
    blend_genomes(result, n, g, c, smooth ? 0.0 : stagger);
    for (int k = 0; k < n; k++) f3b_genome_free_xforms(&g[k]);
    return 0;
+}
+
+
+/* ---- writing genomes (flam3_print, flam3_print_xform, flam3.c:1674-2474) ---------------- */
+/* The text flam3_print_to_string gives (no edit history, no 2.7 compatibility mode), character
+ * for character for every fixture (tests/test_cpu_frontend.py). The parameters of a variation
+ * are written when its weight is not zero, in the reference's order: */
+static const struct {
+   int var;
+   const char *params; /* XML names, in print order */
+} k_print_order[] = {
+   {VAR_BLOB, "blob_low blob_high blob_waves"}, {VAR_PDJ, "pdj_a pdj_b pdj_c pdj_d"}, {VAR_FAN2, "fan2_x fan2_y"},
+   {VAR_RINGS2, "rings2_val"}, {VAR_PERSPECTIVE, "perspective_angle perspective_dist"},
+   {VAR_JULIAN, "julian_power julian_dist"}, {VAR_JULIASCOPE, "juliascope_power juliascope_dist"},
+   {VAR_RADIAL_BLUR, "radial_blur_angle"}, {VAR_PIE, "pie_slices pie_rotation pie_thickness"},
+   {VAR_NGON, "ngon_sides ngon_power ngon_corners ngon_circle"}, {VAR_CURL, "curl_c1 curl_c2"},
+   {VAR_RECTANGLES, "rectangles_x rectangles_y"}, {VAR_DISC2, "disc2_rot disc2_twist"},
+   {VAR_SUPER_SHAPE, "super_shape_rnd super_shape_m super_shape_n1 super_shape_n2 super_shape_n3 super_shape_holes"},
+   {VAR_FLOWER, "flower_petals flower_holes"}, {VAR_CONIC, "conic_eccentricity conic_holes"},
+   {VAR_PARABOLA, "parabola_height parabola_width"}, {VAR_BENT2, "bent2_x bent2_y"}, {VAR_BIPOLAR, "bipolar_shift"},
+   {VAR_CELL, "cell_size"}, {VAR_CPOW, "cpow_i cpow_r cpow_power"},
+   {VAR_CURVE, "curve_xamp curve_yamp curve_xlength curve_ylength"}, {VAR_ESCHER, "escher_beta"},
+   {VAR_LAZYSUSAN, "lazysusan_x lazysusan_y lazysusan_spin lazysusan_space lazysusan_twist"},
+   {VAR_MODULUS, "modulus_x modulus_y"},
+   {VAR_OSCILLOSCOPE, "oscilloscope_separation oscilloscope_frequency oscilloscope_amplitude oscilloscope_damping"},
+   {VAR_POPCORN2, "popcorn2_x popcorn2_y popcorn2_c"},
+   /* (separation's four parameters are never written: flam3_print_xform forgets to note that the
+    * variation is present, flam3.c:1945-2030 - a genome loses them on its way through a file) */
+   {VAR_SPLIT, "split_xsize split_ysize"}, {VAR_SPLITS, "splits_x splits_y"}, {VAR_STRIPES, "stripes_space stripes_warp"},
+   {VAR_WEDGE, "wedge_angle wedge_hole wedge_count wedge_swirl"},
+   {VAR_WEDGE_JULIA, "wedge_julia_angle wedge_julia_count wedge_julia_power wedge_julia_dist"},
+   {VAR_WEDGE_SPH, "wedge_sph_angle wedge_sph_hole wedge_sph_count wedge_sph_swirl"},
+   {VAR_WHORL, "whorl_inside whorl_outside"}, {VAR_WAVES2, "waves2_scalex waves2_scaley waves2_freqx waves2_freqy"},
+   {VAR_AUGER, "auger_sym auger_weight auger_freq auger_scale"}, {VAR_FLUX, "flux_spread"},
+   {VAR_MOBIUS, "mobius_re_a mobius_im_a mobius_re_b mobius_im_b mobius_re_c mobius_im_c mobius_re_d mobius_im_d"},
+};
+
+typedef struct {
+   char *s;
+   size_t n, cap;
+   int failed;
+} f3b_text;
+static void text_add(f3b_text *t, const char *fmt, ...) {
+   va_list ap;
+   for (int pass = 0; pass < 2 && !t->failed; pass++) {
+      va_start(ap, fmt);
+      const int need = vsnprintf(t->s + t->n, t->cap - t->n, fmt, ap);
+      va_end(ap);
+      if (need < 0) {
+         t->failed = 1;
+         return;
+      }
+      if ((size_t)need < t->cap - t->n) {
+         t->n += (size_t)need;
+         return;
+      }
+      size_t cap = t->cap * 2 + (size_t)need + 64;
+      char *grown = (char *)realloc(t->s, cap);
+      if (!grown) {
+         t->failed = 1;
+         return;
+      }
+      t->s = grown;
+      t->cap = cap;
+   }
+}
+static const char *word_of(const f3b_word *words, int value) {
+   for (; words->word; words++)
+      if (words->value == value) return words->word;
+   return NULL;
+}
+static double xform_param(const flam3_xform *x, const char *xml_name, size_t len) {
+   char name[64];
+   if (len >= sizeof(name)) return 0.0;
+   memcpy(name, xml_name, len);
+   name[len] = 0;
+   const char *field = name;
+   for (size_t a = 0; a < sizeof(k_xform_aliases) / sizeof(k_xform_aliases[0]); a++)
+      if (!strcmp(name, k_xform_aliases[a].alias)) field = k_xform_aliases[a].name;
+   for (size_t i = 0; i < sizeof(k_xform_params) / sizeof(k_xform_params[0]); i++)
+      if (!strcmp(field, k_xform_params[i].name)) return *(const double *)((const char *)x + k_xform_params[i].off);
+   return 0.0;
+}
+static void print_xform(f3b_text *t, const flam3_xform *x, int is_final, int nstd, const double *chaos_row) {
+   if (is_final) text_add(t, "   <finalxform ");
+   else text_add(t, "   <xform weight=\"%g\" ", x->density);
+   text_add(t, "color=\"%g\" color_speed=\"%g\" ", x->color, x->color_speed);
+   if (!is_final) text_add(t, "animate=\"%g\" ", x->animate);
+   for (int j = 0; j < flam3_nvariations; j++)
+      if (j != VAR_TWINTRIAN && x->var[j] != 0.0) text_add(t, "%s=\"%g\" ", k_variation_names[j], x->var[j]);
+   for (size_t g = 0; g < sizeof(k_print_order) / sizeof(k_print_order[0]); g++) {
+      if (x->var[k_print_order[g].var] == 0.0) continue;
+      for (const char *p = k_print_order[g].params; *p;) {
+         const size_t len = strcspn(p, " ");
+         text_add(t, "%.*s=\"%g\" ", (int)len, p, xform_param(x, p, len));
+         p += len;
+         while (*p == ' ') p++;
+      }
+   }
+   text_add(t, "coefs=\"%g %g %g %g %g %g\"", x->c[0][0], x->c[0][1], x->c[1][0], x->c[1][1], x->c[2][0], x->c[2][1]);
+   if (!is_identity(x->post))
+      text_add(t, " post=\"%g %g %g %g %g %g\"", x->post[0][0], x->post[0][1], x->post[1][0], x->post[1][1], x->post[2][0],
+               x->post[2][1]);
+   if (!is_final) {
+      int ncols = nstd;
+      while (ncols > 0 && chaos_row[ncols - 1] == 1.0) ncols--;
+      if (ncols > 0) {
+         text_add(t, " chaos=\"");
+         for (int j = 0; j < ncols; j++) text_add(t, "%g ", chaos_row[j]);
+         text_add(t, "\"");
+      }
+   }
+   text_add(t, " opacity=\"%g\"/>\n", x->opacity);
+}
+
+char *f3b_print_flam3(const flam3_genome *cp, const char *version, const char *extra_attributes) {
+   f3b_text t = {(char *)malloc(1 << 14), 0, 1 << 14, 0};
+   if (!t.s) return NULL;
+   t.s[0] = 0;
+   text_add(&t, "<flame version=\"%s\" time=\"%g\"", version ? version : "FLAM3-B200", cp->time);
+   if (cp->flame_name[0]) text_add(&t, " name=\"%s\"", cp->flame_name);
+   text_add(&t, " size=\"%d %d\" center=\"%g %g\" scale=\"%g\"", cp->width, cp->height, cp->center[0], cp->center[1],
+            cp->pixels_per_unit);
+   if (cp->zoom != 0.0) text_add(&t, " zoom=\"%g\"", cp->zoom);
+   text_add(&t, " rotate=\"%g\" supersample=\"%d\" filter=\"%g\"", cp->rotate, cp->spatial_oversample, cp->spatial_filter_radius);
+   const char *w = word_of(k_filter_shapes, cp->spatial_filter_select);
+   if (w) text_add(&t, " filter_shape=\"%s\"", w);
+   w = word_of(k_temporal, cp->temporal_filter_type);
+   if (w) text_add(&t, " temporal_filter_type=\"%s\"", w);
+   if (cp->temporal_filter_type == flam3_temporal_exp) text_add(&t, " temporal_filter_exp=\"%g\"", cp->temporal_filter_exp);
+   text_add(&t, " temporal_filter_width=\"%g\" quality=\"%g\" passes=\"%d\" temporal_samples=\"%d\"", cp->temporal_filter_width,
+            cp->sample_density, cp->nbatches, cp->ntemporal_samples);
+   text_add(&t, " background=\"%g %g %g\" brightness=\"%g\" gamma=\"%g\" highlight_power=\"%g\" vibrancy=\"%g\"", cp->background[0],
+            cp->background[1], cp->background[2], cp->brightness, cp->gamma, cp->highlight_power, cp->vibrancy);
+   text_add(&t, " estimator_radius=\"%g\" estimator_minimum=\"%g\" estimator_curve=\"%g\" gamma_threshold=\"%g\"", cp->estimator,
+            cp->estimator_minimum, cp->estimator_curve, cp->gam_lin_thresh);
+   w = word_of(k_palette_mode, cp->palette_mode);
+   if (w) text_add(&t, " palette_mode=\"%s\"", w);
+   if (cp->interpolation != flam3_interpolation_linear) text_add(&t, " interpolation=\"smooth\"");
+   w = cp->interpolation_type == flam3_inttype_compat ? "old" : word_of(k_interp_type, cp->interpolation_type);
+   if (w) text_add(&t, " interpolation_type=\"%s\"", w);
+   w = word_of(k_palette_interp, cp->palette_interpolation);
+   if (w) text_add(&t, " palette_interpolation=\"%s\"", w);
+   if (cp->palette_interpolation == flam3_palette_interpolation_hsv_circular && cp->hsv_rgb_palette_blend > 0.0)
+      text_add(&t, " hsv_rgb_palette_blend=\"%g\"", cp->hsv_rgb_palette_blend);
+   if (extra_attributes) text_add(&t, " %s", extra_attributes);
+   text_add(&t, ">\n");
+   if (cp->symmetry) text_add(&t, "   <symmetry kind=\"%d\"/>\n", cp->symmetry);
+   const int nstd = cp->num_xforms - (cp->final_xform_index >= 0);
+   for (int i = 0; i < cp->num_xforms; i++)
+      print_xform(&t, &cp->xform[i], i == cp->final_xform_index, nstd, i == cp->final_xform_index ? NULL : cp->chaos[i]);
+   for (int i = 0; i < 256; i++) {
+      const double r = cp->palette[i].color[0] * 255.0, g = cp->palette[i].color[1] * 255.0;
+      const double b = cp->palette[i].color[2] * 255.0, a = cp->palette[i].color[3] * 255.0;
+      if (a == 255.0) text_add(&t, "   <color index=\"%d\" rgb=\"%.6g %.6g %.6g\"/>\n", i, r, g, b);
+      else text_add(&t, "      <color index=\"%d\" rgba=\"%.6g %.6g %.6g %.6g\"/>\n", i, r, g, b, a);
+   }
+   text_add(&t, "</flame>\n");
+   if (t.failed) {
+      free(t.s);
+      return NULL;
+   }
+   return t.s;
 }
 
 /* ---- output ----------------------------------------------------------------------------- */

@@ -43,6 +43,12 @@ int f3b_genome_copy(flam3_genome *dest, const flam3_genome *src);
  * result is what the reference's function gives, byte for byte. Returns 0, or 1 out of memory. */
 int f3b_interpolate(flam3_genome *cps, int ncps, double time, double stagger, flam3_genome *result);
 
+/* flam3_print_to_string (flam3.c:1628, flam3_print :1674, flam3_print_xform :1899) without edit
+ * history or 2.7 compatibility: the genome as XML text, character for character what the
+ * reference writes when `version` is its version string ("FLAM3-" + flam3_version(); NULL:
+ * "FLAM3-B200"). malloc'd; NULL when out of memory. */
+char *f3b_print_flam3(const flam3_genome *cp, const char *version, const char *extra_attributes);
+
 /* binary PPM like flam3-render's format=ppm (flam3-render.c:384-390); 16-bit samples are
  * written big-endian as the format requires */
 int f3b_write_ppm(const char *path, const void *image, int width, int height, int nchan, int bytes_per_channel);

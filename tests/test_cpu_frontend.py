@@ -184,6 +184,51 @@ def test_palette_library_and_hue_rotation(tmp_path):
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
 
 
+@pytest.mark.parametrize("path", _fixtures(), ids=lambda p: os.path.basename(p))
+def test_own_writer_equals_the_reference_printer(gpu, path):
+    """f3b_print_flam3 against flam3_print_to_string on every fixture genome: the same text,
+    character for character (attribute order, %g formatting, which variation parameters are
+    written, chaos rows cut after their last non-1 entry, rgb / rgba palette lines)."""
+    import ctypes as C
+    d = gpu._dll
+    d.flam3_version.restype = C.c_char_p
+    version = b"FLAM3-" + d.flam3_version()
+    d.f3b_print_flam3.restype = C.c_void_p
+    d.f3b_print_flam3.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    g = gpu.parse(open(path).read())
+    size = gpu.abi_sizes()["flam3_genome"]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    for i in range(g.n):
+        want = gpu.print_genome(g, i)
+        ptr = d.f3b_print_flam3(g.ptr + i * size, version, None)
+        assert ptr
+        got = C.string_at(ptr).decode()
+        libc.free(ptr)
+        assert got == want
+
+
+def test_own_writer_on_every_attribute(gpu):
+    import ctypes as C
+    d = gpu._dll
+    d.flam3_version.restype = C.c_char_p
+    version = b"FLAM3-" + d.flam3_version()
+    d.f3b_print_flam3.restype = C.c_void_p
+    d.f3b_print_flam3.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    g = gpu.parse(EXTRA)
+    size = gpu.abi_sizes()["flam3_genome"]
+    for i in range(g.n):
+        got = C.string_at(d.f3b_print_flam3(g.ptr + i * size, version, None)).decode()
+        assert got == gpu.print_genome(g, i)
+    # and the text reads back as the reference reads its own text (not as the same genome where a
+    # palette has alpha: flam3_print writes the premultiplied colours, the parser multiplies again)
+    text = "<flames>" + "".join(C.string_at(d.f3b_print_flam3(g.ptr + i * size, version, None)).decode()
+                                for i in range(g.n)) + "</flames>"
+    mine, theirs = gpu.parse_own(text), gpu.parse(text)
+    assert [gpu.print_genome(mine, i) for i in range(mine.n)] == [gpu.print_genome(theirs, i) for i in range(theirs.n)]
+    assert gpu.print_genome(mine, 1) == gpu.print_genome(g, 1) and gpu.print_genome(mine, 2) == gpu.print_genome(g, 2)
+
+
 def _interp_pairs():
     fx = [f for f in _fixtures() if os.sep + "c5" + os.sep in f]
     # neighbours in the sorted list: unrelated random genomes with different numbers of xforms,

@@ -85,3 +85,5 @@ def test_standalone_renderer_png(tmp_path):
     data = open(os.path.join(tmp, "p_00000.png"), "rb").read()
     assert data[:8] == b"\x89PNG\r\n\x1a\n"
     assert data[16:26] == (640).to_bytes(4, "big") + (480).to_bytes(4, "big") + bytes([16, 6])
+    # the genome travels in a text chunk, as with flam3-render (png.c:64-90)
+    assert b"<flame version=" in data and b"</flame>" in data and b"temporal_samples=" in data

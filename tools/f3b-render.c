@@ -45,6 +45,18 @@ static const char *env_or(const char *name, const char *dflt) {
 /* one flam3_render call and its image file */
 static int render_and_write(flam3_frame *f, int width, int height, int channels, int transp, const char *format,
                             const char *name, int verbose) {
+   /* the genome that goes into the PNG's comment: the flame itself, or for an animation frame the
+    * one interpolated at the frame's time (flam3-render.c:367, flam3-animate.c:287-291) */
+   char *genome_text = NULL;
+   if (strcmp(format, "ppm")) {
+      flam3_genome centre;
+      memset(&centre, 0, sizeof(centre));
+      if (f->ngenomes == 1) genome_text = f3b_print_flam3(&f->genomes[0], NULL, NULL);
+      else if (!f3b_interpolate(f->genomes, f->ngenomes, f->time, 0.0, &centre)) {
+         genome_text = f3b_print_flam3(&centre, NULL, NULL);
+         f3b_genome_free_xforms(&centre);
+      }
+   }
    const size_t bytes = (size_t)channels * width * height * f->bytes_per_channel;
    void *image = calloc(bytes, 1);
    stat_struct stats;
@@ -67,7 +79,7 @@ static int render_and_write(flam3_frame *f, int width, int height, int channels,
       snprintf(badvals, sizeof(badvals), "%g", stats.badvals / (double)(stats.num_iters ? stats.num_iters : 1));
       snprintf(iters, sizeof(iters), "%g", (double)stats.num_iters);
       snprintf(secs, sizeof(secs), "%d", stats.render_seconds);
-      fpc.genome = (char *)"";
+      fpc.genome = genome_text ? genome_text : (char *)"";
       fpc.badvals = badvals;
       fpc.numiters = iters;
       fpc.rtime = secs;
@@ -76,6 +88,7 @@ static int render_and_write(flam3_frame *f, int width, int height, int channels,
    }
    if (verbose) fprintf(stderr, "done.\n");
    free(image);
+   free(genome_text);
    return 0;
 }
 
