@@ -39,7 +39,8 @@ def test_standalone_renderer_links_no_reference_code():
 @pytest.mark.gpu
 @pytest.mark.parametrize("fixture,extra", [("test_both.flam3", {}),
                                            ("c5/c5_mix101.flam3", {"qs": "0.05"}),
-                                           ("c5/c5_var33.flam3", {"qs": "0.05", "ss": "0.5", "nthreads": "4"})])
+                                           ("c5/c5_var33.flam3", {"qs": "0.05", "ss": "0.5", "nthreads": "4"}),
+                                           ("test_flame1.flam3", {"qs": "2", "nstrips": "7"})])
 def test_standalone_renderer_writes_the_same_bytes(tmp_path, fixture, extra):
     tmp = str(tmp_path)
     path = os.path.join(ROOT, "tests", "golden", fixture)

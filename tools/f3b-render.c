@@ -6,7 +6,7 @@
  * that matters for stills):
  *
  *    in (default stdin), prefix, out, format (ppm | png), qs, ss, bits (33), bpc (8 | 16, 16 needs png),
- *    nthreads, sub_batch_size, earlyclip, pixel_aspect, transparency, isaac_seed, verbose,
+ *    nthreads, sub_batch_size, earlyclip, pixel_aspect, transparency, isaac_seed, verbose, nstrips,
  *    flam3_palettes, F3B_DEVICE / F3B_DEVICES
  *
  *    env format=ppm prefix=out/ tools/_build/f3b-render < some.flam3
@@ -21,6 +21,7 @@
  * last one's - 1), named <prefix>%05d.<format> by time; the genomes between the key frames
  * come from this front end's own interpolation (f3b_interpolate).
  */
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -42,9 +43,9 @@ static const char *env_or(const char *name, const char *dflt) {
    return v ? v : dflt;
 }
 
-/* one flam3_render call and its image file */
-static int render_and_write(flam3_frame *f, int width, int height, int channels, int transp, const char *format,
-                            const char *name, int verbose) {
+/* the image file of a rendered frame */
+static int write_image(flam3_frame *f, const void *image, const stat_struct *stats, int width, int height, int channels,
+                       const char *format, const char *name, int verbose) {
    /* the genome that goes into the PNG's comment: the flame itself, or for an animation frame the
     * one interpolated at the frame's time (flam3-render.c:367, flam3-animate.c:287-291) */
    char *genome_text = NULL;
@@ -56,13 +57,6 @@ static int render_and_write(flam3_frame *f, int width, int height, int channels,
          genome_text = f3b_print_flam3(&centre, NULL, NULL);
          f3b_genome_free_xforms(&centre);
       }
-   }
-   const size_t bytes = (size_t)channels * width * height * f->bytes_per_channel;
-   void *image = calloc(bytes, 1);
-   stat_struct stats;
-   if (!image || flam3_render(f, image, flam3_field_both, channels, transp, &stats)) {
-      fprintf(stderr, "error rendering image: aborting.\n");
-      return 1;
    }
    if (verbose) fprintf(stderr, "writing %s...", name);
    if (!strcmp(format, "ppm")) {
@@ -76,20 +70,33 @@ static int render_and_write(flam3_frame *f, int width, int height, int channels,
       flam3_img_comments fpc;
       memset(&fpc, 0, sizeof(fpc));
       char badvals[64], iters[64], secs[64];
-      snprintf(badvals, sizeof(badvals), "%g", stats.badvals / (double)(stats.num_iters ? stats.num_iters : 1));
-      snprintf(iters, sizeof(iters), "%g", (double)stats.num_iters);
-      snprintf(secs, sizeof(secs), "%d", stats.render_seconds);
+      snprintf(badvals, sizeof(badvals), "%g", stats->badvals / (double)(stats->num_iters ? stats->num_iters : 1));
+      snprintf(iters, sizeof(iters), "%g", (double)stats->num_iters);
+      snprintf(secs, sizeof(secs), "%d", stats->render_seconds);
       fpc.genome = genome_text ? genome_text : (char *)"";
       fpc.badvals = badvals;
       fpc.numiters = iters;
       fpc.rtime = secs;
-      write_png(fp, image, width, height, &fpc, f->bytes_per_channel);
+      write_png(fp, (void *)image, width, height, &fpc, f->bytes_per_channel);
       fclose(fp);
    }
    if (verbose) fprintf(stderr, "done.\n");
-   free(image);
    free(genome_text);
    return 0;
+}
+/* one flam3_render call and its image file */
+static int render_and_write(flam3_frame *f, int width, int height, int channels, int transp, const char *format,
+                            const char *name, int verbose) {
+   const size_t bytes = (size_t)channels * width * height * f->bytes_per_channel;
+   void *image = calloc(bytes, 1);
+   stat_struct stats;
+   if (!image || flam3_render(f, image, flam3_field_both, channels, transp, &stats)) {
+      fprintf(stderr, "error rendering image: aborting.\n");
+      return 1;
+   }
+   const int rc = write_image(f, image, &stats, width, height, channels, format, name, verbose);
+   free(image);
+   return rc;
 }
 
 int main(void) {
@@ -213,7 +220,50 @@ int main(void) {
       char name[4096];
       if (out) snprintf(name, sizeof(name), "%s", out);
       else snprintf(name, sizeof(name), "%s%05d.%s", prefix, i, format);
-      if (render_and_write(&f, cps[i].width, cps[i].height, channels, transp, format, name, verbose)) return 1;
+      const int nstrips = atoi(env_or("nstrips", "1"));
+      if (nstrips <= 1) {
+         if (render_and_write(&f, cps[i].width, cps[i].height, channels, transp, format, name, verbose)) return 1;
+         continue;
+      }
+      /* nstrips (flam3-render.c:277-345): the frame as horizontal strips, each one a render of a
+       * genome with the strip's height and centre and nstrips times the quality, all from the
+       * same state of the frame's random context */
+      if (nstrips > cps[i].height) {
+         fprintf(stderr, "cannot have more strips than rows but %d>%d.\n", nstrips, cps[i].height);
+         return 1;
+      }
+      const int full_h = cps[i].height, strip_h = (int)ceil(full_h / (double)nstrips);
+      const double cy = cps[i].center[1], ppu = cps[i].pixels_per_unit * pow(2.0, cps[i].zoom), q = cps[i].sample_density;
+      const size_t row_bytes = (size_t)cps[i].width * channels * f.bytes_per_channel;
+      char *image = (char *)calloc(row_bytes, (size_t)full_h);
+      if (!image) return 1;
+      const double first_centre = cy - ((nstrips - 1) * strip_h) / (2 * ppu);
+      const randctx rc0 = f.rc;
+      stat_struct stats, total;
+      memset(&total, 0, sizeof(total));
+      cps[i].sample_density = q * nstrips;
+      for (int strip = 0; strip < nstrips; strip++) {
+         cps[i].height = strip_h;
+         cps[i].center[1] = first_centre + strip_h * (double)strip / ppu;
+         if (strip_h * (strip + 1) > full_h) { /* the last strip may be shorter */
+            cps[i].height = full_h - strip_h * strip;
+            cps[i].center[1] -= (strip_h - cps[i].height) * 0.5 / ppu;
+         }
+         f.rc = rc0;
+         if (verbose) fprintf(stderr, "strip = %d/%d\n", strip + 1, nstrips);
+         if (flam3_render(&f, image + (size_t)strip_h * strip * row_bytes, flam3_field_both, channels, transp, &stats)) {
+            fprintf(stderr, "error rendering image: aborting.\n");
+            return 1;
+         }
+         total.badvals += stats.badvals;
+         total.num_iters += stats.num_iters;
+         total.render_seconds += stats.render_seconds;
+      }
+      cps[i].sample_density = q;
+      cps[i].height = full_h;
+      cps[i].center[1] = cy;
+      if (write_image(&f, image, &total, cps[i].width, full_h, channels, format, name, verbose)) return 1;
+      free(image);
    }
    f3b_free_genomes(cps, ncps);
    return 0;
