@@ -19,7 +19,7 @@
  * libxml2 works the same).
  *
  * Deliberately NOT read (an error says so instead of guessing): <symmetry kind="0"> (a random
- * symmetry), motion elements, the pre-2008 two-palette <palette index0= ...> blend, <edit> history (skipped
+ * symmetry), the pre-2008 two-palette <palette index0= ...> blend, <edit> history (skipped
  * silently: it does not affect rendering). Parity: for every fixture genome the reference's
  * own printer (flam3_print_to_string) gives the same text for the genome parsed here as for
  * the one parsed by the reference (tests/test_cpu_frontend.py).
@@ -636,7 +636,7 @@ typedef struct {
    double scalar;
 } xaos_entry;
 
-static int xform_from_xml(xmlNode *node, flam3_xform *x, int std_index, xaos_entry **xaos, int *nxaos) {
+static int xform_from_xml(xmlNode *node, flam3_xform *x, int std_index, xaos_entry **xaos, int *nxaos, int motion) {
    if (!node->properties) {
       fprintf(stderr, "Error: No attributes for element.\n");
       return 1;
@@ -654,7 +654,10 @@ static int xform_from_xml(xmlNode *node, flam3_xform *x, int std_index, xaos_ent
       else if (!strcmp(name, "animate")) x->animate = to_double(val);
       else if (!strcmp(name, "opacity")) x->opacity = to_double(val);
       else if (!strcmp(name, "plotmode")) {
-         if (!strcmp(val, "off")) x->opacity = 0.0;
+         if (motion) {
+            fprintf(stderr, "error: motion element cannot have a plotmode attribute.\n");
+            rc = 1;
+         } else if (!strcmp(val, "off")) x->opacity = 0.0;
       } else if (!strcmp(name, "color")) { /* one coordinate; an old second one is read and dropped */
          double two[2];
          x->color = 0.0;
@@ -688,6 +691,9 @@ static int xform_from_xml(xmlNode *node, flam3_xform *x, int std_index, xaos_ent
             fprintf(stderr, "error: bad value in var attribute '%s'\n", val);
             rc = 1;
          }
+      } else if (!strcmp(name, "chaos") && motion) {
+         fprintf(stderr, "error: motion element cannot have a chaos attribute.\n");
+         rc = 1;
       } else if (!strcmp(name, "chaos")) {
          /* entries that are not 1 are remembered and applied when all xforms are known */
          int to = 0;
@@ -704,9 +710,15 @@ static int xform_from_xml(xmlNode *node, flam3_xform *x, int std_index, xaos_ent
                (*nxaos)++;
             }
          }
-      } else if (!strcmp(name, "motion_frequency") || !strcmp(name, "motion_function")) {
-         fprintf(stderr, "Error: Motion parameters should not be specified in xforms.\n");
-         rc = 1;
+      } else if (!strcmp(name, "motion_frequency")) x->motion_freq = to_int(val);
+      else if (!strcmp(name, "motion_function")) {
+         if (!strcmp(val, "sin")) x->motion_func = MOTION_SIN;
+         else if (!strcmp(val, "triangle")) x->motion_func = MOTION_TRIANGLE;
+         else if (!strcmp(val, "hill")) x->motion_func = MOTION_HILL;
+         else {
+            fprintf(stderr, "Error: unknown motion function '%s'\n", val);
+            rc = 1;
+         }
       } else if (!strcmp(name, "super_shape_rnd")) {
          const double v = to_double(val);
          x->super_shape_rnd = v < 0 ? 0 : (v > 1 ? 1 : v);
@@ -730,10 +742,22 @@ static int xform_from_xml(xmlNode *node, flam3_xform *x, int std_index, xaos_ent
       xmlFree(val);
       if (rc) return 1;
    }
+   if (motion) return 0;
+   if (x->motion_freq != 0 || x->motion_func != 0) {
+      fprintf(stderr, "Error: Motion parameters should not be specified in xforms.\n");
+      return 1;
+   }
+   /* <motion> children (parser.c:763-777): xforms that start from all zeros and say what to add
+    * to their parent, as a function of time, when flam3-genome builds sequences; a render does
+    * not look at them */
    for (xmlNode *c = node->children; c; c = c->next)
       if (c->type == XML_ELEMENT_NODE && !xmlStrcmp(c->name, (const xmlChar *)"motion")) {
-         fprintf(stderr, "f3b_parse_flam3: motion elements are not supported by this front end\n");
-         return 1;
+         flam3_xform *grown = (flam3_xform *)realloc(x->motion, (size_t)(x->num_motion + 1) * sizeof(flam3_xform));
+         if (!grown) return 1;
+         x->motion = grown;
+         memset(&x->motion[x->num_motion], 0, sizeof(flam3_xform));
+         x->num_motion++;
+         if (xform_from_xml(c, &x->motion[x->num_motion - 1], 0, NULL, NULL, 1)) return 1;
       }
    return 0;
 }
@@ -887,7 +911,7 @@ static int flame_from_xml(xmlNode *flame, flam3_genome *cp) {
             break;
          }
          cp->xform[at].var[0] = 0.0;
-         rc = xform_from_xml(c, &cp->xform[at], is_final ? -1 : nstd, &xaos, &nxaos);
+         rc = xform_from_xml(c, &cp->xform[at], is_final ? -1 : nstd, &xaos, &nxaos, 0);
          if (!rc && is_final && cp->xform[at].density != 0.0) {
             fprintf(stderr, "Error: Final xforms should not have weight specified.\n");
             rc = 1;
@@ -1454,8 +1478,10 @@ static const struct {
    {VAR_MODULUS, "modulus_x modulus_y"},
    {VAR_OSCILLOSCOPE, "oscilloscope_separation oscilloscope_frequency oscilloscope_amplitude oscilloscope_damping"},
    {VAR_POPCORN2, "popcorn2_x popcorn2_y popcorn2_c"},
-   /* (separation's four parameters are never written: flam3_print_xform forgets to note that the
-    * variation is present, flam3.c:1945-2030 - a genome loses them on its way through a file) */
+   /* (for an xform separation's four parameters are never written: flam3_print_xform forgets to
+    * note that the variation is present, flam3.c:1945-2030 - a genome loses them on its way
+    * through a file; motion elements do write them) */
+   {-VAR_SEPARATION, "separation_x separation_y separation_xinside separation_yinside"},
    {VAR_SPLIT, "split_xsize split_ysize"}, {VAR_SPLITS, "splits_x splits_y"}, {VAR_STRIPES, "stripes_space stripes_warp"},
    {VAR_WEDGE, "wedge_angle wedge_hole wedge_count wedge_swirl"},
    {VAR_WEDGE_JULIA, "wedge_julia_angle wedge_julia_count wedge_julia_power wedge_julia_dist"},
@@ -1511,6 +1537,38 @@ static double xform_param(const flam3_xform *x, const char *xml_name, size_t len
       if (!strcmp(field, k_xform_params[i].name)) return *(const double *)((const char *)x + k_xform_params[i].off);
    return 0.0;
 }
+static int is_zero_matrix(const double m[3][2]) {
+   return m[0][0] == 0.0 && m[0][1] == 0.0 && m[1][0] == 0.0 && m[1][1] == 0.0 && m[2][0] == 0.0 && m[2][1] == 0.0;
+}
+/* a <motion> element: only what is not zero, the parameters under their FIELD names with %f
+ * (flam3.c:1896, 2291-2440) */
+static void print_motion(f3b_text *t, const flam3_xform *x) {
+   text_add(t, "      <motion motion_frequency=\"%d\" ", x->motion_freq);
+   if (x->motion_func == MOTION_SIN) text_add(t, "motion_function=\"sin\" ");
+   else if (x->motion_func == MOTION_TRIANGLE) text_add(t, "motion_function=\"triangle\" ");
+   else if (x->motion_func == MOTION_HILL) text_add(t, "motion_function=\"hill\" ");
+   if (x->color != 0.0) text_add(t, "color=\"%g\" ", x->color);
+   if (x->color_speed != 0.0) text_add(t, "color_speed=\"%g\" ", x->color_speed);
+   for (int j = 0; j < flam3_nvariations; j++)
+      if (j != VAR_TWINTRIAN && x->var[j] != 0.0) text_add(t, "%s=\"%g\" ", k_variation_names[j], x->var[j]);
+   for (size_t g = 0; g < sizeof(k_print_order) / sizeof(k_print_order[0]); g++)
+      for (const char *p = k_print_order[g].params; *p;) {
+         const size_t len = strcspn(p, " ");
+         const double v = xform_param(x, p, len);
+         if (v != 0.0) {
+            if (!strncmp(p, "oscilloscope_", 13)) text_add(t, "oscope_%.*s=\"%f\" ", (int)(len - 13), p + 13, v);
+            else text_add(t, "%.*s=\"%f\" ", (int)len, p, v);
+         }
+         p += len;
+         while (*p == ' ') p++;
+      }
+   if (!is_zero_matrix(x->c))
+      text_add(t, "coefs=\"%g %g %g %g %g %g\"", x->c[0][0], x->c[0][1], x->c[1][0], x->c[1][1], x->c[2][0], x->c[2][1]);
+   if (!is_zero_matrix(x->post))
+      text_add(t, " post=\"%g %g %g %g %g %g\"", x->post[0][0], x->post[0][1], x->post[1][0], x->post[1][1], x->post[2][0],
+               x->post[2][1]);
+   text_add(t, "/>\n");
+}
 static void print_xform(f3b_text *t, const flam3_xform *x, int is_final, int nstd, const double *chaos_row) {
    if (is_final) text_add(t, "   <finalxform ");
    else text_add(t, "   <xform weight=\"%g\" ", x->density);
@@ -1519,7 +1577,7 @@ static void print_xform(f3b_text *t, const flam3_xform *x, int is_final, int nst
    for (int j = 0; j < flam3_nvariations; j++)
       if (j != VAR_TWINTRIAN && x->var[j] != 0.0) text_add(t, "%s=\"%g\" ", k_variation_names[j], x->var[j]);
    for (size_t g = 0; g < sizeof(k_print_order) / sizeof(k_print_order[0]); g++) {
-      if (x->var[k_print_order[g].var] == 0.0) continue;
+      if (k_print_order[g].var < 0 || x->var[k_print_order[g].var] == 0.0) continue;
       for (const char *p = k_print_order[g].params; *p;) {
          const size_t len = strcspn(p, " ");
          text_add(t, "%.*s=\"%g\" ", (int)len, p, xform_param(x, p, len));
@@ -1540,7 +1598,13 @@ static void print_xform(f3b_text *t, const flam3_xform *x, int is_final, int nst
          text_add(t, "\"");
       }
    }
-   text_add(t, " opacity=\"%g\"/>\n", x->opacity);
+   text_add(t, " opacity=\"%g\"", x->opacity);
+   if (x->num_motion > 0) {
+      text_add(t, ">\n");
+      for (int m = 0; m < x->num_motion; m++) print_motion(t, &x->motion[m]);
+      text_add(t, is_final ? "   </finalxform>\n" : "   </xform>\n");
+   } else
+      text_add(t, "/>\n");
 }
 
 char *f3b_print_flam3(const flam3_genome *cp, const char *version, const char *extra_attributes) {

@@ -332,3 +332,9 @@ int h_xform_nondata_ranges(int *out) {
 #undef SPAN
    return n / 2;
 }
+/* the motion elements of xform xf of genome idx (raw), *n = how many */
+const void *h_xform_motion(void *cps, int idx, int xf, int *n) {
+   flam3_genome *g = (flam3_genome *)cps + idx;
+   *n = g->xform[xf].num_motion;
+   return g->xform[xf].motion;
+}

@@ -64,7 +64,20 @@ def _raw(lib, genomes):
             xs[:, xranges[2 * k]:xranges[2 * k] + xranges[2 * k + 1]] = 0
         nstd = num.value - (1 if fin.value >= 0 else 0)
         chaos = [[d.h_genome_chaos_row(genomes.ptr, i, r)[c] for c in range(nstd)] for r in range(nstd)]
-        out.append((bytes(g), xs, chaos))
+        # motion elements ride along with the xform array: same masks, one row each
+        d.h_xform_motion.restype = C.c_void_p
+        d.h_xform_motion.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        rows = [xs]
+        for xf in range(num.value):
+            nm = C.c_int()
+            mp = d.h_xform_motion(genomes.ptr, i, xf, C.byref(nm))
+            if nm.value:
+                m = np.frombuffer(C.string_at(mp, nm.value * sizes["flam3_xform"]), dtype=np.uint8).reshape(nm.value, -1).copy()
+                for k in range(nx):
+                    m[:, xranges[2 * k]:xranges[2 * k] + xranges[2 * k + 1]] = 0
+                m[:, 0] ^= np.uint8(xf + 1)   # (tie the rows to their xform)
+                rows.append(m)
+        out.append((bytes(g), np.concatenate(rows), chaos))
     return out
 
 
@@ -278,9 +291,50 @@ def test_own_interpolation_equals_flam3_interpolate(gpu, quad):
         d.clear_cp(rb, 0)
 
 
+MOTION = """
+<flame time="0" size="64 48" center="0 0" scale="20">
+   <xform weight="0.5" color="0.3" coefs="1 0.1 -0.1 1 0.2 0.3" linear="0.5" julian="0.4" julian_power="3" julian_dist="0.8">
+      <motion motion_frequency="2" motion_function="sin" color="0.1" julian_power="1.5" coefs="0 0 0 0 0.3 0"/>
+      <motion motion_frequency="1" motion_function="hill" linear="0.25" oscilloscope_frequency="0.5" oscope_damping="0.125"
+              separation_x="0.2" post="0.1 0 0 0.1 0 0" color_speed="0.05"/>
+   </xform>
+   <xform weight="0.5" color="1" coefs="0.5 0 0 0.5 0.5 0" spherical="1" oscilloscope="0.2"/>
+   <finalxform color="0" coefs="1 0 0 1 0 0" linear="1">
+      <motion motion_frequency="3" motion_function="triangle" coefs="0 0.2 -0.2 0 0 0"/>
+   </finalxform>
+   <color index="0" rgb="255 0 0"/><color index="255" rgb="0 0 255"/>
+</flame>
+"""
+
+
+def test_motion_elements(gpu):
+    """<motion> children of xforms (parser.c:763-777; they act in flam3-genome's sequences only):
+    read into the same bytes as the reference's parser, written like the reference's printer
+    (field names, %f, only what is not zero), and the text reads back alike."""
+    import ctypes as C
+    import numpy as np
+    a, b = _raw(gpu, gpu.parse(MOTION)), _raw(gpu, gpu.parse_own(MOTION))
+    assert a[0][0] == b[0][0] and a[0][2] == b[0][2]
+    assert a[0][1].shape == b[0][1].shape and a[0][1].shape[0] == 3 + 3 and np.array_equal(a[0][1], b[0][1])
+    d = gpu._dll
+    d.flam3_version.restype = C.c_char_p
+    d.f3b_print_flam3.restype = C.c_void_p
+    d.f3b_print_flam3.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+    g = gpu.parse(MOTION)
+    want = gpu.print_genome(g, 0)
+    got = C.string_at(d.f3b_print_flam3(g.ptr, b"FLAM3-" + d.flam3_version(), None)).decode()
+    assert "<motion motion_frequency" in want and got == want
+    again_a, again_b = _raw(gpu, gpu.parse(got)), _raw(gpu, gpu.parse_own(got))
+    assert np.array_equal(again_a[0][1], again_b[0][1]) and again_a[0][0] == again_b[0][0]
+    for bad in ('<flame size="10 10"><xform weight="1" coefs="1 0 0 1 0 0" motion_frequency="2"/></flame>',
+                '<flame size="10 10"><xform weight="1" coefs="1 0 0 1 0 0"><motion motion_function="saw"/></xform></flame>',
+                '<flame size="10 10"><xform weight="1" coefs="1 0 0 1 0 0"><motion motion_function="sin" chaos="1 2"/></xform></flame>'):
+        with pytest.raises(ValueError):
+            gpu.parse_own(bad)
+
+
 def test_own_parser_refuses_what_it_does_not_read(gpu):
     for bad in ('<flame size="10 10"><symmetry kind="0"/><xform weight="1" coefs="1 0 0 1 0 0" linear="1"/></flame>',
-                '<flame size="10 10"><xform weight="1" coefs="1 0 0 1 0 0" linear="1"><motion linear="1"/></xform></flame>',
                 '<flame size="10 10"><palette index0="1" index1="2" blend="0.5"/><xform weight="1" coefs="1 0 0 1 0 0"/></flame>',
                 '<flame size="10 oops"><xform weight="1" coefs="1 0 0 1 0 0"/></flame>',
                 '<flame size="10 10"><xform weight="1x" coefs="1 0 0 1 0 0"/></flame>'):
