@@ -18,9 +18,8 @@
  * (this repository's mini-DOM behind the libxml2 entry points the reference uses; a real
  * libxml2 works the same).
  *
- * Deliberately NOT read (an error says so instead of guessing): <symmetry kind="0"> (a random
- * symmetry), the pre-2008 two-palette <palette index0= ...> blend, <edit> history (skipped
- * silently: it does not affect rendering). Parity: for every fixture genome the reference's
+ * Deliberately NOT read (an error says so instead of guessing): the pre-2008 two-palette
+ * <palette index0= ...> blend; <edit> history is skipped silently (it does not affect rendering). Parity: for every fixture genome the reference's
  * own printer (flam3_print_to_string) gives the same text for the genome parsed here as for
  * the one parsed by the reference (tests/test_cpu_frontend.py).
  */
@@ -379,10 +378,14 @@ static int symmetry_order(const flam3_xform *a, const flam3_xform *b) {
 }
 static int add_symmetry(flam3_genome *cp, int kind) {
    if (kind == 0) {
-      fprintf(stderr, "f3b_parse_flam3: <symmetry kind=\"0\"/> (a random symmetry) is not supported by this front end\n");
-      return -1;
+      /* a symmetry drawn from the C library's random(), with the reference's odds and in its
+       * order of draws (flam3.c:2564-2579): the same state of random() gives the same genome */
+      static const int common[] = {-4, -3, -2, -2, -2, -1, -1, -1, 2, 2, 2, 3, 3, 4, 4};
+      if (random() & 1) kind = common[random() % (long)(sizeof(common) / sizeof(common[0]))];
+      else if (random() & 31) kind = (int)(random() % 13) - 6;
+      else kind = (int)(random() % 51) - 25;
    }
-   if (kind == 1) return 0;
+   if (kind == 1 || kind == 0) return 0;
    cp->symmetry = kind;
    int added = 0;
    for (int pass = (kind < 0 ? 0 : 1), n = kind < 0 ? -kind : kind, k = 1; pass < 2 || k < n;) {

@@ -333,8 +333,27 @@ def test_motion_elements(gpu):
             gpu.parse_own(bad)
 
 
+def test_random_symmetry_follows_the_c_library(gpu):
+    """<symmetry kind="0"/>: a symmetry drawn from random(). From the same state of the C
+    library's generator both parsers draw the same one and add the same xforms."""
+    import ctypes as C
+    libc = C.CDLL(None)
+    xml = '<flame size="10 10"><symmetry kind="0"/><xform weight="1" color="0.3" coefs="0.5 0 0 0.5 0.1 0" linear="1"/></flame>'
+    kinds = set()
+    for seed in range(1, 40):
+        libc.srandom(seed)
+        a = gpu.parse(xml)
+        libc.srandom(seed)
+        b = gpu.parse_own(xml)
+        ta, tb = gpu.print_genome(a, 0), gpu.print_genome(b, 0)
+        assert ta == tb, seed
+        m = re.search(r'<symmetry kind="(-?\d+)"', ta)
+        kinds.add(int(m.group(1)) if m else 1)
+    assert len(kinds) >= 6, kinds
+
+
 def test_own_parser_refuses_what_it_does_not_read(gpu):
-    for bad in ('<flame size="10 10"><symmetry kind="0"/><xform weight="1" coefs="1 0 0 1 0 0" linear="1"/></flame>',
+    for bad in (
                 '<flame size="10 10"><palette index0="1" index1="2" blend="0.5"/><xform weight="1" coefs="1 0 0 1 0 0"/></flame>',
                 '<flame size="10 oops"><xform weight="1" coefs="1 0 0 1 0 0"/></flame>',
                 '<flame size="10 10"><xform weight="1x" coefs="1 0 0 1 0 0"/></flame>'):
