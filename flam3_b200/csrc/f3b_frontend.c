@@ -18,8 +18,7 @@
  * (this repository's mini-DOM behind the libxml2 entry points the reference uses; a real
  * libxml2 works the same).
  *
- * Deliberately NOT read (an error says so instead of guessing): the pre-2008 two-palette
- * <palette index0= ...> blend; <edit> history is skipped silently (it does not affect rendering). Parity: for every fixture genome the reference's
+ * <edit> history is skipped silently (it does not affect rendering). Parity: for every fixture genome the reference's
  * own printer (flam3_print_to_string) gives the same text for the genome parsed here as for
  * the one parsed by the reference (tests/test_cpu_frontend.py).
  */
@@ -878,25 +877,61 @@ static int flame_from_xml(xmlNode *flame, flam3_genome *cp) {
             xmlFree(val);
          }
       } else if (!strcmp(tag, "palette")) {
-         int count = 0, bytes = 0;
+         int count = 0, bytes = 0, old_style = 0, new_style = 0;
+         int index0 = flam3_palette_random, index1 = flam3_palette_random;
+         double hue0 = 0.0, hue1 = 0.0, blend = 0.5;
+         if (!c->properties) {
+            fprintf(stderr, "Error:  No attributes for palette element.\n");
+            rc = 1;
+         }
          for (xmlAttrPtr a = c->properties; a && !rc; a = a->next) {
             char *val = (char *)xmlGetProp(c, a->name);
             const char *an = (const char *)a->name;
-            if (!strcmp(an, "count")) count = to_int(val);
+            if (!strcmp(an, "count")) count = to_int(val), new_style++;
             else if (!strcmp(an, "format")) {
+               new_style++;
                bytes = !strcmp(val, "RGB") ? 3 : (!strcmp(val, "RGBA") ? 4 : 0);
                if (!bytes) {
                   fprintf(stderr, "Error: Unrecognized palette format string (%s)\n", val);
                   rc = 1;
                }
-            } else {
-               fprintf(stderr, "f3b_parse_flam3: palette attribute '%s' (the old two-palette blend) is not "
-                               "supported by this front end\n", an);
+            } else if (!strcmp(an, "index0")) index0 = to_int(val), old_style++;
+            else if (!strcmp(an, "index1")) index1 = to_int(val), old_style++;
+            else if (!strcmp(an, "hue0")) hue0 = to_double(val), old_style++;
+            else if (!strcmp(an, "hue1")) hue1 = to_double(val), old_style++;
+            else if (!strcmp(an, "blend")) blend = to_double(val), old_style++;
+            else {
+               fprintf(stderr, "Error:  Unknown palette attribute '%s'\n", an);
                rc = 1;
             }
             xmlFree(val);
          }
-         if (!rc) {
+         if (!rc && old_style && new_style) {
+            fprintf(stderr, "Error: mixing of old and new palette tag syntax not allowed.\n");
+            rc = 1;
+         }
+         if (!rc && old_style) {
+            /* the pre-2008 way (interpolate_cmap, interpolation.c:149-192): two palettes of the
+             * library, rotated in hue, blended in HSV the shorter way round the hue circle */
+            flam3_palette p0, p1;
+            if (f3b_get_palette(index0, p0, hue0) < 0) fprintf(stderr, "unable to retrieve palette %d, setting to white\n", index0);
+            if (f3b_get_palette(index1, p1, hue1) < 0) fprintf(stderr, "unable to retrieve palette %d, setting to white\n", index1);
+            for (int i = 0; i < 256; i++) {
+               double s5[5], t5[5];
+               rgb_to_hsv(p0[i].color, s5);
+               rgb_to_hsv(p1[i].color, t5);
+               s5[3] = p0[i].color[3];
+               t5[3] = p1[i].color[3];
+               s5[4] = p0[i].index;
+               t5[4] = p1[i].index;
+               if (s5[0] - t5[0] > 3.0) s5[0] -= 6.0;
+               if (s5[0] - t5[0] < -3.0) s5[0] += 6.0;
+               for (int j = 0; j < 5; j++) t5[j] = ((1.0 - blend) * s5[j]) + (blend * t5[j]);
+               hsv_to_rgb(t5, cp->palette[i].color);
+               cp->palette[i].color[3] = t5[3];
+               cp->palette[i].index = t5[4];
+            }
+         } else if (!rc) {
             char *text = (char *)xmlNodeGetContent(c);
             rc = hex_colors(text ? text : "", cp, count, bytes ? bytes : 3);
             if (text) xmlFree(text);

@@ -17,8 +17,7 @@ extern "C" {
 /* flam3_parse_xml2 (flam3.c:1423-1520) with scan_for_flame_nodes / parse_flame_element /
  * parse_xform_xml (parser.c:220-1257): every <flame> of the XML text, in document order.
  * defaults_on = flam3_defaults_on / flam3_defaults_off. Returns NULL (after a message on
- * stderr) on any error, including the one element this front end does not read: the old
- * two-palette <palette index0=...> blend. Free with
+ * stderr) on any error. Free with
  * f3b_free_genomes. */
 flam3_genome *f3b_parse_flam3(const char *xmltext, int defaults_on, int *ncps);
 void f3b_free_genomes(flam3_genome *genomes, int n);

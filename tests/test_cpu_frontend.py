@@ -162,21 +162,24 @@ import test_cpu_frontend as T
 lib = fb.load_dropin()
 xml = '<flames>' + ''.join(
     '<flame time="%%d" size="32 32" palette="%%d" hue="%%s"><xform weight="1" color="0" coefs="1 0 0 1 0 0" linear="1"/></flame>'
-    %% (i, n, h) for i, (n, h) in enumerate([(3, "0"), (3, "0.37"), (11, "-0.2"), (42, "0.999"), (42, "2.5")])) + '</flames>'
+    %% (i, n, h) for i, (n, h) in enumerate([(3, "0"), (3, "0.37"), (11, "-0.2"), (42, "0.999"), (42, "2.5")])) + ''.join(
+    '<flame time="%%d" size="32 32"><palette index0="%%d" hue0="%%s" index1="%%d" hue1="%%s" blend="%%s"/>'
+    '<xform weight="1" color="0" coefs="1 0 0 1 0 0" linear="1"/></flame>' %% ((10 + i,) + t)
+    for i, t in enumerate([(3, "0.1", 42, "0.5", "0.3"), (11, "0", 3, "0", "0.5"), (42, "0.9", 11, "0.2", "0.85")])) + '</flames>'
 a, b = T._raw(lib, lib.parse(xml)), T._raw(lib, lib.parse_own(xml))
-assert len(a) == len(b) == 5
+assert len(a) == len(b) == 8
 for (ga, xa, ca), (gb, xb, cb) in zip(a, b):
     diff = [i for i in range(len(ga)) if ga[i] != gb[i]]
     assert not diff, diff[:20]
     assert np.array_equal(xa, xb)
 pal = np.frombuffer(a[1][0], dtype=np.uint8)
-assert len(set(a[k][0] for k in range(5))) == 5      # the palettes were found and rotated
+assert len(set(a[k][0] for k in range(8))) == 8      # the palettes were found, rotated, blended
 print("ok")
 """
 
 
 def test_palette_library_and_hue_rotation(tmp_path):
-    """palette="N" hue="h": the library file (the path comes from the environment variable the
+    """palette="N" hue="h" and the pre-2008 <palette index0= hue0= index1= hue1= blend=/>: the library file (the path comes from the environment variable the
     reference reads, palettes.c:117) and the hexcone rotation, against the reference's parser on
     a library written here. In a fresh process: both sides read the library once."""
     import subprocess
@@ -354,7 +357,7 @@ def test_random_symmetry_follows_the_c_library(gpu):
 
 def test_own_parser_refuses_what_it_does_not_read(gpu):
     for bad in (
-                '<flame size="10 10"><palette index0="1" index1="2" blend="0.5"/><xform weight="1" coefs="1 0 0 1 0 0"/></flame>',
+                '<flame size="10 10"><palette index0="1" count="256" format="RGB"/><xform weight="1" coefs="1 0 0 1 0 0"/></flame>',
                 '<flame size="10 oops"><xform weight="1" coefs="1 0 0 1 0 0"/></flame>',
                 '<flame size="10 10"><xform weight="1x" coefs="1 0 0 1 0 0"/></flame>'):
         with pytest.raises(ValueError):
