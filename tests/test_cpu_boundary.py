@@ -40,6 +40,19 @@ def test_dropin_exports_the_reference_entry_points(gpu):
         assert hasattr(gpu._dll, n)
 
 
+def test_frontend_symbols_are_exported(gpu):
+    """include/flam3_b200_frontend.h: every function it declares is in the drop-in library (and
+    linked into f3b-render)."""
+    names = declared_functions("flam3_b200_frontend.h")
+    assert {"f3b_parse_flam3", "f3b_get_palette", "f3b_interpolate", "f3b_print_flam3", "f3b_write_ppm",
+            "f3b_genome_copy"} <= set(names)
+    for n in names:
+        assert hasattr(gpu._dll, n), "drop-in libflam3.so lacks %s" % n
+    out = subprocess.run(["nm", os.path.join(ROOT, "dropin", "_build", "f3b-render")], capture_output=True, text=True).stdout
+    for n in names:
+        assert re.search(r" T %s$" % n, out, flags=re.M), "f3b-render lacks %s" % n
+
+
 def test_struct_sizes_are_the_reference_abi(gpu):
     # SURVEY.md §8(b): layouts are ABI
     assert gpu.abi_sizes() == dict(randctx=288, flam3_xform=3240, flam3_genome=10728,
