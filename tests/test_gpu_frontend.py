@@ -68,11 +68,14 @@ def test_standalone_animation_writes_the_same_bytes(tmp_path, flame0, flame1):
     path = os.path.join(tmp, "anim.flam3")
     with open(path, "w") as f:
         f.write("<flames>" + a + b + "</flames>")
-    _run(OWN, tmp, "own_", path, begin="3", end="4")
+    _run(OWN, tmp, "own_", path, begin="3", end="4", write_genome="1")
     _run(os.path.join(ROOT, "dropin", "_build", "flam3-animate"), tmp, "cli_", path, begin="3", end="4")
-    own = sorted(f for f in os.listdir(tmp) if f.startswith("own_"))
+    own = sorted(f for f in os.listdir(tmp) if f.startswith("own_") and f.endswith(".ppm"))
     cli = sorted(f for f in os.listdir(tmp) if f.startswith("cli_"))
     assert own == ["own_00003.ppm", "own_00004.ppm"] and len(cli) == 2
+    # write_genome: the frame's interpolated genome beside the image (flam3-animate.c:264-279)
+    text = open(os.path.join(tmp, "own_00003.ppm.flam3")).read()
+    assert text.startswith("<flame version=") and 'time="3"' in text and text.rstrip().endswith("</flame>")
     for x, y in zip(own, cli):
         da, db = open(os.path.join(tmp, x), "rb").read(), open(os.path.join(tmp, y), "rb").read()
         assert len(da) > 1000 and da == db, (x, y)

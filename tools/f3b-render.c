@@ -7,6 +7,7 @@
  *
  *    in (default stdin), prefix, out, format (ppm | png), qs, ss, bits (33), bpc (8 | 16, 16 needs png),
  *    nthreads, sub_batch_size, earlyclip, pixel_aspect, transparency, isaac_seed, verbose, nstrips,
+ *    write_genome (animation frames),
  *    flam3_palettes, F3B_DEVICE / F3B_DEVICES
  *
  *    env format=ppm prefix=out/ tools/_build/f3b-render < some.flam3
@@ -49,7 +50,8 @@ static int write_image(flam3_frame *f, const void *image, const stat_struct *sta
    /* the genome that goes into the PNG's comment: the flame itself, or for an animation frame the
     * one interpolated at the frame's time (flam3-render.c:367, flam3-animate.c:287-291) */
    char *genome_text = NULL;
-   if (strcmp(format, "ppm")) {
+   const int write_genome = f->ngenomes > 1 && atoi(env_or("write_genome", "0")); /* flam3-animate.c:264-279 */
+   if (strcmp(format, "ppm") || write_genome) {
       flam3_genome centre;
       memset(&centre, 0, sizeof(centre));
       if (f->ngenomes == 1) genome_text = f3b_print_flam3(&f->genomes[0], NULL, NULL);
@@ -59,6 +61,17 @@ static int write_image(flam3_frame *f, const void *image, const stat_struct *sta
       }
    }
    if (verbose) fprintf(stderr, "writing %s...", name);
+   if (write_genome && genome_text) { /* the frame's interpolated genome beside the image */
+      char gname[4200];
+      snprintf(gname, sizeof(gname), "%s.flam3", name);
+      FILE *gf = fopen(gname, "w");
+      if (!gf) {
+         perror(gname);
+         return 1;
+      }
+      fputs(genome_text, gf);
+      fclose(gf);
+   }
    if (!strcmp(format, "ppm")) {
       if (f3b_write_ppm(name, image, width, height, channels, f->bytes_per_channel)) return 1;
    } else {
