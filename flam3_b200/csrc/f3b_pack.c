@@ -11,6 +11,9 @@
  *   the dmap and camera set-up of render_rectangle              rect.c:778-827
  */
 #include <math.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -558,17 +561,58 @@ int f3b_pack_sample(const flam3_genome *cp, const f3b_camera *cam, double color_
    for (int i = 0; i < cp->num_xforms; i++)
       if (cp->xform[i].opacity != 1.0) plot_ready = 0;
    int packed = plot_ready && floor_adds;
+   const int truncate = plot_ready && floor_adds; /* what the integer bucket add keeps */
    for (int j = 0; j < 256; j++) {
+      const double *col = cp->palette[j].color;
       uint32_t rgba = 0;
+#if defined(__SSE2__)
+      /* two channels at a time (this loop is 1024 conversions per temporal sample, 70 % of the
+       * packer's time): the same multiplications in the same order; floor as a truncating
+       * conversion, which is what it is for 0 <= c < 2^31 - anything else takes the scalar way */
+      const __m128d k255 = _mm_set1_pd(255.0), ks = _mm_set1_pd(color_scalar);
+      __m128d c01 = _mm_mul_pd(_mm_mul_pd(_mm_loadu_pd(col), k255), ks);
+      __m128d c23 = _mm_mul_pd(_mm_mul_pd(_mm_loadu_pd(col + 2), k255), ks);
+      const __m128d lo = _mm_setzero_pd(), hi = _mm_set1_pd(2147483648.0);
+      const int in_range = _mm_movemask_pd(_mm_and_pd(_mm_cmpge_pd(c01, lo), _mm_cmplt_pd(c01, hi))) == 3 &&
+                           _mm_movemask_pd(_mm_and_pd(_mm_cmpge_pd(c23, lo), _mm_cmplt_pd(c23, hi))) == 3;
+      if (in_range) {
+         const __m128i i01 = _mm_cvttpd_epi32(c01), i23 = _mm_cvttpd_epi32(c23);
+         if (truncate) {
+            c01 = _mm_cvtepi32_pd(i01);
+            c23 = _mm_cvtepi32_pd(i23);
+         }
+         const __m128 f4 = _mm_movelh_ps(_mm_cvtpd_ps(c01), _mm_cvtpd_ps(c23));
+         _mm_storeu_ps((float *)(w + o + j * 4), f4);
+         const __m128i i4 = _mm_unpacklo_epi64(i01, i23); /* the four truncated values */
+         /* all four are whole numbers <= 255 exactly when truncation changed nothing (or was
+          * asked for) and no value exceeds 255 */
+         const __m128d top = _mm_set1_pd(255.0);
+         const int small = _mm_movemask_pd(_mm_cmple_pd(c01, top)) == 3 && _mm_movemask_pd(_mm_cmple_pd(c23, top)) == 3;
+         if (small) {
+            uint32_t v[4];
+            _mm_storeu_si128((__m128i *)v, i4);
+            rgba = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+         } else {
+            packed = 0;
+            uint32_t v[4];
+            double c[4];
+            _mm_storeu_si128((__m128i *)v, i4);
+            _mm_storeu_pd(c, c01);
+            _mm_storeu_pd(c + 2, c23);
+            for (int k = 0; k < 4; k++)
+               if (c[k] <= 255.0) rgba |= v[k] << (8 * k);
+         }
+      } else
+#endif
       for (int k = 0; k < 4; k++) {
-         double c = cp->palette[j].color[k] * 255.0 * color_scalar;
-         if (plot_ready && floor_adds) c = floor(c); /* what the integer bucket add keeps */
+         double c = col[k] * 255.0 * color_scalar;
+         if (truncate) c = floor(c);
          w[o + j * 4 + k] = f2u(c);
          if (!(c >= 0.0 && c <= 255.0)) packed = 0;
          else rgba |= (uint32_t)c << (8 * k);
       }
       w[o + 1024 + j] = rgba;
-      if (cp->palette[j].color[3] * 255.0 * color_scalar != 255.0) alpha_ok = 0;
+      if (col[3] * 255.0 * color_scalar != 255.0) alpha_ok = 0;
    }
    w[F3B_H_PLOT] = (plot_ready ? F3B_PLOT_READY : 0u) | (packed ? F3B_PLOT_PACKED : 0u);
    o += 256 * 5;
